@@ -1,0 +1,440 @@
+// hq_api.cu — the C ABI (include/hq_b200.h): context, device memory, launch orchestration.
+// No CPU fallback: every compute entry fails with HQ_ERR_CUDA if the device is unusable.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/hq_b200.h"
+#include "../../include/hq_plugin.hpp"
+#include "hq_kernels.cuh"
+#include "hq_math.h"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t count) {
+        if (count <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+        if (e == cudaSuccess) cap = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <typename T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t count) {
+        if (count <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&p), count * sizeof(T));
+        if (e == cudaSuccess) cap = count;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct hq_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int clock_khz = 0;
+    char name[128] = {0};
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // image state (this rank's shard)
+    size_t n = 0, stride = 0;
+    int width = 0, rows = 0, whitepoint = 0;
+    bool have_image = false, have_unit = false;
+    DevBuf<uint8_t> d_rgb;
+    DevBuf<float> d_lab, d_unit;
+
+    // evaluation scratch
+    DevBuf<float> d_pal;
+    DevBuf<float4> d_pal_lab, d_pal_rgb;
+    DevBuf<unsigned long long> d_results;
+    DevBuf<uint8_t> d_idx;
+    DevBuf<uint8_t> d_out_rgb;
+    DevBuf<float> d_out_f32;
+    PinBuf<float> h_pal;
+    PinBuf<unsigned long long> h_results;
+
+    hq_allreduce_fn allreduce = nullptr;
+    void* allreduce_user = nullptr;
+    std::atomic<bool> stop{false};
+    volatile bool stop_flag_view = false;
+};
+
+namespace {
+
+int fail(hq_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define HQ_CUDA(c, call)                                                                   \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess)                                                            \
+            return fail((c), HQ_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+int bind_device(hq_ctx* c) {
+    HQ_CUDA(c, cudaSetDevice(c->device));
+    return HQ_OK;
+}
+
+// sRGB-assign mode needs the unit planes; they are produced on first use from the resident RGB
+int ensure_unit(hq_ctx* c, cudaStream_t st) {
+    if (c->have_unit) return HQ_OK;
+    HQ_CUDA(c, c->d_unit.reserve(3 * c->stride));
+    HQ_CUDA(c, hq::launch_rgb_to_lab(c->d_rgb.p, c->n, c->stride, c->whitepoint, c->d_lab.p, c->d_unit.p, c->sm_count, st));
+    c->have_unit = true;
+    return HQ_OK;
+}
+
+int convert_image(hq_ctx* c, int width, int rows, int whitepoint, cudaStream_t st) {
+    c->width = width; c->rows = rows; c->whitepoint = whitepoint;
+    c->have_unit = false;
+    HQ_CUDA(c, c->d_lab.reserve(3 * c->stride > 0 ? 3 * c->stride : 1));
+    HQ_CUDA(c, hq::launch_rgb_to_lab(c->d_rgb.p, c->n, c->stride, whitepoint, c->d_lab.p, nullptr, c->sm_count, st));
+    c->have_image = true;
+    return HQ_OK;
+}
+
+int check_eval_args(hq_ctx* c, int B, int K, int space) {
+    if (!c) return HQ_ERR_INVALID;
+    if (!c->have_image) return fail(c, HQ_ERR_NO_IMAGE, "no image: call hq_set_image_u8 first");
+    if (B < 1 || K < 1) return fail(c, HQ_ERR_INVALID, "B and K must be >= 1 (got B=%d K=%d)", B, K);
+    if (K > HQ_MAX_COLORS) return fail(c, HQ_ERR_UNSUPPORTED, "K=%d exceeds HQ_MAX_COLORS=%d", K, HQ_MAX_COLORS);
+    if (space != HQ_SPACE_LAB && space != HQ_SPACE_SRGB) return fail(c, HQ_ERR_INVALID, "unknown space %d", space);
+    return HQ_OK;
+}
+
+int eval_device(hq_ctx* c, const float* d_palettes, int B, int K, int space, int flags, unsigned long long* d_results,
+                void* d_idx, cudaStream_t st) {
+    const int K8 = hq::padded_colors(K);
+    const bool sums = (flags & HQ_EVAL_SUMS) != 0;
+    const int words = hq::result_words(K, sums);
+    HQ_CUDA(c, c->d_pal_lab.reserve((size_t)B * K8));
+    HQ_CUDA(c, c->d_pal_rgb.reserve((size_t)B * K8));
+    if (space == HQ_SPACE_SRGB) { int rc = ensure_unit(c, st); if (rc) return rc; }
+    HQ_CUDA(c, cudaMemsetAsync(d_results, 0, (size_t)B * words * 8, st));
+    HQ_CUDA(c, hq::launch_palette_features(d_palettes, B, K, c->whitepoint, c->d_pal_lab.p, c->d_pal_rgb.p, st));
+    hq::AssignArgs a;
+    a.lab = c->d_lab.p; a.unit = c->d_unit.p; a.n = c->n; a.stride = c->stride;
+    a.pal_lab = c->d_pal_lab.p; a.pal_rgb = c->d_pal_rgb.p;
+    a.B = B; a.K = K; a.space = space; a.want_sums = sums;
+    a.results = d_results; a.idx_out = d_idx; a.sm_count = c->sm_count;
+    a.variant = (flags & HQ_EVAL_FORCE_DIRECT) ? 1 : ((flags & HQ_EVAL_FORCE_CHUNKED) ? 2 : 0);
+    HQ_CUDA(c, hq::launch_assign_reduce(a, st));
+    return HQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hq_create(int device, hq_ctx** out) {
+    if (!out) return fail(nullptr, HQ_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, HQ_ERR_CUDA, "no CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= ndev) return fail(nullptr, HQ_ERR_INVALID, "device %d out of range [0,%d)", device, ndev);
+    hq_ctx* c = new hq_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete c;
+        return fail(nullptr, HQ_ERR_CUDA, "device %d init failed: %s", device, cudaGetErrorString(e));
+    }
+    if (prop.major < 10) {
+        cudaStreamDestroy(c->stream);
+        delete c;
+        return fail(nullptr, HQ_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    }
+    c->sm_count = prop.multiProcessorCount;
+    cudaDeviceGetAttribute(&c->clock_khz, cudaDevAttrClockRate, device);
+    snprintf(c->name, sizeof c->name, "%s", prop.name);
+    *out = c;
+    return HQ_OK;
+}
+
+void hq_destroy(hq_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    c->d_rgb.release(); c->d_lab.release(); c->d_unit.release(); c->d_pal.release();
+    c->d_pal_lab.release(); c->d_pal_rgb.release(); c->d_results.release(); c->d_idx.release();
+    c->d_out_rgb.release(); c->d_out_f32.release(); c->h_pal.release(); c->h_results.release();
+    delete c;
+}
+
+const char* hq_last_error(const hq_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int hq_device_info(const hq_ctx* c, int* sm_count, int* sm_clock_khz, char* name, int name_len) {
+    if (!c) return HQ_ERR_INVALID;
+    if (sm_count) *sm_count = c->sm_count;
+    if (sm_clock_khz) *sm_clock_khz = c->clock_khz;
+    if (name && name_len > 0) snprintf(name, (size_t)name_len, "%s", c->name);
+    return HQ_OK;
+}
+
+uint64_t hq_image_pixels(const hq_ctx* c) { return c ? (uint64_t)c->n : 0; }
+
+int hq_set_image_u8(hq_ctx* c, const uint8_t* rgb, int width, int rows, int whitepoint) {
+    if (!c) return HQ_ERR_INVALID;
+    if (width < 0 || rows < 0 || (!rgb && (size_t)width * rows > 0)) return fail(c, HQ_ERR_INVALID, "bad image arguments");
+    if (whitepoint != HQ_WHITEPOINT_D65 && whitepoint != HQ_WHITEPOINT_D50) return fail(c, HQ_ERR_INVALID, "unknown white point %d", whitepoint);
+    int rc = bind_device(c); if (rc) return rc;
+    c->have_image = false;
+    c->n = (size_t)width * rows;
+    c->stride = hq::plane_stride(c->n);
+    HQ_CUDA(c, c->d_rgb.reserve(c->n * 3 > 0 ? c->n * 3 : 1));
+    if (c->n) HQ_CUDA(c, cudaMemcpyAsync(c->d_rgb.p, rgb, c->n * 3, cudaMemcpyHostToDevice, c->stream));
+    rc = convert_image(c, width, rows, whitepoint, c->stream); if (rc) return rc;
+    HQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HQ_OK;
+}
+
+int hq_set_image_u8_device(hq_ctx* c, const void* d_rgb, int width, int rows, int whitepoint, void* stream) {
+    if (!c) return HQ_ERR_INVALID;
+    if (width < 0 || rows < 0 || (!d_rgb && (size_t)width * rows > 0)) return fail(c, HQ_ERR_INVALID, "bad image arguments");
+    if (whitepoint != HQ_WHITEPOINT_D65 && whitepoint != HQ_WHITEPOINT_D50) return fail(c, HQ_ERR_INVALID, "unknown white point %d", whitepoint);
+    int rc = bind_device(c); if (rc) return rc;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    c->have_image = false;
+    c->n = (size_t)width * rows;
+    c->stride = hq::plane_stride(c->n);
+    HQ_CUDA(c, c->d_rgb.reserve(c->n * 3 > 0 ? c->n * 3 : 1));
+    if (c->n) HQ_CUDA(c, cudaMemcpyAsync(c->d_rgb.p, d_rgb, c->n * 3, cudaMemcpyDeviceToDevice, st));
+    return convert_image(c, width, rows, whitepoint, st);
+}
+
+int hq_get_lab(hq_ctx* c, float* planes) {
+    if (!c || !planes) return HQ_ERR_INVALID;
+    if (!c->have_image) return fail(c, HQ_ERR_NO_IMAGE, "no image");
+    int rc = bind_device(c); if (rc) return rc;
+    for (int pl = 0; pl < 3 && c->n; ++pl)
+        HQ_CUDA(c, cudaMemcpyAsync(planes + (size_t)pl * c->n, c->d_lab.p + (size_t)pl * c->stride, c->n * sizeof(float),
+                                   cudaMemcpyDeviceToHost, c->stream));
+    HQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HQ_OK;
+}
+
+int hq_result_words(int K, int flags) { return hq::result_words(K, (flags & HQ_EVAL_SUMS) != 0); }
+
+int hq_eval_palettes_device(hq_ctx* c, const void* d_palettes, int B, int K, int space, int flags, void* d_results, void* stream) {
+    int rc = check_eval_args(c, B, K, space); if (rc) return rc;
+    if (!d_palettes || !d_results) return fail(c, HQ_ERR_INVALID, "NULL device buffer");
+    rc = bind_device(c); if (rc) return rc;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    return eval_device(c, static_cast<const float*>(d_palettes), B, K, space, flags, static_cast<unsigned long long*>(d_results), nullptr, st);
+}
+
+int hq_eval_palettes(hq_ctx* c, const float* palettes, int B, int K, int space, int flags, int64_t* err_fx, uint64_t* counts, int64_t* sums_fx) {
+    int rc = check_eval_args(c, B, K, space); if (rc) return rc;
+    if (!palettes) return fail(c, HQ_ERR_INVALID, "palettes is NULL");
+    const bool sums = (flags & HQ_EVAL_SUMS) != 0;
+    if (sums_fx && !sums) return fail(c, HQ_ERR_INVALID, "sums_fx requires HQ_EVAL_SUMS");
+    rc = bind_device(c); if (rc) return rc;
+    const size_t npal = (size_t)B * K * 4;
+    const int words = hq::result_words(K, sums);
+    const size_t nwords = (size_t)B * words;
+    HQ_CUDA(c, c->h_pal.reserve(npal));
+    HQ_CUDA(c, c->d_pal.reserve(npal));
+    HQ_CUDA(c, c->h_results.reserve(nwords));
+    HQ_CUDA(c, c->d_results.reserve(nwords));
+    std::memcpy(c->h_pal.p, palettes, npal * sizeof(float));
+    HQ_CUDA(c, cudaMemcpyAsync(c->d_pal.p, c->h_pal.p, npal * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    rc = eval_device(c, c->d_pal.p, B, K, space, flags, c->d_results.p, nullptr, c->stream); if (rc) return rc;
+    if (c->allreduce) {
+        if (c->allreduce(c->allreduce_user, c->d_results.p, nwords, c->stream) != 0)
+            return fail(c, HQ_ERR_CALLBACK, "all-reduce hook failed");
+    }
+    HQ_CUDA(c, cudaMemcpyAsync(c->h_results.p, c->d_results.p, nwords * 8, cudaMemcpyDeviceToHost, c->stream));
+    HQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int b = 0; b < B; ++b) {
+        const unsigned long long* w = c->h_results.p + (size_t)b * words;
+        if (err_fx) err_fx[b] = (int64_t)w[0];
+        if (counts) std::memcpy(counts + (size_t)b * K, w + 1, sizeof(uint64_t) * K);
+        if (sums_fx) std::memcpy(sums_fx + (size_t)b * K * 3, w + 1 + K, sizeof(int64_t) * 3 * K);
+    }
+    return HQ_OK;
+}
+
+double hq_cost(int64_t err_fx, const uint64_t* counts, int K, uint64_t n_total, float delta) {
+    double penalty = 0;
+    for (int k = 0; k < K; ++k)
+        if (counts[k] == 0) penalty += delta;
+    const double sum = (double)err_fx * (1.0 / 16777216.0);
+    return sum / (double)n_total + penalty;
+}
+
+int hq_quantize(hq_ctx* c, const float* palette, int K, int space, uint8_t* out_rgb, float* out_f32, uint16_t* out_idx) {
+    int rc = check_eval_args(c, 1, K, space); if (rc) return rc;
+    if (!palette) return fail(c, HQ_ERR_INVALID, "palette is NULL");
+    rc = bind_device(c); if (rc) return rc;
+    const size_t n = c->n;
+    const bool idx16 = K > 256;
+    const size_t npal = (size_t)K * 4;
+    const int words = hq::result_words(K, false);
+    HQ_CUDA(c, c->h_pal.reserve(npal));
+    HQ_CUDA(c, c->d_pal.reserve(npal));
+    HQ_CUDA(c, c->d_results.reserve(words));
+    HQ_CUDA(c, c->d_idx.reserve((c->stride ? c->stride : 1) * (idx16 ? 2 : 1)));
+    std::memcpy(c->h_pal.p, palette, npal * sizeof(float));
+    HQ_CUDA(c, cudaMemcpyAsync(c->d_pal.p, c->h_pal.p, npal * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    rc = eval_device(c, c->d_pal.p, 1, K, space, 0, c->d_results.p, c->d_idx.p, c->stream); if (rc) return rc;
+    if (out_rgb) HQ_CUDA(c, c->d_out_rgb.reserve(n * 3 > 0 ? n * 3 : 1));
+    if (out_f32) HQ_CUDA(c, c->d_out_f32.reserve(n * 4 > 0 ? n * 4 : 1));
+    if (out_rgb || out_f32)
+        HQ_CUDA(c, hq::launch_apply_palette(c->d_idx.p, idx16, n, c->d_pal.p, K, out_rgb ? c->d_out_rgb.p : nullptr,
+                                            out_f32 ? c->d_out_f32.p : nullptr, c->stream));
+    if (n) {
+        if (out_rgb) HQ_CUDA(c, cudaMemcpyAsync(out_rgb, c->d_out_rgb.p, n * 3, cudaMemcpyDeviceToHost, c->stream));
+        if (out_f32) HQ_CUDA(c, cudaMemcpyAsync(out_f32, c->d_out_f32.p, n * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    std::vector<uint8_t> idx8;
+    if (out_idx && n) {
+        if (idx16) {
+            HQ_CUDA(c, cudaMemcpyAsync(out_idx, c->d_idx.p, n * 2, cudaMemcpyDeviceToHost, c->stream));
+        } else {
+            idx8.resize(n);
+            HQ_CUDA(c, cudaMemcpyAsync(idx8.data(), c->d_idx.p, n, cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
+    HQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (out_idx && n && !idx16)
+        for (size_t i = 0; i < n; ++i) out_idx[i] = idx8[i];
+    return HQ_OK;
+}
+
+int hq_set_allreduce(hq_ctx* c, hq_allreduce_fn fn, void* user) {
+    if (!c) return HQ_ERR_INVALID;
+    c->allreduce = fn;
+    c->allreduce_user = user;
+    return HQ_OK;
+}
+
+void hq_swasa_default_params(hq_swasa_params* p) {
+    if (!p) return;
+    const hq::HybridQuantization d;
+    p->population = d.populationSize; p->imax = d.imax; p->iTc = d.iTc; p->delta = d.delta;
+    p->convergence = d.convEnable ? 1 : 0; p->conv_delay = d.convDelay; p->conv_spread = d.convSpread;
+    p->t0 = d.T0; p->alpha = d.alpha; p->s0 = d.s0; p->beta = d.beta; p->space = d.space; p->seed = d.seed;
+}
+
+int hq_find_best_quantization(hq_ctx* c, int K, const hq_swasa_params* p, uint64_t n_total, float* best_colors,
+                              double* best_error, double* trace_costs, int* iterations_done) {
+    if (!c || !p || !best_colors) return c ? fail(c, HQ_ERR_INVALID, "NULL argument") : HQ_ERR_INVALID;
+    int rc = check_eval_args(c, p->population, K, p->space); if (rc) return rc;
+    if (p->imax < 1 || p->iTc < 1) return fail(c, HQ_ERR_INVALID, "imax and iTc must be >= 1");
+    c->stop.store(false);
+    c->stop_flag_view = false;
+    try {
+        hq::ImageManipulation backend(c, false, p->convergence != 0);
+        backend.setStopFlag(&c->stop_flag_view);
+        hq::JavaRandom random(p->seed);
+        hq::SWASA swasa(p->population, p->imax, p->iTc, p->delta, p->conv_delay, p->conv_spread, p->t0, p->alpha, p->s0, p->beta, &random);
+        double err = 0;
+        const std::vector<float> best = backend.findBestQuantization(K, swasa, n_total, p->space, &err, trace_costs, iterations_done);
+        std::memcpy(best_colors, best.data(), sizeof(float) * best.size());
+        if (best_error) *best_error = err;
+    } catch (const std::exception& ex) {
+        if (c->err.empty()) c->err = ex.what();
+        return HQ_ERR_CUDA;
+    }
+    return HQ_OK;
+}
+
+void hq_request_stop(hq_ctx* c) {
+    if (!c) return;
+    c->stop.store(true);
+    c->stop_flag_view = true;
+}
+
+void hq_java_random_seed(hq_java_random* r, int64_t seed) { hq::JavaRandom j(seed); r->state = j.state(); }
+int32_t hq_java_random_next(hq_java_random* r, int bits) { hq::JavaRandom j; j.setState(r->state); const int32_t v = j.next(bits); r->state = j.state(); return v; }
+float hq_java_random_next_float(hq_java_random* r) { hq::JavaRandom j; j.setState(r->state); const float v = j.nextFloat(); r->state = j.state(); return v; }
+double hq_java_random_next_double(hq_java_random* r) { hq::JavaRandom j; j.setState(r->state); const double v = j.nextDouble(); r->state = j.state(); return v; }
+
+static hq::SWASA make_swasa(const hq_swasa_params* p, hq::JavaRandom* j) {
+    return hq::SWASA(p->population, p->imax, p->iTc, p->delta, p->conv_delay, p->conv_spread, p->t0, p->alpha, p->s0, p->beta, j);
+}
+void hq_swasa_generate_random_colors(hq_java_random* r, int K, float* colors) {
+    hq_swasa_params d; hq_swasa_default_params(&d);
+    hq::JavaRandom j; j.setState(r->state);
+    make_swasa(&d, &j).generateRandomColors(K, colors);
+    r->state = j.state();
+}
+void hq_swasa_generate_neighboring_colors(const hq_swasa_params* p, hq_java_random* r, const float* colors, float* next_colors, int K, int iteration) {
+    hq::JavaRandom j; j.setState(r->state);
+    make_swasa(p, &j).generateNeighboringColors(colors, next_colors, K, iteration);
+    r->state = j.state();
+}
+float hq_swasa_max_step_width(const hq_swasa_params* p, int iteration) {
+    hq::JavaRandom j;
+    return make_swasa(p, &j).maxStepWidth(iteration);
+}
+
+int hq_host_math_range(int which, uint32_t first_bits, uint32_t count, float* out, int threads) {
+    if (!out || which < 0 || which > 2) return HQ_ERR_INVALID;
+    if (threads < 1) threads = 1;
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back([=] {
+            const uint64_t lo = (uint64_t)count * t / threads, hi = (uint64_t)count * (t + 1) / threads;
+            for (uint64_t i = lo; i < hi; ++i) {
+                const float v = HQ_U2F(first_bits + (uint32_t)i);
+                out[i] = which == 0 ? hq_cbrtf(v) : (which == 1 ? hq_pow_2p4f(v) : hq_srgb_decode(v));
+            }
+        });
+    for (auto& th : pool) th.join();
+    return HQ_OK;
+}
+
+int hq_device_math_range(hq_ctx* c, int which, uint32_t first_bits, uint32_t count, float* out) {
+    if (!c || !out || which < 0 || which > 2) return HQ_ERR_INVALID;
+    int rc = bind_device(c); if (rc) return rc;
+    DevBuf<float> d;
+    HQ_CUDA(c, d.reserve(count ? count : 1));
+    cudaError_t e = hq::launch_math_probe(which, first_bits, count, d.p, c->stream);
+    if (e == cudaSuccess && count) e = cudaMemcpyAsync(out, d.p, (size_t)count * 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    d.release();
+    if (e != cudaSuccess) return fail(c, HQ_ERR_CUDA, "math probe failed: %s", cudaGetErrorString(e));
+    return HQ_OK;
+}
+
+void hq_host_srgb_to_lab(const float rgb[3], int whitepoint, float lab[3]) {
+    const hq_float3 v = hq_srgb_to_lab(rgb[0], rgb[1], rgb[2], hq_whitepoint(whitepoint));
+    lab[0] = v.x; lab[1] = v.y; lab[2] = v.z;
+}
+
+}  // extern "C"

@@ -1,0 +1,519 @@
+// hq_kernels.cu — hand-written sm_100a kernels of the HybridQuantization hot path.
+//
+//   rgb_to_lab_kernel        RGB->CIELAB of every pixel   (replaces RGB2XYZ + Opp2LAB,
+//                            OptimizedConvolution.cl:79-90,124-145, with the Java CPU
+//                            arithmetic of ScielabProcessor.java:279-311)
+//   palette_features_kernel  candidate palettes -> Lab    (same arithmetic, B*K colours)
+//   assign_reduce_kernel     nearest-palette argmin fused with the per-colour counts /
+//                            Lab sums / total-error reduction, many candidates per launch
+//                            (replaces quantizeAndConvertToOpp :172-199, CIEDE :201-209,
+//                            the used-colour flags and the host-side averageArray of
+//                            ImageManipulation.java:620-727,736-768)
+//   apply_palette_kernel     final image                  (quantize, :147-170)
+//
+// HBM layout: the image lives as SoA fp32 planes [3][stride] (stride = n rounded up to 32
+// pixels) so that every warp load is one fully coalesced 128-bit access; palettes live as
+// padded float4 tables [B][K8].  All reductions are integers (counts, 2^-24 fixed point),
+// hence independent of block order, grid size and GPU count.
+//
+// Tensor cores are deliberately not used: the inner dimension of the distance is 3.
+#include "hq_kernels.cuh"
+#include "hq_math.h"
+
+namespace hq {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kPxPerThread = 4;
+constexpr int kTilePx = kThreads * kPxPerThread;  // 1024 pixels per CTA iteration
+constexpr int kChunk = 8;                         // colours per running-min chunk
+constexpr float kFar = 1e18f;                     // padding colour coordinate
+
+// ---- packed fp32x2 arithmetic (sm_100a FADD2 / FMUL2 / FFMA2), IEEE round-to-nearest,
+// ---- no flush-to-zero: bit-identical per lane to __fsub_rn / __fmul_rn / __fmaf_rn.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {  // FMNMX3
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// squared distances of one pixel to a PAIR of colours; same rounding sequence as hq_dist2
+__device__ __forceinline__ uint64_t dist2_pair(uint64_t X, uint64_t Y, uint64_t Z, uint64_t P0,
+                                               uint64_t P1, uint64_t P2) {
+    const uint64_t d0 = sub2(X, P0), d1 = sub2(Y, P1), d2 = sub2(Z, P2);
+    return fma2(d2, d2, fma2(d1, d1, mul2(d0, d0)));
+}
+
+// ====================================================================== RGB -> Lab
+constexpr int kRlPxPerThread = 16;
+constexpr int kRlTilePx = kThreads * kRlPxPerThread;  // 4096 px = 12288 B of packed RGB
+
+__global__ void __launch_bounds__(kThreads)
+rgb_to_lab_kernel(const uint8_t* __restrict__ rgb, size_t n, size_t stride, int whitepoint,
+                  float* __restrict__ lab, float* __restrict__ unit) {
+    __shared__ __align__(16) uint32_t s_stage[kRlTilePx * 3 / 4];  // 3072 words
+    __shared__ float s_lin[256];
+    __shared__ float s_unit[256];
+    const int tid = threadIdx.x;
+    {   // 256-entry decode table: the u8 -> linear-light map has only 256 values
+        const float u = hq_u8_to_unit((uint32_t)tid);
+        s_unit[tid] = u;
+        s_lin[tid] = hq_srgb_decode(u);
+    }
+    const hq_float3 white = hq_whitepoint(whitepoint);
+    const size_t ntiles = (n + kRlTilePx - 1) / kRlTilePx;
+    const bool aligned = (reinterpret_cast<uintptr_t>(rgb) & 15) == 0;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const size_t px0 = tile * kRlTilePx;
+        const size_t byte0 = px0 * 3;
+        const size_t tile_px = (n - px0 < (size_t)kRlTilePx) ? (n - px0) : (size_t)kRlTilePx;
+        __syncthreads();  // previous tile fully consumed (and the tables written)
+        if (tile_px == (size_t)kRlTilePx && aligned) {
+            // 3 fully coalesced 128-bit loads per thread
+            const uint4* src = reinterpret_cast<const uint4*>(rgb + byte0);
+            uint4* dst = reinterpret_cast<uint4*>(s_stage);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) dst[tid + r * kThreads] = __ldg(src + tid + r * kThreads);
+        } else {
+            uint8_t* dst = reinterpret_cast<uint8_t*>(s_stage);
+            const size_t nbytes = tile_px * 3;
+            for (size_t i = tid; i < (size_t)kRlTilePx * 3; i += kThreads)
+                dst[i] = (i < nbytes) ? rgb[byte0 + i] : (uint8_t)0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kRlPxPerThread / 4; ++r) {
+            const int grp = r * kThreads + tid;  // group of 4 pixels = 3 words, bank-conflict free
+            const uint32_t w0 = s_stage[3 * grp], w1 = s_stage[3 * grp + 1], w2 = s_stage[3 * grp + 2];
+            const uint32_t c[12] = {w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u, w0 >> 24,
+                                    w1 & 255u, (w1 >> 8) & 255u, (w1 >> 16) & 255u, w1 >> 24,
+                                    w2 & 255u, (w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24};
+            float L[4], A[4], Bv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const hq_float3 v = hq_linrgb_to_lab(s_lin[c[3 * j]], s_lin[c[3 * j + 1]], s_lin[c[3 * j + 2]], white);
+                L[j] = v.x; A[j] = v.y; Bv[j] = v.z;
+            }
+            const size_t p = px0 + 4 * (size_t)grp;
+            if (p + 4 <= n) {
+                *reinterpret_cast<float4*>(lab + p) = make_float4(L[0], L[1], L[2], L[3]);
+                *reinterpret_cast<float4*>(lab + stride + p) = make_float4(A[0], A[1], A[2], A[3]);
+                *reinterpret_cast<float4*>(lab + 2 * stride + p) = make_float4(Bv[0], Bv[1], Bv[2], Bv[3]);
+                if (unit) {
+                    *reinterpret_cast<float4*>(unit + p) = make_float4(s_unit[c[0]], s_unit[c[3]], s_unit[c[6]], s_unit[c[9]]);
+                    *reinterpret_cast<float4*>(unit + stride + p) = make_float4(s_unit[c[1]], s_unit[c[4]], s_unit[c[7]], s_unit[c[10]]);
+                    *reinterpret_cast<float4*>(unit + 2 * stride + p) = make_float4(s_unit[c[2]], s_unit[c[5]], s_unit[c[8]], s_unit[c[11]]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (p + j < n) {
+                        lab[p + j] = L[j]; lab[stride + p + j] = A[j]; lab[2 * stride + p + j] = Bv[j];
+                        if (unit) {
+                            unit[p + j] = s_unit[c[3 * j]];
+                            unit[stride + p + j] = s_unit[c[3 * j + 1]];
+                            unit[2 * stride + p + j] = s_unit[c[3 * j + 2]];
+                        }
+                    }
+            }
+        }
+    }
+}
+
+// ====================================================================== palettes -> features
+__global__ void palette_features_kernel(const float* __restrict__ pal, int B, int K, int K8,
+                                        int whitepoint, float4* __restrict__ pal_lab,
+                                        float4* __restrict__ pal_rgb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * K8) return;
+    const int b = i / K8, k = i - b * K8;
+    float4 lab = make_float4(kFar, kFar, kFar, 0.f), rgbv = lab;
+    if (k < K) {
+        const float4 c = reinterpret_cast<const float4*>(pal)[(size_t)b * K + k];
+        const hq_float3 v = hq_srgb_to_lab(c.x, c.y, c.z, hq_whitepoint(whitepoint));
+        lab = make_float4(v.x, v.y, v.z, 0.f);
+        rgbv = make_float4(c.x, c.y, c.z, 0.f);
+    }
+    pal_lab[i] = lab;
+    pal_rgb[i] = rgbv;
+}
+
+// ====================================================================== assign + reduce
+struct AssignParams {
+    const float* feat;   // [3][stride] planes the argmin runs on (Lab, or unit sRGB)
+    const float* lab;    // [3][stride] Lab planes (scoring / sums)
+    size_t n, stride;
+    const float4* pal_feat;  // [B][K8]
+    const float4* pal_lab;   // [B][K8]
+    int K, K8, words;
+    unsigned long long* results;
+    void* idx_out;
+};
+
+template <bool SRGB, bool SUMS>
+__host__ __device__ constexpr size_t assign_smem_bytes(int K8, int variant) {
+    size_t s = (size_t)K8 / 2 * 16;                       // colour pairs (f0,f0',f1,f1')
+    if (SRGB) s += (size_t)K8 * 16;                       // Lab of the palette for scoring
+    if (SUMS) s += (size_t)K8 * 3 * 8;                    // per-colour Lab sums
+    s += (size_t)K8 / 2 * 8;                              // colour pairs (f2,f2')
+    if (variant == 2) s += (size_t)3 * (K8 / kChunk) * (kChunk + 1) * 4;  // skewed SoA copy
+    s += (size_t)K8 * 4;                                  // per-colour counts
+    return s;
+}
+
+// VARIANT 1: running (min, index) per colour — best for small palettes.
+// VARIANT 2: running min per chunk of 8 colours with FMNMX3 (one ALU op per colour pair),
+//            the winning chunk is re-evaluated once per pixel to recover the index;
+//            the first colour whose distance EQUALS the minimum wins, i.e. the reference's
+//            strict '<' / lowest-index rule (OptimizedConvolution.cl:186).
+template <int VARIANT, bool SRGB, bool SUMS, int IDXW>
+__global__ void __launch_bounds__(kThreads, 2) assign_reduce_kernel(const AssignParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int K = p.K, K8 = p.K8;
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x;  // candidate index varies fastest: co-resident CTAs share pixels in L2
+    const int skew_len = (K8 / kChunk) * (kChunk + 1);
+
+    unsigned char* sp = smem_raw;
+    float4* s_pla = reinterpret_cast<float4*>(sp); sp += (size_t)K8 / 2 * 16;
+    float4* s_lab = reinterpret_cast<float4*>(sp); if (SRGB) sp += (size_t)K8 * 16;
+    unsigned long long* s_sum = reinterpret_cast<unsigned long long*>(sp); if (SUMS) sp += (size_t)K8 * 3 * 8;
+    float2* s_pb = reinterpret_cast<float2*>(sp); sp += (size_t)K8 / 2 * 8;
+    float* s_sk = reinterpret_cast<float*>(sp); if (VARIANT == 2) sp += (size_t)3 * skew_len * 4;
+    unsigned int* s_cnt = reinterpret_cast<unsigned int*>(sp);
+
+    {
+        const float4* gf = p.pal_feat + (size_t)b * K8;
+        const float4* gl = p.pal_lab + (size_t)b * K8;
+        float* pla_f = reinterpret_cast<float*>(s_pla);
+        float* pb_f = reinterpret_cast<float*>(s_pb);
+        for (int k = tid; k < K8; k += kThreads) {
+            const float4 f = gf[k];
+            pla_f[(k >> 1) * 4 + (k & 1)] = f.x;
+            pla_f[(k >> 1) * 4 + 2 + (k & 1)] = f.y;
+            pb_f[k] = f.z;
+            if (VARIANT == 2) {
+                const int s = (k / kChunk) * (kChunk + 1) + (k % kChunk);
+                s_sk[s] = f.x; s_sk[skew_len + s] = f.y; s_sk[2 * skew_len + s] = f.z;
+            }
+            if (SRGB) s_lab[k] = gl[k];
+            s_cnt[k] = 0u;
+            if (SUMS) { s_sum[3 * k] = 0ull; s_sum[3 * k + 1] = 0ull; s_sum[3 * k + 2] = 0ull; }
+        }
+    }
+    __syncthreads();
+
+    const float* f0 = p.feat; const float* f1 = p.feat + p.stride; const float* f2 = p.feat + 2 * p.stride;
+    const float* l0 = p.lab;  const float* l1 = p.lab + p.stride;  const float* l2 = p.lab + 2 * p.stride;
+    const size_t n = p.n;
+    const size_t ntiles = (n + kTilePx - 1) / kTilePx;
+    const float INF = __int_as_float(0x7f800000);
+    long long err_acc = 0;
+
+    for (size_t tile = blockIdx.y; tile < ntiles; tile += gridDim.y) {
+        const size_t base = tile * kTilePx + (size_t)kPxPerThread * tid;
+        float x0[4], x1[4], x2[4];
+        int nvalid;
+        if (base + 4 <= n) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(f0 + base));
+            const float4 c = __ldg(reinterpret_cast<const float4*>(f1 + base));
+            const float4 d = __ldg(reinterpret_cast<const float4*>(f2 + base));
+            x0[0] = a.x; x0[1] = a.y; x0[2] = a.z; x0[3] = a.w;
+            x1[0] = c.x; x1[1] = c.y; x1[2] = c.z; x1[3] = c.w;
+            x2[0] = d.x; x2[1] = d.y; x2[2] = d.z; x2[3] = d.w;
+            nvalid = 4;
+        } else {
+            nvalid = base < n ? (int)(n - base) : 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool ok = j < nvalid;
+                x0[j] = ok ? f0[base + j] : 0.f; x1[j] = ok ? f1[base + j] : 0.f; x2[j] = ok ? f2[base + j] : 0.f;
+            }
+        }
+
+        float best[4] = {INF, INF, INF, INF};
+        int idx[4] = {0, 0, 0, 0};
+        uint64_t X[4], Y[4], Z[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { X[j] = pack2(x0[j], x0[j]); Y[j] = pack2(x1[j], x1[j]); Z[j] = pack2(x2[j], x2[j]); }
+
+        if (VARIANT == 1) {
+#pragma unroll 4
+            for (int q = 0; q < K8 / 2; ++q) {
+                const float4 la = s_pla[q];
+                const float2 bb = s_pb[q];
+                const uint64_t P0 = pack2(la.x, la.y), P1 = pack2(la.z, la.w), P2 = pack2(bb.x, bb.y);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float dlo, dhi;
+                    unpack2(dist2_pair(X[j], Y[j], Z[j], P0, P1, P2), dlo, dhi);
+                    if (dlo < best[j]) { best[j] = dlo; idx[j] = 2 * q; }
+                    if (dhi < best[j]) { best[j] = dhi; idx[j] = 2 * q + 1; }
+                }
+            }
+        } else {
+            int cidx[4] = {0, 0, 0, 0};
+            const int nchunks = K8 / kChunk;
+            for (int c = 0; c < nchunks; ++c) {
+                float m[4] = {INF, INF, INF, INF};
+#pragma unroll
+                for (int q = 0; q < kChunk / 2; ++q) {
+                    const float4 la = s_pla[c * (kChunk / 2) + q];
+                    const float2 bb = s_pb[c * (kChunk / 2) + q];
+                    const uint64_t P0 = pack2(la.x, la.y), P1 = pack2(la.z, la.w), P2 = pack2(bb.x, bb.y);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float dlo, dhi;
+                        unpack2(dist2_pair(X[j], Y[j], Z[j], P0, P1, P2), dlo, dhi);
+                        m[j] = min3(m[j], dlo, dhi);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (m[j] < best[j]) { best[j] = m[j]; cidx[j] = c; }
+            }
+            // recover the index: lowest colour of the winning chunk whose distance equals the min
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int s0 = cidx[j] * (kChunk + 1);
+                int found = 0;
+#pragma unroll
+                for (int i = kChunk - 1; i >= 0; --i) {
+                    const float d = hq_dist2(x0[j], x1[j], x2[j], s_sk[s0 + i], s_sk[skew_len + s0 + i], s_sk[2 * skew_len + s0 + i]);
+                    if (d == best[j]) found = i;
+                }
+                idx[j] = cidx[j] * kChunk + found;
+            }
+        }
+
+        // ---- per-pixel epilogue: error, counts, sums, indices
+        float q0[4], q1[4], q2[4];  // Lab of the pixel
+        if (SRGB) {
+            if (nvalid == 4) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(l0 + base));
+                const float4 c = __ldg(reinterpret_cast<const float4*>(l1 + base));
+                const float4 d = __ldg(reinterpret_cast<const float4*>(l2 + base));
+                q0[0] = a.x; q0[1] = a.y; q0[2] = a.z; q0[3] = a.w;
+                q1[0] = c.x; q1[1] = c.y; q1[2] = c.z; q1[3] = c.w;
+                q2[0] = d.x; q2[1] = d.y; q2[2] = d.z; q2[3] = d.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool ok = j < nvalid;
+                    q0[j] = ok ? l0[base + j] : 0.f; q1[j] = ok ? l1[base + j] : 0.f; q2[j] = ok ? l2[base + j] : 0.f;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { q0[j] = x0[j]; q1[j] = x1[j]; q2[j] = x2[j]; }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < nvalid) {
+                float d2v = best[j];
+                if (SRGB) {  // assign in sRGB, score in CIELAB (OptimizedConvolution.cl:209)
+                    const float4 pl = s_lab[idx[j]];
+                    d2v = hq_dist2(q0[j], q1[j], q2[j], pl.x, pl.y, pl.z);
+                }
+                err_acc += hq_to_fx(HQ_FSQRT(d2v));
+                atomicAdd(&s_cnt[idx[j]], 1u);
+                if (SUMS) {
+                    atomicAdd(&s_sum[3 * idx[j]], (unsigned long long)hq_to_fx(q0[j]));
+                    atomicAdd(&s_sum[3 * idx[j] + 1], (unsigned long long)hq_to_fx(q1[j]));
+                    atomicAdd(&s_sum[3 * idx[j] + 2], (unsigned long long)hq_to_fx(q2[j]));
+                }
+            }
+        }
+        if (IDXW == 1) {
+            uint8_t* o = reinterpret_cast<uint8_t*>(p.idx_out) + (size_t)b * p.stride + base;
+            if (nvalid == 4) {
+                *reinterpret_cast<uint32_t*>(o) = (uint32_t)idx[0] | ((uint32_t)idx[1] << 8) | ((uint32_t)idx[2] << 16) | ((uint32_t)idx[3] << 24);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (j < nvalid) o[j] = (uint8_t)idx[j];
+            }
+        } else if (IDXW == 2) {
+            uint16_t* o = reinterpret_cast<uint16_t*>(p.idx_out) + (size_t)b * p.stride + base;
+            if (nvalid == 4) {
+                *reinterpret_cast<uint2*>(o) = make_uint2((uint32_t)idx[0] | ((uint32_t)idx[1] << 16), (uint32_t)idx[2] | ((uint32_t)idx[3] << 16));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (j < nvalid) o[j] = (uint16_t)idx[j];
+            }
+        }
+    }
+
+    // ---- CTA reduction: warp shuffles -> shared -> one global atomic per (CTA, quantity)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) err_acc += __shfl_down_sync(0xffffffffu, err_acc, off);
+    __shared__ long long s_err[kThreads / 32];
+    if ((tid & 31) == 0) s_err[tid >> 5] = err_acc;
+    __syncthreads();  // also orders every shared atomic before the flush below
+    unsigned long long* out = p.results + (size_t)b * p.words;
+    if (tid == 0) {
+        long long e = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) e += s_err[w];
+        if (e != 0) atomicAdd(out, (unsigned long long)e);
+    }
+    for (int k = tid; k < K; k += kThreads) {
+        const unsigned int c = s_cnt[k];
+        if (c) {
+            atomicAdd(out + 1 + k, (unsigned long long)c);
+            if (SUMS) {
+                atomicAdd(out + 1 + K + 3 * k, s_sum[3 * k]);
+                atomicAdd(out + 1 + K + 3 * k + 1, s_sum[3 * k + 1]);
+                atomicAdd(out + 1 + K + 3 * k + 2, s_sum[3 * k + 2]);
+            }
+        }
+    }
+}
+
+template <int VARIANT, bool SRGB, bool SUMS, int IDXW>
+cudaError_t launch_assign_t(const AssignParams& p, int B, int sm_count, cudaStream_t stream) {
+    auto kern = assign_reduce_kernel<VARIANT, SRGB, SUMS, IDXW>;
+    const size_t smem = assign_smem_bytes<SRGB, SUMS>(p.K8, VARIANT);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    const long long slots = (long long)sm_count * occ;
+    const long long ntiles = (long long)((p.n + kTilePx - 1) / kTilePx);
+    // CTAs per candidate: fill the resident slots with whole waves, never more CTAs than tiles
+    long long G = slots / B;
+    if (G < 1) G = 1;
+    if (G > ntiles) G = ntiles;
+    if (G < 1) G = 1;
+    if (G > 65535) G = 65535;
+    const dim3 grid((unsigned)B, (unsigned)G);
+    kern<<<grid, kThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <int VARIANT, bool SRGB, bool SUMS>
+cudaError_t launch_assign_i(const AssignParams& p, int B, int idxw, int sm, cudaStream_t st) {
+    if (idxw == 0) return launch_assign_t<VARIANT, SRGB, SUMS, 0>(p, B, sm, st);
+    if (idxw == 1) return launch_assign_t<VARIANT, SRGB, SUMS, 1>(p, B, sm, st);
+    return launch_assign_t<VARIANT, SRGB, SUMS, 2>(p, B, sm, st);
+}
+template <int VARIANT>
+cudaError_t launch_assign_v(const AssignParams& p, int B, bool srgb, bool sums, int idxw, int sm, cudaStream_t st) {
+    if (srgb) return sums ? launch_assign_i<VARIANT, true, true>(p, B, idxw, sm, st) : launch_assign_i<VARIANT, true, false>(p, B, idxw, sm, st);
+    return sums ? launch_assign_i<VARIANT, false, true>(p, B, idxw, sm, st) : launch_assign_i<VARIANT, false, false>(p, B, idxw, sm, st);
+}
+
+// ====================================================================== final image
+template <typename IdxT>
+__global__ void apply_palette_kernel(const IdxT* __restrict__ idx, size_t n, const float4* __restrict__ pal,
+                                     int K, uint8_t* __restrict__ out_rgb, float4* __restrict__ out_f32) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int k = (int)idx[i];
+    if (k >= K) k = K - 1;
+    const float4 c = __ldg(pal + k);
+    if (out_f32) out_f32[i] = c;  // quantize() returns the palette colour itself (cl:168)
+    if (out_rgb) {
+        // HybridQuantization.java:122 (Icy convertToType(UBYTE, rescale), third-party):
+        // the build defines float -> u8 as (int)(c * 255 + 0.5)
+        out_rgb[3 * i] = (uint8_t)__float2int_rz(HQ_FADD(HQ_FMUL(c.x, 255.0f), 0.5f));
+        out_rgb[3 * i + 1] = (uint8_t)__float2int_rz(HQ_FADD(HQ_FMUL(c.y, 255.0f), 0.5f));
+        out_rgb[3 * i + 2] = (uint8_t)__float2int_rz(HQ_FADD(HQ_FMUL(c.z, 255.0f), 0.5f));
+    }
+}
+
+__global__ void math_probe_kernel(int which, uint32_t first_bits, uint32_t count, float* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float v = __uint_as_float(first_bits + i);
+    float r;
+    if (which == 0) r = hq_cbrtf(v);
+    else if (which == 1) r = hq_pow_2p4f(v);
+    else r = hq_srgb_decode(v);
+    out[i] = r;
+}
+
+}  // namespace
+
+// ====================================================================== launchers
+cudaError_t launch_rgb_to_lab(const uint8_t* d_rgb, size_t n, size_t stride, int whitepoint, float* d_lab,
+                              float* d_unit, int sm_count, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const size_t ntiles = (n + kRlTilePx - 1) / kRlTilePx;
+    size_t grid = (size_t)sm_count * 8;
+    if (grid > ntiles) grid = ntiles;
+    rgb_to_lab_kernel<<<(unsigned)grid, kThreads, 0, stream>>>(d_rgb, n, stride, whitepoint, d_lab, d_unit);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_palette_features(const float* d_palettes, int B, int K, int whitepoint,
+                                    float4* d_pal_lab, float4* d_pal_rgb, cudaStream_t stream) {
+    const int K8 = padded_colors(K);
+    const int total = B * K8;
+    if (total == 0) return cudaSuccess;
+    palette_features_kernel<<<(total + 127) / 128, 128, 0, stream>>>(d_palettes, B, K, K8, whitepoint, d_pal_lab, d_pal_rgb);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_assign_reduce(const AssignArgs& a, cudaStream_t stream) {
+    if (a.B <= 0 || a.K <= 0 || a.K > kMaxColors) return cudaErrorInvalidValue;
+    if (a.n == 0) return cudaSuccess;
+    if (a.space == 1 && a.unit == nullptr) return cudaErrorInvalidValue;
+    AssignParams p;
+    p.feat = a.space == 1 ? a.unit : a.lab;
+    p.lab = a.lab;
+    p.n = a.n; p.stride = a.stride;
+    p.pal_feat = a.space == 1 ? a.pal_rgb : a.pal_lab;
+    p.pal_lab = a.pal_lab;
+    p.K = a.K; p.K8 = padded_colors(a.K);
+    p.words = result_words(a.K, a.want_sums);
+    p.results = a.results;
+    p.idx_out = a.idx_out;
+    const int idxw = a.idx_out ? (a.K <= 256 ? 1 : 2) : 0;
+    int variant = a.variant;
+    if (variant == 0) variant = (a.K <= 16) ? 1 : 2;
+    if (variant == 1) return launch_assign_v<1>(p, a.B, a.space == 1, a.want_sums, idxw, a.sm_count, stream);
+    return launch_assign_v<2>(p, a.B, a.space == 1, a.want_sums, idxw, a.sm_count, stream);
+}
+
+cudaError_t launch_apply_palette(const void* d_idx, bool idx16, size_t n, const float* d_palette, int K,
+                                 uint8_t* d_out_rgb, float* d_out_f32, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (idx16)
+        apply_palette_kernel<uint16_t><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(d_idx), n, reinterpret_cast<const float4*>(d_palette), K, d_out_rgb, reinterpret_cast<float4*>(d_out_f32));
+    else
+        apply_palette_kernel<uint8_t><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint8_t*>(d_idx), n, reinterpret_cast<const float4*>(d_palette), K, d_out_rgb, reinterpret_cast<float4*>(d_out_f32));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_math_probe(int which, uint32_t first_bits, uint32_t count, float* d_out, cudaStream_t stream) {
+    if (count == 0) return cudaSuccess;
+    math_probe_kernel<<<(count + 255) / 256, 256, 0, stream>>>(which, first_bits, count, d_out);
+    return cudaGetLastError();
+}
+
+}  // namespace hq

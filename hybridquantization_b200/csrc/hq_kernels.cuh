@@ -1,0 +1,55 @@
+// hq_kernels.cuh — launch interface of the sm_100a kernels (implemented in hq_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace hq {
+
+constexpr int kMaxColors = 1024;  // palette sizes the fused kernel stages in shared memory
+constexpr int kPadColors = 8;     // palettes are padded to a multiple of this with far colours
+
+inline int padded_colors(int K) { return (K + kPadColors - 1) / kPadColors * kPadColors; }
+
+// result words (8 bytes each) per candidate: [0] sum of error (2^-24 fixed point, int64),
+// [1 .. K] per-colour pixel counts (u64), then if sums are requested
+// [1+K .. 1+4K) per-colour (sum L, sum a, sum b) in 2^-24 fixed point (int64).
+inline int result_words(int K, bool want_sums) { return 1 + K + (want_sums ? 3 * K : 0); }
+
+// plane stride (floats / index elements) for n pixels: rows of every SoA plane start 128-B aligned
+inline size_t plane_stride(size_t n) { return (n + 31) / 32 * 32; }
+
+// packed u8 RGB -> fp32 planes.  lab = [3][stride] (L, a, b); unit = [3][stride] (r, g, b)/255 or null.
+cudaError_t launch_rgb_to_lab(const uint8_t* d_rgb, size_t n, size_t stride, int whitepoint,
+                              float* d_lab, float* d_unit, int sm_count, cudaStream_t stream);
+
+// palettes [B][K][4] sRGB floats -> padded feature tables [B][K8] float4:
+// pal_lab = (L, a, b, 0), pal_rgb = (r, g, b, 0); pad entries are 1e18.
+cudaError_t launch_palette_features(const float* d_palettes, int B, int K, int whitepoint,
+                                    float4* d_pal_lab, float4* d_pal_rgb, cudaStream_t stream);
+
+struct AssignArgs {
+    const float* lab;      // [3][stride]
+    const float* unit;     // [3][stride], required when space == 1
+    size_t n, stride;
+    const float4* pal_lab; // [B][K8]
+    const float4* pal_rgb; // [B][K8]
+    int B, K;
+    int space;             // 0 LAB, 1 SRGB-assign / LAB-score
+    bool want_sums;
+    unsigned long long* results;  // [B][result_words], must be zeroed by the caller
+    void* idx_out;         // [B][stride] u8 (K <= 256) or u16, or null
+    int sm_count;
+    int variant;           // 0 auto, 1 direct index tracking, 2 chunked min + recompute
+};
+cudaError_t launch_assign_reduce(const AssignArgs& a, cudaStream_t stream);
+
+// indices -> output image of the chosen palette colours (u8 RGB packed and/or float RGBA)
+cudaError_t launch_apply_palette(const void* d_idx, bool idx16, size_t n, const float* d_palette /*[K][4]*/,
+                                 int K, uint8_t* d_out_rgb, float* d_out_f32, cudaStream_t stream);
+
+// test hooks: run the single-source routines of hq_math.h on the device over a float range
+cudaError_t launch_math_probe(int which, uint32_t first_bits, uint32_t count, float* d_out,
+                              cudaStream_t stream);
+
+}  // namespace hq

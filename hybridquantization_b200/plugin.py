@@ -1,0 +1,297 @@
+"""Python mirror of the reference's plugin interface for the hot path, over the C ABI.
+
+Class and method names follow the reference so that tests read like tests of the plugin:
+  JavaRandom          icy.util.Random / java.util.Random      (SWASA.java:46-48)
+  SWASA               SWASA.java
+  ImageManipulation   ImageManipulation.java (the backend the CUDA library replaces)
+  ScielabProcessor    ScielabProcessor.java  (white point + bestColors façade)
+  HybridQuantization  HybridQuantization.java (parameter surface :185-257, quantization() :93-137)
+Everything numeric happens in libhq_b200.so; this file only marshals numpy arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import (EVAL_FORCE_CHUNKED, EVAL_FORCE_DIRECT, EVAL_SUMS, SPACE_LAB, SPACE_SRGB, WHITEPOINT_D50,
+                   WHITEPOINT_D65, HqError, JavaRandomState, SwasaParams)
+
+__all__ = ["JavaRandom", "SWASA", "ImageManipulation", "ScielabProcessor", "HybridQuantization", "HqError",
+           "SPACE_LAB", "SPACE_SRGB", "WHITEPOINT_D65", "WHITEPOINT_D50"]
+
+
+def _ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class JavaRandom:
+    """java.util.Random LCG with an explicit seed (the reference's generator is unseeded)."""
+
+    def __init__(self, seed: int = 0):
+        self._s = JavaRandomState()
+        _lib.load().hq_java_random_seed(C.byref(self._s), seed)
+
+    def next(self, bits: int) -> int:
+        return _lib.load().hq_java_random_next(C.byref(self._s), bits)
+
+    def nextInt(self) -> int:
+        return self.next(32)
+
+    def nextFloat(self) -> float:
+        return _lib.load().hq_java_random_next_float(C.byref(self._s))
+
+    def nextDouble(self) -> float:
+        return _lib.load().hq_java_random_next_double(C.byref(self._s))
+
+
+class SWASA:
+    """SWASA.java: schedule parameters; the accept/reject loop itself runs in the library's
+    host driver (hq_find_best_quantization), which uses the same C++ class."""
+
+    def __init__(self, population=4, imax=5000, iTc=20, delta=2.0, convDelay=0.75, convSpread=0.15, t0=20.0,
+                 alpha=0.9, s0=100.0, beta=5.3, seed=77760, convergence=True, space=SPACE_LAB):
+        p = SwasaParams()
+        _lib.load().hq_swasa_default_params(C.byref(p))
+        p.population, p.imax, p.iTc, p.delta = population, imax, iTc, delta
+        p.convergence, p.conv_delay, p.conv_spread = int(bool(convergence)), convDelay, convSpread
+        p.t0, p.alpha, p.s0, p.beta = t0, alpha, s0, beta
+        p.space, p.seed = space, seed
+        self.params = p
+        self.random = JavaRandom(seed)
+
+    def getImax(self) -> int:
+        return self.params.imax
+
+    def getPopulationSize(self) -> int:
+        return self.params.population
+
+    def generateRandomColors(self, numberOfColors: int) -> np.ndarray:
+        out = np.empty((numberOfColors, 4), np.float32)
+        _lib.load().hq_swasa_generate_random_colors(C.byref(self.random._s), numberOfColors, _ptr(out))
+        return out
+
+    def maxStepWidth(self, i: int) -> float:
+        return _lib.load().hq_swasa_max_step_width(C.byref(self.params), i)
+
+    def generateNeighboringColors(self, colors: np.ndarray, iteration: int) -> np.ndarray:
+        colors = np.ascontiguousarray(colors, np.float32)
+        out = np.empty_like(colors)
+        _lib.load().hq_swasa_generate_neighboring_colors(C.byref(self.params), C.byref(self.random._s), _ptr(colors),
+                                                         _ptr(out), colors.shape[0], iteration)
+        return out
+
+    def computePenalty(self, counts: np.ndarray) -> float:
+        return float(np.count_nonzero(np.asarray(counts) == 0)) * float(np.float32(self.params.delta))
+
+
+class ImageManipulation:
+    """The compute backend (ImageManipulation.java) on one GPU.  Creation raises HqError when
+    no usable device exists — the reference's silent zero-output mode (:79-92) is gone."""
+
+    def __init__(self, deltaEType: str = "CIE76", verbose: bool = False, convergence: bool = True, device: int = 0):
+        if deltaEType != "CIE76":
+            raise ValueError("only CIE76 is implemented (the plugin never selects another, HybridQuantization.java:96)")
+        self._lib = _lib.load()
+        self._ctx = C.c_void_p()
+        self.verbose, self.convergence = verbose, convergence
+        rc = self._lib.hq_create(device, C.byref(self._ctx))
+        if rc != 0:
+            msg = self._lib.hq_last_error(None)
+            self._ctx = C.c_void_p()
+            raise HqError(rc, msg.decode() if msg else "")
+        self._cb = None
+        self.shape = None
+
+    # -- lifetime
+    def getCudaAvailable(self) -> bool:
+        return bool(self._ctx)
+
+    def close(self) -> None:
+        if self._ctx:
+            self._lib.hq_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def deviceInfo(self) -> dict:
+        sm, clk = C.c_int(), C.c_int()
+        name = C.create_string_buffer(128)
+        _lib.check(self._ctx, self._lib.hq_device_info(self._ctx, C.byref(sm), C.byref(clk), name, 128))
+        return {"name": name.value.decode(), "sm_count": sm.value, "sm_clock_khz": clk.value}
+
+    # -- image
+    def setImage(self, rgb: np.ndarray, whitepoint: int = WHITEPOINT_D65) -> None:
+        """rgb: uint8 [rows, width, 3] (this rank's rows)."""
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        if rgb.ndim != 3 or rgb.shape[2] != 3:
+            raise ValueError("Please open an image with 3 or more channels")  # HybridQuantization.java:68-69
+        self.shape = rgb.shape[:2]
+        _lib.check(self._ctx, self._lib.hq_set_image_u8(self._ctx, _ptr(rgb), rgb.shape[1], rgb.shape[0], whitepoint))
+
+    def setImageDevice(self, d_rgb_ptr: int, width: int, rows: int, whitepoint: int = WHITEPOINT_D65, stream: int = 0):
+        self.shape = (rows, width)
+        _lib.check(self._ctx, self._lib.hq_set_image_u8_device(self._ctx, d_rgb_ptr, width, rows, whitepoint, stream or None))
+
+    def pixels(self) -> int:
+        return int(self._lib.hq_image_pixels(self._ctx))
+
+    def labImage(self) -> np.ndarray:
+        out = np.empty((3, self.pixels()), np.float32)
+        _lib.check(self._ctx, self._lib.hq_get_lab(self._ctx, _ptr(out)))
+        return out
+
+    # -- evaluation
+    def evalPalettes(self, palettes: np.ndarray, space: int = SPACE_LAB, sums: bool = False, flags: int = 0) -> dict:
+        """palettes float32 [B, K, 4] (R,G,B,0).  Returns exact integer reductions."""
+        palettes = np.ascontiguousarray(palettes, np.float32)
+        if palettes.ndim == 2:
+            palettes = palettes[None]
+        B, K, four = palettes.shape
+        if four != 4:
+            raise ValueError("palettes must be [B, K, 4]")
+        err = np.empty(B, np.int64)
+        counts = np.empty((B, K), np.uint64)
+        sums_fx = np.empty((B, K, 3), np.int64) if sums else None
+        fl = flags | (EVAL_SUMS if sums else 0)
+        _lib.check(self._ctx, self._lib.hq_eval_palettes(self._ctx, _ptr(palettes), B, K, space, fl, _ptr(err), _ptr(counts), _ptr(sums_fx)))
+        return {"err_fx": err, "counts": counts, "sums_fx": sums_fx}
+
+    def evalPalettesDevice(self, d_palettes_ptr: int, B: int, K: int, d_results_ptr: int, space: int = SPACE_LAB,
+                           flags: int = 0, stream: int = 0) -> None:
+        _lib.check(self._ctx, self._lib.hq_eval_palettes_device(self._ctx, d_palettes_ptr, B, K, space, flags, d_results_ptr, stream or None))
+
+    def resultWords(self, K: int, flags: int = 0) -> int:
+        return self._lib.hq_result_words(K, flags)
+
+    def cost(self, err_fx: int, counts: np.ndarray, n_total: int, delta: float) -> float:
+        counts = np.ascontiguousarray(counts, np.uint64)
+        return self._lib.hq_cost(int(err_fx), _ptr(counts), counts.shape[0], n_total, delta)
+
+    def computeQuantizationErrorPopulation(self, colors: np.ndarray, swasa: SWASA, n_total: int = 0, space: int = SPACE_LAB) -> np.ndarray:
+        """ImageManipulation.java:620-727: one cost per candidate palette."""
+        r = self.evalPalettes(colors, space)
+        n_total = n_total or self.pixels()
+        return np.array([self.cost(r["err_fx"][i], r["counts"][i], n_total, swasa.params.delta) for i in range(len(r["err_fx"]))])
+
+    def setAllreduce(self, fn) -> None:
+        """fn(d_words_ptr: int, n_words: int, stream: int) -> 0 on success; None removes the hook."""
+        if fn is None:
+            self._cb = None
+            _lib.check(self._ctx, self._lib.hq_set_allreduce(self._ctx, _lib.ALLREDUCE_FN(), None))
+            return
+
+        def tramp(_user, d_words, n_words, stream):
+            try:
+                return int(fn(d_words or 0, n_words, stream or 0) or 0)
+            except Exception as exc:  # surfaces as HQ_ERR_CALLBACK
+                print(f"[hq] all-reduce hook raised: {exc!r}", flush=True)
+                return 1
+
+        self._cb = _lib.ALLREDUCE_FN(tramp)
+        _lib.check(self._ctx, self._lib.hq_set_allreduce(self._ctx, self._cb, None))
+
+    def findBestQuantization(self, nbOfColors: int, simulatedAnnealing: SWASA, n_total: int = 0, trace: bool = False):
+        """ImageManipulation.java:383-591.  Returns (bestColors [K,4], bestError, trace|None, iterations)."""
+        p = simulatedAnnealing.params
+        p.convergence = int(bool(self.convergence and p.convergence))
+        best = np.empty((nbOfColors, 4), np.float32)
+        best_err, its = C.c_double(), C.c_int()
+        tr = np.empty(((p.imax + 1), p.population), np.float64) if trace else None
+        _lib.check(self._ctx, self._lib.hq_find_best_quantization(self._ctx, nbOfColors, C.byref(p), n_total, _ptr(best),
+                                                                    C.byref(best_err), _ptr(tr), C.byref(its)))
+        return best, best_err.value, tr, its.value
+
+    def requestStop(self) -> None:
+        self._lib.hq_request_stop(self._ctx)
+
+    def quantize(self, colors: np.ndarray, space: int = SPACE_LAB, want_f32: bool = False) -> dict:
+        """ImageManipulation.java:770-798 -> packed u8 image, indices, optionally the float RGBA image."""
+        colors = np.ascontiguousarray(colors, np.float32)
+        n = self.pixels()
+        rgb = np.empty((n, 3), np.uint8)
+        idx = np.empty(n, np.uint16)
+        f32 = np.empty((n, 4), np.float32) if want_f32 else None
+        _lib.check(self._ctx, self._lib.hq_quantize(self._ctx, _ptr(colors), colors.shape[0], space, _ptr(rgb), _ptr(f32), _ptr(idx)))
+        if self.shape is not None:
+            rgb = rgb.reshape(self.shape[0], self.shape[1], 3)
+        return {"rgb": rgb, "idx": idx, "f32": f32}
+
+
+class ScielabProcessor:
+    """ScielabProcessor.java reduced to the hot path: white point + bestColors façade."""
+
+    D50, D65 = "D50", "D65"
+
+    def __init__(self, dpi: int = 72, viewingDistance: float = 45.0, whitepoint: str = "D65", imageProcessor: ImageManipulation | None = None):
+        self.dpi, self.viewingDistance = dpi, viewingDistance
+        self.whitepoint = WHITEPOINT_D50 if whitepoint == "D50" else WHITEPOINT_D65
+        self.imageProcessing = imageProcessor
+
+    def sRGBToScielab(self, rgb: np.ndarray) -> None:
+        self.imageProcessing.setImage(rgb, self.whitepoint)
+
+    def bestColors(self, nbOfColors: int, simulatedAnnealing: SWASA, n_total: int = 0):
+        return self.imageProcessing.findBestQuantization(nbOfColors, simulatedAnnealing, n_total)
+
+    def close(self) -> None:
+        self.imageProcessing.close()
+
+
+@dataclass
+class HybridQuantization:
+    """The plugin's parameters (HybridQuantization.java:185-257; names as the EzVar fields) and
+    its quantization() entry (:93-137) without the Icy GUI objects."""
+
+    nbOfColors: int = 8
+    populationSize: int = 4
+    imax: int = 5000
+    delta: float = 2.0
+    ConvEnable: bool = True
+    ConvDelay: float = 0.75
+    ConvSpread: float = 0.15
+    T0: float = 20.0
+    iTc: int = 20
+    alpha: float = 0.9
+    s0: float = 100.0
+    beta: float = 5.3
+    dpi: int = 72
+    ViewingDistance: float = 45.0
+    WhitePoint: str = "D65"
+    Verbose: bool = False
+    # added: reproducibility, assignment space, device
+    seed: int = 77760
+    space: int = SPACE_LAB
+    device: int = 0
+    result: dict = field(default_factory=dict, repr=False)
+
+    def makeSWASA(self) -> SWASA:
+        return SWASA(self.populationSize, self.imax, self.iTc, self.delta, self.ConvDelay, self.ConvSpread, self.T0,
+                     self.alpha, self.s0, self.beta, seed=self.seed, convergence=self.ConvEnable, space=self.space)
+
+    def quantization(self, rgb: np.ndarray) -> dict:
+        if rgb is None or rgb.size == 0:
+            raise ValueError("Please open an image first.")  # :65-67
+        imageProcessor = ImageManipulation("CIE76", self.Verbose, self.ConvEnable, self.device)  # :96
+        try:
+            swasa = self.makeSWASA()  # :97
+            scielabProcessor = ScielabProcessor(self.dpi, self.ViewingDistance, self.WhitePoint, imageProcessor)  # :101
+            scielabProcessor.sRGBToScielab(rgb)  # :104
+            best, err, _, its = scielabProcessor.bestColors(self.nbOfColors, swasa)  # :107
+            q = imageProcessor.quantize(best, self.space)  # :109
+            self.result = {"bestColors": best, "bestError": err, "iterations": its, "image": q["rgb"], "idx": q["idx"]}
+            return self.result
+        finally:
+            imageProcessor.close()  # :136

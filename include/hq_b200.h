@@ -1,0 +1,168 @@
+/* hq_b200.h — C ABI of the B200-native HybridQuantization hot path (libhq_b200.so).
+ *
+ * This is the drop-in boundary: it replaces the reference's JavaCL/OpenCL backend class
+ * `ImageManipulation` (ImageManipulation.java) for the path
+ *     RGB -> CIELAB  ->  nearest-palette assignment  ->  per-colour counts / Lab sums /
+ *     total error  ->  SWASA candidate scoring,
+ * and nothing else.  Plain pointers and sizes only; a JNI / cgo / ctypes stub can bind
+ * every entry directly (INTEGRATION.md shows the JNI stub for the reference's plugin).
+ *
+ * Citations are File:line under
+ * /root/reference/src/plugins/dbrasseur/hybridquantization/.
+ *
+ * Error behaviour: every entry returns HQ_OK (0) or an error code; the text is available
+ * from hq_last_error().  There is NO CPU / OpenCL fallback: where the reference silently
+ * returns zero arrays without a device (ImageManipulation.java:397,773), this library
+ * fails loudly.
+ *
+ * Threading: a context is single-caller, like the reference's backend object which is only
+ * used from EzPlug's execute() thread.  hq_request_stop() alone may be called from another
+ * thread (the reference's stopExecution(), HybridQuantization.java:311-315).
+ */
+#ifndef HQ_B200_H
+#define HQ_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    HQ_OK = 0,
+    HQ_ERR_INVALID = 1,     /* bad argument */
+    HQ_ERR_CUDA = 2,        /* CUDA runtime / driver error, no device */
+    HQ_ERR_NO_IMAGE = 3,    /* hq_set_image_* has not been called */
+    HQ_ERR_UNSUPPORTED = 4, /* e.g. K > HQ_MAX_COLORS */
+    HQ_ERR_CALLBACK = 5     /* the all-reduce hook reported failure */
+};
+
+enum { HQ_WHITEPOINT_D65 = 0, HQ_WHITEPOINT_D50 = 1 }; /* ScielabProcessor.java:19-21 */
+
+/* HQ_SPACE_LAB : assign and score in CIELAB (the accelerated path's default).
+ * HQ_SPACE_SRGB: assign by sRGB distance exactly as OptimizedConvolution.cl:178-193 does,
+ *                score by CIELAB distance (CIEDE/CIE76, cl:209). */
+enum { HQ_SPACE_LAB = 0, HQ_SPACE_SRGB = 1 };
+
+enum {
+    HQ_EVAL_SUMS = 1,            /* also reduce per-colour Lab sums */
+    HQ_EVAL_FORCE_DIRECT = 2,    /* kernel variant selection, for tests / profiling */
+    HQ_EVAL_FORCE_CHUNKED = 4
+};
+
+#define HQ_MAX_COLORS 1024
+
+typedef struct hq_ctx hq_ctx;
+
+/* ---- lifetime: replaces the constructor / close() (ImageManipulation.java:52-93, :265-269) */
+int hq_create(int device, hq_ctx** out);
+void hq_destroy(hq_ctx* ctx);
+/* ctx may be NULL: then the message of the last failed hq_create() on this thread */
+const char* hq_last_error(const hq_ctx* ctx);
+int hq_device_info(const hq_ctx* ctx, int* sm_count, int* sm_clock_khz, char* name, int name_len);
+
+/* ---- image upload + RGB->CIELAB: replaces the uploads at ImageManipulation.java:451,471-472
+ * and RGBtoXYZ/XYZtoScielab (:100, :285) with the identity spatial filter.
+ * rgb: packed u8, 3 bytes per pixel, row-major, `rows` rows of `width` pixels: the caller's
+ * shard of the image (all of it on one GPU).  Host pointer. */
+int hq_set_image_u8(hq_ctx* ctx, const uint8_t* rgb, int width, int rows, int whitepoint);
+/* same with the packed RGB already resident in device memory; runs on `stream` (a
+ * cudaStream_t, NULL = the context's stream) and does not synchronise */
+int hq_set_image_u8_device(hq_ctx* ctx, const void* d_rgb, int width, int rows, int whitepoint,
+                           void* stream);
+/* debug / parity: the Lab planes [3][n] (L plane, a plane, b plane) */
+int hq_get_lab(hq_ctx* ctx, float* planes);
+uint64_t hq_image_pixels(const hq_ctx* ctx);
+
+/* ---- candidate evaluation: replaces computeQuantizationErrorPopulation
+ * (ImageManipulation.java:620-727): kernels quantizeAndConvertToOpp + CIEDE, the
+ * used-colour flags and the host-side averageArray.
+ * palettes: [B][K][4] floats, sRGB in [0,1] laid out R,G,B,0 as SWASA.java:42-50.
+ * Outputs (each may be NULL), all exact integers so that shards add up bit-identically:
+ *   err_fx [B]        sum over pixels of round(dE * 2^24)
+ *   counts [B][K]     pixels assigned to each colour (colour used <=> count > 0)
+ *   sums_fx[B][K][3]  sum of round(L|a|b * 2^24) of the pixels of each colour
+ *                     (requires HQ_EVAL_SUMS in flags)
+ * If an all-reduce hook is installed the outputs are the totals over all ranks. */
+int hq_eval_palettes(hq_ctx* ctx, const float* palettes, int B, int K, int space, int flags,
+                     int64_t* err_fx, uint64_t* counts, int64_t* sums_fx);
+
+/* number of 8-byte words per candidate in the device result buffer:
+ * [0] err_fx, [1..K] counts, then with HQ_EVAL_SUMS [1+K .. 1+4K) sums */
+int hq_result_words(int K, int flags);
+/* fully asynchronous variant on device memory: d_palettes [B][K][4] floats, d_results
+ * [B][hq_result_words] words (zeroed by the call).  Runs on `stream` (cudaStream_t; NULL =
+ * the context's stream), no host synchronisation, no all-reduce. */
+int hq_eval_palettes_device(hq_ctx* ctx, const void* d_palettes, int B, int K, int space,
+                            int flags, void* d_results, void* stream);
+
+/* cost = (sum dE)/N + delta * #{unused colours}: averageArray + computePenalty
+ * (ImageManipulation.java:712,736-752; SWASA.java:74-82).  Pure host arithmetic. */
+double hq_cost(int64_t err_fx, const uint64_t* counts, int K, uint64_t n_total, float delta);
+
+/* ---- final image: replaces quantize() (ImageManipulation.java:770-798, kernel cl:147-170).
+ * Any output may be NULL.  out_rgb packed u8 [n][3]; out_f32 [n][4] floats (what the
+ * reference returns); out_idx [n] palette indices. */
+int hq_quantize(hq_ctx* ctx, const float* palette, int K, int space, uint8_t* out_rgb,
+                float* out_f32, uint16_t* out_idx);
+
+/* ---- multi-GPU: pixel rows are sharded across ranks (one context per GPU); the only
+ * exchange is a sum of the integer result words.  The hook is called on the context's
+ * stream order with the DEVICE buffer; it must leave the element-wise int64 sum over all
+ * ranks in place (e.g. ncclAllReduce(ncclInt64, ncclSum) / torch.distributed.all_reduce)
+ * and return 0. */
+typedef int (*hq_allreduce_fn)(void* user, void* d_words, size_t n_words, void* stream);
+int hq_set_allreduce(hq_ctx* ctx, hq_allreduce_fn fn, void* user);
+
+/* ---- the annealing search: replaces findBestQuantization (ImageManipulation.java:383-591)
+ * with SWASA.java's schedule.  Accept/reject logic and RNG stay on the host; only the
+ * population scoring runs on the GPU (one launch per iteration, batch = population). */
+typedef struct {
+    int population;     /* "Population size"            HybridQuantization.java:197 (4) */
+    int imax;           /* "Max iterations"             :199 (5000) */
+    int iTc;            /* "Iterations per temperature" :214 (20) */
+    float delta;        /* "Penalty Constant"           :201 (2) */
+    int convergence;    /* "Pop Convergence"            :204 (true) */
+    float conv_delay;   /* "Convergence delay"          :206 (0.75) */
+    float conv_spread;  /* "Convergence spread"         :208 (0.15) */
+    float t0;           /* "Initial temperature"        :212 (20) */
+    float alpha;        /* "Cooling coefficient"        :216 (0.9) */
+    float s0;           /* "Initial Step size"          :223 (100) */
+    float beta;         /* "Adaptation constant"        :224 (5.3) */
+    int space;          /* HQ_SPACE_* (added; default LAB) */
+    int64_t seed;       /* java.util.Random seed (added: the reference's RNG is unseeded) */
+} hq_swasa_params;
+void hq_swasa_default_params(hq_swasa_params* p);
+
+/* n_total: pixels of the WHOLE image (all ranks); 0 = this context's pixel count.
+ * best_colors [K][4]; trace_costs (optional) receives (imax+1)*population costs in
+ * evaluation order; iterations_done (optional) < imax if hq_request_stop() intervened. */
+int hq_find_best_quantization(hq_ctx* ctx, int K, const hq_swasa_params* p, uint64_t n_total,
+                              float* best_colors, double* best_error, double* trace_costs,
+                              int* iterations_done);
+void hq_request_stop(hq_ctx* ctx); /* EzStoppable.stopExecution, HybridQuantization.java:311 */
+
+/* ---- host-side pieces of the plugin that callers outside C++ may want ---- */
+/* java.util.Random-compatible generator */
+typedef struct { uint64_t state; } hq_java_random;
+void hq_java_random_seed(hq_java_random* r, int64_t seed);
+int32_t hq_java_random_next(hq_java_random* r, int bits);
+float hq_java_random_next_float(hq_java_random* r);
+double hq_java_random_next_double(hq_java_random* r);
+/* SWASA.java:40-52, :91-101, :69-72 */
+void hq_swasa_generate_random_colors(hq_java_random* r, int K, float* colors);
+void hq_swasa_generate_neighboring_colors(const hq_swasa_params* p, hq_java_random* r,
+                                          const float* colors, float* next_colors, int K,
+                                          int iteration);
+float hq_swasa_max_step_width(const hq_swasa_params* p, int iteration);
+
+/* ---- test hooks: the single-source arithmetic of csrc/hq_math.h evaluated on the host
+ * (which: 0 cube root, 1 pow 2.4f, 2 sRGB decode) over `count` consecutive float bit
+ * patterns starting at first_bits, and the same on the device. */
+int hq_host_math_range(int which, uint32_t first_bits, uint32_t count, float* out, int threads);
+int hq_device_math_range(hq_ctx* ctx, int which, uint32_t first_bits, uint32_t count, float* out);
+void hq_host_srgb_to_lab(const float rgb[3], int whitepoint, float lab[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HQ_B200_H */

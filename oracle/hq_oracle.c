@@ -1,0 +1,490 @@
+/* hq_oracle.c — CPU ORACLE (test infrastructure only; see hq_oracle.h for the rules).
+ *
+ * Plain C restatement of the reference's algorithm for the hot path.  PARITY UNPINNED:
+ * the reference has no tests/golden vectors and cannot be built or run here.
+ * Compile with -ffp-contract=off: every fp32 expression below is meant to round after
+ * each operation, as Java float arithmetic does; fused multiply-adds appear only where
+ * they are written as fmaf().  Transcendentals are glibc's pow/exp/tanh in double, the
+ * counterpart of Java's Math.pow/exp/tanh.
+ *
+ * Citations: File:line under /root/reference/src/plugins/dbrasseur/hybridquantization/.
+ */
+#define _GNU_SOURCE
+#include "hq_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ colour arithmetic */
+
+/* ScielabProcessor.java:20-21 */
+static const float WHITE[2][3] = {{0.95047f, 1.0f, 1.0883f}, {0.966797f, 1.0f, 0.825188f}};
+
+/* ScielabProcessor.java:59-61 — evaluated at run time in fp32, in Java's order:
+ *   LABDELTA = 6f/29f; LABDELTA2 = LABDELTA*LABDELTA; LABDELTA3 = LABDELTA2*LABDELTA;
+ * :301 uses 3*LABDELTA2 (int*float -> float) and 4.0f/29.0f. */
+static float C_LABDELTA3, C_3LABDELTA2, C_4_29;
+__attribute__((constructor)) static void init_constants(void) {
+    volatile float six = 6.0f, tn = 29.0f, four = 4.0f, three = 3.0f;
+    volatile float d = six / tn;
+    volatile float d2 = d * d;
+    volatile float d3 = d2 * d;
+    volatile float t3 = three * d2;
+    volatile float f429 = four / tn;
+    C_LABDELTA3 = d3; C_3LABDELTA2 = t3; C_4_29 = f429;
+}
+
+float hqo_lab_constants(int which) {
+    if (which == 0) return C_LABDELTA3;
+    if (which == 1) return C_3LABDELTA2;
+    return C_4_29;
+}
+
+/* HybridQuantization.java:95 (Icy convertToType(FLOAT, rescale) — third-party, unpinned):
+ * the build defines u8 -> float as (float)(c / 255.0). */
+float hqo_u8_to_unit(unsigned c) { return (float)((double)c / 255.0); }
+
+/* (float)Math.pow(b, 2.4f): the float literal widens to 2.4000000953674316 */
+float hqo_pow_2p4(float b) { return (float)pow((double)b, (double)2.4f); }
+/* (float)Math.pow(t, 1.0 / 3.0) */
+float hqo_cbrt_pow(float t) { return (float)pow((double)t, 1.0 / 3.0); }
+
+/* ScielabProcessor.java:282 */
+float hqo_srgb_decode(float c) {
+    if (c <= 0.04045f) return c / 12.92f;
+    return hqo_pow_2p4((c + 0.055f) / 1.055f);
+}
+
+/* ScielabProcessor.java:279-291 */
+void hqo_srgb_to_opp(const float rgb[3], float opp[3]) {
+    const float R = hqo_srgb_decode(rgb[0]);
+    const float G = hqo_srgb_decode(rgb[1]);
+    const float B = hqo_srgb_decode(rgb[2]);
+    opp[0] = 0.26641335000823f * R + 0.60316740257478f * G + 0.0011333302293f * B;
+    opp[1] = -0.12197400229389f * R + 0.05598088396616f * G + 0.01326365114329f * B;
+    opp[2] = -0.08033445917708f * R + -0.33146741170125f * G + 0.44913244757774f * B;
+}
+
+static float lab_f(float t) { /* ScielabProcessor.java:301 */
+    if (t > C_LABDELTA3) return hqo_cbrt_pow(t);
+    return (t / C_3LABDELTA2) + C_4_29;
+}
+
+/* ScielabProcessor.java:293-311 */
+void hqo_opp_to_lab(const float opp[3], int whitepoint, float lab[3]) {
+    const float* ill = WHITE[whitepoint == HQO_WHITE_D50 ? 1 : 0];
+    const float X = 0.97959616044562807864f * opp[0] + -1.5347157012664408981f * opp[1] +
+                    0.44459764330437399288f * opp[2];
+    const float Y = 1.188977906742323787f * opp[0] + 0.7643549575179937615f * opp[1] +
+                    0.13512574791125839373f * opp[2];
+    const float Z = 1.2318333139247290457f * opp[0] + 1.1631592597636512884f * opp[1] +
+                    2.0784075888008567862f * opp[2];
+    const float fx = lab_f(X / ill[0]);
+    const float fy = lab_f(Y / ill[1]);
+    const float fz = lab_f(Z / ill[2]);
+    lab[0] = 116.0f * fy - 16.0f;
+    lab[1] = 500.0f * (fx - fy);
+    lab[2] = 200.0f * (fy - fz);
+}
+
+/* ScielabProcessor.java:432 : OpptoLab(sRGBtoOpp(px)) */
+void hqo_srgb_to_lab(const float rgb[3], int whitepoint, float lab[3]) {
+    float opp[3];
+    hqo_srgb_to_opp(rgb, opp);
+    hqo_opp_to_lab(opp, whitepoint, lab);
+}
+
+/* ------------------------------------------------------------------ threading helper */
+typedef void (*range_fn)(void* ctx, size_t lo, size_t hi, int tid);
+typedef struct { range_fn fn; void* ctx; size_t lo, hi; int tid; } range_job;
+static void* range_tramp(void* p) {
+    range_job* j = (range_job*)p;
+    j->fn(j->ctx, j->lo, j->hi, j->tid);
+    return NULL;
+}
+static void parallel_ranges(size_t n, int threads, range_fn fn, void* ctx) {
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    if ((size_t)threads > n) threads = n ? (int)n : 1;
+    if (threads == 1) { fn(ctx, 0, n, 0); return; }
+    pthread_t th[256];
+    range_job jobs[256];
+    for (int t = 0; t < threads; ++t) {
+        jobs[t].fn = fn; jobs[t].ctx = ctx; jobs[t].tid = t;
+        jobs[t].lo = n * (size_t)t / (size_t)threads;
+        jobs[t].hi = n * (size_t)(t + 1) / (size_t)threads;
+        pthread_create(&th[t], NULL, range_tramp, &jobs[t]);
+    }
+    for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+}
+
+/* ------------------------------------------------------------------ image planes */
+typedef struct {
+    const uint8_t* rgb; int wp;
+    float *ur, *ug, *ub, *ll, *la, *lb;
+    float unit[256], lin[256];
+} planes_ctx;
+
+static void planes_range(void* p, size_t lo, size_t hi, int tid) {
+    (void)tid;
+    planes_ctx* c = (planes_ctx*)p;
+    for (size_t i = lo; i < hi; ++i) {
+        const unsigned r = c->rgb[3 * i], g = c->rgb[3 * i + 1], b = c->rgb[3 * i + 2];
+        if (c->ur) { c->ur[i] = c->unit[r]; c->ug[i] = c->unit[g]; c->ub[i] = c->unit[b]; }
+        if (c->ll) {
+            /* identical to hqo_srgb_to_lab on (unit[r],unit[g],unit[b]); the decode of a
+             * u8 channel only has 256 possible values, so it is tabulated */
+            const float R = c->lin[r], G = c->lin[g], B = c->lin[b];
+            float opp[3], lab[3];
+            opp[0] = 0.26641335000823f * R + 0.60316740257478f * G + 0.0011333302293f * B;
+            opp[1] = -0.12197400229389f * R + 0.05598088396616f * G + 0.01326365114329f * B;
+            opp[2] = -0.08033445917708f * R + -0.33146741170125f * G + 0.44913244757774f * B;
+            hqo_opp_to_lab(opp, c->wp, lab);
+            c->ll[i] = lab[0]; c->la[i] = lab[1]; c->lb[i] = lab[2];
+        }
+    }
+}
+
+void hqo_image_planes(const uint8_t* rgb, size_t n, int whitepoint, float* unit_r, float* unit_g,
+                      float* unit_b, float* lab_l, float* lab_a, float* lab_b, int threads) {
+    planes_ctx c;
+    c.rgb = rgb; c.wp = whitepoint;
+    c.ur = unit_r; c.ug = unit_g; c.ub = unit_b; c.ll = lab_l; c.la = lab_a; c.lb = lab_b;
+    for (unsigned v = 0; v < 256; ++v) {
+        c.unit[v] = hqo_u8_to_unit(v);
+        c.lin[v] = hqo_srgb_decode(c.unit[v]);
+    }
+    parallel_ranges(n, threads, planes_range, &c);
+}
+
+/* ------------------------------------------------------------------ assign + reduce */
+static int64_t to_fx(float v) { return (int64_t)llrintf(v * 16777216.0f); }
+
+/* squared distance as the build pins OpenCL distance() (OptimizedConvolution.cl:180,185):
+ * fp32 differences, dx*dx, then fma(dy,dy,.), fma(dz,dz,.) */
+static inline float dist2(float x0, float x1, float x2, float p0, float p1, float p2) {
+    const float d0 = x0 - p0, d1 = x1 - p1, d2 = x2 - p2;
+    return fmaf(d2, d2, fmaf(d1, d1, d0 * d0));
+}
+
+typedef struct {
+    const float *f0, *f1, *f2; /* assignment features [n] */
+    const float *l0, *l1, *l2; /* Lab planes [n] */
+    const float* pal_feat;     /* [B][K][3] assignment features of the palettes */
+    const float* pal_lab;      /* [B][K][3] */
+    int B, K, space;
+    size_t n;
+    uint16_t* idx;             /* [B][n] or NULL */
+    int threads;
+    int64_t* t_err;            /* [threads][B] */
+    uint64_t* t_cnt;           /* [threads][B][K] */
+    int64_t* t_sum;            /* [threads][B][K][3] */
+} assign_ctx;
+
+#define BLK 256
+static void assign_range(void* p, size_t lo, size_t hi, int tid) {
+    assign_ctx* c = (assign_ctx*)p;
+    const int K = c->K;
+    float best[BLK];
+    int bidx[BLK];
+    for (int b = 0; b < c->B; ++b) {
+        const float* pf = c->pal_feat + (size_t)b * K * 3;
+        const float* pl = c->pal_lab + (size_t)b * K * 3;
+        int64_t err = 0;
+        uint64_t* cnt = c->t_cnt + ((size_t)tid * c->B + b) * K;
+        int64_t* sum = c->t_sum + ((size_t)tid * c->B + b) * K * 3;
+        for (size_t base = lo; base < hi; base += BLK) {
+            const int m = (int)((hi - base) < BLK ? (hi - base) : BLK);
+            const float* x0 = c->f0 + base; const float* x1 = c->f1 + base; const float* x2 = c->f2 + base;
+            /* OptimizedConvolution.cl:179-192: start from colour 0, replace on strict < */
+            for (int i = 0; i < m; ++i) { best[i] = dist2(x0[i], x1[i], x2[i], pf[0], pf[1], pf[2]); bidx[i] = 0; }
+            for (int k = 1; k < K; ++k) {
+                const float p0 = pf[3 * k], p1 = pf[3 * k + 1], p2 = pf[3 * k + 2];
+                for (int i = 0; i < m; ++i) {
+                    const float d = dist2(x0[i], x1[i], x2[i], p0, p1, p2);
+                    const int lt = d < best[i];
+                    best[i] = lt ? d : best[i];
+                    bidx[i] = lt ? k : bidx[i];
+                }
+            }
+            for (int i = 0; i < m; ++i) {
+                const size_t px = base + i;
+                const int k = bidx[i];
+                float d2v = best[i];
+                if (c->space == HQO_SPACE_SRGB) /* score in Lab (OptimizedConvolution.cl:209) */
+                    d2v = dist2(c->l0[px], c->l1[px], c->l2[px], pl[3 * k], pl[3 * k + 1], pl[3 * k + 2]);
+                err += to_fx(sqrtf(d2v));
+                cnt[k] += 1;
+                sum[3 * k] += to_fx(c->l0[px]);
+                sum[3 * k + 1] += to_fx(c->l1[px]);
+                sum[3 * k + 2] += to_fx(c->l2[px]);
+                if (c->idx) c->idx[(size_t)b * c->n + px] = (uint16_t)k;
+            }
+        }
+        c->t_err[(size_t)tid * c->B + b] = err;
+    }
+}
+
+void hqo_assign_reduce_planes(const float* unit_rgb3, const float* lab3, size_t n, int whitepoint,
+                              const float* palettes, int B, int K, int space, int64_t* err_fx,
+                              uint64_t* counts, int64_t* sums_fx, uint16_t* idx, int threads) {
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    if ((size_t)threads > n) threads = n ? (int)n : 1;
+    assign_ctx c;
+    memset(&c, 0, sizeof c);
+    float* pal_lab = (float*)malloc(sizeof(float) * (size_t)B * K * 3);
+    float* pal_rgb = (float*)malloc(sizeof(float) * (size_t)B * K * 3);
+    for (size_t j = 0; j < (size_t)B * K; ++j) {
+        const float* s = palettes + 4 * j;
+        pal_rgb[3 * j] = s[0]; pal_rgb[3 * j + 1] = s[1]; pal_rgb[3 * j + 2] = s[2];
+        hqo_srgb_to_lab(s, whitepoint, pal_lab + 3 * j);
+    }
+    c.l0 = lab3; c.l1 = lab3 + n; c.l2 = lab3 + 2 * n;
+    if (space == HQO_SPACE_SRGB) { c.f0 = unit_rgb3; c.f1 = unit_rgb3 + n; c.f2 = unit_rgb3 + 2 * n; c.pal_feat = pal_rgb; }
+    else { c.f0 = c.l0; c.f1 = c.l1; c.f2 = c.l2; c.pal_feat = pal_lab; }
+    c.pal_lab = pal_lab;
+    c.B = B; c.K = K; c.space = space; c.n = n; c.idx = idx; c.threads = threads;
+    c.t_err = (int64_t*)calloc((size_t)threads * B, sizeof(int64_t));
+    c.t_cnt = (uint64_t*)calloc((size_t)threads * B * K, sizeof(uint64_t));
+    c.t_sum = (int64_t*)calloc((size_t)threads * B * K * 3, sizeof(int64_t));
+    parallel_ranges(n, threads, assign_range, &c);
+    for (int b = 0; b < B; ++b) {
+        int64_t e = 0;
+        for (int t = 0; t < threads; ++t) e += c.t_err[(size_t)t * B + b];
+        if (err_fx) err_fx[b] = e;
+        for (int k = 0; k < K; ++k) {
+            uint64_t cn = 0; int64_t s0 = 0, s1 = 0, s2 = 0;
+            for (int t = 0; t < threads; ++t) {
+                const size_t o = ((size_t)t * B + b) * K + k;
+                cn += c.t_cnt[o]; s0 += c.t_sum[3 * o]; s1 += c.t_sum[3 * o + 1]; s2 += c.t_sum[3 * o + 2];
+            }
+            if (counts) counts[(size_t)b * K + k] = cn;
+            if (sums_fx) { int64_t* d = sums_fx + ((size_t)b * K + k) * 3; d[0] = s0; d[1] = s1; d[2] = s2; }
+        }
+    }
+    free(c.t_err); free(c.t_cnt); free(c.t_sum); free(pal_lab); free(pal_rgb);
+}
+
+void hqo_assign_reduce(const uint8_t* rgb, size_t n, int whitepoint, const float* palettes, int B,
+                       int K, int space, int64_t* err_fx, uint64_t* counts, int64_t* sums_fx,
+                       uint16_t* idx, int threads) {
+    float* lab = (float*)malloc(sizeof(float) * 3 * (n ? n : 1));
+    float* unit = (float*)malloc(sizeof(float) * 3 * (n ? n : 1));
+    hqo_image_planes(rgb, n, whitepoint, unit, unit + n, unit + 2 * n, lab, lab + n, lab + 2 * n, threads);
+    hqo_assign_reduce_planes(unit, lab, n, whitepoint, palettes, B, K, space, err_fx, counts, sums_fx, idx, threads);
+    free(lab); free(unit);
+}
+
+/* ImageManipulation.java:712 : averageArray(err) + computePenalty(used)
+ *   averageArray: double sum / length (:736-752);  computePenalty: += delta per unused (SWASA.java:74-82)
+ * The build's sum is the 2^-24 fixed-point integer (exact, order independent). */
+double hqo_cost(int64_t err_fx, const uint64_t* counts, int K, uint64_t n_total, float delta) {
+    double penalty = 0;
+    for (int k = 0; k < K; ++k)
+        if (counts[k] == 0) penalty += delta;
+    const double sum = (double)err_fx * (1.0 / 16777216.0);
+    return sum / (double)n_total + penalty;
+}
+
+/* OptimizedConvolution.cl:147-170 + HybridQuantization.java:111-122 */
+void hqo_quantize(const uint8_t* rgb, size_t n, int whitepoint, const float* palette, int K,
+                  int space, uint8_t* out_rgb, float* out_f32, uint16_t* idx, int threads) {
+    uint16_t* own = idx ? idx : (uint16_t*)malloc(sizeof(uint16_t) * (n ? n : 1));
+    hqo_assign_reduce(rgb, n, whitepoint, palette, 1, K, space, NULL, NULL, NULL, own, threads);
+    for (size_t i = 0; i < n; ++i) {
+        const float* c = palette + 4 * (size_t)own[i];
+        if (out_f32) { out_f32[4 * i] = c[0]; out_f32[4 * i + 1] = c[1]; out_f32[4 * i + 2] = c[2]; out_f32[4 * i + 3] = c[3]; }
+        if (out_rgb)
+            for (int ch = 0; ch < 3; ++ch) out_rgb[3 * i + ch] = (uint8_t)(int)(c[ch] * 255.0f + 0.5f);
+    }
+    if (!idx) free(own);
+}
+
+/* ------------------------------------------------------------------ java.util.Random */
+void hqo_rng_seed(hqo_rng* r, int64_t seed) {
+    r->state = ((uint64_t)seed ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1);
+}
+int32_t hqo_rng_next(hqo_rng* r, int bits) {
+    r->state = (r->state * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1);
+    return (int32_t)(int64_t)(r->state >> (48 - bits));
+}
+float hqo_rng_next_float(hqo_rng* r) { return (float)hqo_rng_next(r, 24) / (float)(1 << 24); }
+double hqo_rng_next_double(hqo_rng* r) {
+    const int64_t hi = (int64_t)hqo_rng_next(r, 26) << 27;
+    const int64_t lo = hqo_rng_next(r, 27);
+    return (double)(hi + lo) * 0x1.0p-53;
+}
+
+/* ------------------------------------------------------------------ SWASA */
+void hqo_swasa_defaults(hqo_swasa_params* p) { /* HybridQuantization.java:192-233 */
+    p->population = 4; p->imax = 5000; p->iTc = 20; p->delta = 2.0f; p->convergence = 1;
+    p->conv_delay = 0.75f; p->conv_spread = 0.15f; p->t0 = 20.0f; p->alpha = 0.9f;
+    p->s0 = 100.0f; p->beta = 5.3f; p->whitepoint = HQO_WHITE_D65; p->space = HQO_SPACE_LAB;
+    p->seed = 77760;
+}
+
+/* SWASA.java:40-52 */
+void hqo_generate_random_colors(hqo_rng* r, int K, float* colors) {
+    for (int i = 0; i < K; ++i) {
+        colors[4 * i] = hqo_rng_next_float(r);
+        colors[4 * i + 1] = hqo_rng_next_float(r);
+        colors[4 * i + 2] = hqo_rng_next_float(r);
+        colors[4 * i + 3] = 0.0f;
+    }
+}
+
+/* SWASA.java:69-72 : (float)(2*s0/(1+Math.exp(beta*i/imax))) */
+float hqo_max_step_width(const hqo_swasa_params* p, int ite) {
+    const float arg = p->beta * (float)ite / (float)p->imax;
+    const float two_s0 = 2.0f * p->s0;
+    return (float)((double)two_s0 / (1.0 + exp((double)arg)));
+}
+
+static float clampf(float v, float mn, float mx) { /* SWASA.java:103-106 */
+    return v > mn ? (v > mx ? mx : v) : mn;
+}
+
+/* SWASA.java:91-101 */
+void hqo_generate_neighboring_colors(const hqo_swasa_params* p, hqo_rng* r, const float* colors,
+                                     float* next, int K, int ite) {
+    const float w = hqo_max_step_width(p, ite) / 256.0f;
+    for (int i = 0; i < K; ++i) {
+        for (int ch = 0; ch < 3; ++ch) {
+            const float u = hqo_rng_next_float(r) * 2.0f - 1.0f;
+            next[4 * i + ch] = clampf(colors[4 * i + ch] + u * w, 0.0f, 1.0f);
+        }
+        next[4 * i + 3] = 0.0f;
+    }
+}
+
+/* ImageManipulation.java:383-591 with the scoring of SURVEY D2 (identity spatial filter) */
+double hqo_find_best_quantization(const uint8_t* rgb, int w, int h, int K,
+                                  const hqo_swasa_params* p, float* best_colors,
+                                  double* trace_costs, int threads) {
+    const size_t n = (size_t)w * h;
+    const int P = p->population;
+    const size_t pal = (size_t)K * 4;
+    float* lab = (float*)malloc(sizeof(float) * 3 * n);
+    float* unit = (float*)malloc(sizeof(float) * 3 * n);
+    hqo_image_planes(rgb, n, p->whitepoint, unit, unit + n, unit + 2 * n, lab, lab + n, lab + 2 * n, threads);
+    float* colors = (float*)malloc(sizeof(float) * P * pal);
+    float* current = (float*)malloc(sizeof(float) * P * pal);
+    double* cur_err = (double*)calloc((size_t)(P > 0 ? P : 1), sizeof(double));
+    double* errs = (double*)malloc(sizeof(double) * P);
+    int64_t* err_fx = (int64_t*)malloc(sizeof(int64_t) * P);
+    uint64_t* counts = (uint64_t*)malloc(sizeof(uint64_t) * P * K);
+    hqo_rng rng;
+    hqo_rng_seed(&rng, p->seed);
+    float temperature = p->t0; /* SWASA.reset(), :30-34 */
+
+    for (int i = 0; i < P; ++i) hqo_generate_random_colors(&rng, K, colors + i * pal); /* :413-417 */
+    hqo_assign_reduce_planes(unit, lab, n, p->whitepoint, colors, P, K, p->space, err_fx, counts, NULL, NULL, threads);
+    for (int i = 0; i < P; ++i) {
+        cur_err[i] = hqo_cost(err_fx[i], counts + (size_t)i * K, K, n, p->delta);
+        if (trace_costs) trace_costs[i] = cur_err[i];
+    }
+    int mn = 0; /* argmin, :843-856 (strict >) */
+    for (int i = 1; i < P; ++i) if (cur_err[mn] > cur_err[i]) mn = i;
+    double best_err = cur_err[mn];
+    memcpy(best_colors, colors + mn * pal, sizeof(float) * pal);
+
+    for (int ite = 1; ite <= p->imax; ++ite) { /* :497 */
+        if (ite % p->iTc == 0) temperature *= p->alpha; /* SWASA.java:84-89 */
+        for (int j = 0; j < P; ++j)                     /* :508-511 */
+            hqo_generate_neighboring_colors(p, &rng, colors + j * pal, current + j * pal, K, ite);
+        hqo_assign_reduce_planes(unit, lab, n, p->whitepoint, current, P, K, p->space, err_fx, counts, NULL, NULL, threads);
+        for (int i = 0; i < P; ++i) {
+            errs[i] = hqo_cost(err_fx[i], counts + (size_t)i * K, K, n, p->delta);
+            if (trace_costs) trace_costs[(size_t)ite * P + i] = errs[i];
+        }
+        double minerror = DBL_MAX; int minidx = 0; /* :516-517 */
+        for (int i = 0; i < P; ++i) {
+            if (P > 1 && errs[i] < minerror) { minerror = errs[i]; minidx = i; } /* :520-524 */
+            const double dE = errs[i] - cur_err[i];
+            /* SWASA.java:54-57,64-67 : the RNG is drawn only when dE > 0 */
+            const int accepted = dE <= 0 || exp(-dE / (double)temperature) > hqo_rng_next_double(&rng);
+            if (accepted) {
+                cur_err[i] = errs[i];
+                memcpy(colors + i * pal, current + i * pal, sizeof(float) * pal);
+                if (cur_err[i] < best_err) {
+                    best_err = cur_err[i];
+                    memcpy(best_colors, current + i * pal, sizeof(float) * pal);
+                }
+            }
+        }
+        for (int i = 0; p->convergence && P > 1 && i < P; ++i) { /* :538-545 */
+            /* SWASA.java:59-62 : float argument, double tanh */
+            const float num = (float)ite - p->conv_delay * (float)p->imax;
+            const float den = p->conv_spread * (float)p->imax;
+            const double keep = -(tanh((double)(num / den))) / 2 + 0.5;
+            if (!(keep > hqo_rng_next_double(&rng))) {
+                cur_err[i] = minerror;
+                memcpy(colors + i * pal, current + minidx * pal, sizeof(float) * pal);
+            }
+        }
+    }
+    free(lab); free(unit); free(colors); free(current); free(cur_err); free(errs); free(err_fx); free(counts);
+    return best_err;
+}
+
+/* ------------------------------------------------------------------ range evaluation (tests) */
+typedef struct { int which; uint32_t first; float* out; } mrange_ctx;
+static void mrange_fn(void* p, size_t lo, size_t hi, int tid) {
+    (void)tid;
+    mrange_ctx* c = (mrange_ctx*)p;
+    for (size_t i = lo; i < hi; ++i) {
+        const uint32_t u = c->first + (uint32_t)i;
+        float v; memcpy(&v, &u, 4);
+        c->out[i] = c->which == 0 ? hqo_cbrt_pow(v) : (c->which == 1 ? hqo_pow_2p4(v) : hqo_srgb_decode(v));
+    }
+}
+/* which: 0 (float)pow(t,1.0/3.0), 1 (float)pow(b,2.4f), 2 sRGB decode; over `count`
+ * consecutive float bit patterns starting at first_bits */
+void hqo_math_range(int which, uint32_t first_bits, uint32_t count, float* out, int threads) {
+    mrange_ctx c = {which, first_bits, out};
+    parallel_ranges(count, threads, mrange_fn, &c);
+}
+
+/* ------------------------------------------------------------------ synthetic images */
+static uint64_t splitmix64(uint64_t* s) {
+    uint64_t z = (*s += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+/* uniform: byte j of the image is byte (j%8) (little-endian) of SplitMix64 output j/8 + 2.
+ * smooth: per channel a bilinear blend of four corner bytes (outputs 0 and 1) plus
+ * ((uniform byte) % 17) - 8, clamped to 0..255. */
+void hqo_synth_image(uint8_t* rgb, int w, int h, uint64_t seed, int smooth) {
+    uint64_t s = seed;
+    const uint64_t o0 = splitmix64(&s), o1 = splitmix64(&s);
+    const size_t nbytes = (size_t)w * h * 3;
+    uint64_t cur = 0;
+    for (size_t j = 0; j < nbytes; ++j) {
+        if ((j & 7) == 0) cur = splitmix64(&s);
+        rgb[j] = (uint8_t)(cur >> (8 * (j & 7)));
+    }
+    if (!smooth) return;
+    int corner[3][4];
+    for (int c = 0; c < 3; ++c)
+        for (int q = 0; q < 4; ++q) {
+            const int b = c * 4 + q;
+            corner[c][q] = (int)(((b < 8 ? o0 : o1) >> (8 * (b & 7))) & 0xff);
+        }
+    const int64_t wd = w > 1 ? w - 1 : 1, hd = h > 1 ? h - 1 : 1;
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x)
+            for (int c = 0; c < 3; ++c) {
+                const size_t j = ((size_t)y * w + x) * 3 + c;
+                const int64_t top = corner[c][0] * (wd - x) + (int64_t)corner[c][1] * x;
+                const int64_t bot = corner[c][2] * (wd - x) + (int64_t)corner[c][3] * x;
+                const int64_t base = (top * (hd - y) + bot * y) / (wd * hd);
+                int64_t v = base + (int)(rgb[j] % 17) - 8;
+                rgb[j] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+            }
+}

@@ -1,0 +1,95 @@
+"""The oracle against everything that pins it: analytic anchors, java.util.Random
+known answers (Appendix B) and the committed golden vectors.  CPU only."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import bits, from_bits, idx_crc, load_golden
+
+
+def test_lab_constants_match_java_fp32_evaluation(oracle):
+    # ScielabProcessor.java:59-61 evaluated in fp32
+    d = np.float32(6.0) / np.float32(29.0)
+    d2 = np.float32(d * d)
+    d3 = np.float32(d2 * d)
+    L = oracle.load()
+    assert np.float32(L.hqo_lab_constants(0)) == d3
+    assert np.float32(L.hqo_lab_constants(1)) == np.float32(np.float32(3.0) * d2)
+    assert np.float32(L.hqo_lab_constants(2)) == np.float32(4.0) / np.float32(29.0)
+    assert abs(float(d3) - 0.008856452070) < 1e-11
+
+
+@pytest.mark.parametrize("rgb,lab", [
+    ((0, 0, 0), (0.0, 0.0, 0.0)),
+    ((1, 1, 1), (100.0, 0.0, -0.03245)),
+    ((1, 0, 0), (53.2408, 80.0925, 67.1947)),
+    ((0, 1, 0), (87.7347, -86.1827, 83.1638)),
+    ((0, 0, 1), (32.2970, 79.1875, -107.8912)),
+    ((128 / 255, 128 / 255, 128 / 255), (53.5850, 0.0, -0.01947)),
+])
+def test_lab_anchors(oracle, rgb, lab):
+    got = oracle.srgb_to_lab(np.array(rgb, np.float32))
+    assert np.allclose(got, lab, atol=1e-3), (got, lab)
+
+
+def test_java_random_known_answers(oracle):
+    L = oracle.load()
+    r = oracle.Rng()
+    L.hqo_rng_seed(C.byref(r), 42)
+    assert L.hqo_rng_next(C.byref(r), 32) == -1170105035
+    L.hqo_rng_seed(C.byref(r), 0)
+    assert L.hqo_rng_next(C.byref(r), 32) == -1155484576
+    L.hqo_rng_seed(C.byref(r), 0)
+    assert L.hqo_rng_next_double(C.byref(r)) == 0.730967787376657
+    L.hqo_rng_seed(C.byref(r), 42)
+    got = [L.hqo_rng_next_float(C.byref(r)) for _ in range(3)]
+    assert [float(g).hex() for g in got] == ["0x1.74833a0000000p-1", "0x1.bfd1400000000p-5", "0x1.5dcf760000000p-1"]
+    L.hqo_rng_seed(C.byref(r), 42)
+    assert [L.hqo_rng_next_double(C.byref(r)) for _ in range(2)] == [0.7275636800328681, 0.6832234717598454]
+
+
+def test_golden_lab_vectors(oracle):
+    g = load_golden("lab_vectors.json")
+    u8 = np.array(g["u8"], np.uint8)
+    unit, lab65 = oracle.image_planes(u8, oracle.WHITE_D65, 2)
+    _, lab50 = oracle.image_planes(u8, oracle.WHITE_D50, 1)
+    assert np.array_equal(bits(unit.T.copy()).ravel(), bits(from_bits(g["unit"])))
+    assert np.array_equal(bits(lab65.T.copy()).ravel(), bits(from_bits(g["lab_d65"])))
+    assert np.array_equal(bits(lab50.T.copy()).ravel(), bits(from_bits(g["lab_d50"])))
+    cols = from_bits(g["float_rgb"], (-1, 3))
+    want = from_bits(g["float_lab_d65"], (-1, 3))
+    for c, w in zip(cols, want):
+        assert np.array_equal(bits(oracle.srgb_to_lab(c)), bits(w))
+    # the pixel path (u8 -> LUT) and the palette path (float) agree on u8-representable colours
+    for i in range(len(u8)):
+        assert np.array_equal(bits(oracle.srgb_to_lab(unit[:, i].copy())), bits(lab65[:, i].copy()))
+
+
+def test_golden_assign_vectors(oracle):
+    from hybridquantization_b200 import synth
+
+    g = load_golden("assign_vectors.json")
+    for name, v in g.items():
+        img = synth.synth_image(v["w"], v["h"], v["seed"], v["smooth"])
+        pal = synth.synth_palettes(v["B"], v["K"])
+        for threads in (1, 3):
+            r = oracle.assign_reduce(img, pal, v["space"], oracle.WHITE_D65, want_idx=True, threads=threads)
+            assert [int(x) for x in r["err_fx"]] == v["err_fx"], name
+            assert r["counts"].tolist() == v["counts"], name
+            assert r["sums_fx"].tolist() == v["sums_fx"], name
+            assert [idx_crc(r["idx"][b], v["w"] * v["h"]) for b in range(v["B"])] == v["idx_crc"], name
+
+
+def test_golden_swasa_vectors(oracle):
+    from hybridquantization_b200 import synth
+
+    g = load_golden("swasa_vectors.json")
+    for name, v in g.items():
+        img = synth.synth_image(v["w"], v["h"], v["image_seed"], v["smooth"])
+        p = oracle.swasa_params(population=v["population"], imax=v["imax"], iTc=v["iTc"], convergence=v["convergence"],
+                                space=v["space"], seed=v["seed"])
+        best, err, tr = oracle.find_best_quantization(img, v["K"], p, trace=True, threads=2)
+        assert float(err).hex() == v["best_error"], name
+        assert np.array_equal(bits(best).ravel(), bits(from_bits(v["best_colors"]))), name
+        assert [float(x).hex() for x in tr.reshape(-1)] == v["trace"], name
