@@ -77,6 +77,9 @@ struct hq_ctx {
 
     hq_allreduce_fn allreduce = nullptr;
     void* allreduce_user = nullptr;
+    bool profiling = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
     std::atomic<bool> stop{false};
     volatile bool stop_flag_view = false;
 };
@@ -148,7 +151,9 @@ int eval_device(hq_ctx* c, const float* d_palettes, int B, int K, int space, int
     a.B = B; a.K = K; a.space = space; a.want_sums = sums;
     a.results = d_results; a.idx_out = d_idx; a.sm_count = c->sm_count;
     a.variant = (flags & HQ_EVAL_FORCE_DIRECT) ? 1 : ((flags & HQ_EVAL_FORCE_CHUNKED) ? 2 : 0);
+    if (c->profiling) HQ_CUDA(c, cudaEventRecord(c->ev0, st));
     HQ_CUDA(c, hq::launch_assign_reduce(a, st));
+    if (c->profiling) { HQ_CUDA(c, cudaEventRecord(c->ev1, st)); c->ev_valid = true; }
     return HQ_OK;
 }
 
@@ -189,6 +194,8 @@ void hq_destroy(hq_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
     c->d_rgb.release(); c->d_lab.release(); c->d_unit.release(); c->d_pal.release();
     c->d_pal_lab.release(); c->d_pal_rgb.release(); c->d_results.release(); c->d_idx.release();
     c->d_out_rgb.release(); c->d_out_f32.release(); c->h_pal.release(); c->h_results.release();
@@ -401,6 +408,53 @@ void hq_swasa_generate_neighboring_colors(const hq_swasa_params* p, hq_java_rand
 float hq_swasa_max_step_width(const hq_swasa_params* p, int iteration) {
     hq::JavaRandom j;
     return make_swasa(p, &j).maxStepWidth(iteration);
+}
+
+int hq_set_profiling(hq_ctx* c, int enabled) {
+    if (!c) return HQ_ERR_INVALID;
+    int rc = bind_device(c); if (rc) return rc;
+    if (enabled && !c->ev0) { HQ_CUDA(c, cudaEventCreate(&c->ev0)); HQ_CUDA(c, cudaEventCreate(&c->ev1)); }
+    c->profiling = enabled != 0;
+    c->ev_valid = false;
+    return HQ_OK;
+}
+
+int hq_last_assign_ms(hq_ctx* c, float* ms) {
+    if (!c || !ms) return HQ_ERR_INVALID;
+    if (!c->ev_valid) return fail(c, HQ_ERR_INVALID, "no profiled evaluation yet (hq_set_profiling)");
+    int rc = bind_device(c); if (rc) return rc;
+    HQ_CUDA(c, cudaEventSynchronize(c->ev1));
+    HQ_CUDA(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return HQ_OK;
+}
+
+int hq_measure_fp32_peak(hq_ctx* c, double* tflops_ffma, double* tflops_ffma2) {
+    if (!c) return HQ_ERR_INVALID;
+    int rc = bind_device(c); if (rc) return rc;
+    DevBuf<float> d;
+    HQ_CUDA(c, d.reserve(1));
+    cudaEvent_t e0, e1;
+    HQ_CUDA(c, cudaEventCreate(&e0));
+    HQ_CUDA(c, cudaEventCreate(&e1));
+    const int iters = 40000;  // 40000 * 32 FMA * 1024 threads/SM: ~20 ms per launch
+    double best[2] = {0, 0};
+    for (int packed = 0; packed < 2; ++packed)
+        for (int rep = 0; rep < 4; ++rep) {
+            HQ_CUDA(c, cudaEventRecord(e0, c->stream));
+            HQ_CUDA(c, hq::launch_fp32_peak(packed != 0, iters, c->sm_count, d.p, c->stream));
+            HQ_CUDA(c, cudaEventRecord(e1, c->stream));
+            HQ_CUDA(c, cudaEventSynchronize(e1));
+            float ms = 0;
+            HQ_CUDA(c, cudaEventElapsedTime(&ms, e0, e1));
+            const double flop = (double)iters * 32.0 * (packed ? 4.0 : 2.0) * 256.0 * 4.0 * c->sm_count;
+            const double tf = flop / (ms * 1e-3) / 1e12;
+            if (rep > 0 && tf > best[packed]) best[packed] = tf;
+        }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    d.release();
+    if (tflops_ffma) *tflops_ffma = best[0];
+    if (tflops_ffma2) *tflops_ffma2 = best[1];
+    return HQ_OK;
 }
 
 int hq_host_math_range(int which, uint32_t first_bits, uint32_t count, float* out, int threads) {

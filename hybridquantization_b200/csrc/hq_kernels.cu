@@ -456,7 +456,37 @@ __global__ void math_probe_kernel(int which, uint32_t first_bits, uint32_t count
     out[i] = r;
 }
 
+// FP32 ceiling probe: 8 independent FMA chains per thread, 8 warps per CTA, 4 CTAs per SM
+template <bool PACKED>
+__global__ void __launch_bounds__(kThreads) fp32_peak_kernel(int iters, float* __restrict__ out) {
+    float s = 1.0f + 1e-7f * (float)threadIdx.x, t = 1e-9f * (float)blockIdx.x;
+    float a[8];
+    uint64_t A[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = (float)i; A[i] = pack2((float)i, (float)-i); }
+    const uint64_t S = pack2(s, s), T = pack2(t, t);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (PACKED) A[i] = fma2(A[i], S, T);
+                else a[i] = __fmaf_rn(a[i], s, t);
+            }
+    }
+    float r = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { float lo, hi; unpack2(A[i], lo, hi); r += a[i] + lo + hi; }
+    if (r == 12345.678f) out[0] = r;
+}
+
 }  // namespace
+
+cudaError_t launch_fp32_peak(bool packed, int iters, int sm_count, float* d_out, cudaStream_t stream) {
+    if (packed) fp32_peak_kernel<true><<<sm_count * 4, kThreads, 0, stream>>>(iters, d_out);
+    else fp32_peak_kernel<false><<<sm_count * 4, kThreads, 0, stream>>>(iters, d_out);
+    return cudaGetLastError();
+}
 
 // ====================================================================== launchers
 cudaError_t launch_rgb_to_lab(const uint8_t* d_rgb, size_t n, size_t stride, int whitepoint, float* d_lab,

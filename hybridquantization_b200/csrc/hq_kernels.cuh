@@ -52,4 +52,7 @@ cudaError_t launch_apply_palette(const void* d_idx, bool idx16, size_t n, const 
 cudaError_t launch_math_probe(int which, uint32_t first_bits, uint32_t count, float* d_out,
                               cudaStream_t stream);
 
+// FFMA-saturating probe: `iters` x 32 dependent-chain FMAs per thread (8 chains), scalar or packed
+cudaError_t launch_fp32_peak(bool packed, int iters, int sm_count, float* d_out, cudaStream_t stream);
+
 }  // namespace hq

@@ -1,0 +1,63 @@
+"""Multi-GPU plumbing: pixel-row sharding + the one exchange step (an integer all-reduce of the
+per-candidate result words) over torch.distributed (NCCL on GPUs, gloo in CPU tests).
+
+One process per GPU.  Each rank uploads only its rows; every rank runs the identical host-side
+annealing loop with the identical seed, so after the all-reduce all ranks take the same
+accept/reject decisions — the trajectory does not depend on the number of GPUs because the
+reduced quantities are exact integers.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def row_shard(height: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous block of rows [r0, r1) of rank `rank`: rows r*H/G .. (r+1)*H/G."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError("bad rank / world size")
+    return height * rank // world_size, height * (rank + 1) // world_size
+
+
+def allreduce_words(t):
+    """In-place SUM all-reduce of an int64 tensor of result words (no-op when not distributed)."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+class _DevWords:
+    """Exposes a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr: int, n_words: int):
+        self.__cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+def install_nccl_allreduce(backend) -> None:
+    """Installs the backend's all-reduce hook: sums the device result words over all ranks with
+    torch.distributed (NCCL), ordered on the library's own stream."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        backend.setAllreduce(None)
+        return
+
+    def hook(d_ptr: int, n_words: int, stream: int) -> int:
+        t = torch.as_tensor(_DevWords(d_ptr, n_words), device=torch.device("cuda", torch.cuda.current_device()))
+        ext = torch.cuda.ExternalStream(stream) if stream else torch.cuda.current_stream()
+        with torch.cuda.stream(ext):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return 0
+
+    backend.setAllreduce(hook)
+
+
+def reduce_partials_numpy(parts: list[dict]) -> dict:
+    """Host-side statement of what the all-reduce computes (used by the CPU gloo tests)."""
+    out = {k: np.zeros_like(parts[0][k]) for k in ("err_fx", "counts", "sums_fx") if parts[0].get(k) is not None}
+    for p in parts:
+        for k in out:
+            out[k] += p[k]
+    return out

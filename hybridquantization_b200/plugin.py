@@ -132,6 +132,20 @@ class ImageManipulation:
         _lib.check(self._ctx, self._lib.hq_device_info(self._ctx, C.byref(sm), C.byref(clk), name, 128))
         return {"name": name.value.decode(), "sm_count": sm.value, "sm_clock_khz": clk.value}
 
+    # -- measurement hooks
+    def setProfiling(self, enabled: bool) -> None:
+        _lib.check(self._ctx, self._lib.hq_set_profiling(self._ctx, int(enabled)))
+
+    def lastAssignMs(self) -> float:
+        ms = C.c_float()
+        _lib.check(self._ctx, self._lib.hq_last_assign_ms(self._ctx, C.byref(ms)))
+        return ms.value
+
+    def measureFp32Peak(self) -> dict:
+        a, b = C.c_double(), C.c_double()
+        _lib.check(self._ctx, self._lib.hq_measure_fp32_peak(self._ctx, C.byref(a), C.byref(b)))
+        return {"ffma_tflops": a.value, "ffma2_tflops": b.value}
+
     # -- image
     def setImage(self, rgb: np.ndarray, whitepoint: int = WHITEPOINT_D65) -> None:
         """rgb: uint8 [rows, width, 3] (this rank's rows)."""

@@ -46,6 +46,15 @@ def synth_image(width: int, height: int, seed: int, smooth: bool = False) -> np.
     return out
 
 
+def synth_image_rows(width: int, height: int, seed: int, r0: int, r1: int) -> np.ndarray:
+    """Rows [r0, r1) of the UNIFORM synth_image(width, height, seed) without generating the rest
+    (a rank's shard of a large image)."""
+    b0, b1 = r0 * width * 3, r1 * width * 3
+    w0, w1 = b0 // 8, (b1 + 7) // 8
+    words = _splitmix64(seed, 2 + w0, max(w1 - w0, 0))
+    return words.view(np.uint8)[b0 - 8 * w0: b1 - 8 * w0].copy().reshape(r1 - r0, width, 3)
+
+
 class _JavaRandomNp:
     """java.util.Random in pure Python ints (host-side test data only)."""
 

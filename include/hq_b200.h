@@ -155,6 +155,14 @@ void hq_swasa_generate_neighboring_colors(const hq_swasa_params* p, hq_java_rand
                                           int iteration);
 float hq_swasa_max_step_width(const hq_swasa_params* p, int iteration);
 
+/* ---- measurement hooks (bench.py): CUDA events recorded on the launching stream right
+ * around the assign+reduce kernel of the most recent evaluation; and an FFMA-saturating
+ * microbenchmark giving the FP32 CUDA-core ceiling of THIS device at its current clocks
+ * (scalar FFMA and packed FFMA2), the denominator of the large-K roofline. */
+int hq_set_profiling(hq_ctx* ctx, int enabled);
+int hq_last_assign_ms(hq_ctx* ctx, float* ms);
+int hq_measure_fp32_peak(hq_ctx* ctx, double* tflops_ffma, double* tflops_ffma2);
+
 /* ---- test hooks: the single-source arithmetic of csrc/hq_math.h evaluated on the host
  * (which: 0 cube root, 1 pow 2.4f, 2 sRGB decode) over `count` consecutive float bit
  * patterns starting at first_bits, and the same on the device. */

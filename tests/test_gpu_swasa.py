@@ -1,0 +1,76 @@
+"""Fixed-seed SWASA runs: the GPU path must reproduce the oracle's trajectory bit for bit —
+every candidate cost of every iteration, the final palette and the quantised image."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import bits, from_bits, load_golden
+from hybridquantization_b200 import SPACE_LAB, SPACE_SRGB, SWASA, HybridQuantization, synth
+
+pytestmark = pytest.mark.gpu
+THREADS = max(1, len(os.sched_getaffinity(0)))
+
+
+def test_golden_swasa_vectors_on_gpu(backend):
+    g = load_golden("swasa_vectors.json")
+    for name, v in g.items():
+        img = synth.synth_image(v["w"], v["h"], v["image_seed"], v["smooth"])
+        backend.setImage(img)
+        backend.convergence = True
+        sw = SWASA(population=v["population"], imax=v["imax"], iTc=v["iTc"], seed=v["seed"], convergence=bool(v["convergence"]), space=v["space"])
+        best, err, tr, its = backend.findBestQuantization(v["K"], sw, trace=True)
+        assert its == v["imax"]
+        assert [float(x).hex() for x in tr.reshape(-1)] == v["trace"], name
+        assert float(err).hex() == v["best_error"], name
+        assert np.array_equal(bits(best).ravel(), bits(from_bits(v["best_colors"]))), name
+
+
+@pytest.mark.parametrize("space", [SPACE_LAB, SPACE_SRGB])
+def test_c1_512x512_k16_trajectory_matches_oracle(backend, oracle, space):
+    # BASELINE config C1 (reference defaults, population 4) with a shortened schedule
+    img = synth.synth_image(512, 512, synth.SEED_BASE + 1, smooth=True)
+    imax = 400
+    backend.setImage(img)
+    backend.convergence = True
+    sw = SWASA(population=4, imax=imax, seed=77760, space=space)
+    best, err, tr, its = backend.findBestQuantization(16, sw, trace=True)
+    p = oracle.swasa_params(population=4, imax=imax, seed=77760, space=space)
+    obest, oerr, otr = oracle.find_best_quantization(img, 16, p, trace=True, threads=THREADS)
+    assert its == imax
+    assert np.array_equal(tr.view(np.uint64), otr.view(np.uint64))
+    assert err == oerr
+    assert np.array_equal(bits(best), bits(obest))
+    got = backend.quantize(best, space)
+    want = oracle.quantize(img, obest, space)
+    assert np.array_equal(got["rgb"].reshape(-1, 3), want["rgb"]) and np.array_equal(got["idx"], want["idx"])
+
+
+def test_plugin_entry_point_end_to_end(oracle):
+    img = synth.synth_image(96, 64, 5, smooth=True)
+    hq = HybridQuantization(nbOfColors=8, populationSize=4, imax=150, seed=4242)
+    res = hq.quantization(img)
+    p = oracle.swasa_params(population=4, imax=150, seed=4242)
+    obest, oerr, _ = oracle.find_best_quantization(img, 8, p, threads=THREADS)
+    assert res["bestError"] == oerr and np.array_equal(bits(res["bestColors"]), bits(obest))
+    assert np.array_equal(res["image"].reshape(-1, 3), oracle.quantize(img, obest)["rgb"])
+    assert res["image"].shape == img.shape and res["image"].dtype == np.uint8
+    with pytest.raises(ValueError):
+        hq.quantization(np.zeros((0, 0, 3), np.uint8))
+
+
+def test_stop_request_returns_best_so_far(backend):
+    # EzStoppable (HybridQuantization.java:311-319): the flag is polled once per iteration
+    import threading
+    import time
+
+    img = synth.synth_image(512, 512, 3)
+    backend.setImage(img)
+    sw = SWASA(population=4, imax=200000, seed=1)
+    t = threading.Timer(0.5, backend.requestStop)
+    t.start()
+    t0 = time.time()
+    best, err, _, its = backend.findBestQuantization(64, sw)
+    t.join()
+    assert 0 < its < 200000 and time.time() - t0 < 30
+    assert np.isfinite(err) and best.shape == (64, 4)

@@ -23,3 +23,9 @@ def test_palettes_follow_generate_random_colors_order(oracle):
     for b in range(3):
         L.hqo_generate_random_colors(C.byref(r), 5, want[b].ctypes.data_as(C.c_void_p))
     assert np.array_equal(pal.view(np.uint32), want.view(np.uint32))
+
+
+def test_row_generation_matches_whole_image():
+    whole = synth.synth_image(37, 29, 99)
+    for r0, r1 in ((0, 29), (0, 1), (3, 17), (28, 29), (5, 5)):
+        assert np.array_equal(synth.synth_image_rows(37, 29, 99, r0, r1), whole[r0:r1])
