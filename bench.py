@@ -176,10 +176,16 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
     K, B = a.colors, a.batch
     flags = {0: 0, 1: EVAL_FORCE_DIRECT, 2: EVAL_FORCE_CHUNKED}[a.variant]
 
+    # a dedicated (non-default) stream: the C ABI takes a cudaStream_t and treats NULL as "the
+    # context's own stream", so every launch and every timing event below is on this one stream
+    bench_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(bench_stream)
+
     # inputs resident in HBM before the timed region
     img = synth.synth_image_rows(a.width, H, synth.SEED_BASE + 3, r0, r1)
     d_img = torch.from_numpy(img).to(dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    stream = bench_stream.cuda_stream
+    assert stream != 0
     be.setImageDevice(d_img.data_ptr(), a.width, r1 - r0, stream=stream)
     pal = synth.synth_palettes(B, K)
     d_pal = torch.from_numpy(pal).to(dev)
@@ -191,7 +197,7 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
     peak = be.measureFp32Peak()  # FFMA microbenchmark at this device's current clocks
 
     def step():
-        be.evalPalettesDevice(d_pal.data_ptr(), B, K, d_res.data_ptr(), a.space, flags, torch.cuda.current_stream().cuda_stream)
+        be.evalPalettesDevice(d_pal.data_ptr(), B, K, d_res.data_ptr(), a.space, flags, stream)
         if world > 1:
             dist.all_reduce(d_res, op=dist.ReduceOp.SUM)
 

@@ -71,6 +71,7 @@ SIGNATURES = {
     "hq_swasa_max_step_width": (C.c_float, [C.POINTER(SwasaParams), C.c_int]),
     "hq_set_profiling": (C.c_int, [_P, C.c_int]),
     "hq_last_assign_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "hq_last_rgb_to_lab_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "hq_measure_fp32_peak": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "hq_host_math_range": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, _P, C.c_int]),
     "hq_device_math_range": (C.c_int, [_P, C.c_int, C.c_uint32, C.c_uint32, _P]),

@@ -78,8 +78,8 @@ struct hq_ctx {
     hq_allreduce_fn allreduce = nullptr;
     void* allreduce_user = nullptr;
     bool profiling = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool ev_valid = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    bool ev_valid = false, ev_rl_valid = false;
     std::atomic<bool> stop{false};
     volatile bool stop_flag_view = false;
 };
@@ -121,7 +121,9 @@ int convert_image(hq_ctx* c, int width, int rows, int whitepoint, cudaStream_t s
     c->width = width; c->rows = rows; c->whitepoint = whitepoint;
     c->have_unit = false;
     HQ_CUDA(c, c->d_lab.reserve(3 * c->stride > 0 ? 3 * c->stride : 1));
+    if (c->profiling) HQ_CUDA(c, cudaEventRecord(c->ev2, st));
     HQ_CUDA(c, hq::launch_rgb_to_lab(c->d_rgb.p, c->n, c->stride, whitepoint, c->d_lab.p, nullptr, c->sm_count, st));
+    if (c->profiling) { HQ_CUDA(c, cudaEventRecord(c->ev3, st)); c->ev_rl_valid = true; }
     c->have_image = true;
     return HQ_OK;
 }
@@ -196,6 +198,8 @@ void hq_destroy(hq_ctx* c) {
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev2) cudaEventDestroy(c->ev2);
+    if (c->ev3) cudaEventDestroy(c->ev3);
     c->d_rgb.release(); c->d_lab.release(); c->d_unit.release(); c->d_pal.release();
     c->d_pal_lab.release(); c->d_pal_rgb.release(); c->d_results.release(); c->d_idx.release();
     c->d_out_rgb.release(); c->d_out_f32.release(); c->h_pal.release(); c->h_results.release();
@@ -413,9 +417,13 @@ float hq_swasa_max_step_width(const hq_swasa_params* p, int iteration) {
 int hq_set_profiling(hq_ctx* c, int enabled) {
     if (!c) return HQ_ERR_INVALID;
     int rc = bind_device(c); if (rc) return rc;
-    if (enabled && !c->ev0) { HQ_CUDA(c, cudaEventCreate(&c->ev0)); HQ_CUDA(c, cudaEventCreate(&c->ev1)); }
+    if (enabled && !c->ev0) {
+        HQ_CUDA(c, cudaEventCreate(&c->ev0)); HQ_CUDA(c, cudaEventCreate(&c->ev1));
+        HQ_CUDA(c, cudaEventCreate(&c->ev2)); HQ_CUDA(c, cudaEventCreate(&c->ev3));
+    }
     c->profiling = enabled != 0;
     c->ev_valid = false;
+    c->ev_rl_valid = false;
     return HQ_OK;
 }
 
@@ -425,6 +433,15 @@ int hq_last_assign_ms(hq_ctx* c, float* ms) {
     int rc = bind_device(c); if (rc) return rc;
     HQ_CUDA(c, cudaEventSynchronize(c->ev1));
     HQ_CUDA(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return HQ_OK;
+}
+
+int hq_last_rgb_to_lab_ms(hq_ctx* c, float* ms) {
+    if (!c || !ms) return HQ_ERR_INVALID;
+    if (!c->ev_rl_valid) return fail(c, HQ_ERR_INVALID, "no profiled image conversion yet (hq_set_profiling)");
+    int rc = bind_device(c); if (rc) return rc;
+    HQ_CUDA(c, cudaEventSynchronize(c->ev3));
+    HQ_CUDA(c, cudaEventElapsedTime(ms, c->ev2, c->ev3));
     return HQ_OK;
 }
 

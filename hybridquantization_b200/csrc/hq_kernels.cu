@@ -403,9 +403,13 @@ cudaError_t launch_assign_t(const AssignParams& p, int B, int sm_count, cudaStre
     if (occ < 1) occ = 1;
     const long long slots = (long long)sm_count * occ;
     const long long ntiles = (long long)((p.n + kTilePx - 1) / kTilePx);
-    // CTAs per candidate: fill the resident slots with whole waves, never more CTAs than tiles
-    long long G = slots / B;
-    if (G < 1) G = 1;
+    // CTAs per candidate (G): B*G must be a whole number of waves of the `slots` resident CTAs,
+    // otherwise the last wave leaves SMs idle (first measurement: 256 CTAs on 296 slots ->
+    // 20 SMs half empty).  G = slots / gcd(B, slots) is the smallest such count; it is then
+    // doubled while every CTA still gets >= 32 tiles, which shortens the ragged tail.
+    auto gcd = [](long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a; };
+    long long G = slots / gcd((long long)B, slots);
+    while (G * 2 * 32 <= ntiles && G * 2 * B <= slots * 16) G *= 2;
     if (G > ntiles) G = ntiles;
     if (G < 1) G = 1;
     if (G > 65535) G = 65535;

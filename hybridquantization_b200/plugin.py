@@ -141,6 +141,11 @@ class ImageManipulation:
         _lib.check(self._ctx, self._lib.hq_last_assign_ms(self._ctx, C.byref(ms)))
         return ms.value
 
+    def lastRgbToLabMs(self) -> float:
+        ms = C.c_float()
+        _lib.check(self._ctx, self._lib.hq_last_rgb_to_lab_ms(self._ctx, C.byref(ms)))
+        return ms.value
+
     def measureFp32Peak(self) -> dict:
         a, b = C.c_double(), C.c_double()
         _lib.check(self._ctx, self._lib.hq_measure_fp32_peak(self._ctx, C.byref(a), C.byref(b)))

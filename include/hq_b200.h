@@ -161,6 +161,7 @@ float hq_swasa_max_step_width(const hq_swasa_params* p, int iteration);
  * (scalar FFMA and packed FFMA2), the denominator of the large-K roofline. */
 int hq_set_profiling(hq_ctx* ctx, int enabled);
 int hq_last_assign_ms(hq_ctx* ctx, float* ms);
+int hq_last_rgb_to_lab_ms(hq_ctx* ctx, float* ms);
 int hq_measure_fp32_peak(hq_ctx* ctx, double* tflops_ffma, double* tflops_ffma2);
 
 /* ---- test hooks: the single-source arithmetic of csrc/hq_math.h evaluated on the host

@@ -1,0 +1,61 @@
+"""torchrun worker for tests/test_gpu_multi.py: every rank holds a row shard, the integer result
+words are all-reduced over NCCL through the C ABI's hook, and the totals plus a full sharded
+SWASA run must equal the single-GPU result computed on rank 0 over the whole image."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+from hybridquantization_b200 import SWASA, ImageManipulation, synth  # noqa: E402
+from hybridquantization_b200.dist import install_nccl_allreduce, row_shard  # noqa: E402
+
+
+def main():
+    out_path = sys.argv[1]
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w, h, K, B = 1031, 517, 64, 5
+    img = synth.synth_image(w, h, 31337, smooth=True)
+    pal = synth.synth_palettes(B, K)
+    r0, r1 = row_shard(h, world, rank)
+    be = ImageManipulation("CIE76", False, True, local)
+    be.setImage(img[r0:r1])
+    install_nccl_allreduce(be)
+    got = be.evalPalettes(pal, sums=True)                     # totals over all ranks
+    sw = SWASA(population=4, imax=60, seed=2024)
+    best, err, tr, its = be.findBestQuantization(K, sw, n_total=w * h, trace=True)
+    res = {"rank": rank, "ok": True}
+    # every rank must hold identical totals / trajectory
+    blob = torch.from_numpy(np.concatenate([got["err_fx"], got["counts"].astype(np.int64).ravel(), got["sums_fx"].ravel(),
+                                            tr.view(np.int64).ravel(), best.view(np.int32).astype(np.int64).ravel()])).cuda()
+    ref = blob.clone()
+    dist.broadcast(ref, 0)
+    res["same_on_all_ranks"] = bool(torch.equal(blob, ref))
+    if rank == 0:
+        single = ImageManipulation("CIE76", False, True, local)
+        single.setImage(img)
+        want = single.evalPalettes(pal, sums=True)
+        sbest, serr, str_, _ = single.findBestQuantization(K, SWASA(population=4, imax=60, seed=2024), trace=True)
+        single.close()
+        res["totals_equal_single_gpu"] = all(np.array_equal(got[k], want[k]) for k in ("err_fx", "counts", "sums_fx"))
+        res["trajectory_equal_single_gpu"] = bool(np.array_equal(tr.view(np.uint64), str_.view(np.uint64)) and err == serr and
+                                                  np.array_equal(best.view(np.uint32), sbest.view(np.uint32)))
+        res["iterations"] = its
+    be.close()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, res)
+    if rank == 0:
+        json.dump(gathered, open(out_path, "w"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

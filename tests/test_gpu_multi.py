@@ -1,0 +1,36 @@
+"""Row-sharded multi-GPU path on real devices (needs >= 2 GPUs: `gpurun --gpus 2`): the NCCL
+all-reduce of the integer partials makes totals and the SWASA trajectory identical to 1 GPU."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_equals_single_gpu(world, tmp_path, hqlib):
+    import torch
+
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs, have {torch.cuda.device_count()}")
+    out = tmp_path / "res.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(REPO, "tests", "multi_gpu_worker.py"), str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    res = json.load(open(out))
+    assert len(res) == world and all(x["same_on_all_ranks"] for x in res)
+    assert res[0]["totals_equal_single_gpu"] and res[0]["trajectory_equal_single_gpu"] and res[0]["iterations"] == 60
