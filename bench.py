@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--colors", type=int, default=256)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--space", type=int, default=0)
-    ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 direct, 2 chunked (profiling)")
+    ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 direct, 2 chunked, 3 prefilter (profiling)")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -154,7 +154,7 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
     import torch
     import torch.distributed as dist
 
-    from hybridquantization_b200 import EVAL_FORCE_CHUNKED, EVAL_FORCE_DIRECT, ImageManipulation, build, synth
+    from hybridquantization_b200 import EVAL_FORCE_CHUNKED, EVAL_FORCE_DIRECT, EVAL_FORCE_PREFILTER, ImageManipulation, build, synth
     from hybridquantization_b200.dist import install_nccl_allreduce, row_shard
 
     if not torch.cuda.is_available():
@@ -174,7 +174,7 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
     r0, r1 = row_shard(H, world, rank)
     n_shard, n_total = a.width * (r1 - r0), a.width * H
     K, B = a.colors, a.batch
-    flags = {0: 0, 1: EVAL_FORCE_DIRECT, 2: EVAL_FORCE_CHUNKED}[a.variant]
+    flags = {0: 0, 1: EVAL_FORCE_DIRECT, 2: EVAL_FORCE_CHUNKED, 3: EVAL_FORCE_PREFILTER}[a.variant]
 
     # a dedicated (non-default) stream: the C ABI takes a cudaStream_t and treats NULL as "the
     # context's own stream", so every launch and every timing event below is on this one stream

@@ -15,7 +15,7 @@ HQ_OK = 0
 ERR_NAMES = {1: "HQ_ERR_INVALID", 2: "HQ_ERR_CUDA", 3: "HQ_ERR_NO_IMAGE", 4: "HQ_ERR_UNSUPPORTED", 5: "HQ_ERR_CALLBACK"}
 WHITEPOINT_D65, WHITEPOINT_D50 = 0, 1
 SPACE_LAB, SPACE_SRGB = 0, 1
-EVAL_SUMS, EVAL_FORCE_DIRECT, EVAL_FORCE_CHUNKED = 1, 2, 4
+EVAL_SUMS, EVAL_FORCE_DIRECT, EVAL_FORCE_CHUNKED, EVAL_FORCE_PREFILTER = 1, 2, 4, 8
 MAX_COLORS = 1024
 
 

@@ -152,7 +152,7 @@ int eval_device(hq_ctx* c, const float* d_palettes, int B, int K, int space, int
     a.pal_lab = c->d_pal_lab.p; a.pal_rgb = c->d_pal_rgb.p;
     a.B = B; a.K = K; a.space = space; a.want_sums = sums;
     a.results = d_results; a.idx_out = d_idx; a.sm_count = c->sm_count;
-    a.variant = (flags & HQ_EVAL_FORCE_DIRECT) ? 1 : ((flags & HQ_EVAL_FORCE_CHUNKED) ? 2 : 0);
+    a.variant = (flags & HQ_EVAL_FORCE_DIRECT) ? 1 : ((flags & HQ_EVAL_FORCE_CHUNKED) ? 2 : ((flags & HQ_EVAL_FORCE_PREFILTER) ? 3 : 0));
     if (c->profiling) HQ_CUDA(c, cudaEventRecord(c->ev0, st));
     HQ_CUDA(c, hq::launch_assign_reduce(a, st));
     if (c->profiling) { HQ_CUDA(c, cudaEventRecord(c->ev1, st)); c->ev_valid = true; }

@@ -168,53 +168,102 @@ struct AssignParams {
     const float4* pal_feat;  // [B][K8]
     const float4* pal_lab;   // [B][K8]
     int K, K8, words;
+    float xmax0, xmax1, xmax2;  // bounds of |feature| over the image (prefilter error bound)
     unsigned long long* results;
     void* idx_out;
 };
 
-template <bool SRGB, bool SUMS>
-__host__ __device__ constexpr size_t assign_smem_bytes(int K8, int variant) {
-    size_t s = (size_t)K8 / 2 * 16;                       // colour pairs (f0,f0',f1,f1')
-    if (SRGB) s += (size_t)K8 * 16;                       // Lab of the palette for scoring
-    if (SUMS) s += (size_t)K8 * 3 * 8;                    // per-colour Lab sums
-    s += (size_t)K8 / 2 * 8;                              // colour pairs (f2,f2')
-    if (variant == 2) s += (size_t)3 * (K8 / kChunk) * (kChunk + 1) * 4;  // skewed SoA copy
-    s += (size_t)K8 * 4;                                  // per-colour counts
-    return s;
+constexpr int kWorklistCap = 1024;  // ambiguous pixels deferred per CTA (variant 3)
+
+// shared-memory carve-up, identical on host (size) and device (pointers)
+template <int VARIANT, bool SRGB, bool SUMS>
+struct AssignSmem {
+    size_t off_pairs01, off_lab, off_sum, off_pairs2, off_coef, off_skew, off_cnt, off_wl, total;
+    int skew_len;
+    __host__ __device__ explicit AssignSmem(int K8) {
+        skew_len = (K8 / kChunk) * (kChunk + 1);
+        size_t o = 0;
+        off_pairs01 = o; if (VARIANT != 3) o += (size_t)K8 / 2 * 16;       // (f0,f0',f1,f1') per colour pair
+        off_coef = o;    if (VARIANT == 3) o += (size_t)K8 * 16;           // (-2p0,-2p1,-2p2,|p|^2) per colour
+        off_lab = o;     if (SRGB) o += (size_t)K8 * 16;                   // Lab of the palette for scoring
+        off_sum = o;     if (SUMS) o += (size_t)K8 * 3 * 8;                // per-colour Lab sums
+        off_pairs2 = o;  if (VARIANT != 3) o += (size_t)K8 / 2 * 8;        // (f2,f2') per colour pair
+        off_skew = o;    if (VARIANT != 1) o += (size_t)3 * skew_len * 4;  // skewed SoA copy of the features
+        off_cnt = o;     o += (size_t)K8 * 4;                              // per-colour counts
+        off_wl = o;      if (VARIANT == 3) o += (size_t)kWorklistCap * 4;
+        total = o;
+    }
+};
+
+// exact squared distances of one pixel to the 8 colours of chunk c: lowest index of the minimum
+__device__ __forceinline__ void exact_chunk(const float* __restrict__ s_sk, int skew_len, int c, float x0, float x1,
+                                            float x2, float& bd, int& bi) {
+    const int s0 = c * (kChunk + 1);
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i) {
+        const float d = hq_dist2(x0, x1, x2, s_sk[s0 + i], s_sk[skew_len + s0 + i], s_sk[2 * skew_len + s0 + i]);
+        if (d < bd) { bd = d; bi = c * kChunk + i; }  // strict '<', ascending index: first wins
+    }
 }
 
-// VARIANT 1: running (min, index) per colour — best for small palettes.
-// VARIANT 2: running min per chunk of 8 colours with FMNMX3 (one ALU op per colour pair),
-//            the winning chunk is re-evaluated once per pixel to recover the index;
-//            the first colour whose distance EQUALS the minimum wins, i.e. the reference's
-//            strict '<' / lowest-index rule (OptimizedConvolution.cl:186).
+// VARIANT 1: running (min, index) per colour, direct (x-p)^2 form — small palettes.
+// VARIANT 2: direct form, running min per chunk of 8 colours with FMNMX3; the winning chunk is
+//            re-evaluated once per pixel to recover the index (first colour whose distance equals
+//            the minimum = the reference's strict '<' / lowest-index rule, OptimizedConvolution.cl:186).
+// VARIANT 3: PREFILTER.  s_k = x.(-2 p_k) + |p_k|^2 = d^2 - |x|^2 costs 3 FMA per (pixel, colour)
+//            instead of 6 FMA-pipe operations, but its fp32 cancellation error is too large to
+//            decide with.  It is only used to find the chunk that can contain the winner:
+//              |s_k - (D_k - |x|^2)| <= E      (E from the magnitudes actually present, see below)
+//              exact winner k* satisfies  s(k*) <= s_min + T,  T = 2E + 2.1*gamma*D_min
+//            (gamma = 6*2^-24 bounds the relative error of the exact fp32 distance).  If the
+//            second-best CHUNK minimum exceeds s_min + T the winner lies in the best chunk, which
+//            is then evaluated EXACTLY (direct form, first-wins).  Otherwise the pixel is ambiguous
+//            (≈0.1 % at K=256) and goes through the exact sweep over all colours — deferred to a
+//            per-CTA worklist so that warps do not diverge.  Results are bit-identical to variants 1/2.
 template <int VARIANT, bool SRGB, bool SUMS, int IDXW>
-__global__ void __launch_bounds__(kThreads, 2) assign_reduce_kernel(const AssignParams p) {
+__global__ void __launch_bounds__(kThreads, VARIANT == 3 ? 3 : 2) assign_reduce_kernel(const AssignParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = p.K, K8 = p.K8;
     const int tid = threadIdx.x;
     const int b = blockIdx.x;  // candidate index varies fastest: co-resident CTAs share pixels in L2
-    const int skew_len = (K8 / kChunk) * (kChunk + 1);
-
-    unsigned char* sp = smem_raw;
-    float4* s_pla = reinterpret_cast<float4*>(sp); sp += (size_t)K8 / 2 * 16;
-    float4* s_lab = reinterpret_cast<float4*>(sp); if (SRGB) sp += (size_t)K8 * 16;
-    unsigned long long* s_sum = reinterpret_cast<unsigned long long*>(sp); if (SUMS) sp += (size_t)K8 * 3 * 8;
-    float2* s_pb = reinterpret_cast<float2*>(sp); sp += (size_t)K8 / 2 * 8;
-    float* s_sk = reinterpret_cast<float*>(sp); if (VARIANT == 2) sp += (size_t)3 * skew_len * 4;
-    unsigned int* s_cnt = reinterpret_cast<unsigned int*>(sp);
-
+    const AssignSmem<VARIANT, SRGB, SUMS> L(K8);
+    const int skew_len = L.skew_len;
+    float4* s_pla = reinterpret_cast<float4*>(smem_raw + L.off_pairs01);
+    float4* s_coef = reinterpret_cast<float4*>(smem_raw + L.off_coef);
+    float4* s_lab = reinterpret_cast<float4*>(smem_raw + L.off_lab);
+    unsigned long long* s_sum = reinterpret_cast<unsigned long long*>(smem_raw + L.off_sum);
+    float2* s_pb = reinterpret_cast<float2*>(smem_raw + L.off_pairs2);
+    float* s_sk = reinterpret_cast<float*>(smem_raw + L.off_skew);
+    unsigned int* s_cnt = reinterpret_cast<unsigned int*>(smem_raw + L.off_cnt);
+    unsigned int* s_wl = reinterpret_cast<unsigned int*>(smem_raw + L.off_wl);
+    __shared__ unsigned int s_wl_n;
+    __shared__ unsigned int s_bound[4];  // max |p0|, |p1|, |p2|, |p|^2 over the real colours (float bits)
+    if (tid < 4) s_bound[tid] = 0u;
+    if (tid == 0) s_wl_n = 0u;
+    __syncthreads();
     {
         const float4* gf = p.pal_feat + (size_t)b * K8;
         const float4* gl = p.pal_lab + (size_t)b * K8;
         float* pla_f = reinterpret_cast<float*>(s_pla);
         float* pb_f = reinterpret_cast<float*>(s_pb);
+        float m0 = 0.f, m1 = 0.f, m2 = 0.f, me = 0.f;
         for (int k = tid; k < K8; k += kThreads) {
             const float4 f = gf[k];
-            pla_f[(k >> 1) * 4 + (k & 1)] = f.x;
-            pla_f[(k >> 1) * 4 + 2 + (k & 1)] = f.y;
-            pb_f[k] = f.z;
-            if (VARIANT == 2) {
+            if (VARIANT != 3) {
+                pla_f[(k >> 1) * 4 + (k & 1)] = f.x;
+                pla_f[(k >> 1) * 4 + 2 + (k & 1)] = f.y;
+                pb_f[k] = f.z;
+            } else {
+                if (k < K) {
+                    // |p|^2 rounded once from fp64; -2p is exact
+                    const float e = (float)__fma_rn((double)f.z, (double)f.z, __fma_rn((double)f.y, (double)f.y, __dmul_rn((double)f.x, (double)f.x)));
+                    s_coef[k] = make_float4(-2.f * f.x, -2.f * f.y, -2.f * f.z, e);
+                    m0 = fmaxf(m0, fabsf(f.x)); m1 = fmaxf(m1, fabsf(f.y)); m2 = fmaxf(m2, fabsf(f.z)); me = fmaxf(me, e);
+                } else {
+                    s_coef[k] = make_float4(0.f, 0.f, 0.f, 1e30f);  // padding never wins
+                }
+            }
+            if (VARIANT != 1) {
                 const int s = (k / kChunk) * (kChunk + 1) + (k % kChunk);
                 s_sk[s] = f.x; s_sk[skew_len + s] = f.y; s_sk[2 * skew_len + s] = f.z;
             }
@@ -222,15 +271,54 @@ __global__ void __launch_bounds__(kThreads, 2) assign_reduce_kernel(const Assign
             s_cnt[k] = 0u;
             if (SUMS) { s_sum[3 * k] = 0ull; s_sum[3 * k + 1] = 0ull; s_sum[3 * k + 2] = 0ull; }
         }
+        if (VARIANT == 3) {  // non-negative floats order like their bit patterns
+            atomicMax(&s_bound[0], __float_as_uint(m0)); atomicMax(&s_bound[1], __float_as_uint(m1));
+            atomicMax(&s_bound[2], __float_as_uint(m2)); atomicMax(&s_bound[3], __float_as_uint(me));
+        }
     }
     __syncthreads();
+    // prefilter error bound: |p|^2 carries one rounding, each of the 3 fma's one more, all of
+    // magnitude <= R = max|p|^2 + 2*sum_i max|x_i|*max|p_i|;  E = 4u*R, inflated by 25 %.
+    float E = 0.f;
+    if (VARIANT == 3) {
+        const float R = __uint_as_float(s_bound[3]) + 2.f * (p.xmax0 * __uint_as_float(s_bound[0]) + p.xmax1 * __uint_as_float(s_bound[1]) +
+                                                             p.xmax2 * __uint_as_float(s_bound[2]));
+        E = 5.0f * 5.9604645e-8f * R + 1e-30f;
+    }
 
     const float* f0 = p.feat; const float* f1 = p.feat + p.stride; const float* f2 = p.feat + 2 * p.stride;
     const float* l0 = p.lab;  const float* l1 = p.lab + p.stride;  const float* l2 = p.lab + 2 * p.stride;
     const size_t n = p.n;
     const size_t ntiles = (n + kTilePx - 1) / kTilePx;
     const float INF = __int_as_float(0x7f800000);
+    const int nchunks = K8 / kChunk;
     long long err_acc = 0;
+    unsigned long long* out = p.results + (size_t)b * p.words;
+
+    // error / counts / sums / index of ONE resolved pixel (q = its Lab, d2v = exact squared distance in
+    // the assignment space)
+    auto resolve = [&](size_t px, int k, float d2v, float q0, float q1, float q2, bool write_idx) {
+        if (SRGB) {  // assign in sRGB, score in CIELAB (OptimizedConvolution.cl:209)
+            const float4 pl = s_lab[k];
+            d2v = hq_dist2(q0, q1, q2, pl.x, pl.y, pl.z);
+        }
+        err_acc += hq_to_fx(HQ_FSQRT(d2v));
+        atomicAdd(&s_cnt[k], 1u);
+        if (SUMS) {
+            atomicAdd(&s_sum[3 * k], (unsigned long long)hq_to_fx(q0));
+            atomicAdd(&s_sum[3 * k + 1], (unsigned long long)hq_to_fx(q1));
+            atomicAdd(&s_sum[3 * k + 2], (unsigned long long)hq_to_fx(q2));
+        }
+        if (write_idx) {
+            if (IDXW == 1) reinterpret_cast<uint8_t*>(p.idx_out)[(size_t)b * p.stride + px] = (uint8_t)k;
+            if (IDXW == 2) reinterpret_cast<uint16_t*>(p.idx_out)[(size_t)b * p.stride + px] = (uint16_t)k;
+        }
+    };
+    // exact sweep over every colour (ambiguous pixels of variant 3)
+    auto exact_all = [&](float x0, float x1, float x2, float& bd, int& bi) {
+        bd = INF; bi = 0;
+        for (int c = 0; c < nchunks; ++c) exact_chunk(s_sk, skew_len, c, x0, x1, x2, bd, bi);
+    };
 
     for (size_t tile = blockIdx.y; tile < ntiles; tile += gridDim.y) {
         const size_t base = tile * kTilePx + (size_t)kPxPerThread * tid;
@@ -253,13 +341,14 @@ __global__ void __launch_bounds__(kThreads, 2) assign_reduce_kernel(const Assign
             }
         }
 
-        float best[4] = {INF, INF, INF, INF};
+        float best[4] = {INF, INF, INF, INF};  // exact squared distance of the winner
         int idx[4] = {0, 0, 0, 0};
-        uint64_t X[4], Y[4], Z[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { X[j] = pack2(x0[j], x0[j]); Y[j] = pack2(x1[j], x1[j]); Z[j] = pack2(x2[j], x2[j]); }
+        bool deferred[4] = {false, false, false, false};
 
         if (VARIANT == 1) {
+            uint64_t X[4], Y[4], Z[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { X[j] = pack2(x0[j], x0[j]); Y[j] = pack2(x1[j], x1[j]); Z[j] = pack2(x2[j], x2[j]); }
 #pragma unroll 4
             for (int q = 0; q < K8 / 2; ++q) {
                 const float4 la = s_pla[q];
@@ -273,9 +362,11 @@ __global__ void __launch_bounds__(kThreads, 2) assign_reduce_kernel(const Assign
                     if (dhi < best[j]) { best[j] = dhi; idx[j] = 2 * q + 1; }
                 }
             }
-        } else {
+        } else if (VARIANT == 2) {
+            uint64_t X[4], Y[4], Z[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { X[j] = pack2(x0[j], x0[j]); Y[j] = pack2(x1[j], x1[j]); Z[j] = pack2(x2[j], x2[j]); }
             int cidx[4] = {0, 0, 0, 0};
-            const int nchunks = K8 / kChunk;
             for (int c = 0; c < nchunks; ++c) {
                 float m[4] = {INF, INF, INF, INF};
 #pragma unroll
@@ -294,7 +385,6 @@ __global__ void __launch_bounds__(kThreads, 2) assign_reduce_kernel(const Assign
                 for (int j = 0; j < 4; ++j)
                     if (m[j] < best[j]) { best[j] = m[j]; cidx[j] = c; }
             }
-            // recover the index: lowest colour of the winning chunk whose distance equals the min
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int s0 = cidx[j] * (kChunk + 1);
@@ -305,6 +395,53 @@ __global__ void __launch_bounds__(kThreads, 2) assign_reduce_kernel(const Assign
                     if (d == best[j]) found = i;
                 }
                 idx[j] = cidx[j] * kChunk + found;
+            }
+        } else {
+            // ---- prefilter sweep: two pixel PAIRS per thread, palette coefficients broadcast
+            const uint64_t X0 = pack2(x0[0], x0[1]), X1 = pack2(x0[2], x0[3]);
+            const uint64_t Y0 = pack2(x1[0], x1[1]), Y1 = pack2(x1[2], x1[3]);
+            const uint64_t Z0 = pack2(x2[0], x2[1]), Z1 = pack2(x2[2], x2[3]);
+            float sbest[4] = {INF, INF, INF, INF}, second[4] = {INF, INF, INF, INF};
+            int cidx[4] = {0, 0, 0, 0};
+            for (int c = 0; c < nchunks; ++c) {
+                float m[4] = {INF, INF, INF, INF};
+#pragma unroll
+                for (int q = 0; q < kChunk; q += 2) {
+                    const float4 u = s_coef[c * kChunk + q], v = s_coef[c * kChunk + q + 1];
+                    const uint64_t ua = pack2(u.x, u.x), ub = pack2(u.y, u.y), uc = pack2(u.z, u.z), ue = pack2(u.w, u.w);
+                    const uint64_t va = pack2(v.x, v.x), vb = pack2(v.y, v.y), vc = pack2(v.z, v.z), ve = pack2(v.w, v.w);
+                    float a0, a1, b0, b1;
+                    unpack2(fma2(X0, ua, fma2(Y0, ub, fma2(Z0, uc, ue))), a0, a1);
+                    unpack2(fma2(X0, va, fma2(Y0, vb, fma2(Z0, vc, ve))), b0, b1);
+                    m[0] = min3(m[0], a0, b0); m[1] = min3(m[1], a1, b1);
+                    unpack2(fma2(X1, ua, fma2(Y1, ub, fma2(Z1, uc, ue))), a0, a1);
+                    unpack2(fma2(X1, va, fma2(Y1, vb, fma2(Z1, vc, ve))), b0, b1);
+                    m[2] = min3(m[2], a0, b0); m[3] = min3(m[3], a1, b1);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    second[j] = fminf(second[j], fmaxf(m[j], sbest[j]));  // 2nd smallest chunk minimum
+                    if (m[j] < sbest[j]) { sbest[j] = m[j]; cidx[j] = c; }
+                }
+            }
+            // ---- decide: unique chunk -> exact evaluation of that chunk; else defer / exact sweep
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < nvalid) {
+                    const float nx = fmaf(x2[j], x2[j], fmaf(x1[j], x1[j], x0[j] * x0[j]));
+                    const float T = 2.01f * E + 1.0e-6f * (fabsf(sbest[j] + nx) + E);
+                    if (second[j] > sbest[j] + T) {
+                        exact_chunk(s_sk, skew_len, cidx[j], x0[j], x1[j], x2[j], best[j], idx[j]);
+                    } else {
+                        const unsigned slot = atomicAdd(&s_wl_n, 1u);
+                        if (slot < (unsigned)kWorklistCap && base + j < 0xffffffffull) {
+                            s_wl[slot] = (unsigned)(base + j);
+                            deferred[j] = true;
+                        } else {
+                            exact_all(x0[j], x1[j], x2[j], best[j], idx[j]);  // worklist full: resolve here
+                        }
+                    }
+                }
             }
         }
 
@@ -330,22 +467,8 @@ __global__ void __launch_bounds__(kThreads, 2) assign_reduce_kernel(const Assign
             for (int j = 0; j < 4; ++j) { q0[j] = x0[j]; q1[j] = x1[j]; q2[j] = x2[j]; }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (j < nvalid) {
-                float d2v = best[j];
-                if (SRGB) {  // assign in sRGB, score in CIELAB (OptimizedConvolution.cl:209)
-                    const float4 pl = s_lab[idx[j]];
-                    d2v = hq_dist2(q0[j], q1[j], q2[j], pl.x, pl.y, pl.z);
-                }
-                err_acc += hq_to_fx(HQ_FSQRT(d2v));
-                atomicAdd(&s_cnt[idx[j]], 1u);
-                if (SUMS) {
-                    atomicAdd(&s_sum[3 * idx[j]], (unsigned long long)hq_to_fx(q0[j]));
-                    atomicAdd(&s_sum[3 * idx[j] + 1], (unsigned long long)hq_to_fx(q1[j]));
-                    atomicAdd(&s_sum[3 * idx[j] + 2], (unsigned long long)hq_to_fx(q2[j]));
-                }
-            }
-        }
+        for (int j = 0; j < 4; ++j)
+            if (j < nvalid && !deferred[j]) resolve(base + j, idx[j], best[j], q0[j], q1[j], q2[j], false);
         if (IDXW == 1) {
             uint8_t* o = reinterpret_cast<uint8_t*>(p.idx_out) + (size_t)b * p.stride + base;
             if (nvalid == 4) {
@@ -365,13 +488,25 @@ __global__ void __launch_bounds__(kThreads, 2) assign_reduce_kernel(const Assign
         }
     }
 
+    if (VARIANT == 3) {
+        // ---- deferred (ambiguous) pixels: exact sweep over all colours, one pixel per thread.
+        // The barrier also orders the packed index stores above before the per-pixel fix-ups.
+        __syncthreads();
+        const unsigned nwl = min(s_wl_n, (unsigned)kWorklistCap);
+        for (unsigned i = tid; i < nwl; i += kThreads) {
+            const size_t px = s_wl[i];
+            float bd; int bi;
+            exact_all(f0[px], f1[px], f2[px], bd, bi);
+            resolve(px, bi, bd, l0[px], l1[px], l2[px], true);
+        }
+    }
+
     // ---- CTA reduction: warp shuffles -> shared -> one global atomic per (CTA, quantity)
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) err_acc += __shfl_down_sync(0xffffffffu, err_acc, off);
     __shared__ long long s_err[kThreads / 32];
     if ((tid & 31) == 0) s_err[tid >> 5] = err_acc;
     __syncthreads();  // also orders every shared atomic before the flush below
-    unsigned long long* out = p.results + (size_t)b * p.words;
     if (tid == 0) {
         long long e = 0;
 #pragma unroll
@@ -394,7 +529,7 @@ __global__ void __launch_bounds__(kThreads, 2) assign_reduce_kernel(const Assign
 template <int VARIANT, bool SRGB, bool SUMS, int IDXW>
 cudaError_t launch_assign_t(const AssignParams& p, int B, int sm_count, cudaStream_t stream) {
     auto kern = assign_reduce_kernel<VARIANT, SRGB, SUMS, IDXW>;
-    const size_t smem = assign_smem_bytes<SRGB, SUMS>(p.K8, VARIANT);
+    const size_t smem = AssignSmem<VARIANT, SRGB, SUMS>(p.K8).total;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;
@@ -527,10 +662,15 @@ cudaError_t launch_assign_reduce(const AssignArgs& a, cudaStream_t stream) {
     p.results = a.results;
     p.idx_out = a.idx_out;
     const int idxw = a.idx_out ? (a.K <= 256 ? 1 : 2) : 0;
+    // |feature| bounds of the image for the prefilter's error bound: CIELAB of in-gamut sRGB has
+    // L in [0,100], |a|,|b| < 128 (extremes 98.3 / 107.9); unit sRGB is in [0,1]
+    if (a.space == 1) { p.xmax0 = p.xmax1 = p.xmax2 = 1.0f; }
+    else { p.xmax0 = 100.5f; p.xmax1 = 128.0f; p.xmax2 = 128.0f; }
     int variant = a.variant;
-    if (variant == 0) variant = (a.K <= 16) ? 1 : 2;
+    if (variant == 0) variant = (a.K <= 16) ? 1 : 3;
     if (variant == 1) return launch_assign_v<1>(p, a.B, a.space == 1, a.want_sums, idxw, a.sm_count, stream);
-    return launch_assign_v<2>(p, a.B, a.space == 1, a.want_sums, idxw, a.sm_count, stream);
+    if (variant == 2) return launch_assign_v<2>(p, a.B, a.space == 1, a.want_sums, idxw, a.sm_count, stream);
+    return launch_assign_v<3>(p, a.B, a.space == 1, a.want_sums, idxw, a.sm_count, stream);
 }
 
 cudaError_t launch_apply_palette(const void* d_idx, bool idx16, size_t n, const float* d_palette, int K,

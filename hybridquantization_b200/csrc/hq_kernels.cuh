@@ -40,7 +40,7 @@ struct AssignArgs {
     unsigned long long* results;  // [B][result_words], must be zeroed by the caller
     void* idx_out;         // [B][stride] u8 (K <= 256) or u16, or null
     int sm_count;
-    int variant;           // 0 auto, 1 direct index tracking, 2 chunked min + recompute
+    int variant;           // 0 auto, 1 direct index tracking, 2 chunked min + recompute, 3 prefilter + exact
 };
 cudaError_t launch_assign_reduce(const AssignArgs& a, cudaStream_t stream);
 

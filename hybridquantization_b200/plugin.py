@@ -16,7 +16,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _lib
-from ._lib import (EVAL_FORCE_CHUNKED, EVAL_FORCE_DIRECT, EVAL_SUMS, SPACE_LAB, SPACE_SRGB, WHITEPOINT_D50,
+from ._lib import (EVAL_FORCE_CHUNKED, EVAL_FORCE_DIRECT, EVAL_FORCE_PREFILTER, EVAL_SUMS, SPACE_LAB, SPACE_SRGB, WHITEPOINT_D50,
                    WHITEPOINT_D65, HqError, JavaRandomState, SwasaParams)
 
 __all__ = ["JavaRandom", "SWASA", "ImageManipulation", "ScielabProcessor", "HybridQuantization", "HqError",

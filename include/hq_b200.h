@@ -46,7 +46,8 @@ enum { HQ_SPACE_LAB = 0, HQ_SPACE_SRGB = 1 };
 enum {
     HQ_EVAL_SUMS = 1,            /* also reduce per-colour Lab sums */
     HQ_EVAL_FORCE_DIRECT = 2,    /* kernel variant selection, for tests / profiling */
-    HQ_EVAL_FORCE_CHUNKED = 4
+    HQ_EVAL_FORCE_CHUNKED = 4,
+    HQ_EVAL_FORCE_PREFILTER = 8  /* expanded-form prefilter + exact re-check (default for K > 16) */
 };
 
 #define HQ_MAX_COLORS 1024

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from helpers import bits, fbits, from_bits, idx_crc, load_golden
-from hybridquantization_b200 import (EVAL_FORCE_CHUNKED, EVAL_FORCE_DIRECT, SPACE_LAB, SPACE_SRGB, WHITEPOINT_D50,
+from hybridquantization_b200 import (EVAL_FORCE_CHUNKED, EVAL_FORCE_DIRECT, EVAL_FORCE_PREFILTER, SPACE_LAB, SPACE_SRGB, WHITEPOINT_D50,
                                      WHITEPOINT_D65, synth)
 
 pytestmark = pytest.mark.gpu
@@ -78,7 +78,7 @@ def test_assign_reduce_palette_sizes(backend, oracle, K, space):
     _check(backend, oracle, img, synth.synth_palettes(3, K), space)
 
 
-@pytest.mark.parametrize("flags", [EVAL_FORCE_DIRECT, EVAL_FORCE_CHUNKED])
+@pytest.mark.parametrize("flags", [EVAL_FORCE_DIRECT, EVAL_FORCE_CHUNKED, EVAL_FORCE_PREFILTER])
 @pytest.mark.parametrize("K", [1, 5, 16, 40, 256])
 def test_both_kernel_variants(backend, oracle, flags, K):
     img = synth.synth_image(300, 71, synth.SEED_BASE + 2, smooth=True)
@@ -105,7 +105,7 @@ def test_d50_white_point(backend, oracle):
 
 def test_tie_rule_lowest_index_wins(backend, oracle):
     img = synth.synth_image(128, 64, 7)
-    for K, flags in ((6, EVAL_FORCE_DIRECT), (6, EVAL_FORCE_CHUNKED), (40, EVAL_FORCE_CHUNKED)):
+    for K, flags in ((6, EVAL_FORCE_DIRECT), (6, EVAL_FORCE_CHUNKED), (40, EVAL_FORCE_CHUNKED), (6, EVAL_FORCE_PREFILTER), (40, EVAL_FORCE_PREFILTER)):
         pal = synth.synth_palettes(1, K)
         pal[0, K - 2] = pal[0, 1]   # duplicates later in the palette must never be chosen
         pal[0, K - 1] = pal[0, 0]
@@ -118,6 +118,33 @@ def test_tie_rule_lowest_index_wins(backend, oracle):
         assert np.array_equal(got["counts"], want["counts"])
         q = backend.quantize(pal[0])
         assert np.array_equal(q["idx"], oracle.quantize(img, pal[0])["idx"])
+
+
+def test_prefilter_worklist_overflow_and_near_ties(backend, oracle):
+    # every pixel identical AND the winning colour duplicated in another chunk: every pixel is
+    # ambiguous for the prefilter, the per-CTA worklist (1024) overflows and the in-place exact
+    # sweep must give the same integers
+    img = np.full((257, 131, 3), 201, np.uint8)
+    unit, _ = oracle.image_planes(img[:1, :1])
+    pal = synth.synth_palettes(2, 40)
+    pal[:, 3, :3] = unit[:, 0]
+    pal[:, 29, :3] = unit[:, 0]           # exact duplicate of the winner, chunk 3
+    pal[0, 17, :3] = unit[:, 0] + np.float32(1e-6)   # near tie, chunk 2
+    _check(backend, oracle, img, pal, SPACE_LAB, EVAL_FORCE_PREFILTER)
+    _check(backend, oracle, img, pal, SPACE_SRGB, EVAL_FORCE_PREFILTER)
+    # clustered palettes: colours a few ulps apart scattered over different chunks
+    rng = np.random.default_rng(3)
+    img = synth.synth_image(400, 300, 123, smooth=True)
+    pal = synth.synth_palettes(3, 64)
+    for b in range(3):
+        base = pal[b, :8].copy()
+        for k in range(8, 64):
+            pal[b, k, :3] = base[k % 8, :3] + (rng.integers(-3, 4, 3) * np.float32(6e-8)).astype(np.float32)
+    pal = np.clip(pal, 0, 1).astype(np.float32)
+    _check(backend, oracle, img, pal, SPACE_LAB, EVAL_FORCE_PREFILTER)
+    backend.setImage(img)
+    for b in range(3):
+        assert np.array_equal(backend.quantize(pal[b])["idx"], oracle.quantize(img, pal[b])["idx"])
 
 
 def test_flat_image_worst_case_contention(backend, oracle):

@@ -22,7 +22,7 @@ sys.path.insert(0, REPO)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from hybridquantization_b200 import EVAL_FORCE_CHUNKED, EVAL_FORCE_DIRECT, SWASA, ImageManipulation, synth  # noqa: E402
+from hybridquantization_b200 import EVAL_FORCE_CHUNKED, EVAL_FORCE_DIRECT, EVAL_FORCE_PREFILTER, SWASA, ImageManipulation, synth  # noqa: E402
 
 
 def main():
@@ -96,7 +96,7 @@ def main():
             words = be.resultWords(K, 0)
             d_res = torch.zeros((B, words), dtype=torch.int64, device=dev)
             row = {"K": K, "B": B}
-            for name, fl in (("auto", 0), ("direct", EVAL_FORCE_DIRECT), ("chunked", EVAL_FORCE_CHUNKED)):
+            for name, fl in (("auto", 0), ("direct", EVAL_FORCE_DIRECT), ("chunked", EVAL_FORCE_CHUNKED), ("prefilter", EVAL_FORCE_PREFILTER)):
                 if name != "auto" and (a.quick or B == 64 and K > 256):
                     continue
                 ms, best = timed(lambda: be.evalPalettesDevice(d_pal.data_ptr(), B, K, d_res.data_ptr(), 0, fl, st.cuda_stream), reps=3 if B == 64 else 7)
