@@ -63,7 +63,7 @@ struct hq_ctx {
     int width = 0, rows = 0, whitepoint = 0;
     bool have_image = false, have_unit = false;
     DevBuf<uint8_t> d_rgb;
-    DevBuf<float> d_lab, d_unit;
+    DevBuf<float> d_lab, d_unit, d_table;
 
     // evaluation scratch
     DevBuf<float> d_pal;
@@ -112,7 +112,7 @@ int bind_device(hq_ctx* c) {
 int ensure_unit(hq_ctx* c, cudaStream_t st) {
     if (c->have_unit) return HQ_OK;
     HQ_CUDA(c, c->d_unit.reserve(3 * c->stride));
-    HQ_CUDA(c, hq::launch_rgb_to_lab(c->d_rgb.p, c->n, c->stride, c->whitepoint, c->d_lab.p, c->d_unit.p, c->sm_count, st));
+    HQ_CUDA(c, hq::launch_rgb_to_lab(c->d_rgb.p, c->n, c->stride, c->whitepoint, c->d_table.p, c->d_lab.p, c->d_unit.p, c->sm_count, st));
     c->have_unit = true;
     return HQ_OK;
 }
@@ -122,7 +122,7 @@ int convert_image(hq_ctx* c, int width, int rows, int whitepoint, cudaStream_t s
     c->have_unit = false;
     HQ_CUDA(c, c->d_lab.reserve(3 * c->stride > 0 ? 3 * c->stride : 1));
     if (c->profiling) HQ_CUDA(c, cudaEventRecord(c->ev2, st));
-    HQ_CUDA(c, hq::launch_rgb_to_lab(c->d_rgb.p, c->n, c->stride, whitepoint, c->d_lab.p, nullptr, c->sm_count, st));
+    HQ_CUDA(c, hq::launch_rgb_to_lab(c->d_rgb.p, c->n, c->stride, whitepoint, c->d_table.p, c->d_lab.p, nullptr, c->sm_count, st));
     if (c->profiling) { HQ_CUDA(c, cudaEventRecord(c->ev3, st)); c->ev_rl_valid = true; }
     c->have_image = true;
     return HQ_OK;
@@ -185,6 +185,12 @@ int hq_create(int device, hq_ctx** out) {
         delete c;
         return fail(nullptr, HQ_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     }
+    if ((e = c->d_table.reserve(512)) != cudaSuccess || (e = hq::launch_decode_table(c->d_table.p, c->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) {
+        cudaStreamDestroy(c->stream);
+        delete c;
+        return fail(nullptr, HQ_ERR_CUDA, "device %d: decode table kernel failed: %s (is the library built for this GPU?)", device, cudaGetErrorString(e));
+    }
     c->sm_count = prop.multiProcessorCount;
     cudaDeviceGetAttribute(&c->clock_khz, cudaDevAttrClockRate, device);
     snprintf(c->name, sizeof c->name, "%s", prop.name);
@@ -200,7 +206,7 @@ void hq_destroy(hq_ctx* c) {
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
     if (c->ev3) cudaEventDestroy(c->ev3);
-    c->d_rgb.release(); c->d_lab.release(); c->d_unit.release(); c->d_pal.release();
+    c->d_rgb.release(); c->d_lab.release(); c->d_unit.release(); c->d_table.release(); c->d_pal.release();
     c->d_pal_lab.release(); c->d_pal_rgb.release(); c->d_results.release(); c->d_idx.release();
     c->d_out_rgb.release(); c->d_out_f32.release(); c->h_pal.release(); c->h_results.release();
     delete c;
@@ -475,7 +481,7 @@ int hq_measure_fp32_peak(hq_ctx* c, double* tflops_ffma, double* tflops_ffma2) {
 }
 
 int hq_host_math_range(int which, uint32_t first_bits, uint32_t count, float* out, int threads) {
-    if (!out || which < 0 || which > 2) return HQ_ERR_INVALID;
+    if (!out || which < 0 || which > 7) return HQ_ERR_INVALID;
     if (threads < 1) threads = 1;
     std::vector<std::thread> pool;
     for (int t = 0; t < threads; ++t)
@@ -483,7 +489,7 @@ int hq_host_math_range(int which, uint32_t first_bits, uint32_t count, float* ou
             const uint64_t lo = (uint64_t)count * t / threads, hi = (uint64_t)count * (t + 1) / threads;
             for (uint64_t i = lo; i < hi; ++i) {
                 const float v = HQ_U2F(first_bits + (uint32_t)i);
-                out[i] = which == 0 ? hq_cbrtf(v) : (which == 1 ? hq_pow_2p4f(v) : hq_srgb_decode(v));
+                out[i] = hq_math_probe(which, v);
             }
         });
     for (auto& th : pool) th.join();
@@ -491,7 +497,7 @@ int hq_host_math_range(int which, uint32_t first_bits, uint32_t count, float* ou
 }
 
 int hq_device_math_range(hq_ctx* c, int which, uint32_t first_bits, uint32_t count, float* out) {
-    if (!c || !out || which < 0 || which > 2) return HQ_ERR_INVALID;
+    if (!c || !out || which < 0 || which > 7) return HQ_ERR_INVALID;
     int rc = bind_device(c); if (rc) return rc;
     DevBuf<float> d;
     HQ_CUDA(c, d.reserve(count ? count : 1));
@@ -504,7 +510,7 @@ int hq_device_math_range(hq_ctx* c, int which, uint32_t first_bits, uint32_t cou
 }
 
 void hq_host_srgb_to_lab(const float rgb[3], int whitepoint, float lab[3]) {
-    const hq_float3 v = hq_srgb_to_lab(rgb[0], rgb[1], rgb[2], hq_whitepoint(whitepoint));
+    const hq_float3 v = hq_srgb_to_lab(rgb[0], rgb[1], rgb[2], hq_make_white(whitepoint));
     lab[0] = v.x; lab[1] = v.y; lab[2] = v.z;
 }
 

@@ -67,35 +67,42 @@ __device__ __forceinline__ uint64_t dist2_pair(uint64_t X, uint64_t Y, uint64_t 
 }
 
 // ====================================================================== RGB -> Lab
-constexpr int kRlPxPerThread = 16;
-constexpr int kRlTilePx = kThreads * kRlPxPerThread;  // 4096 px = 12288 B of packed RGB
+constexpr int kRlTilePx = kThreads * 4;  // 1024 px = 3072 B of packed RGB per CTA iteration
+
+// 256-entry u8 -> unit / linear-light tables ([0..255] unit, [256..511] linear), built once per context
+__global__ void decode_table_kernel(float* __restrict__ table) {
+    const int v = threadIdx.x;
+    const float u = hq_u8_to_unit((uint32_t)v);
+    table[v] = u;
+    table[256 + v] = hq_srgb_decode(u);
+}
 
 __global__ void __launch_bounds__(kThreads)
 rgb_to_lab_kernel(const uint8_t* __restrict__ rgb, size_t n, size_t stride, int whitepoint,
-                  float* __restrict__ lab, float* __restrict__ unit) {
-    __shared__ __align__(16) uint32_t s_stage[kRlTilePx * 3 / 4];  // 3072 words
+                  const float* __restrict__ table, float* __restrict__ lab, float* __restrict__ unit) {
+    __shared__ __align__(16) uint32_t s_stage[kRlTilePx * 3 / 4];  // 768 words
     __shared__ float s_lin[256];
     __shared__ float s_unit[256];
     const int tid = threadIdx.x;
-    {   // 256-entry decode table: the u8 -> linear-light map has only 256 values
-        const float u = hq_u8_to_unit((uint32_t)tid);
-        s_unit[tid] = u;
-        s_lin[tid] = hq_srgb_decode(u);
-    }
-    const hq_float3 white = hq_whitepoint(whitepoint);
+    s_unit[tid] = table[tid];
+    s_lin[tid] = table[256 + tid];
+    const hq_white white = hq_make_white(whitepoint);
     const size_t ntiles = (n + kRlTilePx - 1) / kRlTilePx;
     const bool aligned = (reinterpret_cast<uintptr_t>(rgb) & 15) == 0;
+    // software pipeline: the next tile's 16 bytes are in flight while this tile is converted
+    const bool loader = tid < kRlTilePx * 3 / 16;
+    uint4 pre = make_uint4(0, 0, 0, 0);
+    auto full_tile = [&](size_t t) { return aligned && (t + 1) * (size_t)kRlTilePx <= n; };
+    if (blockIdx.x < ntiles && full_tile(blockIdx.x) && loader)
+        pre = __ldg(reinterpret_cast<const uint4*>(rgb + (size_t)blockIdx.x * kRlTilePx * 3) + tid);
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const size_t px0 = tile * kRlTilePx;
         const size_t byte0 = px0 * 3;
         const size_t tile_px = (n - px0 < (size_t)kRlTilePx) ? (n - px0) : (size_t)kRlTilePx;
         __syncthreads();  // previous tile fully consumed (and the tables written)
-        if (tile_px == (size_t)kRlTilePx && aligned) {
-            // 3 fully coalesced 128-bit loads per thread
-            const uint4* src = reinterpret_cast<const uint4*>(rgb + byte0);
-            uint4* dst = reinterpret_cast<uint4*>(s_stage);
-#pragma unroll
-            for (int r = 0; r < 3; ++r) dst[tid + r * kThreads] = __ldg(src + tid + r * kThreads);
+        if (full_tile(tile)) {
+            // fully coalesced 128-bit loads: 192 x 16 B = one tile (byte0 is a multiple of 3072)
+            if (loader) reinterpret_cast<uint4*>(s_stage)[tid] = pre;
         } else {
             uint8_t* dst = reinterpret_cast<uint8_t*>(s_stage);
             const size_t nbytes = tile_px * 3;
@@ -103,41 +110,43 @@ rgb_to_lab_kernel(const uint8_t* __restrict__ rgb, size_t n, size_t stride, int 
                 dst[i] = (i < nbytes) ? rgb[byte0 + i] : (uint8_t)0;
         }
         __syncthreads();
+        {
+            const size_t nt = tile + gridDim.x;
+            if (nt < ntiles && full_tile(nt) && loader)
+                pre = __ldg(reinterpret_cast<const uint4*>(rgb + nt * (size_t)kRlTilePx * 3) + tid);
+        }
+        // 4 pixels = 3 words per thread, bank-conflict free (word stride 3 is coprime with 32)
+        const uint32_t w0 = s_stage[3 * tid], w1 = s_stage[3 * tid + 1], w2 = s_stage[3 * tid + 2];
+        const uint32_t c[12] = {w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u, w0 >> 24,
+                                w1 & 255u, (w1 >> 8) & 255u, (w1 >> 16) & 255u, w1 >> 24,
+                                w2 & 255u, (w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24};
+        float L[4], A[4], Bv[4];
 #pragma unroll
-        for (int r = 0; r < kRlPxPerThread / 4; ++r) {
-            const int grp = r * kThreads + tid;  // group of 4 pixels = 3 words, bank-conflict free
-            const uint32_t w0 = s_stage[3 * grp], w1 = s_stage[3 * grp + 1], w2 = s_stage[3 * grp + 2];
-            const uint32_t c[12] = {w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u, w0 >> 24,
-                                    w1 & 255u, (w1 >> 8) & 255u, (w1 >> 16) & 255u, w1 >> 24,
-                                    w2 & 255u, (w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24};
-            float L[4], A[4], Bv[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const hq_float3 v = hq_linrgb_to_lab(s_lin[c[3 * j]], s_lin[c[3 * j + 1]], s_lin[c[3 * j + 2]], white);
-                L[j] = v.x; A[j] = v.y; Bv[j] = v.z;
+        for (int j = 0; j < 4; ++j) {
+            const hq_float3 v = hq_linrgb_to_lab(s_lin[c[3 * j]], s_lin[c[3 * j + 1]], s_lin[c[3 * j + 2]], white);
+            L[j] = v.x; A[j] = v.y; Bv[j] = v.z;
+        }
+        const size_t p = px0 + 4 * (size_t)tid;
+        if (p + 4 <= n) {  // 128-bit coalesced plane stores
+            *reinterpret_cast<float4*>(lab + p) = make_float4(L[0], L[1], L[2], L[3]);
+            *reinterpret_cast<float4*>(lab + stride + p) = make_float4(A[0], A[1], A[2], A[3]);
+            *reinterpret_cast<float4*>(lab + 2 * stride + p) = make_float4(Bv[0], Bv[1], Bv[2], Bv[3]);
+            if (unit) {
+                *reinterpret_cast<float4*>(unit + p) = make_float4(s_unit[c[0]], s_unit[c[3]], s_unit[c[6]], s_unit[c[9]]);
+                *reinterpret_cast<float4*>(unit + stride + p) = make_float4(s_unit[c[1]], s_unit[c[4]], s_unit[c[7]], s_unit[c[10]]);
+                *reinterpret_cast<float4*>(unit + 2 * stride + p) = make_float4(s_unit[c[2]], s_unit[c[5]], s_unit[c[8]], s_unit[c[11]]);
             }
-            const size_t p = px0 + 4 * (size_t)grp;
-            if (p + 4 <= n) {
-                *reinterpret_cast<float4*>(lab + p) = make_float4(L[0], L[1], L[2], L[3]);
-                *reinterpret_cast<float4*>(lab + stride + p) = make_float4(A[0], A[1], A[2], A[3]);
-                *reinterpret_cast<float4*>(lab + 2 * stride + p) = make_float4(Bv[0], Bv[1], Bv[2], Bv[3]);
-                if (unit) {
-                    *reinterpret_cast<float4*>(unit + p) = make_float4(s_unit[c[0]], s_unit[c[3]], s_unit[c[6]], s_unit[c[9]]);
-                    *reinterpret_cast<float4*>(unit + stride + p) = make_float4(s_unit[c[1]], s_unit[c[4]], s_unit[c[7]], s_unit[c[10]]);
-                    *reinterpret_cast<float4*>(unit + 2 * stride + p) = make_float4(s_unit[c[2]], s_unit[c[5]], s_unit[c[8]], s_unit[c[11]]);
-                }
-            } else {
+        } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (p + j < n) {
-                        lab[p + j] = L[j]; lab[stride + p + j] = A[j]; lab[2 * stride + p + j] = Bv[j];
-                        if (unit) {
-                            unit[p + j] = s_unit[c[3 * j]];
-                            unit[stride + p + j] = s_unit[c[3 * j + 1]];
-                            unit[2 * stride + p + j] = s_unit[c[3 * j + 2]];
-                        }
+            for (int j = 0; j < 4; ++j)
+                if (p + j < n) {
+                    lab[p + j] = L[j]; lab[stride + p + j] = A[j]; lab[2 * stride + p + j] = Bv[j];
+                    if (unit) {
+                        unit[p + j] = s_unit[c[3 * j]];
+                        unit[stride + p + j] = s_unit[c[3 * j + 1]];
+                        unit[2 * stride + p + j] = s_unit[c[3 * j + 2]];
                     }
-            }
+                }
         }
     }
 }
@@ -152,7 +161,7 @@ __global__ void palette_features_kernel(const float* __restrict__ pal, int B, in
     float4 lab = make_float4(kFar, kFar, kFar, 0.f), rgbv = lab;
     if (k < K) {
         const float4 c = reinterpret_cast<const float4*>(pal)[(size_t)b * K + k];
-        const hq_float3 v = hq_srgb_to_lab(c.x, c.y, c.z, hq_whitepoint(whitepoint));
+        const hq_float3 v = hq_srgb_to_lab(c.x, c.y, c.z, hq_make_white(whitepoint));
         lab = make_float4(v.x, v.y, v.z, 0.f);
         rgbv = make_float4(c.x, c.y, c.z, 0.f);
     }
@@ -588,11 +597,7 @@ __global__ void math_probe_kernel(int which, uint32_t first_bits, uint32_t count
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const float v = __uint_as_float(first_bits + i);
-    float r;
-    if (which == 0) r = hq_cbrtf(v);
-    else if (which == 1) r = hq_pow_2p4f(v);
-    else r = hq_srgb_decode(v);
-    out[i] = r;
+    out[i] = hq_math_probe(which, v);
 }
 
 // FP32 ceiling probe: 8 independent FMA chains per thread, 8 warps per CTA, 4 CTAs per SM
@@ -628,13 +633,18 @@ cudaError_t launch_fp32_peak(bool packed, int iters, int sm_count, float* d_out,
 }
 
 // ====================================================================== launchers
-cudaError_t launch_rgb_to_lab(const uint8_t* d_rgb, size_t n, size_t stride, int whitepoint, float* d_lab,
-                              float* d_unit, int sm_count, cudaStream_t stream) {
+cudaError_t launch_decode_table(float* d_table, cudaStream_t stream) {
+    decode_table_kernel<<<1, 256, 0, stream>>>(d_table);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rgb_to_lab(const uint8_t* d_rgb, size_t n, size_t stride, int whitepoint, const float* d_table,
+                              float* d_lab, float* d_unit, int sm_count, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     const size_t ntiles = (n + kRlTilePx - 1) / kRlTilePx;
-    size_t grid = (size_t)sm_count * 8;
+    size_t grid = (size_t)sm_count * 8;  // 8 resident CTAs per SM, grid-stride over 1024-px tiles
     if (grid > ntiles) grid = ntiles;
-    rgb_to_lab_kernel<<<(unsigned)grid, kThreads, 0, stream>>>(d_rgb, n, stride, whitepoint, d_lab, d_unit);
+    rgb_to_lab_kernel<<<(unsigned)grid, kThreads, 0, stream>>>(d_rgb, n, stride, whitepoint, d_table, d_lab, d_unit);
     return cudaGetLastError();
 }
 

@@ -20,7 +20,9 @@ inline int result_words(int K, bool want_sums) { return 1 + K + (want_sums ? 3 *
 inline size_t plane_stride(size_t n) { return (n + 31) / 32 * 32; }
 
 // packed u8 RGB -> fp32 planes.  lab = [3][stride] (L, a, b); unit = [3][stride] (r, g, b)/255 or null.
-cudaError_t launch_rgb_to_lab(const uint8_t* d_rgb, size_t n, size_t stride, int whitepoint,
+// d_table: 512 floats built once by launch_decode_table (u8 -> unit, u8 -> linear light)
+cudaError_t launch_decode_table(float* d_table, cudaStream_t stream);
+cudaError_t launch_rgb_to_lab(const uint8_t* d_rgb, size_t n, size_t stride, int whitepoint, const float* d_table,
                               float* d_lab, float* d_unit, int sm_count, cudaStream_t stream);
 
 // palettes [B][K][4] sRGB floats -> padded feature tables [B][K8] float4:

@@ -82,6 +82,7 @@ static inline double hq_u2d_host(uint64_t u) { double d; memcpy(&d, &u, 8); retu
 #define HQ_LABDELTA3 0x1.22354ep-7f        /* 0.008856452070 */
 #define HQ_3LABDELTA2 0x1.070050p-3f       /* 3*LABDELTA2 = 0.128418565 */
 #define HQ_4_OVER_29 0x1.1a7b96p-3f        /* 4f/29f = 0.137931034 */
+#define HQ_RCP_3LABDELTA2 0x1.f25eccp+2f    /* RN(1 / (3*LABDELTA2)) = 7.787036 */
 
 enum { HQ_WHITE_D65 = 0, HQ_WHITE_D50 = 1 };
 
@@ -97,34 +98,71 @@ HQ_HD hq_float3 hq_whitepoint(int wp) {
     return w;
 }
 
+// exact float -> double of a positive NORMAL float with integer operations (on sm_100a the
+// F2F conversion runs on the 16-lane XU pipe, which was the busiest unit of rgb_to_lab_kernel)
+HQ_HD double hq_widen_pos(float f) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t b = __float_as_uint(f);
+    return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+#else
+    return (double)f;
+#endif
+}
+
 // ---------------------------------------------------------------- (float)pow(t, 1.0/3.0)
 // Restates `(float)Math.pow(t, 1.0 / 3.0)` (ScielabProcessor.java:301,303,305) for
 // positive normal t.  Inverse-cube-root Newton in fp32 from a bit seed, then two
 // Newton steps on y^3 = t in fp64 whose residual is formed with one fma; the fp64
 // value is within 1 ulp(double) of the true root before the final narrowing.
 HQ_HD float hq_cbrtf(float t) {
+#if defined(__CUDA_ARCH__)
+    // device seed: x ~ t^(-1/3) = 2^(-log2(t)/3) from the SFU approximations (rel. error < 1e-6).
+    // The SFU results are not reproducible on the host, but the value returned below does not
+    // depend on the seed unless the true root sits within ~1e-17 of a rounding boundary; that
+    // this never happens is verified EXHAUSTIVELY on the B200 against the oracle for every float
+    // of the domain (tests/test_gpu_parity.py::test_device_math_exhaustive).
+    float lg, x;
+    asm("lg2.approx.f32 %0, %1;" : "=f"(lg) : "f"(t));
+    asm("ex2.approx.f32 %0, %1;" : "=f"(x) : "f"(HQ_FMUL(lg, -0x1.555556p-2f)));
+#else
     const uint32_t bits = HQ_F2U(t);
     float x = HQ_U2F(0x54a2fa8cu - bits / 3u);  // x ~ t^(-1/3), |rel err| < 3.3 %
     const float t3 = HQ_FMUL(t, -0x1.555556p-2f);  // -t/3
     const float c43 = 0x1.555556p+0f;              // 4/3
-#pragma unroll
     for (int i = 0; i < 3; ++i) {  // x <- x * (4/3 - t/3 * x^3): e -> -2 e^2
         const float x2 = HQ_FMUL(x, x);
         const float x3 = HQ_FMUL(x2, x);
         const float w = HQ_FFMA(t3, x3, c43);
         x = HQ_FMUL(x, w);
     }
-    const double xd = (double)x, td = (double)t;
+#endif
+    const double xd = hq_widen_pos(x), td = hq_widen_pos(t);
     const double x2 = HQ_DMUL(xd, xd);
     double y = HQ_DMUL(td, x2);                         // t * t^(-2/3)
     const double h = HQ_DMUL(x2, 0x1.5555555555555p-2);  // ~ 1 / (3 y^2)
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 2; ++i) {  // Newton on y^3 = t, residual with one fma: e -> 16 eps^2 -> ~1e-18
         const double s = HQ_DMUL(y, y);
         const double r = HQ_DFMA(s, y, -td);
         y = HQ_DFMA(-r, h, y);
     }
     return (float)y;
+}
+
+// ---------------------------------------------------------------- x / c for a constant c
+// Correctly rounded quotient without the division unit (Markstein): q0 = RN(x*rc), the
+// remainder x - q0*c is exact in one fma, q = RN(q0 + rem*rc).  rc = RN(1/c).  Verified
+// exhaustively equal to x / c for every float with 2^-60 <= |x| <= 4 and the five constants the
+// path divides by (both white points' X and Z, and 3*LABDELTA2) — tests/test_math_exhaustive.py;
+// outside that range (zero, subnormal remainders, large values) the true division is used.
+HQ_HD float hq_div_const(float x, float c, float rc) {
+    const uint32_t ax = HQ_F2U(x) & 0x7fffffffu;
+    if (ax - 0x21800000u <= 0x40800000u - 0x21800000u) {
+        const float q0 = HQ_FMUL(x, rc);
+        const float rem = HQ_FFMA(-q0, c, x);
+        return HQ_FFMA(rem, rc, q0);
+    }
+    return HQ_FDIV(x, c);
 }
 
 // ---------------------------------------------------------------- (float)pow(b, 2.4f)
@@ -218,24 +256,34 @@ HQ_HD hq_float3 hq_linrgb_to_opp(float R, float G, float B) {
 
 // ScielabProcessor.java:301 (one channel of XYZ -> Lab)
 HQ_HD float hq_lab_f(float t) {
-    const float lin = HQ_FADD(HQ_FDIV(t, HQ_3LABDELTA2), HQ_4_OVER_29);
-    // the cube-root routine needs a positive normal argument; its value is only
-    // selected when t > LABDELTA3
-    const float root = hq_cbrtf(t > HQ_LABDELTA3 ? t : 1.0f);
-    return (t > HQ_LABDELTA3) ? root : lin;
+    if (t > HQ_LABDELTA3) return hq_cbrtf(t);
+    return HQ_FADD(hq_div_const(t, HQ_3LABDELTA2, HQ_RCP_3LABDELTA2), HQ_4_OVER_29);
 }
 
-// ScielabProcessor.java:295-310 (opponent -> XYZ -> Lab)
-HQ_HD hq_float3 hq_opp_to_lab(hq_float3 o, hq_float3 white) {
+// white point with the reciprocals the constant division needs
+struct hq_white {
+    float x, y, z, rx, rz;
+};
+HQ_HD hq_white hq_make_white(int wp) {
+    const hq_float3 w = hq_whitepoint(wp);
+    hq_white o;
+    o.x = w.x; o.y = w.y; o.z = w.z;
+    o.rx = HQ_FDIV(1.0f, w.x); o.rz = HQ_FDIV(1.0f, w.z);
+    return o;
+}
+
+// ScielabProcessor.java:295-310 (opponent -> XYZ -> Lab).  Y / illuminant[1] with illuminant[1] == 1.0f
+// is Y itself for both white points (:20-21).
+HQ_HD hq_float3 hq_opp_to_lab(hq_float3 o, hq_white white) {
     const float X = hq_dot3(0.97959616044562807864f, o.x, -1.5347157012664408981f, o.y,
                             0.44459764330437399288f, o.z);
     const float Y = hq_dot3(1.188977906742323787f, o.x, 0.7643549575179937615f, o.y,
                             0.13512574791125839373f, o.z);
     const float Z = hq_dot3(1.2318333139247290457f, o.x, 1.1631592597636512884f, o.y,
                             2.0784075888008567862f, o.z);
-    const float fx = hq_lab_f(HQ_FDIV(X, white.x));
-    const float fy = hq_lab_f(HQ_FDIV(Y, white.y));
-    const float fz = hq_lab_f(HQ_FDIV(Z, white.z));
+    const float fx = hq_lab_f(hq_div_const(X, white.x, white.rx));
+    const float fy = hq_lab_f(white.y == 1.0f ? Y : HQ_FDIV(Y, white.y));
+    const float fz = hq_lab_f(hq_div_const(Z, white.z, white.rz));
     hq_float3 lab;
     lab.x = HQ_FSUB(HQ_FMUL(116.0f, fy), 16.0f);
     lab.y = HQ_FMUL(500.0f, HQ_FSUB(fx, fy));
@@ -244,12 +292,12 @@ HQ_HD hq_float3 hq_opp_to_lab(hq_float3 o, hq_float3 white) {
 }
 
 // linear RGB -> Lab (sRGBtoLab = OpptoLab(sRGBtoOpp(.)), ScielabProcessor.java:432)
-HQ_HD hq_float3 hq_linrgb_to_lab(float R, float G, float B, hq_float3 white) {
+HQ_HD hq_float3 hq_linrgb_to_lab(float R, float G, float B, hq_white white) {
     return hq_opp_to_lab(hq_linrgb_to_opp(R, G, B), white);
 }
 
 // sRGB floats in [0,1] (a palette colour) -> Lab
-HQ_HD hq_float3 hq_srgb_to_lab(float r, float g, float b, hq_float3 white) {
+HQ_HD hq_float3 hq_srgb_to_lab(float r, float g, float b, hq_white white) {
     return hq_linrgb_to_lab(hq_srgb_decode(r), hq_srgb_decode(g), hq_srgb_decode(b), white);
 }
 
@@ -261,6 +309,17 @@ HQ_HD hq_float3 hq_srgb_to_lab(float r, float g, float b, hq_float3 white) {
 HQ_HD float hq_dist2(float x0, float x1, float x2, float p0, float p1, float p2) {
     const float d0 = HQ_FSUB(x0, p0), d1 = HQ_FSUB(x1, p1), d2 = HQ_FSUB(x2, p2);
     return HQ_FFMA(d2, d2, HQ_FFMA(d1, d1, HQ_FMUL(d0, d0)));
+}
+
+// test hook: the restated routines by code (0 cube root, 1 pow 2.4f, 2 sRGB decode,
+// 3/4 x / Xn, x / Zn of D65, 5 x / (3*LABDELTA2), 6/7 x / Xn, x / Zn of D50)
+HQ_HD float hq_math_probe(int which, float v) {
+    if (which == 0) return hq_cbrtf(v);
+    if (which == 1) return hq_pow_2p4f(v);
+    if (which == 2) return hq_srgb_decode(v);
+    if (which == 5) return hq_div_const(v, HQ_3LABDELTA2, HQ_RCP_3LABDELTA2);
+    const hq_white w = hq_make_white(which >= 6 ? HQ_WHITE_D50 : HQ_WHITE_D65);
+    return (which == 3 || which == 6) ? hq_div_const(v, w.x, w.rx) : hq_div_const(v, w.z, w.rz);
 }
 
 // float -> 2^-24 fixed point, round to nearest even (exact for |v| >= 1)

@@ -439,10 +439,21 @@ static void mrange_fn(void* p, size_t lo, size_t hi, int tid) {
     for (size_t i = lo; i < hi; ++i) {
         const uint32_t u = c->first + (uint32_t)i;
         float v; memcpy(&v, &u, 4);
-        c->out[i] = c->which == 0 ? hqo_cbrt_pow(v) : (c->which == 1 ? hqo_pow_2p4(v) : hqo_srgb_decode(v));
+        float r;
+        switch (c->which) {
+            case 0: r = hqo_cbrt_pow(v); break;
+            case 1: r = hqo_pow_2p4(v); break;
+            case 2: r = hqo_srgb_decode(v); break;
+            case 3: r = v / WHITE[0][0]; break;   /* X / illuminant[0], D65 (ScielabProcessor.java:300) */
+            case 4: r = v / WHITE[0][2]; break;   /* Z / illuminant[2], D65 (:304) */
+            case 5: r = v / C_3LABDELTA2; break;  /* t / (3*LABDELTA2) (:301) */
+            case 6: r = v / WHITE[1][0]; break;
+            default: r = v / WHITE[1][2]; break;
+        }
+        c->out[i] = r;
     }
 }
-/* which: 0 (float)pow(t,1.0/3.0), 1 (float)pow(b,2.4f), 2 sRGB decode; over `count`
+/* which: 0 (float)pow(t,1.0/3.0), 1 (float)pow(b,2.4f), 2 sRGB decode, 3-7 the divisions by constants; over `count`
  * consecutive float bit patterns starting at first_bits */
 void hqo_math_range(int which, uint32_t first_bits, uint32_t count, float* out, int threads) {
     mrange_ctx c = {which, first_bits, out};

@@ -17,7 +17,8 @@ THREADS = max(1, len(os.sched_getaffinity(0)))
 
 
 # ------------------------------------------------------------------ arithmetic on the device
-@pytest.mark.parametrize("which,lo,hi", [(0, 0.008856452070, 1.25), (1, 0.0625, 1.0), (2, 0.03, 1.0)])
+@pytest.mark.parametrize("which,lo,hi", [(0, 0.008856452070, 1.25), (1, 0.0625, 1.0), (2, 0.03, 1.0), (3, 0.0, 2.0), (4, 0.0, 2.0), (5, 0.0, 0.01),
+                                          (6, 0.0, 2.0), (7, 0.0, 2.0)])
 def test_device_math_exhaustive(backend, hqlib, oracle, which, lo, hi):
     a, b = fbits(lo), fbits(hi)
     chunk = 1 << 24
