@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhq_b200.so")
+# HQ_B200_LIB selects another build of the SAME library (kernel experiments); there is still no fallback
+LIB_PATH = os.environ.get("HQ_B200_LIB") or os.path.join(_HERE, "libhq_b200.so")
 
 HQ_OK = 0
 ERR_NAMES = {1: "HQ_ERR_INVALID", 2: "HQ_ERR_CUDA", 3: "HQ_ERR_NO_IMAGE", 4: "HQ_ERR_UNSUPPORTED", 5: "HQ_ERR_CALLBACK"}

@@ -183,6 +183,9 @@ struct AssignParams {
 };
 
 constexpr int kWorklistCap = 1024;  // ambiguous pixels deferred per CTA (variant 3)
+#ifndef HQ_PREFILTER_SCALAR
+#define HQ_PREFILTER_SCALAR 0  // 1: scalar FFMA sweep instead of packed FFMA2 (experiment)
+#endif
 
 // shared-memory carve-up, identical on host (size) and device (pointers)
 template <int VARIANT, bool SRGB, bool SUMS>
@@ -229,8 +232,16 @@ __device__ __forceinline__ void exact_chunk(const float* __restrict__ s_sk, int 
 //            is then evaluated EXACTLY (direct form, first-wins).  Otherwise the pixel is ambiguous
 //            (≈0.1 % at K=256) and goes through the exact sweep over all colours — deferred to a
 //            per-CTA worklist so that warps do not diverge.  Results are bit-identical to variants 1/2.
+// 2 CTAs/SM (121 registers, no stack frame) measured 68.8 % of FP32 peak vs 65.5 % at 3 CTAs/SM (80 registers)
+#ifndef HQ_V3_MIN_CTAS
+#define HQ_V3_MIN_CTAS 2
+#endif
+#ifndef HQ_V3_UNROLL
+#define HQ_V3_UNROLL 2
+#endif
+constexpr int kV3Unroll = HQ_V3_UNROLL;  // chunks per unrolled iteration of the prefilter sweep
 template <int VARIANT, bool SRGB, bool SUMS, int IDXW>
-__global__ void __launch_bounds__(kThreads, VARIANT == 3 ? 3 : 2) assign_reduce_kernel(const AssignParams p) {
+__global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : 2) assign_reduce_kernel(const AssignParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = p.K, K8 = p.K8;
     const int tid = threadIdx.x;
@@ -412,11 +423,20 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? 3 : 2) assign_reduce_
             const uint64_t Z0 = pack2(x2[0], x2[1]), Z1 = pack2(x2[2], x2[3]);
             float sbest[4] = {INF, INF, INF, INF}, second[4] = {INF, INF, INF, INF};
             int cidx[4] = {0, 0, 0, 0};
+#pragma unroll (kV3Unroll)
             for (int c = 0; c < nchunks; ++c) {
                 float m[4] = {INF, INF, INF, INF};
 #pragma unroll
                 for (int q = 0; q < kChunk; q += 2) {
                     const float4 u = s_coef[c * kChunk + q], v = s_coef[c * kChunk + q + 1];
+#if HQ_PREFILTER_SCALAR
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float su = __fmaf_rn(x0[j], u.x, __fmaf_rn(x1[j], u.y, __fmaf_rn(x2[j], u.z, u.w)));
+                        const float sv = __fmaf_rn(x0[j], v.x, __fmaf_rn(x1[j], v.y, __fmaf_rn(x2[j], v.z, v.w)));
+                        m[j] = min3(m[j], su, sv);
+                    }
+#else
                     const uint64_t ua = pack2(u.x, u.x), ub = pack2(u.y, u.y), uc = pack2(u.z, u.z), ue = pack2(u.w, u.w);
                     const uint64_t va = pack2(v.x, v.x), vb = pack2(v.y, v.y), vc = pack2(v.z, v.z), ve = pack2(v.w, v.w);
                     float a0, a1, b0, b1;
@@ -426,6 +446,7 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? 3 : 2) assign_reduce_
                     unpack2(fma2(X1, ua, fma2(Y1, ub, fma2(Z1, uc, ue))), a0, a1);
                     unpack2(fma2(X1, va, fma2(Y1, vb, fma2(Z1, vc, ve))), b0, b1);
                     m[2] = min3(m[2], a0, b0); m[3] = min3(m[3], a1, b1);
+#endif
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
