@@ -59,6 +59,12 @@ SIGNATURES = {
     "hq_eval_palettes_device": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "hq_cost": (C.c_double, [C.c_int64, _P, C.c_int, C.c_uint64, C.c_float]),
     "hq_quantize": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P]),
+    "hq_scielab_configure": (C.c_int, [_P, C.c_int, C.c_float]),
+    "hq_scielab_set_filters": (C.c_int, [_P, _P, _P, C.c_int]),
+    "hq_scielab_get_filters": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int)]),
+    "hq_scielab_get_image": (C.c_int, [_P, _P]),
+    "hq_scielab_build_filters": (C.c_int, [C.c_int, C.c_float, _P, _P, C.POINTER(C.c_int)]),
+    "hq_eval_palettes_scielab": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "hq_set_allreduce": (C.c_int, [_P, ALLREDUCE_FN, _P]),
     "hq_swasa_default_params": (None, [C.POINTER(SwasaParams)]),
     "hq_find_best_quantization": (C.c_int, [_P, C.c_int, C.POINTER(SwasaParams), C.c_uint64, _P, C.POINTER(C.c_double), _P, C.POINTER(C.c_int)]),

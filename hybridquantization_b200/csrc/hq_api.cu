@@ -75,6 +75,14 @@ struct hq_ctx {
     PinBuf<float> h_pal;
     PinBuf<unsigned long long> h_results;
 
+    // S-CIELAB stage (next row 1)
+    std::vector<float> sc_filters7, sc_abs3;  // [7][taps], [taps] as ScielabProcessor builds them
+    int sc_taps = 0;
+    bool sc_image_ready = false;
+    DevBuf<float> d_sc_filters, d_sc_opp, d_sc_tmp, d_sc_lab;
+    DevBuf<float4> d_sc_tab;
+    DevBuf<unsigned long long> d_sc_err;
+
     hq_allreduce_fn allreduce = nullptr;
     void* allreduce_user = nullptr;
     bool profiling = false;
@@ -120,6 +128,7 @@ int ensure_unit(hq_ctx* c, cudaStream_t st) {
 int convert_image(hq_ctx* c, int width, int rows, int whitepoint, cudaStream_t st) {
     c->width = width; c->rows = rows; c->whitepoint = whitepoint;
     c->have_unit = false;
+    c->sc_image_ready = false;
     HQ_CUDA(c, c->d_lab.reserve(3 * c->stride > 0 ? 3 * c->stride : 1));
     if (c->profiling) HQ_CUDA(c, cudaEventRecord(c->ev2, st));
     HQ_CUDA(c, hq::launch_rgb_to_lab(c->d_rgb.p, c->n, c->stride, whitepoint, c->d_table.p, c->d_lab.p, nullptr, c->sm_count, st));
@@ -209,6 +218,7 @@ void hq_destroy(hq_ctx* c) {
     c->d_rgb.release(); c->d_lab.release(); c->d_unit.release(); c->d_table.release(); c->d_pal.release();
     c->d_pal_lab.release(); c->d_pal_rgb.release(); c->d_results.release(); c->d_idx.release();
     c->d_out_rgb.release(); c->d_out_f32.release(); c->h_pal.release(); c->h_results.release();
+    c->d_sc_filters.release(); c->d_sc_opp.release(); c->d_sc_tmp.release(); c->d_sc_lab.release(); c->d_sc_tab.release(); c->d_sc_err.release();
     delete c;
 }
 
@@ -349,6 +359,134 @@ int hq_quantize(hq_ctx* c, const float* palette, int K, int space, uint8_t* out_
     HQ_CUDA(c, cudaStreamSynchronize(c->stream));
     if (out_idx && n && !idx16)
         for (size_t i = 0; i < n; ++i) out_idx[i] = idx8[i];
+    return HQ_OK;
+}
+
+// ------------------------------------------------------------------ S-CIELAB stage
+static int sc_upload_filters(hq_ctx* c) {
+    const int T = c->sc_taps;
+    std::vector<float> blk((size_t)8 * T);
+    const float* f = c->sc_filters7.data();
+    for (int t = 0; t < T; ++t) {  // updateOpenCLFilters, ImageManipulation.java:800-841
+        blk[3 * t] = f[0 * T + t]; blk[3 * t + 1] = f[3 * T + t]; blk[3 * t + 2] = f[5 * T + t];                    // k1 = first Gaussian of O1,O2,O3
+        blk[3 * T + 3 * t] = f[1 * T + t]; blk[3 * T + 3 * t + 1] = f[4 * T + t]; blk[3 * T + 3 * t + 2] = f[6 * T + t];  // k2 = second
+        blk[6 * T + t] = f[2 * T + t];                                                                               // k3 = third Gaussian of O1
+        blk[7 * T + t] = c->sc_abs3[t];
+    }
+    HQ_CUDA(c, c->d_sc_filters.reserve(blk.size()));
+    HQ_CUDA(c, cudaMemcpyAsync(c->d_sc_filters.p, blk.data(), blk.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    HQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->sc_image_ready = false;
+    return HQ_OK;
+}
+
+int hq_scielab_set_filters(hq_ctx* c, const float* filters7, const float* abs3, int taps) {
+    if (!c || !filters7 || !abs3) return c ? fail(c, HQ_ERR_INVALID, "NULL filter arrays") : HQ_ERR_INVALID;
+    if (taps < 1 || taps > hq::kMaxScielabTaps || (taps & 1) == 0) return fail(c, HQ_ERR_UNSUPPORTED, "taps must be odd and in [1,%d] (got %d)", hq::kMaxScielabTaps, taps);
+    int rc = bind_device(c); if (rc) return rc;
+    c->sc_filters7.assign(filters7, filters7 + (size_t)7 * taps);
+    c->sc_abs3.assign(abs3, abs3 + taps);
+    c->sc_taps = taps;
+    return sc_upload_filters(c);
+}
+
+int hq_scielab_configure(hq_ctx* c, int dpi, float viewing_distance_cm) {
+    if (!c) return HQ_ERR_INVALID;
+    if (dpi < 1 || !(viewing_distance_cm >= 1.0f)) return fail(c, HQ_ERR_INVALID, "dpi >= 1 and viewing distance >= 1 cm required (HybridQuantization.java:229-231)");
+    const hq::ScielabProcessor::FilterBank bank = hq::ScielabProcessor::buildFilters(dpi, (double)viewing_distance_cm);
+    const std::vector<float> flat = bank.flat();
+    return hq_scielab_set_filters(c, flat.data(), bank.absOfilters.data(), bank.taps());
+}
+
+int hq_scielab_build_filters(int dpi, float viewing_distance_cm, float* filters7, float* abs3, int* taps) {
+    if (!taps || dpi < 1 || !(viewing_distance_cm >= 1.0f)) return HQ_ERR_INVALID;
+    const hq::ScielabProcessor::FilterBank bank = hq::ScielabProcessor::buildFilters(dpi, (double)viewing_distance_cm);
+    const int T = bank.taps();
+    if (filters7 && abs3 && *taps >= T) {
+        const std::vector<float> flat = bank.flat();
+        std::memcpy(filters7, flat.data(), sizeof(float) * 7 * T);
+        std::memcpy(abs3, bank.absOfilters.data(), sizeof(float) * T);
+    }
+    *taps = T;
+    return HQ_OK;
+}
+
+int hq_scielab_get_filters(const hq_ctx* c, float* filters7, float* abs3, int* taps) {
+    if (!c || !taps) return HQ_ERR_INVALID;
+    if (c->sc_taps == 0) return HQ_ERR_INVALID;
+    if (filters7 && abs3 && *taps >= c->sc_taps) {
+        std::memcpy(filters7, c->sc_filters7.data(), sizeof(float) * 7 * c->sc_taps);
+        std::memcpy(abs3, c->sc_abs3.data(), sizeof(float) * c->sc_taps);
+    }
+    *taps = c->sc_taps;
+    return HQ_OK;
+}
+
+// S-CIELAB representation of the resident image (sRGBToScielab, ScielabProcessor.java:374-381)
+static int sc_ensure_image(hq_ctx* c) {
+    if (c->sc_image_ready) return HQ_OK;
+    if (!c->have_image) return fail(c, HQ_ERR_NO_IMAGE, "no image: call hq_set_image_u8 first");
+    if (c->sc_taps == 0) { int rc = hq_scielab_configure(c, 72, 45.0f); if (rc) return rc; }  // plugin defaults :229-231
+    if (c->width < c->sc_taps / 2 || c->rows < c->sc_taps / 2)
+        return fail(c, HQ_ERR_UNSUPPORTED, "image %dx%d is smaller than the filter half-width %d (the reference's single reflection, "
+                    "OptimizedConvolution.cl:20-27, would read out of bounds)", c->width, c->rows, c->sc_taps / 2);
+    if (c->allreduce) return fail(c, HQ_ERR_UNSUPPORTED, "the S-CIELAB stage needs halo rows across shards: single GPU only in this version");
+    HQ_CUDA(c, c->d_sc_opp.reserve(3 * c->stride));
+    HQ_CUDA(c, c->d_sc_tmp.reserve(7 * c->stride));
+    HQ_CUDA(c, c->d_sc_lab.reserve(3 * c->stride));
+    HQ_CUDA(c, hq::launch_sc_rgb_to_opp(c->d_rgb.p, c->n, c->stride, c->d_table.p, c->d_sc_opp.p, c->stream));
+    HQ_CUDA(c, hq::launch_sc_original(c->d_sc_opp.p, c->width, c->rows, c->stride, c->d_sc_filters.p, c->sc_taps, c->whitepoint,
+                                      c->d_sc_tmp.p, c->d_sc_lab.p, c->stream));
+    c->sc_image_ready = true;
+    return HQ_OK;
+}
+
+int hq_scielab_get_image(hq_ctx* c, float* planes) {
+    if (!c || !planes) return HQ_ERR_INVALID;
+    int rc = bind_device(c); if (rc) return rc;
+    rc = sc_ensure_image(c); if (rc) return rc;
+    for (int pl = 0; pl < 3 && c->n; ++pl)
+        HQ_CUDA(c, cudaMemcpyAsync(planes + (size_t)pl * c->n, c->d_sc_lab.p + (size_t)pl * c->stride, c->n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    HQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HQ_OK;
+}
+
+int hq_eval_palettes_scielab(hq_ctx* c, const float* palettes, int B, int K, int space, int64_t* err_fx, uint64_t* counts) {
+    int rc = check_eval_args(c, B, K, space); if (rc) return rc;
+    if (!palettes) return fail(c, HQ_ERR_INVALID, "palettes is NULL");
+    rc = bind_device(c); if (rc) return rc;
+    rc = sc_ensure_image(c); if (rc) return rc;
+    const size_t npal = (size_t)B * K * 4;
+    const int words = hq::result_words(K, false);
+    const size_t nwords = (size_t)B * words;
+    const bool idx16 = K > 256;
+    HQ_CUDA(c, c->h_pal.reserve(npal));
+    HQ_CUDA(c, c->d_pal.reserve(npal));
+    HQ_CUDA(c, c->h_results.reserve(nwords + B));
+    HQ_CUDA(c, c->d_results.reserve(nwords));
+    HQ_CUDA(c, c->d_sc_err.reserve(B));
+    HQ_CUDA(c, c->d_sc_tab.reserve((size_t)B * K));
+    HQ_CUDA(c, c->d_idx.reserve((size_t)B * (c->stride ? c->stride : 1) * (idx16 ? 2 : 1)));
+    std::memcpy(c->h_pal.p, palettes, npal * sizeof(float));
+    HQ_CUDA(c, cudaMemcpyAsync(c->d_pal.p, c->h_pal.p, npal * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    // 1. assignment (quantizeAndConvertToOpp's argmin, cl:178-193): indices + counts for every candidate
+    rc = eval_device(c, c->d_pal.p, B, K, space, 0, c->d_results.p, c->d_idx.p, c->stream); if (rc) return rc;
+    // 2. the K opponent colours each quantised image is made of (cl:194-198)
+    HQ_CUDA(c, hq::launch_sc_palette_opp(c->d_pal.p, B * K, c->d_sc_tab.p, c->stream));
+    HQ_CUDA(c, cudaMemsetAsync(c->d_sc_err.p, 0, (size_t)B * 8, c->stream));
+    // 3. per candidate: separable filters, Opp2LAB, CIE76 against the original, fixed-point sum
+    for (int b = 0; b < B; ++b) {
+        const uint8_t* idx_b = c->d_idx.p + (size_t)b * c->stride * (idx16 ? 2 : 1);
+        HQ_CUDA(c, hq::launch_sc_candidate(idx_b, idx16, c->d_sc_tab.p + (size_t)b * K, c->width, c->rows, c->stride, c->d_sc_filters.p,
+                                           c->sc_taps, c->whitepoint, c->d_sc_tmp.p, c->d_sc_lab.p, c->d_sc_err.p + b, c->stream));
+    }
+    HQ_CUDA(c, cudaMemcpyAsync(c->h_results.p, c->d_results.p, nwords * 8, cudaMemcpyDeviceToHost, c->stream));
+    HQ_CUDA(c, cudaMemcpyAsync(c->h_results.p + nwords, c->d_sc_err.p, (size_t)B * 8, cudaMemcpyDeviceToHost, c->stream));
+    HQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int b = 0; b < B; ++b) {
+        if (err_fx) err_fx[b] = (int64_t)c->h_results.p[nwords + b];
+        if (counts) std::memcpy(counts + (size_t)b * K, c->h_results.p + (size_t)b * words + 1, sizeof(uint64_t) * K);
+    }
     return HQ_OK;
 }
 

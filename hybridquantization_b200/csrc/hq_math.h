@@ -311,6 +311,59 @@ HQ_HD float hq_dist2(float x0, float x1, float x2, float p0, float p1, float p2)
     return HQ_FFMA(d2, d2, HQ_FFMA(d1, d1, HQ_FMUL(d0, d0)));
 }
 
+// ---------------------------------------------------------------- S-CIELAB stage (next row 1)
+// The spatial-filter stage only exists as OpenCL kernels in the reference; their device-defined
+// builtins are pinned as the oracle pins them: dot() left to right without contraction, fma()
+// exact, pow/cbrt correctly rounded, distance() = sqrt of the fma chain.
+//   RGB2XYZm cl:77, XYZ2Oppm cl:110, Opp2XYZm cl:118, RGB2Oppm cl:171
+HQ_HD float hq_cl_dot3(float m0, float m1, float m2, float x, float y, float z) {
+    return HQ_FADD(HQ_FADD(HQ_FMUL(x, m0), HQ_FMUL(y, m1)), HQ_FMUL(z, m2));
+}
+// linear RGB -> XYZ -> opponent (RGB2XYZ cl:79-90 + XYZ2Opp cl:111-116): the ORIGINAL image's route
+HQ_HD hq_float3 hq_cl_linrgb_to_opp_via_xyz(float R, float G, float B) {
+    const float X = hq_cl_dot3(0.4124564f, 0.3575761f, 0.1804375f, R, G, B);
+    const float Y = hq_cl_dot3(0.2126729f, 0.7151522f, 0.0721750f, R, G, B);
+    const float Z = hq_cl_dot3(0.0193339f, 0.1191920f, 0.9503041f, R, G, B);
+    hq_float3 o;
+    o.x = hq_cl_dot3(0.2787336f, 0.7218031f, -0.1065520f, X, Y, Z);
+    o.y = hq_cl_dot3(-0.4487736f, 0.2898056f, -0.0771569f, X, Y, Z);
+    o.z = hq_cl_dot3(0.0859513f, -0.5899859f, 0.5011089f, X, Y, Z);
+    return o;
+}
+// linear RGB -> opponent directly (quantizeAndConvertToOpp cl:194-198): the QUANTISED image's route
+HQ_HD hq_float3 hq_cl_linrgb_to_opp(float R, float G, float B) {
+    hq_float3 o;
+    o.x = hq_cl_dot3(0.266413f, 0.603167f, 0.00113333f, R, G, B);
+    o.y = hq_cl_dot3(-0.124957f, 0.0375879f, -0.133381f, R, G, B);
+    o.z = hq_cl_dot3(-0.0803345f, -0.331467f, 0.449132f, R, G, B);
+    return o;
+}
+// Opp2LAB cl:124-145: LABDELTA3 = 216f/24389f (= 0x1.22354ep-7f, the same float as Java's),
+// kappa = 24389f/27f, f = t > LABDELTA3 ? cbrt(t) : fma(kappa, t, 16)/116
+HQ_HD float hq_cl_lab_f(float t) {
+    if (t > HQ_LABDELTA3) return hq_cbrtf(t);
+    return HQ_FDIV(HQ_FFMA(0x1.c3a5eep+9f, t, 16.0f), 116.0f);
+}
+HQ_HD hq_float3 hq_cl_opp_to_lab(float o0, float o1, float o2, hq_float3 ill) {
+    const float X = hq_cl_dot3(0.624045f, -1.87044f, -0.155304f, o0, o1, o2);
+    const float Y = hq_cl_dot3(1.36606f, 0.931563f, 0.433903f, o0, o1, o2);
+    const float Z = hq_cl_dot3(1.5013f, 1.41761f, 2.53307f, o0, o1, o2);
+    const float fx = hq_cl_lab_f(HQ_FDIV(X, ill.x));
+    const float fy = hq_cl_lab_f(HQ_FDIV(Y, ill.y));
+    const float fz = hq_cl_lab_f(HQ_FDIV(Z, ill.z));
+    hq_float3 lab;
+    lab.x = HQ_FSUB(HQ_FMUL(116.0f, fy), 16.0f);
+    lab.y = HQ_FMUL(500.0f, HQ_FSUB(fx, fy));
+    lab.z = HQ_FMUL(200.0f, HQ_FSUB(fy, fz));
+    return lab;
+}
+// reflect padding of the separable filters (cl:20-27)
+HQ_HD int hq_reflect(int off, int n) {
+    if (off < 0) off = -off - 1;
+    else if (off >= n) off = (n << 1) - off - 1;
+    return off;
+}
+
 // test hook: the restated routines by code (0 cube root, 1 pow 2.4f, 2 sRGB decode,
 // 3/4 x / Xn, x / Zn of D65, 5 x / (3*LABDELTA2), 6/7 x / Xn, x / Zn of D50)
 HQ_HD float hq_math_probe(int which, float v) {

@@ -1,0 +1,166 @@
+// hq_scielab.cu — S-CIELAB spatial-filter stage (scope table row "next 1"): the plugin's real
+// cost is mean CIE76 between S-CIELAB(original) and S-CIELAB(quantised).
+//   original : RGB2XYZ + XYZ2Opp (cl:79-90,111-116) -> 3 separable filter pairs (convolve4Channels /
+//              convolve1Channel, cl:2-74, sequenced at ImageManipulation.java:316-346) -> Opp2LAB
+//   candidate: quantizeAndConvertToOpp (cl:172-199) -> computeScielabKernelsTemp (cl:234-272) ->
+//              computeScielabKernelsEnd (cl:274-306) -> Opp2LAB (cl:124-145) -> CIEDE (cl:201-209)
+// First version: one thread per pixel and per pass, taps read in ascending order so that every fma
+// chain has the reference's order (bit-exact against the oracle).  The reference transposes between
+// the passes; here the vertical pass reads column neighbours directly (coalesced across a row), which
+// is the same arithmetic.
+#include "hq_kernels.cuh"
+#include "hq_math.h"
+
+namespace hq {
+namespace {
+
+constexpr int kScThreads = 256;
+
+// filter block in global memory: [0,3T) k1[t][3], [3T,6T) k2[t][3], [6T,7T) k3[t], [7T,8T) |k3|[t]
+struct ScFilters {
+    const float* data;
+    int taps;
+};
+
+__global__ void sc_rgb_to_opp_kernel(const uint8_t* __restrict__ rgb, size_t n, size_t stride,
+                                     const float* __restrict__ table, float* __restrict__ opp) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float R = __ldg(table + 256 + rgb[3 * i]), G = __ldg(table + 256 + rgb[3 * i + 1]), B = __ldg(table + 256 + rgb[3 * i + 2]);
+    const hq_float3 o = hq_cl_linrgb_to_opp_via_xyz(R, G, B);
+    opp[i] = o.x; opp[stride + i] = o.y; opp[2 * stride + i] = o.z;
+}
+
+// palette colours -> opponent table (the K values the quantised image can take)
+__global__ void sc_palette_opp_kernel(const float* __restrict__ pal, int total, float4* __restrict__ tab) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float4 c = reinterpret_cast<const float4*>(pal)[i];
+    const hq_float3 o = hq_cl_linrgb_to_opp(hq_srgb_decode(c.x), hq_srgb_decode(c.y), hq_srgb_decode(c.z));
+    tab[i] = make_float4(o.x, o.y, o.z, 0.f);
+}
+
+// horizontal pass.  MODE 0: input = opponent planes; MODE 1: input = palette index image + table.
+// Output: 7 planes [7][stride]: (k1 * O1, k1 * O2, k1 * O3, k2 * O1, k2 * O2, k2 * O3, k3 * O1).
+template <int MODE, typename IdxT>
+__global__ void __launch_bounds__(kScThreads)
+sc_hpass_kernel(const float* __restrict__ opp, const IdxT* __restrict__ idx, const float4* __restrict__ tab,
+                int w, int h, size_t stride, ScFilters f, float* __restrict__ tmp) {
+    extern __shared__ float s_f[];  // 7 * taps
+    for (int i = threadIdx.x; i < 7 * f.taps; i += kScThreads) s_f[i] = f.data[i];
+    __syncthreads();
+    const int x = blockIdx.x * kScThreads + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const int half = f.taps / 2;
+    const size_t row = (size_t)y * w;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, c0 = 0.f;
+    for (int t = 0; t < f.taps; ++t) {
+        const size_t p = row + hq_reflect(x + t - half, w);
+        float i0, i1, i2;
+        if (MODE == 0) { i0 = __ldg(opp + p); i1 = __ldg(opp + stride + p); i2 = __ldg(opp + 2 * stride + p); }
+        else { const float4 v = __ldg(tab + idx[p]); i0 = v.x; i1 = v.y; i2 = v.z; }
+        a0 = HQ_FFMA(i0, s_f[3 * t], a0); a1 = HQ_FFMA(i1, s_f[3 * t + 1], a1); a2 = HQ_FFMA(i2, s_f[3 * t + 2], a2);
+        b0 = HQ_FFMA(i0, s_f[3 * f.taps + 3 * t], b0); b1 = HQ_FFMA(i1, s_f[3 * f.taps + 3 * t + 1], b1); b2 = HQ_FFMA(i2, s_f[3 * f.taps + 3 * t + 2], b2);
+        c0 = HQ_FFMA(i0, s_f[6 * f.taps + t], c0);
+    }
+    const size_t o = row + x;
+    tmp[o] = a0; tmp[stride + o] = a1; tmp[2 * stride + o] = a2;
+    tmp[3 * stride + o] = b0; tmp[4 * stride + o] = b1; tmp[5 * stride + o] = b2; tmp[6 * stride + o] = c0;
+}
+
+// vertical pass + combination + Opp2LAB.
+// MODE 0 (original, ImageManipulation.java:319-346): conv = V1(H1) ; conv += V2(H2) ; conv.x += V|3|(H3),
+//         each V a full tap sum started from 0; writes the S-CIELAB planes.
+// MODE 1 (candidate, cl:292-304): out = fma(t1,k1, fma(t2,k2,out)); out.x = fma(t3,|k3|,out.x) per tap;
+//         dE vs the original's S-CIELAB, fixed-point sum -> one atomic per CTA.
+template <int MODE>
+__global__ void __launch_bounds__(kScThreads)
+sc_vpass_kernel(const float* __restrict__ tmp, int w, int h, size_t stride, ScFilters f, hq_float3 ill,
+                float* __restrict__ lab_out, const float* __restrict__ lab_orig, unsigned long long* __restrict__ err_out) {
+    extern __shared__ float s_f[];  // 8 * taps
+    for (int i = threadIdx.x; i < 8 * f.taps; i += kScThreads) s_f[i] = f.data[i];
+    __syncthreads();
+    const int x = blockIdx.x * kScThreads + threadIdx.x, y = blockIdx.y;
+    long long fx = 0;
+    if (x < w) {
+        const int half = f.taps / 2, T = f.taps;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, c0 = 0.f;
+        for (int t = 0; t < T; ++t) {
+            const size_t p = (size_t)hq_reflect(y + t - half, h) * w + x;
+            const float t10 = __ldg(tmp + p), t11 = __ldg(tmp + stride + p), t12 = __ldg(tmp + 2 * stride + p);
+            const float t20 = __ldg(tmp + 3 * stride + p), t21 = __ldg(tmp + 4 * stride + p), t22 = __ldg(tmp + 5 * stride + p);
+            const float t3 = __ldg(tmp + 6 * stride + p);
+            if (MODE == 0) {
+                a0 = HQ_FFMA(t10, s_f[3 * t], a0); a1 = HQ_FFMA(t11, s_f[3 * t + 1], a1); a2 = HQ_FFMA(t12, s_f[3 * t + 2], a2);
+                b0 = HQ_FFMA(t20, s_f[3 * T + 3 * t], b0); b1 = HQ_FFMA(t21, s_f[3 * T + 3 * t + 1], b1); b2 = HQ_FFMA(t22, s_f[3 * T + 3 * t + 2], b2);
+                c0 = HQ_FFMA(t3, s_f[7 * T + t], c0);
+            } else {
+                a0 = HQ_FFMA(t10, s_f[3 * t], HQ_FFMA(t20, s_f[3 * T + 3 * t], a0));
+                a1 = HQ_FFMA(t11, s_f[3 * t + 1], HQ_FFMA(t21, s_f[3 * T + 3 * t + 1], a1));
+                a2 = HQ_FFMA(t12, s_f[3 * t + 2], HQ_FFMA(t22, s_f[3 * T + 3 * t + 2], a2));
+                a0 = HQ_FFMA(t3, s_f[7 * T + t], a0);
+            }
+        }
+        float o0, o1, o2;
+        if (MODE == 0) { o0 = HQ_FADD(HQ_FADD(a0, b0), c0); o1 = HQ_FADD(a1, b1); o2 = HQ_FADD(a2, b2); }
+        else { o0 = a0; o1 = a1; o2 = a2; }
+        const hq_float3 lab = hq_cl_opp_to_lab(o0, o1, o2, ill);
+        const size_t p = (size_t)y * w + x;
+        if (MODE == 0) {
+            lab_out[p] = lab.x; lab_out[stride + p] = lab.y; lab_out[2 * stride + p] = lab.z;
+        } else {
+            const float d2 = hq_dist2(__ldg(lab_orig + p), __ldg(lab_orig + stride + p), __ldg(lab_orig + 2 * stride + p), lab.x, lab.y, lab.z);
+            fx = hq_to_fx(HQ_FSQRT(d2));  // CIE76, cl:209
+        }
+    }
+    if (MODE == 1) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) fx += __shfl_down_sync(0xffffffffu, fx, off);
+        __shared__ long long s_err[kScThreads / 32];
+        if ((threadIdx.x & 31) == 0) s_err[threadIdx.x >> 5] = fx;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long e = 0;
+#pragma unroll
+            for (int i = 0; i < kScThreads / 32; ++i) e += s_err[i];
+            if (e) atomicAdd(err_out, (unsigned long long)e);
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_sc_rgb_to_opp(const uint8_t* d_rgb, size_t n, size_t stride, const float* d_table, float* d_opp, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    sc_rgb_to_opp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_rgb, n, stride, d_table, d_opp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sc_palette_opp(const float* d_palettes, int total, float4* d_tab, cudaStream_t st) {
+    if (total == 0) return cudaSuccess;
+    sc_palette_opp_kernel<<<(total + 127) / 128, 128, 0, st>>>(d_palettes, total, d_tab);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sc_original(const float* d_opp, int w, int h, size_t stride, const float* d_filters, int taps, int whitepoint,
+                               float* d_tmp, float* d_lab_out, cudaStream_t st) {
+    if (w == 0 || h == 0) return cudaSuccess;
+    const ScFilters f{d_filters, taps};
+    const dim3 grid((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)h);
+    sc_hpass_kernel<0, uint8_t><<<grid, kScThreads, 7 * taps * sizeof(float), st>>>(d_opp, nullptr, nullptr, w, h, stride, f, d_tmp);
+    sc_vpass_kernel<0><<<grid, kScThreads, 8 * taps * sizeof(float), st>>>(d_tmp, w, h, stride, f, hq_whitepoint(whitepoint), d_lab_out, nullptr, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sc_candidate(const void* d_idx, bool idx16, const float4* d_tab, int w, int h, size_t stride, const float* d_filters,
+                                int taps, int whitepoint, float* d_tmp, const float* d_lab_orig, unsigned long long* d_err, cudaStream_t st) {
+    if (w == 0 || h == 0) return cudaSuccess;
+    const ScFilters f{d_filters, taps};
+    const dim3 grid((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)h);
+    if (idx16) sc_hpass_kernel<1, uint16_t><<<grid, kScThreads, 7 * taps * sizeof(float), st>>>(nullptr, static_cast<const uint16_t*>(d_idx), d_tab, w, h, stride, f, d_tmp);
+    else sc_hpass_kernel<1, uint8_t><<<grid, kScThreads, 7 * taps * sizeof(float), st>>>(nullptr, static_cast<const uint8_t*>(d_idx), d_tab, w, h, stride, f, d_tmp);
+    sc_vpass_kernel<1><<<grid, kScThreads, 8 * taps * sizeof(float), st>>>(d_tmp, w, h, stride, f, hq_whitepoint(whitepoint), nullptr, d_lab_orig, d_err);
+    return cudaGetLastError();
+}
+
+}  // namespace hq

@@ -205,6 +205,36 @@ class ImageManipulation:
         n_total = n_total or self.pixels()
         return np.array([self.cost(r["err_fx"][i], r["counts"][i], n_total, swasa.params.delta) for i in range(len(r["err_fx"]))])
 
+    # -- S-CIELAB stage (the plugin's real cost; scope row "next 1")
+    def scielabConfigure(self, dpi: int = 72, viewingDistance: float = 45.0) -> None:
+        _lib.check(self._ctx, self._lib.hq_scielab_configure(self._ctx, dpi, viewingDistance))
+
+    def scielabSetFilters(self, filters7: np.ndarray, abs3: np.ndarray) -> None:
+        filters7 = np.ascontiguousarray(filters7, np.float32); abs3 = np.ascontiguousarray(abs3, np.float32)
+        _lib.check(self._ctx, self._lib.hq_scielab_set_filters(self._ctx, _ptr(filters7), _ptr(abs3), filters7.shape[1]))
+
+    def scielabFilters(self):
+        taps = C.c_int(0)
+        _lib.check(self._ctx, self._lib.hq_scielab_get_filters(self._ctx, None, None, C.byref(taps)))
+        f = np.empty((7, taps.value), np.float32); a = np.empty(taps.value, np.float32)
+        _lib.check(self._ctx, self._lib.hq_scielab_get_filters(self._ctx, _ptr(f), _ptr(a), C.byref(taps)))
+        return f, a
+
+    def scielabImage(self) -> np.ndarray:
+        """sRGBToScielab(original) (ScielabProcessor.java:374-381): planes [3, n]"""
+        out = np.empty((3, self.pixels()), np.float32)
+        _lib.check(self._ctx, self._lib.hq_scielab_get_image(self._ctx, _ptr(out)))
+        return out
+
+    def evalPalettesScielab(self, palettes: np.ndarray, space: int = SPACE_SRGB) -> dict:
+        palettes = np.ascontiguousarray(palettes, np.float32)
+        if palettes.ndim == 2:
+            palettes = palettes[None]
+        B, K, _ = palettes.shape
+        err = np.empty(B, np.int64); counts = np.empty((B, K), np.uint64)
+        _lib.check(self._ctx, self._lib.hq_eval_palettes_scielab(self._ctx, _ptr(palettes), B, K, space, _ptr(err), _ptr(counts)))
+        return {"err_fx": err, "counts": counts}
+
     def setAllreduce(self, fn) -> None:
         """fn(d_words_ptr: int, n_words: int, stream: int) -> 0 on success; None removes the hook."""
         if fn is None:
@@ -250,9 +280,20 @@ class ImageManipulation:
 
 
 class ScielabProcessor:
-    """ScielabProcessor.java reduced to the hot path: white point + bestColors façade."""
+    """ScielabProcessor.java: white point, the S-CIELAB filter bank (:66-181) and the bestColors façade."""
 
     D50, D65 = "D50", "D65"
+
+    @staticmethod
+    def buildFilters(dpi: int = 72, viewingDistance: float = 45.0):
+        """(Ofilters flattened [7, taps] = O1g1,O1g2,O1g3,O2g1,O2g2,O3g1,O3g2, absOfilters [taps]); host only"""
+        lib = _lib.load()
+        taps = C.c_int(0)
+        if lib.hq_scielab_build_filters(dpi, viewingDistance, None, None, C.byref(taps)) != 0:
+            raise ValueError("bad dpi / viewing distance")
+        f = np.empty((7, taps.value), np.float32); a = np.empty(taps.value, np.float32)
+        lib.hq_scielab_build_filters(dpi, viewingDistance, _ptr(f), _ptr(a), C.byref(taps))
+        return f, a
 
     def __init__(self, dpi: int = 72, viewingDistance: float = 45.0, whitepoint: str = "D65", imageProcessor: ImageManipulation | None = None):
         self.dpi, self.viewingDistance = dpi, viewingDistance

@@ -106,6 +106,26 @@ double hq_cost(int64_t err_fx, const uint64_t* counts, int K, uint64_t n_total, 
 int hq_quantize(hq_ctx* ctx, const float* palette, int K, int space, uint8_t* out_rgb,
                 float* out_f32, uint16_t* out_idx);
 
+/* ---- S-CIELAB spatial-filter stage (scope row "next 1"): the plugin's real cost is the mean
+ * CIE76 between S-CIELAB(original) and S-CIELAB(quantised image).
+ * hq_scielab_configure builds the separable filter bank of ScielabProcessor.java:66-181 from the
+ * plugin's "Dpi" / "Viewing distance" parameters (HybridQuantization.java:229-231; defaults 72, 45 cm
+ * are applied if it is never called); hq_scielab_set_filters installs a caller-built bank instead
+ * (filters7 = [7][taps]: O1g1,O1g2,O1g3,O2g1,O2g2,O3g1,O3g2; abs3 = |O1g3|; taps odd).
+ * hq_scielab_get_image returns sRGBToScielab(original) (ScielabProcessor.java:374-381) as planes
+ * [3][n].  hq_eval_palettes_scielab replaces computeQuantizationErrorPopulation with its full kernel
+ * chain (ImageManipulation.java:635-699): err_fx[B] = sum of round(dE * 2^24), counts[B][K].
+ * Single GPU in this version (the 21-tap vertical filter needs halo rows across shards). */
+int hq_scielab_configure(hq_ctx* ctx, int dpi, float viewing_distance_cm);
+int hq_scielab_set_filters(hq_ctx* ctx, const float* filters7, const float* abs3, int taps);
+/* *taps: in = capacity of the arrays (entries per filter), out = actual taps */
+int hq_scielab_get_filters(const hq_ctx* ctx, float* filters7, float* abs3, int* taps);
+int hq_scielab_get_image(hq_ctx* ctx, float* planes);
+/* host only (no GPU needed): the filter bank for (dpi, viewing distance); *taps as above */
+int hq_scielab_build_filters(int dpi, float viewing_distance_cm, float* filters7, float* abs3, int* taps);
+int hq_eval_palettes_scielab(hq_ctx* ctx, const float* palettes, int B, int K, int space,
+                             int64_t* err_fx, uint64_t* counts);
+
 /* ---- multi-GPU: pixel rows are sharded across ranks (one context per GPU); the only
  * exchange is a sum of the integer result words.  The hook is called on the context's
  * stream order with the DEVICE buffer; it must leave the element-wise int64 sum over all

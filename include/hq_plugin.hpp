@@ -254,14 +254,94 @@ private:
     std::vector<uint64_t> counts_;
 };
 
-// ScielabProcessor.java, reduced to what the hot path uses: the white point (:19-21,70-76)
-// and the bestColors façade (:383-386).  Filter construction (:78-181) belongs to the
-// S-CIELAB spatial stage, a "next" row of the scope table.
+// ScielabProcessor.java: white point (:19-21,70-76), the S-CIELAB separable filter bank
+// (:78-181, helpers :185-254) and the bestColors façade (:383-386).
 class ScielabProcessor {
 public:
     enum class Whitepoint { D50, D65 };
+    // The filter bank: Ofilters[channel][gaussian][tap] and |Ofilters[0][2]| (:54-55)
+    struct FilterBank {
+        std::vector<float> Ofilters[3][3];
+        std::vector<float> absOfilters;
+        int taps() const { return static_cast<int>(Ofilters[0][0].size()); }
+        // flattened as the C ABI takes it: [7][taps] = O1g1,O1g2,O1g3,O2g1,O2g2,O3g1,O3g2
+        std::vector<float> flat() const {
+            std::vector<float> f;
+            const int count[3] = {3, 2, 2};
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < count[i]; ++j) f.insert(f.end(), Ofilters[i][j].begin(), Ofilters[i][j].end());
+            return f;
+        }
+    };
+
     ScielabProcessor(int dpi, double viewingDistance, Whitepoint whitepoint, ImageManipulation* imageProcessor)
-        : dpi_(dpi), viewingDistance_(viewingDistance), whitepoint_(whitepoint), imageProcessing_(imageProcessor) {}
+        : dpi_(dpi), viewingDistance_(viewingDistance), whitepoint_(whitepoint), imageProcessing_(imageProcessor),
+          bank_(buildFilters(dpi, viewingDistance)) {}
+
+    // :238-254 — a centred Gaussian that sums to one
+    static std::vector<float> gauss(float halfwidth, int width) {
+        const float alpha = 2 * static_cast<float>(std::sqrt(std::log(2.0))) / (halfwidth - 1);
+        std::vector<float> result(width);
+        const int offset = width / 2;
+        double sum = 0;
+        for (int i = 0; i < width; ++i) {
+            const float e = -alpha * alpha * static_cast<float>(i - offset) * static_cast<float>(i - offset);
+            result[i] = static_cast<float>(std::exp(static_cast<double>(e)));
+            sum += result[i];
+        }
+        for (float& v : result) v = static_cast<float>(static_cast<double>(v) / sum);
+        return result;
+    }
+
+    // :66-181 — everything the constructor computes before handing the filters to the backend
+    static FilterBank buildFilters(int dpi, double viewingDistance) {
+        static const float weights[3][3] = {{1.00327f, 0.114416f, -0.117686f}, {0.616725f, 0.383275f, 0}, {0.567885f, 0.432115f, 0}};  // :44-48
+        static const float halfwidths[3][3] = {{0.05f, 0.225f, 7.0f}, {0.0685f, 0.826f, 0}, {0.0920f, 0.6451f, 0}};                      // :49-53
+        static const int count[3] = {3, 2, 2};
+        const double kPi = 3.14159265358979323846;
+        int sampPerDeg = static_cast<int>(std::llround(dpi / ((180 / kPi) * std::atan(2.54 / viewingDistance))));  // :80
+        int uprate = 1;
+        if (sampPerDeg < 224) {  // :81-88 (minSAMPPERDEG :23)
+            uprate = static_cast<int>(std::ceil(224 * 1.0 / sampPerDeg));
+            sampPerDeg *= uprate;
+        }
+        const int width = static_cast<int>(std::ceil(sampPerDeg / 2.0)) * 2 - 1;  // :102
+        FilterBank bank;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < count[i]; ++j) {
+                std::vector<float> f = gauss(halfwidths[i][j] * static_cast<float>(sampPerDeg), width);  // :97,112
+                const float w = weights[i][j];
+                const float sign = w > 0 ? 1.0f : (w < 0 ? -1.0f : 0.0f);
+                const float factor = static_cast<float>(std::sqrt(static_cast<double>(std::fabs(w)))) * sign;  // :113
+                for (float& v : f) v *= factor;
+                bank.Ofilters[i][j] = std::move(f);
+            }
+        if (uprate > 1) {  // :122-173: triangular up-sampling kernel, convolve, keep every uprate-th sample around the centre
+            const int upLen = uprate * 2 - 1;
+            std::vector<float> upcol(upLen);
+            for (int i = 0; i < upLen; ++i) upcol[i] = static_cast<float>(uprate - std::abs(uprate - i - 1)) * 1.0f / static_cast<float>(uprate);  // :129
+            upcol = resize1D(upcol, upLen + width - 1);  // :132
+            const int mid = width / 2;
+            std::vector<int> downs;  // :146-164
+            for (int v = mid - (mid / uprate) * uprate; v <= mid; v += uprate) downs.push_back(v);
+            for (int v = mid + uprate; static_cast<int>(downs.size()) < 2 * (mid / uprate) + 1; v += uprate) downs.push_back(v);
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < count[i]; ++j) {
+                    const std::vector<float> up = conv1D(bank.Ofilters[i][j], upcol);  // :136-144
+                    std::vector<float> picked(downs.size());
+                    for (size_t q = 0; q < downs.size(); ++q) picked[q] = up[downs[q]];  // :166-172, extractWithIndices :222-230
+                    bank.Ofilters[i][j] = std::move(picked);
+                }
+        }
+        bank.absOfilters.resize(bank.Ofilters[0][2].size());  // :174-178
+        for (size_t i = 0; i < bank.absOfilters.size(); ++i) {
+            const float v = bank.Ofilters[0][2][i];
+            bank.absOfilters[i] = v * (v < 0 ? -1 : 1);
+        }
+        return bank;
+    }
+
+    const FilterBank& filters() const { return bank_; }
     int whitepointCode() const { return whitepoint_ == Whitepoint::D50 ? HQ_WHITEPOINT_D50 : HQ_WHITEPOINT_D65; }
     // sRGBToScielab (:374-381) with the identity filter: uploads the image, converts on the GPU
     void sRGBToScielab(const uint8_t* rgb, int w, int rows) { imageProcessing_->setImage(rgb, w, rows, whitepointCode()); }
@@ -271,10 +351,30 @@ public:
     void close() { imageProcessing_->close(); }  // :440-443
 
 private:
+    static std::vector<float> conv1D(const std::vector<float>& data, const std::vector<float>& filter) {  // :185-201
+        std::vector<float> result(data.size(), 0.0f);
+        const int n = static_cast<int>(data.size()), offset = static_cast<int>(filter.size()) / 2;
+        for (int i = 0; i < n; ++i)
+            for (int j = -offset; j <= offset; ++j)
+                if (i + j >= 0 && i + j < n) result[i] += filter[j + offset] * data[i + j];
+        return result;
+    }
+    static std::vector<float> resize1D(const std::vector<float>& src, int newSize) {  // :203-220
+        std::vector<float> res(newSize, 0.0f);
+        const int n = static_cast<int>(src.size());
+        const int pad = std::abs(newSize - n) / 2;
+        if (newSize > n) {
+            for (int i = 0; i < n; ++i) res[pad + i] = src[i];
+        } else {
+            for (int i = 0; i < newSize; ++i) res[i] = src[pad + i];
+        }
+        return res;
+    }
     int dpi_;
     double viewingDistance_;
     Whitepoint whitepoint_;
     ImageManipulation* imageProcessing_;
+    FilterBank bank_;
 };
 
 // HybridQuantization.java: the parameter surface (:185-257, unchanged names, defaults and

@@ -431,6 +431,266 @@ double hqo_find_best_quantization(const uint8_t* rgb, int w, int h, int K,
     return best_err;
 }
 
+/* ------------------------------------------------------------------ S-CIELAB filter bank
+ * ScielabProcessor.java:66-181 (constructor), :185-254 (conv1D, resize1D, extractWithIndices, gauss).
+ * Java float/double promotion is followed expression by expression. */
+static const float SC_WEIGHTS[3][3] = {{1.00327f, 0.114416f, -0.117686f}, {0.616725f, 0.383275f, 0.f}, {0.567885f, 0.432115f, 0.f}}; /* :44-48 */
+static const float SC_HALFWIDTHS[3][3] = {{0.05f, 0.225f, 7.0f}, {0.0685f, 0.826f, 0.f}, {0.0920f, 0.6451f, 0.f}};                  /* :49-53 */
+static const int SC_COUNT[3] = {3, 2, 2};
+
+static void sc_gauss(float halfwidth, int width, float* result) { /* :238-254 */
+    const float alpha = 2 * (float)sqrt(log(2)) / (halfwidth - 1);
+    const int offset = width / 2;
+    double sum = 0;
+    for (int i = 0; i < width; ++i) {
+        const float arg = -alpha * alpha * (float)(i - offset) * (float)(i - offset);
+        result[i] = (float)exp((double)arg);
+        sum += result[i];
+    }
+    for (int i = 0; i < width; ++i) result[i] = (float)((double)result[i] / sum);
+}
+
+static void sc_conv1d(const float* data, int n, const float* filter, int fl, float* result) { /* :185-201 */
+    const int offset = fl / 2;
+    for (int i = 0; i < n; ++i) {
+        float acc = 0.0f;
+        for (int j = -offset; j <= offset; ++j)
+            if (!(i + j < 0 || i + j >= n)) acc += filter[j + offset] * data[i + j];
+        result[i] = acc;
+    }
+}
+
+/* filters[7][taps]: O1 (three Gaussians), O2 (two), O3 (two), in the order
+ * [0]=O1g1 [1]=O1g2 [2]=O1g3 [3]=O2g1 [4]=O2g2 [5]=O3g1 [6]=O3g2; abs3[taps] = |O1g3|.
+ * Returns the number of taps (<= max_taps) or -1. */
+int hqo_scielab_filters(int dpi, double viewing_distance, float* filters, float* abs3, int max_taps) {
+    int samp = (int)llround((double)dpi / ((180 / M_PI) * atan(2.54 / viewing_distance))); /* :80 */
+    int uprate = 1;
+    if (samp < 224) { uprate = (int)ceil(224 * 1.0 / samp); samp *= uprate; }                /* :81-88 */
+    const int width = (int)(ceil(samp / 2.0)) * 2 - 1;                                       /* :102 */
+    float* g[7]; int gi = 0;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < SC_COUNT[i]; ++j) {
+            float* f = (float*)malloc(sizeof(float) * width);
+            const float spread = SC_HALFWIDTHS[i][j] * (float)samp;                          /* :97 */
+            sc_gauss(spread, width, f);                                                      /* :112 */
+            const float w = SC_WEIGHTS[i][j];
+            const float factor = (float)sqrt((double)fabsf(w)) * (w > 0 ? 1.0f : (w < 0 ? -1.0f : 0.0f)); /* :113 */
+            for (int k = 0; k < width; ++k) f[k] *= factor;
+            g[gi++] = f;
+        }
+    int taps = width;
+    if (uprate > 1) {                                                                         /* :122-173 */
+        const int ul = uprate * 2 - 1;
+        const int fl = ul + width - 1;
+        float* up = (float*)calloc(fl, sizeof(float));
+        const int pad = (fl - ul) / 2;
+        for (int i = 0; i < ul; ++i) up[pad + i] = (float)(uprate - abs(uprate - i - 1)) * 1.0f / (float)uprate; /* :129, resize :203-220 */
+        const int mid = width / 2;
+        taps = 2 * (mid / uprate) + 1;                                                        /* :148 */
+        if (taps > max_taps) { for (int q = 0; q < 7; ++q) free(g[q]); free(up); return -1; }
+        int* downs = (int*)malloc(sizeof(int) * taps);
+        const int nlow = mid / uprate + 1;                                                    /* :149-163 */
+        for (int i = 0; i < nlow; ++i) downs[i] = mid - (nlow - 1 - i) * uprate;
+        for (int i = nlow, j = mid + uprate; i < taps; ++i, j += uprate) downs[i] = j;
+        float* tmp = (float*)malloc(sizeof(float) * width);
+        for (int q = 0; q < 7; ++q) {
+            sc_conv1d(g[q], width, up, fl, tmp);                                              /* :136-144 */
+            for (int i = 0; i < taps; ++i) filters[(size_t)q * taps + i] = tmp[downs[i]];      /* :166-172 */
+        }
+        free(tmp); free(downs); free(up);
+    } else {
+        if (taps > max_taps) { for (int q = 0; q < 7; ++q) free(g[q]); return -1; }
+        for (int q = 0; q < 7; ++q) memcpy(filters + (size_t)q * taps, g[q], sizeof(float) * taps);
+    }
+    for (int i = 0; i < taps; ++i) { const float v = filters[2 * (size_t)taps + i]; abs3[i] = v * (v < 0 ? -1 : 1); } /* :174-178 */
+    for (int q = 0; q < 7; ++q) free(g[q]);
+    return taps;
+}
+
+/* ------------------------------------------------------------------ S-CIELAB pipeline (next row 1)
+ * The plugin's real cost: S-CIELAB(original) vs S-CIELAB(quantised), CIE76, mean + penalty.
+ * Follows the OpenCL kernels (the only implementation the reference has of this stage):
+ *   RGB2XYZ cl:79-90, XYZ2Opp cl:111-116, convolve4Channels cl:2-40, convolve1Channel cl:42-74,
+ *   quantizeAndConvertToOpp cl:172-199, computeScielabKernelsTemp cl:234-272,
+ *   computeScielabKernelsEnd cl:274-306, Opp2LAB cl:124-145, CIEDE cl:201-209,
+ *   host sequencing ImageManipulation.java:285-370 (original) and :620-727 (candidates).
+ * Device-defined OpenCL builtins are pinned: pow(x,2.4f) and cbrt correctly rounded to fp32, dot()
+ * left to right without contraction, fma() exact, distance() = sqrtf(fma chain). */
+static const float CL_RGB2XYZ[3][3] = {{0.4124564f, 0.3575761f, 0.1804375f}, {0.2126729f, 0.7151522f, 0.0721750f}, {0.0193339f, 0.1191920f, 0.9503041f}}; /* cl:77 */
+static const float CL_XYZ2OPP[3][3] = {{0.2787336f, 0.7218031f, -0.1065520f}, {-0.4487736f, 0.2898056f, -0.0771569f}, {0.0859513f, -0.5899859f, 0.5011089f}}; /* cl:110 */
+static const float CL_OPP2XYZ[3][3] = {{0.624045f, -1.87044f, -0.155304f}, {1.36606f, 0.931563f, 0.433903f}, {1.5013f, 1.41761f, 2.53307f}};                  /* cl:118 */
+static const float CL_RGB2OPP[3][3] = {{0.266413f, 0.603167f, 0.00113333f}, {-0.124957f, 0.0375879f, -0.133381f}, {-0.0803345f, -0.331467f, 0.449132f}};    /* cl:171 */
+
+static inline float cl_dot3(const float m[3], float x, float y, float z) { return (x * m[0] + y * m[1]) + z * m[2]; }
+static inline int reflect(int off, int n) { /* cl:20-27 */
+    if (off < 0) off = -off - 1;
+    else if (off >= n) off = (n << 1) - off - 1;
+    return off;
+}
+
+static void cl_opp_to_lab(const float opp[3], const float ill[3], float lab[3]) { /* cl:124-145 */
+    volatile float n216 = 216.0f, d24389 = 24389.0f, n27 = 27.0f;
+    const float LABDELTA3 = n216 / d24389, kappa = d24389 / n27; /* cl:122-123 */
+    float f[3];
+    for (int c = 0; c < 3; ++c) {
+        const float v = cl_dot3(CL_OPP2XYZ[c], opp[0], opp[1], opp[2]);
+        const float t = v / ill[c];
+        f[c] = (t > LABDELTA3) ? hqo_cbrt_pow(t) : fmaf(kappa, t, 16.0f) / 116.0f;
+    }
+    lab[0] = 116.0f * f[1] - 16.0f;
+    lab[1] = 500.0f * (f[0] - f[1]);
+    lab[2] = 200.0f * (f[1] - f[2]);
+}
+
+/* one separable pass of convolve4Channels / convolve1Channel on `nch` interleaved channels: in is
+ * [rows][cols][nch], out is TRANSPOSED [cols][rows][nch]; k[t][c]; accumulates (+=) if update */
+typedef struct { const float* in; float* out; const float* k; int rows, cols, nch, taps, update; } conv_ctx;
+static void conv_rows(void* p, size_t lo, size_t hi, int tid) {
+    (void)tid;
+    conv_ctx* c = (conv_ctx*)p;
+    const int half = c->taps / 2;
+    for (size_t i = lo; i < hi; ++i)
+        for (int j = 0; j < c->cols; ++j)
+            for (int ch = 0; ch < c->nch; ++ch) {
+                float acc = 0.0f;
+                for (int t = 0; t < c->taps; ++t) {
+                    const int off = reflect(j + t - half, c->cols);
+                    acc = fmaf(c->in[(i * c->cols + off) * c->nch + ch], c->k[t * c->nch + ch], acc);
+                }
+                float* o = &c->out[((size_t)j * c->rows + i) * c->nch + ch];
+                *o = c->update ? *o + acc : acc;
+            }
+}
+static void conv_pass(const float* in, float* out, const float* k, int rows, int cols, int nch, int taps, int update, int threads) {
+    conv_ctx c = {in, out, k, rows, cols, nch, taps, update};
+    parallel_ranges((size_t)rows, threads, conv_rows, &c);
+}
+
+/* filters [7][taps] as hqo_scielab_filters returns them -> k1[t][3], k2[t][3] (updateOpenCLFilters, ImageManipulation.java:800-841) */
+static void pack_filters(const float* filters, int taps, float* k1, float* k2) {
+    for (int t = 0; t < taps; ++t) {
+        k1[3 * t] = filters[0 * taps + t]; k1[3 * t + 1] = filters[3 * taps + t]; k1[3 * t + 2] = filters[5 * taps + t];
+        k2[3 * t] = filters[1 * taps + t]; k2[3 * t + 1] = filters[4 * taps + t]; k2[3 * t + 2] = filters[6 * taps + t];
+    }
+}
+
+/* S-CIELAB representation of the ORIGINAL image: sRGBToScielab (ScielabProcessor.java:374-381) */
+void hqo_scielab_image(const uint8_t* rgb, int w, int h, int whitepoint, const float* filters, const float* abs3,
+                       int taps, float* lab /*[3][n]*/, int threads) {
+    const size_t n = (size_t)w * h;
+    const float* ill = WHITE[whitepoint == HQO_WHITE_D50 ? 1 : 0];
+    float lin[256];
+    for (unsigned v = 0; v < 256; ++v) lin[v] = hqo_srgb_decode(hqo_u8_to_unit(v));
+    float* opp = (float*)malloc(sizeof(float) * 3 * n);
+    float* tmp = (float*)malloc(sizeof(float) * 3 * n);
+    float* conv = (float*)malloc(sizeof(float) * 3 * n);
+    float* o1 = (float*)malloc(sizeof(float) * n);
+    float* t1 = (float*)malloc(sizeof(float) * n);
+    float* c1 = (float*)malloc(sizeof(float) * n);
+    float* k1 = (float*)malloc(sizeof(float) * 3 * taps);
+    float* k2 = (float*)malloc(sizeof(float) * 3 * taps);
+    pack_filters(filters, taps, k1, k2);
+    for (size_t i = 0; i < n; ++i) { /* RGB2XYZ cl:79-90 then XYZ2Opp cl:111-116 */
+        const float R = lin[rgb[3 * i]], G = lin[rgb[3 * i + 1]], B = lin[rgb[3 * i + 2]];
+        const float X = cl_dot3(CL_RGB2XYZ[0], R, G, B), Y = cl_dot3(CL_RGB2XYZ[1], R, G, B), Z = cl_dot3(CL_RGB2XYZ[2], R, G, B);
+        for (int c = 0; c < 3; ++c) opp[3 * i + c] = cl_dot3(CL_XYZ2OPP[c], X, Y, Z);
+        o1[i] = opp[3 * i];
+    }
+    /* ImageManipulation.java:319-346: (H then V) with k1, += (H then V) with k2, .x += (H k3, V |k3|) */
+    conv_pass(opp, tmp, k1, h, w, 3, taps, 0, threads);
+    conv_pass(tmp, conv, k1, w, h, 3, taps, 0, threads);
+    conv_pass(opp, tmp, k2, h, w, 3, taps, 0, threads);
+    conv_pass(tmp, conv, k2, w, h, 3, taps, 1, threads);
+    conv_pass(o1, t1, filters + 2 * (size_t)taps, h, w, 1, taps, 0, threads);
+    for (size_t i = 0; i < n; ++i) c1[i] = conv[3 * i];
+    conv_pass(t1, c1, abs3, w, h, 1, taps, 1, threads);
+    for (size_t i = 0; i < n; ++i) {
+        float o[3] = {c1[i], conv[3 * i + 1], conv[3 * i + 2]}, l[3];
+        cl_opp_to_lab(o, ill, l);
+        lab[i] = l[0]; lab[n + i] = l[1]; lab[2 * n + i] = l[2];
+    }
+    free(opp); free(tmp); free(conv); free(o1); free(t1); free(c1); free(k1); free(k2);
+}
+
+typedef struct {
+    const uint16_t* idx; const float* opp_tab; /* [K][3] */
+    const float *k1, *k2, *k3, *abs3; int w, h, taps;
+    float *t1, *t2, *t3; /* transposed [w][h][3], [w][h][3], [w][h] */
+    const float* orig; const float* ill; size_t n;
+    int64_t* t_err; /* per thread */
+} sc_ctx;
+static void sc_temp_rows(void* p, size_t lo, size_t hi, int tid) { /* computeScielabKernelsTemp cl:234-272 */
+    (void)tid;
+    sc_ctx* c = (sc_ctx*)p;
+    const int half = c->taps / 2, w = c->w, h = c->h;
+    for (size_t i = lo; i < hi; ++i)
+        for (int j = 0; j < w; ++j) {
+            float a1[3] = {0, 0, 0}, a2[3] = {0, 0, 0}, a3 = 0;
+            for (int t = 0; t < c->taps; ++t) {
+                const float* in = c->opp_tab + 3 * (size_t)c->idx[i * w + reflect(j + t - half, w)];
+                for (int ch = 0; ch < 3; ++ch) { a1[ch] = fmaf(in[ch], c->k1[3 * t + ch], a1[ch]); a2[ch] = fmaf(in[ch], c->k2[3 * t + ch], a2[ch]); }
+                a3 = fmaf(in[0], c->k3[t], a3);
+            }
+            const size_t o = (size_t)j * h + i;
+            for (int ch = 0; ch < 3; ++ch) { c->t1[3 * o + ch] = a1[ch]; c->t2[3 * o + ch] = a2[ch]; }
+            c->t3[o] = a3;
+        }
+}
+static void sc_end_rows(void* p, size_t lo, size_t hi, int tid) { /* computeScielabKernelsEnd cl:274-306 + Opp2LAB + CIEDE */
+    sc_ctx* c = (sc_ctx*)p;
+    const int half = c->taps / 2, w = c->w, h = c->h;
+    int64_t err = 0;
+    for (size_t j = lo; j < hi; ++j)      /* rows of the transposed images = image columns */
+        for (int i = 0; i < h; ++i) {
+            float out[3] = {0, 0, 0};
+            for (int t = 0; t < c->taps; ++t) {
+                const size_t o = j * h + reflect(i + t - half, h);
+                for (int ch = 0; ch < 3; ++ch) out[ch] = fmaf(c->t1[3 * o + ch], c->k1[3 * t + ch], fmaf(c->t2[3 * o + ch], c->k2[3 * t + ch], out[ch]));
+                out[0] = fmaf(c->t3[o], c->abs3[t], out[0]);
+            }
+            float lab[3];
+            cl_opp_to_lab(out, c->ill, lab);
+            const size_t px = (size_t)i * w + j;
+            err += to_fx(sqrtf(dist2(c->orig[px], c->orig[c->n + px], c->orig[2 * c->n + px], lab[0], lab[1], lab[2]))); /* cl:209 */
+        }
+    c->t_err[tid] += err;
+}
+
+/* candidate costs with the S-CIELAB pipeline.  scielab_orig = hqo_scielab_image(...) [3][n] */
+void hqo_scielab_eval(const uint8_t* rgb, int w, int h, int whitepoint, const float* filters, const float* abs3, int taps,
+                      const float* scielab_orig, const float* palettes, int B, int K, int space, int64_t* err_fx,
+                      uint64_t* counts, int threads) {
+    const size_t n = (size_t)w * h;
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    uint16_t* idx = (uint16_t*)malloc(sizeof(uint16_t) * n * B);
+    hqo_assign_reduce(rgb, n, whitepoint, palettes, B, K, space, NULL, counts, NULL, idx, threads);
+    sc_ctx c; memset(&c, 0, sizeof c);
+    float* k1 = (float*)malloc(sizeof(float) * 3 * taps); float* k2 = (float*)malloc(sizeof(float) * 3 * taps);
+    pack_filters(filters, taps, k1, k2);
+    float* tab = (float*)malloc(sizeof(float) * 3 * K);
+    c.k1 = k1; c.k2 = k2; c.k3 = filters + 2 * (size_t)taps; c.abs3 = abs3; c.w = w; c.h = h; c.taps = taps; c.n = n;
+    c.t1 = (float*)malloc(sizeof(float) * 3 * n); c.t2 = (float*)malloc(sizeof(float) * 3 * n); c.t3 = (float*)malloc(sizeof(float) * n);
+    c.orig = scielab_orig; c.ill = WHITE[whitepoint == HQO_WHITE_D50 ? 1 : 0]; c.opp_tab = tab;
+    c.t_err = (int64_t*)malloc(sizeof(int64_t) * 256);
+    for (int b = 0; b < B; ++b) {
+        for (int k = 0; k < K; ++k) { /* cl:194-198: decode the chosen palette colour, RGB -> Opp */
+            const float* pc = palettes + ((size_t)b * K + k) * 4;
+            const float R = hqo_srgb_decode(pc[0]), G = hqo_srgb_decode(pc[1]), Bl = hqo_srgb_decode(pc[2]);
+            for (int ch = 0; ch < 3; ++ch) tab[3 * k + ch] = cl_dot3(CL_RGB2OPP[ch], R, G, Bl);
+        }
+        c.idx = idx + (size_t)b * n;
+        memset(c.t_err, 0, sizeof(int64_t) * 256);
+        parallel_ranges((size_t)h, threads, sc_temp_rows, &c);
+        parallel_ranges((size_t)w, threads, sc_end_rows, &c);
+        int64_t e = 0;
+        for (int t = 0; t < 256; ++t) e += c.t_err[t];
+        err_fx[b] = e;
+    }
+    free(idx); free(k1); free(k2); free(tab); free(c.t1); free(c.t2); free(c.t3); free(c.t_err);
+}
+
 /* ------------------------------------------------------------------ range evaluation (tests) */
 typedef struct { int which; uint32_t first; float* out; } mrange_ctx;
 static void mrange_fn(void* p, size_t lo, size_t hi, int tid) {

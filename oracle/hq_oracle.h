@@ -92,6 +92,18 @@ double hqo_find_best_quantization(const uint8_t* rgb, int w, int h, int K,
                                   const hqo_swasa_params* p, float* best_colors,
                                   double* trace_costs, int threads);
 
+/* ---- S-CIELAB (next row 1): filter bank of ScielabProcessor.java:66-181.  filters [7][taps]
+ * (O1g1,O1g2,O1g3,O2g1,O2g2,O3g1,O3g2), abs3 [taps]; returns taps or -1 */
+int hqo_scielab_filters(int dpi, double viewing_distance, float* filters, float* abs3, int max_taps);
+/* S-CIELAB representation of the original image, lab [3][n] (ScielabProcessor.sRGBToScielab :374-381) */
+void hqo_scielab_image(const uint8_t* rgb, int w, int h, int whitepoint, const float* filters, const float* abs3,
+                       int taps, float* lab, int threads);
+/* candidate costs through quantise -> Opp -> separable filters -> Lab -> CIE76 vs scielab_orig
+ * (ImageManipulation.java:620-727): err_fx[B], counts[B][K] */
+void hqo_scielab_eval(const uint8_t* rgb, int w, int h, int whitepoint, const float* filters, const float* abs3, int taps,
+                      const float* scielab_orig, const float* palettes, int B, int K, int space, int64_t* err_fx,
+                      uint64_t* counts, int threads);
+
 /* tests: evaluate which (0 cube-root pow, 1 pow 2.4f, 2 sRGB decode) over consecutive float bit patterns */
 void hqo_math_range(int which, uint32_t first_bits, uint32_t count, float* out, int threads);
 

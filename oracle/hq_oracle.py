@@ -67,6 +67,9 @@ def load() -> C.CDLL:
         L.hqo_find_best_quantization.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.POINTER(SwasaParams), _P, _P, C.c_int]
         L.hqo_synth_image.argtypes = [_P, C.c_int, C.c_int, C.c_uint64, C.c_int]
         L.hqo_math_range.argtypes = [C.c_int, C.c_uint32, C.c_uint32, _P, C.c_int]
+        L.hqo_scielab_filters.restype = C.c_int; L.hqo_scielab_filters.argtypes = [C.c_int, C.c_double, _P, _P, C.c_int]
+        L.hqo_scielab_image.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, C.c_int]
+        L.hqo_scielab_eval.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int]
         _lib = L
     return _lib
 
@@ -156,3 +159,36 @@ def math_range(which: int, first_bits: int, count: int, threads=None) -> np.ndar
     out = np.empty(count, np.float32)
     load().hqo_math_range(which, first_bits, count, _ptr(out), threads or default_threads())
     return out
+
+
+def scielab_filters(dpi=72, viewing_distance=45.0, max_taps=4096):
+    """(filters [7, taps], abs3 [taps]) of ScielabProcessor.java:66-181"""
+    f = np.zeros(7 * max_taps, np.float32); a = np.zeros(max_taps, np.float32)
+    t = load().hqo_scielab_filters(dpi, float(viewing_distance), _ptr(f), _ptr(a), max_taps)
+    if t < 0:
+        raise ValueError("too many taps")
+    return f[:7 * t].reshape(7, t).copy(), a[:t].copy()
+
+
+def scielab_image(rgb_u8, filters, abs3, whitepoint=WHITE_D65, threads=None) -> np.ndarray:
+    rgb = np.ascontiguousarray(rgb_u8, np.uint8)
+    h, w = rgb.shape[:2]
+    lab = np.empty((3, h * w), np.float32)
+    filters = np.ascontiguousarray(filters, np.float32); abs3 = np.ascontiguousarray(abs3, np.float32)
+    load().hqo_scielab_image(_ptr(rgb), w, h, whitepoint, _ptr(filters), _ptr(abs3), filters.shape[1], _ptr(lab), threads or default_threads())
+    return lab
+
+
+def scielab_eval(rgb_u8, filters, abs3, scielab_orig, palettes, space=SPACE_SRGB, whitepoint=WHITE_D65, threads=None):
+    rgb = np.ascontiguousarray(rgb_u8, np.uint8)
+    h, w = rgb.shape[:2]
+    palettes = np.ascontiguousarray(palettes, np.float32)
+    if palettes.ndim == 2:
+        palettes = palettes[None]
+    B, K, _ = palettes.shape
+    err = np.empty(B, np.int64); counts = np.empty((B, K), np.uint64)
+    filters = np.ascontiguousarray(filters, np.float32); abs3 = np.ascontiguousarray(abs3, np.float32)
+    so = np.ascontiguousarray(scielab_orig, np.float32)
+    load().hqo_scielab_eval(_ptr(rgb), w, h, whitepoint, _ptr(filters), _ptr(abs3), filters.shape[1], _ptr(so), _ptr(palettes), B, K, space,
+                            _ptr(err), _ptr(counts), threads or default_threads())
+    return {"err_fx": err, "counts": counts}

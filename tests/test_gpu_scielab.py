@@ -1,0 +1,65 @@
+"""S-CIELAB stage on the GPU against the oracle: the S-CIELAB representation of the original image and
+the candidate costs through the full kernel chain, bit for bit."""
+import os
+
+import numpy as np
+import pytest
+
+from hybridquantization_b200 import SPACE_LAB, SPACE_SRGB, WHITEPOINT_D50, HqError, synth
+
+pytestmark = pytest.mark.gpu
+THREADS = max(1, len(os.sched_getaffinity(0)))
+
+
+@pytest.mark.parametrize("w,h,smooth,wp", [(64, 48, True, 0), (97, 33, False, 0), (10, 10, False, 0), (300, 11, True, 1), (513, 257, True, 0)])
+def test_scielab_of_original_matches_oracle(backend, oracle, w, h, smooth, wp):
+    img = synth.synth_image(w, h, 77 + w, smooth)
+    backend.setImage(img, wp)
+    backend.scielabConfigure(72, 45.0)
+    f, a = backend.scielabFilters()
+    of, oa = oracle.scielab_filters(72, 45.0)
+    assert np.array_equal(f.view(np.uint32), of.view(np.uint32)) and np.array_equal(a.view(np.uint32), oa.view(np.uint32))
+    got = backend.scielabImage()
+    want = oracle.scielab_image(img, of, oa, wp, THREADS)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("K,space", [(8, SPACE_SRGB), (16, SPACE_LAB), (256, SPACE_SRGB), (300, SPACE_SRGB)])
+def test_scielab_candidate_costs_match_oracle(backend, oracle, K, space):
+    img = synth.synth_image(211, 97, 5, smooth=True)
+    pal = synth.synth_palettes(3, K)
+    backend.setImage(img)
+    backend.scielabConfigure(72, 45.0)
+    of, oa = oracle.scielab_filters(72, 45.0)
+    so = oracle.scielab_image(img, of, oa, 0, THREADS)
+    got = backend.evalPalettesScielab(pal, space)
+    want = oracle.scielab_eval(img, of, oa, so, pal, space, 0, THREADS)
+    assert np.array_equal(got["err_fx"], want["err_fx"])
+    assert np.array_equal(got["counts"], want["counts"])
+
+
+def test_other_viewing_conditions_and_custom_filters(backend, oracle):
+    img = synth.synth_image(160, 120, 9, smooth=True)
+    pal = synth.synth_palettes(2, 12)
+    backend.setImage(img, WHITEPOINT_D50)
+    for dpi, dist in ((96, 60.0), (150, 40.0)):
+        backend.scielabConfigure(dpi, dist)
+        of, oa = oracle.scielab_filters(dpi, dist)
+        so = oracle.scielab_image(img, of, oa, 1, THREADS)
+        assert np.array_equal(backend.scielabImage().view(np.uint32), so.view(np.uint32))
+        got = backend.evalPalettesScielab(pal)
+        want = oracle.scielab_eval(img, of, oa, so, pal, 1, 1, THREADS)
+        assert np.array_equal(got["err_fx"], want["err_fx"])
+    # identity filter bank (single tap): the stage degenerates to a per-pixel colour pipeline
+    ident = np.zeros((7, 1), np.float32); ident[[0, 3, 5]] = 1.0
+    backend.scielabSetFilters(ident, np.zeros(1, np.float32))
+    so = oracle.scielab_image(img, ident, np.zeros(1, np.float32), 1, THREADS)
+    assert np.array_equal(backend.scielabImage().view(np.uint32), so.view(np.uint32))
+
+
+def test_too_small_image_is_rejected(backend):
+    backend.setImage(synth.synth_image(9, 40, 1))
+    backend.scielabConfigure(72, 45.0)
+    with pytest.raises(HqError) as e:
+        backend.scielabImage()
+    assert e.value.code == 4
