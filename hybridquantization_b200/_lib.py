@@ -16,6 +16,7 @@ HQ_OK = 0
 ERR_NAMES = {1: "HQ_ERR_INVALID", 2: "HQ_ERR_CUDA", 3: "HQ_ERR_NO_IMAGE", 4: "HQ_ERR_UNSUPPORTED", 5: "HQ_ERR_CALLBACK"}
 WHITEPOINT_D65, WHITEPOINT_D50 = 0, 1
 SPACE_LAB, SPACE_SRGB = 0, 1
+COST_LAB, COST_SCIELAB = 0, 1
 EVAL_SUMS, EVAL_FORCE_DIRECT, EVAL_FORCE_CHUNKED, EVAL_FORCE_PREFILTER = 1, 2, 4, 8
 MAX_COLORS = 1024
 
@@ -33,7 +34,7 @@ class SwasaParams(C.Structure):
         ("population", C.c_int), ("imax", C.c_int), ("iTc", C.c_int), ("delta", C.c_float),
         ("convergence", C.c_int), ("conv_delay", C.c_float), ("conv_spread", C.c_float),
         ("t0", C.c_float), ("alpha", C.c_float), ("s0", C.c_float), ("beta", C.c_float),
-        ("space", C.c_int), ("seed", C.c_int64),
+        ("space", C.c_int), ("seed", C.c_int64), ("cost_model", C.c_int),
     ]
 
 

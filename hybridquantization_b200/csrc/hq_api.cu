@@ -503,6 +503,7 @@ void hq_swasa_default_params(hq_swasa_params* p) {
     p->population = d.populationSize; p->imax = d.imax; p->iTc = d.iTc; p->delta = d.delta;
     p->convergence = d.convEnable ? 1 : 0; p->conv_delay = d.convDelay; p->conv_spread = d.convSpread;
     p->t0 = d.T0; p->alpha = d.alpha; p->s0 = d.s0; p->beta = d.beta; p->space = d.space; p->seed = d.seed;
+    p->cost_model = d.costModel;
 }
 
 int hq_find_best_quantization(hq_ctx* c, int K, const hq_swasa_params* p, uint64_t n_total, float* best_colors,
@@ -515,6 +516,7 @@ int hq_find_best_quantization(hq_ctx* c, int K, const hq_swasa_params* p, uint64
     try {
         hq::ImageManipulation backend(c, false, p->convergence != 0);
         backend.setStopFlag(&c->stop_flag_view);
+        backend.setCostModel(p->cost_model);
         hq::JavaRandom random(p->seed);
         hq::SWASA swasa(p->population, p->imax, p->iTc, p->delta, p->conv_delay, p->conv_spread, p->t0, p->alpha, p->s0, p->beta, &random);
         double err = 0;

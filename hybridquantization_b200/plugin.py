@@ -16,10 +16,10 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _lib
-from ._lib import (EVAL_FORCE_CHUNKED, EVAL_FORCE_DIRECT, EVAL_FORCE_PREFILTER, EVAL_SUMS, SPACE_LAB, SPACE_SRGB, WHITEPOINT_D50,
+from ._lib import (COST_LAB, COST_SCIELAB, EVAL_FORCE_CHUNKED, EVAL_FORCE_DIRECT, EVAL_FORCE_PREFILTER, EVAL_SUMS, SPACE_LAB, SPACE_SRGB, WHITEPOINT_D50,
                    WHITEPOINT_D65, HqError, JavaRandomState, SwasaParams)
 
-__all__ = ["JavaRandom", "SWASA", "ImageManipulation", "ScielabProcessor", "HybridQuantization", "HqError",
+__all__ = ["COST_LAB", "COST_SCIELAB", "JavaRandom", "SWASA", "ImageManipulation", "ScielabProcessor", "HybridQuantization", "HqError",
            "SPACE_LAB", "SPACE_SRGB", "WHITEPOINT_D65", "WHITEPOINT_D50"]
 
 
@@ -52,13 +52,13 @@ class SWASA:
     host driver (hq_find_best_quantization), which uses the same C++ class."""
 
     def __init__(self, population=4, imax=5000, iTc=20, delta=2.0, convDelay=0.75, convSpread=0.15, t0=20.0,
-                 alpha=0.9, s0=100.0, beta=5.3, seed=77760, convergence=True, space=SPACE_LAB):
+                 alpha=0.9, s0=100.0, beta=5.3, seed=77760, convergence=True, space=SPACE_LAB, costModel=COST_LAB):
         p = SwasaParams()
         _lib.load().hq_swasa_default_params(C.byref(p))
         p.population, p.imax, p.iTc, p.delta = population, imax, iTc, delta
         p.convergence, p.conv_delay, p.conv_spread = int(bool(convergence)), convDelay, convSpread
         p.t0, p.alpha, p.s0, p.beta = t0, alpha, s0, beta
-        p.space, p.seed = space, seed
+        p.space, p.seed, p.cost_model = space, seed, costModel
         self.params = p
         self.random = JavaRandom(seed)
 
@@ -334,12 +334,13 @@ class HybridQuantization:
     # added: reproducibility, assignment space, device
     seed: int = 77760
     space: int = SPACE_LAB
+    costModel: int = COST_LAB  # COST_SCIELAB scores exactly like the reference plugin (with space=SPACE_SRGB)
     device: int = 0
     result: dict = field(default_factory=dict, repr=False)
 
     def makeSWASA(self) -> SWASA:
         return SWASA(self.populationSize, self.imax, self.iTc, self.delta, self.ConvDelay, self.ConvSpread, self.T0,
-                     self.alpha, self.s0, self.beta, seed=self.seed, convergence=self.ConvEnable, space=self.space)
+                     self.alpha, self.s0, self.beta, seed=self.seed, convergence=self.ConvEnable, space=self.space, costModel=self.costModel)
 
     def quantization(self, rgb: np.ndarray) -> dict:
         if rgb is None or rgb.size == 0:
@@ -349,6 +350,8 @@ class HybridQuantization:
             swasa = self.makeSWASA()  # :97
             scielabProcessor = ScielabProcessor(self.dpi, self.ViewingDistance, self.WhitePoint, imageProcessor)  # :101
             scielabProcessor.sRGBToScielab(rgb)  # :104
+            if self.costModel == COST_SCIELAB:
+                imageProcessor.scielabConfigure(self.dpi, self.ViewingDistance)  # :101,180
             best, err, _, its = scielabProcessor.bestColors(self.nbOfColors, swasa)  # :107
             q = imageProcessor.quantize(best, self.space)  # :109
             self.result = {"bestColors": best, "bestError": err, "iterations": its, "image": q["rgb"], "idx": q["idx"]}

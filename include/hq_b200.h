@@ -43,6 +43,10 @@ enum { HQ_WHITEPOINT_D65 = 0, HQ_WHITEPOINT_D50 = 1 }; /* ScielabProcessor.java:
  *                score by CIELAB distance (CIEDE/CIE76, cl:209). */
 enum { HQ_SPACE_LAB = 0, HQ_SPACE_SRGB = 1 };
 
+/* what a candidate is scored with: HQ_COST_LAB = sum ||Lab(px) - Lab(P[idx])|| (identity spatial filter,
+ * the accelerated path); HQ_COST_SCIELAB = the reference's full S-CIELAB chain (hq_eval_palettes_scielab) */
+enum { HQ_COST_LAB = 0, HQ_COST_SCIELAB = 1 };
+
 enum {
     HQ_EVAL_SUMS = 1,            /* also reduce per-colour Lab sums */
     HQ_EVAL_FORCE_DIRECT = 2,    /* kernel variant selection, for tests / profiling */
@@ -151,6 +155,7 @@ typedef struct {
     float beta;         /* "Adaptation constant"        :224 (5.3) */
     int space;          /* HQ_SPACE_* (added; default LAB) */
     int64_t seed;       /* java.util.Random seed (added: the reference's RNG is unseeded) */
+    int cost_model;     /* HQ_COST_* (added; default HQ_COST_LAB) */
 } hq_swasa_params;
 void hq_swasa_default_params(hq_swasa_params* p);
 

@@ -150,6 +150,7 @@ public:
         ctx_ = nullptr;
     }
     void setStopFlag(const volatile bool* flag) { stopFlag_ = flag; }
+    void setCostModel(int costModel) { costModel_ = costModel; }  // HQ_COST_LAB | HQ_COST_SCIELAB
 
     // upload + RGB->CIELAB (the uploads of :451,:471-472 and RGBtoXYZ/XYZtoScielab)
     void setImage(const uint8_t* rgb, int w, int rows, int whitepoint) {
@@ -161,8 +162,10 @@ public:
                                                            const SWASA& swasa, uint64_t nTotal, int space) {
         errFx_.resize(populationSize);
         counts_.resize(static_cast<size_t>(populationSize) * nbOfColors);
-        check(hq_eval_palettes(ctx_, colors, populationSize, nbOfColors, space, 0, errFx_.data(), counts_.data(), nullptr),
-              "hq_eval_palettes");
+        if (costModel_ == HQ_COST_SCIELAB)  // the reference's own kernel chain (:635-699)
+            check(hq_eval_palettes_scielab(ctx_, colors, populationSize, nbOfColors, space, errFx_.data(), counts_.data()), "hq_eval_palettes_scielab");
+        else
+            check(hq_eval_palettes(ctx_, colors, populationSize, nbOfColors, space, 0, errFx_.data(), counts_.data(), nullptr), "hq_eval_palettes");
         std::vector<double> results(populationSize);
         for (int i = 0; i < populationSize; ++i) {
             // :712 averageArray(err) + computePenalty(used)
@@ -250,6 +253,7 @@ private:
     hq_ctx* ctx_ = nullptr;
     bool verbose_, convergence_, owns_;
     const volatile bool* stopFlag_ = nullptr;
+    int costModel_ = HQ_COST_LAB;
     std::vector<int64_t> errFx_;
     std::vector<uint64_t> counts_;
 };
@@ -399,6 +403,7 @@ struct HybridQuantization {
     // added (not in the reference): reproducibility + assignment space + device
     int64_t seed = 77760;
     int space = HQ_SPACE_LAB;
+    int costModel = HQ_COST_LAB;  // HQ_COST_SCIELAB = score exactly like the reference plugin (use with HQ_SPACE_SRGB)
     int device = 0;
     volatile bool stopFlag = false;  // :52
 
@@ -413,10 +418,16 @@ struct HybridQuantization {
         stopFlag = false;
         ImageManipulation imageProcessor(ImageManipulation::deltaETypes::CIE76, verbose, convEnable, device);  // :96
         imageProcessor.setStopFlag(&stopFlag);
+        imageProcessor.setCostModel(costModel);
         JavaRandom random(seed);
         SWASA swasa(populationSize, imax, iTc, delta, convDelay, convSpread, T0, alpha, s0, beta, &random);  // :97
         ScielabProcessor scielabProcessor(dpi, viewingDistance, whitePoint, &imageProcessor);               // :101
         scielabProcessor.sRGBToScielab(rgb, w, h);                                                          // :104
+        if (costModel == HQ_COST_SCIELAB) {  // :180 updateOpenCLFilters with the bank built from dpi / viewing distance
+            const std::vector<float> flat = scielabProcessor.filters().flat();
+            if (hq_scielab_set_filters(imageProcessor.context(), flat.data(), scielabProcessor.filters().absOfilters.data(), scielabProcessor.filters().taps()) != HQ_OK)
+                throw std::runtime_error(std::string("hq_scielab_set_filters: ") + hq_last_error(imageProcessor.context()));
+        }
         std::vector<float> best = scielabProcessor.bestColors(nbOfColors, swasa, 0, space, bestError);     // :107
         if (outRgb) imageProcessor.quantize(best.data(), nbOfColors, space, outRgb);                        // :109
         scielabProcessor.close();                                                                           // :136

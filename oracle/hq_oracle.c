@@ -324,7 +324,7 @@ void hqo_swasa_defaults(hqo_swasa_params* p) { /* HybridQuantization.java:192-23
     p->population = 4; p->imax = 5000; p->iTc = 20; p->delta = 2.0f; p->convergence = 1;
     p->conv_delay = 0.75f; p->conv_spread = 0.15f; p->t0 = 20.0f; p->alpha = 0.9f;
     p->s0 = 100.0f; p->beta = 5.3f; p->whitepoint = HQO_WHITE_D65; p->space = HQO_SPACE_LAB;
-    p->seed = 77760;
+    p->seed = 77760; p->cost_model = 0; p->dpi = 72; p->viewing_distance = 45.0f;
 }
 
 /* SWASA.java:40-52 */
@@ -377,12 +377,27 @@ double hqo_find_best_quantization(const uint8_t* rgb, int w, int h, int K,
     double* errs = (double*)malloc(sizeof(double) * P);
     int64_t* err_fx = (int64_t*)malloc(sizeof(int64_t) * P);
     uint64_t* counts = (uint64_t*)malloc(sizeof(uint64_t) * P * K);
+    /* scoring: identity-filter Lab cost, or the reference's full S-CIELAB chain (ImageManipulation.java:635-699) */
+    float *sc_filters = NULL, *sc_abs3 = NULL, *sc_orig = NULL; int sc_taps = 0;
+    if (p->cost_model == 1) {
+        sc_filters = (float*)malloc(sizeof(float) * 7 * 4096); sc_abs3 = (float*)malloc(sizeof(float) * 4096);
+        sc_taps = hqo_scielab_filters(p->dpi, (double)p->viewing_distance, sc_filters, sc_abs3, 4096);
+        sc_orig = (float*)malloc(sizeof(float) * 3 * n);
+        hqo_scielab_image(rgb, w, h, p->whitepoint, sc_filters, sc_abs3, sc_taps, sc_orig, threads);
+    }
+#define EVAL_POPULATION(pal)                                                                                             \
+    do {                                                                                                                 \
+        if (p->cost_model == 1)                                                                                          \
+            hqo_scielab_eval(rgb, w, h, p->whitepoint, sc_filters, sc_abs3, sc_taps, sc_orig, (pal), P, K, p->space, err_fx, counts, threads); \
+        else                                                                                                             \
+            hqo_assign_reduce_planes(unit, lab, n, p->whitepoint, (pal), P, K, p->space, err_fx, counts, NULL, NULL, threads); \
+    } while (0)
     hqo_rng rng;
     hqo_rng_seed(&rng, p->seed);
     float temperature = p->t0; /* SWASA.reset(), :30-34 */
 
     for (int i = 0; i < P; ++i) hqo_generate_random_colors(&rng, K, colors + i * pal); /* :413-417 */
-    hqo_assign_reduce_planes(unit, lab, n, p->whitepoint, colors, P, K, p->space, err_fx, counts, NULL, NULL, threads);
+    EVAL_POPULATION(colors);
     for (int i = 0; i < P; ++i) {
         cur_err[i] = hqo_cost(err_fx[i], counts + (size_t)i * K, K, n, p->delta);
         if (trace_costs) trace_costs[i] = cur_err[i];
@@ -396,7 +411,7 @@ double hqo_find_best_quantization(const uint8_t* rgb, int w, int h, int K,
         if (ite % p->iTc == 0) temperature *= p->alpha; /* SWASA.java:84-89 */
         for (int j = 0; j < P; ++j)                     /* :508-511 */
             hqo_generate_neighboring_colors(p, &rng, colors + j * pal, current + j * pal, K, ite);
-        hqo_assign_reduce_planes(unit, lab, n, p->whitepoint, current, P, K, p->space, err_fx, counts, NULL, NULL, threads);
+        EVAL_POPULATION(current);
         for (int i = 0; i < P; ++i) {
             errs[i] = hqo_cost(err_fx[i], counts + (size_t)i * K, K, n, p->delta);
             if (trace_costs) trace_costs[(size_t)ite * P + i] = errs[i];
@@ -428,6 +443,8 @@ double hqo_find_best_quantization(const uint8_t* rgb, int w, int h, int K,
         }
     }
     free(lab); free(unit); free(colors); free(current); free(cur_err); free(errs); free(err_fx); free(counts);
+    free(sc_filters); free(sc_abs3); free(sc_orig);
+#undef EVAL_POPULATION
     return best_err;
 }
 

@@ -77,6 +77,8 @@ typedef struct {
     float t0, alpha, s0, beta;        /* :212,216,223,224 */
     int whitepoint, space;
     int64_t seed;
+    int cost_model;                   /* 0 Lab / identity filter, 1 full S-CIELAB chain */
+    int dpi; float viewing_distance;  /* HybridQuantization.java:229-231 */
 } hqo_swasa_params;
 void hqo_swasa_defaults(hqo_swasa_params* p);
 

@@ -19,7 +19,8 @@ class SwasaParams(C.Structure):
     _fields_ = [("population", C.c_int), ("imax", C.c_int), ("iTc", C.c_int), ("delta", C.c_float),
                 ("convergence", C.c_int), ("conv_delay", C.c_float), ("conv_spread", C.c_float),
                 ("t0", C.c_float), ("alpha", C.c_float), ("s0", C.c_float), ("beta", C.c_float),
-                ("whitepoint", C.c_int), ("space", C.c_int), ("seed", C.c_int64)]
+                ("whitepoint", C.c_int), ("space", C.c_int), ("seed", C.c_int64),
+                ("cost_model", C.c_int), ("dpi", C.c_int), ("viewing_distance", C.c_float)]
 
 
 class Rng(C.Structure):

@@ -5,7 +5,8 @@ import os
 import numpy as np
 import pytest
 
-from hybridquantization_b200 import SPACE_LAB, SPACE_SRGB, WHITEPOINT_D50, HqError, synth
+from helpers import bits
+from hybridquantization_b200 import COST_SCIELAB, SPACE_LAB, SPACE_SRGB, SWASA, WHITEPOINT_D50, HqError, HybridQuantization, synth
 
 pytestmark = pytest.mark.gpu
 THREADS = max(1, len(os.sched_getaffinity(0)))
@@ -63,3 +64,27 @@ def test_too_small_image_is_rejected(backend):
     with pytest.raises(HqError) as e:
         backend.scielabImage()
     assert e.value.code == 4
+
+
+def test_swasa_with_scielab_cost_matches_oracle(backend, oracle):
+    # the reference configuration: assignment by sRGB distance, S-CIELAB cost, reference defaults (P=4)
+    img = synth.synth_image(128, 96, 11, smooth=True)
+    backend.setImage(img)
+    backend.scielabConfigure(72, 45.0)
+    backend.convergence = True
+    sw = SWASA(population=4, imax=80, seed=555, space=SPACE_SRGB, costModel=COST_SCIELAB)
+    best, err, tr, its = backend.findBestQuantization(12, sw, trace=True)
+    p = oracle.swasa_params(population=4, imax=80, seed=555, space=oracle.SPACE_SRGB, cost_model=1)
+    obest, oerr, otr = oracle.find_best_quantization(img, 12, p, trace=True, threads=THREADS)
+    assert its == 80 and np.array_equal(tr.view(np.uint64), otr.view(np.uint64))
+    assert err == oerr and np.array_equal(bits(best), bits(obest))
+
+
+def test_plugin_entry_with_reference_scoring(oracle):
+    img = synth.synth_image(80, 64, 21, smooth=True)
+    hq = HybridQuantization(nbOfColors=8, populationSize=3, imax=40, seed=9, space=SPACE_SRGB, costModel=COST_SCIELAB, dpi=96, ViewingDistance=60.0)
+    res = hq.quantization(img)
+    p = oracle.swasa_params(population=3, imax=40, seed=9, space=oracle.SPACE_SRGB, cost_model=1, dpi=96, viewing_distance=60.0)
+    obest, oerr, _ = oracle.find_best_quantization(img, 8, p, threads=THREADS)
+    assert res["bestError"] == oerr and np.array_equal(bits(res["bestColors"]), bits(obest))
+    assert np.array_equal(res["image"].reshape(-1, 3), oracle.quantize(img, obest, oracle.SPACE_SRGB)["rgb"])

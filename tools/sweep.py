@@ -107,6 +107,28 @@ def main():
                              "bound": "hbm" if 12.0 * n / (hbm * 1e9) > 8.0 * K * n * B / (p_fp32 * 1e12) else "fp32"}
             out["k_sweep"].append(row)
 
+    # ---- S-CIELAB stage (next row 1): full reference cost chain per candidate, through the host-buffer C ABI
+    out["scielab"] = []
+    for (w, h, K, B) in ((1920, 1080, 256, 4), (3840, 2160, 256, 4), (3840, 2160, 256, 16)):
+        img = synth.synth_image_rows(w, h, synth.SEED_BASE + 2, 0, h)
+        be.setImage(img)
+        be.scielabConfigure(72, 45.0)
+        t0 = time.perf_counter(); be.scielabImage(); t_img = time.perf_counter() - t0
+        pal = synth.synth_palettes(B, K)
+        be.evalPalettesScielab(pal, 1)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            r = be.evalPalettesScielab(pal, 1)
+        dt = (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            be.evalPalettes(pal, 1)
+        dt_plain = (time.perf_counter() - t0) / reps
+        out["scielab"].append({"w": w, "h": h, "K": K, "B": B, "scielab_of_original_s": t_img, "eval_ms": dt * 1e3, "evals_per_s": B / dt,
+                               "gpixel_per_s": B * w * h / dt / 1e9, "identity_filter_eval_ms": dt_plain * 1e3,
+                               "filter_stage_ms_per_candidate": (dt - dt_plain) * 1e3 / B})
+
     # ---- full SWASA runs through the C ABI (host buffers, host annealing loop)
     if not a.skip_swasa:
         out["swasa"] = []
