@@ -77,6 +77,8 @@ struct hq_ctx {
 
     // S-CIELAB stage (next row 1)
     std::vector<float> sc_filters7, sc_abs3;  // [7][taps], [taps] as ScielabProcessor builds them
+    std::vector<float> sc_block;              // [8][taps] device layout, host copy
+    bool sc_generic = false;                  // test hook: force the generic (any-taps) kernels
     int sc_taps = 0;
     bool sc_image_ready = false;
     DevBuf<float> d_sc_filters, d_sc_opp, d_sc_tmp, d_sc_lab;
@@ -373,6 +375,7 @@ static int sc_upload_filters(hq_ctx* c) {
         blk[6 * T + t] = f[2 * T + t];                                                                               // k3 = third Gaussian of O1
         blk[7 * T + t] = c->sc_abs3[t];
     }
+    c->sc_block = blk;
     HQ_CUDA(c, c->d_sc_filters.reserve(blk.size()));
     HQ_CUDA(c, cudaMemcpyAsync(c->d_sc_filters.p, blk.data(), blk.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     HQ_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -396,6 +399,13 @@ int hq_scielab_configure(hq_ctx* c, int dpi, float viewing_distance_cm) {
     const hq::ScielabProcessor::FilterBank bank = hq::ScielabProcessor::buildFilters(dpi, (double)viewing_distance_cm);
     const std::vector<float> flat = bank.flat();
     return hq_scielab_set_filters(c, flat.data(), bank.absOfilters.data(), bank.taps());
+}
+
+int hq_scielab_force_generic(hq_ctx* c, int enabled) {
+    if (!c) return HQ_ERR_INVALID;
+    c->sc_generic = enabled != 0;
+    c->sc_image_ready = false;
+    return HQ_OK;
 }
 
 int hq_scielab_build_filters(int dpi, float viewing_distance_cm, float* filters7, float* abs3, int* taps) {
@@ -435,8 +445,8 @@ static int sc_ensure_image(hq_ctx* c) {
     HQ_CUDA(c, c->d_sc_tmp.reserve(7 * c->stride));
     HQ_CUDA(c, c->d_sc_lab.reserve(3 * c->stride));
     HQ_CUDA(c, hq::launch_sc_rgb_to_opp(c->d_rgb.p, c->n, c->stride, c->d_table.p, c->d_sc_opp.p, c->stream));
-    HQ_CUDA(c, hq::launch_sc_original(c->d_sc_opp.p, c->width, c->rows, c->stride, c->d_sc_filters.p, c->sc_taps, c->whitepoint,
-                                      c->d_sc_tmp.p, c->d_sc_lab.p, c->stream));
+    HQ_CUDA(c, hq::launch_sc_original(c->d_sc_opp.p, c->width, c->rows, c->stride, c->d_sc_filters.p, c->sc_generic ? nullptr : c->sc_block.data(), c->sc_taps,
+                                      c->whitepoint, c->d_sc_tmp.p, c->d_sc_lab.p, c->stream));
     c->sc_image_ready = true;
     return HQ_OK;
 }
@@ -478,7 +488,8 @@ int hq_eval_palettes_scielab(hq_ctx* c, const float* palettes, int B, int K, int
     for (int b = 0; b < B; ++b) {
         const uint8_t* idx_b = c->d_idx.p + (size_t)b * c->stride * (idx16 ? 2 : 1);
         HQ_CUDA(c, hq::launch_sc_candidate(idx_b, idx16, c->d_sc_tab.p + (size_t)b * K, c->width, c->rows, c->stride, c->d_sc_filters.p,
-                                           c->sc_taps, c->whitepoint, c->d_sc_tmp.p, c->d_sc_lab.p, c->d_sc_err.p + b, c->stream));
+                                           c->sc_generic ? nullptr : c->sc_block.data(), c->sc_taps, c->whitepoint, c->d_sc_tmp.p, c->d_sc_lab.p,
+                                           c->d_sc_err.p + b, c->stream));
     }
     HQ_CUDA(c, cudaMemcpyAsync(c->h_results.p, c->d_results.p, nwords * 8, cudaMemcpyDeviceToHost, c->stream));
     HQ_CUDA(c, cudaMemcpyAsync(c->h_results.p + nwords, c->d_sc_err.p, (size_t)B * 8, cudaMemcpyDeviceToHost, c->stream));

@@ -59,11 +59,14 @@ constexpr int kMaxScielabTaps = 255;
 cudaError_t launch_sc_rgb_to_opp(const uint8_t* d_rgb, size_t n, size_t stride, const float* d_table, float* d_opp, cudaStream_t st);
 cudaError_t launch_sc_palette_opp(const float* d_palettes, int total, float4* d_tab, cudaStream_t st);
 // original image: opp planes -> S-CIELAB Lab planes (d_tmp: 7 planes of scratch)
-cudaError_t launch_sc_original(const float* d_opp, int w, int h, size_t stride, const float* d_filters, int taps, int whitepoint,
-                               float* d_tmp, float* d_lab_out, cudaStream_t st);
+// h_filters: the same block on the host (nullptr = always use the generic kernels); with taps == 21
+// (plugin defaults) the specialised kernels take it as a kernel parameter
+cudaError_t launch_sc_original(const float* d_opp, int w, int h, size_t stride, const float* d_filters, const float* h_filters, int taps,
+                               int whitepoint, float* d_tmp, float* d_lab_out, cudaStream_t st);
 // one candidate: index image + opponent table -> fixed-point sum of dE against d_lab_orig, added to *d_err
 cudaError_t launch_sc_candidate(const void* d_idx, bool idx16, const float4* d_tab, int w, int h, size_t stride, const float* d_filters,
-                                int taps, int whitepoint, float* d_tmp, const float* d_lab_orig, unsigned long long* d_err, cudaStream_t st);
+                                const float* h_filters, int taps, int whitepoint, float* d_tmp, const float* d_lab_orig,
+                                unsigned long long* d_err, cudaStream_t st);
 
 // FFMA-saturating probe: `iters` x 32 dependent-chain FMAs per thread (8 chains), scalar or packed
 cudaError_t launch_fp32_peak(bool packed, int iters, int sm_count, float* d_out, cudaStream_t stream);

@@ -128,6 +128,136 @@ sc_vpass_kernel(const float* __restrict__ tmp, int w, int h, size_t stride, ScFi
     }
 }
 
+// ---------------------------------------------------------------- specialised kernels, taps = 21
+// (the plugin's default geometry: dpi 72, 45 cm).  Same arithmetic and tap order as the generic
+// kernels above; the filter bank travels as a kernel parameter so every coefficient is a constant-bank
+// operand of its FFMA, inputs are staged once in shared memory (horizontal) or streamed through a
+// register sliding window (vertical), so each value is loaded ~1.3x / 3.5x instead of 21x.
+constexpr int kT = 21, kHalf = 10;
+struct Filt21 { float v[8 * kT]; };  // k1[t][3], k2[t][3], k3[t], |k3|[t]
+
+constexpr int kHOut = 4;                          // outputs per thread (horizontal)
+constexpr int kHSeg = kScThreads * kHOut;         // 1024 pixels of one row per CTA
+
+template <int MODE, typename IdxT>
+__global__ void __launch_bounds__(kScThreads)
+sc_hpass21_kernel(const float* __restrict__ opp, const IdxT* __restrict__ idx, const float4* __restrict__ tab,
+                  int w, int h, size_t stride, const __grid_constant__ Filt21 f, float* __restrict__ tmp) {
+    __shared__ float s_in[3][kHSeg + 2 * kHalf];
+    const int x0 = blockIdx.x * kHSeg, y = blockIdx.y;
+    const size_t row = (size_t)y * w;
+    for (int i = threadIdx.x; i < kHSeg + 2 * kHalf; i += kScThreads) {
+        const int xx = x0 - kHalf + i;
+        float i0 = 0.f, i1 = 0.f, i2 = 0.f;
+        if (xx < w + kHalf) {  // positions beyond the last output's right halo are never used
+            const size_t p = row + hq_reflect(xx, w);
+            if (MODE == 0) { i0 = __ldg(opp + p); i1 = __ldg(opp + stride + p); i2 = __ldg(opp + 2 * stride + p); }
+            else { const float4 v = __ldg(tab + idx[p]); i0 = v.x; i1 = v.y; i2 = v.z; }
+        }
+        s_in[0][i] = i0; s_in[1][i] = i1; s_in[2][i] = i2;
+    }
+    __syncthreads();
+    const int lx = threadIdx.x * kHOut;
+    if (x0 + lx >= w) return;
+    float acc[kHOut][7];
+#pragma unroll
+    for (int o = 0; o < kHOut; ++o)
+#pragma unroll
+        for (int c = 0; c < 7; ++c) acc[o][c] = 0.f;
+    float win[3][kHOut + kT - 1];
+#pragma unroll
+    for (int i = 0; i < kHOut + kT - 1; ++i) { win[0][i] = s_in[0][lx + i]; win[1][i] = s_in[1][lx + i]; win[2][i] = s_in[2][lx + i]; }
+#pragma unroll
+    for (int t = 0; t < kT; ++t)
+#pragma unroll
+        for (int o = 0; o < kHOut; ++o) {
+            const float i0 = win[0][o + t], i1 = win[1][o + t], i2 = win[2][o + t];
+            acc[o][0] = HQ_FFMA(i0, f.v[3 * t], acc[o][0]); acc[o][1] = HQ_FFMA(i1, f.v[3 * t + 1], acc[o][1]); acc[o][2] = HQ_FFMA(i2, f.v[3 * t + 2], acc[o][2]);
+            acc[o][3] = HQ_FFMA(i0, f.v[3 * kT + 3 * t], acc[o][3]); acc[o][4] = HQ_FFMA(i1, f.v[3 * kT + 3 * t + 1], acc[o][4]); acc[o][5] = HQ_FFMA(i2, f.v[3 * kT + 3 * t + 2], acc[o][5]);
+            acc[o][6] = HQ_FFMA(i0, f.v[6 * kT + t], acc[o][6]);
+        }
+    const size_t o0 = row + x0 + lx;
+    if (x0 + lx + kHOut <= w && ((row + x0 + lx) & 3) == 0) {
+#pragma unroll
+        for (int c = 0; c < 7; ++c)
+            *reinterpret_cast<float4*>(tmp + c * stride + o0) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+    } else {
+#pragma unroll
+        for (int o = 0; o < kHOut; ++o)
+            if (x0 + lx + o < w)
+#pragma unroll
+                for (int c = 0; c < 7; ++c) tmp[c * stride + o0 + o] = acc[o][c];
+    }
+}
+
+constexpr int kVRows = 8;  // output rows per thread (vertical): 28 input rows stream through registers
+
+template <int MODE>
+__global__ void __launch_bounds__(kScThreads)
+sc_vpass21_kernel(const float* __restrict__ tmp, int w, int h, size_t stride, const __grid_constant__ Filt21 f, hq_float3 ill,
+                  float* __restrict__ lab_out, const float* __restrict__ lab_orig, unsigned long long* __restrict__ err_out) {
+    const int x = blockIdx.x * kScThreads + threadIdx.x, y0 = blockIdx.y * kVRows;
+    long long fx = 0;
+    if (x < w) {
+        float a[kVRows][3], b[kVRows][3], c3[kVRows];
+#pragma unroll
+        for (int o = 0; o < kVRows; ++o) { a[o][0] = a[o][1] = a[o][2] = 0.f; b[o][0] = b[o][1] = b[o][2] = 0.f; c3[o] = 0.f; }
+#pragma unroll
+        for (int r = 0; r < kVRows + kT - 1; ++r) {
+            const size_t p = (size_t)hq_reflect(y0 - kHalf + r, h) * w + x;  // rows past the image are reflected; unused outputs are discarded
+            const float t10 = __ldg(tmp + p), t11 = __ldg(tmp + stride + p), t12 = __ldg(tmp + 2 * stride + p);
+            const float t20 = __ldg(tmp + 3 * stride + p), t21 = __ldg(tmp + 4 * stride + p), t22 = __ldg(tmp + 5 * stride + p);
+            const float t3 = __ldg(tmp + 6 * stride + p);
+#pragma unroll
+            for (int o = 0; o < kVRows; ++o) {
+                const int t = r - o;  // tap index of input row r for output row o: ascending in r, i.e. the reference's order
+                if (t >= 0 && t < kT) {
+                    if (MODE == 0) {
+                        a[o][0] = HQ_FFMA(t10, f.v[3 * t], a[o][0]); a[o][1] = HQ_FFMA(t11, f.v[3 * t + 1], a[o][1]); a[o][2] = HQ_FFMA(t12, f.v[3 * t + 2], a[o][2]);
+                        b[o][0] = HQ_FFMA(t20, f.v[3 * kT + 3 * t], b[o][0]); b[o][1] = HQ_FFMA(t21, f.v[3 * kT + 3 * t + 1], b[o][1]); b[o][2] = HQ_FFMA(t22, f.v[3 * kT + 3 * t + 2], b[o][2]);
+                        c3[o] = HQ_FFMA(t3, f.v[7 * kT + t], c3[o]);
+                    } else {
+                        a[o][0] = HQ_FFMA(t10, f.v[3 * t], HQ_FFMA(t20, f.v[3 * kT + 3 * t], a[o][0]));
+                        a[o][1] = HQ_FFMA(t11, f.v[3 * t + 1], HQ_FFMA(t21, f.v[3 * kT + 3 * t + 1], a[o][1]));
+                        a[o][2] = HQ_FFMA(t12, f.v[3 * t + 2], HQ_FFMA(t22, f.v[3 * kT + 3 * t + 2], a[o][2]));
+                        a[o][0] = HQ_FFMA(t3, f.v[7 * kT + t], a[o][0]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < kVRows; ++o) {
+            const int y = y0 + o;
+            if (y < h) {
+                float o0, o1, o2;
+                if (MODE == 0) { o0 = HQ_FADD(HQ_FADD(a[o][0], b[o][0]), c3[o]); o1 = HQ_FADD(a[o][1], b[o][1]); o2 = HQ_FADD(a[o][2], b[o][2]); }
+                else { o0 = a[o][0]; o1 = a[o][1]; o2 = a[o][2]; }
+                const hq_float3 lab = hq_cl_opp_to_lab(o0, o1, o2, ill);
+                const size_t p = (size_t)y * w + x;
+                if (MODE == 0) {
+                    lab_out[p] = lab.x; lab_out[stride + p] = lab.y; lab_out[2 * stride + p] = lab.z;
+                } else {
+                    const float d2 = hq_dist2(__ldg(lab_orig + p), __ldg(lab_orig + stride + p), __ldg(lab_orig + 2 * stride + p), lab.x, lab.y, lab.z);
+                    fx += hq_to_fx(HQ_FSQRT(d2));
+                }
+            }
+        }
+    }
+    if (MODE == 1) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) fx += __shfl_down_sync(0xffffffffu, fx, off);
+        __shared__ long long s_err[kScThreads / 32];
+        if ((threadIdx.x & 31) == 0) s_err[threadIdx.x >> 5] = fx;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long e = 0;
+#pragma unroll
+            for (int i = 0; i < kScThreads / 32; ++i) e += s_err[i];
+            if (e) atomicAdd(err_out, (unsigned long long)e);
+        }
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_sc_rgb_to_opp(const uint8_t* d_rgb, size_t n, size_t stride, const float* d_table, float* d_opp, cudaStream_t st) {
@@ -142,9 +272,17 @@ cudaError_t launch_sc_palette_opp(const float* d_palettes, int total, float4* d_
     return cudaGetLastError();
 }
 
-cudaError_t launch_sc_original(const float* d_opp, int w, int h, size_t stride, const float* d_filters, int taps, int whitepoint,
-                               float* d_tmp, float* d_lab_out, cudaStream_t st) {
+cudaError_t launch_sc_original(const float* d_opp, int w, int h, size_t stride, const float* d_filters, const float* h_filters, int taps,
+                               int whitepoint, float* d_tmp, float* d_lab_out, cudaStream_t st) {
     if (w == 0 || h == 0) return cudaSuccess;
+    if (taps == kT && h_filters) {
+        Filt21 f21;
+        for (int i = 0; i < 8 * kT; ++i) f21.v[i] = h_filters[i];
+        const dim3 gh((unsigned)((w + kHSeg - 1) / kHSeg), (unsigned)h), gv((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)((h + kVRows - 1) / kVRows));
+        sc_hpass21_kernel<0, uint8_t><<<gh, kScThreads, 0, st>>>(d_opp, nullptr, nullptr, w, h, stride, f21, d_tmp);
+        sc_vpass21_kernel<0><<<gv, kScThreads, 0, st>>>(d_tmp, w, h, stride, f21, hq_whitepoint(whitepoint), d_lab_out, nullptr, nullptr);
+        return cudaGetLastError();
+    }
     const ScFilters f{d_filters, taps};
     const dim3 grid((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)h);
     sc_hpass_kernel<0, uint8_t><<<grid, kScThreads, 7 * taps * sizeof(float), st>>>(d_opp, nullptr, nullptr, w, h, stride, f, d_tmp);
@@ -153,8 +291,18 @@ cudaError_t launch_sc_original(const float* d_opp, int w, int h, size_t stride, 
 }
 
 cudaError_t launch_sc_candidate(const void* d_idx, bool idx16, const float4* d_tab, int w, int h, size_t stride, const float* d_filters,
-                                int taps, int whitepoint, float* d_tmp, const float* d_lab_orig, unsigned long long* d_err, cudaStream_t st) {
+                                const float* h_filters, int taps, int whitepoint, float* d_tmp, const float* d_lab_orig,
+                                unsigned long long* d_err, cudaStream_t st) {
     if (w == 0 || h == 0) return cudaSuccess;
+    if (taps == kT && h_filters) {
+        Filt21 f21;
+        for (int i = 0; i < 8 * kT; ++i) f21.v[i] = h_filters[i];
+        const dim3 gh((unsigned)((w + kHSeg - 1) / kHSeg), (unsigned)h), gv((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)((h + kVRows - 1) / kVRows));
+        if (idx16) sc_hpass21_kernel<1, uint16_t><<<gh, kScThreads, 0, st>>>(nullptr, static_cast<const uint16_t*>(d_idx), d_tab, w, h, stride, f21, d_tmp);
+        else sc_hpass21_kernel<1, uint8_t><<<gh, kScThreads, 0, st>>>(nullptr, static_cast<const uint8_t*>(d_idx), d_tab, w, h, stride, f21, d_tmp);
+        sc_vpass21_kernel<1><<<gv, kScThreads, 0, st>>>(d_tmp, w, h, stride, f21, hq_whitepoint(whitepoint), nullptr, d_lab_orig, d_err);
+        return cudaGetLastError();
+    }
     const ScFilters f{d_filters, taps};
     const dim3 grid((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)h);
     if (idx16) sc_hpass_kernel<1, uint16_t><<<grid, kScThreads, 7 * taps * sizeof(float), st>>>(nullptr, static_cast<const uint16_t*>(d_idx), d_tab, w, h, stride, f, d_tmp);

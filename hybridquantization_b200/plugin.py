@@ -213,6 +213,9 @@ class ImageManipulation:
         filters7 = np.ascontiguousarray(filters7, np.float32); abs3 = np.ascontiguousarray(abs3, np.float32)
         _lib.check(self._ctx, self._lib.hq_scielab_set_filters(self._ctx, _ptr(filters7), _ptr(abs3), filters7.shape[1]))
 
+    def scielabForceGeneric(self, enabled: bool) -> None:
+        _lib.check(self._ctx, self._lib.hq_scielab_force_generic(self._ctx, int(enabled)))
+
     def scielabFilters(self):
         taps = C.c_int(0)
         _lib.check(self._ctx, self._lib.hq_scielab_get_filters(self._ctx, None, None, C.byref(taps)))

@@ -125,6 +125,8 @@ int hq_scielab_set_filters(hq_ctx* ctx, const float* filters7, const float* abs3
 /* *taps: in = capacity of the arrays (entries per filter), out = actual taps */
 int hq_scielab_get_filters(const hq_ctx* ctx, float* filters7, float* abs3, int* taps);
 int hq_scielab_get_image(hq_ctx* ctx, float* planes);
+/* test hook: 1 = always run the generic any-tap-count kernels instead of the 21-tap specialisation */
+int hq_scielab_force_generic(hq_ctx* ctx, int enabled);
 /* host only (no GPU needed): the filter bank for (dpi, viewing distance); *taps as above */
 int hq_scielab_build_filters(int dpi, float viewing_distance_cm, float* filters7, float* abs3, int* taps);
 int hq_eval_palettes_scielab(hq_ctx* ctx, const float* palettes, int B, int K, int space,

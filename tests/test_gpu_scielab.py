@@ -39,6 +39,23 @@ def test_scielab_candidate_costs_match_oracle(backend, oracle, K, space):
     assert np.array_equal(got["counts"], want["counts"])
 
 
+def test_generic_and_specialised_kernels_agree(backend, oracle):
+    # taps == 21 runs the specialised kernels; the generic ones must give the same integers
+    for (w, h) in ((1037, 53), (64, 300), (2051, 19)):
+        img = synth.synth_image(w, h, 3, smooth=True)
+        pal = synth.synth_palettes(2, 24)
+        backend.setImage(img)
+        backend.scielabConfigure(72, 45.0)
+        res = []
+        for generic in (False, True):
+            backend.scielabForceGeneric(generic)
+            res.append((backend.scielabImage().view(np.uint32).copy(), backend.evalPalettesScielab(pal)["err_fx"].copy()))
+        backend.scielabForceGeneric(False)
+        assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+        of, oa = oracle.scielab_filters(72, 45.0)
+        assert np.array_equal(res[0][0], oracle.scielab_image(img, of, oa, 0, THREADS).view(np.uint32))
+
+
 def test_other_viewing_conditions_and_custom_filters(backend, oracle):
     img = synth.synth_image(160, 120, 9, smooth=True)
     pal = synth.synth_palettes(2, 12)
