@@ -81,7 +81,8 @@ struct hq_ctx {
     bool sc_generic = false;                  // test hook: force the generic (any-taps) kernels
     int sc_taps = 0;
     bool sc_image_ready = false;
-    DevBuf<float> d_sc_filters, d_sc_opp, d_sc_tmp, d_sc_lab;
+    DevBuf<float> d_sc_filters, d_sc_opp, d_sc_tmp, d_sc_lab, d_sc_lab2, d_sc_map;
+    DevBuf<uint8_t> d_sc_rgb2, d_sc_map8;
     DevBuf<float4> d_sc_tab;
     DevBuf<unsigned long long> d_sc_err;
 
@@ -221,6 +222,7 @@ void hq_destroy(hq_ctx* c) {
     c->d_pal_lab.release(); c->d_pal_rgb.release(); c->d_results.release(); c->d_idx.release();
     c->d_out_rgb.release(); c->d_out_f32.release(); c->h_pal.release(); c->h_results.release();
     c->d_sc_filters.release(); c->d_sc_opp.release(); c->d_sc_tmp.release(); c->d_sc_lab.release(); c->d_sc_tab.release(); c->d_sc_err.release();
+    c->d_sc_lab2.release(); c->d_sc_map.release(); c->d_sc_rgb2.release(); c->d_sc_map8.release();
     delete c;
 }
 
@@ -458,6 +460,34 @@ int hq_scielab_get_image(hq_ctx* c, float* planes) {
     for (int pl = 0; pl < 3 && c->n; ++pl)
         HQ_CUDA(c, cudaMemcpyAsync(planes + (size_t)pl * c->n, c->d_sc_lab.p + (size_t)pl * c->stride, c->n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     HQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HQ_OK;
+}
+
+// error-image mode: HybridQuantization.errorImage (:139-182) + ImageManipulation.computeError (:858-894)
+int hq_error_image(hq_ctx* c, const uint8_t* quantized_rgb, float* error_map, uint8_t* error_map_u8, double* mean_de) {
+    if (!c || !quantized_rgb) return c ? fail(c, HQ_ERR_INVALID, "quantized_rgb is NULL") : HQ_ERR_INVALID;
+    int rc = bind_device(c); if (rc) return rc;
+    rc = sc_ensure_image(c); if (rc) return rc;
+    const size_t n = c->n;
+    HQ_CUDA(c, c->d_sc_rgb2.reserve(n * 3 > 0 ? n * 3 : 1));
+    HQ_CUDA(c, c->d_sc_lab2.reserve(3 * c->stride));
+    HQ_CUDA(c, c->d_sc_err.reserve(1));
+    if (error_map) HQ_CUDA(c, c->d_sc_map.reserve(n ? n : 1));
+    if (error_map_u8) HQ_CUDA(c, c->d_sc_map8.reserve(n ? n : 1));
+    HQ_CUDA(c, cudaMemcpyAsync(c->d_sc_rgb2.p, quantized_rgb, n * 3, cudaMemcpyHostToDevice, c->stream));
+    // S-CIELAB of the second image through the same route as the original (sRGBToScielab, ScielabProcessor.java:374-381)
+    HQ_CUDA(c, hq::launch_sc_rgb_to_opp(c->d_sc_rgb2.p, n, c->stride, c->d_table.p, c->d_sc_opp.p, c->stream));
+    HQ_CUDA(c, hq::launch_sc_original(c->d_sc_opp.p, c->width, c->rows, c->stride, c->d_sc_filters.p, c->sc_generic ? nullptr : c->sc_block.data(),
+                                      c->sc_taps, c->whitepoint, c->d_sc_tmp.p, c->d_sc_lab2.p, c->stream));
+    HQ_CUDA(c, cudaMemsetAsync(c->d_sc_err.p, 0, 8, c->stream));
+    HQ_CUDA(c, hq::launch_sc_error_image(c->d_sc_lab.p, c->d_sc_lab2.p, n, c->stride, error_map ? c->d_sc_map.p : nullptr,
+                                         error_map_u8 ? c->d_sc_map8.p : nullptr, c->d_sc_err.p, c->stream));
+    unsigned long long sum = 0;
+    HQ_CUDA(c, cudaMemcpyAsync(&sum, c->d_sc_err.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    if (error_map && n) HQ_CUDA(c, cudaMemcpyAsync(error_map, c->d_sc_map.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (error_map_u8 && n) HQ_CUDA(c, cudaMemcpyAsync(error_map_u8, c->d_sc_map8.p, n, cudaMemcpyDeviceToHost, c->stream));
+    HQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (mean_de) *mean_de = n ? ((double)(int64_t)sum * (1.0 / 16777216.0)) / (double)n : 0.0;  // :893 error/errorArray.length
     return HQ_OK;
 }
 

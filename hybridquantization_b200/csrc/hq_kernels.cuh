@@ -68,6 +68,10 @@ cudaError_t launch_sc_candidate(const void* d_idx, bool idx16, const float4* d_t
                                 const float* h_filters, int taps, int whitepoint, float* d_tmp, const float* d_lab_orig,
                                 unsigned long long* d_err, cudaStream_t st);
 
+// error-image mode: dE map between two S-CIELAB images + fixed-point sum
+cudaError_t launch_sc_error_image(const float* d_lab_a, const float* d_lab_b, size_t n, size_t stride, float* d_map, uint8_t* d_map_u8,
+                                  unsigned long long* d_err, cudaStream_t st);
+
 // FFMA-saturating probe: `iters` x 32 dependent-chain FMAs per thread (8 chains), scalar or packed
 cudaError_t launch_fp32_peak(bool packed, int iters, int sm_count, float* d_out, cudaStream_t stream);
 

@@ -258,7 +258,43 @@ sc_vpass21_kernel(const float* __restrict__ tmp, int w, int h, size_t stride, co
     }
 }
 
+// error-image mode (ImageManipulation.computeError :858-894): dE between two S-CIELAB images, the
+// map value ((255 - dE)^2) / (255*255) (:890) and the fixed-point sum of dE
+__global__ void sc_error_image_kernel(const float* __restrict__ lab_a, const float* __restrict__ lab_b, size_t n, size_t stride,
+                                      float* __restrict__ map_out, uint8_t* __restrict__ map_u8, unsigned long long* __restrict__ err_out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    long long fx = 0;
+    if (i < n) {
+        const float e = HQ_FSQRT(hq_dist2(lab_a[i], lab_a[stride + i], lab_a[2 * stride + i], lab_b[i], lab_b[stride + i], lab_b[2 * stride + i]));
+        const float d = HQ_FSUB(255.0f, e);
+        const float v = HQ_FDIV(HQ_FMUL(d, d), 65025.0f);
+        if (map_out) map_out[i] = v;
+        if (map_u8) {
+            const float q = HQ_FADD(HQ_FMUL(v, 255.0f), 0.5f);
+            map_u8[i] = (uint8_t)__float2int_rz(fminf(fmaxf(q, 0.0f), 255.0f));
+        }
+        fx = hq_to_fx(e);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) fx += __shfl_down_sync(0xffffffffu, fx, off);
+    __shared__ long long s_err[8];
+    if ((threadIdx.x & 31) == 0) s_err[threadIdx.x >> 5] = fx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long e = 0;
+        for (int k = 0; k < 8; ++k) e += s_err[k];
+        if (e) atomicAdd(err_out, (unsigned long long)e);
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_sc_error_image(const float* d_lab_a, const float* d_lab_b, size_t n, size_t stride, float* d_map, uint8_t* d_map_u8,
+                                  unsigned long long* d_err, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    sc_error_image_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_lab_a, d_lab_b, n, stride, d_map, d_map_u8, d_err);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_sc_rgb_to_opp(const uint8_t* d_rgb, size_t n, size_t stride, const float* d_table, float* d_opp, cudaStream_t st) {
     if (n == 0) return cudaSuccess;

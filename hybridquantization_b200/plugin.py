@@ -238,6 +238,19 @@ class ImageManipulation:
         _lib.check(self._ctx, self._lib.hq_eval_palettes_scielab(self._ctx, _ptr(palettes), B, K, space, _ptr(err), _ptr(counts)))
         return {"err_fx": err, "counts": counts}
 
+    def computeError(self, quantized_rgb: np.ndarray) -> dict:
+        """Error-image mode (ImageManipulation.computeError :858-894): mean dE between S-CIELAB(original) and
+        S-CIELAB(quantized) and the ((255-dE)^2)/255^2 map."""
+        q = np.ascontiguousarray(quantized_rgb, np.uint8)
+        if q.size != self.pixels() * 3:
+            raise ValueError("Mismatching image sizes or not enough channels, abort.")  # HybridQuantization.java:81
+        emap = np.empty(self.pixels(), np.float32); e8 = np.empty(self.pixels(), np.uint8)
+        mean = C.c_double()
+        _lib.check(self._ctx, self._lib.hq_error_image(self._ctx, _ptr(q), _ptr(emap), _ptr(e8), C.byref(mean)))
+        if self.shape is not None:
+            emap, e8 = emap.reshape(self.shape), e8.reshape(self.shape)
+        return {"deltaE": mean.value, "errorImage": emap, "errorImageU8": e8}
+
     def setAllreduce(self, fn) -> None:
         """fn(d_words_ptr: int, n_words: int, stream: int) -> 0 on success; None removes the hook."""
         if fn is None:
@@ -340,6 +353,22 @@ class HybridQuantization:
     costModel: int = COST_LAB  # COST_SCIELAB scores exactly like the reference plugin (with space=SPACE_SRGB)
     device: int = 0
     result: dict = field(default_factory=dict, repr=False)
+
+    def errorImage(self, original: np.ndarray, quantized: np.ndarray) -> dict:
+        """HybridQuantization.errorImage (:139-182): S-CIELAB dE image between two images."""
+        if original is None or original.size == 0:
+            raise ValueError("Please open/select the original image first.")  # :76-77
+        if quantized is None or quantized.size == 0:
+            raise ValueError("Please open/select the quantized image first.")  # :78-79
+        if original.shape != quantized.shape or original.shape[-1] < 3:
+            raise ValueError("Mismatching image sizes or not enough channels, abort.")  # :80-81
+        imageProcessor = ImageManipulation("CIE76", self.Verbose, False, self.device)  # :145
+        try:
+            imageProcessor.setImage(original, WHITEPOINT_D50 if self.WhitePoint == "D50" else WHITEPOINT_D65)
+            imageProcessor.scielabConfigure(self.dpi, self.ViewingDistance)  # :146
+            return imageProcessor.computeError(quantized)  # :153,160
+        finally:
+            imageProcessor.close()
 
     def makeSWASA(self) -> SWASA:
         return SWASA(self.populationSize, self.imax, self.iTc, self.delta, self.ConvDelay, self.ConvSpread, self.T0,

@@ -125,6 +125,11 @@ int hq_scielab_set_filters(hq_ctx* ctx, const float* filters7, const float* abs3
 /* *taps: in = capacity of the arrays (entries per filter), out = actual taps */
 int hq_scielab_get_filters(const hq_ctx* ctx, float* filters7, float* abs3, int* taps);
 int hq_scielab_get_image(hq_ctx* ctx, float* planes);
+/* error-image mode (scope row "next 2"): HybridQuantization.errorImage (HybridQuantization.java:139-182)
+ * + ImageManipulation.computeError (ImageManipulation.java:858-894).  quantized_rgb: packed u8 image of
+ * the resident image's size.  error_map [n] = ((255 - dE)^2)/(255*255) (:890), error_map_u8 [n] its
+ * 8-bit rendering, *mean_de = mean dE between the two S-CIELAB images.  Outputs may be NULL. */
+int hq_error_image(hq_ctx* ctx, const uint8_t* quantized_rgb, float* error_map, uint8_t* error_map_u8, double* mean_de);
 /* test hook: 1 = always run the generic any-tap-count kernels instead of the 21-tap specialisation */
 int hq_scielab_force_generic(hq_ctx* ctx, int enabled);
 /* host only (no GPU needed): the filter bank for (dpi, viewing distance); *taps as above */

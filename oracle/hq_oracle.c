@@ -708,6 +708,26 @@ void hqo_scielab_eval(const uint8_t* rgb, int w, int h, int whitepoint, const fl
     free(idx); free(k1); free(k2); free(tab); free(c.t1); free(c.t2); free(c.t3); free(c.t_err);
 }
 
+/* error-image mode: ImageManipulation.computeError (:858-894) on two S-CIELAB images */
+double hqo_error_image(const uint8_t* rgb_a, const uint8_t* rgb_b, int w, int h, int whitepoint, const float* filters, const float* abs3,
+                       int taps, float* error_map, uint8_t* error_map_u8, int threads) {
+    const size_t n = (size_t)w * h;
+    float* la = (float*)malloc(sizeof(float) * 3 * n); float* lb = (float*)malloc(sizeof(float) * 3 * n);
+    hqo_scielab_image(rgb_a, w, h, whitepoint, filters, abs3, taps, la, threads);
+    hqo_scielab_image(rgb_b, w, h, whitepoint, filters, abs3, taps, lb, threads);
+    int64_t sum = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const float e = sqrtf(dist2(la[i], la[n + i], la[2 * n + i], lb[i], lb[n + i], lb[2 * n + i])); /* cl:209 */
+        const float d = 255.0f - e;
+        const float v = (d * d) / 65025.0f; /* :890 ((255-e)*(255-e))/(255*255) */
+        if (error_map) error_map[i] = v;
+        if (error_map_u8) { float q = v * 255.0f + 0.5f; q = q < 0 ? 0 : (q > 255 ? 255 : q); error_map_u8[i] = (uint8_t)(int)q; }
+        sum += to_fx(e);
+    }
+    free(la); free(lb);
+    return n ? ((double)sum * (1.0 / 16777216.0)) / (double)n : 0.0;
+}
+
 /* ------------------------------------------------------------------ range evaluation (tests) */
 typedef struct { int which; uint32_t first; float* out; } mrange_ctx;
 static void mrange_fn(void* p, size_t lo, size_t hi, int tid) {

@@ -106,6 +106,10 @@ void hqo_scielab_eval(const uint8_t* rgb, int w, int h, int whitepoint, const fl
                       const float* scielab_orig, const float* palettes, int B, int K, int space, int64_t* err_fx,
                       uint64_t* counts, int threads);
 
+/* error-image mode (ImageManipulation.computeError :858-894): returns mean dE; maps optional */
+double hqo_error_image(const uint8_t* rgb_a, const uint8_t* rgb_b, int w, int h, int whitepoint, const float* filters, const float* abs3,
+                       int taps, float* error_map, uint8_t* error_map_u8, int threads);
+
 /* tests: evaluate which (0 cube-root pow, 1 pow 2.4f, 2 sRGB decode) over consecutive float bit patterns */
 void hqo_math_range(int which, uint32_t first_bits, uint32_t count, float* out, int threads);
 

@@ -71,6 +71,8 @@ def load() -> C.CDLL:
         L.hqo_scielab_filters.restype = C.c_int; L.hqo_scielab_filters.argtypes = [C.c_int, C.c_double, _P, _P, C.c_int]
         L.hqo_scielab_image.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, C.c_int]
         L.hqo_scielab_eval.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int]
+        L.hqo_error_image.restype = C.c_double
+        L.hqo_error_image.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int]
         _lib = L
     return _lib
 
@@ -193,3 +195,13 @@ def scielab_eval(rgb_u8, filters, abs3, scielab_orig, palettes, space=SPACE_SRGB
     load().hqo_scielab_eval(_ptr(rgb), w, h, whitepoint, _ptr(filters), _ptr(abs3), filters.shape[1], _ptr(so), _ptr(palettes), B, K, space,
                             _ptr(err), _ptr(counts), threads or default_threads())
     return {"err_fx": err, "counts": counts}
+
+
+def error_image(rgb_a, rgb_b, filters, abs3, whitepoint=WHITE_D65, threads=None):
+    a = np.ascontiguousarray(rgb_a, np.uint8); b = np.ascontiguousarray(rgb_b, np.uint8)
+    h, w = a.shape[:2]
+    emap = np.empty(h * w, np.float32); e8 = np.empty(h * w, np.uint8)
+    filters = np.ascontiguousarray(filters, np.float32); abs3 = np.ascontiguousarray(abs3, np.float32)
+    mean = load().hqo_error_image(_ptr(a), _ptr(b), w, h, whitepoint, _ptr(filters), _ptr(abs3), filters.shape[1], _ptr(emap), _ptr(e8),
+                                  threads or default_threads())
+    return {"deltaE": mean, "errorImage": emap, "errorImageU8": e8}

@@ -105,3 +105,25 @@ def test_plugin_entry_with_reference_scoring(oracle):
     obest, oerr, _ = oracle.find_best_quantization(img, 8, p, threads=THREADS)
     assert res["bestError"] == oerr and np.array_equal(bits(res["bestColors"]), bits(obest))
     assert np.array_equal(res["image"].reshape(-1, 3), oracle.quantize(img, obest, oracle.SPACE_SRGB)["rgb"])
+
+
+def test_error_image_mode_matches_oracle(backend, oracle):
+    # HybridQuantization.errorImage (:139-182): original vs an actually quantised image
+    img = synth.synth_image(150, 90, 4, smooth=True)
+    pal = synth.synth_palettes(1, 10)[0]
+    quant = oracle.quantize(img, pal, oracle.SPACE_SRGB)["rgb"].reshape(img.shape)
+    backend.setImage(img)
+    backend.scielabConfigure(72, 45.0)
+    got = backend.computeError(quant)
+    of, oa = oracle.scielab_filters(72, 45.0)
+    want = oracle.error_image(img, quant, of, oa, 0, THREADS)
+    assert got["deltaE"] == want["deltaE"]
+    assert np.array_equal(got["errorImage"].reshape(-1).view(np.uint32), want["errorImage"].view(np.uint32))
+    assert np.array_equal(got["errorImageU8"].reshape(-1), want["errorImageU8"])
+    same = backend.computeError(img)
+    assert same["deltaE"] == 0.0 and (same["errorImage"] == 1.0).all()
+    res = HybridQuantization(dpi=96, ViewingDistance=60.0).errorImage(img, quant)
+    of, oa = oracle.scielab_filters(96, 60.0)
+    assert res["deltaE"] == oracle.error_image(img, quant, of, oa, 0, THREADS)["deltaE"]
+    with pytest.raises(ValueError):
+        HybridQuantization().errorImage(img, quant[:-1])
