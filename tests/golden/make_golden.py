@@ -66,6 +66,19 @@ def main():
                       "imax": p.imax, "iTc": p.iTc, "convergence": p.convergence, "space": p.space, "seed": 77760,
                       "best_error": float(err).hex(), "best_colors": fbits(best), "trace": [float(v).hex() for v in tr.reshape(-1)]}
     json.dump(runs, open(os.path.join(HERE, "swasa_vectors.json"), "w"), indent=0)
+    # 4. S-CIELAB stage (next row 1): filter bank, S-CIELAB of a small image, candidate costs, error image
+    f, a = O.scielab_filters(72, 45.0)
+    img = synth.synth_image(40, 32, synth.SEED_BASE + 1, True)
+    so = O.scielab_image(img, f, a, O.WHITE_D65, 1)
+    pal = synth.synth_palettes(3, 9)
+    ev = O.scielab_eval(img, f, a, so, pal, O.SPACE_SRGB, O.WHITE_D65, 1)
+    quant = O.quantize(img, pal[0], O.SPACE_SRGB)["rgb"].reshape(img.shape)
+    ei = O.error_image(img, quant, f, a, O.WHITE_D65, 1)
+    json.dump({"dpi": 72, "viewing_distance": 45.0, "filters": fbits(f), "abs3": fbits(a), "taps": int(f.shape[1]),
+               "w": 40, "h": 32, "seed": synth.SEED_BASE + 1, "smooth": True, "scielab_image": fbits(so),
+               "K": 9, "B": 3, "space": O.SPACE_SRGB, "err_fx": [int(v) for v in ev["err_fx"]], "counts": ev["counts"].tolist(),
+               "error_image_mean": float(ei["deltaE"]).hex(), "error_image_u8_sum": int(ei["errorImageU8"].astype(np.int64).sum())},
+              open(os.path.join(HERE, "scielab_vectors.json"), "w"), indent=0)
     print("golden vectors written to", HERE)
 
 

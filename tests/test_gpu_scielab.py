@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import bits
+from helpers import bits, from_bits, load_golden
 from hybridquantization_b200 import COST_SCIELAB, SPACE_LAB, SPACE_SRGB, SWASA, WHITEPOINT_D50, HqError, HybridQuantization, synth
 
 pytestmark = pytest.mark.gpu
@@ -127,3 +127,20 @@ def test_error_image_mode_matches_oracle(backend, oracle):
     assert res["deltaE"] == oracle.error_image(img, quant, of, oa, 0, THREADS)["deltaE"]
     with pytest.raises(ValueError):
         HybridQuantization().errorImage(img, quant[:-1])
+
+
+def test_golden_scielab_vectors_on_gpu(backend):
+    g = load_golden("scielab_vectors.json")
+    img = synth.synth_image(g["w"], g["h"], g["seed"], g["smooth"])
+    backend.setImage(img)
+    backend.scielabConfigure(g["dpi"], g["viewing_distance"])
+    f, a = backend.scielabFilters()
+    assert np.array_equal(bits(f).ravel(), bits(from_bits(g["filters"]))) and np.array_equal(bits(a), bits(from_bits(g["abs3"])))
+    assert np.array_equal(bits(backend.scielabImage()).ravel(), bits(from_bits(g["scielab_image"])))
+    pal = synth.synth_palettes(g["B"], g["K"])
+    ev = backend.evalPalettesScielab(pal, g["space"])
+    assert [int(v) for v in ev["err_fx"]] == g["err_fx"] and ev["counts"].tolist() == g["counts"]
+    q = backend.quantize(pal[0], g["space"])["rgb"]
+    ei = backend.computeError(q)
+    assert float(ei["deltaE"]).hex() == g["error_image_mean"]
+    assert int(ei["errorImageU8"].astype(np.int64).sum()) == g["error_image_u8_sum"]

@@ -93,3 +93,22 @@ def test_golden_swasa_vectors(oracle):
         assert float(err).hex() == v["best_error"], name
         assert np.array_equal(bits(best).ravel(), bits(from_bits(v["best_colors"]))), name
         assert [float(x).hex() for x in tr.reshape(-1)] == v["trace"], name
+
+
+def test_golden_scielab_vectors(oracle):
+    from hybridquantization_b200 import synth
+
+    g = load_golden("scielab_vectors.json")
+    f, a = oracle.scielab_filters(g["dpi"], g["viewing_distance"])
+    assert f.shape[1] == g["taps"]
+    assert np.array_equal(bits(f).ravel(), bits(from_bits(g["filters"]))) and np.array_equal(bits(a), bits(from_bits(g["abs3"])))
+    img = synth.synth_image(g["w"], g["h"], g["seed"], g["smooth"])
+    so = oracle.scielab_image(img, f, a, oracle.WHITE_D65, 3)
+    assert np.array_equal(bits(so).ravel(), bits(from_bits(g["scielab_image"])))
+    pal = synth.synth_palettes(g["B"], g["K"])
+    ev = oracle.scielab_eval(img, f, a, so, pal, g["space"], oracle.WHITE_D65, 2)
+    assert [int(v) for v in ev["err_fx"]] == g["err_fx"] and ev["counts"].tolist() == g["counts"]
+    quant = oracle.quantize(img, pal[0], g["space"])["rgb"].reshape(img.shape)
+    ei = oracle.error_image(img, quant, f, a)
+    assert float(ei["deltaE"]).hex() == g["error_image_mean"]
+    assert int(ei["errorImageU8"].astype(np.int64).sum()) == g["error_image_u8_sum"]
