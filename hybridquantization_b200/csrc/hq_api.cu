@@ -60,7 +60,10 @@ struct hq_ctx {
 
     // image state (this rank's shard)
     size_t n = 0, stride = 0;
-    int width = 0, rows = 0, whitepoint = 0;
+    int width = 0, rows = 0, whitepoint = 0;   // rows = local rows INCLUDING halo rows
+    int halo_top = 0, halo_bottom = 0, own_rows = 0;  // rows [halo_top, halo_top + own_rows) are this rank's own
+    int g_row0 = 0, g_rows = 0;                // global index of the first own row, global image height
+    size_t own_lo = 0, own_hi = 0;             // own pixel range inside the local arrays
     bool have_image = false, have_unit = false;
     DevBuf<uint8_t> d_rgb;
     DevBuf<float> d_lab, d_unit, d_table;
@@ -128,8 +131,10 @@ int ensure_unit(hq_ctx* c, cudaStream_t st) {
     return HQ_OK;
 }
 
-int convert_image(hq_ctx* c, int width, int rows, int whitepoint, cudaStream_t st) {
-    c->width = width; c->rows = rows; c->whitepoint = whitepoint;
+int convert_image(hq_ctx* c, int width, int own_rows, int halo_top, int halo_bottom, int g_row0, int g_rows, int whitepoint, cudaStream_t st) {
+    c->width = width; c->rows = halo_top + own_rows + halo_bottom; c->whitepoint = whitepoint;
+    c->halo_top = halo_top; c->halo_bottom = halo_bottom; c->own_rows = own_rows; c->g_row0 = g_row0; c->g_rows = g_rows;
+    c->own_lo = (size_t)halo_top * width; c->own_hi = (size_t)(halo_top + own_rows) * width;
     c->have_unit = false;
     c->sc_image_ready = false;
     HQ_CUDA(c, c->d_lab.reserve(3 * c->stride > 0 ? 3 * c->stride : 1));
@@ -164,6 +169,7 @@ int eval_device(hq_ctx* c, const float* d_palettes, int B, int K, int space, int
     a.pal_lab = c->d_pal_lab.p; a.pal_rgb = c->d_pal_rgb.p;
     a.B = B; a.K = K; a.space = space; a.want_sums = sums;
     a.results = d_results; a.idx_out = d_idx; a.sm_count = c->sm_count;
+    a.own_lo = c->own_lo; a.own_hi = c->own_hi;
     a.variant = (flags & HQ_EVAL_FORCE_DIRECT) ? 1 : ((flags & HQ_EVAL_FORCE_CHUNKED) ? 2 : ((flags & HQ_EVAL_FORCE_PREFILTER) ? 3 : 0));
     if (c->profiling) HQ_CUDA(c, cudaEventRecord(c->ev0, st));
     HQ_CUDA(c, hq::launch_assign_reduce(a, st));
@@ -236,11 +242,15 @@ int hq_device_info(const hq_ctx* c, int* sm_count, int* sm_clock_khz, char* name
     return HQ_OK;
 }
 
-uint64_t hq_image_pixels(const hq_ctx* c) { return c ? (uint64_t)c->n : 0; }
+uint64_t hq_image_pixels(const hq_ctx* c) { return c ? (uint64_t)(c->own_hi - c->own_lo) : 0; }
 
-int hq_set_image_u8(hq_ctx* c, const uint8_t* rgb, int width, int rows, int whitepoint) {
+int hq_set_image_u8_sharded(hq_ctx* c, const uint8_t* rgb, int width, int own_rows, int halo_top, int halo_bottom,
+                            int global_row0, int global_rows, int whitepoint) {
     if (!c) return HQ_ERR_INVALID;
-    if (width < 0 || rows < 0 || (!rgb && (size_t)width * rows > 0)) return fail(c, HQ_ERR_INVALID, "bad image arguments");
+    const long long rows = (long long)halo_top + own_rows + halo_bottom;
+    if (width < 0 || own_rows < 0 || halo_top < 0 || halo_bottom < 0 || (!rgb && (size_t)width * rows > 0)) return fail(c, HQ_ERR_INVALID, "bad image arguments");
+    if (global_row0 < halo_top || global_row0 + own_rows + halo_bottom > global_rows)
+        return fail(c, HQ_ERR_INVALID, "shard rows [%d,%d) with halos %d/%d do not fit a %d-row image", global_row0, global_row0 + own_rows, halo_top, halo_bottom, global_rows);
     if (whitepoint != HQ_WHITEPOINT_D65 && whitepoint != HQ_WHITEPOINT_D50) return fail(c, HQ_ERR_INVALID, "unknown white point %d", whitepoint);
     int rc = bind_device(c); if (rc) return rc;
     c->have_image = false;
@@ -248,9 +258,13 @@ int hq_set_image_u8(hq_ctx* c, const uint8_t* rgb, int width, int rows, int whit
     c->stride = hq::plane_stride(c->n);
     HQ_CUDA(c, c->d_rgb.reserve(c->n * 3 > 0 ? c->n * 3 : 1));
     if (c->n) HQ_CUDA(c, cudaMemcpyAsync(c->d_rgb.p, rgb, c->n * 3, cudaMemcpyHostToDevice, c->stream));
-    rc = convert_image(c, width, rows, whitepoint, c->stream); if (rc) return rc;
+    rc = convert_image(c, width, own_rows, halo_top, halo_bottom, global_row0, global_rows, whitepoint, c->stream); if (rc) return rc;
     HQ_CUDA(c, cudaStreamSynchronize(c->stream));
     return HQ_OK;
+}
+
+int hq_set_image_u8(hq_ctx* c, const uint8_t* rgb, int width, int rows, int whitepoint) {
+    return hq_set_image_u8_sharded(c, rgb, width, rows, 0, 0, 0, rows, whitepoint);
 }
 
 int hq_set_image_u8_device(hq_ctx* c, const void* d_rgb, int width, int rows, int whitepoint, void* stream) {
@@ -264,15 +278,16 @@ int hq_set_image_u8_device(hq_ctx* c, const void* d_rgb, int width, int rows, in
     c->stride = hq::plane_stride(c->n);
     HQ_CUDA(c, c->d_rgb.reserve(c->n * 3 > 0 ? c->n * 3 : 1));
     if (c->n) HQ_CUDA(c, cudaMemcpyAsync(c->d_rgb.p, d_rgb, c->n * 3, cudaMemcpyDeviceToDevice, st));
-    return convert_image(c, width, rows, whitepoint, st);
+    return convert_image(c, width, rows, 0, 0, 0, rows, whitepoint, st);
 }
 
 int hq_get_lab(hq_ctx* c, float* planes) {
     if (!c || !planes) return HQ_ERR_INVALID;
     if (!c->have_image) return fail(c, HQ_ERR_NO_IMAGE, "no image");
     int rc = bind_device(c); if (rc) return rc;
-    for (int pl = 0; pl < 3 && c->n; ++pl)
-        HQ_CUDA(c, cudaMemcpyAsync(planes + (size_t)pl * c->n, c->d_lab.p + (size_t)pl * c->stride, c->n * sizeof(float),
+    const size_t no = c->own_hi - c->own_lo;
+    for (int pl = 0; pl < 3 && no; ++pl)
+        HQ_CUDA(c, cudaMemcpyAsync(planes + (size_t)pl * no, c->d_lab.p + (size_t)pl * c->stride + c->own_lo, no * sizeof(float),
                                    cudaMemcpyDeviceToHost, c->stream));
     HQ_CUDA(c, cudaStreamSynchronize(c->stream));
     return HQ_OK;
@@ -347,22 +362,23 @@ int hq_quantize(hq_ctx* c, const float* palette, int K, int space, uint8_t* out_
     if (out_rgb || out_f32)
         HQ_CUDA(c, hq::launch_apply_palette(c->d_idx.p, idx16, n, c->d_pal.p, K, out_rgb ? c->d_out_rgb.p : nullptr,
                                             out_f32 ? c->d_out_f32.p : nullptr, c->stream));
-    if (n) {
-        if (out_rgb) HQ_CUDA(c, cudaMemcpyAsync(out_rgb, c->d_out_rgb.p, n * 3, cudaMemcpyDeviceToHost, c->stream));
-        if (out_f32) HQ_CUDA(c, cudaMemcpyAsync(out_f32, c->d_out_f32.p, n * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    const size_t lo = c->own_lo, no = c->own_hi - c->own_lo;  // a shard returns its own rows only
+    if (no) {
+        if (out_rgb) HQ_CUDA(c, cudaMemcpyAsync(out_rgb, c->d_out_rgb.p + lo * 3, no * 3, cudaMemcpyDeviceToHost, c->stream));
+        if (out_f32) HQ_CUDA(c, cudaMemcpyAsync(out_f32, c->d_out_f32.p + lo * 4, no * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     }
     std::vector<uint8_t> idx8;
-    if (out_idx && n) {
+    if (out_idx && no) {
         if (idx16) {
-            HQ_CUDA(c, cudaMemcpyAsync(out_idx, c->d_idx.p, n * 2, cudaMemcpyDeviceToHost, c->stream));
+            HQ_CUDA(c, cudaMemcpyAsync(out_idx, c->d_idx.p + lo * 2, no * 2, cudaMemcpyDeviceToHost, c->stream));
         } else {
-            idx8.resize(n);
-            HQ_CUDA(c, cudaMemcpyAsync(idx8.data(), c->d_idx.p, n, cudaMemcpyDeviceToHost, c->stream));
+            idx8.resize(no);
+            HQ_CUDA(c, cudaMemcpyAsync(idx8.data(), c->d_idx.p + lo, no, cudaMemcpyDeviceToHost, c->stream));
         }
     }
     HQ_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (out_idx && n && !idx16)
-        for (size_t i = 0; i < n; ++i) out_idx[i] = idx8[i];
+    if (out_idx && no && !idx16)
+        for (size_t i = 0; i < no; ++i) out_idx[i] = idx8[i];
     return HQ_OK;
 }
 
@@ -434,21 +450,31 @@ int hq_scielab_get_filters(const hq_ctx* c, float* filters7, float* abs3, int* t
     return HQ_OK;
 }
 
+static hq::ScRows sc_rows(const hq_ctx* c) { return hq::ScRows{c->halo_top, c->own_rows, c->g_row0 - c->halo_top, c->g_rows}; }
+
 // S-CIELAB representation of the resident image (sRGBToScielab, ScielabProcessor.java:374-381)
 static int sc_ensure_image(hq_ctx* c) {
     if (c->sc_image_ready) return HQ_OK;
     if (!c->have_image) return fail(c, HQ_ERR_NO_IMAGE, "no image: call hq_set_image_u8 first");
     if (c->sc_taps == 0) { int rc = hq_scielab_configure(c, 72, 45.0f); if (rc) return rc; }  // plugin defaults :229-231
-    if (c->width < c->sc_taps / 2 || c->rows < c->sc_taps / 2)
+    const int half = c->sc_taps / 2;
+    if (c->width < half || c->g_rows < half)
         return fail(c, HQ_ERR_UNSUPPORTED, "image %dx%d is smaller than the filter half-width %d (the reference's single reflection, "
-                    "OptimizedConvolution.cl:20-27, would read out of bounds)", c->width, c->rows, c->sc_taps / 2);
-    if (c->allreduce) return fail(c, HQ_ERR_UNSUPPORTED, "the S-CIELAB stage needs halo rows across shards: single GPU only in this version");
+                    "OptimizedConvolution.cl:20-27, would read out of bounds)", c->width, c->g_rows, half);
+    {   // a row shard must carry the neighbours' rows the vertical filter reaches (reflection is at the GLOBAL borders)
+        const int need_top = c->g_row0 < half ? c->g_row0 : half;
+        const int below = c->g_rows - (c->g_row0 + c->own_rows);
+        const int need_bottom = below < half ? below : half;
+        if (c->halo_top < need_top || c->halo_bottom < need_bottom || (c->own_rows > 0 && c->rows < half))
+            return fail(c, HQ_ERR_UNSUPPORTED, "S-CIELAB on a row shard needs %d halo rows above and %d below (got %d / %d): use hq_set_image_u8_sharded",
+                        need_top, need_bottom, c->halo_top, c->halo_bottom);
+    }
     HQ_CUDA(c, c->d_sc_opp.reserve(3 * c->stride));
     HQ_CUDA(c, c->d_sc_tmp.reserve(7 * c->stride));
     HQ_CUDA(c, c->d_sc_lab.reserve(3 * c->stride));
     HQ_CUDA(c, hq::launch_sc_rgb_to_opp(c->d_rgb.p, c->n, c->stride, c->d_table.p, c->d_sc_opp.p, c->stream));
     HQ_CUDA(c, hq::launch_sc_original(c->d_sc_opp.p, c->width, c->rows, c->stride, c->d_sc_filters.p, c->sc_generic ? nullptr : c->sc_block.data(), c->sc_taps,
-                                      c->whitepoint, c->d_sc_tmp.p, c->d_sc_lab.p, c->stream));
+                                      c->whitepoint, sc_rows(c), c->d_sc_tmp.p, c->d_sc_lab.p, c->stream));
     c->sc_image_ready = true;
     return HQ_OK;
 }
@@ -457,8 +483,9 @@ int hq_scielab_get_image(hq_ctx* c, float* planes) {
     if (!c || !planes) return HQ_ERR_INVALID;
     int rc = bind_device(c); if (rc) return rc;
     rc = sc_ensure_image(c); if (rc) return rc;
-    for (int pl = 0; pl < 3 && c->n; ++pl)
-        HQ_CUDA(c, cudaMemcpyAsync(planes + (size_t)pl * c->n, c->d_sc_lab.p + (size_t)pl * c->stride, c->n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    const size_t no = c->own_hi - c->own_lo;
+    for (int pl = 0; pl < 3 && no; ++pl)
+        HQ_CUDA(c, cudaMemcpyAsync(planes + (size_t)pl * no, c->d_sc_lab.p + (size_t)pl * c->stride + c->own_lo, no * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     HQ_CUDA(c, cudaStreamSynchronize(c->stream));
     return HQ_OK;
 }
@@ -478,16 +505,20 @@ int hq_error_image(hq_ctx* c, const uint8_t* quantized_rgb, float* error_map, ui
     // S-CIELAB of the second image through the same route as the original (sRGBToScielab, ScielabProcessor.java:374-381)
     HQ_CUDA(c, hq::launch_sc_rgb_to_opp(c->d_sc_rgb2.p, n, c->stride, c->d_table.p, c->d_sc_opp.p, c->stream));
     HQ_CUDA(c, hq::launch_sc_original(c->d_sc_opp.p, c->width, c->rows, c->stride, c->d_sc_filters.p, c->sc_generic ? nullptr : c->sc_block.data(),
-                                      c->sc_taps, c->whitepoint, c->d_sc_tmp.p, c->d_sc_lab2.p, c->stream));
+                                      c->sc_taps, c->whitepoint, sc_rows(c), c->d_sc_tmp.p, c->d_sc_lab2.p, c->stream));
     HQ_CUDA(c, cudaMemsetAsync(c->d_sc_err.p, 0, 8, c->stream));
-    HQ_CUDA(c, hq::launch_sc_error_image(c->d_sc_lab.p, c->d_sc_lab2.p, n, c->stride, error_map ? c->d_sc_map.p : nullptr,
+    const size_t lo = c->own_lo, no = c->own_hi - c->own_lo;  // maps and the sum cover the own rows
+    HQ_CUDA(c, hq::launch_sc_error_image(c->d_sc_lab.p + lo, c->d_sc_lab2.p + lo, no, c->stride, error_map ? c->d_sc_map.p : nullptr,
                                          error_map_u8 ? c->d_sc_map8.p : nullptr, c->d_sc_err.p, c->stream));
+    if (c->allreduce && c->allreduce(c->allreduce_user, c->d_sc_err.p, 1, c->stream) != 0) return fail(c, HQ_ERR_CALLBACK, "all-reduce hook failed");
     unsigned long long sum = 0;
     HQ_CUDA(c, cudaMemcpyAsync(&sum, c->d_sc_err.p, 8, cudaMemcpyDeviceToHost, c->stream));
-    if (error_map && n) HQ_CUDA(c, cudaMemcpyAsync(error_map, c->d_sc_map.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    if (error_map_u8 && n) HQ_CUDA(c, cudaMemcpyAsync(error_map_u8, c->d_sc_map8.p, n, cudaMemcpyDeviceToHost, c->stream));
+    if (error_map && no) HQ_CUDA(c, cudaMemcpyAsync(error_map, c->d_sc_map.p, no * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (error_map_u8 && no) HQ_CUDA(c, cudaMemcpyAsync(error_map_u8, c->d_sc_map8.p, no, cudaMemcpyDeviceToHost, c->stream));
     HQ_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (mean_de) *mean_de = n ? ((double)(int64_t)sum * (1.0 / 16777216.0)) / (double)n : 0.0;  // :893 error/errorArray.length
+    const double n_all = (double)c->width * (double)c->g_rows;  // with the hook the sum is over the whole image
+    const double n_div = c->allreduce ? n_all : (double)no;
+    if (mean_de) *mean_de = n_div > 0 ? ((double)(int64_t)sum * (1.0 / 16777216.0)) / n_div : 0.0;  // :893 error/errorArray.length
     return HQ_OK;
 }
 
@@ -518,14 +549,16 @@ int hq_eval_palettes_scielab(hq_ctx* c, const float* palettes, int B, int K, int
     for (int b = 0; b < B; ++b) {
         const uint8_t* idx_b = c->d_idx.p + (size_t)b * c->stride * (idx16 ? 2 : 1);
         HQ_CUDA(c, hq::launch_sc_candidate(idx_b, idx16, c->d_sc_tab.p + (size_t)b * K, c->width, c->rows, c->stride, c->d_sc_filters.p,
-                                           c->sc_generic ? nullptr : c->sc_block.data(), c->sc_taps, c->whitepoint, c->d_sc_tmp.p, c->d_sc_lab.p,
-                                           c->d_sc_err.p + b, c->stream));
+                                           c->sc_generic ? nullptr : c->sc_block.data(), c->sc_taps, c->whitepoint, sc_rows(c), c->d_sc_tmp.p,
+                                           c->d_sc_lab.p, c->d_sc_err.p + b, c->stream));
     }
+    // word 0 of every candidate <- the S-CIELAB error sum, so that one all-reduce covers error and counts
+    HQ_CUDA(c, cudaMemcpy2DAsync(c->d_results.p, (size_t)words * 8, c->d_sc_err.p, 8, 8, (size_t)B, cudaMemcpyDeviceToDevice, c->stream));
+    if (c->allreduce && c->allreduce(c->allreduce_user, c->d_results.p, nwords, c->stream) != 0) return fail(c, HQ_ERR_CALLBACK, "all-reduce hook failed");
     HQ_CUDA(c, cudaMemcpyAsync(c->h_results.p, c->d_results.p, nwords * 8, cudaMemcpyDeviceToHost, c->stream));
-    HQ_CUDA(c, cudaMemcpyAsync(c->h_results.p + nwords, c->d_sc_err.p, (size_t)B * 8, cudaMemcpyDeviceToHost, c->stream));
     HQ_CUDA(c, cudaStreamSynchronize(c->stream));
     for (int b = 0; b < B; ++b) {
-        if (err_fx) err_fx[b] = (int64_t)c->h_results.p[nwords + b];
+        if (err_fx) err_fx[b] = (int64_t)c->h_results.p[(size_t)b * words];
         if (counts) std::memcpy(counts + (size_t)b * K, c->h_results.p + (size_t)b * words + 1, sizeof(uint64_t) * K);
     }
     return HQ_OK;

@@ -178,6 +178,7 @@ struct AssignParams {
     const float4* pal_lab;   // [B][K8]
     int K, K8, words;
     float xmax0, xmax1, xmax2;  // bounds of |feature| over the image (prefilter error bound)
+    size_t own_lo, own_hi;      // pixels [own_lo, own_hi) are reduced; the rest (halo rows of a shard) only get an index
     unsigned long long* results;
     void* idx_out;
 };
@@ -318,6 +319,11 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : 2) a
     // error / counts / sums / index of ONE resolved pixel (q = its Lab, d2v = exact squared distance in
     // the assignment space)
     auto resolve = [&](size_t px, int k, float d2v, float q0, float q1, float q2, bool write_idx) {
+        if (write_idx) {
+            if (IDXW == 1) reinterpret_cast<uint8_t*>(p.idx_out)[(size_t)b * p.stride + px] = (uint8_t)k;
+            if (IDXW == 2) reinterpret_cast<uint16_t*>(p.idx_out)[(size_t)b * p.stride + px] = (uint16_t)k;
+        }
+        if (px < p.own_lo || px >= p.own_hi) return;  // halo pixel of a row shard: assigned, not counted
         if (SRGB) {  // assign in sRGB, score in CIELAB (OptimizedConvolution.cl:209)
             const float4 pl = s_lab[k];
             d2v = hq_dist2(q0, q1, q2, pl.x, pl.y, pl.z);
@@ -328,10 +334,6 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : 2) a
             atomicAdd(&s_sum[3 * k], (unsigned long long)hq_to_fx(q0));
             atomicAdd(&s_sum[3 * k + 1], (unsigned long long)hq_to_fx(q1));
             atomicAdd(&s_sum[3 * k + 2], (unsigned long long)hq_to_fx(q2));
-        }
-        if (write_idx) {
-            if (IDXW == 1) reinterpret_cast<uint8_t*>(p.idx_out)[(size_t)b * p.stride + px] = (uint8_t)k;
-            if (IDXW == 2) reinterpret_cast<uint16_t*>(p.idx_out)[(size_t)b * p.stride + px] = (uint16_t)k;
         }
     };
     // exact sweep over every colour (ambiguous pixels of variant 3)
@@ -692,6 +694,7 @@ cudaError_t launch_assign_reduce(const AssignArgs& a, cudaStream_t stream) {
     p.words = result_words(a.K, a.want_sums);
     p.results = a.results;
     p.idx_out = a.idx_out;
+    p.own_lo = a.own_lo; p.own_hi = a.own_hi > a.own_lo ? a.own_hi : a.n;
     const int idxw = a.idx_out ? (a.K <= 256 ? 1 : 2) : 0;
     // |feature| bounds of the image for the prefilter's error bound: CIELAB of in-gamut sRGB has
     // L in [0,100], |a|,|b| < 128 (extremes 98.3 / 107.9); unit sRGB is in [0,1]

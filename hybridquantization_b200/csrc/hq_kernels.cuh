@@ -42,6 +42,7 @@ struct AssignArgs {
     unsigned long long* results;  // [B][result_words], must be zeroed by the caller
     void* idx_out;         // [B][stride] u8 (K <= 256) or u16, or null
     int sm_count;
+    size_t own_lo = 0, own_hi = 0;  // reduce only pixels [own_lo, own_hi) (0,0 = all): halo rows of a shard are assigned but not counted
     int variant;           // 0 auto, 1 direct index tracking, 2 chunked min + recompute, 3 prefilter + exact
 };
 cudaError_t launch_assign_reduce(const AssignArgs& a, cudaStream_t stream);
@@ -54,6 +55,12 @@ cudaError_t launch_apply_palette(const void* d_idx, bool idx16, size_t n, const 
 cudaError_t launch_math_probe(int which, uint32_t first_bits, uint32_t count, float* d_out,
                               cudaStream_t stream);
 
+// rows of a shard for the vertical filter: outputs are local rows [y_begin, y_begin + y_count); local row 0 is
+// global row g0 of an image of gh rows (reflection happens at the GLOBAL borders)
+struct ScRows {
+    int y_begin, y_count, g0, gh;
+};
+
 // ---- S-CIELAB stage (hq_scielab.cu).  d_filters: [8][taps] = k1[t][3], k2[t][3], k3[t], |k3|[t]
 constexpr int kMaxScielabTaps = 255;
 cudaError_t launch_sc_rgb_to_opp(const uint8_t* d_rgb, size_t n, size_t stride, const float* d_table, float* d_opp, cudaStream_t st);
@@ -62,10 +69,10 @@ cudaError_t launch_sc_palette_opp(const float* d_palettes, int total, float4* d_
 // h_filters: the same block on the host (nullptr = always use the generic kernels); with taps == 21
 // (plugin defaults) the specialised kernels take it as a kernel parameter
 cudaError_t launch_sc_original(const float* d_opp, int w, int h, size_t stride, const float* d_filters, const float* h_filters, int taps,
-                               int whitepoint, float* d_tmp, float* d_lab_out, cudaStream_t st);
+                               int whitepoint, ScRows rows, float* d_tmp, float* d_lab_out, cudaStream_t st);
 // one candidate: index image + opponent table -> fixed-point sum of dE against d_lab_orig, added to *d_err
 cudaError_t launch_sc_candidate(const void* d_idx, bool idx16, const float4* d_tab, int w, int h, size_t stride, const float* d_filters,
-                                const float* h_filters, int taps, int whitepoint, float* d_tmp, const float* d_lab_orig,
+                                const float* h_filters, int taps, int whitepoint, ScRows rows, float* d_tmp, const float* d_lab_orig,
                                 unsigned long long* d_err, cudaStream_t st);
 
 // error-image mode: dE map between two S-CIELAB images + fixed-point sum

@@ -75,18 +75,18 @@ sc_hpass_kernel(const float* __restrict__ opp, const IdxT* __restrict__ idx, con
 //         dE vs the original's S-CIELAB, fixed-point sum -> one atomic per CTA.
 template <int MODE>
 __global__ void __launch_bounds__(kScThreads)
-sc_vpass_kernel(const float* __restrict__ tmp, int w, int h, size_t stride, ScFilters f, hq_float3 ill,
+sc_vpass_kernel(const float* __restrict__ tmp, int w, int h, size_t stride, ScFilters f, hq_float3 ill, ScRows rows,
                 float* __restrict__ lab_out, const float* __restrict__ lab_orig, unsigned long long* __restrict__ err_out) {
     extern __shared__ float s_f[];  // 8 * taps
     for (int i = threadIdx.x; i < 8 * f.taps; i += kScThreads) s_f[i] = f.data[i];
     __syncthreads();
-    const int x = blockIdx.x * kScThreads + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * kScThreads + threadIdx.x, y = rows.y_begin + blockIdx.y;
     long long fx = 0;
     if (x < w) {
         const int half = f.taps / 2, T = f.taps;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, c0 = 0.f;
         for (int t = 0; t < T; ++t) {
-            const size_t p = (size_t)hq_reflect(y + t - half, h) * w + x;
+            const size_t p = (size_t)(hq_reflect(rows.g0 + y + t - half, rows.gh) - rows.g0) * w + x;
             const float t10 = __ldg(tmp + p), t11 = __ldg(tmp + stride + p), t12 = __ldg(tmp + 2 * stride + p);
             const float t20 = __ldg(tmp + 3 * stride + p), t21 = __ldg(tmp + 4 * stride + p), t22 = __ldg(tmp + 5 * stride + p);
             const float t3 = __ldg(tmp + 6 * stride + p);
@@ -194,9 +194,9 @@ constexpr int kVRows = 8;  // output rows per thread (vertical): 28 input rows s
 
 template <int MODE>
 __global__ void __launch_bounds__(kScThreads)
-sc_vpass21_kernel(const float* __restrict__ tmp, int w, int h, size_t stride, const __grid_constant__ Filt21 f, hq_float3 ill,
+sc_vpass21_kernel(const float* __restrict__ tmp, int w, int h, size_t stride, const __grid_constant__ Filt21 f, hq_float3 ill, ScRows rows,
                   float* __restrict__ lab_out, const float* __restrict__ lab_orig, unsigned long long* __restrict__ err_out) {
-    const int x = blockIdx.x * kScThreads + threadIdx.x, y0 = blockIdx.y * kVRows;
+    const int x = blockIdx.x * kScThreads + threadIdx.x, y0 = rows.y_begin + blockIdx.y * kVRows;
     long long fx = 0;
     if (x < w) {
         float a[kVRows][3], b[kVRows][3], c3[kVRows];
@@ -204,7 +204,10 @@ sc_vpass21_kernel(const float* __restrict__ tmp, int w, int h, size_t stride, co
         for (int o = 0; o < kVRows; ++o) { a[o][0] = a[o][1] = a[o][2] = 0.f; b[o][0] = b[o][1] = b[o][2] = 0.f; c3[o] = 0.f; }
 #pragma unroll
         for (int r = 0; r < kVRows + kT - 1; ++r) {
-            const size_t p = (size_t)hq_reflect(y0 - kHalf + r, h) * w + x;  // rows past the image are reflected; unused outputs are discarded
+            // reflection at the GLOBAL image borders; rows only needed by discarded outputs are clamped into the local array
+            int lr = hq_reflect(rows.g0 + y0 - kHalf + r, rows.gh) - rows.g0;
+            lr = lr < 0 ? 0 : (lr >= h ? h - 1 : lr);
+            const size_t p = (size_t)lr * w + x;
             const float t10 = __ldg(tmp + p), t11 = __ldg(tmp + stride + p), t12 = __ldg(tmp + 2 * stride + p);
             const float t20 = __ldg(tmp + 3 * stride + p), t21 = __ldg(tmp + 4 * stride + p), t22 = __ldg(tmp + 5 * stride + p);
             const float t3 = __ldg(tmp + 6 * stride + p);
@@ -228,7 +231,7 @@ sc_vpass21_kernel(const float* __restrict__ tmp, int w, int h, size_t stride, co
 #pragma unroll
         for (int o = 0; o < kVRows; ++o) {
             const int y = y0 + o;
-            if (y < h) {
+            if (y < rows.y_begin + rows.y_count) {
                 float o0, o1, o2;
                 if (MODE == 0) { o0 = HQ_FADD(HQ_FADD(a[o][0], b[o][0]), c3[o]); o1 = HQ_FADD(a[o][1], b[o][1]); o2 = HQ_FADD(a[o][2], b[o][2]); }
                 else { o0 = a[o][0]; o1 = a[o][1]; o2 = a[o][2]; }
@@ -309,41 +312,41 @@ cudaError_t launch_sc_palette_opp(const float* d_palettes, int total, float4* d_
 }
 
 cudaError_t launch_sc_original(const float* d_opp, int w, int h, size_t stride, const float* d_filters, const float* h_filters, int taps,
-                               int whitepoint, float* d_tmp, float* d_lab_out, cudaStream_t st) {
-    if (w == 0 || h == 0) return cudaSuccess;
+                               int whitepoint, ScRows rows, float* d_tmp, float* d_lab_out, cudaStream_t st) {
+    if (w == 0 || h == 0 || rows.y_count == 0) return cudaSuccess;
     if (taps == kT && h_filters) {
         Filt21 f21;
         for (int i = 0; i < 8 * kT; ++i) f21.v[i] = h_filters[i];
-        const dim3 gh((unsigned)((w + kHSeg - 1) / kHSeg), (unsigned)h), gv((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)((h + kVRows - 1) / kVRows));
+        const dim3 gh((unsigned)((w + kHSeg - 1) / kHSeg), (unsigned)h), gv((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)((rows.y_count + kVRows - 1) / kVRows));
         sc_hpass21_kernel<0, uint8_t><<<gh, kScThreads, 0, st>>>(d_opp, nullptr, nullptr, w, h, stride, f21, d_tmp);
-        sc_vpass21_kernel<0><<<gv, kScThreads, 0, st>>>(d_tmp, w, h, stride, f21, hq_whitepoint(whitepoint), d_lab_out, nullptr, nullptr);
+        sc_vpass21_kernel<0><<<gv, kScThreads, 0, st>>>(d_tmp, w, h, stride, f21, hq_whitepoint(whitepoint), rows, d_lab_out, nullptr, nullptr);
         return cudaGetLastError();
     }
     const ScFilters f{d_filters, taps};
-    const dim3 grid((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)h);
+    const dim3 grid((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)h), gridv((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)rows.y_count);
     sc_hpass_kernel<0, uint8_t><<<grid, kScThreads, 7 * taps * sizeof(float), st>>>(d_opp, nullptr, nullptr, w, h, stride, f, d_tmp);
-    sc_vpass_kernel<0><<<grid, kScThreads, 8 * taps * sizeof(float), st>>>(d_tmp, w, h, stride, f, hq_whitepoint(whitepoint), d_lab_out, nullptr, nullptr);
+    sc_vpass_kernel<0><<<gridv, kScThreads, 8 * taps * sizeof(float), st>>>(d_tmp, w, h, stride, f, hq_whitepoint(whitepoint), rows, d_lab_out, nullptr, nullptr);
     return cudaGetLastError();
 }
 
 cudaError_t launch_sc_candidate(const void* d_idx, bool idx16, const float4* d_tab, int w, int h, size_t stride, const float* d_filters,
-                                const float* h_filters, int taps, int whitepoint, float* d_tmp, const float* d_lab_orig,
+                                const float* h_filters, int taps, int whitepoint, ScRows rows, float* d_tmp, const float* d_lab_orig,
                                 unsigned long long* d_err, cudaStream_t st) {
-    if (w == 0 || h == 0) return cudaSuccess;
+    if (w == 0 || h == 0 || rows.y_count == 0) return cudaSuccess;
     if (taps == kT && h_filters) {
         Filt21 f21;
         for (int i = 0; i < 8 * kT; ++i) f21.v[i] = h_filters[i];
-        const dim3 gh((unsigned)((w + kHSeg - 1) / kHSeg), (unsigned)h), gv((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)((h + kVRows - 1) / kVRows));
+        const dim3 gh((unsigned)((w + kHSeg - 1) / kHSeg), (unsigned)h), gv((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)((rows.y_count + kVRows - 1) / kVRows));
         if (idx16) sc_hpass21_kernel<1, uint16_t><<<gh, kScThreads, 0, st>>>(nullptr, static_cast<const uint16_t*>(d_idx), d_tab, w, h, stride, f21, d_tmp);
         else sc_hpass21_kernel<1, uint8_t><<<gh, kScThreads, 0, st>>>(nullptr, static_cast<const uint8_t*>(d_idx), d_tab, w, h, stride, f21, d_tmp);
-        sc_vpass21_kernel<1><<<gv, kScThreads, 0, st>>>(d_tmp, w, h, stride, f21, hq_whitepoint(whitepoint), nullptr, d_lab_orig, d_err);
+        sc_vpass21_kernel<1><<<gv, kScThreads, 0, st>>>(d_tmp, w, h, stride, f21, hq_whitepoint(whitepoint), rows, nullptr, d_lab_orig, d_err);
         return cudaGetLastError();
     }
     const ScFilters f{d_filters, taps};
-    const dim3 grid((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)h);
+    const dim3 grid((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)h), gridv((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)rows.y_count);
     if (idx16) sc_hpass_kernel<1, uint16_t><<<grid, kScThreads, 7 * taps * sizeof(float), st>>>(nullptr, static_cast<const uint16_t*>(d_idx), d_tab, w, h, stride, f, d_tmp);
     else sc_hpass_kernel<1, uint8_t><<<grid, kScThreads, 7 * taps * sizeof(float), st>>>(nullptr, static_cast<const uint8_t*>(d_idx), d_tab, w, h, stride, f, d_tmp);
-    sc_vpass_kernel<1><<<grid, kScThreads, 8 * taps * sizeof(float), st>>>(d_tmp, w, h, stride, f, hq_whitepoint(whitepoint), nullptr, d_lab_orig, d_err);
+    sc_vpass_kernel<1><<<gridv, kScThreads, 8 * taps * sizeof(float), st>>>(d_tmp, w, h, stride, f, hq_whitepoint(whitepoint), rows, nullptr, d_lab_orig, d_err);
     return cudaGetLastError();
 }
 

@@ -18,6 +18,13 @@ def row_shard(height: int, world_size: int, rank: int) -> tuple[int, int]:
     return height * rank // world_size, height * (rank + 1) // world_size
 
 
+def row_shard_with_halo(height: int, world_size: int, rank: int, halo: int) -> tuple[int, int, int, int]:
+    """(r0, r1, halo_top, halo_bottom): the rank's own rows [r0, r1) and how many neighbour rows to upload with
+    them for the S-CIELAB stage (halo = taps // 2; fewer at the global borders)."""
+    r0, r1 = row_shard(height, world_size, rank)
+    return r0, r1, min(halo, r0), min(halo, height - r1)
+
+
 def allreduce_words(t):
     """In-place SUM all-reduce of an int64 tensor of result words (no-op when not distributed)."""
     import torch.distributed as dist

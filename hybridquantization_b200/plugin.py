@@ -104,6 +104,7 @@ class ImageManipulation:
             raise HqError(rc, msg.decode() if msg else "")
         self._cb = None
         self.shape = None
+        self._local_pixels = 0
 
     # -- lifetime
     def getCudaAvailable(self) -> bool:
@@ -158,10 +159,22 @@ class ImageManipulation:
         if rgb.ndim != 3 or rgb.shape[2] != 3:
             raise ValueError("Please open an image with 3 or more channels")  # HybridQuantization.java:68-69
         self.shape = rgb.shape[:2]
+        self._local_pixels = rgb.shape[0] * rgb.shape[1]
         _lib.check(self._ctx, self._lib.hq_set_image_u8(self._ctx, _ptr(rgb), rgb.shape[1], rgb.shape[0], whitepoint))
+
+    def setImageSharded(self, rgb_local: np.ndarray, halo_top: int, halo_bottom: int, global_row0: int, global_rows: int,
+                        whitepoint: int = WHITEPOINT_D65) -> None:
+        """rgb_local: uint8 [halo_top + own_rows + halo_bottom, width, 3]; see hq_set_image_u8_sharded."""
+        rgb = np.ascontiguousarray(rgb_local, np.uint8)
+        own = rgb.shape[0] - halo_top - halo_bottom
+        self.shape = (own, rgb.shape[1])
+        self._local_pixels = rgb.shape[0] * rgb.shape[1]
+        _lib.check(self._ctx, self._lib.hq_set_image_u8_sharded(self._ctx, _ptr(rgb), rgb.shape[1], own, halo_top, halo_bottom,
+                                                                  global_row0, global_rows, whitepoint))
 
     def setImageDevice(self, d_rgb_ptr: int, width: int, rows: int, whitepoint: int = WHITEPOINT_D65, stream: int = 0):
         self.shape = (rows, width)
+        self._local_pixels = rows * width
         _lib.check(self._ctx, self._lib.hq_set_image_u8_device(self._ctx, d_rgb_ptr, width, rows, whitepoint, stream or None))
 
     def pixels(self) -> int:
@@ -242,7 +255,7 @@ class ImageManipulation:
         """Error-image mode (ImageManipulation.computeError :858-894): mean dE between S-CIELAB(original) and
         S-CIELAB(quantized) and the ((255-dE)^2)/255^2 map."""
         q = np.ascontiguousarray(quantized_rgb, np.uint8)
-        if q.size != self.pixels() * 3:
+        if q.size != self._local_pixels * 3:  # a shard passes its own rows plus the same halo rows as the original
             raise ValueError("Mismatching image sizes or not enough channels, abort.")  # HybridQuantization.java:81
         emap = np.empty(self.pixels(), np.float32); e8 = np.empty(self.pixels(), np.uint8)
         mean = C.c_double()

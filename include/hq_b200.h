@@ -70,6 +70,13 @@ int hq_device_info(const hq_ctx* ctx, int* sm_count, int* sm_clock_khz, char* na
  * rgb: packed u8, 3 bytes per pixel, row-major, `rows` rows of `width` pixels: the caller's
  * shard of the image (all of it on one GPU).  Host pointer. */
 int hq_set_image_u8(hq_ctx* ctx, const uint8_t* rgb, int width, int rows, int whitepoint);
+/* A row shard WITH halo rows (needed by the S-CIELAB stage, whose vertical filter reaches taps/2 rows
+ * into the neighbours): rgb holds halo_top + own_rows + halo_bottom rows; the first OWN row is row
+ * global_row0 of an image of global_rows rows.  Every reduction (counts, sums, errors), hq_image_pixels,
+ * hq_get_lab, hq_quantize and hq_scielab_get_image cover the own rows only; halo pixels are assigned so
+ * that the quantised halo feeds the filter.  hq_set_image_u8 == no halo, the whole image. */
+int hq_set_image_u8_sharded(hq_ctx* ctx, const uint8_t* rgb, int width, int own_rows, int halo_top, int halo_bottom,
+                            int global_row0, int global_rows, int whitepoint);
 /* same with the packed RGB already resident in device memory; runs on `stream` (a
  * cudaStream_t, NULL = the context's stream) and does not synchronise */
 int hq_set_image_u8_device(hq_ctx* ctx, const void* d_rgb, int width, int rows, int whitepoint,
@@ -119,7 +126,7 @@ int hq_quantize(hq_ctx* ctx, const float* palette, int K, int space, uint8_t* ou
  * hq_scielab_get_image returns sRGBToScielab(original) (ScielabProcessor.java:374-381) as planes
  * [3][n].  hq_eval_palettes_scielab replaces computeQuantizationErrorPopulation with its full kernel
  * chain (ImageManipulation.java:635-699): err_fx[B] = sum of round(dE * 2^24), counts[B][K].
- * Single GPU in this version (the 21-tap vertical filter needs halo rows across shards). */
+ * Row shards need taps/2 halo rows (hq_set_image_u8_sharded); the all-reduce hook then sums errors and counts. */
 int hq_scielab_configure(hq_ctx* ctx, int dpi, float viewing_distance_cm);
 int hq_scielab_set_filters(hq_ctx* ctx, const float* filters7, const float* abs3, int taps);
 /* *taps: in = capacity of the arrays (entries per filter), out = actual taps */

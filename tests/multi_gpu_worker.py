@@ -12,8 +12,8 @@ import torch.distributed as dist
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 
-from hybridquantization_b200 import SWASA, ImageManipulation, synth  # noqa: E402
-from hybridquantization_b200.dist import install_nccl_allreduce, row_shard  # noqa: E402
+from hybridquantization_b200 import COST_SCIELAB, SPACE_SRGB, SWASA, ImageManipulation, synth  # noqa: E402
+from hybridquantization_b200.dist import install_nccl_allreduce, row_shard, row_shard_with_halo  # noqa: E402
 
 
 def main():
@@ -49,6 +49,26 @@ def main():
                                                   np.array_equal(best.view(np.uint32), sbest.view(np.uint32)))
         res["iterations"] = its
     be.close()
+    # ---- the S-CIELAB stage on row shards with halo rows, all-reduced over NCCL
+    r0, r1, top, bot = row_shard_with_halo(h, world, rank, 10)
+    sc = ImageManipulation("CIE76", False, True, local)
+    sc.setImageSharded(img[r0 - top:r1 + bot], top, bot, r0, h)
+    sc.scielabConfigure(72, 45.0)
+    install_nccl_allreduce(sc)
+    sc_tot = sc.evalPalettesScielab(pal[:2, :32])
+    sw2 = SWASA(population=3, imax=25, seed=7, space=SPACE_SRGB, costModel=COST_SCIELAB)
+    sbest2, serr2, str2, _ = sc.findBestQuantization(32, sw2, n_total=w * h, trace=True)
+    sc.close()
+    if rank == 0:
+        one = ImageManipulation("CIE76", False, True, local)
+        one.setImage(img)
+        one.scielabConfigure(72, 45.0)
+        ref = one.evalPalettesScielab(pal[:2, :32])
+        obest2, oerr2, otr2, _ = one.findBestQuantization(32, SWASA(population=3, imax=25, seed=7, space=SPACE_SRGB, costModel=COST_SCIELAB), trace=True)
+        one.close()
+        res["scielab_totals_equal_single_gpu"] = bool(np.array_equal(sc_tot["err_fx"], ref["err_fx"]) and np.array_equal(sc_tot["counts"], ref["counts"]))
+        res["scielab_trajectory_equal_single_gpu"] = bool(np.array_equal(str2.view(np.uint64), otr2.view(np.uint64)) and serr2 == oerr2 and
+                                                          np.array_equal(sbest2.view(np.uint32), obest2.view(np.uint32)))
     gathered = [None] * world
     dist.all_gather_object(gathered, res)
     if rank == 0:

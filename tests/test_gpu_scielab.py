@@ -144,3 +144,50 @@ def test_golden_scielab_vectors_on_gpu(backend):
     ei = backend.computeError(q)
     assert float(ei["deltaE"]).hex() == g["error_image_mean"]
     assert int(ei["errorImageU8"].astype(np.int64).sum()) == g["error_image_u8_sum"]
+
+
+@pytest.mark.parametrize("h,world", [(97, 3), (64, 2), (45, 4)])
+def test_row_shards_with_halo_add_up(backend, oracle, h, world):
+    # what each rank of a multi-GPU run computes, emulated one shard after the other on one GPU:
+    # own rows + 10 halo rows; errors / counts of the shards must add up to the whole image exactly
+    from hybridquantization_b200.dist import row_shard_with_halo
+
+    w, K = 131, 20
+    img = synth.synth_image(w, h, 17, smooth=True)
+    pal = synth.synth_palettes(3, K)
+    backend.setImage(img)
+    backend.scielabConfigure(72, 45.0)
+    whole_sc = backend.evalPalettesScielab(pal)
+    whole_id = backend.evalPalettes(pal, SPACE_SRGB, sums=True)
+    whole_img = backend.scielabImage()
+    whole_q = backend.quantize(pal[0], SPACE_SRGB)
+    quant = whole_q["rgb"].reshape(img.shape)
+    whole_err = backend.computeError(quant)
+    err = np.zeros(3, np.int64); cnt = np.zeros((3, K), np.uint64)
+    ierr = np.zeros(3, np.int64); icnt = np.zeros((3, K), np.uint64); isum = np.zeros((3, K, 3), np.int64)
+    sc_rows, q_rows, e_rows, e_sum = [], [], [], 0.0
+    for rank in range(world):
+        r0, r1, top, bot = row_shard_with_halo(h, world, rank, 10)
+        backend.setImageSharded(img[r0 - top:r1 + bot], top, bot, r0, h)
+        assert backend.pixels() == (r1 - r0) * w
+        r = backend.evalPalettesScielab(pal)
+        err += r["err_fx"]; cnt += r["counts"]
+        r = backend.evalPalettes(pal, SPACE_SRGB, sums=True)
+        ierr += r["err_fx"]; icnt += r["counts"]; isum += r["sums_fx"]
+        sc_rows.append(backend.scielabImage().reshape(3, r1 - r0, w))
+        q_rows.append(backend.quantize(pal[0], SPACE_SRGB)["rgb"])
+        e = backend.computeError(quant[r0 - top:r1 + bot])
+        e_rows.append(e["errorImage"]); e_sum += e["deltaE"] * (r1 - r0) * w
+    assert np.array_equal(err, whole_sc["err_fx"]) and np.array_equal(cnt, whole_sc["counts"])
+    assert np.array_equal(ierr, whole_id["err_fx"]) and np.array_equal(icnt, whole_id["counts"]) and np.array_equal(isum, whole_id["sums_fx"])
+    assert np.array_equal(np.concatenate(sc_rows, axis=1).reshape(3, -1).view(np.uint32), whole_img.view(np.uint32))
+    assert np.array_equal(np.concatenate(q_rows, axis=0), whole_q["rgb"])
+    assert np.array_equal(np.concatenate(e_rows, axis=0).view(np.uint32), whole_err["errorImage"].view(np.uint32))
+    assert abs(e_sum / (h * w) - whole_err["deltaE"]) < 1e-9
+    # a shard without the halo rows it needs is rejected for the S-CIELAB stage (but fine for the identity cost)
+    r0, r1, _, _ = row_shard_with_halo(h, world, 1, 10)
+    backend.setImageSharded(img[r0:r1], 0, 0, r0, h)
+    with pytest.raises(HqError) as ex:
+        backend.evalPalettesScielab(pal)
+    assert ex.value.code == 4
+    backend.evalPalettes(pal)
