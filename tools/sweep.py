@@ -29,6 +29,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--skip-swasa", action="store_true")
+    ap.add_argument("--only-scielab", action="store_true")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
@@ -59,7 +60,7 @@ def main():
 
     # ---- RGB -> Lab (15 B/pixel algorithmic: 3 B read + 12 B written)
     out["rgb_to_lab"] = []
-    for (w, h) in ((1920, 1080), (3840, 2160), (8192, 8192)):
+    for (w, h) in (() if a.only_scielab else ((1920, 1080), (3840, 2160), (8192, 8192))):
         img = synth.synth_image_rows(w, h, synth.SEED_BASE + 3, 0, h)
         d_img = torch.from_numpy(img).to(dev)
         be.setProfiling(True)
@@ -86,7 +87,7 @@ def main():
     d_img = torch.from_numpy(img).to(dev)
     be.setImageDevice(d_img.data_ptr(), w, h, stream=st.cuda_stream)
     out["k_sweep"] = []
-    ks = (8, 16, 32, 64, 128, 256, 512, 1024)
+    ks = () if a.only_scielab else (8, 16, 32, 64, 128, 256, 512, 1024)
     for K in ks:
         for B in (1, 64):
             if a.quick and B == 64 and K > 256:
@@ -109,7 +110,7 @@ def main():
 
     # ---- S-CIELAB stage (next row 1): full reference cost chain per candidate, through the host-buffer C ABI
     out["scielab"] = []
-    for (w, h, K, B) in ((1920, 1080, 256, 4), (3840, 2160, 256, 4), (3840, 2160, 256, 16)):
+    for (w, h, K, B) in (((3840, 2160, 256, 4),) if a.only_scielab else ((1920, 1080, 256, 4), (3840, 2160, 256, 4), (3840, 2160, 256, 16))):
         img = synth.synth_image_rows(w, h, synth.SEED_BASE + 2, 0, h)
         be.setImage(img)
         be.scielabConfigure(72, 45.0)
