@@ -43,6 +43,7 @@ class JavaRandomState(C.Structure):
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+PROGRESS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_double)
 
 # every symbol include/hq_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
@@ -73,6 +74,7 @@ SIGNATURES = {
     "hq_swasa_default_params": (None, [C.POINTER(SwasaParams)]),
     "hq_find_best_quantization": (C.c_int, [_P, C.c_int, C.POINTER(SwasaParams), C.c_uint64, _P, C.POINTER(C.c_double), _P, C.POINTER(C.c_int)]),
     "hq_request_stop": (None, [_P]),
+    "hq_set_progress": (C.c_int, [_P, PROGRESS_FN, _P]),
     "hq_java_random_seed": (None, [C.POINTER(JavaRandomState), C.c_int64]),
     "hq_java_random_next": (C.c_int32, [C.POINTER(JavaRandomState), C.c_int]),
     "hq_java_random_next_float": (C.c_float, [C.POINTER(JavaRandomState)]),

@@ -89,6 +89,8 @@ struct hq_ctx {
     DevBuf<float4> d_sc_tab;
     DevBuf<unsigned long long> d_sc_err;
 
+    hq_progress_fn progress = nullptr;
+    void* progress_user = nullptr;
     hq_allreduce_fn allreduce = nullptr;
     void* allreduce_user = nullptr;
     bool profiling = false;
@@ -591,6 +593,7 @@ int hq_find_best_quantization(hq_ctx* c, int K, const hq_swasa_params* p, uint64
         hq::ImageManipulation backend(c, false, p->convergence != 0);
         backend.setStopFlag(&c->stop_flag_view);
         backend.setCostModel(p->cost_model);
+        backend.setProgress(c->progress, c->progress_user);
         hq::JavaRandom random(p->seed);
         hq::SWASA swasa(p->population, p->imax, p->iTc, p->delta, p->conv_delay, p->conv_spread, p->t0, p->alpha, p->s0, p->beta, &random);
         double err = 0;
@@ -601,6 +604,13 @@ int hq_find_best_quantization(hq_ctx* c, int K, const hq_swasa_params* p, uint64
         if (c->err.empty()) c->err = ex.what();
         return HQ_ERR_CUDA;
     }
+    return HQ_OK;
+}
+
+int hq_set_progress(hq_ctx* c, hq_progress_fn fn, void* user) {
+    if (!c) return HQ_ERR_INVALID;
+    c->progress = fn;
+    c->progress_user = user;
     return HQ_OK;
 }
 

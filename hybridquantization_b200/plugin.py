@@ -292,6 +292,11 @@ class ImageManipulation:
                                                                     C.byref(best_err), _ptr(tr), C.byref(its)))
         return best, best_err.value, tr, its.value
 
+    def setProgress(self, fn) -> None:
+        """fn(iteration, max_iterations, best_error) every 10 iterations (the plugin's progress bar, :546-551)."""
+        self._progress_cb = _lib.PROGRESS_FN((lambda _u, i, m, e: fn(i, m, e)) if fn else 0)
+        _lib.check(self._ctx, self._lib.hq_set_progress(self._ctx, self._progress_cb, None))
+
     def requestStop(self) -> None:
         self._lib.hq_request_stop(self._ctx)
 

@@ -180,6 +180,11 @@ int hq_find_best_quantization(hq_ctx* ctx, int K, const hq_swasa_params* p, uint
                               float* best_colors, double* best_error, double* trace_costs,
                               int* iterations_done);
 void hq_request_stop(hq_ctx* ctx); /* EzStoppable.stopExecution, HybridQuantization.java:311 */
+/* progress hook: called from hq_find_best_quantization every 10 iterations with (iteration, max
+ * iterations, best error so far), where the reference updates Icy's progress bar
+ * (ImageManipulation.java:546-551, HybridQuantization.updateProgressBar :265-270).  NULL removes it. */
+typedef void (*hq_progress_fn)(void* user, int iteration, int max_iterations, double best_error);
+int hq_set_progress(hq_ctx* ctx, hq_progress_fn fn, void* user);
 
 /* ---- host-side pieces of the plugin that callers outside C++ may want ---- */
 /* java.util.Random-compatible generator */

@@ -151,6 +151,8 @@ public:
     }
     void setStopFlag(const volatile bool* flag) { stopFlag_ = flag; }
     void setCostModel(int costModel) { costModel_ = costModel; }  // HQ_COST_LAB | HQ_COST_SCIELAB
+    // updateProgressBar (HybridQuantization.java:265-270), invoked every 10 iterations (:546-551)
+    void setProgress(void (*fn)(void*, int, int, double), void* user) { progress_ = fn; progressUser_ = user; }
 
     // upload + RGB->CIELAB (the uploads of :451,:471-472 and RGBtoXYZ/XYZtoScielab)
     void setImage(const uint8_t* rgb, int w, int rows, int whitepoint) {
@@ -231,6 +233,7 @@ public:
                     std::memcpy(colors.data() + i * pal, currentColors.data() + minerroridx * pal, sizeof(float) * pal);
                 }
             }
+            if (ite % 10 == 0 && progress_) progress_(progressUser_, ite, maxiter, bestError);  // :546-551
         }
         if (verbose_) std::printf("Final error : %.5f\n", bestError);  // :589
         if (bestErrorOut) *bestErrorOut = bestError;
@@ -254,6 +257,8 @@ private:
     bool verbose_, convergence_, owns_;
     const volatile bool* stopFlag_ = nullptr;
     int costModel_ = HQ_COST_LAB;
+    void (*progress_)(void*, int, int, double) = nullptr;
+    void* progressUser_ = nullptr;
     std::vector<int64_t> errFx_;
     std::vector<uint64_t> counts_;
 };

@@ -74,3 +74,14 @@ def test_stop_request_returns_best_so_far(backend):
     t.join()
     assert 0 < its < 200000 and time.time() - t0 < 30
     assert np.isfinite(err) and best.shape == (64, 4)
+
+
+def test_progress_hook_every_ten_iterations(backend):
+    img = synth.synth_image(64, 64, 2)
+    backend.setImage(img)
+    seen = []
+    backend.setProgress(lambda i, m, e: seen.append((i, m, e)))
+    best, err, _, its = backend.findBestQuantization(8, SWASA(population=2, imax=35, seed=3))
+    backend.setProgress(None)
+    assert [s[0] for s in seen] == [10, 20, 30] and all(s[1] == 35 for s in seen)
+    assert seen[-1][2] >= err and all(a[2] >= b[2] for a, b in zip(seen, seen[1:]))   # best error never increases
