@@ -8,7 +8,8 @@ rows sharded one block per rank, and the only exchange is an NCCL all-reduce of 
 result words (weak scaling; at N=8 this is the 64 MP configuration, configs[3]).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            # the CUDA path
-  python bench.py --impl reference [--gpus N] [--steps K] ...     # the CPU path (oracle port), rank 0 only
+  python bench.py --impl reference [--gpus N] [--steps K] ...     # the reference's own kernels on the host cores
+                                                                  # (oracle/_ref; oracle port if absent), rank 0 only
 
 value  : pixel x candidate assignments per second (Gpixel/s), inputs resident in HBM, device timed
 e2e    : the same through the host-buffer C ABI call hq_eval_palettes (H2D palettes, D2H results)
@@ -134,18 +135,91 @@ def run_cpu(a, steps: int, warmup: int, candidates_per_step: int, seconds_budget
             "evals_per_s": candidates_per_step * len(times) / total}
 
 
+def run_reference_kernels(a, steps: int, warmup: int, seconds_budget: float | None = None) -> dict | None:
+    """Times the REFERENCE'S OWN kernels (OptimizedConvolution.cl compiled for the CPU into oracle/_ref by
+    oracle/ref_build/build_ref.sh) on all host cores.  One step = ONE candidate palette over the full per-GPU image
+    (a bounded sample of the GPU arm's 64-candidate step), through the reference's candidate chain for this path:
+    quantizeAndConvertToOpp (argmin + used flags) -> Opp2LAB -> CIEDE -> host double mean
+    (ImageManipulation.java:644-665,712), i.e. computeQuantizationErrorPopulation with the spatial-filter kernels
+    skipped (the identity-filter cost the north star's path scores).  The full chain including
+    computeScielabKernelsTemp/End is timed once and reported beside it.  Returns None when oracle/_ref is absent."""
+    from hybridquantization_b200 import synth
+    from oracle import hq_oracle as O
+    from oracle import hq_ref as R
+
+    if not R.build():
+        return None
+    L = R.load()
+    cores = R.default_threads()
+    w, h, K = a.width, a.rows_per_gpu, a.colors
+    n = w * h
+    img = synth.synth_image_rows(w, h, synth.SEED_BASE + 3, 0, h)
+    pal = synth.synth_palettes(a.batch, K)
+    rgb4 = R.makeinline(R.unit_planes(img))
+    # Lab of the original through the reference's kernels (RGB2XYZ -> XYZ2Opp -> Opp2LAB): the comparison image of CIEDE
+    xyz = R.rgb_to_xyz(R.unit_planes(img), cores)
+    opp0 = np.zeros_like(xyz); lab0 = np.zeros_like(xyz)
+    L.refcl_XYZ2Opp(R._ptr(xyz), R._ptr(opp0), n, cores)
+    L.refcl_Opp2LAB(R._ptr(opp0), R.D65[0], R.D65[1], R.D65[2], R._ptr(lab0), n, cores)
+    del xyz
+    opp = np.zeros((n, 4), np.float32); lab = np.zeros((n, 4), np.float32); err = np.zeros(n, np.float32)
+
+    def one(colors, full_chain=False):
+        used = np.zeros(K, np.int32)
+        L.refcl_quantizeAndConvertToOpp(R._ptr(rgb4), R._ptr(colors), K, R._ptr(used), R._ptr(opp), n, cores)
+        src = opp
+        if full_chain:
+            L.refcl_computeScielabKernelsTemp(R._ptr(opp), R._ptr(pk["filters4"][0]), R._ptr(pk["filters4"][1]), R._ptr(pk["filter3"]), pk["half"], w, h,
+                                              R._ptr(t1), R._ptr(t2), R._ptr(t3), n, cores)
+            L.refcl_computeScielabKernelsEnd(R._ptr(t1), R._ptr(t2), R._ptr(t3), R._ptr(pk["filters4"][0]), R._ptr(pk["filters4"][1]), R._ptr(pk["absfilter3"]),
+                                             pk["half"], h, w, R._ptr(conv), n, cores)
+            src = conv
+        L.refcl_Opp2LAB(R._ptr(src), R.D65[0], R.D65[1], R.D65[2], R._ptr(lab), n, cores)
+        L.refcl_CIEDE(R._ptr(lab0), R._ptr(lab), R._ptr(err), n, cores)
+        return float(err.sum(dtype=np.float64)) / n + 2.0 * int((used == 0).sum())   # averageArray + computePenalty (:712)
+
+    times = []
+    t_start = time.perf_counter()
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        cost = one(pal[s % a.batch])
+        dt = time.perf_counter() - t0
+        assert np.isfinite(cost)
+        if s >= warmup:
+            times.append(dt)
+        if seconds_budget is not None and s >= warmup and time.perf_counter() - t_start > seconds_budget:
+            break
+    f, ab = O.scielab_filters(72, 45.0)
+    pk = R.pack_filters(f, ab)
+    t1 = np.zeros((n, 4), np.float32); t2 = np.zeros((n, 4), np.float32); t3 = np.zeros(n, np.float32); conv = np.zeros((n, 4), np.float32)
+    t0 = time.perf_counter(); one(pal[0], True); full_s = time.perf_counter() - t0
+    total = sum(times)
+    return {"value": n * len(times) / total / 1e9, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"{len(times)} steps x 1 of {a.batch} candidates, full {w}x{h} image, K={K}; the reference's OptimizedConvolution.cl kernels "
+                      f"(quantizeAndConvertToOpp, Opp2LAB, CIEDE) compiled for the CPU (oracle/_ref, g++ -O3 x86-64-v3), {cores} threads, host double mean",
+            "ms_per_step": 1e3 * total / len(times), "steps": len(times), "evals_per_s": len(times) / total,
+            "full_chain_with_spatial_filters": {"value": n / full_s / 1e9, "unit": UNIT, "ms_per_candidate": 1e3 * full_s}}
+
+
 def main_reference(a, rank: int, world: int) -> None:
     if rank != 0:
         return
-    r = run_cpu(a, a.steps, a.warmup, candidates_per_step=1)
+    r = run_reference_kernels(a, a.steps, a.warmup)
+    note = ("reference arm: the reference's own OpenCL kernels (quantizeAndConvertToOpp -> Opp2LAB -> CIEDE -> host mean) compiled for the CPU "
+            "from /root/reference by oracle/ref_build/build_ref.sh, all host cores, one candidate per step; the Java/JavaCL host cannot run here (no JDK)")
+    if r is None:
+        r = run_cpu(a, a.steps, a.warmup, candidates_per_step=1)
+        note = ("reference arm: oracle/_ref is absent on this machine; this is the C oracle port (oracle/hq_oracle.c) timed on the host cores, "
+                "one candidate per step")
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": r["steps"],
             "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a, 1), "note": "CPU arm: the reference has no CPU implementation of this path and no JDK/OpenCL "
-                       "exists here; this is the C oracle port timed on the host cores, one candidate per step"},
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "config": {"workload": workload_name(a, 1), "note": note},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample") if k in r},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "swasa_evals_per_s": r["evals_per_s"]}
+    if "full_chain_with_spatial_filters" in r:
+        line["full_chain_with_spatial_filters"] = r["full_chain_with_spatial_filters"]
     print(json.dumps(line), flush=True)
 
 
@@ -306,8 +380,12 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
                                     "kernel_ms": rl_ms, "algorithmic_bytes_per_pixel": 15, "runs": "once per image, not per step",
                                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if hbm_peak else None}]
     if world == 1 and rank == 0 and not a.no_cpu_baseline:
-        cb = run_cpu(a, steps=1000, warmup=1, candidates_per_step=1, seconds_budget=a.cpu_baseline_seconds)
+        cb = run_reference_kernels(a, steps=1000, warmup=1, seconds_budget=a.cpu_baseline_seconds)
+        port = run_cpu(a, steps=1000, warmup=1, candidates_per_step=1, seconds_budget=a.cpu_baseline_seconds if cb is None else a.cpu_baseline_seconds / 2)
+        if cb is None:
+            cb = port
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"]["oracle_port"] = {k: port[k] for k in ("value", "unit", "cores", "sample")}
     be.close()
     if world > 1:
         dist.barrier()

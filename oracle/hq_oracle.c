@@ -1,7 +1,7 @@
 /* hq_oracle.c — CPU ORACLE (test infrastructure only; see hq_oracle.h for the rules).
  *
- * Plain C restatement of the reference's algorithm for the hot path.  PARITY UNPINNED:
- * the reference has no tests/golden vectors and cannot be built or run here.
+ * Plain C restatement of the reference's algorithm for the hot path, pinned bit for bit against the
+ * reference's own sources compiled for the CPU (oracle/_ref, tests/test_ref_pinning.py; see hq_oracle.h).
  * Compile with -ffp-contract=off: every fp32 expression below is meant to round after
  * each operation, as Java float arithmetic does; fused multiply-adds appear only where
  * they are written as fmaf().  Transcendentals are glibc's pow/exp/tanh in double, the

@@ -112,3 +112,72 @@ def test_golden_scielab_vectors(oracle):
     ei = oracle.error_image(img, quant, f, a)
     assert float(ei["deltaE"]).hex() == g["error_image_mean"]
     assert int(ei["errorImageU8"].astype(np.int64).sum()) == g["error_image_u8_sum"]
+
+
+# ---------------------------------------------------------------- fixtures generated by the REFERENCE'S OWN code
+# tests/golden/ref_vectors.json comes from oracle/_ref (the reference's sources compiled for the CPU,
+# tests/golden/make_ref_golden.py); these checks need neither /root/reference nor the _ref library.
+def test_reference_golden_java_lab(oracle):
+    g = load_golden("ref_vectors.json")["java_lab"]
+    u8 = np.array(g["u8"], np.uint8)
+    assert np.array_equal(bits(oracle.image_planes(u8, oracle.WHITE_D65, 1)[1].T.copy()).ravel(), bits(from_bits(g["lab_d65"])))
+    assert np.array_equal(bits(oracle.image_planes(u8, oracle.WHITE_D50, 1)[1].T.copy()).ravel(), bits(from_bits(g["lab_d50"])))
+    for c, w in zip(from_bits(g["float_rgb"], (-1, 3)), from_bits(g["float_lab_d65"], (-1, 3))):
+        assert np.array_equal(bits(oracle.srgb_to_lab(c)), bits(w))
+
+
+def test_reference_golden_filters(oracle):
+    for v in load_golden("ref_vectors.json")["filters"].values():
+        f, a = oracle.scielab_filters(v["dpi"], v["vd"])
+        assert f.shape[1] == v["taps"]
+        assert np.array_equal(bits(f).ravel(), bits(from_bits(v["filters"]))) and np.array_equal(bits(a), bits(from_bits(v["abs3"])))
+
+
+def test_reference_golden_opencl_chain(oracle):
+    from hybridquantization_b200 import synth
+
+    g = load_golden("ref_vectors.json")["cl"]
+    img = synth.synth_image(g["w"], g["h"], g["seed"], g["smooth"])
+    f, a = oracle.scielab_filters()
+    so = oracle.scielab_image(img, f, a)
+    assert np.array_equal(bits(so).ravel(), bits(from_bits(g["scielab_image"])))
+    pal = synth.synth_palettes(g["B"], g["K"])
+    ev = oracle.scielab_eval(img, f, a, so, pal, oracle.SPACE_SRGB)
+    assert [int(v) for v in ev["err_fx"]] == g["err_fx"]
+    assert [[int(c > 0) for c in row] for row in ev["counts"]] == g["used"]
+    for i in range(g["B"]):  # reference: double sum of floats / N + penalty; build: 2^-24 fixed point
+        assert abs(oracle.cost(ev["err_fx"][i], ev["counts"][i], g["w"] * g["h"], 0.5) - float.fromhex(g["costs"][i])) <= 2.0 ** -25
+    q = oracle.quantize(img, pal[0], oracle.SPACE_SRGB)
+    assert [float(v).hex() for v in q["f32"][:, :3].astype(np.float64).sum(axis=0)] == g["quantize_rgb_sum"]
+    assert [int(c > 0) for c in np.bincount(q["idx"], minlength=g["K"])] == g["quantize_used"]
+
+
+def test_reference_golden_swasa(oracle):
+    g = load_golden("ref_vectors.json")["swasa"]
+    L = oracle.load()
+    p = oracle.swasa_params(**g["params"])
+    r = oracle.Rng(); L.hqo_rng_seed(C.byref(r), g["seed"])
+    K = g["K"]
+    cur = np.zeros((K, 4), np.float32); L.hqo_generate_random_colors(C.byref(r), K, cur.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(bits(cur).ravel(), bits(from_bits(g["colors"][0])))
+    for it, want in zip(g["iterations"], g["colors"][1:]):
+        nxt = np.zeros_like(cur)
+        L.hqo_generate_neighboring_colors(C.byref(p), C.byref(r), cur.ctypes.data_as(C.c_void_p), nxt.ctypes.data_as(C.c_void_p), K, it)
+        assert np.array_equal(bits(nxt).ravel(), bits(from_bits(want)))
+        cur = nxt
+    assert [f"{int(np.float32(L.hqo_max_step_width(C.byref(p), i)).view(np.uint32)):08x}" for i in g["iterations"]] == g["step_width"]
+
+
+def test_reference_golden_whole_search(oracle):
+    """the plugin's search run from reference code only vs the oracle's reference-faithful mode"""
+    from hybridquantization_b200 import synth
+
+    for name, v in load_golden("ref_vectors.json")["search"].items():
+        img = synth.synth_image(v["w"], v["h"], v["image_seed"], True)
+        p = oracle.swasa_params(population=v["population"], imax=v["imax"], iTc=v["iTc"], seed=v["seed"], convergence=int(v["convergence"]),
+                                space=oracle.SPACE_SRGB, cost_model=1)
+        best, err, tr = oracle.find_best_quantization(img, v["K"], p, trace=True)
+        want = np.array([float.fromhex(x) for x in v["trace"]])
+        assert np.allclose(tr.reshape(-1), want, rtol=0, atol=2.0 ** -24), name
+        assert abs(err - float.fromhex(v["best_error"])) <= 2.0 ** -24, name
+        assert np.array_equal(bits(best).ravel(), bits(from_bits(v["best_colors"]))), name
