@@ -49,6 +49,12 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t dup2(float v) { return pack2(v, v); }
 __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
     uint64_t d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
@@ -67,7 +73,6 @@ __device__ __forceinline__ uint64_t dist2_pair(uint64_t X, uint64_t Y, uint64_t 
 }
 
 // ====================================================================== RGB -> Lab
-constexpr int kRlTilePx = kThreads * 4;  // 1024 px = 3072 B of packed RGB per CTA iteration
 
 // 256-entry u8 -> unit / linear-light tables ([0..255] unit, [256..511] linear), built once per context
 __global__ void decode_table_kernel(float* __restrict__ table) {
@@ -77,56 +82,143 @@ __global__ void decode_table_kernel(float* __restrict__ table) {
     table[256 + v] = hq_srgb_decode(u);
 }
 
+// ---- Lab of a PAIR of pixels from their linear-light RGB, packed f32x2 (sm_100a FMUL2 / FADD2 / FFMA2: one
+// instruction per two pixels).  Every packed lane performs the operation sequence of the single-source scalar
+// routines of hq_math.h — hq_dot3 (products and sums rounded, no contraction), the Markstein constant division
+// of hq_div_const, the fp32 cube root of hq_cbrtf — so each lane's result is bit-identical to theirs.  What is
+// dropped is hq_div_const's operand-range check: the kernel's inputs are u8 triples, and ALL 2^24 of them are
+// compared with the oracle for both white points on the device (test_rgb_to_lab_all_16m_colours).
+// Returns a 2-bit mask of the lanes whose cube roots need the fp64 routine (then the pixel is redone by
+// lab_of_pixel_f64).
+__device__ __noinline__ hq_float3 lab_of_pixel_f64(float R, float G, float B, hq_white white) {
+    return hq_linrgb_to_lab_f64(R, G, B, white);
+}
+// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even though both carry an explicit rounding
+// modifier (observed on CUDA 12.9: L = 116*fy - 16 came out unrounded), which Java float arithmetic must not do.
+// Wherever a packed PRODUCT feeds a packed SUM the sum is therefore written as fma(p, ONE, q) with ONE = (1.0f, 1.0f)
+// taken from a kernel parameter: p*1 + q rounds exactly like p + q, and an fma cannot be fused any further.
+__device__ __forceinline__ uint64_t add2_of_product(uint64_t p, uint64_t q, uint64_t ONE) { return fma2(p, ONE, q); }
+__device__ __forceinline__ uint64_t dot3_pair(float a, uint64_t x, float b, uint64_t y, float c, uint64_t z, uint64_t ONE) {
+    return add2_of_product(mul2(z, dup2(c)), add2_of_product(mul2(y, dup2(b)), mul2(x, dup2(a)), ONE), ONE);
+}
+__device__ __forceinline__ uint64_t div_const_pair(uint64_t x, float c, float rc) {  // RN(x / c), Markstein
+    const uint64_t q0 = mul2(x, dup2(rc));
+    const uint64_t rem = fma2(q0, dup2(-c), x);
+    return fma2(rem, dup2(rc), q0);
+}
+// ScielabProcessor.java:301 on two values; amb gets bit 0 / bit 1 set when lane 0 / 1 needs the fp64 cube root.
+// Lane for lane the operation sequence of hq_cbrtf_fast (hq_math.h).
+__device__ __forceinline__ uint64_t lab_f_pair(uint64_t t2, unsigned& amb, uint64_t ONE) {
+    float t0, t1;
+    unpack2(t2, t0, t1);
+    const uint64_t lin = add2(div_const_pair(t2, HQ_3LABDELTA2, HQ_RCP_3LABDELTA2), dup2(HQ_4_OVER_29));
+    float lg0, lg1, e0, e1, y0, y1, rq0, rq1;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg0) : "f"(t0));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg1) : "f"(t1));
+    unpack2(mul2(pack2(lg0, lg1), dup2(0x1.555556p-2f)), e0, e1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(e0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y1) : "f"(e1));
+    const uint64_t y = pack2(y0, y1), yn = y ^ 0x8000000080000000ull;
+    const uint64_t q = mul2(y, y);
+    const uint64_t nql = fma2(yn, y, q);      // q - y*y, exact
+    const uint64_t p = mul2(q, y);
+    const uint64_t npl = fma2(q, yn, p);      // p - q*y, exact
+    const uint64_t r = fma2(nql, y, add2(sub2(t2, p), npl));  // t - y^3
+    float q0, q1;
+    unpack2(q, q0, q1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rq0) : "f"(q0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rq1) : "f"(q1));
+    const uint64_t d = mul2(mul2(r, dup2(0x1.555556p-2f)), pack2(rq0, rq1));
+    const uint64_t s_lo = add2(y, fma2(y, dup2(-HQ_CBRT_ETA), d));
+    const uint64_t s_hi = add2(y, fma2(y, dup2(HQ_CBRT_ETA), d));
+    float a0, a1, b0, b1, l0, l1;
+    unpack2(s_lo, a0, a1); unpack2(s_hi, b0, b1); unpack2(lin, l0, l1);
+    const bool big0 = t0 > HQ_LABDELTA3, big1 = t1 > HQ_LABDELTA3;
+    if (big0 && a0 != b0) amb |= 1u;
+    if (big1 && a1 != b1) amb |= 2u;
+    (void)ONE;
+    return pack2(big0 ? a0 : l0, big1 ? a1 : l1);
+}
+__device__ __forceinline__ unsigned lab_of_pixel_pair(uint64_t R, uint64_t G, uint64_t B, const hq_white& white, uint64_t ONE,
+                                                      uint64_t& L, uint64_t& A, uint64_t& Bv) {
+    // ScielabProcessor.java:286-290, :295-298 (constants as in hq_linrgb_to_opp / hq_opp_to_lab)
+    const uint64_t ox = dot3_pair(0.26641335000823f, R, 0.60316740257478f, G, 0.0011333302293f, B, ONE);
+    const uint64_t oy = dot3_pair(-0.12197400229389f, R, 0.05598088396616f, G, 0.01326365114329f, B, ONE);
+    const uint64_t oz = dot3_pair(-0.08033445917708f, R, -0.33146741170125f, G, 0.44913244757774f, B, ONE);
+    const uint64_t X = dot3_pair(0.97959616044562807864f, ox, -1.5347157012664408981f, oy, 0.44459764330437399288f, oz, ONE);
+    const uint64_t Y = dot3_pair(1.188977906742323787f, ox, 0.7643549575179937615f, oy, 0.13512574791125839373f, oz, ONE);
+    const uint64_t Z = dot3_pair(1.2318333139247290457f, ox, 1.1631592597636512884f, oy, 2.0784075888008567862f, oz, ONE);
+    unsigned amb = 0u;
+    const uint64_t fx = lab_f_pair(div_const_pair(X, white.x, white.rx), amb, ONE);
+    const uint64_t fy = lab_f_pair(Y, amb, ONE);  // illuminant[1] == 1.0f for both white points (:20-21)
+    const uint64_t fz = lab_f_pair(div_const_pair(Z, white.z, white.rz), amb, ONE);
+    L = add2_of_product(mul2(dup2(116.0f), fy), dup2(-16.0f), ONE);
+    A = mul2(dup2(500.0f), sub2(fx, fy));
+    Bv = mul2(dup2(200.0f), sub2(fy, fz));
+    return amb;
+}
+
+constexpr int kRlWarpPx = 128;  // pixels per warp iteration: 384 B of packed RGB, 4 pixels per lane
 __global__ void __launch_bounds__(kThreads)
-rgb_to_lab_kernel(const uint8_t* __restrict__ rgb, size_t n, size_t stride, int whitepoint,
+rgb_to_lab_kernel(const uint8_t* __restrict__ rgb, size_t n, size_t stride, int whitepoint, float one,
                   const float* __restrict__ table, float* __restrict__ lab, float* __restrict__ unit) {
-    __shared__ __align__(16) uint32_t s_stage[kRlTilePx * 3 / 4];  // 768 words
+    const uint64_t ONE = dup2(one);  // 1.0f that ptxas cannot see (add2_of_product)
+    __shared__ __align__(16) uint32_t s_stage[kThreads / 32][kRlWarpPx * 3 / 4];  // 96 words per warp
     __shared__ float s_lin[256];
     __shared__ float s_unit[256];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     s_unit[tid] = table[tid];
     s_lin[tid] = table[256 + tid];
+    __syncthreads();  // the only CTA-wide barrier: every warp stages and converts its own tiles
     const hq_white white = hq_make_white(whitepoint);
-    const size_t ntiles = (n + kRlTilePx - 1) / kRlTilePx;
+    uint32_t* stage = s_stage[warp];
+    const size_t ntiles = (n + kRlWarpPx - 1) / kRlWarpPx;
+    const size_t tstride = (size_t)gridDim.x * (kThreads / 32);
     const bool aligned = (reinterpret_cast<uintptr_t>(rgb) & 15) == 0;
-    // software pipeline: the next tile's 16 bytes are in flight while this tile is converted
-    const bool loader = tid < kRlTilePx * 3 / 16;
+    // software pipeline: the next tile's 16 bytes per lane are in flight while this tile is converted
+    const bool loader = lane < kRlWarpPx * 3 / 16;  // 24 lanes x 16 B = 384 B, fully coalesced
+    auto full_tile = [&](size_t t) { return aligned && (t + 1) * (size_t)kRlWarpPx <= n; };
+    size_t tile = (size_t)blockIdx.x * (kThreads / 32) + warp;  // a CTA's 8 warps cover 1024 consecutive pixels
     uint4 pre = make_uint4(0, 0, 0, 0);
-    auto full_tile = [&](size_t t) { return aligned && (t + 1) * (size_t)kRlTilePx <= n; };
-    if (blockIdx.x < ntiles && full_tile(blockIdx.x) && loader)
-        pre = __ldg(reinterpret_cast<const uint4*>(rgb + (size_t)blockIdx.x * kRlTilePx * 3) + tid);
-    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const size_t px0 = tile * kRlTilePx;
-        const size_t byte0 = px0 * 3;
-        const size_t tile_px = (n - px0 < (size_t)kRlTilePx) ? (n - px0) : (size_t)kRlTilePx;
-        __syncthreads();  // previous tile fully consumed (and the tables written)
+    if (tile < ntiles && full_tile(tile) && loader) pre = __ldg(reinterpret_cast<const uint4*>(rgb + tile * (size_t)(kRlWarpPx * 3)) + lane);
+    for (; tile < ntiles; tile += tstride) {
+        const size_t px0 = tile * kRlWarpPx;
+        __syncwarp();  // the previous tile's words have been read by every lane
         if (full_tile(tile)) {
-            // fully coalesced 128-bit loads: 192 x 16 B = one tile (byte0 is a multiple of 3072)
-            if (loader) reinterpret_cast<uint4*>(s_stage)[tid] = pre;
+            if (loader) reinterpret_cast<uint4*>(stage)[lane] = pre;
         } else {
-            uint8_t* dst = reinterpret_cast<uint8_t*>(s_stage);
-            const size_t nbytes = tile_px * 3;
-            for (size_t i = tid; i < (size_t)kRlTilePx * 3; i += kThreads)
-                dst[i] = (i < nbytes) ? rgb[byte0 + i] : (uint8_t)0;
+            const size_t byte0 = px0 * 3, nbytes = (n - px0 < (size_t)kRlWarpPx ? n - px0 : (size_t)kRlWarpPx) * 3;
+            uint8_t* dst = reinterpret_cast<uint8_t*>(stage);
+            for (size_t i = lane; i < (size_t)kRlWarpPx * 3; i += 32) dst[i] = (i < nbytes) ? rgb[byte0 + i] : (uint8_t)0;
         }
-        __syncthreads();
+        __syncwarp();
         {
-            const size_t nt = tile + gridDim.x;
-            if (nt < ntiles && full_tile(nt) && loader)
-                pre = __ldg(reinterpret_cast<const uint4*>(rgb + nt * (size_t)kRlTilePx * 3) + tid);
+            const size_t nt = tile + tstride;
+            if (nt < ntiles && full_tile(nt) && loader) pre = __ldg(reinterpret_cast<const uint4*>(rgb + nt * (size_t)(kRlWarpPx * 3)) + lane);
         }
-        // 4 pixels = 3 words per thread, bank-conflict free (word stride 3 is coprime with 32)
-        const uint32_t w0 = s_stage[3 * tid], w1 = s_stage[3 * tid + 1], w2 = s_stage[3 * tid + 2];
+        // 4 pixels = 3 words per lane, bank-conflict free (word stride 3 is coprime with 32)
+        const uint32_t w0 = stage[3 * lane], w1 = stage[3 * lane + 1], w2 = stage[3 * lane + 2];
         const uint32_t c[12] = {w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u, w0 >> 24,
                                 w1 & 255u, (w1 >> 8) & 255u, (w1 >> 16) & 255u, w1 >> 24,
                                 w2 & 255u, (w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24};
-        float L[4], A[4], Bv[4];
+        float lin[12];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const hq_float3 v = hq_linrgb_to_lab(s_lin[c[3 * j]], s_lin[c[3 * j + 1]], s_lin[c[3 * j + 2]], white);
-            L[j] = v.x; A[j] = v.y; Bv[j] = v.z;
+        for (int i = 0; i < 12; ++i) lin[i] = s_lin[c[i]];
+        float L[4], A[4], Bv[4];
+        unsigned amb = 0u;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {  // two pixel PAIRS, packed f32x2 arithmetic
+            uint64_t l2, a2, b2;
+            amb |= lab_of_pixel_pair(pack2(lin[6 * h], lin[6 * h + 3]), pack2(lin[6 * h + 1], lin[6 * h + 4]), pack2(lin[6 * h + 2], lin[6 * h + 5]),
+                                     white, ONE, l2, a2, b2) << (2 * h);
+            unpack2(l2, L[2 * h], L[2 * h + 1]); unpack2(a2, A[2 * h], A[2 * h + 1]); unpack2(b2, Bv[2 * h], Bv[2 * h + 1]);
         }
-        const size_t p = px0 + 4 * (size_t)tid;
+        if (amb) {  // a cube root within 2^-15 ulp of a rounding boundary (~1 pixel in 5,000): that pixel through the fp64 routine
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (amb & (1u << j)) { const hq_float3 v = lab_of_pixel_f64(lin[3 * j], lin[3 * j + 1], lin[3 * j + 2], white); L[j] = v.x; A[j] = v.y; Bv[j] = v.z; }
+        }
+        const size_t p = px0 + 4 * (size_t)lane;
         if (p + 4 <= n) {  // 128-bit coalesced plane stores
             *reinterpret_cast<float4*>(lab + p) = make_float4(L[0], L[1], L[2], L[3]);
             *reinterpret_cast<float4*>(lab + stride + p) = make_float4(A[0], A[1], A[2], A[3]);
@@ -664,10 +756,17 @@ cudaError_t launch_decode_table(float* d_table, cudaStream_t stream) {
 cudaError_t launch_rgb_to_lab(const uint8_t* d_rgb, size_t n, size_t stride, int whitepoint, const float* d_table,
                               float* d_lab, float* d_unit, int sm_count, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    const size_t ntiles = (n + kRlTilePx - 1) / kRlTilePx;
-    size_t grid = (size_t)sm_count * 8;  // 8 resident CTAs per SM, grid-stride over 1024-px tiles
-    if (grid > ntiles) grid = ntiles;
-    rgb_to_lab_kernel<<<(unsigned)grid, kThreads, 0, stream>>>(d_rgb, n, stride, whitepoint, d_table, d_lab, d_unit);
+    const size_t ntiles = (n + kRlWarpPx - 1) / kRlWarpPx;
+    static int occ = 0;  // resident CTAs per SM (register-limited), queried once
+    if (occ == 0) {
+        int o = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, rgb_to_lab_kernel, kThreads, 0) != cudaSuccess || o < 1) o = 4;
+        occ = o;
+    }
+    size_t grid = (size_t)sm_count * occ;  // exactly one wave of resident CTAs, warps grid-stride over 128-px tiles
+    const size_t need = (ntiles + kThreads / 32 - 1) / (kThreads / 32);
+    if (grid > need) grid = need;
+    rgb_to_lab_kernel<<<(unsigned)grid, kThreads, 0, stream>>>(d_rgb, n, stride, whitepoint, 1.0f, d_table, d_lab, d_unit);
     return cudaGetLastError();
 }
 

@@ -111,10 +111,10 @@ HQ_HD double hq_widen_pos(float f) {
 
 // ---------------------------------------------------------------- (float)pow(t, 1.0/3.0)
 // Restates `(float)Math.pow(t, 1.0 / 3.0)` (ScielabProcessor.java:301,303,305) for
-// positive normal t.  Inverse-cube-root Newton in fp32 from a bit seed, then two
-// Newton steps on y^3 = t in fp64 whose residual is formed with one fma; the fp64
-// value is within 1 ulp(double) of the true root before the final narrowing.
-HQ_HD float hq_cbrtf(float t) {
+// positive normal t.  REFERENCE ROUTINE (host, and the device's fallback): inverse-cube-root
+// Newton in fp32 from a seed, then two Newton steps on y^3 = t in fp64 whose residual is formed
+// with one fma; the fp64 value is within 1 ulp(double) of the true root before the final narrowing.
+HQ_HD float hq_cbrtf_f64(float t) {
 #if defined(__CUDA_ARCH__)
     // device seed: x ~ t^(-1/3) = 2^(-log2(t)/3) from the SFU approximations (rel. error < 1e-6).
     // The SFU results are not reproducible on the host, but the value returned below does not
@@ -147,6 +147,45 @@ HQ_HD float hq_cbrtf(float t) {
         y = HQ_DFMA(-r, h, y);
     }
     return (float)y;
+}
+
+#if defined(__CUDACC__)
+// DEVICE FAST PATH, fp32 only.  y0 = 2^(log2(t)/3) from the SFU (rel. error ~2^-21), then ONE Newton
+// correction whose residual t - y0^3 is formed without cancellation error: y0*y0 = q + ql and
+// q*y0 = p + pl exactly (fma), t - p is exact (Sterbenz), so r = ((t - p) - pl) - ql*y0 carries a
+// relative error of ~2^-24 only.  d = r / (3 q) is the correction (|d| <= ~8 ulp, known to ~2^-18 ulp
+// including Newton's second-order term).  The root is y0 + d: it is rounded twice, with d moved down and up
+// by y0 * 2^-39 (2^-16 .. 2^-15 ulp, several times the uncertainty of d).  When both roundings agree that
+// float is the correctly rounded root; when they differ (the root is within 2^-15 ulp of a rounding
+// boundary, one input in ~16,000) the fp64 routine above decides.  The boundaries of (float)pow(t, 1.0/3.0)
+// (double pow, then narrowed) sit at the same midpoints to 2^-29 ulp, far inside that window.  Equality with
+// the oracle for EVERY float of the domain is verified on the B200 (test_device_math_exhaustive).
+// The SFU operations carry .ftz: all operands are normal floats on the domain, .ftz only removes the
+// denormal pre-scaling code nvcc otherwise wraps around MUFU.
+#define HQ_CBRT_ETA 0x1p-39f
+__device__ __forceinline__ float hq_cbrtf_fast(float t) {
+    float lg, y0, rq;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(t));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(__fmul_rn(lg, 0x1.555556p-2f)));
+    const float q = __fmul_rn(y0, y0);
+    const float nql = __fmaf_rn(-y0, y0, q);   // q - y0*y0, exact
+    const float p = __fmul_rn(q, y0);
+    const float npl = __fmaf_rn(q, -y0, p);    // p - q*y0, exact
+    const float r = __fmaf_rn(nql, y0, __fadd_rn(__fsub_rn(t, p), npl));  // t - y0^3
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rq) : "f"(q));
+    const float d = __fmul_rn(__fmul_rn(r, 0x1.555556p-2f), rq);
+    const float s_lo = __fadd_rn(y0, __fmaf_rn(y0, -HQ_CBRT_ETA, d));
+    const float s_hi = __fadd_rn(y0, __fmaf_rn(y0, HQ_CBRT_ETA, d));
+    if (s_lo != s_hi) return hq_cbrtf_f64(t);
+    return s_lo;
+}
+#endif
+HQ_HD float hq_cbrtf(float t) {
+#if defined(__CUDA_ARCH__)
+    return hq_cbrtf_fast(t);
+#else
+    return hq_cbrtf_f64(t);
+#endif
 }
 
 // ---------------------------------------------------------------- x / c for a constant c
@@ -259,6 +298,10 @@ HQ_HD float hq_lab_f(float t) {
     if (t > HQ_LABDELTA3) return hq_cbrtf(t);
     return HQ_FADD(hq_div_const(t, HQ_3LABDELTA2, HQ_RCP_3LABDELTA2), HQ_4_OVER_29);
 }
+HQ_HD float hq_lab_f_f64(float t) {  // same with the fp64 cube root only (the device's re-check path)
+    if (t > HQ_LABDELTA3) return hq_cbrtf_f64(t);
+    return HQ_FADD(hq_div_const(t, HQ_3LABDELTA2, HQ_RCP_3LABDELTA2), HQ_4_OVER_29);
+}
 
 // white point with the reciprocals the constant division needs
 struct hq_white {
@@ -294,6 +337,22 @@ HQ_HD hq_float3 hq_opp_to_lab(hq_float3 o, hq_white white) {
 // linear RGB -> Lab (sRGBtoLab = OpptoLab(sRGBtoOpp(.)), ScielabProcessor.java:432)
 HQ_HD hq_float3 hq_linrgb_to_lab(float R, float G, float B, hq_white white) {
     return hq_opp_to_lab(hq_linrgb_to_opp(R, G, B), white);
+}
+// the same through the fp64 cube root only: what rgb_to_lab_kernel falls back to for the pixels its packed
+// fp32 fast path cannot decide
+HQ_HD hq_float3 hq_linrgb_to_lab_f64(float R, float G, float B, hq_white white) {
+    const hq_float3 o = hq_linrgb_to_opp(R, G, B);
+    const float X = hq_dot3(0.97959616044562807864f, o.x, -1.5347157012664408981f, o.y, 0.44459764330437399288f, o.z);
+    const float Y = hq_dot3(1.188977906742323787f, o.x, 0.7643549575179937615f, o.y, 0.13512574791125839373f, o.z);
+    const float Z = hq_dot3(1.2318333139247290457f, o.x, 1.1631592597636512884f, o.y, 2.0784075888008567862f, o.z);
+    const float fx = hq_lab_f_f64(hq_div_const(X, white.x, white.rx));
+    const float fy = hq_lab_f_f64(white.y == 1.0f ? Y : HQ_FDIV(Y, white.y));
+    const float fz = hq_lab_f_f64(hq_div_const(Z, white.z, white.rz));
+    hq_float3 lab;
+    lab.x = HQ_FSUB(HQ_FMUL(116.0f, fy), 16.0f);
+    lab.y = HQ_FMUL(500.0f, HQ_FSUB(fx, fy));
+    lab.z = HQ_FMUL(200.0f, HQ_FSUB(fy, fz));
+    return lab;
 }
 
 // sRGB floats in [0,1] (a palette colour) -> Lab
