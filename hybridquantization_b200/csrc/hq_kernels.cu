@@ -106,19 +106,19 @@ __device__ __forceinline__ uint64_t div_const_pair(uint64_t x, float c, float rc
     const uint64_t rem = fma2(q0, dup2(-c), x);
     return fma2(rem, dup2(rc), q0);
 }
-// ScielabProcessor.java:301 on two values; amb gets bit 0 / bit 1 set when lane 0 / 1 needs the fp64 cube root.
-// Lane for lane the operation sequence of hq_cbrtf_fast (hq_math.h).
-__device__ __forceinline__ uint64_t lab_f_pair(uint64_t t2, unsigned& amb, uint64_t ONE) {
+// cube roots of two values, lane for lane the operation sequence of hq_cbrtf_fast (hq_math.h); amb is set when
+// either lane's two roundings disagree (ordered compare: a lane holding 0 produces NaN here, is never flagged and
+// is replaced by the linear segment in lab_of_pixel_pair)
+__device__ __forceinline__ uint64_t cbrt_pair(uint64_t t2, bool& amb) {
     float t0, t1;
     unpack2(t2, t0, t1);
-    const uint64_t lin = add2(div_const_pair(t2, HQ_3LABDELTA2, HQ_RCP_3LABDELTA2), dup2(HQ_4_OVER_29));
     float lg0, lg1, e0, e1, y0, y1, rq0, rq1;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg0) : "f"(t0));
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg1) : "f"(t1));
     unpack2(mul2(pack2(lg0, lg1), dup2(0x1.555556p-2f)), e0, e1);
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(e0));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y1) : "f"(e1));
-    const uint64_t y = pack2(y0, y1), yn = y ^ 0x8000000080000000ull;
+    const uint64_t y = pack2(y0, y1), yn = pack2(-y0, -y1);
     const uint64_t q = mul2(y, y);
     const uint64_t nql = fma2(yn, y, q);      // q - y*y, exact
     const uint64_t p = mul2(q, y);
@@ -131,27 +131,36 @@ __device__ __forceinline__ uint64_t lab_f_pair(uint64_t t2, unsigned& amb, uint6
     const uint64_t d = mul2(mul2(r, dup2(0x1.555556p-2f)), pack2(rq0, rq1));
     const uint64_t s_lo = add2(y, fma2(y, dup2(-HQ_CBRT_ETA), d));
     const uint64_t s_hi = add2(y, fma2(y, dup2(HQ_CBRT_ETA), d));
-    float a0, a1, b0, b1, l0, l1;
-    unpack2(s_lo, a0, a1); unpack2(s_hi, b0, b1); unpack2(lin, l0, l1);
-    const bool big0 = t0 > HQ_LABDELTA3, big1 = t1 > HQ_LABDELTA3;
-    if (big0 && a0 != b0) amb |= 1u;
-    if (big1 && a1 != b1) amb |= 2u;
-    (void)ONE;
-    return pack2(big0 ? a0 : l0, big1 ? a1 : l1);
+    float a0, a1, b0, b1;
+    unpack2(s_lo, a0, a1); unpack2(s_hi, b0, b1);
+    amb = amb || (a0 < b0) || (a1 < b1);
+    return s_lo;
 }
-__device__ __forceinline__ unsigned lab_of_pixel_pair(uint64_t R, uint64_t G, uint64_t B, const hq_white& white, uint64_t ONE,
-                                                      uint64_t& L, uint64_t& A, uint64_t& Bv) {
+// the linear segment of ScielabProcessor.java:301, t / (3*LABDELTA2) + 4f/29f, for the lanes with t <= LABDELTA3
+__device__ __forceinline__ uint64_t lab_f_blend_pair(uint64_t t2, uint64_t cb) {
+    float t0, t1, c0, c1, l0, l1;
+    unpack2(t2, t0, t1); unpack2(cb, c0, c1);
+    unpack2(add2(div_const_pair(t2, HQ_3LABDELTA2, HQ_RCP_3LABDELTA2), dup2(HQ_4_OVER_29)), l0, l1);
+    return pack2(t0 > HQ_LABDELTA3 ? c0 : l0, t1 > HQ_LABDELTA3 ? c1 : l1);
+}
+__device__ __forceinline__ bool lab_of_pixel_pair(uint64_t R, uint64_t G, uint64_t B, const hq_white& white, uint64_t ONE,
+                                                  uint64_t& L, uint64_t& A, uint64_t& Bv) {
     // ScielabProcessor.java:286-290, :295-298 (constants as in hq_linrgb_to_opp / hq_opp_to_lab)
     const uint64_t ox = dot3_pair(0.26641335000823f, R, 0.60316740257478f, G, 0.0011333302293f, B, ONE);
     const uint64_t oy = dot3_pair(-0.12197400229389f, R, 0.05598088396616f, G, 0.01326365114329f, B, ONE);
     const uint64_t oz = dot3_pair(-0.08033445917708f, R, -0.33146741170125f, G, 0.44913244757774f, B, ONE);
     const uint64_t X = dot3_pair(0.97959616044562807864f, ox, -1.5347157012664408981f, oy, 0.44459764330437399288f, oz, ONE);
-    const uint64_t Y = dot3_pair(1.188977906742323787f, ox, 0.7643549575179937615f, oy, 0.13512574791125839373f, oz, ONE);
+    const uint64_t ty = dot3_pair(1.188977906742323787f, ox, 0.7643549575179937615f, oy, 0.13512574791125839373f, oz, ONE);
     const uint64_t Z = dot3_pair(1.2318333139247290457f, ox, 1.1631592597636512884f, oy, 2.0784075888008567862f, oz, ONE);
-    unsigned amb = 0u;
-    const uint64_t fx = lab_f_pair(div_const_pair(X, white.x, white.rx), amb, ONE);
-    const uint64_t fy = lab_f_pair(Y, amb, ONE);  // illuminant[1] == 1.0f for both white points (:20-21)
-    const uint64_t fz = lab_f_pair(div_const_pair(Z, white.z, white.rz), amb, ONE);
+    const uint64_t tx = div_const_pair(X, white.x, white.rx);  // illuminant[1] == 1.0f for both white points (:20-21): ty = Y
+    const uint64_t tz = div_const_pair(Z, white.z, white.rz);
+    bool amb = false;
+    uint64_t fx = cbrt_pair(tx, amb), fy = cbrt_pair(ty, amb), fz = cbrt_pair(tz, amb);
+    float x0, x1, y0, y1, z0, z1;
+    unpack2(tx, x0, x1); unpack2(ty, y0, y1); unpack2(tz, z0, z1);
+    if (!(fminf(min3(x0, x1, y0), min3(y1, z0, z1)) > HQ_LABDELTA3)) {  // a dark pixel: some value on the linear segment
+        fx = lab_f_blend_pair(tx, fx); fy = lab_f_blend_pair(ty, fy); fz = lab_f_blend_pair(tz, fz);
+    }
     L = add2_of_product(mul2(dup2(116.0f), fy), dup2(-16.0f), ONE);
     A = mul2(dup2(500.0f), sub2(fx, fy));
     Bv = mul2(dup2(200.0f), sub2(fy, fz));
@@ -159,7 +168,8 @@ __device__ __forceinline__ unsigned lab_of_pixel_pair(uint64_t R, uint64_t G, ui
 }
 
 constexpr int kRlWarpPx = 128;  // pixels per warp iteration: 384 B of packed RGB, 4 pixels per lane
-__global__ void __launch_bounds__(kThreads)
+template <bool UNIT>
+__global__ void __launch_bounds__(kThreads, 4)
 rgb_to_lab_kernel(const uint8_t* __restrict__ rgb, size_t n, size_t stride, int whitepoint, float one,
                   const float* __restrict__ table, float* __restrict__ lab, float* __restrict__ unit) {
     const uint64_t ONE = dup2(one);  // 1.0f that ptxas cannot see (add2_of_product)
@@ -172,19 +182,20 @@ rgb_to_lab_kernel(const uint8_t* __restrict__ rgb, size_t n, size_t stride, int 
     __syncthreads();  // the only CTA-wide barrier: every warp stages and converts its own tiles
     const hq_white white = hq_make_white(whitepoint);
     uint32_t* stage = s_stage[warp];
-    const size_t ntiles = (n + kRlWarpPx - 1) / kRlWarpPx;
-    const size_t tstride = (size_t)gridDim.x * (kThreads / 32);
-    const bool aligned = (reinterpret_cast<uintptr_t>(rgb) & 15) == 0;
-    // software pipeline: the next tile's 16 bytes per lane are in flight while this tile is converted
+    const uint32_t ntiles = (uint32_t)((n + kRlWarpPx - 1) / kRlWarpPx);
+    // tiles [0, nfull) are complete and 16-byte aligned: staged with one 128-bit load per lane
+    const uint32_t nfull = (reinterpret_cast<uintptr_t>(rgb) & 15) == 0 ? (uint32_t)(n / kRlWarpPx) : 0u;
+    const uint32_t tstride = gridDim.x * (kThreads / 32);
     const bool loader = lane < kRlWarpPx * 3 / 16;  // 24 lanes x 16 B = 384 B, fully coalesced
-    auto full_tile = [&](size_t t) { return aligned && (t + 1) * (size_t)kRlWarpPx <= n; };
-    size_t tile = (size_t)blockIdx.x * (kThreads / 32) + warp;  // a CTA's 8 warps cover 1024 consecutive pixels
+    const uint4* src = reinterpret_cast<const uint4*>(rgb) + lane;
+    uint32_t tile = blockIdx.x * (kThreads / 32) + warp;  // a CTA's 8 warps cover 1024 consecutive pixels
+    // software pipeline: the next tile's 16 bytes per lane are in flight while this tile is converted
     uint4 pre = make_uint4(0, 0, 0, 0);
-    if (tile < ntiles && full_tile(tile) && loader) pre = __ldg(reinterpret_cast<const uint4*>(rgb + tile * (size_t)(kRlWarpPx * 3)) + lane);
+    if (tile < nfull && loader) pre = __ldg(src + (size_t)tile * (kRlWarpPx * 3 / 16));
     for (; tile < ntiles; tile += tstride) {
-        const size_t px0 = tile * kRlWarpPx;
+        const size_t px0 = (size_t)tile * kRlWarpPx;
         __syncwarp();  // the previous tile's words have been read by every lane
-        if (full_tile(tile)) {
+        if (tile < nfull) {
             if (loader) reinterpret_cast<uint4*>(stage)[lane] = pre;
         } else {
             const size_t byte0 = px0 * 3, nbytes = (n - px0 < (size_t)kRlWarpPx ? n - px0 : (size_t)kRlWarpPx) * 3;
@@ -192,51 +203,47 @@ rgb_to_lab_kernel(const uint8_t* __restrict__ rgb, size_t n, size_t stride, int 
             for (size_t i = lane; i < (size_t)kRlWarpPx * 3; i += 32) dst[i] = (i < nbytes) ? rgb[byte0 + i] : (uint8_t)0;
         }
         __syncwarp();
-        {
-            const size_t nt = tile + tstride;
-            if (nt < ntiles && full_tile(nt) && loader) pre = __ldg(reinterpret_cast<const uint4*>(rgb + nt * (size_t)(kRlWarpPx * 3)) + lane);
-        }
+        if (tile + tstride < nfull && loader) pre = __ldg(src + (size_t)(tile + tstride) * (kRlWarpPx * 3 / 16));
         // 4 pixels = 3 words per lane, bank-conflict free (word stride 3 is coprime with 32)
         const uint32_t w0 = stage[3 * lane], w1 = stage[3 * lane + 1], w2 = stage[3 * lane + 2];
-        const uint32_t c[12] = {w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u, w0 >> 24,
-                                w1 & 255u, (w1 >> 8) & 255u, (w1 >> 16) & 255u, w1 >> 24,
-                                w2 & 255u, (w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24};
+        auto byte_of = [&](int i) { const uint32_t w = i < 4 ? w0 : (i < 8 ? w1 : w2); return (w >> (8 * (i & 3))) & 255u; };
         float lin[12];
 #pragma unroll
-        for (int i = 0; i < 12; ++i) lin[i] = s_lin[c[i]];
+        for (int i = 0; i < 12; ++i) lin[i] = s_lin[byte_of(i)];
         float L[4], A[4], Bv[4];
-        unsigned amb = 0u;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {  // two pixel PAIRS, packed f32x2 arithmetic
             uint64_t l2, a2, b2;
-            amb |= lab_of_pixel_pair(pack2(lin[6 * h], lin[6 * h + 3]), pack2(lin[6 * h + 1], lin[6 * h + 4]), pack2(lin[6 * h + 2], lin[6 * h + 5]),
-                                     white, ONE, l2, a2, b2) << (2 * h);
+            const bool amb = lab_of_pixel_pair(pack2(lin[6 * h], lin[6 * h + 3]), pack2(lin[6 * h + 1], lin[6 * h + 4]),
+                                               pack2(lin[6 * h + 2], lin[6 * h + 5]), white, ONE, l2, a2, b2);
             unpack2(l2, L[2 * h], L[2 * h + 1]); unpack2(a2, A[2 * h], A[2 * h + 1]); unpack2(b2, Bv[2 * h], Bv[2 * h + 1]);
-        }
-        if (amb) {  // a cube root within 2^-15 ulp of a rounding boundary (~1 pixel in 5,000): that pixel through the fp64 routine
+            if (amb) {  // a cube root within 2^-15 ulp of a rounding boundary (about one pair in 3,000): both pixels through fp64
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (amb & (1u << j)) { const hq_float3 v = lab_of_pixel_f64(lin[3 * j], lin[3 * j + 1], lin[3 * j + 2], white); L[j] = v.x; A[j] = v.y; Bv[j] = v.z; }
+                for (int j = 2 * h; j < 2 * h + 2; ++j) {
+                    const hq_float3 v = lab_of_pixel_f64(lin[3 * j], lin[3 * j + 1], lin[3 * j + 2], white);
+                    L[j] = v.x; A[j] = v.y; Bv[j] = v.z;
+                }
+            }
         }
         const size_t p = px0 + 4 * (size_t)lane;
         if (p + 4 <= n) {  // 128-bit coalesced plane stores
             *reinterpret_cast<float4*>(lab + p) = make_float4(L[0], L[1], L[2], L[3]);
             *reinterpret_cast<float4*>(lab + stride + p) = make_float4(A[0], A[1], A[2], A[3]);
             *reinterpret_cast<float4*>(lab + 2 * stride + p) = make_float4(Bv[0], Bv[1], Bv[2], Bv[3]);
-            if (unit) {
-                *reinterpret_cast<float4*>(unit + p) = make_float4(s_unit[c[0]], s_unit[c[3]], s_unit[c[6]], s_unit[c[9]]);
-                *reinterpret_cast<float4*>(unit + stride + p) = make_float4(s_unit[c[1]], s_unit[c[4]], s_unit[c[7]], s_unit[c[10]]);
-                *reinterpret_cast<float4*>(unit + 2 * stride + p) = make_float4(s_unit[c[2]], s_unit[c[5]], s_unit[c[8]], s_unit[c[11]]);
+            if (UNIT) {
+                *reinterpret_cast<float4*>(unit + p) = make_float4(s_unit[byte_of(0)], s_unit[byte_of(3)], s_unit[byte_of(6)], s_unit[byte_of(9)]);
+                *reinterpret_cast<float4*>(unit + stride + p) = make_float4(s_unit[byte_of(1)], s_unit[byte_of(4)], s_unit[byte_of(7)], s_unit[byte_of(10)]);
+                *reinterpret_cast<float4*>(unit + 2 * stride + p) = make_float4(s_unit[byte_of(2)], s_unit[byte_of(5)], s_unit[byte_of(8)], s_unit[byte_of(11)]);
             }
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if (p + j < n) {
                     lab[p + j] = L[j]; lab[stride + p + j] = A[j]; lab[2 * stride + p + j] = Bv[j];
-                    if (unit) {
-                        unit[p + j] = s_unit[c[3 * j]];
-                        unit[stride + p + j] = s_unit[c[3 * j + 1]];
-                        unit[2 * stride + p + j] = s_unit[c[3 * j + 2]];
+                    if (UNIT) {
+                        unit[p + j] = s_unit[byte_of(3 * j)];
+                        unit[stride + p + j] = s_unit[byte_of(3 * j + 1)];
+                        unit[2 * stride + p + j] = s_unit[byte_of(3 * j + 2)];
                     }
                 }
         }
@@ -756,17 +763,13 @@ cudaError_t launch_decode_table(float* d_table, cudaStream_t stream) {
 cudaError_t launch_rgb_to_lab(const uint8_t* d_rgb, size_t n, size_t stride, int whitepoint, const float* d_table,
                               float* d_lab, float* d_unit, int sm_count, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
+    if (n / kRlWarpPx >= 0xffffffffull) return cudaErrorInvalidValue;  // 32-bit tile counters
     const size_t ntiles = (n + kRlWarpPx - 1) / kRlWarpPx;
-    static int occ = 0;  // resident CTAs per SM (register-limited), queried once
-    if (occ == 0) {
-        int o = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, rgb_to_lab_kernel, kThreads, 0) != cudaSuccess || o < 1) o = 4;
-        occ = o;
-    }
-    size_t grid = (size_t)sm_count * occ;  // exactly one wave of resident CTAs, warps grid-stride over 128-px tiles
+    size_t grid = (size_t)sm_count * 4;  // one wave of the 4 resident CTAs per SM (__launch_bounds__), warps grid-stride over 128-px tiles
     const size_t need = (ntiles + kThreads / 32 - 1) / (kThreads / 32);
     if (grid > need) grid = need;
-    rgb_to_lab_kernel<<<(unsigned)grid, kThreads, 0, stream>>>(d_rgb, n, stride, whitepoint, 1.0f, d_table, d_lab, d_unit);
+    if (d_unit) rgb_to_lab_kernel<true><<<(unsigned)grid, kThreads, 0, stream>>>(d_rgb, n, stride, whitepoint, 1.0f, d_table, d_lab, d_unit);
+    else rgb_to_lab_kernel<false><<<(unsigned)grid, kThreads, 0, stream>>>(d_rgb, n, stride, whitepoint, 1.0f, d_table, d_lab, d_unit);
     return cudaGetLastError();
 }
 
