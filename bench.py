@@ -228,7 +228,7 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
     import torch
     import torch.distributed as dist
 
-    from hybridquantization_b200 import EVAL_FORCE_CHUNKED, EVAL_FORCE_DIRECT, EVAL_FORCE_PREFILTER, ImageManipulation, build, synth
+    from hybridquantization_b200 import EVAL_FORCE_CHUNKED, EVAL_FORCE_DIRECT, EVAL_FORCE_PREFILTER, EVAL_PRUNE, ImageManipulation, build, synth
     from hybridquantization_b200.dist import install_nccl_allreduce, row_shard
 
     if not torch.cuda.is_available():
@@ -330,6 +330,54 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
     e2e_value = n_total * B * a.steps / float(t_e2e.item()) / 1e9
     sampler.stop()
 
+    # ---- the same step through the EXACT PRUNED kernel (HQ_EVAL_PRUNE, csrc/hq_pruned.cu): identical integers, ~K/S times
+    # less arithmetic.  Reported beside the exhaustive kernel, never instead of it: `value`, `e2e` and `roofline` above are
+    # the exhaustive sweep the north star's roofline is defined on.
+    pruned = None
+    if a.space == 0:
+        d_res2 = torch.zeros_like(d_res)
+        def pstep():
+            be.evalPalettesDevice(d_pal.data_ptr(), B, K, d_res2.data_ptr(), a.space, flags | EVAL_PRUNE, stream)
+            if world > 1:
+                dist.all_reduce(d_res2, op=dist.ReduceOp.SUM)
+        for _ in range(a.warmup):
+            flush.fill_(1)
+            pstep()
+        torch.cuda.synchronize()
+        if not torch.equal(d_res2, d_res):
+            raise SystemExit("bench: the pruned kernel's integers differ from the exhaustive kernel's")
+        be.setProfiling(True)
+        pev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        for i in range(a.steps):
+            flush.fill_(i & 255)
+            pev[i][0].record()
+            pstep()
+            pev[i][1].record()
+        torch.cuda.synchronize()
+        stats = be.pruningStats()
+        be.setProfiling(False)
+        p_ms = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in pev)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(p_ms, op=dist.ReduceOp.MAX)
+        p_s = float(p_ms.item()) * 1e-3
+        t0 = time.perf_counter()
+        for i in range(a.steps):
+            r2 = be.evalPalettes(pal, a.space, flags=flags | EVAL_PRUNE)
+        t_p = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_p, op=dist.ReduceOp.MAX)
+        assert np.array_equal(r2["err_fx"], r["err_fx"]) and np.array_equal(r2["counts"], r["counts"])
+        pruned = {"value": n_total * B * a.steps / p_s / 1e9, "unit": UNIT, "ms_per_step": 1e3 * p_s / a.steps,
+                  "swasa_evals_per_s": B * a.steps / p_s, "speedup_over_exhaustive": total_s / p_s,
+                  "e2e": {"value": n_total * B * a.steps / float(t_p.item()) / 1e9, "unit": UNIT, "evals_per_s": B * a.steps / float(t_p.item())},
+                  "chunks": stats["chunks"], "mean_surviving_colours": stats["mean_survivors"], "of_colours": K,
+                  "identical_to_exhaustive": True,
+                  "note": "exact geometric pruning (hq_pruned.cu): pixels cell-sorted once per image, per (chunk, candidate) only colours that can be "
+                          "nearest to some pixel of the chunk are swept; not the kernel the roofline above describes"}
+
     # ---- the one-time image conversion kernel (HBM-bound by design: 15 B/pixel), CUDA events around the kernel
     be.setProfiling(True)
     rl_ms = []
@@ -379,6 +427,8 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
                                     "peak": hbm_peak, "unit": "GB/s", "frac": (15.0 * n_shard / (rl_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
                                     "kernel_ms": rl_ms, "algorithmic_bytes_per_pixel": 15, "runs": "once per image, not per step",
                                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if hbm_peak else None}]
+    if pruned is not None:
+        line["pruned"] = pruned
     if world == 1 and rank == 0 and not a.no_cpu_baseline:
         cb = run_reference_kernels(a, steps=1000, warmup=1, seconds_budget=a.cpu_baseline_seconds)
         port = run_cpu(a, steps=1000, warmup=1, candidates_per_step=1, seconds_budget=a.cpu_baseline_seconds if cb is None else a.cpu_baseline_seconds / 2)

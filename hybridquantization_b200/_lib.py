@@ -17,7 +17,8 @@ ERR_NAMES = {1: "HQ_ERR_INVALID", 2: "HQ_ERR_CUDA", 3: "HQ_ERR_NO_IMAGE", 4: "HQ
 WHITEPOINT_D65, WHITEPOINT_D50 = 0, 1
 SPACE_LAB, SPACE_SRGB = 0, 1
 COST_LAB, COST_SCIELAB = 0, 1
-EVAL_SUMS, EVAL_FORCE_DIRECT, EVAL_FORCE_CHUNKED, EVAL_FORCE_PREFILTER = 1, 2, 4, 8
+EVAL_SUMS, EVAL_FORCE_DIRECT, EVAL_FORCE_CHUNKED, EVAL_FORCE_PREFILTER, EVAL_PRUNE = 1, 2, 4, 8, 16
+PRUNE_OFF, PRUNE_AUTO, PRUNE_ON = 0, 1, 2
 MAX_COLORS = 1024
 
 
@@ -75,6 +76,8 @@ SIGNATURES = {
     "hq_find_best_quantization": (C.c_int, [_P, C.c_int, C.POINTER(SwasaParams), C.c_uint64, _P, C.POINTER(C.c_double), _P, C.POINTER(C.c_int)]),
     "hq_request_stop": (None, [_P]),
     "hq_set_progress": (C.c_int, [_P, PROGRESS_FN, _P]),
+    "hq_set_pruning": (C.c_int, [_P, C.c_int]),
+    "hq_pruning_stats": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_double)]),
     "hq_java_random_seed": (None, [C.POINTER(JavaRandomState), C.c_int64]),
     "hq_java_random_next": (C.c_int32, [C.POINTER(JavaRandomState), C.c_int]),
     "hq_java_random_next_float": (C.c_float, [C.POINTER(JavaRandomState)]),

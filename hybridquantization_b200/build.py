@@ -46,7 +46,7 @@ def sources() -> list[str]:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    cu = [os.path.join(CSRC, "hq_kernels.cu"), os.path.join(CSRC, "hq_scielab.cu"), os.path.join(CSRC, "hq_api.cu")]
+    cu = [os.path.join(CSRC, f) for f in ("hq_kernels.cu", "hq_pruned.cu", "hq_scielab.cu", "hq_api.cu")]
     if not force and not _stale(LIB, sources()):
         return LIB
     cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + cu

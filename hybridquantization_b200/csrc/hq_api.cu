@@ -78,6 +78,16 @@ struct hq_ctx {
     PinBuf<float> h_pal;
     PinBuf<unsigned long long> h_results;
 
+    // exact pruning (hq_pruned.cu): cell-sorted copy of the own pixels, chunk table, boxes; built on first use per image
+    int prune_mode = HQ_PRUNE_AUTO;
+    bool pruned_ready = false;
+    size_t sstride = 0;
+    unsigned nchunks = 0;
+    DevBuf<float> d_sorted, d_box;
+    DevBuf<unsigned> d_pr_scratch, d_chunk_start, d_chunk_len;
+    DevBuf<unsigned long long> d_pr_stats;
+    PinBuf<unsigned long long> h_pr_small;
+
     // S-CIELAB stage (next row 1)
     std::vector<float> sc_filters7, sc_abs3;  // [7][taps], [taps] as ScielabProcessor builds them
     std::vector<float> sc_block;              // [8][taps] device layout, host copy
@@ -139,6 +149,7 @@ int convert_image(hq_ctx* c, int width, int own_rows, int halo_top, int halo_bot
     c->own_lo = (size_t)halo_top * width; c->own_hi = (size_t)(halo_top + own_rows) * width;
     c->have_unit = false;
     c->sc_image_ready = false;
+    c->pruned_ready = false;
     HQ_CUDA(c, c->d_lab.reserve(3 * c->stride > 0 ? 3 * c->stride : 1));
     if (c->profiling) HQ_CUDA(c, cudaEventRecord(c->ev2, st));
     HQ_CUDA(c, hq::launch_rgb_to_lab(c->d_rgb.p, c->n, c->stride, whitepoint, c->d_table.p, c->d_lab.p, nullptr, c->sm_count, st));
@@ -153,6 +164,31 @@ int check_eval_args(hq_ctx* c, int B, int K, int space) {
     if (B < 1 || K < 1) return fail(c, HQ_ERR_INVALID, "B and K must be >= 1 (got B=%d K=%d)", B, K);
     if (K > HQ_MAX_COLORS) return fail(c, HQ_ERR_UNSUPPORTED, "K=%d exceeds HQ_MAX_COLORS=%d", K, HQ_MAX_COLORS);
     if (space != HQ_SPACE_LAB && space != HQ_SPACE_SRGB) return fail(c, HQ_ERR_INVALID, "unknown space %d", space);
+    return HQ_OK;
+}
+
+// cell-sorted copy of the own pixels + chunk table + boxes for the pruned kernel (one host synchronisation, once per image)
+int ensure_pruned(hq_ctx* c, cudaStream_t st) {
+    if (c->pruned_ready) return HQ_OK;
+    const size_t n_own = c->own_hi - c->own_lo;
+    c->sstride = hq::plane_stride(n_own);
+    const size_t words = hq::pruned_scratch_words();
+    HQ_CUDA(c, c->d_sorted.reserve(3 * c->sstride > 0 ? 3 * c->sstride : 1));
+    HQ_CUDA(c, c->d_pr_scratch.reserve(words));
+    HQ_CUDA(c, c->h_pr_small.reserve(2));
+    HQ_CUDA(c, c->d_pr_stats.reserve(2));
+    HQ_CUDA(c, cudaMemsetAsync(c->d_pr_stats.p, 0, 16, st));
+    HQ_CUDA(c, hq::launch_pruned_build_cells(c->d_lab.p, c->stride, c->own_lo, c->own_hi, c->d_pr_scratch.p, c->d_sorted.p, c->sstride, c->sm_count, st));
+    unsigned totals[2] = {0, 0};
+    HQ_CUDA(c, cudaMemcpyAsync(totals, c->d_pr_scratch.p + words - 2, sizeof totals, cudaMemcpyDeviceToHost, st));
+    HQ_CUDA(c, cudaStreamSynchronize(st));
+    if (totals[0] != n_own) return fail(c, HQ_ERR_CUDA, "pruning: cell sort covered %u of %zu pixels", totals[0], n_own);
+    c->nchunks = totals[1];
+    HQ_CUDA(c, c->d_chunk_start.reserve(c->nchunks ? c->nchunks : 1));
+    HQ_CUDA(c, c->d_chunk_len.reserve(c->nchunks ? c->nchunks : 1));
+    HQ_CUDA(c, c->d_box.reserve(c->nchunks ? 6 * (size_t)c->nchunks : 1));
+    HQ_CUDA(c, hq::launch_pruned_build_chunks(c->d_pr_scratch.p, c->d_sorted.p, c->sstride, c->nchunks, c->d_chunk_start.p, c->d_chunk_len.p, c->d_box.p, st));
+    c->pruned_ready = true;
     return HQ_OK;
 }
 
@@ -173,8 +209,18 @@ int eval_device(hq_ctx* c, const float* d_palettes, int B, int K, int space, int
     a.results = d_results; a.idx_out = d_idx; a.sm_count = c->sm_count;
     a.own_lo = c->own_lo; a.own_hi = c->own_hi;
     a.variant = (flags & HQ_EVAL_FORCE_DIRECT) ? 1 : ((flags & HQ_EVAL_FORCE_CHUNKED) ? 2 : ((flags & HQ_EVAL_FORCE_PREFILTER) ? 3 : 0));
+    const bool prune = (flags & HQ_EVAL_PRUNE) != 0 && space == HQ_SPACE_LAB && d_idx == nullptr;
+    if (prune) { int rc = ensure_pruned(c, st); if (rc) return rc; }
     if (c->profiling) HQ_CUDA(c, cudaEventRecord(c->ev0, st));
-    HQ_CUDA(c, hq::launch_assign_reduce(a, st));
+    if (prune) {
+        hq::PrunedArgs pa;
+        pa.sorted = c->d_sorted.p; pa.sstride = c->sstride; pa.chunk_start = c->d_chunk_start.p; pa.chunk_len = c->d_chunk_len.p;
+        pa.box = c->d_box.p; pa.nchunks = c->nchunks; pa.pal_lab = c->d_pal_lab.p; pa.B = B; pa.K = K; pa.want_sums = sums;
+        pa.results = d_results; pa.stats = c->profiling ? c->d_pr_stats.p : nullptr; pa.sm_count = c->sm_count;
+        HQ_CUDA(c, hq::launch_pruned_assign(pa, st));
+    } else {
+        HQ_CUDA(c, hq::launch_assign_reduce(a, st));
+    }
     if (c->profiling) { HQ_CUDA(c, cudaEventRecord(c->ev1, st)); c->ev_valid = true; }
     return HQ_OK;
 }
@@ -231,6 +277,8 @@ void hq_destroy(hq_ctx* c) {
     c->d_out_rgb.release(); c->d_out_f32.release(); c->h_pal.release(); c->h_results.release();
     c->d_sc_filters.release(); c->d_sc_opp.release(); c->d_sc_tmp.release(); c->d_sc_lab.release(); c->d_sc_tab.release(); c->d_sc_err.release();
     c->d_sc_lab2.release(); c->d_sc_map.release(); c->d_sc_rgb2.release(); c->d_sc_map8.release();
+    c->d_sorted.release(); c->d_box.release(); c->d_pr_scratch.release(); c->d_chunk_start.release(); c->d_chunk_len.release();
+    c->d_pr_stats.release(); c->h_pr_small.release();
     delete c;
 }
 
@@ -594,6 +642,11 @@ int hq_find_best_quantization(hq_ctx* c, int K, const hq_swasa_params* p, uint64
         backend.setStopFlag(&c->stop_flag_view);
         backend.setCostModel(p->cost_model);
         backend.setProgress(c->progress, c->progress_user);
+        {   // exact pruning of the population scoring (bit-identical costs, so the trajectory is unchanged)
+            const bool allowed = p->space == HQ_SPACE_LAB && p->cost_model == HQ_COST_LAB;
+            const bool pays = K >= 32 && c->own_hi - c->own_lo >= 65536;
+            backend.setEvalFlags(allowed && (c->prune_mode == HQ_PRUNE_ON || (c->prune_mode == HQ_PRUNE_AUTO && pays)) ? HQ_EVAL_PRUNE : 0);
+        }
         hq::JavaRandom random(p->seed);
         hq::SWASA swasa(p->population, p->imax, p->iTc, p->delta, p->conv_delay, p->conv_spread, p->t0, p->alpha, p->s0, p->beta, &random);
         double err = 0;
@@ -603,6 +656,28 @@ int hq_find_best_quantization(hq_ctx* c, int K, const hq_swasa_params* p, uint64
     } catch (const std::exception& ex) {
         if (c->err.empty()) c->err = ex.what();
         return HQ_ERR_CUDA;
+    }
+    return HQ_OK;
+}
+
+int hq_set_pruning(hq_ctx* c, int mode) {
+    if (!c) return HQ_ERR_INVALID;
+    if (mode != HQ_PRUNE_OFF && mode != HQ_PRUNE_AUTO && mode != HQ_PRUNE_ON) return fail(c, HQ_ERR_INVALID, "unknown pruning mode %d", mode);
+    c->prune_mode = mode;
+    return HQ_OK;
+}
+
+int hq_pruning_stats(hq_ctx* c, uint32_t* chunks, double* mean_survivors) {
+    if (!c) return HQ_ERR_INVALID;
+    if (!c->have_image) return fail(c, HQ_ERR_NO_IMAGE, "no image");
+    int rc = bind_device(c); if (rc) return rc;
+    rc = ensure_pruned(c, c->stream); if (rc) return rc;
+    if (chunks) *chunks = c->nchunks;
+    if (mean_survivors) {
+        unsigned long long st[2] = {0, 0};
+        HQ_CUDA(c, cudaMemcpyAsync(st, c->d_pr_stats.p, sizeof st, cudaMemcpyDeviceToHost, c->stream));
+        HQ_CUDA(c, cudaStreamSynchronize(c->stream));
+        *mean_survivors = st[1] ? (double)st[0] / (double)st[1] : 0.0;
     }
     return HQ_OK;
 }

@@ -47,6 +47,28 @@ struct AssignArgs {
 };
 cudaError_t launch_assign_reduce(const AssignArgs& a, cudaStream_t stream);
 
+// ---- exact assignment with geometric pruning (hq_pruned.cu): the own pixels are counting-sorted once per image by a
+// coarse CIELAB cell into chunks of <= kPrunedChunkPx pixels with exact bounding boxes; per (chunk, candidate) only
+// the colours that can be nearest to some pixel of the chunk are swept.  Results are bit-identical to
+// launch_assign_reduce (LAB space, no index image).
+constexpr int kPrunedChunkPx = 2048;
+size_t pruned_scratch_words();  // unsigned words of scratch launch_pruned_build_cells needs (totals at [.. - 2]: pixels, chunks)
+cudaError_t launch_pruned_build_cells(const float* d_lab, size_t stride, size_t own_lo, size_t own_hi, unsigned* d_scratch, float* d_sorted,
+                                      size_t sstride, int sm_count, cudaStream_t st);
+cudaError_t launch_pruned_build_chunks(const unsigned* d_scratch, const float* d_sorted, size_t sstride, unsigned nchunks, unsigned* d_chunk_start,
+                                       unsigned* d_chunk_len, float* d_box, cudaStream_t st);
+struct PrunedArgs {
+    const float* sorted; size_t sstride;          // [3][sstride] Lab of the own pixels in cell order
+    const unsigned* chunk_start; const unsigned* chunk_len; const float* box; unsigned nchunks;
+    const float4* pal_lab;                        // [B][K8]
+    int B, K;
+    bool want_sums;
+    unsigned long long* results;                  // [B][result_words], zeroed by the caller
+    unsigned long long* stats;                    // optional [2]: survivors summed over (chunk, candidate), number of (chunk, candidate)
+    int sm_count;
+};
+cudaError_t launch_pruned_assign(const PrunedArgs& a, cudaStream_t st);
+
 // indices -> output image of the chosen palette colours (u8 RGB packed and/or float RGBA)
 cudaError_t launch_apply_palette(const void* d_idx, bool idx16, size_t n, const float* d_palette /*[K][4]*/,
                                  int K, uint8_t* d_out_rgb, float* d_out_f32, cudaStream_t stream);

@@ -1,0 +1,336 @@
+// hq_pruned.cu — EXACT nearest-palette assignment with geometric pruning (opt-in fast path of the
+// population scoring, HQ_EVAL_PRUNE).
+//
+// The exhaustive kernel (assign_reduce_kernel, hq_kernels.cu) evaluates all N*K pixel-colour pairs per
+// candidate, as quantizeAndConvertToOpp does (OptimizedConvolution.cl:178-193).  Every output of the
+// scoring step is a SUM over pixels (error, per-colour counts, Lab sums), so the pixels may be visited
+// in any order.  Once per image the own pixels are therefore counting-sorted by a coarse CIELAB cell
+// (5 bits per axis) and cut into chunks of <= 2048 pixels that never straddle a cell; each chunk keeps
+// its exact bounding box.  Per (chunk, candidate) a CTA then
+//   1. bounds every colour against the box:  dmin_k <= |x - p_k| <= dmax_k  for every pixel x of the chunk,
+//   2. takes U = min_k dmax_k (some colour is within U of every pixel) and keeps the colours with
+//      dmin_k^2 <= U^2 * (1 + 2^-18): a discarded colour is strictly farther from every pixel of the chunk
+//      than the colour that realises U, by a margin ~250x the rounding error of the fp32 distances, so it
+//      can neither win nor tie,
+//   3. runs the exact direct-form sweep (hq_dist2, strict '<', ascending colour index = the reference's
+//      first-wins rule, cl:186) over the survivors only — typically 4-10 of 256.
+// Winner, distance, counts, sums and error are bit-identical to the exhaustive kernel
+// (tests/test_gpu_pruned.py); what changes is the amount of arithmetic: ~N*(S + c) instead of N*K.
+//
+// No index image is produced here (the pixel order is permuted): hq_quantize and the S-CIELAB chain keep
+// using the exhaustive kernel.
+#include "hq_kernels.cuh"
+#include "hq_math.h"
+
+namespace hq {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kPxPerThread = kPrunedChunkPx / kThreads;  // 8
+constexpr int kCellBits = 5;
+constexpr int kCells = 1 << (3 * kCellBits);  // 32768
+
+// coarse CIELAB cell of a pixel: L in [0,100] -> 32 slabs of 3.125, a and b in [-128,128) -> 32 slabs of 8.
+// Only a partition: any deterministic function works, exactness is irrelevant.
+__device__ __forceinline__ unsigned cell_of(float L, float a, float b) {
+    const int l = min(max(__float2int_rd(L * 0.32f), 0), 31);
+    const int u = min(max(__float2int_rd((a + 128.0f) * 0.125f), 0), 31);
+    const int v = min(max(__float2int_rd((b + 128.0f) * 0.125f), 0), 31);
+    return (unsigned)((l << 10) | (u << 5) | v);
+}
+
+__global__ void cell_hist_kernel(const float* __restrict__ lab, size_t stride, size_t lo, size_t hi, unsigned* __restrict__ hist) {
+    for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x)
+        atomicAdd(&hist[cell_of(lab[i], lab[stride + i], lab[2 * stride + i])], 1u);
+}
+
+// one CTA of 1024 threads: exclusive scans of the cell populations (pixel offsets) and of the chunks per cell
+__global__ void __launch_bounds__(1024) cell_scan_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ cell_off,
+                                                         unsigned* __restrict__ chunk_base, unsigned* __restrict__ totals) {
+    __shared__ unsigned s_px[1024], s_ch[1024];
+    const int t = threadIdx.x;
+    constexpr int per = kCells / 1024;  // 32 consecutive cells per thread
+    unsigned px = 0, ch = 0;
+    for (int i = 0; i < per; ++i) {
+        const unsigned h = hist[t * per + i];
+        px += h; ch += (h + kPrunedChunkPx - 1) / kPrunedChunkPx;
+    }
+    s_px[t] = px; s_ch[t] = ch;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan
+        const unsigned a = t >= off ? s_px[t - off] : 0u, b = t >= off ? s_ch[t - off] : 0u;
+        __syncthreads();
+        s_px[t] += a; s_ch[t] += b;
+        __syncthreads();
+    }
+    unsigned opx = s_px[t] - px, och = s_ch[t] - ch;
+    for (int i = 0; i < per; ++i) {
+        const unsigned h = hist[t * per + i];
+        cell_off[t * per + i] = opx; chunk_base[t * per + i] = och;
+        opx += h; och += (h + kPrunedChunkPx - 1) / kPrunedChunkPx;
+    }
+    if (t == 1023) { totals[0] = s_px[t]; totals[1] = s_ch[t]; }
+}
+
+__global__ void cell_scatter_kernel(const float* __restrict__ lab, size_t stride, size_t lo, size_t hi, const unsigned* __restrict__ cell_off,
+                                    unsigned* __restrict__ cursor, float* __restrict__ sorted, size_t sstride) {
+    for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
+        const float L = lab[i], a = lab[stride + i], b = lab[2 * stride + i];
+        const unsigned c = cell_of(L, a, b);
+        const size_t pos = (size_t)cell_off[c] + atomicAdd(&cursor[c], 1u);
+        sorted[pos] = L; sorted[sstride + pos] = a; sorted[2 * sstride + pos] = b;
+    }
+}
+
+__global__ void chunk_table_kernel(const unsigned* __restrict__ hist, const unsigned* __restrict__ cell_off, const unsigned* __restrict__ chunk_base,
+                                   unsigned* __restrict__ chunk_start, unsigned* __restrict__ chunk_len) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= kCells) return;
+    const unsigned h = hist[c];
+    for (unsigned j = 0, left = h; left > 0; ++j) {
+        const unsigned len = left < (unsigned)kPrunedChunkPx ? left : (unsigned)kPrunedChunkPx;
+        chunk_start[chunk_base[c] + j] = cell_off[c] + j * kPrunedChunkPx;
+        chunk_len[chunk_base[c] + j] = len;
+        left -= len;
+    }
+}
+
+// exact bounding box of every chunk: one warp per chunk; box = (lo0, lo1, lo2, hi0, hi1, hi2)
+__global__ void chunk_box_kernel(const float* __restrict__ sorted, size_t sstride, const unsigned* __restrict__ chunk_start,
+                                 const unsigned* __restrict__ chunk_len, unsigned nchunks, float* __restrict__ box) {
+    const unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= nchunks) return;
+    const size_t s = chunk_start[w];
+    const unsigned len = chunk_len[w];
+    const float INF = __int_as_float(0x7f800000);
+    float lo[3] = {INF, INF, INF}, hi[3] = {-INF, -INF, -INF};
+    for (unsigned i = lane; i < len; i += 32)
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+            const float v = sorted[pl * sstride + s + i];
+            lo[pl] = fminf(lo[pl], v); hi[pl] = fmaxf(hi[pl], v);
+        }
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            lo[pl] = fminf(lo[pl], __shfl_xor_sync(0xffffffffu, lo[pl], off));
+            hi[pl] = fmaxf(hi[pl], __shfl_xor_sync(0xffffffffu, hi[pl], off));
+        }
+    if (lane == 0) {
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) { box[6 * (size_t)w + pl] = lo[pl]; box[6 * (size_t)w + 3 + pl] = hi[pl]; }
+    }
+}
+
+struct PrunedParams {
+    const float* sorted; size_t sstride;
+    const unsigned* chunk_start; const unsigned* chunk_len; const float* box; unsigned nchunks;
+    const float4* pal_lab;  // [B][K8]
+    int B, K, K8, words, b_per_cta;
+    unsigned long long* results;
+    unsigned long long* stats;  // optional: [0] += survivors summed over (chunk, candidate), [1] += (chunk, candidate) pairs
+};
+
+template <bool SUMS>
+__global__ void __launch_bounds__(kThreads, 2) pruned_assign_kernel(const PrunedParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int K = p.K, K8 = p.K8, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float4* s_surv = reinterpret_cast<float4*>(smem_raw);                                   // [K8] Lab of the survivors
+    unsigned long long* s_sum = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)K8 * 16);  // [3*K8] (SUMS)
+    unsigned* s_cnt = reinterpret_cast<unsigned*>(smem_raw + (size_t)K8 * 16 + (SUMS ? (size_t)K8 * 24 : 0));  // [K8]
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(s_cnt + K8);                   // [K8] colour index of survivor i
+    __shared__ float s_red[kThreads / 32];
+    __shared__ unsigned s_wc[kThreads / 32];
+    __shared__ long long s_err[kThreads / 32];
+
+    const unsigned chunk = blockIdx.x;
+    const size_t start = p.chunk_start[chunk];
+    const unsigned len = p.chunk_len[chunk];
+    const float INF = __int_as_float(0x7f800000);
+    // the chunk's pixels stay in registers for every candidate this CTA scores
+    float x0[kPxPerThread], x1[kPxPerThread], x2[kPxPerThread];
+#pragma unroll
+    for (int j = 0; j < kPxPerThread; ++j) {
+        const unsigned i = j * kThreads + tid;
+        const bool ok = i < len;
+        x0[j] = ok ? __ldg(p.sorted + start + i) : 0.f;
+        x1[j] = ok ? __ldg(p.sorted + p.sstride + start + i) : 0.f;
+        x2[j] = ok ? __ldg(p.sorted + 2 * p.sstride + start + i) : 0.f;
+    }
+    float lo[3], hi[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { lo[a] = __ldg(p.box + 6 * (size_t)chunk + a); hi[a] = __ldg(p.box + 6 * (size_t)chunk + 3 + a); }
+
+    const int b_begin = blockIdx.y * p.b_per_cta, b_end = min(p.B, b_begin + p.b_per_cta);
+    constexpr int kRounds = kMaxColors / kThreads;  // 4: colour k = tid + 256*r
+    for (int b = b_begin; b < b_end; ++b) {
+        const float4* pal = p.pal_lab + (size_t)b * K8;
+        // ---- 1. bounds of every colour against the box
+        float4 col[kRounds];
+        float dmin2[kRounds];
+        float umin = INF;
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) {
+            const int k = tid + r * kThreads;
+            dmin2[r] = INF;
+            if (k < K) {
+                const float4 c = __ldg(pal + k);
+                col[r] = c;
+                const float pc[3] = {c.x, c.y, c.z};
+                float mn = 0.f, mx = 0.f;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const float below = lo[a] - pc[a], above = pc[a] - hi[a];      // > 0 when the colour lies outside the slab
+                    const float near = fmaxf(fmaxf(below, above), 0.f);
+                    const float far = fmaxf(pc[a] - lo[a], hi[a] - pc[a]);
+                    mn = fmaf(near, near, mn); mx = fmaf(far, far, mx);
+                }
+                dmin2[r] = mn;
+                umin = fminf(umin, mx);
+            }
+        }
+        // ---- 2. U = min over colours of dmax^2
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) umin = fminf(umin, __shfl_xor_sync(0xffffffffu, umin, off));
+        if (lane == 0) s_red[warp] = umin;
+        __syncthreads();
+        float U = s_red[0];
+#pragma unroll
+        for (int w = 1; w < kThreads / 32; ++w) U = fminf(U, s_red[w]);
+        // survivors: dmin^2 <= U * (1 + 2^-18) (+ an absolute floor for U == 0); everything else is strictly farther
+        const float thr = fmaf(U, 0x1p-18f, U) + 1e-30f;
+        // ---- ordered compaction (ascending colour index), round by round
+        unsigned S = 0;
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) {
+            if (r * kThreads >= K) break;
+            const bool keep = dmin2[r] <= thr;
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) s_wc[warp] = __popc(bal);
+            __syncthreads();
+            unsigned woff = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) { const unsigned c = s_wc[w]; if (w < warp) woff += c; total += c; }
+            if (keep) {
+                const unsigned pos = S + woff + __popc(bal & ((1u << lane) - 1u));
+                s_surv[pos] = col[r];
+                s_list[pos] = (unsigned short)(tid + r * kThreads);
+            }
+            S += total;
+            __syncthreads();  // s_wc is reused by the next round
+        }
+        for (unsigned i = tid; i < S; i += kThreads) {
+            s_cnt[i] = 0u;
+            if (SUMS) { s_sum[3 * i] = 0ull; s_sum[3 * i + 1] = 0ull; s_sum[3 * i + 2] = 0ull; }
+        }
+        __syncthreads();
+        // ---- 3. exact sweep over the survivors: strict '<', ascending index = lowest index wins
+        float best[kPxPerThread];
+        int bi[kPxPerThread];
+#pragma unroll
+        for (int j = 0; j < kPxPerThread; ++j) { best[j] = INF; bi[j] = 0; }
+        for (unsigned i = 0; i < S; ++i) {
+            const float4 q = s_surv[i];
+#pragma unroll
+            for (int j = 0; j < kPxPerThread; ++j) {
+                const float d = hq_dist2(x0[j], x1[j], x2[j], q.x, q.y, q.z);
+                if (d < best[j]) { best[j] = d; bi[j] = (int)i; }
+            }
+        }
+        // ---- epilogue: error, counts, sums (per survivor slot), then one flush per touched colour
+        long long err_acc = 0;
+#pragma unroll
+        for (int j = 0; j < kPxPerThread; ++j) {
+            if ((unsigned)(j * kThreads + tid) < len) {
+                err_acc += hq_to_fx(HQ_FSQRT(best[j]));
+                atomicAdd(&s_cnt[bi[j]], 1u);
+                if (SUMS) {
+                    atomicAdd(&s_sum[3 * bi[j]], (unsigned long long)hq_to_fx(x0[j]));
+                    atomicAdd(&s_sum[3 * bi[j] + 1], (unsigned long long)hq_to_fx(x1[j]));
+                    atomicAdd(&s_sum[3 * bi[j] + 2], (unsigned long long)hq_to_fx(x2[j]));
+                }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) err_acc += __shfl_down_sync(0xffffffffu, err_acc, off);
+        if (lane == 0) s_err[warp] = err_acc;
+        __syncthreads();  // also orders the shared atomics before the flush
+        unsigned long long* out = p.results + (size_t)b * p.words;
+        if (tid == 0) {
+            long long e = 0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) e += s_err[w];
+            if (e != 0) atomicAdd(out, (unsigned long long)e);
+            if (p.stats) { atomicAdd(p.stats, (unsigned long long)S); atomicAdd(p.stats + 1, 1ull); }
+        }
+        for (unsigned i = tid; i < S; i += kThreads) {
+            const unsigned c = s_cnt[i];
+            if (c) {
+                const int k = s_list[i];
+                atomicAdd(out + 1 + k, (unsigned long long)c);
+                if (SUMS) {
+                    atomicAdd(out + 1 + K + 3 * k, s_sum[3 * i]);
+                    atomicAdd(out + 1 + K + 3 * k + 1, s_sum[3 * i + 1]);
+                    atomicAdd(out + 1 + K + 3 * k + 2, s_sum[3 * i + 2]);
+                }
+            }
+        }
+        __syncthreads();  // the shared lists are rebuilt for the next candidate
+    }
+}
+
+}  // namespace
+
+size_t pruned_scratch_words() { return (size_t)kCells * 4 + 2; }  // hist, cell_off, chunk_base, cursor, totals
+
+cudaError_t launch_pruned_build_cells(const float* d_lab, size_t stride, size_t own_lo, size_t own_hi, unsigned* d_scratch, float* d_sorted,
+                                      size_t sstride, int sm_count, cudaStream_t st) {
+    unsigned *hist = d_scratch, *cell_off = d_scratch + kCells, *chunk_base = d_scratch + 2 * kCells, *cursor = d_scratch + 3 * kCells,
+             *totals = d_scratch + 4 * kCells;
+    cudaError_t e = cudaMemsetAsync(d_scratch, 0, pruned_scratch_words() * sizeof(unsigned), st);
+    if (e != cudaSuccess) return e;
+    if (own_hi > own_lo) cell_hist_kernel<<<sm_count * 8, 256, 0, st>>>(d_lab, stride, own_lo, own_hi, hist);
+    cell_scan_kernel<<<1, 1024, 0, st>>>(hist, cell_off, chunk_base, totals);
+    if (own_hi > own_lo) cell_scatter_kernel<<<sm_count * 8, 256, 0, st>>>(d_lab, stride, own_lo, own_hi, cell_off, cursor, d_sorted, sstride);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pruned_build_chunks(const unsigned* d_scratch, const float* d_sorted, size_t sstride, unsigned nchunks, unsigned* d_chunk_start,
+                                       unsigned* d_chunk_len, float* d_box, cudaStream_t st) {
+    const unsigned *hist = d_scratch, *cell_off = d_scratch + kCells, *chunk_base = d_scratch + 2 * kCells;
+    chunk_table_kernel<<<kCells / 256, 256, 0, st>>>(hist, cell_off, chunk_base, d_chunk_start, d_chunk_len);
+    if (nchunks) chunk_box_kernel<<<(nchunks * 32 + 255) / 256, 256, 0, st>>>(d_sorted, sstride, d_chunk_start, d_chunk_len, nchunks, d_box);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pruned_assign(const PrunedArgs& a, cudaStream_t st) {
+    if (a.B <= 0 || a.K <= 0 || a.K > kMaxColors) return cudaErrorInvalidValue;
+    if (a.nchunks == 0) return cudaSuccess;
+    PrunedParams p;
+    p.sorted = a.sorted; p.sstride = a.sstride; p.chunk_start = a.chunk_start; p.chunk_len = a.chunk_len; p.box = a.box; p.nchunks = a.nchunks;
+    p.pal_lab = a.pal_lab; p.B = a.B; p.K = a.K; p.K8 = padded_colors(a.K); p.words = result_words(a.K, a.want_sums);
+    p.results = a.results; p.stats = a.stats;
+    // every CTA keeps its chunk in registers and loops over candidates; split the candidates over gridDim.y only as far
+    // as needed to fill the machine (>= 8 CTAs per SM)
+    int groups = 1;
+    while ((long long)a.nchunks * groups < (long long)a.sm_count * 8 && groups < a.B) groups *= 2;
+    if (groups > a.B) groups = a.B;
+    p.b_per_cta = (a.B + groups - 1) / groups;
+    groups = (a.B + p.b_per_cta - 1) / p.b_per_cta;
+    const size_t smem = (size_t)p.K8 * (16 + 4 + 2) + (a.want_sums ? (size_t)p.K8 * 24 : 0);
+    const dim3 grid(a.nchunks, (unsigned)groups);
+    cudaError_t e;
+    if (a.want_sums) {
+        e = cudaFuncSetAttribute(pruned_assign_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        pruned_assign_kernel<true><<<grid, kThreads, smem, st>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(pruned_assign_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        pruned_assign_kernel<false><<<grid, kThreads, smem, st>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace hq

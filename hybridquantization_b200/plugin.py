@@ -297,6 +297,15 @@ class ImageManipulation:
         self._progress_cb = _lib.PROGRESS_FN((lambda _u, i, m, e: fn(i, m, e)) if fn else 0)
         _lib.check(self._ctx, self._lib.hq_set_progress(self._ctx, self._progress_cb, None))
 
+    def setPruning(self, mode: int) -> None:
+        """PRUNE_OFF | PRUNE_AUTO (default) | PRUNE_ON: whether the search scores populations with the exact pruned kernel"""
+        _lib.check(self._ctx, self._lib.hq_set_pruning(self._ctx, mode))
+
+    def pruningStats(self) -> dict:
+        ch, ms = C.c_uint32(), C.c_double()
+        _lib.check(self._ctx, self._lib.hq_pruning_stats(self._ctx, C.byref(ch), C.byref(ms)))
+        return {"chunks": ch.value, "mean_survivors": ms.value}
+
     def requestStop(self) -> None:
         self._lib.hq_request_stop(self._ctx)
 

@@ -51,7 +51,9 @@ enum {
     HQ_EVAL_SUMS = 1,            /* also reduce per-colour Lab sums */
     HQ_EVAL_FORCE_DIRECT = 2,    /* kernel variant selection, for tests / profiling */
     HQ_EVAL_FORCE_CHUNKED = 4,
-    HQ_EVAL_FORCE_PREFILTER = 8  /* expanded-form prefilter + exact re-check (default for K > 16) */
+    HQ_EVAL_FORCE_PREFILTER = 8, /* expanded-form prefilter + exact re-check (default for K > 16) */
+    HQ_EVAL_PRUNE = 16           /* exact assignment with geometric pruning (LAB space; same integers as the exhaustive
+                                  * kernel, ~10x less arithmetic at K=256): see hq_set_pruning */
 };
 
 #define HQ_MAX_COLORS 1024
@@ -106,6 +108,19 @@ int hq_result_words(int K, int flags);
  * the context's stream), no host synchronisation, no all-reduce. */
 int hq_eval_palettes_device(hq_ctx* ctx, const void* d_palettes, int B, int K, int space,
                             int flags, void* d_results, void* stream);
+
+/* ---- exact pruning (added; no reference counterpart: the reference sweeps all K colours for every pixel, cl:178-193).
+ * Every output of the scoring step is a sum over pixels, so the pixel order is free: once per image the own pixels are
+ * sorted by a coarse CIELAB cell into chunks with exact bounding boxes, and per (chunk, candidate) only the colours that
+ * can be the nearest one of some pixel of the chunk are compared.  Outputs are bit-identical to the exhaustive kernel.
+ * HQ_EVAL_PRUNE selects it per call (LAB space only; ignored otherwise).  hq_set_pruning chooses what the annealing search
+ * (hq_find_best_quantization) does: HQ_PRUNE_OFF never, HQ_PRUNE_AUTO (default) when K >= 32, the shard has >= 65,536
+ * pixels and the search runs in LAB space with the LAB cost model, HQ_PRUNE_ON whenever the space and cost model allow.
+ * hq_pruning_stats: chunks of the resident image and, when profiling is enabled, the mean number of colours that
+ * survived per (chunk, candidate) since the image was set. */
+enum { HQ_PRUNE_OFF = 0, HQ_PRUNE_AUTO = 1, HQ_PRUNE_ON = 2 };
+int hq_set_pruning(hq_ctx* ctx, int mode);
+int hq_pruning_stats(hq_ctx* ctx, uint32_t* chunks, double* mean_survivors);
 
 /* cost = (sum dE)/N + delta * #{unused colours}: averageArray + computePenalty
  * (ImageManipulation.java:712,736-752; SWASA.java:74-82).  Pure host arithmetic. */
