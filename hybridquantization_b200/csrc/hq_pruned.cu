@@ -132,152 +132,178 @@ struct PrunedParams {
     unsigned long long* stats;  // optional: [0] += survivors summed over (chunk, candidate), [1] += (chunk, candidate) pairs
 };
 
-template <bool SUMS>
-__global__ void __launch_bounds__(kThreads, 2) pruned_assign_kernel(const PrunedParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int K = p.K, K8 = p.K8, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float4* s_surv = reinterpret_cast<float4*>(smem_raw);                                   // [K8] Lab of the survivors
-    unsigned long long* s_sum = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)K8 * 16);  // [3*K8] (SUMS)
-    unsigned* s_cnt = reinterpret_cast<unsigned*>(smem_raw + (size_t)K8 * 16 + (SUMS ? (size_t)K8 * 24 : 0));  // [K8]
-    unsigned short* s_list = reinterpret_cast<unsigned short*>(s_cnt + K8);                   // [K8] colour index of survivor i
-    __shared__ float s_red[kThreads / 32];
-    __shared__ unsigned s_wc[kThreads / 32];
-    __shared__ long long s_err[kThreads / 32];
+// shared-memory carve-up: survivors live in per-warp SEGMENTS (segment g = colours [32g, 32g+32), filled from slot 32g
+// upwards in ascending colour order), so the compaction needs no prefix sum across warps and the sweep still visits
+// the survivors in ascending colour index.
+struct PrunedSmem {
+    float4* surv;               // [K32] Lab of the survivor in each slot
+    unsigned long long* sum;    // [3*K32] per-slot Lab sums (SUMS)
+    unsigned* cnt;              // [K32] per-slot pixel counts
+    unsigned short* list;       // [K32] colour index of each slot
+    unsigned* segcnt;           // [K32/32] survivors per segment
+    int K32;                    // K rounded up to whole segments
+};
 
-    const unsigned chunk = blockIdx.x;
-    const size_t start = p.chunk_start[chunk];
-    const unsigned len = p.chunk_len[chunk];
+// One candidate on one chunk whose pixels sit in registers (NS slots of 256 pixels).  3 CTA barriers.
+template <int NS, bool SUMS>
+__device__ __forceinline__ void score_candidate(const PrunedParams& p, const PrunedSmem& sm, unsigned* s_U, long long* s_err, int b, int parity,
+                                                const float (&x0)[NS], const float (&x1)[NS], const float (&x2)[NS], unsigned len,
+                                                const float (&lo)[3], const float (&hi)[3]) {
+    const int K = p.K, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float INF = __int_as_float(0x7f800000);
-    // the chunk's pixels stay in registers for every candidate this CTA scores
-    float x0[kPxPerThread], x1[kPxPerThread], x2[kPxPerThread];
+    constexpr int kRounds = kMaxColors / kThreads;  // colour k = tid + 256*r
+    const int nseg = (K + 31) >> 5;
+    const float4* pal = p.pal_lab + (size_t)b * p.K8;
+    // ---- 1. bounds of every colour against the box; U = min over colours of dmax^2 (non-negative floats order like their bits)
+    float4 col[kRounds];
+    float dmin2[kRounds];
+    float umin = INF;
 #pragma unroll
-    for (int j = 0; j < kPxPerThread; ++j) {
+    for (int r = 0; r < kRounds; ++r) {
+        const int k = tid + r * kThreads;
+        dmin2[r] = INF;
+        if (k < K) {
+            const float4 c = __ldg(pal + k);
+            col[r] = c;
+            const float pc[3] = {c.x, c.y, c.z};
+            float mn = 0.f, mx = 0.f;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float near = fmaxf(fmaxf(lo[a] - pc[a], pc[a] - hi[a]), 0.f);  // > 0 when the colour lies outside the slab
+                const float far = fmaxf(pc[a] - lo[a], hi[a] - pc[a]);
+                mn = fmaf(near, near, mn); mx = fmaf(far, far, mx);
+            }
+            dmin2[r] = mn;
+            umin = fminf(umin, mx);
+        }
+    }
+    const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(umin));
+    if (lane == 0) atomicMin(&s_U[parity], wmin);
+    __syncthreads();  // (1)
+    // survivors: dmin^2 <= U * (1 + 2^-18) (+ an absolute floor for U == 0); every other colour is strictly farther
+    const float U = __uint_as_float(s_U[parity]);
+    const float thr = fmaf(U, 0x1p-18f, U) + 1e-30f;
+    if (tid == 0) s_U[parity ^ 1] = 0x7f800000u;  // for the next candidate (its atomicMin comes after barriers 2 and 3)
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        if (r * kThreads >= K) break;
+        const bool keep = dmin2[r] <= thr;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        const int seg = r * (kThreads / 32) + warp, slot = seg * 32 + __popc(bal & ((1u << lane) - 1u));
+        if (keep) { sm.surv[slot] = col[r]; sm.list[slot] = (unsigned short)(tid + r * kThreads); }  // keep implies k < K, so slot < K32
+        if (lane == 0 && seg * 32 < sm.K32) sm.segcnt[seg] = __popc(bal);
+        if (tid + r * kThreads < sm.K32) {
+            sm.cnt[tid + r * kThreads] = 0u;
+            if (SUMS) { sm.sum[3 * (tid + r * kThreads)] = 0ull; sm.sum[3 * (tid + r * kThreads) + 1] = 0ull; sm.sum[3 * (tid + r * kThreads) + 2] = 0ull; }
+        }
+    }
+    __syncthreads();  // (2)
+    // ---- 2. exact sweep over the survivors: strict '<', ascending colour index = lowest index wins
+    float best[NS];
+    int bi[NS];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) { best[j] = INF; bi[j] = 0; }
+    unsigned S = 0;
+    for (int g = 0; g < nseg; ++g) {
+        const unsigned c = sm.segcnt[g];
+        S += c;
+        for (unsigned i = 0; i < c; ++i) {
+            const float4 q = sm.surv[g * 32 + i];
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                const float d = hq_dist2(x0[j], x1[j], x2[j], q.x, q.y, q.z);
+                if (d < best[j]) { best[j] = d; bi[j] = g * 32 + (int)i; }
+            }
+        }
+    }
+    // ---- 3. error, counts, sums per slot
+    long long err_acc = 0;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        if ((unsigned)(j * kThreads + tid) < len) {
+            err_acc += hq_to_fx(HQ_FSQRT(best[j]));
+            atomicAdd(&sm.cnt[bi[j]], 1u);
+            if (SUMS) {
+                atomicAdd(&sm.sum[3 * bi[j]], (unsigned long long)hq_to_fx(x0[j]));
+                atomicAdd(&sm.sum[3 * bi[j] + 1], (unsigned long long)hq_to_fx(x1[j]));
+                atomicAdd(&sm.sum[3 * bi[j] + 2], (unsigned long long)hq_to_fx(x2[j]));
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) err_acc += __shfl_down_sync(0xffffffffu, err_acc, off);
+    if (lane == 0) s_err[warp] = err_acc;
+    __syncthreads();  // (3) also orders the shared atomics before the flush; the next candidate's barrier (1) orders the flush
+                      // before its writes to these arrays
+    unsigned long long* out = p.results + (size_t)b * p.words;
+    if (tid == 0) {
+        long long e = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) e += s_err[w];
+        if (e != 0) atomicAdd(out, (unsigned long long)e);
+        if (p.stats) { atomicAdd(p.stats, (unsigned long long)S); atomicAdd(p.stats + 1, 1ull); }
+    }
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        if (r * kThreads >= K) break;
+        const int slot = tid + r * kThreads;
+        const unsigned c = (slot < sm.K32 && (unsigned)(slot & 31) < sm.segcnt[slot >> 5]) ? sm.cnt[slot] : 0u;
+        if (c) {
+            const int k = sm.list[slot];
+            atomicAdd(out + 1 + k, (unsigned long long)c);
+            if (SUMS) {
+                atomicAdd(out + 1 + K + 3 * k, sm.sum[3 * slot]);
+                atomicAdd(out + 1 + K + 3 * k + 1, sm.sum[3 * slot + 1]);
+                atomicAdd(out + 1 + K + 3 * k + 2, sm.sum[3 * slot + 2]);
+            }
+        }
+    }
+}
+
+// all candidates of this CTA on one chunk of <= NS*256 pixels
+template <int NS, bool SUMS>
+__device__ __forceinline__ void score_chunk(const PrunedParams& p, const PrunedSmem& sm, unsigned* s_U, long long* s_err, size_t start, unsigned len,
+                                            const float (&lo)[3], const float (&hi)[3]) {
+    const int tid = threadIdx.x;
+    float x0[NS], x1[NS], x2[NS];  // the chunk's pixels stay in registers for every candidate
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
         const unsigned i = j * kThreads + tid;
         const bool ok = i < len;
         x0[j] = ok ? __ldg(p.sorted + start + i) : 0.f;
         x1[j] = ok ? __ldg(p.sorted + p.sstride + start + i) : 0.f;
         x2[j] = ok ? __ldg(p.sorted + 2 * p.sstride + start + i) : 0.f;
     }
+    const int b_begin = blockIdx.y * p.b_per_cta, b_end = min(p.B, b_begin + p.b_per_cta);
+    for (int b = b_begin; b < b_end; ++b) score_candidate<NS, SUMS>(p, sm, s_U, s_err, b, (b - b_begin) & 1, x0, x1, x2, len, lo, hi);
+}
+
+template <bool SUMS>
+__global__ void __launch_bounds__(kThreads, 2) pruned_assign_kernel(const PrunedParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int K32 = (p.K + 31) & ~31;
+    PrunedSmem sm;
+    sm.K32 = K32;
+    sm.surv = reinterpret_cast<float4*>(smem_raw);
+    sm.sum = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)K32 * 16);
+    sm.cnt = reinterpret_cast<unsigned*>(smem_raw + (size_t)K32 * 16 + (SUMS ? (size_t)K32 * 24 : 0));
+    sm.list = reinterpret_cast<unsigned short*>(sm.cnt + K32);
+    sm.segcnt = reinterpret_cast<unsigned*>(sm.list + K32);
+    __shared__ unsigned s_U[2];
+    __shared__ long long s_err[kThreads / 32];
+    if (threadIdx.x < 2) s_U[threadIdx.x] = 0x7f800000u;
+    __syncthreads();
+    const unsigned chunk = blockIdx.x;
+    const size_t start = p.chunk_start[chunk];
+    const unsigned len = p.chunk_len[chunk];
     float lo[3], hi[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) { lo[a] = __ldg(p.box + 6 * (size_t)chunk + a); hi[a] = __ldg(p.box + 6 * (size_t)chunk + 3 + a); }
-
-    const int b_begin = blockIdx.y * p.b_per_cta, b_end = min(p.B, b_begin + p.b_per_cta);
-    constexpr int kRounds = kMaxColors / kThreads;  // 4: colour k = tid + 256*r
-    for (int b = b_begin; b < b_end; ++b) {
-        const float4* pal = p.pal_lab + (size_t)b * K8;
-        // ---- 1. bounds of every colour against the box
-        float4 col[kRounds];
-        float dmin2[kRounds];
-        float umin = INF;
-#pragma unroll
-        for (int r = 0; r < kRounds; ++r) {
-            const int k = tid + r * kThreads;
-            dmin2[r] = INF;
-            if (k < K) {
-                const float4 c = __ldg(pal + k);
-                col[r] = c;
-                const float pc[3] = {c.x, c.y, c.z};
-                float mn = 0.f, mx = 0.f;
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const float below = lo[a] - pc[a], above = pc[a] - hi[a];      // > 0 when the colour lies outside the slab
-                    const float near = fmaxf(fmaxf(below, above), 0.f);
-                    const float far = fmaxf(pc[a] - lo[a], hi[a] - pc[a]);
-                    mn = fmaf(near, near, mn); mx = fmaf(far, far, mx);
-                }
-                dmin2[r] = mn;
-                umin = fminf(umin, mx);
-            }
-        }
-        // ---- 2. U = min over colours of dmax^2
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) umin = fminf(umin, __shfl_xor_sync(0xffffffffu, umin, off));
-        if (lane == 0) s_red[warp] = umin;
-        __syncthreads();
-        float U = s_red[0];
-#pragma unroll
-        for (int w = 1; w < kThreads / 32; ++w) U = fminf(U, s_red[w]);
-        // survivors: dmin^2 <= U * (1 + 2^-18) (+ an absolute floor for U == 0); everything else is strictly farther
-        const float thr = fmaf(U, 0x1p-18f, U) + 1e-30f;
-        // ---- ordered compaction (ascending colour index), round by round
-        unsigned S = 0;
-#pragma unroll
-        for (int r = 0; r < kRounds; ++r) {
-            if (r * kThreads >= K) break;
-            const bool keep = dmin2[r] <= thr;
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0) s_wc[warp] = __popc(bal);
-            __syncthreads();
-            unsigned woff = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < kThreads / 32; ++w) { const unsigned c = s_wc[w]; if (w < warp) woff += c; total += c; }
-            if (keep) {
-                const unsigned pos = S + woff + __popc(bal & ((1u << lane) - 1u));
-                s_surv[pos] = col[r];
-                s_list[pos] = (unsigned short)(tid + r * kThreads);
-            }
-            S += total;
-            __syncthreads();  // s_wc is reused by the next round
-        }
-        for (unsigned i = tid; i < S; i += kThreads) {
-            s_cnt[i] = 0u;
-            if (SUMS) { s_sum[3 * i] = 0ull; s_sum[3 * i + 1] = 0ull; s_sum[3 * i + 2] = 0ull; }
-        }
-        __syncthreads();
-        // ---- 3. exact sweep over the survivors: strict '<', ascending index = lowest index wins
-        float best[kPxPerThread];
-        int bi[kPxPerThread];
-#pragma unroll
-        for (int j = 0; j < kPxPerThread; ++j) { best[j] = INF; bi[j] = 0; }
-        for (unsigned i = 0; i < S; ++i) {
-            const float4 q = s_surv[i];
-#pragma unroll
-            for (int j = 0; j < kPxPerThread; ++j) {
-                const float d = hq_dist2(x0[j], x1[j], x2[j], q.x, q.y, q.z);
-                if (d < best[j]) { best[j] = d; bi[j] = (int)i; }
-            }
-        }
-        // ---- epilogue: error, counts, sums (per survivor slot), then one flush per touched colour
-        long long err_acc = 0;
-#pragma unroll
-        for (int j = 0; j < kPxPerThread; ++j) {
-            if ((unsigned)(j * kThreads + tid) < len) {
-                err_acc += hq_to_fx(HQ_FSQRT(best[j]));
-                atomicAdd(&s_cnt[bi[j]], 1u);
-                if (SUMS) {
-                    atomicAdd(&s_sum[3 * bi[j]], (unsigned long long)hq_to_fx(x0[j]));
-                    atomicAdd(&s_sum[3 * bi[j] + 1], (unsigned long long)hq_to_fx(x1[j]));
-                    atomicAdd(&s_sum[3 * bi[j] + 2], (unsigned long long)hq_to_fx(x2[j]));
-                }
-            }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) err_acc += __shfl_down_sync(0xffffffffu, err_acc, off);
-        if (lane == 0) s_err[warp] = err_acc;
-        __syncthreads();  // also orders the shared atomics before the flush
-        unsigned long long* out = p.results + (size_t)b * p.words;
-        if (tid == 0) {
-            long long e = 0;
-#pragma unroll
-            for (int w = 0; w < kThreads / 32; ++w) e += s_err[w];
-            if (e != 0) atomicAdd(out, (unsigned long long)e);
-            if (p.stats) { atomicAdd(p.stats, (unsigned long long)S); atomicAdd(p.stats + 1, 1ull); }
-        }
-        for (unsigned i = tid; i < S; i += kThreads) {
-            const unsigned c = s_cnt[i];
-            if (c) {
-                const int k = s_list[i];
-                atomicAdd(out + 1 + k, (unsigned long long)c);
-                if (SUMS) {
-                    atomicAdd(out + 1 + K + 3 * k, s_sum[3 * i]);
-                    atomicAdd(out + 1 + K + 3 * k + 1, s_sum[3 * i + 1]);
-                    atomicAdd(out + 1 + K + 3 * k + 2, s_sum[3 * i + 2]);
-                }
-            }
-        }
-        __syncthreads();  // the shared lists are rebuilt for the next candidate
-    }
+    // the sweep and epilogue are specialised on the number of 256-pixel slots the chunk occupies: a half-empty chunk costs half
+    if (len <= 2 * kThreads) score_chunk<2, SUMS>(p, sm, s_U, s_err, start, len, lo, hi);
+    else if (len <= 4 * kThreads) score_chunk<4, SUMS>(p, sm, s_U, s_err, start, len, lo, hi);
+    else if (len <= 6 * kThreads) score_chunk<6, SUMS>(p, sm, s_U, s_err, start, len, lo, hi);
+    else score_chunk<kPxPerThread, SUMS>(p, sm, s_U, s_err, start, len, lo, hi);
 }
 
 }  // namespace
@@ -318,7 +344,8 @@ cudaError_t launch_pruned_assign(const PrunedArgs& a, cudaStream_t st) {
     if (groups > a.B) groups = a.B;
     p.b_per_cta = (a.B + groups - 1) / groups;
     groups = (a.B + p.b_per_cta - 1) / p.b_per_cta;
-    const size_t smem = (size_t)p.K8 * (16 + 4 + 2) + (a.want_sums ? (size_t)p.K8 * 24 : 0);
+    const size_t K32 = ((size_t)a.K + 31) & ~(size_t)31;
+    const size_t smem = K32 * (16 + 4 + 2) + K32 / 32 * 4 + (a.want_sums ? K32 * 24 : 0);
     const dim3 grid(a.nchunks, (unsigned)groups);
     cudaError_t e;
     if (a.want_sums) {
