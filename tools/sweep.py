@@ -22,7 +22,8 @@ sys.path.insert(0, REPO)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from hybridquantization_b200 import EVAL_FORCE_CHUNKED, EVAL_FORCE_DIRECT, EVAL_FORCE_PREFILTER, SWASA, ImageManipulation, synth  # noqa: E402
+from hybridquantization_b200 import (EVAL_FORCE_CHUNKED, EVAL_FORCE_DIRECT, EVAL_FORCE_PREFILTER, EVAL_PRUNE, PRUNE_AUTO, PRUNE_OFF, SWASA,  # noqa: E402
+                                     ImageManipulation, synth)
 
 
 def main():
@@ -30,6 +31,7 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--skip-swasa", action="store_true")
     ap.add_argument("--only-scielab", action="store_true")
+    ap.add_argument("--only-swasa", action="store_true")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
@@ -60,7 +62,7 @@ def main():
 
     # ---- RGB -> Lab (15 B/pixel algorithmic: 3 B read + 12 B written)
     out["rgb_to_lab"] = []
-    for (w, h) in (() if a.only_scielab else ((1920, 1080), (3840, 2160), (8192, 8192))):
+    for (w, h) in (() if (a.only_scielab or a.only_swasa) else ((1920, 1080), (3840, 2160), (8192, 8192))):
         img = synth.synth_image_rows(w, h, synth.SEED_BASE + 3, 0, h)
         d_img = torch.from_numpy(img).to(dev)
         be.setProfiling(True)
@@ -87,7 +89,7 @@ def main():
     d_img = torch.from_numpy(img).to(dev)
     be.setImageDevice(d_img.data_ptr(), w, h, stream=st.cuda_stream)
     out["k_sweep"] = []
-    ks = () if a.only_scielab else (8, 16, 32, 64, 128, 256, 512, 1024)
+    ks = () if (a.only_scielab or a.only_swasa) else (8, 16, 32, 64, 128, 256, 512, 1024)
     for K in ks:
         for B in (1, 64):
             if a.quick and B == 64 and K > 256:
@@ -97,8 +99,8 @@ def main():
             words = be.resultWords(K, 0)
             d_res = torch.zeros((B, words), dtype=torch.int64, device=dev)
             row = {"K": K, "B": B}
-            for name, fl in (("auto", 0), ("direct", EVAL_FORCE_DIRECT), ("chunked", EVAL_FORCE_CHUNKED), ("prefilter", EVAL_FORCE_PREFILTER)):
-                if name != "auto" and (a.quick or B == 64 and K > 256):
+            for name, fl in (("auto", 0), ("pruned", EVAL_PRUNE), ("direct", EVAL_FORCE_DIRECT), ("chunked", EVAL_FORCE_CHUNKED), ("prefilter", EVAL_FORCE_PREFILTER)):
+                if name not in ("auto", "pruned") and (a.quick or B == 64 and K > 256):
                     continue
                 ms, best = timed(lambda: be.evalPalettesDevice(d_pal.data_ptr(), B, K, d_res.data_ptr(), 0, fl, st.cuda_stream), reps=3 if B == 64 else 7)
                 assert int(d_res[0, 1:1 + K].sum().item()) == n
@@ -110,7 +112,7 @@ def main():
 
     # ---- S-CIELAB stage (next row 1): full reference cost chain per candidate, through the host-buffer C ABI
     out["scielab"] = []
-    for (w, h, K, B) in (((3840, 2160, 256, 4),) if a.only_scielab else ((1920, 1080, 256, 4), (3840, 2160, 256, 4), (3840, 2160, 256, 16))):
+    for (w, h, K, B) in (() if a.only_swasa else ((3840, 2160, 256, 4),) if a.only_scielab else ((1920, 1080, 256, 4), (3840, 2160, 256, 4), (3840, 2160, 256, 16))):
         img = synth.synth_image_rows(w, h, synth.SEED_BASE + 2, 0, h)
         be.setImage(img)
         be.scielabConfigure(72, 45.0)
@@ -133,16 +135,27 @@ def main():
     # ---- full SWASA runs through the C ABI (host buffers, host annealing loop)
     if not a.skip_swasa:
         out["swasa"] = []
-        for name, (w, h, K, P, imax) in {"C1_512x512_k16_p4_i5000": (512, 512, 16, 4, 5000),
-                                         "C2_1920x1080_k256_p4_i" + ("100" if a.quick else "1000"): (1920, 1080, 256, 4, 100 if a.quick else 1000)}.items():
-            img = synth.synth_image(w, h, synth.SEED_BASE + 2, smooth=True)
+        # full fixed-seed searches through the C ABI, exhaustive scoring vs exact pruned scoring (same trajectory, same palette)
+        for name, (w, h, K, P, imax, smooth) in {"C1_512x512_k16_p4_i5000": (512, 512, 16, 4, 5000, True),
+                                                 "C2_1920x1080_k256_p4_i" + ("100" if a.quick else "1000"): (1920, 1080, 256, 4, 100 if a.quick else 1000, True),
+                                                 "C2u_1920x1080_k256_p4_uniform_i" + ("100" if a.quick else "1000"): (1920, 1080, 256, 4, 100 if a.quick else 1000, False),
+                                                 "C3_3840x2160_k256_p64_i" + ("10" if a.quick else "100"): (3840, 2160, 256, 64, 10 if a.quick else 100, False)}.items():
+            img = synth.synth_image(w, h, synth.SEED_BASE + 2, smooth=smooth)
             be.setImage(img)
-            sw = SWASA(population=P, imax=imax, seed=77760)
-            t0 = time.perf_counter()
-            best, err, _, its = be.findBestQuantization(K, sw)
-            dt = time.perf_counter() - t0
-            out["swasa"].append({"config": name, "seconds": dt, "iterations": its, "evals_per_s": (its + 1) * P / dt, "best_error": err,
-                                 "gpixel_per_s": (its + 1) * P * w * h / dt / 1e9})
+            row = {"config": name}
+            for mode, label in ((PRUNE_OFF, "exhaustive"), (PRUNE_AUTO, "pruned_auto")):
+                be.setPruning(mode)
+                sw = SWASA(population=P, imax=imax, seed=77760)
+                t0 = time.perf_counter()
+                best, err, _, its = be.findBestQuantization(K, sw)
+                dt = time.perf_counter() - t0
+                row[label] = {"seconds": dt, "iterations": its, "evals_per_s": (its + 1) * P / dt, "best_error": err,
+                              "gpixel_per_s": (its + 1) * P * w * h / dt / 1e9, "best_palette_crc": int(np.bitwise_xor.reduce(best.view(np.uint32).ravel()))}
+            row["identical"] = row["exhaustive"]["best_error"] == row["pruned_auto"]["best_error"] and \
+                row["exhaustive"]["best_palette_crc"] == row["pruned_auto"]["best_palette_crc"]
+            row["speedup"] = row["exhaustive"]["seconds"] / row["pruned_auto"]["seconds"]
+            out["swasa"].append(row)
+        be.setPruning(PRUNE_AUTO)
     be.close()
     print(json.dumps(out))
 
