@@ -12,7 +12,7 @@ import torch.distributed as dist
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 
-from hybridquantization_b200 import COST_SCIELAB, SPACE_SRGB, SWASA, ImageManipulation, synth  # noqa: E402
+from hybridquantization_b200 import COST_SCIELAB, EVAL_PRUNE, PRUNE_OFF, SPACE_SRGB, SWASA, ImageManipulation, synth  # noqa: E402
 from hybridquantization_b200.dist import install_nccl_allreduce, row_shard, row_shard_with_halo  # noqa: E402
 
 
@@ -29,9 +29,11 @@ def main():
     be.setImage(img[r0:r1])
     install_nccl_allreduce(be)
     got = be.evalPalettes(pal, sums=True)                     # totals over all ranks
+    got_pruned = be.evalPalettes(pal, sums=True, flags=EVAL_PRUNE)   # the exact pruned kernel on every shard, same all-reduce
     sw = SWASA(population=4, imax=60, seed=2024)
     best, err, tr, its = be.findBestQuantization(K, sw, n_total=w * h, trace=True)
     res = {"rank": rank, "ok": True}
+    res["pruned_equals_exhaustive"] = all(np.array_equal(got[k], got_pruned[k]) for k in ("err_fx", "counts", "sums_fx"))
     # every rank must hold identical totals / trajectory
     blob = torch.from_numpy(np.concatenate([got["err_fx"], got["counts"].astype(np.int64).ravel(), got["sums_fx"].ravel(),
                                             tr.view(np.int64).ravel(), best.view(np.int32).astype(np.int64).ravel()])).cuda()
@@ -41,6 +43,7 @@ def main():
     if rank == 0:
         single = ImageManipulation("CIE76", False, True, local)
         single.setImage(img)
+        single.setPruning(PRUNE_OFF)   # the single-GPU reference run scores exhaustively; the sharded run above prunes (AUTO)
         want = single.evalPalettes(pal, sums=True)
         sbest, serr, str_, _ = single.findBestQuantization(K, SWASA(population=4, imax=60, seed=2024), trace=True)
         single.close()
