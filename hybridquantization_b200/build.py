@@ -20,8 +20,9 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # operation.  x86-64-v3 (AVX2 + FMA, no AVX-512): the library is built here and runs on the
 # GPU box's CPU.
 HOST_FLAGS = "-fPIC,-ffp-contract=off,-march=x86-64-v3,-fno-math-errno,-Wall"
-# -fmad=false: ptxas must not contract mul+add pairs; every fused multiply-add of the path is written explicitly.
-# (Needed for the packed f32x2 ops too: without it ptxas fused mul.rn.f32x2 + add.rn.f32x2 into FFMA2.)
+# -fmad=false: no contraction of C++-level a*b+c; every fused multiply-add of the path is written explicitly (__fmaf_rn /
+# fma.rn.f32x2).  It does NOT reach inline PTX: ptxas still fuses mul.rn.f32x2 + add.rn.f32x2 — see add2_of_product in
+# csrc/hq_kernels.cu for how the packed pixel path prevents that.
 NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-fmad=false", "-Xcompiler", HOST_FLAGS]
 
 

@@ -135,21 +135,32 @@ struct PrunedParams {
 // shared-memory carve-up: survivors live in per-warp SEGMENTS (segment g = colours [32g, 32g+32), filled from slot 32g
 // upwards in ascending colour order), so the compaction needs no prefix sum across warps and the sweep still visits
 // the survivors in ascending colour index.
-struct PrunedSmem {
+extern __shared__ __align__(16) unsigned char pruned_smem_raw[];
+template <bool SUMS>
+struct PrunedSmem {  // typed views of the dynamic shared memory, recomputed where they are used so that they stay LDS/STS/ATOMS
     float4* surv;               // [K32] Lab of the survivor in each slot
     unsigned long long* sum;    // [3*K32] per-slot Lab sums (SUMS)
     unsigned* cnt;              // [K32] per-slot pixel counts
     unsigned short* list;       // [K32] colour index of each slot
     unsigned* segcnt;           // [K32/32] survivors per segment
     int K32;                    // K rounded up to whole segments
+    __device__ __forceinline__ explicit PrunedSmem(int K) {
+        K32 = (K + 31) & ~31;
+        surv = reinterpret_cast<float4*>(pruned_smem_raw);
+        sum = reinterpret_cast<unsigned long long*>(pruned_smem_raw + (size_t)K32 * 16);
+        cnt = reinterpret_cast<unsigned*>(pruned_smem_raw + (size_t)K32 * 16 + (SUMS ? (size_t)K32 * 24 : 0));
+        list = reinterpret_cast<unsigned short*>(cnt + K32);
+        segcnt = reinterpret_cast<unsigned*>(list + K32);
+    }
 };
 
 // One candidate on one chunk whose pixels sit in registers (NS slots of 256 pixels).  3 CTA barriers.
 template <int NS, bool SUMS>
-__device__ __forceinline__ void score_candidate(const PrunedParams& p, const PrunedSmem& sm, unsigned* s_U, long long* s_err, int b, int parity,
+__device__ __forceinline__ void score_candidate(const PrunedParams& p, unsigned* s_U, long long* s_err, int b, int parity,
                                                 const float (&x0)[NS], const float (&x1)[NS], const float (&x2)[NS], unsigned len,
                                                 const float (&lo)[3], const float (&hi)[3]) {
     const int K = p.K, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const PrunedSmem<SUMS> sm(K);
     const float INF = __int_as_float(0x7f800000);
     constexpr int kRounds = kMaxColors / kThreads;  // colour k = tid + 256*r
     const int nseg = (K + 31) >> 5;
@@ -262,7 +273,7 @@ __device__ __forceinline__ void score_candidate(const PrunedParams& p, const Pru
 
 // all candidates of this CTA on one chunk of <= NS*256 pixels
 template <int NS, bool SUMS>
-__device__ __forceinline__ void score_chunk(const PrunedParams& p, const PrunedSmem& sm, unsigned* s_U, long long* s_err, size_t start, unsigned len,
+__device__ __forceinline__ void score_chunk(const PrunedParams& p, unsigned* s_U, long long* s_err, size_t start, unsigned len,
                                             const float (&lo)[3], const float (&hi)[3]) {
     const int tid = threadIdx.x;
     float x0[NS], x1[NS], x2[NS];  // the chunk's pixels stay in registers for every candidate
@@ -275,20 +286,11 @@ __device__ __forceinline__ void score_chunk(const PrunedParams& p, const PrunedS
         x2[j] = ok ? __ldg(p.sorted + 2 * p.sstride + start + i) : 0.f;
     }
     const int b_begin = blockIdx.y * p.b_per_cta, b_end = min(p.B, b_begin + p.b_per_cta);
-    for (int b = b_begin; b < b_end; ++b) score_candidate<NS, SUMS>(p, sm, s_U, s_err, b, (b - b_begin) & 1, x0, x1, x2, len, lo, hi);
+    for (int b = b_begin; b < b_end; ++b) score_candidate<NS, SUMS>(p, s_U, s_err, b, (b - b_begin) & 1, x0, x1, x2, len, lo, hi);
 }
 
 template <bool SUMS>
 __global__ void __launch_bounds__(kThreads, 2) pruned_assign_kernel(const PrunedParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int K32 = (p.K + 31) & ~31;
-    PrunedSmem sm;
-    sm.K32 = K32;
-    sm.surv = reinterpret_cast<float4*>(smem_raw);
-    sm.sum = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)K32 * 16);
-    sm.cnt = reinterpret_cast<unsigned*>(smem_raw + (size_t)K32 * 16 + (SUMS ? (size_t)K32 * 24 : 0));
-    sm.list = reinterpret_cast<unsigned short*>(sm.cnt + K32);
-    sm.segcnt = reinterpret_cast<unsigned*>(sm.list + K32);
     __shared__ unsigned s_U[2];
     __shared__ long long s_err[kThreads / 32];
     if (threadIdx.x < 2) s_U[threadIdx.x] = 0x7f800000u;
@@ -300,10 +302,10 @@ __global__ void __launch_bounds__(kThreads, 2) pruned_assign_kernel(const Pruned
 #pragma unroll
     for (int a = 0; a < 3; ++a) { lo[a] = __ldg(p.box + 6 * (size_t)chunk + a); hi[a] = __ldg(p.box + 6 * (size_t)chunk + 3 + a); }
     // the sweep and epilogue are specialised on the number of 256-pixel slots the chunk occupies: a half-empty chunk costs half
-    if (len <= 2 * kThreads) score_chunk<2, SUMS>(p, sm, s_U, s_err, start, len, lo, hi);
-    else if (len <= 4 * kThreads) score_chunk<4, SUMS>(p, sm, s_U, s_err, start, len, lo, hi);
-    else if (len <= 6 * kThreads) score_chunk<6, SUMS>(p, sm, s_U, s_err, start, len, lo, hi);
-    else score_chunk<kPxPerThread, SUMS>(p, sm, s_U, s_err, start, len, lo, hi);
+    if (len <= 2 * kThreads) score_chunk<2, SUMS>(p, s_U, s_err, start, len, lo, hi);
+    else if (len <= 4 * kThreads) score_chunk<4, SUMS>(p, s_U, s_err, start, len, lo, hi);
+    else if (len <= 6 * kThreads) score_chunk<6, SUMS>(p, s_U, s_err, start, len, lo, hi);
+    else score_chunk<kPxPerThread, SUMS>(p, s_U, s_err, start, len, lo, hi);
 }
 
 }  // namespace
