@@ -74,3 +74,25 @@ def test_live_reference_kernels(backend, ref, w, h, K, smooth):
     for i in range(2):
         assert int(np.rint(det[i]["err"].astype(np.float64) * 2.0 ** 24).astype(np.int64).sum()) == int(got["err_fx"][i])
         assert np.array_equal(det[i]["used"] != 0, got["counts"][i] > 0)
+
+
+def test_4k_k256_search_and_image_match_the_compiled_reference(backend, ref):
+    """north_star's last clause at the NAMED size: a fixed-seed 3840x2160, K=256 SWASA run (shortened to 10 iterations of a
+    population of 4 so that the reference's kernels finish on the host cores in about half a minute) through the CUDA path in
+    its reference-faithful mode, against the reference's own annealing loop + OpenCL kernel chain + quantize kernel compiled
+    for the CPU: same candidate costs (to the double-sum / fixed-point difference), same palette, same quantised image."""
+    w, h, K, P, imax, seed = 3840, 2160, 256, 4, 10, 20261018
+    img = synth.synth_image(w, h, synth.SEED_BASE + 3, smooth=True)
+    f, a = ref.scielab_filters(72, 45.0)
+    sw = ref.Swasa(population=P, imax=imax, iTc=3)
+    ref.seed(seed)
+    rbest, rerr, rtr = ref.reference_plugin_search(img, K, sw, f, a, trace=True, depth=0)
+    backend.setImage(img)
+    backend.scielabConfigure(72, 45.0)
+    best, err, tr, its = backend.findBestQuantization(K, SWASA(population=P, imax=imax, iTc=3, seed=seed, space=SPACE_SRGB, costModel=COST_SCIELAB), trace=True)
+    assert its == imax and np.allclose(tr, rtr, rtol=0, atol=2.0 ** -23)
+    assert abs(err - rerr) <= 2.0 ** -23 and np.array_equal(bits(best), bits(rbest))
+    # the output image: quantize kernel (cl:147-170) vs hq_quantize in sRGB space
+    rq, rused = ref.quantize(ref.makeinline(ref.unit_planes(img)), rbest)
+    q = backend.quantize(best, SPACE_SRGB, want_f32=True)
+    assert np.array_equal(bits(q["f32"]), bits(rq))
