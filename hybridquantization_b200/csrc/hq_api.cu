@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -129,6 +130,22 @@ int fail(hq_ctx* c, int code, const char* fmt, ...) {
             return fail((c), HQ_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
     } while (0)
 
+// Completion wait of the per-iteration calls (hq_eval_palettes*): poll the stream for a few milliseconds before falling
+// back to cudaStreamSynchronize.  The default synchronisation may yield the CPU, and in a process with other busy threads
+// (a Python host with a thread pool, a JVM) the wake-up then costs as much as a whole pruned scoring step — measured: a
+// 1080p search of 1,000 iterations took 0.18 s instead of 0.09 s, a 4K / 64-candidate one 0.67 s instead of 0.37 s.
+cudaError_t wait_stream(cudaStream_t st) {
+    using clock = std::chrono::steady_clock;
+    const auto t0 = clock::now();
+    for (;;) {
+        for (int i = 0; i < 64; ++i) {
+            const cudaError_t e = cudaStreamQuery(st);
+            if (e != cudaErrorNotReady) return e;
+        }
+        if (clock::now() - t0 > std::chrono::milliseconds(8)) return cudaStreamSynchronize(st);
+    }
+}
+
 int bind_device(hq_ctx* c) {
     HQ_CUDA(c, cudaSetDevice(c->device));
     return HQ_OK;
@@ -200,8 +217,7 @@ int eval_device(hq_ctx* c, const float* d_palettes, int B, int K, int space, int
     HQ_CUDA(c, c->d_pal_lab.reserve((size_t)B * K8));
     HQ_CUDA(c, c->d_pal_rgb.reserve((size_t)B * K8));
     if (space == HQ_SPACE_SRGB) { int rc = ensure_unit(c, st); if (rc) return rc; }
-    HQ_CUDA(c, cudaMemsetAsync(d_results, 0, (size_t)B * words * 8, st));
-    HQ_CUDA(c, hq::launch_palette_features(d_palettes, B, K, c->whitepoint, c->d_pal_lab.p, c->d_pal_rgb.p, st));
+    HQ_CUDA(c, hq::launch_palette_features(d_palettes, B, K, c->whitepoint, c->d_pal_lab.p, c->d_pal_rgb.p, st, d_results, (size_t)B * words));
     hq::AssignArgs a;
     a.lab = c->d_lab.p; a.unit = c->d_unit.p; a.n = c->n; a.stride = c->stride;
     a.pal_lab = c->d_pal_lab.p; a.pal_rgb = c->d_pal_rgb.p;
@@ -374,7 +390,7 @@ int hq_eval_palettes(hq_ctx* c, const float* palettes, int B, int K, int space, 
             return fail(c, HQ_ERR_CALLBACK, "all-reduce hook failed");
     }
     HQ_CUDA(c, cudaMemcpyAsync(c->h_results.p, c->d_results.p, nwords * 8, cudaMemcpyDeviceToHost, c->stream));
-    HQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    HQ_CUDA(c, wait_stream(c->stream));
     for (int b = 0; b < B; ++b) {
         const unsigned long long* w = c->h_results.p + (size_t)b * words;
         if (err_fx) err_fx[b] = (int64_t)w[0];
@@ -606,7 +622,7 @@ int hq_eval_palettes_scielab(hq_ctx* c, const float* palettes, int B, int K, int
     HQ_CUDA(c, cudaMemcpy2DAsync(c->d_results.p, (size_t)words * 8, c->d_sc_err.p, 8, 8, (size_t)B, cudaMemcpyDeviceToDevice, c->stream));
     if (c->allreduce && c->allreduce(c->allreduce_user, c->d_results.p, nwords, c->stream) != 0) return fail(c, HQ_ERR_CALLBACK, "all-reduce hook failed");
     HQ_CUDA(c, cudaMemcpyAsync(c->h_results.p, c->d_results.p, nwords * 8, cudaMemcpyDeviceToHost, c->stream));
-    HQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    HQ_CUDA(c, wait_stream(c->stream));
     for (int b = 0; b < B; ++b) {
         if (err_fx) err_fx[b] = (int64_t)c->h_results.p[(size_t)b * words];
         if (counts) std::memcpy(counts + (size_t)b * K, c->h_results.p + (size_t)b * words + 1, sizeof(uint64_t) * K);

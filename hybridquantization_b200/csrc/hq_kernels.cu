@@ -253,8 +253,10 @@ rgb_to_lab_kernel(const uint8_t* __restrict__ rgb, size_t n, size_t stride, int 
 // ====================================================================== palettes -> features
 __global__ void palette_features_kernel(const float* __restrict__ pal, int B, int K, int K8,
                                         int whitepoint, float4* __restrict__ pal_lab,
-                                        float4* __restrict__ pal_rgb) {
+                                        float4* __restrict__ pal_rgb, unsigned long long* __restrict__ zero, size_t zero_words) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // the result words of the evaluation that follows on the same stream are cleared here (saves a memset node per iteration)
+    for (size_t z = (size_t)i; z < zero_words; z += (size_t)gridDim.x * blockDim.x) zero[z] = 0ull;
     if (i >= B * K8) return;
     const int b = i / K8, k = i - b * K8;
     float4 lab = make_float4(kFar, kFar, kFar, 0.f), rgbv = lab;
@@ -657,16 +659,27 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : 2) a
     }
 }
 
+// per (kernel instantiation, device): the dynamic shared-memory size last configured and the occupancy it gave, so that
+// the per-iteration launches of a search do not pay cudaFuncSetAttribute + an occupancy query every time
+struct LaunchCache { size_t smem = ~(size_t)0; int occ = 0; };
 template <int VARIANT, bool SRGB, bool SUMS, int IDXW>
 cudaError_t launch_assign_t(const AssignParams& p, int B, int sm_count, cudaStream_t stream) {
     auto kern = assign_reduce_kernel<VARIANT, SRGB, SUMS, IDXW>;
     const size_t smem = AssignSmem<VARIANT, SRGB, SUMS>(p.K8).total;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static thread_local LaunchCache cache[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem);
-    if (e != cudaSuccess) return e;
-    if (occ < 1) occ = 1;
+    LaunchCache& lc = cache[dev & 63];
+    if (lc.smem != smem) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int o = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, smem);
+        if (e != cudaSuccess) return e;
+        lc.smem = smem; lc.occ = o < 1 ? 1 : o;
+    }
+    const int occ = lc.occ;
     const long long slots = (long long)sm_count * occ;
     const long long ntiles = (long long)((p.n + kTilePx - 1) / kTilePx);
     // CTAs per candidate (G): B*G must be a whole number of waves of the `slots` resident CTAs,
@@ -774,11 +787,11 @@ cudaError_t launch_rgb_to_lab(const uint8_t* d_rgb, size_t n, size_t stride, int
 }
 
 cudaError_t launch_palette_features(const float* d_palettes, int B, int K, int whitepoint,
-                                    float4* d_pal_lab, float4* d_pal_rgb, cudaStream_t stream) {
+                                    float4* d_pal_lab, float4* d_pal_rgb, cudaStream_t stream, unsigned long long* d_zero, size_t zero_words) {
     const int K8 = padded_colors(K);
     const int total = B * K8;
     if (total == 0) return cudaSuccess;
-    palette_features_kernel<<<(total + 127) / 128, 128, 0, stream>>>(d_palettes, B, K, K8, whitepoint, d_pal_lab, d_pal_rgb);
+    palette_features_kernel<<<(total + 127) / 128, 128, 0, stream>>>(d_palettes, B, K, K8, whitepoint, d_pal_lab, d_pal_rgb, d_zero, zero_words);
     return cudaGetLastError();
 }
 

@@ -26,9 +26,11 @@ cudaError_t launch_rgb_to_lab(const uint8_t* d_rgb, size_t n, size_t stride, int
                               float* d_lab, float* d_unit, int sm_count, cudaStream_t stream);
 
 // palettes [B][K][4] sRGB floats -> padded feature tables [B][K8] float4:
-// pal_lab = (L, a, b, 0), pal_rgb = (r, g, b, 0); pad entries are 1e18.
+// pal_lab = (L, a, b, 0), pal_rgb = (r, g, b, 0); pad entries are 1e18.  Optionally clears d_zero[0 .. zero_words) (the
+// result words of the evaluation launched next on the same stream).
 cudaError_t launch_palette_features(const float* d_palettes, int B, int K, int whitepoint,
-                                    float4* d_pal_lab, float4* d_pal_rgb, cudaStream_t stream);
+                                    float4* d_pal_lab, float4* d_pal_rgb, cudaStream_t stream, unsigned long long* d_zero = nullptr,
+                                    size_t zero_words = 0);
 
 struct AssignArgs {
     const float* lab;      // [3][stride]

@@ -5,8 +5,8 @@
 // candidate, as quantizeAndConvertToOpp does (OptimizedConvolution.cl:178-193).  Every output of the
 // scoring step is a SUM over pixels (error, per-colour counts, Lab sums), so the pixels may be visited
 // in any order.  Once per image the own pixels are therefore counting-sorted by a coarse CIELAB cell
-// (5 bits per axis) and cut into chunks of <= 2048 pixels that never straddle a cell; each chunk keeps
-// its exact bounding box.  Per (chunk, candidate) a CTA then
+// (5 bits per axis), and inside a cell by the Morton code of a 4x4x4 sub-grid, and cut into chunks of <= 2048
+// pixels that never straddle a cell; each chunk keeps its exact bounding box.  Per (chunk, candidate) a CTA then
 //   1. bounds every colour against the box:  dmin_k <= |x - p_k| <= dmax_k  for every pixel x of the chunk,
 //   2. takes U = min_k dmax_k (some colour is within U of every pixel) and keeps the colours with
 //      dmin_k^2 <= U^2 * (1 + 2^-18): a discarded colour is strictly farther from every pixel of the chunk
@@ -27,32 +27,44 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kPxPerThread = kPrunedChunkPx / kThreads;  // 8
-constexpr int kCellBits = 5;
-constexpr int kCells = 1 << (3 * kCellBits);  // 32768
+constexpr int kCellBits = 5;                       // coarse cell: chunks never straddle one
+constexpr int kCells = 1 << (3 * kCellBits);       // 32768
+constexpr int kSubBits = 2;                        // each cell is ordered by a 4 x 4 x 4 Morton sub-grid
+constexpr int kSub = 1 << (3 * kSubBits);          // 64 bins per cell
+constexpr int kBins = kCells * kSub;               // 2,097,152 counting-sort bins
 
-// coarse CIELAB cell of a pixel: L in [0,100] -> 32 slabs of 3.125, a and b in [-128,128) -> 32 slabs of 8.
-// Only a partition: any deterministic function works, exactness is irrelevant.
-__device__ __forceinline__ unsigned cell_of(float L, float a, float b) {
-    const int l = min(max(__float2int_rd(L * 0.32f), 0), 31);
-    const int u = min(max(__float2int_rd((a + 128.0f) * 0.125f), 0), 31);
-    const int v = min(max(__float2int_rd((b + 128.0f) * 0.125f), 0), 31);
-    return (unsigned)((l << 10) | (u << 5) | v);
+// Bin of a pixel: coarse CIELAB cell (L in [0,100] -> 32 slabs of 3.125, a and b in [-128,128) -> 32 slabs of 8) in the
+// high bits, the Morton code of its position inside the cell (2 bits per axis) in the low 6.  Only an ORDER: any
+// deterministic function works, exactness is irrelevant (the chunk boxes are exact).  Ordering the inside of a cell makes
+// the chunks of a crowded cell compact (and their composition deterministic) instead of random subsets of the cell.
+__device__ __forceinline__ unsigned bin_of(float L, float a, float b) {
+    const unsigned l = (unsigned)min(max(__float2int_rd(L * 1.28f), 0), 127);
+    const unsigned u = (unsigned)min(max(__float2int_rd((a + 128.0f) * 0.5f), 0), 127);
+    const unsigned v = (unsigned)min(max(__float2int_rd((b + 128.0f) * 0.5f), 0), 127);
+    const unsigned cell = ((l >> 2) << 10) | ((u >> 2) << 5) | (v >> 2);
+    const unsigned ls = l & 3u, us = u & 3u, vs = v & 3u;
+    const unsigned sub = ((ls & 2u) << 4) | ((us & 2u) << 3) | ((vs & 2u) << 2) | ((ls & 1u) << 2) | ((us & 1u) << 1) | (vs & 1u);
+    return (cell << 6) | sub;
 }
 
 __global__ void cell_hist_kernel(const float* __restrict__ lab, size_t stride, size_t lo, size_t hi, unsigned* __restrict__ hist) {
     for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x)
-        atomicAdd(&hist[cell_of(lab[i], lab[stride + i], lab[2 * stride + i])], 1u);
+        atomicAdd(&hist[bin_of(lab[i], lab[stride + i], lab[2 * stride + i])], 1u);
 }
 
-// one CTA of 1024 threads: exclusive scans of the cell populations (pixel offsets) and of the chunks per cell
-__global__ void __launch_bounds__(1024) cell_scan_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ cell_off,
-                                                         unsigned* __restrict__ chunk_base, unsigned* __restrict__ totals) {
+// one CTA of 1024 threads, 32 cells (2048 bins) per thread: exclusive scan of the bin populations (first sorted position of
+// every bin) and of the chunks per cell
+__global__ void __launch_bounds__(1024) cell_scan_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ bin_off,
+                                                         unsigned* __restrict__ cell_cnt, unsigned* __restrict__ chunk_base,
+                                                         unsigned* __restrict__ totals) {
     __shared__ unsigned s_px[1024], s_ch[1024];
     const int t = threadIdx.x;
     constexpr int per = kCells / 1024;  // 32 consecutive cells per thread
     unsigned px = 0, ch = 0;
     for (int i = 0; i < per; ++i) {
-        const unsigned h = hist[t * per + i];
+        unsigned h = 0;
+        for (int j = 0; j < kSub; ++j) h += hist[(size_t)(t * per + i) * kSub + j];
+        cell_cnt[t * per + i] = h;
         px += h; ch += (h + kPrunedChunkPx - 1) / kPrunedChunkPx;
     }
     s_px[t] = px; s_ch[t] = ch;
@@ -65,31 +77,34 @@ __global__ void __launch_bounds__(1024) cell_scan_kernel(const unsigned* __restr
     }
     unsigned opx = s_px[t] - px, och = s_ch[t] - ch;
     for (int i = 0; i < per; ++i) {
-        const unsigned h = hist[t * per + i];
-        cell_off[t * per + i] = opx; chunk_base[t * per + i] = och;
-        opx += h; och += (h + kPrunedChunkPx - 1) / kPrunedChunkPx;
+        chunk_base[t * per + i] = och;
+        och += (cell_cnt[t * per + i] + kPrunedChunkPx - 1) / kPrunedChunkPx;
+        for (int j = 0; j < kSub; ++j) {
+            bin_off[(size_t)(t * per + i) * kSub + j] = opx;
+            opx += hist[(size_t)(t * per + i) * kSub + j];
+        }
     }
     if (t == 1023) { totals[0] = s_px[t]; totals[1] = s_ch[t]; }
 }
 
-__global__ void cell_scatter_kernel(const float* __restrict__ lab, size_t stride, size_t lo, size_t hi, const unsigned* __restrict__ cell_off,
+__global__ void cell_scatter_kernel(const float* __restrict__ lab, size_t stride, size_t lo, size_t hi, const unsigned* __restrict__ bin_off,
                                     unsigned* __restrict__ cursor, float* __restrict__ sorted, size_t sstride) {
     for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
         const float L = lab[i], a = lab[stride + i], b = lab[2 * stride + i];
-        const unsigned c = cell_of(L, a, b);
-        const size_t pos = (size_t)cell_off[c] + atomicAdd(&cursor[c], 1u);
+        const unsigned c = bin_of(L, a, b);
+        const size_t pos = (size_t)bin_off[c] + atomicAdd(&cursor[c], 1u);
         sorted[pos] = L; sorted[sstride + pos] = a; sorted[2 * sstride + pos] = b;
     }
 }
 
-__global__ void chunk_table_kernel(const unsigned* __restrict__ hist, const unsigned* __restrict__ cell_off, const unsigned* __restrict__ chunk_base,
+__global__ void chunk_table_kernel(const unsigned* __restrict__ cell_cnt, const unsigned* __restrict__ bin_off, const unsigned* __restrict__ chunk_base,
                                    unsigned* __restrict__ chunk_start, unsigned* __restrict__ chunk_len) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= kCells) return;
-    const unsigned h = hist[c];
+    const unsigned h = cell_cnt[c], first = bin_off[(size_t)c * kSub];
     for (unsigned j = 0, left = h; left > 0; ++j) {
         const unsigned len = left < (unsigned)kPrunedChunkPx ? left : (unsigned)kPrunedChunkPx;
-        chunk_start[chunk_base[c] + j] = cell_off[c] + j * kPrunedChunkPx;
+        chunk_start[chunk_base[c] + j] = first + j * kPrunedChunkPx;
         chunk_len[chunk_base[c] + j] = len;
         left -= len;
     }
@@ -310,24 +325,26 @@ __global__ void __launch_bounds__(kThreads, 2) pruned_assign_kernel(const Pruned
 
 }  // namespace
 
-size_t pruned_scratch_words() { return (size_t)kCells * 4 + 2; }  // hist, cell_off, chunk_base, cursor, totals
+// scratch layout (unsigned words): hist[kBins], bin_off[kBins], cursor[kBins], cell_cnt[kCells], chunk_base[kCells], totals[2]
+size_t pruned_scratch_words() { return (size_t)kBins * 3 + (size_t)kCells * 2 + 2; }
 
 cudaError_t launch_pruned_build_cells(const float* d_lab, size_t stride, size_t own_lo, size_t own_hi, unsigned* d_scratch, float* d_sorted,
                                       size_t sstride, int sm_count, cudaStream_t st) {
-    unsigned *hist = d_scratch, *cell_off = d_scratch + kCells, *chunk_base = d_scratch + 2 * kCells, *cursor = d_scratch + 3 * kCells,
-             *totals = d_scratch + 4 * kCells;
+    unsigned *hist = d_scratch, *bin_off = d_scratch + kBins, *cursor = d_scratch + 2 * (size_t)kBins, *cell_cnt = d_scratch + 3 * (size_t)kBins,
+             *chunk_base = cell_cnt + kCells, *totals = chunk_base + kCells;
+    if (own_hi - own_lo >= 0xffffffffull) return cudaErrorInvalidValue;  // 32-bit sorted positions
     cudaError_t e = cudaMemsetAsync(d_scratch, 0, pruned_scratch_words() * sizeof(unsigned), st);
     if (e != cudaSuccess) return e;
     if (own_hi > own_lo) cell_hist_kernel<<<sm_count * 8, 256, 0, st>>>(d_lab, stride, own_lo, own_hi, hist);
-    cell_scan_kernel<<<1, 1024, 0, st>>>(hist, cell_off, chunk_base, totals);
-    if (own_hi > own_lo) cell_scatter_kernel<<<sm_count * 8, 256, 0, st>>>(d_lab, stride, own_lo, own_hi, cell_off, cursor, d_sorted, sstride);
+    cell_scan_kernel<<<1, 1024, 0, st>>>(hist, bin_off, cell_cnt, chunk_base, totals);
+    if (own_hi > own_lo) cell_scatter_kernel<<<sm_count * 8, 256, 0, st>>>(d_lab, stride, own_lo, own_hi, bin_off, cursor, d_sorted, sstride);
     return cudaGetLastError();
 }
 
 cudaError_t launch_pruned_build_chunks(const unsigned* d_scratch, const float* d_sorted, size_t sstride, unsigned nchunks, unsigned* d_chunk_start,
                                        unsigned* d_chunk_len, float* d_box, cudaStream_t st) {
-    const unsigned *hist = d_scratch, *cell_off = d_scratch + kCells, *chunk_base = d_scratch + 2 * kCells;
-    chunk_table_kernel<<<kCells / 256, 256, 0, st>>>(hist, cell_off, chunk_base, d_chunk_start, d_chunk_len);
+    const unsigned *bin_off = d_scratch + kBins, *cell_cnt = d_scratch + 3 * (size_t)kBins, *chunk_base = cell_cnt + kCells;
+    chunk_table_kernel<<<kCells / 256, 256, 0, st>>>(cell_cnt, bin_off, chunk_base, d_chunk_start, d_chunk_len);
     if (nchunks) chunk_box_kernel<<<(nchunks * 32 + 255) / 256, 256, 0, st>>>(d_sorted, sstride, d_chunk_start, d_chunk_len, nchunks, d_box);
     return cudaGetLastError();
 }
@@ -349,16 +366,19 @@ cudaError_t launch_pruned_assign(const PrunedArgs& a, cudaStream_t st) {
     const size_t K32 = ((size_t)a.K + 31) & ~(size_t)31;
     const size_t smem = K32 * (16 + 4 + 2) + K32 / 32 * 4 + (a.want_sums ? K32 * 24 : 0);
     const dim3 grid(a.nchunks, (unsigned)groups);
-    cudaError_t e;
-    if (a.want_sums) {
-        e = cudaFuncSetAttribute(pruned_assign_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static thread_local size_t configured[2][64];  // [sums][device]: dynamic shared memory last set (0 = never)
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    size_t& have = configured[a.want_sums ? 1 : 0][dev & 63];
+    if (have != smem + 1) {
+        e = a.want_sums ? cudaFuncSetAttribute(pruned_assign_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                        : cudaFuncSetAttribute(pruned_assign_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        pruned_assign_kernel<true><<<grid, kThreads, smem, st>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(pruned_assign_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        pruned_assign_kernel<false><<<grid, kThreads, smem, st>>>(p);
+        have = smem + 1;
     }
+    if (a.want_sums) pruned_assign_kernel<true><<<grid, kThreads, smem, st>>>(p);
+    else pruned_assign_kernel<false><<<grid, kThreads, smem, st>>>(p);
     return cudaGetLastError();
 }
 
