@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -100,6 +101,21 @@ struct hq_ctx {
     DevBuf<float4> d_sc_tab;
     DevBuf<unsigned long long> d_sc_err;
 
+    // CUDA graph of one host-buffer evaluation (H2D palettes, palette kernel, scoring kernel, D2H results): a search repeats
+    // the same launch set thousands of times; for small images the per-launch driver cost dominated an iteration
+    struct EvalKey {
+        int B = 0, K = 0, space = 0, flags = 0; unsigned long long image_gen = 0;
+        const void *d_pal = nullptr, *d_results = nullptr, *h_pal = nullptr, *h_results = nullptr, *d_pal_lab = nullptr, *d_pal_rgb = nullptr;
+        bool operator==(const EvalKey& o) const {
+            return B == o.B && K == o.K && space == o.space && flags == o.flags && image_gen == o.image_gen && d_pal == o.d_pal &&
+                   d_results == o.d_results && h_pal == o.h_pal && h_results == o.h_results && d_pal_lab == o.d_pal_lab && d_pal_rgb == o.d_pal_rgb;
+        }
+    };
+    EvalKey graph_key, seen_key;
+    cudaGraphExec_t graph_exec = nullptr;
+    unsigned long long image_gen = 0;
+    bool use_graphs = true;
+
     hq_progress_fn progress = nullptr;
     void* progress_user = nullptr;
     hq_allreduce_fn allreduce = nullptr;
@@ -167,6 +183,7 @@ int convert_image(hq_ctx* c, int width, int own_rows, int halo_top, int halo_bot
     c->have_unit = false;
     c->sc_image_ready = false;
     c->pruned_ready = false;
+    ++c->image_gen;
     HQ_CUDA(c, c->d_lab.reserve(3 * c->stride > 0 ? 3 * c->stride : 1));
     if (c->profiling) HQ_CUDA(c, cudaEventRecord(c->ev2, st));
     HQ_CUDA(c, hq::launch_rgb_to_lab(c->d_rgb.p, c->n, c->stride, whitepoint, c->d_table.p, c->d_lab.p, nullptr, c->sm_count, st));
@@ -273,6 +290,10 @@ int hq_create(int device, hq_ctx** out) {
         delete c;
         return fail(nullptr, HQ_ERR_CUDA, "device %d: decode table kernel failed: %s (is the library built for this GPU?)", device, cudaGetErrorString(e));
     }
+    {   // HQ_NO_CUDA_GRAPHS=1: every evaluation issues its launches one by one (debugging aid)
+        const char* ng = std::getenv("HQ_NO_CUDA_GRAPHS");
+        c->use_graphs = !(ng && ng[0] == '1');
+    }
     c->sm_count = prop.multiProcessorCount;
     cudaDeviceGetAttribute(&c->clock_khz, cudaDevAttrClockRate, device);
     snprintf(c->name, sizeof c->name, "%s", prop.name);
@@ -284,6 +305,7 @@ void hq_destroy(hq_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
@@ -383,13 +405,50 @@ int hq_eval_palettes(hq_ctx* c, const float* palettes, int B, int K, int space, 
     HQ_CUDA(c, c->h_results.reserve(nwords));
     HQ_CUDA(c, c->d_results.reserve(nwords));
     std::memcpy(c->h_pal.p, palettes, npal * sizeof(float));
-    HQ_CUDA(c, cudaMemcpyAsync(c->d_pal.p, c->h_pal.p, npal * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    rc = eval_device(c, c->d_pal.p, B, K, space, flags, c->d_results.p, nullptr, c->stream); if (rc) return rc;
-    if (c->allreduce) {
-        if (c->allreduce(c->allreduce_user, c->d_results.p, nwords, c->stream) != 0)
-            return fail(c, HQ_ERR_CALLBACK, "all-reduce hook failed");
+    // Everything eval_device may allocate or build lazily happens here, outside any capture
+    {
+        const int K8 = hq::padded_colors(K);
+        HQ_CUDA(c, c->d_pal_lab.reserve((size_t)B * K8));
+        HQ_CUDA(c, c->d_pal_rgb.reserve((size_t)B * K8));
+        if (space == HQ_SPACE_SRGB) { rc = ensure_unit(c, c->stream); if (rc) return rc; }
+        if ((flags & HQ_EVAL_PRUNE) && space == HQ_SPACE_LAB) { rc = ensure_pruned(c, c->stream); if (rc) return rc; }
     }
-    HQ_CUDA(c, cudaMemcpyAsync(c->h_results.p, c->d_results.p, nwords * 8, cudaMemcpyDeviceToHost, c->stream));
+    hq_ctx::EvalKey key;
+    key.B = B; key.K = K; key.space = space; key.flags = flags; key.image_gen = c->image_gen; key.d_pal = c->d_pal.p; key.d_results = c->d_results.p;
+    key.h_pal = c->h_pal.p; key.h_results = c->h_results.p; key.d_pal_lab = c->d_pal_lab.p; key.d_pal_rgb = c->d_pal_rgb.p;
+    const bool graphable = c->use_graphs && !c->allreduce && !c->profiling;
+    if (graphable && c->graph_exec && key == c->graph_key) {
+        HQ_CUDA(c, cudaGraphLaunch(c->graph_exec, c->stream));  // the third and later identical calls: one launch for the whole step
+    } else {
+        // first call with this signature: plain launches (also configures the kernels); second: captured into a graph
+        const bool capture = graphable && key == c->seen_key;
+        c->seen_key = key;
+        if (capture) HQ_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        cudaError_t e = cudaMemcpyAsync(c->d_pal.p, c->h_pal.p, npal * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+        rc = e == cudaSuccess ? eval_device(c, c->d_pal.p, B, K, space, flags, c->d_results.p, nullptr, c->stream) : HQ_ERR_CUDA;
+        if (rc == HQ_OK && c->allreduce && c->allreduce(c->allreduce_user, c->d_results.p, nwords, c->stream) != 0)
+            rc = fail(c, HQ_ERR_CALLBACK, "all-reduce hook failed");
+        if (rc == HQ_OK) e = cudaMemcpyAsync(c->h_results.p, c->d_results.p, nwords * 8, cudaMemcpyDeviceToHost, c->stream);
+        if (capture) {
+            cudaGraph_t g = nullptr;
+            const cudaError_t ec = cudaStreamEndCapture(c->stream, &g);
+            if (rc == HQ_OK && e == cudaSuccess && ec == cudaSuccess && g) {
+                if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+                const cudaError_t ei = cudaGraphInstantiate(&c->graph_exec, g, 0);
+                cudaGraphDestroy(g);
+                if (ei != cudaSuccess) { c->graph_exec = nullptr; return fail(c, HQ_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ei)); }
+                c->graph_key = key;
+                HQ_CUDA(c, cudaGraphLaunch(c->graph_exec, c->stream));
+            } else {
+                if (g) cudaGraphDestroy(g);
+                if (rc != HQ_OK) return rc;
+                return fail(c, HQ_ERR_CUDA, "graph capture of the evaluation failed: %s", cudaGetErrorString(e != cudaSuccess ? e : ec));
+            }
+        } else {
+            if (rc != HQ_OK) return rc;
+            if (e != cudaSuccess) return fail(c, HQ_ERR_CUDA, "evaluation launch failed: %s", cudaGetErrorString(e));
+        }
+    }
     HQ_CUDA(c, wait_stream(c->stream));
     for (int b = 0; b < B; ++b) {
         const unsigned long long* w = c->h_results.p + (size_t)b * words;
