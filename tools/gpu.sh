@@ -1,0 +1,58 @@
+#!/bin/bash
+# tools/gpu.sh <task> [args] — the commands run on the B200 box (through `gpurun -- 'bash tools/gpu.sh <task>'`).
+# Outputs land in gpurun_out/ (scratch); what is worth keeping is condensed with tools/ncu_summary.py into profiles/.
+#   tests                 pytest -m gpu + smoke
+#   bench                 bench.py (both arms)
+#   launches              ncu launch list of the bench command (gpu__time_duration per launch)
+#   ncu <kernel-regex> [skip] [bench args...]   one `ncu --set full` capture of a kernel of bench.py, exported as raw + source CSV
+#   sweep                 tools/sweep.py (rgb_to_lab sizes, K sweep, S-CIELAB stage, full searches)
+#   multi N               NCCL parity test + bench at 1 and N GPUs   (gpurun --gpus N)
+#   micro                 FP32-pipe / issue-model microbenchmarks
+set -u
+mkdir -p gpurun_out
+task=${1:-tests}; shift || true
+case "$task" in
+tests)
+    timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -6 | tee gpurun_out/pytest_gpu.txt
+    timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 ;;
+bench)
+    nproc > gpurun_out/host.txt; lscpu | grep "Model name" >> gpurun_out/host.txt
+    timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+    timeout 900 python bench.py "$@" > gpurun_out/bench.json 2> gpurun_out/bench.err
+    tail -c 1500 gpurun_out/bench.json; echo; tail -3 gpurun_out/bench.err ;;
+launches)
+    BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+    $BENCH > gpurun_out/plain.log 2>&1 &&
+    timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/ncu_launches.log 2>&1
+    echo "launch list rc=$?" ;;
+ncu)
+    regex=${1:?kernel regex}; skip=${2:-0}; shift; shift || true
+    BENCH="python bench.py --steps 1 --warmup 3 --no-cpu-baseline $*"
+    $BENCH > gpurun_out/plain_ncu.log 2>&1 &&
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:$regex -s $skip -c 1 -f -o gpurun_out/prof $BENCH > gpurun_out/ncu.log 2>&1
+    echo "capture rc=$?"
+    ncu -i gpurun_out/prof.ncu-rep --page raw --csv > gpurun_out/prof_raw.csv 2>/dev/null
+    ncu -i gpurun_out/prof.ncu-rep --page source --csv > gpurun_out/prof_source.csv 2>/dev/null
+    ls -la gpurun_out/prof* ;;
+sweep)
+    timeout 1200 python tools/sweep.py "$@" > gpurun_out/sweep.json 2> gpurun_out/sweep.err; tail -2 gpurun_out/sweep.err; ls -la gpurun_out/sweep.json ;;
+multi)
+    N=${1:-2}
+    nvidia-smi -L | head -8
+    timeout 900 python -m pytest tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -4
+    for n in 1 $N; do
+        if [ "$n" -eq 1 ]; then timeout 600 python bench.py --gpus 1 --no-cpu-baseline > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+        else timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus "$n" > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err; fi
+        python - <<PY
+import json
+try:
+    d = json.loads([l for l in open('gpurun_out/bench_n$n.json') if l.startswith('{')][-1])
+    print('N=$n exhaustive', round(d['value'], 2), 'Gpixel/s', round(d['ms_per_step'], 3), 'ms/step, frac', round(d['roofline']['frac'], 3), '| pruned', round(d['pruned']['value'], 1), 'Gpixel/s | clocks', d['clocks'])
+except Exception as e:
+    print('N=$n parse failed', e)
+PY
+    done ;;
+micro)
+    for m in microbench microbench2 microbench3; do [ -x tools/$m ] && timeout 200 ./tools/$m > gpurun_out/$m.json 2> gpurun_out/$m.err; done; ls -la gpurun_out/microbench* ;;
+*) echo "unknown task $task"; exit 2 ;;
+esac
