@@ -57,12 +57,15 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 
 def build_microbench(force: bool = False) -> str:
-    src = os.path.join(REPO, "tools", "microbench.cu")
-    out = os.path.join(REPO, "tools", "microbench")
-    if force or _stale(out, [src]):
-        cmd = [_nvcc()] + ARCH + ["-O3", "-lineinfo", "-o", out, src]
-        print("[build]", " ".join(cmd), flush=True)
-        subprocess.run(cmd, check=True)
+    """tools/microbench{,2,3}: FP32-pipe and issue-model probes (binaries are git-ignored, they ship with the gpurun snapshot)"""
+    out = ""
+    for name in ("microbench", "microbench2", "microbench3"):
+        src = os.path.join(REPO, "tools", name + ".cu")
+        out = os.path.join(REPO, "tools", name)
+        if force or _stale(out, [src]):
+            cmd = [_nvcc()] + ARCH + ["-O3", "-lineinfo", "-o", out, src]
+            print("[build]", " ".join(cmd), flush=True)
+            subprocess.run(cmd, check=True)
     return out
 
 
