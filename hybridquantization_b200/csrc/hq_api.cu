@@ -114,7 +114,7 @@ struct hq_ctx {
     EvalKey graph_key, seen_key;
     cudaGraphExec_t graph_exec = nullptr;
     unsigned long long image_gen = 0;
-    bool use_graphs = true;
+    bool use_graphs = false;  // off by default: see hq_set_graphs
 
     hq_progress_fn progress = nullptr;
     void* progress_user = nullptr;
@@ -290,9 +290,9 @@ int hq_create(int device, hq_ctx** out) {
         delete c;
         return fail(nullptr, HQ_ERR_CUDA, "device %d: decode table kernel failed: %s (is the library built for this GPU?)", device, cudaGetErrorString(e));
     }
-    {   // HQ_NO_CUDA_GRAPHS=1: every evaluation issues its launches one by one (debugging aid)
-        const char* ng = std::getenv("HQ_NO_CUDA_GRAPHS");
-        c->use_graphs = !(ng && ng[0] == '1');
+    {   // HQ_CUDA_GRAPHS=1 turns hq_set_graphs on for every new context
+        const char* g = std::getenv("HQ_CUDA_GRAPHS");
+        c->use_graphs = g && g[0] == '1';
     }
     c->sm_count = prop.multiProcessorCount;
     cudaDeviceGetAttribute(&c->clock_khz, cudaDevAttrClockRate, device);
@@ -732,6 +732,13 @@ int hq_find_best_quantization(hq_ctx* c, int K, const hq_swasa_params* p, uint64
         if (c->err.empty()) c->err = ex.what();
         return HQ_ERR_CUDA;
     }
+    return HQ_OK;
+}
+
+int hq_set_graphs(hq_ctx* c, int enabled) {
+    if (!c) return HQ_ERR_INVALID;
+    c->use_graphs = enabled != 0;
+    if (!c->use_graphs && c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; c->graph_key = hq_ctx::EvalKey(); }
     return HQ_OK;
 }
 

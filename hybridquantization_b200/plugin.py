@@ -301,6 +301,10 @@ class ImageManipulation:
         """PRUNE_OFF | PRUNE_AUTO (default) | PRUNE_ON: whether the search scores populations with the exact pruned kernel"""
         _lib.check(self._ctx, self._lib.hq_set_pruning(self._ctx, mode))
 
+    def setGraphs(self, enabled: bool) -> None:
+        """CUDA-graph replay of repeated identical evalPalettes calls (off by default, see hq_set_graphs)"""
+        _lib.check(self._ctx, self._lib.hq_set_graphs(self._ctx, int(bool(enabled))))
+
     def pruningStats(self) -> dict:
         ch, ms = C.c_uint32(), C.c_double()
         _lib.check(self._ctx, self._lib.hq_pruning_stats(self._ctx, C.byref(ch), C.byref(ms)))

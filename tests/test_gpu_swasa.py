@@ -85,3 +85,24 @@ def test_progress_hook_every_ten_iterations(backend):
     backend.setProgress(None)
     assert [s[0] for s in seen] == [10, 20, 30] and all(s[1] == 35 for s in seen)
     assert seen[-1][2] >= err and all(a[2] >= b[2] for a, b in zip(seen, seen[1:]))   # best error never increases
+
+
+def test_cuda_graph_replay_gives_the_same_search(backend, oracle):
+    """hq_set_graphs: the captured launch set must reproduce the plain launches bit for bit, across image and argument changes"""
+    from hybridquantization_b200 import EVAL_PRUNE
+    backend.setGraphs(True)
+    try:
+        for (w, h, K, P, seed) in ((96, 80, 12, 3, 5), (300, 260, 40, 4, 6), (96, 80, 12, 3, 5)):
+            img = synth.synth_image(w, h, seed, True)
+            backend.setImage(img)
+            best, err, tr, its = backend.findBestQuantization(K, SWASA(population=P, imax=30, iTc=5, seed=seed), trace=True)
+            obest, oerr, otr = oracle.find_best_quantization(img, K, oracle.swasa_params(population=P, imax=30, iTc=5, seed=seed), trace=True)
+            assert its == 30 and err == oerr and np.array_equal(tr.view(np.uint64), otr.view(np.uint64))
+            assert np.array_equal(best.view(np.uint32), obest.view(np.uint32))
+            pal = synth.synth_palettes(P, K, seed=seed)
+            want = oracle.assign_reduce(img, pal)
+            for flags in (0, EVAL_PRUNE, 0, 0, EVAL_PRUNE, EVAL_PRUNE, EVAL_PRUNE):   # repeated signatures: plain, captured, replayed
+                got = backend.evalPalettes(pal, flags=flags)
+                assert np.array_equal(got["err_fx"], want["err_fx"]) and np.array_equal(got["counts"], want["counts"])
+    finally:
+        backend.setGraphs(False)
