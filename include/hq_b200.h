@@ -105,7 +105,8 @@ int hq_eval_palettes(hq_ctx* ctx, const float* palettes, int B, int K, int space
 int hq_result_words(int K, int flags);
 /* fully asynchronous variant on device memory: d_palettes [B][K][4] floats, d_results
  * [B][hq_result_words] words (zeroed by the call).  Runs on `stream` (cudaStream_t; NULL =
- * the context's stream), no host synchronisation, no all-reduce. */
+ * the context's stream), no host synchronisation, no all-reduce.  (With HQ_EVAL_PRUNE the first call after an image
+ * change builds the cell-sorted copy of the image and synchronises `stream` once to read the chunk count.) */
 int hq_eval_palettes_device(hq_ctx* ctx, const void* d_palettes, int B, int K, int space,
                             int flags, void* d_results, void* stream);
 
