@@ -20,6 +20,7 @@ COST_LAB, COST_SCIELAB = 0, 1
 EVAL_SUMS, EVAL_FORCE_DIRECT, EVAL_FORCE_CHUNKED, EVAL_FORCE_PREFILTER, EVAL_PRUNE = 1, 2, 4, 8, 16
 PRUNE_OFF, PRUNE_AUTO, PRUNE_ON = 0, 1, 2
 MAX_COLORS = 1024
+MAX_COLORS_PRUNED = 4096
 
 
 class HqError(RuntimeError):

@@ -82,11 +82,19 @@ struct hq_ctx {
 
     // exact pruning (hq_pruned.cu): cell-sorted copy of the own pixels, chunk table, boxes; built on first use per image
     int prune_mode = HQ_PRUNE_AUTO;
-    bool pruned_ready = false;
-    size_t sstride = 0;
-    unsigned nchunks = 0;
-    DevBuf<float> d_sorted, d_box;
-    DevBuf<unsigned> d_pr_scratch, d_chunk_start, d_chunk_len;
+    struct PrunedSet {   // one cell-sorted copy of (a range of) the resident image
+        bool ready = false;
+        int space = -1;
+        size_t sstride = 0;
+        unsigned nchunks = 0;
+        DevBuf<float> sorted, box;
+        DevBuf<unsigned> perm, chunk_start, chunk_len;
+        void release() { sorted.release(); box.release(); perm.release(); chunk_start.release(); chunk_len.release(); ready = false; }
+    };
+    PrunedSet pr_own;   // CIELAB features of the OWN pixels: the LAB cost model (error, counts, sums; no indices)
+    PrunedSet pr_all;   // features of EVERY local pixel (own + halo) in the space asked for, with their image positions:
+                        // index-producing evaluations (the S-CIELAB chain, hq_quantize)
+    DevBuf<unsigned> d_pr_scratch;
     DevBuf<unsigned long long> d_pr_stats;
     PinBuf<unsigned long long> h_pr_small;
 
@@ -182,7 +190,8 @@ int convert_image(hq_ctx* c, int width, int own_rows, int halo_top, int halo_bot
     c->own_lo = (size_t)halo_top * width; c->own_hi = (size_t)(halo_top + own_rows) * width;
     c->have_unit = false;
     c->sc_image_ready = false;
-    c->pruned_ready = false;
+    c->pr_own.ready = false;
+    c->pr_all.ready = false;
     ++c->image_gen;
     HQ_CUDA(c, c->d_lab.reserve(3 * c->stride > 0 ? 3 * c->stride : 1));
     if (c->profiling) HQ_CUDA(c, cudaEventRecord(c->ev2, st));
@@ -196,34 +205,56 @@ int check_eval_args(hq_ctx* c, int B, int K, int space) {
     if (!c) return HQ_ERR_INVALID;
     if (!c->have_image) return fail(c, HQ_ERR_NO_IMAGE, "no image: call hq_set_image_u8 first");
     if (B < 1 || K < 1) return fail(c, HQ_ERR_INVALID, "B and K must be >= 1 (got B=%d K=%d)", B, K);
-    if (K > HQ_MAX_COLORS) return fail(c, HQ_ERR_UNSUPPORTED, "K=%d exceeds HQ_MAX_COLORS=%d", K, HQ_MAX_COLORS);
+    if (K > HQ_MAX_COLORS_PRUNED) return fail(c, HQ_ERR_UNSUPPORTED, "K=%d exceeds HQ_MAX_COLORS_PRUNED=%d", K, HQ_MAX_COLORS_PRUNED);
     if (space != HQ_SPACE_LAB && space != HQ_SPACE_SRGB) return fail(c, HQ_ERR_INVALID, "unknown space %d", space);
     return HQ_OK;
 }
 
-// cell-sorted copy of the own pixels + chunk table + boxes for the pruned kernel (one host synchronisation, once per image)
-int ensure_pruned(hq_ctx* c, cudaStream_t st) {
-    if (c->pruned_ready) return HQ_OK;
-    const size_t n_own = c->own_hi - c->own_lo;
-    c->sstride = hq::plane_stride(n_own);
+// cell-sorted copy of pixels [lo, hi) of the feature planes of `space` + chunk table + boxes for the pruned kernel
+// (one host synchronisation, once per image and set)
+int ensure_pruned(hq_ctx* c, hq_ctx::PrunedSet& ps, int space, size_t lo, size_t hi, bool want_perm, cudaStream_t st) {
+    if (ps.ready && ps.space == space) return HQ_OK;
+    ps.ready = false;
+    const size_t n = hi - lo;
+    ps.sstride = hq::plane_stride(n);
     const size_t words = hq::pruned_scratch_words();
-    HQ_CUDA(c, c->d_sorted.reserve(3 * c->sstride > 0 ? 3 * c->sstride : 1));
+    HQ_CUDA(c, ps.sorted.reserve(3 * ps.sstride > 0 ? 3 * ps.sstride : 1));
+    if (want_perm) HQ_CUDA(c, ps.perm.reserve(n ? n : 1));
     HQ_CUDA(c, c->d_pr_scratch.reserve(words));
-    HQ_CUDA(c, c->h_pr_small.reserve(2));
-    HQ_CUDA(c, c->d_pr_stats.reserve(2));
+    if (!c->d_pr_stats.p) { HQ_CUDA(c, c->d_pr_stats.reserve(2)); }
     HQ_CUDA(c, cudaMemsetAsync(c->d_pr_stats.p, 0, 16, st));
-    HQ_CUDA(c, hq::launch_pruned_build_cells(c->d_lab.p, c->stride, c->own_lo, c->own_hi, c->d_pr_scratch.p, c->d_sorted.p, c->sstride, c->sm_count, st));
+    const float* feat = space == HQ_SPACE_SRGB ? c->d_unit.p : c->d_lab.p;
+    HQ_CUDA(c, hq::launch_pruned_build_cells(feat, c->stride, space, lo, hi, c->d_pr_scratch.p, ps.sorted.p, ps.sstride, want_perm ? ps.perm.p : nullptr,
+                                             c->sm_count, st));
     unsigned totals[2] = {0, 0};
     HQ_CUDA(c, cudaMemcpyAsync(totals, c->d_pr_scratch.p + words - 2, sizeof totals, cudaMemcpyDeviceToHost, st));
     HQ_CUDA(c, cudaStreamSynchronize(st));
-    if (totals[0] != n_own) return fail(c, HQ_ERR_CUDA, "pruning: cell sort covered %u of %zu pixels", totals[0], n_own);
-    c->nchunks = totals[1];
-    HQ_CUDA(c, c->d_chunk_start.reserve(c->nchunks ? c->nchunks : 1));
-    HQ_CUDA(c, c->d_chunk_len.reserve(c->nchunks ? c->nchunks : 1));
-    HQ_CUDA(c, c->d_box.reserve(c->nchunks ? 6 * (size_t)c->nchunks : 1));
-    HQ_CUDA(c, hq::launch_pruned_build_chunks(c->d_pr_scratch.p, c->d_sorted.p, c->sstride, c->nchunks, c->d_chunk_start.p, c->d_chunk_len.p, c->d_box.p, st));
-    c->pruned_ready = true;
+    if (totals[0] != n) return fail(c, HQ_ERR_CUDA, "pruning: cell sort covered %u of %zu pixels", totals[0], n);
+    ps.nchunks = totals[1];
+    HQ_CUDA(c, ps.chunk_start.reserve(ps.nchunks ? ps.nchunks : 1));
+    HQ_CUDA(c, ps.chunk_len.reserve(ps.nchunks ? ps.nchunks : 1));
+    HQ_CUDA(c, ps.box.reserve(ps.nchunks ? 6 * (size_t)ps.nchunks : 1));
+    HQ_CUDA(c, hq::launch_pruned_build_chunks(c->d_pr_scratch.p, ps.sorted.p, ps.sstride, ps.nchunks, ps.chunk_start.p, ps.chunk_len.p, ps.box.p, st));
+    ps.ready = true; ps.space = space;
     return HQ_OK;
+}
+
+// which evaluations go through the pruned kernel: asked for (HQ_EVAL_PRUNE) or forced by K > HQ_MAX_COLORS, and possible:
+// scoring (no index image) needs the features to BE CIELAB (the error is the CIELAB distance); index-producing
+// evaluations work in either space
+bool use_pruned(int K, int space, int flags, bool want_idx) {
+    const bool wanted = (flags & HQ_EVAL_PRUNE) != 0 || K > HQ_MAX_COLORS;
+    return wanted && (want_idx || space == HQ_SPACE_LAB);
+}
+int prepare_pruned(hq_ctx* c, int K, int space, int flags, bool want_idx, cudaStream_t st) {
+    if (!use_pruned(K, space, flags, want_idx)) {
+        if (K > HQ_MAX_COLORS)
+            return fail(c, HQ_ERR_UNSUPPORTED, "K=%d > HQ_MAX_COLORS=%d is only supported where the pruned kernel applies "
+                        "(LAB space, or index-producing calls)", K, HQ_MAX_COLORS);
+        return HQ_OK;
+    }
+    if (space == HQ_SPACE_SRGB) { int rc = ensure_unit(c, st); if (rc) return rc; }
+    return want_idx ? ensure_pruned(c, c->pr_all, space, 0, c->n, true, st) : ensure_pruned(c, c->pr_own, HQ_SPACE_LAB, c->own_lo, c->own_hi, false, st);
 }
 
 int eval_device(hq_ctx* c, const float* d_palettes, int B, int K, int space, int flags, unsigned long long* d_results,
@@ -242,14 +273,17 @@ int eval_device(hq_ctx* c, const float* d_palettes, int B, int K, int space, int
     a.results = d_results; a.idx_out = d_idx; a.sm_count = c->sm_count;
     a.own_lo = c->own_lo; a.own_hi = c->own_hi;
     a.variant = (flags & HQ_EVAL_FORCE_DIRECT) ? 1 : ((flags & HQ_EVAL_FORCE_CHUNKED) ? 2 : ((flags & HQ_EVAL_FORCE_PREFILTER) ? 3 : 0));
-    const bool prune = (flags & HQ_EVAL_PRUNE) != 0 && space == HQ_SPACE_LAB && d_idx == nullptr;
-    if (prune) { int rc = ensure_pruned(c, st); if (rc) return rc; }
+    const bool prune = use_pruned(K, space, flags, d_idx != nullptr);
+    { int rc = prepare_pruned(c, K, space, flags, d_idx != nullptr, st); if (rc) return rc; }
     if (c->profiling) HQ_CUDA(c, cudaEventRecord(c->ev0, st));
     if (prune) {
+        const hq_ctx::PrunedSet& ps = d_idx ? c->pr_all : c->pr_own;
         hq::PrunedArgs pa;
-        pa.sorted = c->d_sorted.p; pa.sstride = c->sstride; pa.chunk_start = c->d_chunk_start.p; pa.chunk_len = c->d_chunk_len.p;
-        pa.box = c->d_box.p; pa.nchunks = c->nchunks; pa.pal_lab = c->d_pal_lab.p; pa.B = B; pa.K = K; pa.want_sums = sums;
+        pa.sorted = ps.sorted.p; pa.sstride = ps.sstride; pa.chunk_start = ps.chunk_start.p; pa.chunk_len = ps.chunk_len.p;
+        pa.box = ps.box.p; pa.nchunks = ps.nchunks; pa.pal = (d_idx && space == HQ_SPACE_SRGB) ? c->d_pal_rgb.p : c->d_pal_lab.p;
+        pa.B = B; pa.K = K; pa.want_sums = sums && !d_idx;
         pa.results = d_results; pa.stats = c->profiling ? c->d_pr_stats.p : nullptr; pa.sm_count = c->sm_count;
+        if (d_idx) { pa.perm = ps.perm.p; pa.idx_out = d_idx; pa.istride = c->stride; pa.own_lo = c->own_lo; pa.own_hi = c->own_hi; }
         HQ_CUDA(c, hq::launch_pruned_assign(pa, st));
     } else {
         HQ_CUDA(c, hq::launch_assign_reduce(a, st));
@@ -315,7 +349,7 @@ void hq_destroy(hq_ctx* c) {
     c->d_out_rgb.release(); c->d_out_f32.release(); c->h_pal.release(); c->h_results.release();
     c->d_sc_filters.release(); c->d_sc_opp.release(); c->d_sc_tmp.release(); c->d_sc_lab.release(); c->d_sc_tab.release(); c->d_sc_err.release();
     c->d_sc_lab2.release(); c->d_sc_map.release(); c->d_sc_rgb2.release(); c->d_sc_map8.release();
-    c->d_sorted.release(); c->d_box.release(); c->d_pr_scratch.release(); c->d_chunk_start.release(); c->d_chunk_len.release();
+    c->pr_own.release(); c->pr_all.release(); c->d_pr_scratch.release();
     c->d_pr_stats.release(); c->h_pr_small.release();
     delete c;
 }
@@ -411,7 +445,7 @@ int hq_eval_palettes(hq_ctx* c, const float* palettes, int B, int K, int space, 
         HQ_CUDA(c, c->d_pal_lab.reserve((size_t)B * K8));
         HQ_CUDA(c, c->d_pal_rgb.reserve((size_t)B * K8));
         if (space == HQ_SPACE_SRGB) { rc = ensure_unit(c, c->stream); if (rc) return rc; }
-        if ((flags & HQ_EVAL_PRUNE) && space == HQ_SPACE_LAB) { rc = ensure_pruned(c, c->stream); if (rc) return rc; }
+        rc = prepare_pruned(c, K, space, flags, false, c->stream); if (rc) return rc;
     }
     hq_ctx::EvalKey key;
     key.B = B; key.K = K; key.space = space; key.flags = flags; key.image_gen = c->image_gen; key.d_pal = c->d_pal.p; key.d_results = c->d_results.p;
@@ -481,7 +515,7 @@ int hq_quantize(hq_ctx* c, const float* palette, int K, int space, uint8_t* out_
     HQ_CUDA(c, c->d_idx.reserve((c->stride ? c->stride : 1) * (idx16 ? 2 : 1)));
     std::memcpy(c->h_pal.p, palette, npal * sizeof(float));
     HQ_CUDA(c, cudaMemcpyAsync(c->d_pal.p, c->h_pal.p, npal * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    rc = eval_device(c, c->d_pal.p, 1, K, space, 0, c->d_results.p, c->d_idx.p, c->stream); if (rc) return rc;
+    rc = eval_device(c, c->d_pal.p, 1, K, space, K > HQ_MAX_COLORS ? HQ_EVAL_PRUNE : 0, c->d_results.p, c->d_idx.p, c->stream); if (rc) return rc;
     if (out_rgb) HQ_CUDA(c, c->d_out_rgb.reserve(n * 3 > 0 ? n * 3 : 1));
     if (out_f32) HQ_CUDA(c, c->d_out_f32.reserve(n * 4 > 0 ? n * 4 : 1));
     if (out_rgb || out_f32)
@@ -666,7 +700,9 @@ int hq_eval_palettes_scielab(hq_ctx* c, const float* palettes, int B, int K, int
     std::memcpy(c->h_pal.p, palettes, npal * sizeof(float));
     HQ_CUDA(c, cudaMemcpyAsync(c->d_pal.p, c->h_pal.p, npal * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     // 1. assignment (quantizeAndConvertToOpp's argmin, cl:178-193): indices + counts for every candidate
-    rc = eval_device(c, c->d_pal.p, B, K, space, 0, c->d_results.p, c->d_idx.p, c->stream); if (rc) return rc;
+    //    (exact pruned kernel where it pays: same indices and counts)
+    const bool prune_idx = K > HQ_MAX_COLORS || (c->prune_mode != HQ_PRUNE_OFF && K >= 32 && c->n >= 65536);
+    rc = eval_device(c, c->d_pal.p, B, K, space, prune_idx ? HQ_EVAL_PRUNE : 0, c->d_results.p, c->d_idx.p, c->stream); if (rc) return rc;
     // 2. the K opponent colours each quantised image is made of (cl:194-198)
     HQ_CUDA(c, hq::launch_sc_palette_opp(c->d_pal.p, B * K, c->d_sc_tab.p, c->stream));
     HQ_CUDA(c, cudaMemsetAsync(c->d_sc_err.p, 0, (size_t)B * 8, c->stream));
@@ -720,7 +756,7 @@ int hq_find_best_quantization(hq_ctx* c, int K, const hq_swasa_params* p, uint64
         {   // exact pruning of the population scoring (bit-identical costs, so the trajectory is unchanged)
             const bool allowed = p->space == HQ_SPACE_LAB && p->cost_model == HQ_COST_LAB;
             const bool pays = K >= 32 && c->own_hi - c->own_lo >= 65536;
-            backend.setEvalFlags(allowed && (c->prune_mode == HQ_PRUNE_ON || (c->prune_mode == HQ_PRUNE_AUTO && pays)) ? HQ_EVAL_PRUNE : 0);
+            backend.setEvalFlags(allowed && (K > HQ_MAX_COLORS || c->prune_mode == HQ_PRUNE_ON || (c->prune_mode == HQ_PRUNE_AUTO && pays)) ? HQ_EVAL_PRUNE : 0);
         }
         hq::JavaRandom random(p->seed);
         hq::SWASA swasa(p->population, p->imax, p->iTc, p->delta, p->conv_delay, p->conv_spread, p->t0, p->alpha, p->s0, p->beta, &random);
@@ -753,8 +789,8 @@ int hq_pruning_stats(hq_ctx* c, uint32_t* chunks, double* mean_survivors) {
     if (!c) return HQ_ERR_INVALID;
     if (!c->have_image) return fail(c, HQ_ERR_NO_IMAGE, "no image");
     int rc = bind_device(c); if (rc) return rc;
-    rc = ensure_pruned(c, c->stream); if (rc) return rc;
-    if (chunks) *chunks = c->nchunks;
+    rc = ensure_pruned(c, c->pr_own, HQ_SPACE_LAB, c->own_lo, c->own_hi, false, c->stream); if (rc) return rc;
+    if (chunks) *chunks = c->pr_own.nchunks;
     if (mean_survivors) {
         unsigned long long st[2] = {0, 0};
         HQ_CUDA(c, cudaMemcpyAsync(st, c->d_pr_stats.p, sizeof st, cudaMemcpyDeviceToHost, c->stream));

@@ -54,20 +54,26 @@ cudaError_t launch_assign_reduce(const AssignArgs& a, cudaStream_t stream);
 // the colours that can be nearest to some pixel of the chunk are swept.  Results are bit-identical to
 // launch_assign_reduce (LAB space, no index image).
 constexpr int kPrunedChunkPx = 2048;
+constexpr int kMaxColorsPruned = 4096;  // the pruned kernel's shared memory holds ~26 B (50 B with sums) per colour
 size_t pruned_scratch_words();  // unsigned words of scratch launch_pruned_build_cells needs (totals at [.. - 2]: pixels, chunks)
-cudaError_t launch_pruned_build_cells(const float* d_lab, size_t stride, size_t own_lo, size_t own_hi, unsigned* d_scratch, float* d_sorted,
-                                      size_t sstride, int sm_count, cudaStream_t st);
+// d_feat: [3][stride] feature planes (Lab for space 0, unit sRGB for space 1); pixels [lo, hi) are sorted into d_sorted
+// [3][sstride]; d_perm (optional) receives the image position of every sorted pixel
+cudaError_t launch_pruned_build_cells(const float* d_feat, size_t stride, int space, size_t lo, size_t hi, unsigned* d_scratch, float* d_sorted,
+                                      size_t sstride, unsigned* d_perm, int sm_count, cudaStream_t st);
 cudaError_t launch_pruned_build_chunks(const unsigned* d_scratch, const float* d_sorted, size_t sstride, unsigned nchunks, unsigned* d_chunk_start,
                                        unsigned* d_chunk_len, float* d_box, cudaStream_t st);
 struct PrunedArgs {
-    const float* sorted; size_t sstride;          // [3][sstride] Lab of the own pixels in cell order
+    const float* sorted; size_t sstride;          // [3][sstride] features of the pixels in cell order
     const unsigned* chunk_start; const unsigned* chunk_len; const float* box; unsigned nchunks;
-    const float4* pal_lab;                        // [B][K8]
+    const float4* pal;                            // [B][K8] palette in the same feature space
     int B, K;
     bool want_sums;
     unsigned long long* results;                  // [B][result_words], zeroed by the caller
     unsigned long long* stats;                    // optional [2]: survivors summed over (chunk, candidate), number of (chunk, candidate)
     int sm_count;
+    // index-producing mode: idx_out [B][istride] (u8 for K <= 256, else u16) written through perm; error word stays 0,
+    // counts cover the image positions [own_lo, own_hi) only
+    const unsigned* perm = nullptr; void* idx_out = nullptr; size_t istride = 0, own_lo = 0, own_hi = 0;
 };
 cudaError_t launch_pruned_assign(const PrunedArgs& a, cudaStream_t st);
 

@@ -33,23 +33,27 @@ constexpr int kSubBits = 2;                        // each cell is ordered by a 
 constexpr int kSub = 1 << (3 * kSubBits);          // 64 bins per cell
 constexpr int kBins = kCells * kSub;               // 2,097,152 counting-sort bins
 
-// Bin of a pixel: coarse CIELAB cell (L in [0,100] -> 32 slabs of 3.125, a and b in [-128,128) -> 32 slabs of 8) in the
-// high bits, the Morton code of its position inside the cell (2 bits per axis) in the low 6.  Only an ORDER: any
-// deterministic function works, exactness is irrelevant (the chunk boxes are exact).  Ordering the inside of a cell makes
-// the chunks of a crowded cell compact (and their composition deterministic) instead of random subsets of the cell.
-__device__ __forceinline__ unsigned bin_of(float L, float a, float b) {
-    const unsigned l = (unsigned)min(max(__float2int_rd(L * 1.28f), 0), 127);
-    const unsigned u = (unsigned)min(max(__float2int_rd((a + 128.0f) * 0.5f), 0), 127);
-    const unsigned v = (unsigned)min(max(__float2int_rd((b + 128.0f) * 0.5f), 0), 127);
+// Bin of a pixel: coarse cell of the feature space (7 bits per axis after the affine map q = (f + off) * scale, top 5 = the
+// cell) in the high bits, the Morton code of its position inside the cell (low 2 bits per axis) in the low 6.
+//   CIELAB: L in [0,100] -> scale 1.28; a, b in [-128,128) -> off 128, scale 0.5   (cells of 3.1 x 8 x 8)
+//   sRGB:   r, g, b in [0,1] -> scale 128                                         (cells of 1/32 per axis)
+// Only an ORDER: any deterministic function works, exactness is irrelevant (the chunk boxes are exact).  Ordering the
+// inside of a cell makes the chunks of a crowded cell compact (and their composition deterministic) instead of random
+// subsets of the cell.
+struct BinMap { float off[3], scale[3]; };
+__device__ __forceinline__ unsigned bin_of(float f0, float f1, float f2, const BinMap& m) {
+    const unsigned l = (unsigned)min(max(__float2int_rd((f0 + m.off[0]) * m.scale[0]), 0), 127);
+    const unsigned u = (unsigned)min(max(__float2int_rd((f1 + m.off[1]) * m.scale[1]), 0), 127);
+    const unsigned v = (unsigned)min(max(__float2int_rd((f2 + m.off[2]) * m.scale[2]), 0), 127);
     const unsigned cell = ((l >> 2) << 10) | ((u >> 2) << 5) | (v >> 2);
     const unsigned ls = l & 3u, us = u & 3u, vs = v & 3u;
     const unsigned sub = ((ls & 2u) << 4) | ((us & 2u) << 3) | ((vs & 2u) << 2) | ((ls & 1u) << 2) | ((us & 1u) << 1) | (vs & 1u);
     return (cell << 6) | sub;
 }
 
-__global__ void cell_hist_kernel(const float* __restrict__ lab, size_t stride, size_t lo, size_t hi, unsigned* __restrict__ hist) {
+__global__ void cell_hist_kernel(const float* __restrict__ feat, size_t stride, size_t lo, size_t hi, BinMap m, unsigned* __restrict__ hist) {
     for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x)
-        atomicAdd(&hist[bin_of(lab[i], lab[stride + i], lab[2 * stride + i])], 1u);
+        atomicAdd(&hist[bin_of(feat[i], feat[stride + i], feat[2 * stride + i], m)], 1u);
 }
 
 // one CTA of 1024 threads, 32 cells (2048 bins) per thread: exclusive scan of the bin populations (first sorted position of
@@ -87,13 +91,14 @@ __global__ void __launch_bounds__(1024) cell_scan_kernel(const unsigned* __restr
     if (t == 1023) { totals[0] = s_px[t]; totals[1] = s_ch[t]; }
 }
 
-__global__ void cell_scatter_kernel(const float* __restrict__ lab, size_t stride, size_t lo, size_t hi, const unsigned* __restrict__ bin_off,
-                                    unsigned* __restrict__ cursor, float* __restrict__ sorted, size_t sstride) {
+__global__ void cell_scatter_kernel(const float* __restrict__ feat, size_t stride, size_t lo, size_t hi, BinMap m, const unsigned* __restrict__ bin_off,
+                                    unsigned* __restrict__ cursor, float* __restrict__ sorted, size_t sstride, unsigned* __restrict__ perm) {
     for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
-        const float L = lab[i], a = lab[stride + i], b = lab[2 * stride + i];
-        const unsigned c = bin_of(L, a, b);
+        const float f0 = feat[i], f1 = feat[stride + i], f2 = feat[2 * stride + i];
+        const unsigned c = bin_of(f0, f1, f2, m);
         const size_t pos = (size_t)bin_off[c] + atomicAdd(&cursor[c], 1u);
-        sorted[pos] = L; sorted[sstride + pos] = a; sorted[2 * sstride + pos] = b;
+        sorted[pos] = f0; sorted[sstride + pos] = f1; sorted[2 * sstride + pos] = f2;
+        if (perm) perm[pos] = (unsigned)i;  // where the pixel sits in the image (index-producing evaluations)
     }
 }
 
@@ -141,10 +146,13 @@ __global__ void chunk_box_kernel(const float* __restrict__ sorted, size_t sstrid
 struct PrunedParams {
     const float* sorted; size_t sstride;
     const unsigned* chunk_start; const unsigned* chunk_len; const float* box; unsigned nchunks;
-    const float4* pal_lab;  // [B][K8]
+    const float4* pal;      // [B][K8] palette in the feature space of the sorted copy
     int B, K, K8, words, b_per_cta;
     unsigned long long* results;
     unsigned long long* stats;  // optional: [0] += survivors summed over (chunk, candidate), [1] += (chunk, candidate) pairs
+    // index-producing mode (IDXW != 0): the winner of sorted pixel i goes to idx_out[b * istride + perm[i]]; only pixels
+    // whose image position lies in [own_lo, own_hi) are counted (halo rows of a shard are assigned, not counted)
+    const unsigned* perm; void* idx_out; size_t istride, own_lo, own_hi;
 };
 
 // shared-memory carve-up: survivors live in per-warp SEGMENTS (segment g = colours [32g, 32g+32), filled from slot 32g
@@ -153,55 +161,57 @@ struct PrunedParams {
 extern __shared__ __align__(16) unsigned char pruned_smem_raw[];
 template <bool SUMS>
 struct PrunedSmem {  // typed views of the dynamic shared memory, recomputed where they are used so that they stay LDS/STS/ATOMS
-    float4* surv;               // [K32] Lab of the survivor in each slot
+    float4* surv;               // [K32] feature of the survivor in each slot
     unsigned long long* sum;    // [3*K32] per-slot Lab sums (SUMS)
     unsigned* cnt;              // [K32] per-slot pixel counts
-    unsigned short* list;       // [K32] colour index of each slot
+    float* dmin;                // [K32] lower bound dmin^2 of every colour against the box
     unsigned* segcnt;           // [K32/32] survivors per segment
+    unsigned short* list;       // [K32] colour index of each slot
     int K32;                    // K rounded up to whole segments
     __device__ __forceinline__ explicit PrunedSmem(int K) {
         K32 = (K + 31) & ~31;
         surv = reinterpret_cast<float4*>(pruned_smem_raw);
         sum = reinterpret_cast<unsigned long long*>(pruned_smem_raw + (size_t)K32 * 16);
         cnt = reinterpret_cast<unsigned*>(pruned_smem_raw + (size_t)K32 * 16 + (SUMS ? (size_t)K32 * 24 : 0));
-        list = reinterpret_cast<unsigned short*>(cnt + K32);
-        segcnt = reinterpret_cast<unsigned*>(list + K32);
+        dmin = reinterpret_cast<float*>(cnt + K32);
+        segcnt = reinterpret_cast<unsigned*>(dmin + K32);
+        list = reinterpret_cast<unsigned short*>(segcnt + K32 / 32);
     }
 };
+inline size_t pruned_smem_bytes(int K, bool sums) {
+    const size_t K32 = ((size_t)K + 31) & ~(size_t)31;
+    return K32 * (16 + 4 + 4 + 2) + K32 / 32 * 4 + (sums ? K32 * 24 : 0);
+}
 
 // One candidate on one chunk whose pixels sit in registers (NS slots of 256 pixels).  3 CTA barriers.
-template <int NS, bool SUMS>
+// IDXW: 0 = scoring (error, counts, optional sums), 1 / 2 = write u8 / u16 indices through perm and count own pixels only.
+template <int NS, bool SUMS, int IDXW>
 __device__ __forceinline__ void score_candidate(const PrunedParams& p, unsigned* s_U, long long* s_err, int b, int parity,
-                                                const float (&x0)[NS], const float (&x1)[NS], const float (&x2)[NS], unsigned len,
+                                                const float (&x0)[NS], const float (&x1)[NS], const float (&x2)[NS], size_t start, unsigned len,
                                                 const float (&lo)[3], const float (&hi)[3]) {
     const int K = p.K, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const PrunedSmem<SUMS> sm(K);
     const float INF = __int_as_float(0x7f800000);
-    constexpr int kRounds = kMaxColors / kThreads;  // colour k = tid + 256*r
     const int nseg = (K + 31) >> 5;
-    const float4* pal = p.pal_lab + (size_t)b * p.K8;
+    const float4* pal = p.pal + (size_t)b * p.K8;
     // ---- 1. bounds of every colour against the box; U = min over colours of dmax^2 (non-negative floats order like their bits)
-    float4 col[kRounds];
-    float dmin2[kRounds];
     float umin = INF;
-#pragma unroll
-    for (int r = 0; r < kRounds; ++r) {
-        const int k = tid + r * kThreads;
-        dmin2[r] = INF;
+    for (int k = tid; k < sm.K32; k += kThreads) {
+        float mn = INF;
         if (k < K) {
             const float4 c = __ldg(pal + k);
-            col[r] = c;
             const float pc[3] = {c.x, c.y, c.z};
-            float mn = 0.f, mx = 0.f;
+            float mx = 0.f;
+            mn = 0.f;
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 const float near = fmaxf(fmaxf(lo[a] - pc[a], pc[a] - hi[a]), 0.f);  // > 0 when the colour lies outside the slab
                 const float far = fmaxf(pc[a] - lo[a], hi[a] - pc[a]);
                 mn = fmaf(near, near, mn); mx = fmaf(far, far, mx);
             }
-            dmin2[r] = mn;
             umin = fminf(umin, mx);
         }
+        sm.dmin[k] = mn;  // read back by the same thread after barrier (1); nothing the previous candidate's flush still reads
     }
     const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(umin));
     if (lane == 0) atomicMin(&s_U[parity], wmin);
@@ -210,18 +220,14 @@ __device__ __forceinline__ void score_candidate(const PrunedParams& p, unsigned*
     const float U = __uint_as_float(s_U[parity]);
     const float thr = fmaf(U, 0x1p-18f, U) + 1e-30f;
     if (tid == 0) s_U[parity ^ 1] = 0x7f800000u;  // for the next candidate (its atomicMin comes after barriers 2 and 3)
-#pragma unroll
-    for (int r = 0; r < kRounds; ++r) {
-        if (r * kThreads >= K) break;
-        const bool keep = dmin2[r] <= thr;
+    for (int k = tid; k < sm.K32; k += kThreads) {  // k >> 5 is warp-uniform: each warp compacts its own 32-colour segment
+        const bool keep = sm.dmin[k] <= thr;        // false for the padding (INF)
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        const int seg = r * (kThreads / 32) + warp, slot = seg * 32 + __popc(bal & ((1u << lane) - 1u));
-        if (keep) { sm.surv[slot] = col[r]; sm.list[slot] = (unsigned short)(tid + r * kThreads); }  // keep implies k < K, so slot < K32
-        if (lane == 0 && seg * 32 < sm.K32) sm.segcnt[seg] = __popc(bal);
-        if (tid + r * kThreads < sm.K32) {
-            sm.cnt[tid + r * kThreads] = 0u;
-            if (SUMS) { sm.sum[3 * (tid + r * kThreads)] = 0ull; sm.sum[3 * (tid + r * kThreads) + 1] = 0ull; sm.sum[3 * (tid + r * kThreads) + 2] = 0ull; }
-        }
+        const int slot = (k & ~31) + __popc(bal & ((1u << lane) - 1u));
+        if (keep) { sm.surv[slot] = __ldg(pal + k); sm.list[slot] = (unsigned short)k; }
+        if (lane == 0) sm.segcnt[k >> 5] = __popc(bal);
+        sm.cnt[k] = 0u;
+        if (SUMS) { sm.sum[3 * k] = 0ull; sm.sum[3 * k + 1] = 0ull; sm.sum[3 * k + 2] = 0ull; }
     }
     __syncthreads();  // (2)
     // ---- 2. exact sweep over the survivors: strict '<', ascending colour index = lowest index wins
@@ -242,38 +248,48 @@ __device__ __forceinline__ void score_candidate(const PrunedParams& p, unsigned*
             }
         }
     }
-    // ---- 3. error, counts, sums per slot
+    // ---- 3. per-slot counts, and either error / sums (scoring) or the index image
     long long err_acc = 0;
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
-        if ((unsigned)(j * kThreads + tid) < len) {
-            err_acc += hq_to_fx(HQ_FSQRT(best[j]));
-            atomicAdd(&sm.cnt[bi[j]], 1u);
-            if (SUMS) {
-                atomicAdd(&sm.sum[3 * bi[j]], (unsigned long long)hq_to_fx(x0[j]));
-                atomicAdd(&sm.sum[3 * bi[j] + 1], (unsigned long long)hq_to_fx(x1[j]));
-                atomicAdd(&sm.sum[3 * bi[j] + 2], (unsigned long long)hq_to_fx(x2[j]));
+        const unsigned i = j * kThreads + tid;
+        if (i < len) {
+            if (IDXW == 0) {
+                err_acc += hq_to_fx(HQ_FSQRT(best[j]));
+                atomicAdd(&sm.cnt[bi[j]], 1u);
+                if (SUMS) {
+                    atomicAdd(&sm.sum[3 * bi[j]], (unsigned long long)hq_to_fx(x0[j]));
+                    atomicAdd(&sm.sum[3 * bi[j] + 1], (unsigned long long)hq_to_fx(x1[j]));
+                    atomicAdd(&sm.sum[3 * bi[j] + 2], (unsigned long long)hq_to_fx(x2[j]));
+                }
+            } else {
+                const size_t px = __ldg(p.perm + start + i);
+                const unsigned k = sm.list[bi[j]];
+                if (IDXW == 1) reinterpret_cast<uint8_t*>(p.idx_out)[(size_t)b * p.istride + px] = (uint8_t)k;
+                else reinterpret_cast<uint16_t*>(p.idx_out)[(size_t)b * p.istride + px] = (uint16_t)k;
+                if (px >= p.own_lo && px < p.own_hi) atomicAdd(&sm.cnt[bi[j]], 1u);
             }
         }
     }
+    if (IDXW == 0) {
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) err_acc += __shfl_down_sync(0xffffffffu, err_acc, off);
-    if (lane == 0) s_err[warp] = err_acc;
+        for (int off = 16; off > 0; off >>= 1) err_acc += __shfl_down_sync(0xffffffffu, err_acc, off);
+        if (lane == 0) s_err[warp] = err_acc;
+    }
     __syncthreads();  // (3) also orders the shared atomics before the flush; the next candidate's barrier (1) orders the flush
                       // before its writes to these arrays
     unsigned long long* out = p.results + (size_t)b * p.words;
     if (tid == 0) {
-        long long e = 0;
+        if (IDXW == 0) {
+            long long e = 0;
 #pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) e += s_err[w];
-        if (e != 0) atomicAdd(out, (unsigned long long)e);
+            for (int w = 0; w < kThreads / 32; ++w) e += s_err[w];
+            if (e != 0) atomicAdd(out, (unsigned long long)e);
+        }
         if (p.stats) { atomicAdd(p.stats, (unsigned long long)S); atomicAdd(p.stats + 1, 1ull); }
     }
-#pragma unroll
-    for (int r = 0; r < kRounds; ++r) {
-        if (r * kThreads >= K) break;
-        const int slot = tid + r * kThreads;
-        const unsigned c = (slot < sm.K32 && (unsigned)(slot & 31) < sm.segcnt[slot >> 5]) ? sm.cnt[slot] : 0u;
+    for (int slot = tid; slot < sm.K32; slot += kThreads) {
+        const unsigned c = ((unsigned)(slot & 31) < sm.segcnt[slot >> 5]) ? sm.cnt[slot] : 0u;
         if (c) {
             const int k = sm.list[slot];
             atomicAdd(out + 1 + k, (unsigned long long)c);
@@ -287,7 +303,7 @@ __device__ __forceinline__ void score_candidate(const PrunedParams& p, unsigned*
 }
 
 // all candidates of this CTA on one chunk of <= NS*256 pixels
-template <int NS, bool SUMS>
+template <int NS, bool SUMS, int IDXW>
 __device__ __forceinline__ void score_chunk(const PrunedParams& p, unsigned* s_U, long long* s_err, size_t start, unsigned len,
                                             const float (&lo)[3], const float (&hi)[3]) {
     const int tid = threadIdx.x;
@@ -301,10 +317,10 @@ __device__ __forceinline__ void score_chunk(const PrunedParams& p, unsigned* s_U
         x2[j] = ok ? __ldg(p.sorted + 2 * p.sstride + start + i) : 0.f;
     }
     const int b_begin = blockIdx.y * p.b_per_cta, b_end = min(p.B, b_begin + p.b_per_cta);
-    for (int b = b_begin; b < b_end; ++b) score_candidate<NS, SUMS>(p, s_U, s_err, b, (b - b_begin) & 1, x0, x1, x2, len, lo, hi);
+    for (int b = b_begin; b < b_end; ++b) score_candidate<NS, SUMS, IDXW>(p, s_U, s_err, b, (b - b_begin) & 1, x0, x1, x2, start, len, lo, hi);
 }
 
-template <bool SUMS>
+template <bool SUMS, int IDXW>
 __global__ void __launch_bounds__(kThreads, 2) pruned_assign_kernel(const PrunedParams p) {
     __shared__ unsigned s_U[2];
     __shared__ long long s_err[kThreads / 32];
@@ -317,10 +333,26 @@ __global__ void __launch_bounds__(kThreads, 2) pruned_assign_kernel(const Pruned
 #pragma unroll
     for (int a = 0; a < 3; ++a) { lo[a] = __ldg(p.box + 6 * (size_t)chunk + a); hi[a] = __ldg(p.box + 6 * (size_t)chunk + 3 + a); }
     // the sweep and epilogue are specialised on the number of 256-pixel slots the chunk occupies: a half-empty chunk costs half
-    if (len <= 2 * kThreads) score_chunk<2, SUMS>(p, s_U, s_err, start, len, lo, hi);
-    else if (len <= 4 * kThreads) score_chunk<4, SUMS>(p, s_U, s_err, start, len, lo, hi);
-    else if (len <= 6 * kThreads) score_chunk<6, SUMS>(p, s_U, s_err, start, len, lo, hi);
-    else score_chunk<kPxPerThread, SUMS>(p, s_U, s_err, start, len, lo, hi);
+    if (len <= 2 * kThreads) score_chunk<2, SUMS, IDXW>(p, s_U, s_err, start, len, lo, hi);
+    else if (len <= 4 * kThreads) score_chunk<4, SUMS, IDXW>(p, s_U, s_err, start, len, lo, hi);
+    else if (len <= 6 * kThreads) score_chunk<6, SUMS, IDXW>(p, s_U, s_err, start, len, lo, hi);
+    else score_chunk<kPxPerThread, SUMS, IDXW>(p, s_U, s_err, start, len, lo, hi);
+}
+
+template <bool SUMS, int IDXW>
+cudaError_t launch_pruned_t(const PrunedParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+    static thread_local size_t configured[64];  // per device: dynamic shared memory last set + 1 (0 = never)
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    size_t& have = configured[dev & 63];
+    if (have != smem + 1) {
+        e = cudaFuncSetAttribute(pruned_assign_kernel<SUMS, IDXW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        have = smem + 1;
+    }
+    pruned_assign_kernel<SUMS, IDXW><<<grid, kThreads, smem, st>>>(p);
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -328,16 +360,24 @@ __global__ void __launch_bounds__(kThreads, 2) pruned_assign_kernel(const Pruned
 // scratch layout (unsigned words): hist[kBins], bin_off[kBins], cursor[kBins], cell_cnt[kCells], chunk_base[kCells], totals[2]
 size_t pruned_scratch_words() { return (size_t)kBins * 3 + (size_t)kCells * 2 + 2; }
 
-cudaError_t launch_pruned_build_cells(const float* d_lab, size_t stride, size_t own_lo, size_t own_hi, unsigned* d_scratch, float* d_sorted,
-                                      size_t sstride, int sm_count, cudaStream_t st) {
+static BinMap bin_map(int space) {
+    BinMap m;
+    if (space == 1) { for (int a = 0; a < 3; ++a) { m.off[a] = 0.f; m.scale[a] = 128.f; } }
+    else { m.off[0] = 0.f; m.scale[0] = 1.28f; m.off[1] = m.off[2] = 128.f; m.scale[1] = m.scale[2] = 0.5f; }
+    return m;
+}
+
+cudaError_t launch_pruned_build_cells(const float* d_feat, size_t stride, int space, size_t lo, size_t hi, unsigned* d_scratch, float* d_sorted,
+                                      size_t sstride, unsigned* d_perm, int sm_count, cudaStream_t st) {
     unsigned *hist = d_scratch, *bin_off = d_scratch + kBins, *cursor = d_scratch + 2 * (size_t)kBins, *cell_cnt = d_scratch + 3 * (size_t)kBins,
              *chunk_base = cell_cnt + kCells, *totals = chunk_base + kCells;
-    if (own_hi - own_lo >= 0xffffffffull) return cudaErrorInvalidValue;  // 32-bit sorted positions
+    if (hi - lo >= 0xffffffffull || hi >= 0xffffffffull) return cudaErrorInvalidValue;  // 32-bit sorted positions / image positions
     cudaError_t e = cudaMemsetAsync(d_scratch, 0, pruned_scratch_words() * sizeof(unsigned), st);
     if (e != cudaSuccess) return e;
-    if (own_hi > own_lo) cell_hist_kernel<<<sm_count * 8, 256, 0, st>>>(d_lab, stride, own_lo, own_hi, hist);
+    const BinMap m = bin_map(space);
+    if (hi > lo) cell_hist_kernel<<<sm_count * 8, 256, 0, st>>>(d_feat, stride, lo, hi, m, hist);
     cell_scan_kernel<<<1, 1024, 0, st>>>(hist, bin_off, cell_cnt, chunk_base, totals);
-    if (own_hi > own_lo) cell_scatter_kernel<<<sm_count * 8, 256, 0, st>>>(d_lab, stride, own_lo, own_hi, bin_off, cursor, d_sorted, sstride);
+    if (hi > lo) cell_scatter_kernel<<<sm_count * 8, 256, 0, st>>>(d_feat, stride, lo, hi, m, bin_off, cursor, d_sorted, sstride, d_perm);
     return cudaGetLastError();
 }
 
@@ -350,12 +390,14 @@ cudaError_t launch_pruned_build_chunks(const unsigned* d_scratch, const float* d
 }
 
 cudaError_t launch_pruned_assign(const PrunedArgs& a, cudaStream_t st) {
-    if (a.B <= 0 || a.K <= 0 || a.K > kMaxColors) return cudaErrorInvalidValue;
+    if (a.B <= 0 || a.K <= 0 || a.K > kMaxColorsPruned) return cudaErrorInvalidValue;
     if (a.nchunks == 0) return cudaSuccess;
+    if (a.idx_out && (a.want_sums || !a.perm)) return cudaErrorInvalidValue;
     PrunedParams p;
     p.sorted = a.sorted; p.sstride = a.sstride; p.chunk_start = a.chunk_start; p.chunk_len = a.chunk_len; p.box = a.box; p.nchunks = a.nchunks;
-    p.pal_lab = a.pal_lab; p.B = a.B; p.K = a.K; p.K8 = padded_colors(a.K); p.words = result_words(a.K, a.want_sums);
+    p.pal = a.pal; p.B = a.B; p.K = a.K; p.K8 = padded_colors(a.K); p.words = result_words(a.K, a.want_sums);
     p.results = a.results; p.stats = a.stats;
+    p.perm = a.perm; p.idx_out = a.idx_out; p.istride = a.istride; p.own_lo = a.own_lo; p.own_hi = a.own_hi;
     // every CTA keeps its chunk in registers and loops over candidates; split the candidates over gridDim.y only as far
     // as needed to fill the machine (>= 8 CTAs per SM)
     int groups = 1;
@@ -363,23 +405,10 @@ cudaError_t launch_pruned_assign(const PrunedArgs& a, cudaStream_t st) {
     if (groups > a.B) groups = a.B;
     p.b_per_cta = (a.B + groups - 1) / groups;
     groups = (a.B + p.b_per_cta - 1) / p.b_per_cta;
-    const size_t K32 = ((size_t)a.K + 31) & ~(size_t)31;
-    const size_t smem = K32 * (16 + 4 + 2) + K32 / 32 * 4 + (a.want_sums ? K32 * 24 : 0);
+    const size_t smem = pruned_smem_bytes(a.K, a.want_sums);
     const dim3 grid(a.nchunks, (unsigned)groups);
-    static thread_local size_t configured[2][64];  // [sums][device]: dynamic shared memory last set (0 = never)
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    size_t& have = configured[a.want_sums ? 1 : 0][dev & 63];
-    if (have != smem + 1) {
-        e = a.want_sums ? cudaFuncSetAttribute(pruned_assign_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                        : cudaFuncSetAttribute(pruned_assign_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        have = smem + 1;
-    }
-    if (a.want_sums) pruned_assign_kernel<true><<<grid, kThreads, smem, st>>>(p);
-    else pruned_assign_kernel<false><<<grid, kThreads, smem, st>>>(p);
-    return cudaGetLastError();
+    if (a.idx_out) return a.K <= 256 ? launch_pruned_t<false, 1>(p, grid, smem, st) : launch_pruned_t<false, 2>(p, grid, smem, st);
+    return a.want_sums ? launch_pruned_t<true, 0>(p, grid, smem, st) : launch_pruned_t<false, 0>(p, grid, smem, st);
 }
 
 }  // namespace hq

@@ -56,7 +56,9 @@ enum {
                                   * kernel, ~10x less arithmetic at K=256): see hq_set_pruning */
 };
 
-#define HQ_MAX_COLORS 1024
+#define HQ_MAX_COLORS 1024          /* palette sizes the exhaustive kernel stages in shared memory */
+#define HQ_MAX_COLORS_PRUNED 4096   /* palette sizes of the pruned kernel: 1024 < K <= 4096 works wherever that kernel applies
+                                     * (LAB-space scoring, the S-CIELAB chain, hq_quantize) and is selected automatically */
 
 typedef struct hq_ctx hq_ctx;
 

@@ -193,8 +193,11 @@ def test_errors_are_loud(backend, hqlib):
     assert e.value.code == 3  # HQ_ERR_NO_IMAGE
     fresh.setImage(synth.synth_image(8, 8, 1))
     with pytest.raises(HqError) as e:
-        fresh.evalPalettes(synth.synth_palettes(1, 1025))
+        fresh.evalPalettes(synth.synth_palettes(1, 4097))           # beyond HQ_MAX_COLORS_PRUNED
     assert e.value.code == 4  # HQ_ERR_UNSUPPORTED
+    with pytest.raises(HqError) as e:
+        fresh.evalPalettes(synth.synth_palettes(1, 1025), SPACE_SRGB)  # > HQ_MAX_COLORS where the pruned kernel cannot score
+    assert e.value.code == 4
     with pytest.raises(ValueError):
         fresh.setImage(np.zeros((4, 4), np.uint8))  # fewer than 3 channels (HybridQuantization.java:68)
     fresh.close()

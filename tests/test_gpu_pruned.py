@@ -7,7 +7,7 @@ import pytest
 from hypothesis import HealthCheck, given, settings
 from hypothesis import strategies as st
 
-from hybridquantization_b200 import EVAL_PRUNE, PRUNE_OFF, PRUNE_ON, SPACE_LAB, SWASA, WHITEPOINT_D50, synth
+from hybridquantization_b200 import COST_SCIELAB, EVAL_PRUNE, PRUNE_AUTO, PRUNE_OFF, PRUNE_ON, SPACE_LAB, SPACE_SRGB, SWASA, WHITEPOINT_D50, synth
 
 pytestmark = pytest.mark.gpu
 THREADS = max(1, len(os.sched_getaffinity(0)))
@@ -94,3 +94,65 @@ def test_search_trajectory_unchanged_by_pruning(backend, oracle):
         assert its == 60 and err == oerr and np.array_equal(tr.view(np.uint64), otr.view(np.uint64))
         assert np.array_equal(best.view(np.uint32), obest.view(np.uint32))
     backend.setPruning(1)
+
+
+# ---------------------------------------------------------------- palettes beyond HQ_MAX_COLORS (the plugin allows up to 2^24 colours)
+@pytest.mark.parametrize("K", [1025, 1500, 4096])
+def test_large_palettes_are_scored_by_the_pruned_kernel(backend, oracle, K):
+    img = synth.synth_image(400, 300, K, K % 2 == 0)
+    pal = synth.synth_palettes(2, K, seed=K)
+    backend.setImage(img)
+    got = backend.evalPalettes(pal, SPACE_LAB, sums=True)           # no flag: K > 1024 selects the pruned kernel by itself
+    want = oracle.assign_reduce(img, pal, SPACE_LAB, threads=THREADS)
+    _same(got, want)
+
+
+@pytest.mark.parametrize("K,space", [(2000, SPACE_LAB), (1100, SPACE_SRGB), (300, SPACE_SRGB)])
+def test_quantize_with_large_palettes(backend, oracle, K, space):
+    img = synth.synth_image(320, 200, 3 + K, True)
+    pal = synth.synth_palettes(1, K, seed=K)[0]
+    backend.setImage(img)
+    got = backend.quantize(pal, space, want_f32=True)
+    want = oracle.quantize(img, pal, space, threads=THREADS)
+    assert np.array_equal(got["idx"], want["idx"]) and np.array_equal(got["rgb"].reshape(-1, 3), want["rgb"])
+    assert np.array_equal(got["f32"].view(np.uint32), want["f32"].view(np.uint32))
+
+
+# ---------------------------------------------------------------- index-producing pruning inside the S-CIELAB chain
+@pytest.mark.parametrize("w,h,K,space", [(640, 360, 256, SPACE_SRGB), (512, 300, 64, SPACE_LAB), (300, 260, 1500, SPACE_SRGB)])
+def test_scielab_chain_with_pruned_assignment(backend, oracle, w, h, K, space):
+    """hq_eval_palettes_scielab assigns with the pruned kernel (indices scattered through the sort permutation) when it
+    pays or K > 1024: errors and counts must equal the oracle's and the exhaustive assignment's"""
+    img = synth.synth_image(w, h, 11 + K, True)
+    pal = synth.synth_palettes(3, K, seed=K)
+    backend.setImage(img)
+    backend.scielabConfigure(72, 45.0)
+    f, a = oracle.scielab_filters(72, 45.0)
+    so = oracle.scielab_image(img, f, a, 0, THREADS)
+    want = oracle.scielab_eval(img, f, a, so, pal, space, 0, THREADS)
+    backend.setPruning(PRUNE_AUTO)
+    got = backend.evalPalettesScielab(pal, space)
+    assert np.array_equal(got["err_fx"], want["err_fx"]) and np.array_equal(got["counts"], want["counts"])
+    if K <= 1024:
+        backend.setPruning(PRUNE_OFF)
+        ex = backend.evalPalettesScielab(pal, space)
+        backend.setPruning(PRUNE_AUTO)
+        assert np.array_equal(ex["err_fx"], got["err_fx"]) and np.array_equal(ex["counts"], got["counts"])
+
+
+def test_scielab_pruned_assignment_on_row_shards(backend, oracle):
+    """halo pixels are assigned (their colours feed the filter) but not counted, exactly as in the exhaustive path"""
+    img = synth.synth_image(360, 300, 21, True)
+    pal = synth.synth_palettes(2, 128)
+    backend.scielabConfigure(72, 45.0)
+    f, a = oracle.scielab_filters(72, 45.0)
+    so = oracle.scielab_image(img, f, a, 0, THREADS)
+    want = oracle.scielab_eval(img, f, a, so, pal, SPACE_SRGB, 0, THREADS)
+    err = np.zeros(2, np.int64); cnt = np.zeros((2, 128), np.uint64)
+    for (r0, r1) in ((0, 150), (150, 300)):
+        top, bot = min(10, r0), min(10, 300 - r1)
+        backend.setImageSharded(img[r0 - top:r1 + bot], top, bot, r0, 300)
+        backend.scielabConfigure(72, 45.0)
+        r = backend.evalPalettesScielab(pal, SPACE_SRGB)
+        err += r["err_fx"]; cnt += r["counts"]
+    assert np.array_equal(err, want["err_fx"]) and np.array_equal(cnt, want["counts"])
