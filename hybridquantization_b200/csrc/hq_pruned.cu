@@ -56,19 +56,25 @@ __global__ void cell_hist_kernel(const float* __restrict__ feat, size_t stride, 
         atomicAdd(&hist[bin_of(feat[i], feat[stride + i], feat[2 * stride + i], m)], 1u);
 }
 
-// one CTA of 1024 threads, 32 cells (2048 bins) per thread: exclusive scan of the bin populations (first sorted position of
-// every bin) and of the chunks per cell
-__global__ void __launch_bounds__(1024) cell_scan_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ bin_off,
-                                                         unsigned* __restrict__ cell_cnt, unsigned* __restrict__ chunk_base,
-                                                         unsigned* __restrict__ totals) {
+// population of every cell = sum of its kSub bins (one thread per cell)
+__global__ void cell_count_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ cell_cnt) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= kCells) return;
+    unsigned h = 0;
+    for (int j = 0; j < kSub; ++j) h += hist[(size_t)c * kSub + j];
+    cell_cnt[c] = h;
+}
+
+// one CTA of 1024 threads, 32 cells per thread: exclusive scans of the cell populations (first sorted position of every
+// cell) and of the chunks per cell
+__global__ void __launch_bounds__(1024) cell_scan_kernel(const unsigned* __restrict__ cell_cnt, unsigned* __restrict__ cell_off,
+                                                         unsigned* __restrict__ chunk_base, unsigned* __restrict__ totals) {
     __shared__ unsigned s_px[1024], s_ch[1024];
     const int t = threadIdx.x;
     constexpr int per = kCells / 1024;  // 32 consecutive cells per thread
     unsigned px = 0, ch = 0;
     for (int i = 0; i < per; ++i) {
-        unsigned h = 0;
-        for (int j = 0; j < kSub; ++j) h += hist[(size_t)(t * per + i) * kSub + j];
-        cell_cnt[t * per + i] = h;
+        const unsigned h = cell_cnt[t * per + i];
         px += h; ch += (h + kPrunedChunkPx - 1) / kPrunedChunkPx;
     }
     s_px[t] = px; s_ch[t] = ch;
@@ -81,14 +87,22 @@ __global__ void __launch_bounds__(1024) cell_scan_kernel(const unsigned* __restr
     }
     unsigned opx = s_px[t] - px, och = s_ch[t] - ch;
     for (int i = 0; i < per; ++i) {
-        chunk_base[t * per + i] = och;
-        och += (cell_cnt[t * per + i] + kPrunedChunkPx - 1) / kPrunedChunkPx;
-        for (int j = 0; j < kSub; ++j) {
-            bin_off[(size_t)(t * per + i) * kSub + j] = opx;
-            opx += hist[(size_t)(t * per + i) * kSub + j];
-        }
+        const unsigned h = cell_cnt[t * per + i];
+        cell_off[t * per + i] = opx; chunk_base[t * per + i] = och;
+        opx += h; och += (h + kPrunedChunkPx - 1) / kPrunedChunkPx;
     }
     if (t == 1023) { totals[0] = s_px[t]; totals[1] = s_ch[t]; }
+}
+
+// first sorted position of every bin: the cell's offset plus the populations of the cell's earlier bins (one thread per cell)
+__global__ void bin_offset_kernel(const unsigned* __restrict__ hist, const unsigned* __restrict__ cell_off, unsigned* __restrict__ bin_off) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= kCells) return;
+    unsigned o = cell_off[c];
+    for (int j = 0; j < kSub; ++j) {
+        bin_off[(size_t)c * kSub + j] = o;
+        o += hist[(size_t)c * kSub + j];
+    }
 }
 
 __global__ void cell_scatter_kernel(const float* __restrict__ feat, size_t stride, size_t lo, size_t hi, BinMap m, const unsigned* __restrict__ bin_off,
@@ -102,11 +116,11 @@ __global__ void cell_scatter_kernel(const float* __restrict__ feat, size_t strid
     }
 }
 
-__global__ void chunk_table_kernel(const unsigned* __restrict__ cell_cnt, const unsigned* __restrict__ bin_off, const unsigned* __restrict__ chunk_base,
+__global__ void chunk_table_kernel(const unsigned* __restrict__ cell_cnt, const unsigned* __restrict__ cell_off, const unsigned* __restrict__ chunk_base,
                                    unsigned* __restrict__ chunk_start, unsigned* __restrict__ chunk_len) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= kCells) return;
-    const unsigned h = cell_cnt[c], first = bin_off[(size_t)c * kSub];
+    const unsigned h = cell_cnt[c], first = cell_off[c];
     for (unsigned j = 0, left = h; left > 0; ++j) {
         const unsigned len = left < (unsigned)kPrunedChunkPx ? left : (unsigned)kPrunedChunkPx;
         chunk_start[chunk_base[c] + j] = first + j * kPrunedChunkPx;
@@ -194,23 +208,27 @@ __device__ __forceinline__ void score_candidate(const PrunedParams& p, unsigned*
     const float INF = __int_as_float(0x7f800000);
     const int nseg = (K + 31) >> 5;
     const float4* pal = p.pal + (size_t)b * p.K8;
-    // ---- 1. bounds of every colour against the box; U = min over colours of dmax^2 (non-negative floats order like their bits)
+    // ---- 1. bounds of every colour against the box; U = min over colours of dmax^2 (non-negative floats order like their bits).
+    // Colour k = tid stays in registers (all there is for K <= 256); colours tid + 256, tid + 512, ... go through sm.dmin.
     float umin = INF;
-    for (int k = tid; k < sm.K32; k += kThreads) {
-        float mn = INF;
-        if (k < K) {
-            const float4 c = __ldg(pal + k);
-            const float pc[3] = {c.x, c.y, c.z};
-            float mx = 0.f;
-            mn = 0.f;
+    auto bounds = [&](const float4& c, float& mn) {
+        const float pc[3] = {c.x, c.y, c.z};
+        float mx = 0.f;
+        mn = 0.f;
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const float near = fmaxf(fmaxf(lo[a] - pc[a], pc[a] - hi[a]), 0.f);  // > 0 when the colour lies outside the slab
-                const float far = fmaxf(pc[a] - lo[a], hi[a] - pc[a]);
-                mn = fmaf(near, near, mn); mx = fmaf(far, far, mx);
-            }
-            umin = fminf(umin, mx);
+        for (int a = 0; a < 3; ++a) {
+            const float near = fmaxf(fmaxf(lo[a] - pc[a], pc[a] - hi[a]), 0.f);  // > 0 when the colour lies outside the slab
+            const float far = fmaxf(pc[a] - lo[a], hi[a] - pc[a]);
+            mn = fmaf(near, near, mn); mx = fmaf(far, far, mx);
         }
+        umin = fminf(umin, mx);
+    };
+    float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float mn0 = INF;
+    if (tid < K) { c0 = __ldg(pal + tid); bounds(c0, mn0); }
+    for (int k = tid + kThreads; k < sm.K32; k += kThreads) {
+        float mn = INF;
+        if (k < K) bounds(__ldg(pal + k), mn);
         sm.dmin[k] = mn;  // read back by the same thread after barrier (1); nothing the previous candidate's flush still reads
     }
     const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(umin));
@@ -221,10 +239,10 @@ __device__ __forceinline__ void score_candidate(const PrunedParams& p, unsigned*
     const float thr = fmaf(U, 0x1p-18f, U) + 1e-30f;
     if (tid == 0) s_U[parity ^ 1] = 0x7f800000u;  // for the next candidate (its atomicMin comes after barriers 2 and 3)
     for (int k = tid; k < sm.K32; k += kThreads) {  // k >> 5 is warp-uniform: each warp compacts its own 32-colour segment
-        const bool keep = sm.dmin[k] <= thr;        // false for the padding (INF)
+        const bool keep = (k == tid ? mn0 : sm.dmin[k]) <= thr;  // false for the padding (INF)
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         const int slot = (k & ~31) + __popc(bal & ((1u << lane) - 1u));
-        if (keep) { sm.surv[slot] = __ldg(pal + k); sm.list[slot] = (unsigned short)k; }
+        if (keep) { sm.surv[slot] = (k == tid) ? c0 : __ldg(pal + k); sm.list[slot] = (unsigned short)k; }
         if (lane == 0) sm.segcnt[k >> 5] = __popc(bal);
         sm.cnt[k] = 0u;
         if (SUMS) { sm.sum[3 * k] = 0ull; sm.sum[3 * k + 1] = 0ull; sm.sum[3 * k + 2] = 0ull; }
@@ -357,8 +375,9 @@ cudaError_t launch_pruned_t(const PrunedParams& p, dim3 grid, size_t smem, cudaS
 
 }  // namespace
 
-// scratch layout (unsigned words): hist[kBins], bin_off[kBins], cursor[kBins], cell_cnt[kCells], chunk_base[kCells], totals[2]
-size_t pruned_scratch_words() { return (size_t)kBins * 3 + (size_t)kCells * 2 + 2; }
+// scratch layout (unsigned words): hist[kBins], bin_off[kBins], cursor[kBins], cell_cnt[kCells], cell_off[kCells],
+// chunk_base[kCells], totals[2]
+size_t pruned_scratch_words() { return (size_t)kBins * 3 + (size_t)kCells * 3 + 2; }
 
 static BinMap bin_map(int space) {
     BinMap m;
@@ -370,21 +389,23 @@ static BinMap bin_map(int space) {
 cudaError_t launch_pruned_build_cells(const float* d_feat, size_t stride, int space, size_t lo, size_t hi, unsigned* d_scratch, float* d_sorted,
                                       size_t sstride, unsigned* d_perm, int sm_count, cudaStream_t st) {
     unsigned *hist = d_scratch, *bin_off = d_scratch + kBins, *cursor = d_scratch + 2 * (size_t)kBins, *cell_cnt = d_scratch + 3 * (size_t)kBins,
-             *chunk_base = cell_cnt + kCells, *totals = chunk_base + kCells;
+             *cell_off = cell_cnt + kCells, *chunk_base = cell_off + kCells, *totals = chunk_base + kCells;
     if (hi - lo >= 0xffffffffull || hi >= 0xffffffffull) return cudaErrorInvalidValue;  // 32-bit sorted positions / image positions
     cudaError_t e = cudaMemsetAsync(d_scratch, 0, pruned_scratch_words() * sizeof(unsigned), st);
     if (e != cudaSuccess) return e;
     const BinMap m = bin_map(space);
     if (hi > lo) cell_hist_kernel<<<sm_count * 8, 256, 0, st>>>(d_feat, stride, lo, hi, m, hist);
-    cell_scan_kernel<<<1, 1024, 0, st>>>(hist, bin_off, cell_cnt, chunk_base, totals);
+    cell_count_kernel<<<kCells / 256, 256, 0, st>>>(hist, cell_cnt);
+    cell_scan_kernel<<<1, 1024, 0, st>>>(cell_cnt, cell_off, chunk_base, totals);
+    bin_offset_kernel<<<kCells / 256, 256, 0, st>>>(hist, cell_off, bin_off);
     if (hi > lo) cell_scatter_kernel<<<sm_count * 8, 256, 0, st>>>(d_feat, stride, lo, hi, m, bin_off, cursor, d_sorted, sstride, d_perm);
     return cudaGetLastError();
 }
 
 cudaError_t launch_pruned_build_chunks(const unsigned* d_scratch, const float* d_sorted, size_t sstride, unsigned nchunks, unsigned* d_chunk_start,
                                        unsigned* d_chunk_len, float* d_box, cudaStream_t st) {
-    const unsigned *bin_off = d_scratch + kBins, *cell_cnt = d_scratch + 3 * (size_t)kBins, *chunk_base = cell_cnt + kCells;
-    chunk_table_kernel<<<kCells / 256, 256, 0, st>>>(cell_cnt, bin_off, chunk_base, d_chunk_start, d_chunk_len);
+    const unsigned *cell_cnt = d_scratch + 3 * (size_t)kBins, *cell_off = cell_cnt + kCells, *chunk_base = cell_off + kCells;
+    chunk_table_kernel<<<kCells / 256, 256, 0, st>>>(cell_cnt, cell_off, chunk_base, d_chunk_start, d_chunk_len);
     if (nchunks) chunk_box_kernel<<<(nchunks * 32 + 255) / 256, 256, 0, st>>>(d_sorted, sstride, d_chunk_start, d_chunk_len, nchunks, d_box);
     return cudaGetLastError();
 }
