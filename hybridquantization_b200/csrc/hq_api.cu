@@ -224,8 +224,9 @@ int ensure_pruned(hq_ctx* c, hq_ctx::PrunedSet& ps, int space, size_t lo, size_t
     if (!c->d_pr_stats.p) { HQ_CUDA(c, c->d_pr_stats.reserve(2)); }
     HQ_CUDA(c, cudaMemsetAsync(c->d_pr_stats.p, 0, 16, st));
     const float* feat = space == HQ_SPACE_SRGB ? c->d_unit.p : c->d_lab.p;
-    HQ_CUDA(c, hq::launch_pruned_build_cells(feat, c->stride, space, lo, hi, c->d_pr_scratch.p, ps.sorted.p, ps.sstride, want_perm ? ps.perm.p : nullptr,
-                                             c->sm_count, st));
+    const int cell_bits = hq::pruned_cell_bits(n, space);
+    HQ_CUDA(c, hq::launch_pruned_build_cells(feat, c->stride, space, cell_bits, lo, hi, c->d_pr_scratch.p, ps.sorted.p, ps.sstride,
+                                             want_perm ? ps.perm.p : nullptr, c->sm_count, st));
     unsigned totals[2] = {0, 0};
     HQ_CUDA(c, cudaMemcpyAsync(totals, c->d_pr_scratch.p + words - 2, sizeof totals, cudaMemcpyDeviceToHost, st));
     HQ_CUDA(c, cudaStreamSynchronize(st));
@@ -234,7 +235,7 @@ int ensure_pruned(hq_ctx* c, hq_ctx::PrunedSet& ps, int space, size_t lo, size_t
     HQ_CUDA(c, ps.chunk_start.reserve(ps.nchunks ? ps.nchunks : 1));
     HQ_CUDA(c, ps.chunk_len.reserve(ps.nchunks ? ps.nchunks : 1));
     HQ_CUDA(c, ps.box.reserve(ps.nchunks ? 6 * (size_t)ps.nchunks : 1));
-    HQ_CUDA(c, hq::launch_pruned_build_chunks(c->d_pr_scratch.p, ps.sorted.p, ps.sstride, ps.nchunks, ps.chunk_start.p, ps.chunk_len.p, ps.box.p, st));
+    HQ_CUDA(c, hq::launch_pruned_build_chunks(c->d_pr_scratch.p, cell_bits, ps.sorted.p, ps.sstride, ps.nchunks, ps.chunk_start.p, ps.chunk_len.p, ps.box.p, st));
     ps.ready = true; ps.space = space;
     return HQ_OK;
 }

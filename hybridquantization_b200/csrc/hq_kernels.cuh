@@ -58,10 +58,12 @@ constexpr int kMaxColorsPruned = 4096;  // the pruned kernel's shared memory hol
 size_t pruned_scratch_words();  // unsigned words of scratch launch_pruned_build_cells needs (totals at [.. - 2]: pixels, chunks)
 // d_feat: [3][stride] feature planes (Lab for space 0, unit sRGB for space 1); pixels [lo, hi) are sorted into d_sorted
 // [3][sstride]; d_perm (optional) receives the image position of every sorted pixel
-cudaError_t launch_pruned_build_cells(const float* d_feat, size_t stride, int space, size_t lo, size_t hi, unsigned* d_scratch, float* d_sorted,
-                                      size_t sstride, unsigned* d_perm, int sm_count, cudaStream_t st);
-cudaError_t launch_pruned_build_chunks(const unsigned* d_scratch, const float* d_sorted, size_t sstride, unsigned nchunks, unsigned* d_chunk_start,
-                                       unsigned* d_chunk_len, float* d_box, cudaStream_t st);
+// cell_bits (3..5, from pruned_cell_bits) = bits per axis of the coarse cells chunks never straddle
+int pruned_cell_bits(size_t n, int space);
+cudaError_t launch_pruned_build_cells(const float* d_feat, size_t stride, int space, int cell_bits, size_t lo, size_t hi, unsigned* d_scratch,
+                                      float* d_sorted, size_t sstride, unsigned* d_perm, int sm_count, cudaStream_t st);
+cudaError_t launch_pruned_build_chunks(const unsigned* d_scratch, int cell_bits, const float* d_sorted, size_t sstride, unsigned nchunks,
+                                       unsigned* d_chunk_start, unsigned* d_chunk_len, float* d_box, cudaStream_t st);
 struct PrunedArgs {
     const float* sorted; size_t sstride;          // [3][sstride] features of the pixels in cell order
     const unsigned* chunk_start; const unsigned* chunk_len; const float* box; unsigned nchunks;

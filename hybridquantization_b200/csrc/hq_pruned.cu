@@ -4,9 +4,10 @@
 // The exhaustive kernel (assign_reduce_kernel, hq_kernels.cu) evaluates all N*K pixel-colour pairs per
 // candidate, as quantizeAndConvertToOpp does (OptimizedConvolution.cl:178-193).  Every output of the
 // scoring step is a SUM over pixels (error, per-colour counts, Lab sums), so the pixels may be visited
-// in any order.  Once per image the own pixels are therefore counting-sorted by a coarse CIELAB cell
-// (5 bits per axis), and inside a cell by the Morton code of a 4x4x4 sub-grid, and cut into chunks of <= 2048
-// pixels that never straddle a cell; each chunk keeps its exact bounding box.  Per (chunk, candidate) a CTA then
+// in any order.  Once per image the pixels are therefore counting-sorted by a coarse cell of the feature space
+// (3 to 5 bits per axis, chosen from the image size), and inside a cell by the Morton code of the finer bits, and
+// cut into chunks of <= 2048 pixels that never straddle a cell; each chunk keeps its exact bounding box.  Per
+// (chunk, candidate) a CTA then
 //   1. bounds every colour against the box:  dmin_k <= |x - p_k| <= dmax_k  for every pixel x of the chunk,
 //   2. takes U = min_k dmax_k (some colour is within U of every pixel) and keeps the colours with
 //      dmin_k^2 <= U^2 * (1 + 2^-18): a discarded colour is strictly farther from every pixel of the chunk
@@ -17,8 +18,10 @@
 // Winner, distance, counts, sums and error are bit-identical to the exhaustive kernel
 // (tests/test_gpu_pruned.py); what changes is the amount of arithmetic: ~N*(S + c) instead of N*K.
 //
-// No index image is produced here (the pixel order is permuted): hq_quantize and the S-CIELAB chain keep
-// using the exhaustive kernel.
+// The index-producing mode (S-CIELAB chain, hq_quantize) sorts every local pixel in the assignment space, keeps
+// each pixel's image position and scatters the winner's index there; the scoring mode needs no index image.
+#include <cstdlib>
+
 #include "hq_kernels.cuh"
 #include "hq_math.h"
 
@@ -27,28 +30,28 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kPxPerThread = kPrunedChunkPx / kThreads;  // 8
-constexpr int kCellBits = 5;                       // coarse cell: chunks never straddle one
-constexpr int kCells = 1 << (3 * kCellBits);       // 32768
-constexpr int kSubBits = 2;                        // each cell is ordered by a 4 x 4 x 4 Morton sub-grid
-constexpr int kSub = 1 << (3 * kSubBits);          // 64 bins per cell
-constexpr int kBins = kCells * kSub;               // 2,097,152 counting-sort bins
+constexpr int kAxisBits = 7;                       // every feature axis is quantised to 7 bits for the ORDER of the sort
+constexpr int kMaxCellBits = 5;                    // of which the top cb (3..5) name the coarse cell: chunks never straddle one
+constexpr int kMaxCells = 1 << (3 * kMaxCellBits); // 32768
+constexpr int kBins = 1 << (3 * kAxisBits);        // 2,097,152 counting-sort bins = cells x Morton sub-grid of the cell
 
-// Bin of a pixel: coarse cell of the feature space (7 bits per axis after the affine map q = (f + off) * scale, top 5 = the
-// cell) in the high bits, the Morton code of its position inside the cell (low 2 bits per axis) in the low 6.
-//   CIELAB: L in [0,100] -> scale 1.28; a, b in [-128,128) -> off 128, scale 0.5   (cells of 3.1 x 8 x 8)
-//   sRGB:   r, g, b in [0,1] -> scale 128                                         (cells of 1/32 per axis)
+// Bin of a pixel: coarse cell of the feature space (top cb bits per axis after the affine map q = (f + off) * scale) in
+// the high bits, the Morton code of its position inside the cell (the remaining 7 - cb bits per axis) in the low bits.
+//   CIELAB: L in [0,100] -> scale 1.28; a, b in [-128,128) -> off 128, scale 0.5   (cb = 5: cells of 3.1 x 8 x 8)
+//   sRGB:   r, g, b in [0,1] -> scale 128                                         (cb = 5: cells of 1/32 per axis)
 // Only an ORDER: any deterministic function works, exactness is irrelevant (the chunk boxes are exact).  Ordering the
 // inside of a cell makes the chunks of a crowded cell compact (and their composition deterministic) instead of random
-// subsets of the cell.
-struct BinMap { float off[3], scale[3]; };
+// subsets of the cell.  cb is chosen per image so that a cell holds about a chunk's worth of pixels (pruned_cell_bits).
+struct BinMap { float off[3], scale[3]; int cb; };
 __device__ __forceinline__ unsigned bin_of(float f0, float f1, float f2, const BinMap& m) {
     const unsigned l = (unsigned)min(max(__float2int_rd((f0 + m.off[0]) * m.scale[0]), 0), 127);
     const unsigned u = (unsigned)min(max(__float2int_rd((f1 + m.off[1]) * m.scale[1]), 0), 127);
     const unsigned v = (unsigned)min(max(__float2int_rd((f2 + m.off[2]) * m.scale[2]), 0), 127);
-    const unsigned cell = ((l >> 2) << 10) | ((u >> 2) << 5) | (v >> 2);
-    const unsigned ls = l & 3u, us = u & 3u, vs = v & 3u;
-    const unsigned sub = ((ls & 2u) << 4) | ((us & 2u) << 3) | ((vs & 2u) << 2) | ((ls & 1u) << 2) | ((us & 1u) << 1) | (vs & 1u);
-    return (cell << 6) | sub;
+    const int sb = kAxisBits - m.cb;
+    const unsigned cell = (((l >> sb) << m.cb | (u >> sb)) << m.cb) | (v >> sb);
+    unsigned sub = 0;
+    for (int i = sb - 1; i >= 0; --i) sub = (sub << 3) | (((l >> i) & 1u) << 2) | (((u >> i) & 1u) << 1) | ((v >> i) & 1u);
+    return (cell << (3 * sb)) | sub;
 }
 
 __global__ void cell_hist_kernel(const float* __restrict__ feat, size_t stride, size_t lo, size_t hi, BinMap m, unsigned* __restrict__ hist) {
@@ -56,25 +59,26 @@ __global__ void cell_hist_kernel(const float* __restrict__ feat, size_t stride, 
         atomicAdd(&hist[bin_of(feat[i], feat[stride + i], feat[2 * stride + i], m)], 1u);
 }
 
-// population of every cell = sum of its kSub bins (one thread per cell)
-__global__ void cell_count_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ cell_cnt) {
+// population of every cell = sum of its nsub bins (one thread per cell)
+__global__ void cell_count_kernel(const unsigned* __restrict__ hist, int ncells, int nsub, unsigned* __restrict__ cell_cnt) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= kCells) return;
+    if (c >= ncells) return;
     unsigned h = 0;
-    for (int j = 0; j < kSub; ++j) h += hist[(size_t)c * kSub + j];
+    for (int j = 0; j < nsub; ++j) h += hist[(size_t)c * nsub + j];
     cell_cnt[c] = h;
 }
 
-// one CTA of 1024 threads, 32 cells per thread: exclusive scans of the cell populations (first sorted position of every
-// cell) and of the chunks per cell
-__global__ void __launch_bounds__(1024) cell_scan_kernel(const unsigned* __restrict__ cell_cnt, unsigned* __restrict__ cell_off,
+// one CTA of 1024 threads, `per` consecutive cells per thread: exclusive scans of the cell populations (first sorted position
+// of every cell) and of the chunks per cell
+__global__ void __launch_bounds__(1024) cell_scan_kernel(const unsigned* __restrict__ cell_cnt, int ncells, unsigned* __restrict__ cell_off,
                                                          unsigned* __restrict__ chunk_base, unsigned* __restrict__ totals) {
     __shared__ unsigned s_px[1024], s_ch[1024];
     const int t = threadIdx.x;
-    constexpr int per = kCells / 1024;  // 32 consecutive cells per thread
+    const int per = (ncells + 1023) / 1024;
     unsigned px = 0, ch = 0;
     for (int i = 0; i < per; ++i) {
-        const unsigned h = cell_cnt[t * per + i];
+        const int c = t * per + i;
+        const unsigned h = c < ncells ? cell_cnt[c] : 0u;
         px += h; ch += (h + kPrunedChunkPx - 1) / kPrunedChunkPx;
     }
     s_px[t] = px; s_ch[t] = ch;
@@ -87,21 +91,24 @@ __global__ void __launch_bounds__(1024) cell_scan_kernel(const unsigned* __restr
     }
     unsigned opx = s_px[t] - px, och = s_ch[t] - ch;
     for (int i = 0; i < per; ++i) {
-        const unsigned h = cell_cnt[t * per + i];
-        cell_off[t * per + i] = opx; chunk_base[t * per + i] = och;
+        const int c = t * per + i;
+        if (c >= ncells) break;
+        const unsigned h = cell_cnt[c];
+        cell_off[c] = opx; chunk_base[c] = och;
         opx += h; och += (h + kPrunedChunkPx - 1) / kPrunedChunkPx;
     }
     if (t == 1023) { totals[0] = s_px[t]; totals[1] = s_ch[t]; }
 }
 
 // first sorted position of every bin: the cell's offset plus the populations of the cell's earlier bins (one thread per cell)
-__global__ void bin_offset_kernel(const unsigned* __restrict__ hist, const unsigned* __restrict__ cell_off, unsigned* __restrict__ bin_off) {
+__global__ void bin_offset_kernel(const unsigned* __restrict__ hist, const unsigned* __restrict__ cell_off, int ncells, int nsub,
+                                  unsigned* __restrict__ bin_off) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= kCells) return;
+    if (c >= ncells) return;
     unsigned o = cell_off[c];
-    for (int j = 0; j < kSub; ++j) {
-        bin_off[(size_t)c * kSub + j] = o;
-        o += hist[(size_t)c * kSub + j];
+    for (int j = 0; j < nsub; ++j) {
+        bin_off[(size_t)c * nsub + j] = o;
+        o += hist[(size_t)c * nsub + j];
     }
 }
 
@@ -117,9 +124,9 @@ __global__ void cell_scatter_kernel(const float* __restrict__ feat, size_t strid
 }
 
 __global__ void chunk_table_kernel(const unsigned* __restrict__ cell_cnt, const unsigned* __restrict__ cell_off, const unsigned* __restrict__ chunk_base,
-                                   unsigned* __restrict__ chunk_start, unsigned* __restrict__ chunk_len) {
+                                   int ncells, unsigned* __restrict__ chunk_start, unsigned* __restrict__ chunk_len) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= kCells) return;
+    if (c >= ncells) return;
     const unsigned h = cell_cnt[c], first = cell_off[c];
     for (unsigned j = 0, left = h; left > 0; ++j) {
         const unsigned len = left < (unsigned)kPrunedChunkPx ? left : (unsigned)kPrunedChunkPx;
@@ -375,37 +382,53 @@ cudaError_t launch_pruned_t(const PrunedParams& p, dim3 grid, size_t smem, cudaS
 
 }  // namespace
 
-// scratch layout (unsigned words): hist[kBins], bin_off[kBins], cursor[kBins], cell_cnt[kCells], cell_off[kCells],
-// chunk_base[kCells], totals[2]
-size_t pruned_scratch_words() { return (size_t)kBins * 3 + (size_t)kCells * 3 + 2; }
+// scratch layout (unsigned words): hist[kBins], bin_off[kBins], cursor[kBins], cell_cnt[kMaxCells], cell_off[kMaxCells],
+// chunk_base[kMaxCells], totals[2]
+size_t pruned_scratch_words() { return (size_t)kBins * 3 + (size_t)kMaxCells * 3 + 2; }
 
-static BinMap bin_map(int space) {
+// Cell size for an image of n pixels: the finest of 5 / 4 / 3 bits per axis at which a non-empty cell still holds about a
+// chunk's worth of pixels.  `occupancy` = expected fraction of non-empty cells for a maximally spread image: the sRGB gamut
+// fills ~1/4 of the CIELAB bounding box, the sRGB cube is full.  (Too fine a grid leaves most chunks nearly empty — 63 pixels
+// per chunk for a 1080p noise image in sRGB space at 5 bits — and the per-chunk work then dominates.)
+int pruned_cell_bits(size_t n, int space) {
+    if (const char* e = std::getenv("HQ_PRUNE_CELL_BITS")) { const int v = std::atoi(e); if (v >= 3 && v <= kMaxCellBits) return v; }
+    const double occupancy = space == 1 ? 1.0 : 0.25;
+    int cb = kMaxCellBits;
+    while (cb > 3 && (double)n < 0.45 * kPrunedChunkPx * occupancy * (double)(1 << (3 * cb))) --cb;
+    return cb;
+}
+
+static BinMap bin_map(int space, int cb) {
     BinMap m;
     if (space == 1) { for (int a = 0; a < 3; ++a) { m.off[a] = 0.f; m.scale[a] = 128.f; } }
     else { m.off[0] = 0.f; m.scale[0] = 1.28f; m.off[1] = m.off[2] = 128.f; m.scale[1] = m.scale[2] = 0.5f; }
+    m.cb = cb;
     return m;
 }
 
-cudaError_t launch_pruned_build_cells(const float* d_feat, size_t stride, int space, size_t lo, size_t hi, unsigned* d_scratch, float* d_sorted,
-                                      size_t sstride, unsigned* d_perm, int sm_count, cudaStream_t st) {
+cudaError_t launch_pruned_build_cells(const float* d_feat, size_t stride, int space, int cell_bits, size_t lo, size_t hi, unsigned* d_scratch,
+                                      float* d_sorted, size_t sstride, unsigned* d_perm, int sm_count, cudaStream_t st) {
+    if (cell_bits < 3 || cell_bits > kMaxCellBits) return cudaErrorInvalidValue;
     unsigned *hist = d_scratch, *bin_off = d_scratch + kBins, *cursor = d_scratch + 2 * (size_t)kBins, *cell_cnt = d_scratch + 3 * (size_t)kBins,
-             *cell_off = cell_cnt + kCells, *chunk_base = cell_off + kCells, *totals = chunk_base + kCells;
+             *cell_off = cell_cnt + kMaxCells, *chunk_base = cell_off + kMaxCells, *totals = chunk_base + kMaxCells;
     if (hi - lo >= 0xffffffffull || hi >= 0xffffffffull) return cudaErrorInvalidValue;  // 32-bit sorted positions / image positions
     cudaError_t e = cudaMemsetAsync(d_scratch, 0, pruned_scratch_words() * sizeof(unsigned), st);
     if (e != cudaSuccess) return e;
-    const BinMap m = bin_map(space);
+    const BinMap m = bin_map(space, cell_bits);
+    const int ncells = 1 << (3 * cell_bits), nsub = kBins / ncells;
     if (hi > lo) cell_hist_kernel<<<sm_count * 8, 256, 0, st>>>(d_feat, stride, lo, hi, m, hist);
-    cell_count_kernel<<<kCells / 256, 256, 0, st>>>(hist, cell_cnt);
-    cell_scan_kernel<<<1, 1024, 0, st>>>(cell_cnt, cell_off, chunk_base, totals);
-    bin_offset_kernel<<<kCells / 256, 256, 0, st>>>(hist, cell_off, bin_off);
+    cell_count_kernel<<<(ncells + 255) / 256, 256, 0, st>>>(hist, ncells, nsub, cell_cnt);
+    cell_scan_kernel<<<1, 1024, 0, st>>>(cell_cnt, ncells, cell_off, chunk_base, totals);
+    bin_offset_kernel<<<(ncells + 255) / 256, 256, 0, st>>>(hist, cell_off, ncells, nsub, bin_off);
     if (hi > lo) cell_scatter_kernel<<<sm_count * 8, 256, 0, st>>>(d_feat, stride, lo, hi, m, bin_off, cursor, d_sorted, sstride, d_perm);
     return cudaGetLastError();
 }
 
-cudaError_t launch_pruned_build_chunks(const unsigned* d_scratch, const float* d_sorted, size_t sstride, unsigned nchunks, unsigned* d_chunk_start,
-                                       unsigned* d_chunk_len, float* d_box, cudaStream_t st) {
-    const unsigned *cell_cnt = d_scratch + 3 * (size_t)kBins, *cell_off = cell_cnt + kCells, *chunk_base = cell_off + kCells;
-    chunk_table_kernel<<<kCells / 256, 256, 0, st>>>(cell_cnt, cell_off, chunk_base, d_chunk_start, d_chunk_len);
+cudaError_t launch_pruned_build_chunks(const unsigned* d_scratch, int cell_bits, const float* d_sorted, size_t sstride, unsigned nchunks,
+                                       unsigned* d_chunk_start, unsigned* d_chunk_len, float* d_box, cudaStream_t st) {
+    const unsigned *cell_cnt = d_scratch + 3 * (size_t)kBins, *cell_off = cell_cnt + kMaxCells, *chunk_base = cell_off + kMaxCells;
+    const int ncells = 1 << (3 * cell_bits);
+    chunk_table_kernel<<<(ncells + 255) / 256, 256, 0, st>>>(cell_cnt, cell_off, chunk_base, ncells, d_chunk_start, d_chunk_len);
     if (nchunks) chunk_box_kernel<<<(nchunks * 32 + 255) / 256, 256, 0, st>>>(d_sorted, sstride, d_chunk_start, d_chunk_len, nchunks, d_box);
     return cudaGetLastError();
 }
