@@ -516,7 +516,8 @@ int hq_quantize(hq_ctx* c, const float* palette, int K, int space, uint8_t* out_
     HQ_CUDA(c, c->d_idx.reserve((c->stride ? c->stride : 1) * (idx16 ? 2 : 1)));
     std::memcpy(c->h_pal.p, palette, npal * sizeof(float));
     HQ_CUDA(c, cudaMemcpyAsync(c->d_pal.p, c->h_pal.p, npal * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    rc = eval_device(c, c->d_pal.p, 1, K, space, K > HQ_MAX_COLORS ? HQ_EVAL_PRUNE : 0, c->d_results.p, c->d_idx.p, c->stream); if (rc) return rc;
+    rc = eval_device(c, c->d_pal.p, 1, K, space, (K > HQ_MAX_COLORS || c->prune_mode == HQ_PRUNE_ON) ? HQ_EVAL_PRUNE : 0, c->d_results.p, c->d_idx.p,
+                     c->stream); if (rc) return rc;
     if (out_rgb) HQ_CUDA(c, c->d_out_rgb.reserve(n * 3 > 0 ? n * 3 : 1));
     if (out_f32) HQ_CUDA(c, c->d_out_f32.reserve(n * 4 > 0 ? n * 4 : 1));
     if (out_rgb || out_f32)
@@ -702,7 +703,7 @@ int hq_eval_palettes_scielab(hq_ctx* c, const float* palettes, int B, int K, int
     HQ_CUDA(c, cudaMemcpyAsync(c->d_pal.p, c->h_pal.p, npal * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     // 1. assignment (quantizeAndConvertToOpp's argmin, cl:178-193): indices + counts for every candidate
     //    (exact pruned kernel where it pays: same indices and counts)
-    const bool prune_idx = K > HQ_MAX_COLORS || (c->prune_mode != HQ_PRUNE_OFF && K >= 32 && c->n >= 65536);
+    const bool prune_idx = K > HQ_MAX_COLORS || c->prune_mode == HQ_PRUNE_ON || (c->prune_mode == HQ_PRUNE_AUTO && K >= 32 && c->n >= 65536);
     rc = eval_device(c, c->d_pal.p, B, K, space, prune_idx ? HQ_EVAL_PRUNE : 0, c->d_results.p, c->d_idx.p, c->stream); if (rc) return rc;
     // 2. the K opponent colours each quantised image is made of (cl:194-198)
     HQ_CUDA(c, hq::launch_sc_palette_opp(c->d_pal.p, B * K, c->d_sc_tab.p, c->stream));

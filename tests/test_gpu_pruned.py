@@ -156,3 +156,30 @@ def test_scielab_pruned_assignment_on_row_shards(backend, oracle):
         r = backend.evalPalettesScielab(pal, SPACE_SRGB)
         err += r["err_fx"]; cnt += r["counts"]
     assert np.array_equal(err, want["err_fx"]) and np.array_equal(cnt, want["counts"])
+
+
+@settings(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture], derandomize=True)
+@given(w=st.integers(10, 200), h=st.integers(10, 60), K=st.integers(1, 300), space=st.integers(0, 1), smooth=st.booleans(),
+       dup=st.booleans(), seed=st.integers(0, 2 ** 31))
+def test_index_producing_mode_random_configurations(backend, oracle, w, h, K, space, smooth, dup, seed):
+    """HQ_PRUNE_ON forces the index-producing pruned kernel in hq_quantize and the S-CIELAB chain at any size: indices,
+    counts and S-CIELAB errors against the oracle"""
+    img = synth.synth_image(w, h, seed, smooth)
+    pal = synth.synth_palettes(2, K, seed=seed % 100000)
+    if dup and K > 1:
+        rng = np.random.default_rng(seed)
+        pal[:, rng.integers(0, K, K // 2 + 1)] = pal[:, rng.integers(0, K, K // 2 + 1)]
+    backend.setPruning(PRUNE_ON)
+    try:
+        backend.setImage(img)
+        q = backend.quantize(pal[0], space)
+        want = oracle.quantize(img, pal[0], space, threads=THREADS)
+        assert np.array_equal(q["idx"], want["idx"]) and np.array_equal(q["rgb"].reshape(-1, 3), want["rgb"])
+        backend.scielabConfigure(72, 45.0)
+        f, a = oracle.scielab_filters(72, 45.0)
+        so = oracle.scielab_image(img, f, a, 0, THREADS)
+        ev = oracle.scielab_eval(img, f, a, so, pal, space, 0, THREADS)
+        got = backend.evalPalettesScielab(pal, space)
+        assert np.array_equal(got["err_fx"], ev["err_fx"]) and np.array_equal(got["counts"], ev["counts"])
+    finally:
+        backend.setPruning(PRUNE_AUTO)
