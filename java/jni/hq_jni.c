@@ -1,6 +1,6 @@
 /* hq_jni.c — thin JNI shim between plugins.dbrasseur.hybridquantization.CudaImageManipulation and
  * the C ABI (include/hq_b200.h).  Compile-guarded: this image has no JDK (no jni.h), so the file
- * is NOT built or tested here.  With a JDK:
+ * is NOT built or run here; tests/test_abi.py type-checks it against a stub of jni.h (tests/stubs/jni.h).  With a JDK:
  *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -I../../include \
  *       -o libhq_jni.so hq_jni.c -L../../hybridquantization_b200 -lhq_b200
  */
@@ -12,6 +12,7 @@
 #ifdef HQ_HAVE_JNI
 #include <jni.h>
 #include <stdint.h>
+#include <stdio.h>
 #include "hq_b200.h"
 
 #define CLS(name) Java_plugins_dbrasseur_hybridquantization_CudaImageManipulation_##name
@@ -44,7 +45,9 @@ JNIEXPORT void JNICALL CLS(nEvalPalettes)(JNIEnv* env, jclass c, jlong h, jfloat
     jfloat* pp = (*env)->GetPrimitiveArrayCritical(env, pal, NULL);
     jlong* pe = (*env)->GetPrimitiveArrayCritical(env, errFx, NULL);
     jlong* pc = (*env)->GetPrimitiveArrayCritical(env, counts, NULL);
-    const int rc = hq_eval_palettes(ctx, pp, b, k, space, 0, (int64_t*)pe, (uint64_t*)pc, NULL);
+    /* a Java host that keeps its own annealing loop gets the exact pruned scoring where it pays (same integers) */
+    const int flags = (space == HQ_SPACE_LAB && k >= 32 && hq_image_pixels(ctx) >= 65536) ? HQ_EVAL_PRUNE : 0;
+    const int rc = hq_eval_palettes(ctx, pp, b, k, space, flags, (int64_t*)pe, (uint64_t*)pc, NULL);
     (*env)->ReleasePrimitiveArrayCritical(env, counts, pc, 0);
     (*env)->ReleasePrimitiveArrayCritical(env, errFx, pe, 0);
     (*env)->ReleasePrimitiveArrayCritical(env, pal, pp, JNI_ABORT);

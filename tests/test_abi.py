@@ -59,3 +59,17 @@ def test_create_fails_loudly_without_gpu(hqlib):
 def test_result_layout(hqlib):
     assert hqlib.hq_result_words(256, 0) == 257
     assert hqlib.hq_result_words(256, 1) == 1 + 4 * 256
+
+
+def test_jni_shim_type_checks_against_the_c_abi():
+    """No JDK in this image: java/jni/hq_jni.c is compiled with -fsyntax-only against tests/stubs/jni.h (JNI types and the four
+    JNIEnv entries it uses) and the real include/hq_b200.h, so a drift between the shim and the C ABI is caught."""
+    import subprocess
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = ["gcc", "-fsyntax-only", "-Wall", "-Werror", "-Wno-unused-parameter", "-I" + os.path.join(repo, "tests", "stubs"), "-I" + os.path.join(repo, "include"),
+           os.path.join(repo, "java", "jni", "hq_jni.c")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # the guard must have seen the stub, i.e. the shim's body was really compiled
+    r2 = subprocess.run(cmd[:1] + ["-E", "-dM"] + cmd[3:], capture_output=True, text=True)
+    assert "HQ_HAVE_JNI" in r2.stdout

@@ -37,3 +37,33 @@ def test_cpp_plugin_end_to_end(oracle, hqlib, tmp_path):
     ores = oracle.assign_reduce(img, pal)
     want = [oracle.cost(int(ores["err_fx"][i]), ores["counts"][i], w * h, 2.0) for i in range(4)]
     assert [float.fromhex(x) for x in got["costs"]] == want
+
+
+def test_jni_shim_through_a_fake_jnienv(oracle, hqlib, tmp_path):
+    """java/jni/hq_jni.c executed on the GPU without a JVM: compiled against tests/stubs/jni.h and driven by
+    tests/cpp/jni_harness.c, whose JNIEnv pins plain C buffers.  Every native method of CudaImageManipulation runs; the
+    integers must equal the oracle's and an unsupported K must raise the Java exception."""
+    exe = str(tmp_path / "jni_harness")
+    libdir = os.path.join(REPO, "hybridquantization_b200")
+    subprocess.run(["gcc", "-O2", "-I", os.path.join(REPO, "tests", "stubs"), "-I", os.path.join(REPO, "include"), "-o", exe,
+                    os.path.join(REPO, "tests", "cpp", "jni_harness.c"), os.path.join(REPO, "java", "jni", "hq_jni.c"),
+                    "-L", libdir, "-lhq_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    w, h, K, B = 320, 240, 48, 3
+    r = subprocess.run([exe, str(w), str(h), str(K)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = json.loads(r.stdout)
+    img = synth.synth_image(w, h, 5)
+    pal = np.zeros((B, K, 4), np.float32)
+    for b in range(B):
+        for k in range(K):
+            for c in range(3):
+                pal[b, k, c] = np.float32(np.float32((b * 7919 + k * 104729 + c * 1299709) % 1000) / np.float32(999.0))
+    want = oracle.assign_reduce(img, pal, threads=THREADS)
+    assert got["pixels"] == w * h and got["threw_on_bad_k"] == 1
+    assert got["err_fx"] == [int(v) for v in want["err_fx"]]
+    assert got["counts"] == [int(v) for v in want["counts"].reshape(-1)]
+    q = oracle.quantize(img, pal[0])["rgb"].reshape(-1)
+    hsh = 0
+    for v in q.tolist():
+        hsh = (hsh * 1099511628211 + v) & 0xFFFFFFFFFFFFFFFF
+    assert got["image_hash"] == hsh
