@@ -79,3 +79,31 @@ def test_c5_palette_sweep_4k_conservation_and_srgb(backend, oracle, K):
     if K <= 128:
         want = oracle.assign_reduce(img, pal, threads=THREADS)
         assert got["err_fx"][0] == want["err_fx"][0] and np.array_equal(got["counts"], want["counts"])
+
+
+def test_pruned_scoring_at_full_sizes(backend):
+    """BASELINE sizes through the exact pruned kernel: identical integers to the exhaustive kernel at 4K (64 candidates) and
+    64 MP; beyond HQ_MAX_COLORS (K = 4096, pruned kernel only) conservation laws hold."""
+    from hybridquantization_b200 import EVAL_PRUNE
+
+    img = synth.synth_image(3840, 2160, synth.SEED_BASE + 3)
+    pal = synth.synth_palettes(64, 256)
+    backend.setImage(img)
+    a = backend.evalPalettes(pal, sums=True)
+    b = backend.evalPalettes(pal, sums=True, flags=EVAL_PRUNE)
+    assert all(np.array_equal(a[k], b[k]) for k in ("err_fx", "counts", "sums_fx"))
+    big = synth.synth_palettes(2, 4096)
+    r = backend.evalPalettes(big, sums=True)
+    assert (r["counts"].sum(axis=1) == 3840 * 2160).all()
+    lab = backend.labImage()
+    tot = np.array([np.rint(lab[c].astype(np.float64) * 16777216.0).astype(np.int64).sum() for c in range(3)])
+    assert np.array_equal(r["sums_fx"][0].sum(axis=0), tot) and np.array_equal(r["sums_fx"][1].sum(axis=0), tot)
+    # a superset palette can only lower the error: the first 256 colours of `big` vs all 4096
+    sub = backend.evalPalettes(big[:, :256].copy(), flags=EVAL_PRUNE)
+    assert (r["err_fx"] <= sub["err_fx"]).all()
+    img = synth.synth_image(8192, 8192, synth.SEED_BASE + 4)
+    pal = synth.synth_palettes(2, 256)
+    backend.setImage(img)
+    a = backend.evalPalettes(pal, sums=True)
+    b = backend.evalPalettes(pal, sums=True, flags=EVAL_PRUNE)
+    assert all(np.array_equal(a[k], b[k]) for k in ("err_fx", "counts", "sums_fx"))
