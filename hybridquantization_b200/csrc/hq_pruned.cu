@@ -346,7 +346,7 @@ __device__ __forceinline__ void score_chunk(const PrunedParams& p, unsigned* s_U
 }
 
 template <bool SUMS, int IDXW>
-__global__ void __launch_bounds__(kThreads, SUMS ? 3 : 4) pruned_assign_kernel(const PrunedParams p) {
+__global__ void __launch_bounds__(kThreads, SUMS ? 2 : 4) pruned_assign_kernel(const PrunedParams p) {
     __shared__ unsigned s_U[2];
     __shared__ long long s_err[kThreads / 32];
     if (threadIdx.x < 2) s_U[threadIdx.x] = 0x7f800000u;
