@@ -757,7 +757,10 @@ int hq_find_best_quantization(hq_ctx* c, int K, const hq_swasa_params* p, uint64
         backend.setProgress(c->progress, c->progress_user);
         {   // exact pruning of the population scoring (bit-identical costs, so the trajectory is unchanged)
             const bool allowed = p->space == HQ_SPACE_LAB && p->cost_model == HQ_COST_LAB;
-            const bool pays = K >= 32 && c->own_hi - c->own_lo >= 65536;
+            // measured crossover (4 candidates, profiles/r01/sweep_v10.json + DESIGN.md section 6): from K = 32 on every image of
+            // >= 256 x 256, from K = 12 on images of >= 1024 x 768
+            const size_t own = c->own_hi - c->own_lo;
+            const bool pays = (K >= 32 && own >= 65536) || (K >= 12 && own >= 786432);
             backend.setEvalFlags(allowed && (K > HQ_MAX_COLORS || c->prune_mode == HQ_PRUNE_ON || (c->prune_mode == HQ_PRUNE_AUTO && pays)) ? HQ_EVAL_PRUNE : 0);
         }
         hq::JavaRandom random(p->seed);

@@ -117,8 +117,8 @@ int hq_eval_palettes_device(hq_ctx* ctx, const void* d_palettes, int B, int K, i
  * sorted by a coarse CIELAB cell into chunks with exact bounding boxes, and per (chunk, candidate) only the colours that
  * can be the nearest one of some pixel of the chunk are compared.  Outputs are bit-identical to the exhaustive kernel.
  * HQ_EVAL_PRUNE selects it per call (LAB space only; ignored otherwise).  hq_set_pruning chooses what the annealing search
- * (hq_find_best_quantization) does: HQ_PRUNE_OFF never, HQ_PRUNE_AUTO (default) when K >= 32, the shard has >= 65,536
- * pixels and the search runs in LAB space with the LAB cost model, HQ_PRUNE_ON whenever the space and cost model allow.
+ * (hq_find_best_quantization) does: HQ_PRUNE_OFF never, HQ_PRUNE_AUTO (default) when it pays — K >= 32 on a shard of >= 65,536
+ * pixels, K >= 12 on one of >= 786,432 — and the search runs in LAB space with the LAB cost model, HQ_PRUNE_ON whenever the space and cost model allow.
  * The same mode governs the index-producing pruned kernel inside hq_eval_palettes_scielab (AUTO: K >= 32 and >= 65,536 pixels)
  * and hq_quantize (AUTO: only for K > HQ_MAX_COLORS); palettes with HQ_MAX_COLORS < K <= HQ_MAX_COLORS_PRUNED always use it.
  * hq_pruning_stats: chunks of the resident image and, when profiling is enabled, the mean number of colours that
