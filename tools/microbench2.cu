@@ -17,16 +17,18 @@
 #define IMNMX(d, a) asm volatile("min.s32 %0, %0, %1;" : "+r"(d) : "r"(a))
 #define SETPSEL(d, a, b) asm volatile("{ .reg .pred p; setp.lt.f32 p, %1, %2; selp.f32 %0, %1, %0, p; }" : "+f"(d) : "f"(a), "f"(b))
 #define LOP(d, a) asm volatile("xor.b32 %0, %0, %1;" : "+r"(d) : "r"(a))
+// 3-input integer min (VIMNMX3): candidate replacement for FMNMX3 on non-negative floats reinterpreted as ints
+#define VIMIN3(d, a, b) d = __vimin3_s32(d, a, b)
 
 enum { M_FFMA, M_FFMA2, M_FMIN, M_FMIN3, M_IADD, M_IMNMX, M_SETPSEL, M_LOP,
        M_FFMA24_FMIN3_4, M_FFMA2_12_FMIN3_4, M_FFMA24_FMIN_8, M_FFMA24_IADD_8, M_FFMA2_12_IADD_8,
-       M_FFMA24_SETPSEL_4, M_FFMA2_12_FMIN_8, M_FFMA24_LOP_8, M_FFMA16_FMIN3_8, M_FFMA2P_12, M_FFMA2P_12_FMIN3_4, M_FFMA2P_12_FMIN3_8, M_FFMA2P_12_FMIN_8, M_COUNT };
+       M_FFMA24_SETPSEL_4, M_FFMA2_12_FMIN_8, M_FFMA24_LOP_8, M_FFMA16_FMIN3_8, M_FFMA2P_12, M_FFMA2P_12_FMIN3_4, M_FFMA2P_12_FMIN3_8, M_FFMA2P_12_FMIN_8, M_VIMIN3, M_FFMA2P_12_VIMIN3_4, M_FFMA2P_12_VIMIN3_8, M_COUNT };
 static const char* names[M_COUNT] = {"ffma", "ffma2", "fmin", "fmin3", "iadd", "imnmx", "setpsel", "lop",
   "ffma24+fmin3x4", "ffma2x12+fmin3x4", "ffma24+fminx8", "ffma24+iaddx8", "ffma2x12+iaddx8",
-  "ffma24+setpselx4", "ffma2x12+fminx8", "ffma24+lopx8", "ffma16+fmin3x8", "ffma2p x12", "ffma2p x12+fmin3x4", "ffma2p x12+fmin3x8", "ffma2p x12+fminx8"};
+  "ffma24+setpselx4", "ffma2x12+fminx8", "ffma24+lopx8", "ffma16+fmin3x8", "ffma2p x12", "ffma2p x12+fmin3x4", "ffma2p x12+fmin3x8", "ffma2p x12+fminx8", "vimin3", "ffma2p x12+vimin3x4", "ffma2p x12+vimin3x8"};
 // warp-level instructions per loop iteration (setp+sel counted as 2)
-static const int instrs[M_COUNT] = {24, 12, 8, 8, 8, 8, 16, 8, 28, 16, 32, 32, 20, 32, 20, 32, 24, 12, 16, 20, 20};
-static const int fma_equiv[M_COUNT] = {24, 24, 0, 0, 0, 0, 0, 0, 24, 24, 24, 24, 24, 24, 24, 24, 16, 24, 24, 24, 24};
+static const int instrs[M_COUNT] = {24, 12, 8, 8, 8, 8, 16, 8, 28, 16, 32, 32, 20, 32, 20, 32, 24, 12, 16, 20, 20, 8, 16, 20};
+static const int fma_equiv[M_COUNT] = {24, 24, 0, 0, 0, 0, 0, 0, 24, 24, 24, 24, 24, 24, 24, 24, 16, 24, 24, 24, 24, 0, 24, 24};
 
 template <int M>
 __global__ void __launch_bounds__(256) k(const float* __restrict__ in, float* __restrict__ out, int iters, unsigned long long* cyc) {
@@ -102,6 +104,15 @@ __global__ void __launch_bounds__(256) k(const float* __restrict__ in, float* __
         } else if (M == M_FFMA2P_12_FMIN_8) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) { FFMA2P(F[3*i], F[(3*i + 5) % 12], f[i]); FMIN(g[2*i], s); FFMA2P(F[3*i+1], F[(3*i + 6) % 12], f[i+4]); FMIN(g[2*i+1], s); FFMA2P(F[3*i+2], F[(3*i + 7) % 12], f[i+8]); }
+        } else if (M == M_VIMIN3) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { VIMIN3(n[i], __float_as_int(f[i]) + it, __float_as_int(f[i + 8])); }
+        } else if (M == M_FFMA2P_12_VIMIN3_4) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { FFMA2P(F[3*i], F[(3*i + 5) % 12], f[i]); FFMA2P(F[3*i+1], F[(3*i + 6) % 12], f[i+4]); VIMIN3(n[i], ni + it, __float_as_int(t)); FFMA2P(F[3*i+2], F[(3*i + 7) % 12], f[i+8]); }
+        } else if (M == M_FFMA2P_12_VIMIN3_8) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { FFMA2P(F[3*i], F[(3*i + 5) % 12], f[i]); VIMIN3(n[2*i], ni + it, __float_as_int(t)); FFMA2P(F[3*i+1], F[(3*i + 6) % 12], f[i+4]); VIMIN3(n[2*i+1], ni - it, __float_as_int(s)); FFMA2P(F[3*i+2], F[(3*i + 7) % 12], f[i+8]); }
         } else if (M == M_FFMA16_FMIN3_8) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) { FFMA(f[2*i], s, t); FMIN3(g[i], s, t); FFMA(f[2*i+1], s, t); }
@@ -122,7 +133,7 @@ __global__ void __launch_bounds__(256) k(const float* __restrict__ in, float* __
 template <int M> void launch(int grid, const float* in, float* out, int iters, unsigned long long* cyc) { k<M><<<grid, 256>>>(in, out, iters, cyc); }
 typedef void (*launch_fn)(int, const float*, float*, int, unsigned long long*);
 template <int... Ms> struct Table { static constexpr launch_fn fns[sizeof...(Ms)] = {launch<Ms>...}; };
-using T = Table<0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20>;
+using T = Table<0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23>;
 
 int main() {
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
