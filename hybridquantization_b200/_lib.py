@@ -79,6 +79,7 @@ SIGNATURES = {
     "hq_set_progress": (C.c_int, [_P, PROGRESS_FN, _P]),
     "hq_set_pruning": (C.c_int, [_P, C.c_int]),
     "hq_set_graphs": (C.c_int, [_P, C.c_int]),
+    "hq_search_eval_flags": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "hq_pruning_stats": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_double)]),
     "hq_java_random_seed": (None, [C.POINTER(JavaRandomState), C.c_int64]),
     "hq_java_random_next": (C.c_int32, [C.POINTER(JavaRandomState), C.c_int]),

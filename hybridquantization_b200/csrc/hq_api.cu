@@ -755,14 +755,7 @@ int hq_find_best_quantization(hq_ctx* c, int K, const hq_swasa_params* p, uint64
         backend.setStopFlag(&c->stop_flag_view);
         backend.setCostModel(p->cost_model);
         backend.setProgress(c->progress, c->progress_user);
-        {   // exact pruning of the population scoring (bit-identical costs, so the trajectory is unchanged)
-            const bool allowed = p->space == HQ_SPACE_LAB && p->cost_model == HQ_COST_LAB;
-            // measured crossover (4 candidates, profiles/r01/sweep_v10.json + DESIGN.md section 6): from K = 32 on every image of
-            // >= 256 x 256, from K = 12 on images of >= 1024 x 768
-            const size_t own = c->own_hi - c->own_lo;
-            const bool pays = (K >= 32 && own >= 65536) || (K >= 12 && own >= 786432);
-            backend.setEvalFlags(allowed && (K > HQ_MAX_COLORS || c->prune_mode == HQ_PRUNE_ON || (c->prune_mode == HQ_PRUNE_AUTO && pays)) ? HQ_EVAL_PRUNE : 0);
-        }
+        backend.setEvalFlags(hq_search_eval_flags(c, K, p->space, p->cost_model));  // exact pruning where it pays: same costs, same trajectory
         hq::JavaRandom random(p->seed);
         hq::SWASA swasa(p->population, p->imax, p->iTc, p->delta, p->conv_delay, p->conv_spread, p->t0, p->alpha, p->s0, p->beta, &random);
         double err = 0;
@@ -774,6 +767,16 @@ int hq_find_best_quantization(hq_ctx* c, int K, const hq_swasa_params* p, uint64
         return HQ_ERR_CUDA;
     }
     return HQ_OK;
+}
+
+int hq_search_eval_flags(const hq_ctx* c, int K, int space, int cost_model) {
+    if (!c || !c->have_image) return 0;
+    if (space != HQ_SPACE_LAB || cost_model != HQ_COST_LAB) return 0;
+    // measured crossover (4 candidates, profiles/r01/sweep_v10.json + DESIGN.md section 6): from K = 32 on every image of
+    // >= 256 x 256, from K = 12 on images of >= 1024 x 768
+    const size_t own = c->own_hi - c->own_lo;
+    const bool pays = (K >= 32 && own >= 65536) || (K >= 12 && own >= 786432);
+    return (K > HQ_MAX_COLORS || c->prune_mode == HQ_PRUNE_ON || (c->prune_mode == HQ_PRUNE_AUTO && pays)) ? HQ_EVAL_PRUNE : 0;
 }
 
 int hq_set_graphs(hq_ctx* c, int enabled) {

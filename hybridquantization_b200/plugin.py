@@ -301,6 +301,10 @@ class ImageManipulation:
         """PRUNE_OFF | PRUNE_AUTO (default) | PRUNE_ON: whether the search scores populations with the exact pruned kernel"""
         _lib.check(self._ctx, self._lib.hq_set_pruning(self._ctx, mode))
 
+    def searchEvalFlags(self, nbOfColors: int, space: int = 0, costModel: int = 0) -> int:
+        """the eval flags the built-in search would use for this image and K (hq_search_eval_flags): EVAL_PRUNE or 0"""
+        return int(self._lib.hq_search_eval_flags(self._ctx, nbOfColors, space, costModel))
+
     def setGraphs(self, enabled: bool) -> None:
         """CUDA-graph replay of repeated identical evalPalettes calls (off by default, see hq_set_graphs)"""
         _lib.check(self._ctx, self._lib.hq_set_graphs(self._ctx, int(bool(enabled))))

@@ -133,6 +133,9 @@ int hq_set_graphs(hq_ctx* ctx, int enabled);
 
 enum { HQ_PRUNE_OFF = 0, HQ_PRUNE_AUTO = 1, HQ_PRUNE_ON = 2 };
 int hq_set_pruning(hq_ctx* ctx, int mode);
+/* the HQ_EVAL_* flags a search loop over hq_eval_palettes should pass for the resident image under the context's pruning
+ * mode (what hq_find_best_quantization and the C++ / Java hosts use): HQ_EVAL_PRUNE or 0 */
+int hq_search_eval_flags(const hq_ctx* ctx, int K, int space, int cost_model);
 int hq_pruning_stats(hq_ctx* ctx, uint32_t* chunks, double* mean_survivors);
 
 /* cost = (sum dE)/N + delta * #{unused colours}: averageArray + computePenalty

@@ -151,7 +151,7 @@ public:
     }
     void setStopFlag(const volatile bool* flag) { stopFlag_ = flag; }
     void setCostModel(int costModel) { costModel_ = costModel; }  // HQ_COST_LAB | HQ_COST_SCIELAB
-    void setEvalFlags(int flags) { evalFlags_ = flags; }           // HQ_EVAL_* passed to hq_eval_palettes (e.g. HQ_EVAL_PRUNE)
+    void setEvalFlags(int flags) { evalFlags_ = flags; }           // HQ_EVAL_* passed to hq_eval_palettes; -1 (default) = hq_search_eval_flags
     // updateProgressBar (HybridQuantization.java:265-270), invoked every 10 iterations (:546-551)
     void setProgress(void (*fn)(void*, int, int, double), void* user) { progress_ = fn; progressUser_ = user; }
 
@@ -167,8 +167,10 @@ public:
         counts_.resize(static_cast<size_t>(populationSize) * nbOfColors);
         if (costModel_ == HQ_COST_SCIELAB)  // the reference's own kernel chain (:635-699)
             check(hq_eval_palettes_scielab(ctx_, colors, populationSize, nbOfColors, space, errFx_.data(), counts_.data()), "hq_eval_palettes_scielab");
-        else
-            check(hq_eval_palettes(ctx_, colors, populationSize, nbOfColors, space, evalFlags_, errFx_.data(), counts_.data(), nullptr), "hq_eval_palettes");
+        else {
+            const int flags = evalFlags_ >= 0 ? evalFlags_ : hq_search_eval_flags(ctx_, nbOfColors, space, costModel_);  // exact pruning where it pays
+            check(hq_eval_palettes(ctx_, colors, populationSize, nbOfColors, space, flags, errFx_.data(), counts_.data(), nullptr), "hq_eval_palettes");
+        }
         std::vector<double> results(populationSize);
         for (int i = 0; i < populationSize; ++i) {
             // :712 averageArray(err) + computePenalty(used)
@@ -258,7 +260,7 @@ private:
     bool verbose_, convergence_, owns_;
     const volatile bool* stopFlag_ = nullptr;
     int costModel_ = HQ_COST_LAB;
-    int evalFlags_ = 0;
+    int evalFlags_ = -1;
     void (*progress_)(void*, int, int, double) = nullptr;
     void* progressUser_ = nullptr;
     std::vector<int64_t> errFx_;

@@ -46,7 +46,7 @@ JNIEXPORT void JNICALL CLS(nEvalPalettes)(JNIEnv* env, jclass c, jlong h, jfloat
     jlong* pe = (*env)->GetPrimitiveArrayCritical(env, errFx, NULL);
     jlong* pc = (*env)->GetPrimitiveArrayCritical(env, counts, NULL);
     /* a Java host that keeps its own annealing loop gets the exact pruned scoring where it pays (same integers) */
-    const int flags = (space == HQ_SPACE_LAB && k >= 32 && hq_image_pixels(ctx) >= 65536) ? HQ_EVAL_PRUNE : 0;
+    const int flags = hq_search_eval_flags(ctx, k, space, HQ_COST_LAB);
     const int rc = hq_eval_palettes(ctx, pp, b, k, space, flags, (int64_t*)pe, (uint64_t*)pc, NULL);
     (*env)->ReleasePrimitiveArrayCritical(env, counts, pc, 0);
     (*env)->ReleasePrimitiveArrayCritical(env, errFx, pe, 0);

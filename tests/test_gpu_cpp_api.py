@@ -14,12 +14,13 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 THREADS = max(1, len(os.sched_getaffinity(0)))
 
 
-def test_cpp_plugin_end_to_end(oracle, hqlib, tmp_path):
+@pytest.mark.parametrize("w,h,K,imax", [(96, 64, 8, 120),      # below the pruning policy's thresholds: exhaustive kernel
+                                        (320, 256, 32, 30)])    # hq_search_eval_flags picks the exact pruned kernel
+def test_cpp_plugin_end_to_end(oracle, hqlib, tmp_path, w, h, K, imax):
     exe = str(tmp_path / "plugin_cpp_test")
     libdir = os.path.join(REPO, "hybridquantization_b200")
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I", os.path.join(REPO, "include"), "-o", exe,
                     os.path.join(REPO, "tests", "cpp", "plugin_cpp_test.cpp"), "-L", libdir, "-lhq_b200", f"-Wl,-rpath,{libdir}"], check=True)
-    w, h, K, imax = 96, 64, 8, 120
     r = subprocess.run([exe, str(w), str(h), str(K), str(imax)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     got = json.loads(r.stdout)

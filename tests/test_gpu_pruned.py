@@ -48,6 +48,24 @@ def test_pruning_actually_prunes(backend):
     assert 1.0 <= s["mean_survivors"] < 64.0, s   # of 256 colours
 
 
+def test_search_policy_call(backend):
+    """hq_search_eval_flags: what the built-in search, the C++ host and the JNI shim all ask before scoring a population"""
+    backend.setImage(synth.synth_image(320, 256, 5))          # 81,920 px
+    assert backend.searchEvalFlags(32, SPACE_LAB) == EVAL_PRUNE
+    assert backend.searchEvalFlags(31, SPACE_LAB) == 0
+    assert backend.searchEvalFlags(256, SPACE_SRGB) == 0        # sRGB search stays exhaustive
+    assert backend.searchEvalFlags(256, SPACE_LAB, COST_SCIELAB) == 0   # the S-CIELAB chain has its own policy
+    assert backend.searchEvalFlags(1500, SPACE_LAB) == EVAL_PRUNE
+    backend.setPruning(PRUNE_OFF)
+    assert backend.searchEvalFlags(256, SPACE_LAB) == 0
+    assert backend.searchEvalFlags(1500, SPACE_LAB) == EVAL_PRUNE      # above HQ_MAX_COLORS only the pruned kernel exists
+    backend.setPruning(PRUNE_ON)
+    assert backend.searchEvalFlags(2, SPACE_LAB) == EVAL_PRUNE
+    backend.setPruning(PRUNE_AUTO)
+    backend.setImage(synth.synth_image(64, 64, 5))
+    assert backend.searchEvalFlags(256, SPACE_LAB) == 0
+
+
 @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture], derandomize=True)
 @given(w=st.integers(1, 400), h=st.integers(1, 60), K=st.integers(1, 300), B=st.integers(1, 4), wp=st.integers(0, 1), smooth=st.booleans(),
        patho=st.sampled_from(["none", "dup", "clamp", "tiny", "far"]), seed=st.integers(0, 2 ** 31))
