@@ -56,6 +56,8 @@ SIGNATURES = {
     "hq_device_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_int]),
     "hq_set_image_u8": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int]),
     "hq_set_image_u8_sharded": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "hq_set_image_f32_planar": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int]),
+    "hq_set_image_f32_planar_sharded": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 7),
     "hq_set_image_u8_device": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "hq_get_lab": (C.c_int, [_P, _P]),
     "hq_image_pixels": (C.c_uint64, [_P]),

@@ -67,6 +67,8 @@ struct hq_ctx {
     int g_row0 = 0, g_rows = 0;                // global index of the first own row, global image height
     size_t own_lo = 0, own_hi = 0;             // own pixel range inside the local arrays
     bool have_image = false, have_unit = false;
+    bool image_f32 = false;                    // the resident image is the planar float one (d_unit); d_rgb is not used then
+    DevBuf<unsigned int> d_flag;               // out-of-range report of the float conversion
     DevBuf<uint8_t> d_rgb;
     DevBuf<float> d_lab, d_unit, d_table;
 
@@ -188,14 +190,15 @@ int convert_image(hq_ctx* c, int width, int own_rows, int halo_top, int halo_bot
     c->width = width; c->rows = halo_top + own_rows + halo_bottom; c->whitepoint = whitepoint;
     c->halo_top = halo_top; c->halo_bottom = halo_bottom; c->own_rows = own_rows; c->g_row0 = g_row0; c->g_rows = g_rows;
     c->own_lo = (size_t)halo_top * width; c->own_hi = (size_t)(halo_top + own_rows) * width;
-    c->have_unit = false;
+    c->have_unit = c->image_f32;  // a float image IS its unit planes
     c->sc_image_ready = false;
     c->pr_own.ready = false;
     c->pr_all.ready = false;
     ++c->image_gen;
     HQ_CUDA(c, c->d_lab.reserve(3 * c->stride > 0 ? 3 * c->stride : 1));
     if (c->profiling) HQ_CUDA(c, cudaEventRecord(c->ev2, st));
-    HQ_CUDA(c, hq::launch_rgb_to_lab(c->d_rgb.p, c->n, c->stride, whitepoint, c->d_table.p, c->d_lab.p, nullptr, c->sm_count, st));
+    if (c->image_f32) HQ_CUDA(c, hq::launch_unit_to_lab(c->d_unit.p, c->n, c->stride, whitepoint, c->d_lab.p, c->d_flag.p, c->sm_count, st));
+    else HQ_CUDA(c, hq::launch_rgb_to_lab(c->d_rgb.p, c->n, c->stride, whitepoint, c->d_table.p, c->d_lab.p, nullptr, c->sm_count, st));
     if (c->profiling) { HQ_CUDA(c, cudaEventRecord(c->ev3, st)); c->ev_rl_valid = true; }
     c->have_image = true;
     return HQ_OK;
@@ -345,7 +348,7 @@ void hq_destroy(hq_ctx* c) {
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
     if (c->ev3) cudaEventDestroy(c->ev3);
-    c->d_rgb.release(); c->d_lab.release(); c->d_unit.release(); c->d_table.release(); c->d_pal.release();
+    c->d_rgb.release(); c->d_flag.release(); c->d_lab.release(); c->d_unit.release(); c->d_table.release(); c->d_pal.release();
     c->d_pal_lab.release(); c->d_pal_rgb.release(); c->d_results.release(); c->d_idx.release();
     c->d_out_rgb.release(); c->d_out_f32.release(); c->h_pal.release(); c->h_results.release();
     c->d_sc_filters.release(); c->d_sc_opp.release(); c->d_sc_tmp.release(); c->d_sc_lab.release(); c->d_sc_tab.release(); c->d_sc_err.release();
@@ -377,6 +380,7 @@ int hq_set_image_u8_sharded(hq_ctx* c, const uint8_t* rgb, int width, int own_ro
     if (whitepoint != HQ_WHITEPOINT_D65 && whitepoint != HQ_WHITEPOINT_D50) return fail(c, HQ_ERR_INVALID, "unknown white point %d", whitepoint);
     int rc = bind_device(c); if (rc) return rc;
     c->have_image = false;
+    c->image_f32 = false;
     c->n = (size_t)width * rows;
     c->stride = hq::plane_stride(c->n);
     HQ_CUDA(c, c->d_rgb.reserve(c->n * 3 > 0 ? c->n * 3 : 1));
@@ -384,6 +388,41 @@ int hq_set_image_u8_sharded(hq_ctx* c, const uint8_t* rgb, int width, int own_ro
     rc = convert_image(c, width, own_rows, halo_top, halo_bottom, global_row0, global_rows, whitepoint, c->stream); if (rc) return rc;
     HQ_CUDA(c, cudaStreamSynchronize(c->stream));
     return HQ_OK;
+}
+
+int hq_set_image_f32_planar_sharded(hq_ctx* c, const float* r, const float* g, const float* b, int width, int own_rows, int halo_top,
+                                    int halo_bottom, int global_row0, int global_rows, int whitepoint) {
+    if (!c) return HQ_ERR_INVALID;
+    const long long rows = (long long)halo_top + own_rows + halo_bottom;
+    if (width < 0 || own_rows < 0 || halo_top < 0 || halo_bottom < 0 || ((!r || !g || !b) && (size_t)width * rows > 0))
+        return fail(c, HQ_ERR_INVALID, "bad image arguments");
+    if (global_row0 < halo_top || global_row0 + own_rows + halo_bottom > global_rows)
+        return fail(c, HQ_ERR_INVALID, "shard rows [%d,%d) with halos %d/%d do not fit a %d-row image", global_row0, global_row0 + own_rows, halo_top, halo_bottom, global_rows);
+    if (whitepoint != HQ_WHITEPOINT_D65 && whitepoint != HQ_WHITEPOINT_D50) return fail(c, HQ_ERR_INVALID, "unknown white point %d", whitepoint);
+    int rc = bind_device(c); if (rc) return rc;
+    c->have_image = false;
+    c->image_f32 = true;
+    c->n = (size_t)width * rows;
+    c->stride = hq::plane_stride(c->n);
+    HQ_CUDA(c, c->d_unit.reserve(3 * c->stride > 0 ? 3 * c->stride : 1));
+    HQ_CUDA(c, c->d_flag.reserve(1));
+    HQ_CUDA(c, cudaMemsetAsync(c->d_flag.p, 0, sizeof(unsigned int), c->stream));
+    const float* planes[3] = {r, g, b};
+    for (int pl = 0; pl < 3 && c->n; ++pl)
+        HQ_CUDA(c, cudaMemcpyAsync(c->d_unit.p + (size_t)pl * c->stride, planes[pl], c->n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    rc = convert_image(c, width, own_rows, halo_top, halo_bottom, global_row0, global_rows, whitepoint, c->stream); if (rc) return rc;
+    unsigned int bad = 0;
+    HQ_CUDA(c, cudaMemcpyAsync(&bad, c->d_flag.p, sizeof bad, cudaMemcpyDeviceToHost, c->stream));
+    HQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (bad) {
+        c->have_image = false;
+        return fail(c, HQ_ERR_INVALID, "float image values must lie in [0,1] (Icy's rescaled convertToType, HybridQuantization.java:95)");
+    }
+    return HQ_OK;
+}
+
+int hq_set_image_f32_planar(hq_ctx* c, const float* r, const float* g, const float* b, int width, int rows, int whitepoint) {
+    return hq_set_image_f32_planar_sharded(c, r, g, b, width, rows, 0, 0, 0, rows, whitepoint);
 }
 
 int hq_set_image_u8(hq_ctx* c, const uint8_t* rgb, int width, int rows, int whitepoint) {
@@ -397,6 +436,7 @@ int hq_set_image_u8_device(hq_ctx* c, const void* d_rgb, int width, int rows, in
     int rc = bind_device(c); if (rc) return rc;
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
     c->have_image = false;
+    c->image_f32 = false;
     c->n = (size_t)width * rows;
     c->stride = hq::plane_stride(c->n);
     HQ_CUDA(c, c->d_rgb.reserve(c->n * 3 > 0 ? c->n * 3 : 1));
@@ -633,7 +673,8 @@ static int sc_ensure_image(hq_ctx* c) {
     HQ_CUDA(c, c->d_sc_opp.reserve(3 * c->stride));
     HQ_CUDA(c, c->d_sc_tmp.reserve(7 * c->stride));
     HQ_CUDA(c, c->d_sc_lab.reserve(3 * c->stride));
-    HQ_CUDA(c, hq::launch_sc_rgb_to_opp(c->d_rgb.p, c->n, c->stride, c->d_table.p, c->d_sc_opp.p, c->stream));
+    if (c->image_f32) HQ_CUDA(c, hq::launch_sc_unit_to_opp(c->d_unit.p, c->n, c->stride, c->d_sc_opp.p, c->stream));
+    else HQ_CUDA(c, hq::launch_sc_rgb_to_opp(c->d_rgb.p, c->n, c->stride, c->d_table.p, c->d_sc_opp.p, c->stream));
     HQ_CUDA(c, hq::launch_sc_original(c->d_sc_opp.p, c->width, c->rows, c->stride, c->d_sc_filters.p, c->sc_generic ? nullptr : c->sc_block.data(), c->sc_taps,
                                       c->whitepoint, sc_rows(c), c->d_sc_tmp.p, c->d_sc_lab.p, c->stream));
     c->sc_image_ready = true;

@@ -250,6 +250,22 @@ rgb_to_lab_kernel(const uint8_t* __restrict__ rgb, size_t n, size_t stride, int 
     }
 }
 
+// ---- planar float image (HybridQuantization.java:95-98: any Icy data type rescaled to floats in [0,1]) -> Lab.
+// No table applies to arbitrary floats: every channel goes through the single-source hq_srgb_decode (exact double pow
+// to float, hq_math.h) like a palette colour does.  Values outside [0,1] (or NaN) lie outside the domain that
+// routine is verified on; they are reported through `bad` and the image is refused.
+__global__ void __launch_bounds__(256) unit_to_lab_kernel(const float* __restrict__ unit, size_t n, size_t stride, int whitepoint,
+                                                          float* __restrict__ lab, unsigned int* __restrict__ bad) {
+    const hq_white white = hq_make_white(whitepoint);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float r = unit[i], g = unit[stride + i], b = unit[2 * stride + i];
+        hq_float3 v; v.x = v.y = v.z = 0.f;
+        if (r >= 0.f && r <= 1.f && g >= 0.f && g <= 1.f && b >= 0.f && b <= 1.f) v = hq_srgb_to_lab(r, g, b, white);
+        else atomicOr(bad, 1u);
+        lab[i] = v.x; lab[stride + i] = v.y; lab[2 * stride + i] = v.z;
+    }
+}
+
 // ====================================================================== palettes -> features
 __global__ void palette_features_kernel(const float* __restrict__ pal, int B, int K, int K8,
                                         int whitepoint, float4* __restrict__ pal_lab,
@@ -770,6 +786,16 @@ cudaError_t launch_fp32_peak(bool packed, int iters, int sm_count, float* d_out,
 // ====================================================================== launchers
 cudaError_t launch_decode_table(float* d_table, cudaStream_t stream) {
     decode_table_kernel<<<1, 256, 0, stream>>>(d_table);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unit_to_lab(const float* d_unit, size_t n, size_t stride, int whitepoint, float* d_lab, unsigned int* d_bad,
+                               int sm_count, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    size_t grid = (n + 255) / 256;
+    const size_t cap = (size_t)(sm_count > 0 ? sm_count : 148) * 8;
+    if (grid > cap) grid = cap;
+    unit_to_lab_kernel<<<(unsigned)grid, 256, 0, stream>>>(d_unit, n, stride, whitepoint, d_lab, d_bad);
     return cudaGetLastError();
 }
 

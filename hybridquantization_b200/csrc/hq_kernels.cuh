@@ -22,6 +22,9 @@ inline size_t plane_stride(size_t n) { return (n + 31) / 32 * 32; }
 // packed u8 RGB -> fp32 planes.  lab = [3][stride] (L, a, b); unit = [3][stride] (r, g, b)/255 or null.
 // d_table: 512 floats built once by launch_decode_table (u8 -> unit, u8 -> linear light)
 cudaError_t launch_decode_table(float* d_table, cudaStream_t stream);
+// planar float sRGB in [0,1] ([3][stride]) -> Lab planes; *d_bad |= 1 when a value is outside [0,1] or NaN
+cudaError_t launch_unit_to_lab(const float* d_unit, size_t n, size_t stride, int whitepoint, float* d_lab, unsigned int* d_bad,
+                               int sm_count, cudaStream_t stream);
 cudaError_t launch_rgb_to_lab(const uint8_t* d_rgb, size_t n, size_t stride, int whitepoint, const float* d_table,
                               float* d_lab, float* d_unit, int sm_count, cudaStream_t stream);
 
@@ -96,6 +99,7 @@ struct ScRows {
 // ---- S-CIELAB stage (hq_scielab.cu).  d_filters: [8][taps] = k1[t][3], k2[t][3], k3[t], |k3|[t]
 constexpr int kMaxScielabTaps = 255;
 cudaError_t launch_sc_rgb_to_opp(const uint8_t* d_rgb, size_t n, size_t stride, const float* d_table, float* d_opp, cudaStream_t st);
+cudaError_t launch_sc_unit_to_opp(const float* d_unit, size_t n, size_t stride, float* d_opp, cudaStream_t st);  // float image
 cudaError_t launch_sc_palette_opp(const float* d_palettes, int total, float4* d_tab, cudaStream_t st);
 // original image: opp planes -> S-CIELAB Lab planes (d_tmp: 7 planes of scratch)
 // h_filters: the same block on the host (nullptr = always use the generic kernels); with taps == 21

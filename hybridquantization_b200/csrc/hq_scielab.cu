@@ -31,6 +31,14 @@ __global__ void sc_rgb_to_opp_kernel(const uint8_t* __restrict__ rgb, size_t n, 
     opp[i] = o.x; opp[stride + i] = o.y; opp[2 * stride + i] = o.z;
 }
 
+// the same for a planar float image: decoded per value, as the reference's RGB2XYZ kernel does (cl:79-90)
+__global__ void sc_unit_to_opp_kernel(const float* __restrict__ unit, size_t n, size_t stride, float* __restrict__ opp) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const hq_float3 o = hq_cl_linrgb_to_opp_via_xyz(hq_srgb_decode(unit[i]), hq_srgb_decode(unit[stride + i]), hq_srgb_decode(unit[2 * stride + i]));
+    opp[i] = o.x; opp[stride + i] = o.y; opp[2 * stride + i] = o.z;
+}
+
 // palette colours -> opponent table (the K values the quantised image can take)
 __global__ void sc_palette_opp_kernel(const float* __restrict__ pal, int total, float4* __restrict__ tab) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -308,6 +316,12 @@ cudaError_t launch_sc_rgb_to_opp(const uint8_t* d_rgb, size_t n, size_t stride, 
 cudaError_t launch_sc_palette_opp(const float* d_palettes, int total, float4* d_tab, cudaStream_t st) {
     if (total == 0) return cudaSuccess;
     sc_palette_opp_kernel<<<(total + 127) / 128, 128, 0, st>>>(d_palettes, total, d_tab);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sc_unit_to_opp(const float* d_unit, size_t n, size_t stride, float* d_opp, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    sc_unit_to_opp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_unit, n, stride, d_opp);
     return cudaGetLastError();
 }
 

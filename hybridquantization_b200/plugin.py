@@ -172,6 +172,20 @@ class ImageManipulation:
         _lib.check(self._ctx, self._lib.hq_set_image_u8_sharded(self._ctx, _ptr(rgb), rgb.shape[1], own, halo_top, halo_bottom,
                                                                   global_row0, global_rows, whitepoint))
 
+    def setImageFloat(self, planes: np.ndarray, whitepoint: int = WHITEPOINT_D65, halo_top: int = 0, halo_bottom: int = 0,
+                      global_row0: int = 0, global_rows: int | None = None) -> None:
+        """planes: float32 [3, rows, width] in [0,1] — `im.getDataXYCAsFloat()` (HybridQuantization.java:95-98), any Icy
+        data type after the rescaling conversion.  With halos: rows = halo_top + own rows + halo_bottom."""
+        p = np.ascontiguousarray(planes, np.float32)
+        if p.ndim != 3 or p.shape[0] < 3:
+            raise ValueError("Please open an image with 3 or more channels")  # HybridQuantization.java:68-69
+        own = p.shape[1] - halo_top - halo_bottom
+        self.shape = (own, p.shape[2])
+        self._local_pixels = p.shape[1] * p.shape[2]
+        _lib.check(self._ctx, self._lib.hq_set_image_f32_planar_sharded(
+            self._ctx, _ptr(p[0]), _ptr(p[1]), _ptr(p[2]), p.shape[2], own, halo_top, halo_bottom, global_row0,
+            own if global_rows is None else global_rows, whitepoint))
+
     def setImageDevice(self, d_rgb_ptr: int, width: int, rows: int, whitepoint: int = WHITEPOINT_D65, stream: int = 0):
         self.shape = (rows, width)
         self._local_pixels = rows * width

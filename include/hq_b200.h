@@ -85,6 +85,15 @@ int hq_set_image_u8_sharded(hq_ctx* ctx, const uint8_t* rgb, int width, int own_
  * cudaStream_t, NULL = the context's stream) and does not synchronise */
 int hq_set_image_u8_device(hq_ctx* ctx, const void* d_rgb, int width, int rows, int whitepoint,
                            void* stream);
+/* The image as the plugin itself holds it: planar floats in [0,1], one array per channel (`im.getDataXYCAsFloat()` after
+ * `IcyBufferedImageUtil.convertToType(..., DataType.FLOAT, true)`, HybridQuantization.java:95-98) — so 16-bit and float
+ * Icy images need no detour through u8.  Each value is decoded on the device exactly as ScielabProcessor.java:282-284
+ * does (double pow, rounded once to float); a u8-derived float image gives the same bits as hq_set_image_u8.
+ * Values outside [0,1] or NaN: HQ_ERR_INVALID.  Host pointers; r, g, b each hold rows*width floats. */
+int hq_set_image_f32_planar(hq_ctx* ctx, const float* r, const float* g, const float* b, int width, int rows, int whitepoint);
+/* row shard with halo rows, arguments as hq_set_image_u8_sharded */
+int hq_set_image_f32_planar_sharded(hq_ctx* ctx, const float* r, const float* g, const float* b, int width, int own_rows,
+                                    int halo_top, int halo_bottom, int global_row0, int global_rows, int whitepoint);
 /* debug / parity: the Lab planes [3][n] (L plane, a plane, b plane) */
 int hq_get_lab(hq_ctx* ctx, float* planes);
 uint64_t hq_image_pixels(const hq_ctx* ctx);

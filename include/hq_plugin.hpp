@@ -159,6 +159,10 @@ public:
     void setImage(const uint8_t* rgb, int w, int rows, int whitepoint) {
         check(hq_set_image_u8(ctx_, rgb, w, rows, whitepoint), "hq_set_image_u8");
     }
+    // the plugin's own representation: im.getDataXYCAsFloat() planes in [0,1] (HybridQuantization.java:95-98)
+    void setImage(const float* r, const float* g, const float* b, int w, int rows, int whitepoint) {
+        check(hq_set_image_f32_planar(ctx_, r, g, b, w, rows, whitepoint), "hq_set_image_f32_planar");
+    }
 
     // :620-727 — evaluates the whole population in one launch
     std::vector<double> computeQuantizationErrorPopulation(int populationSize, const float* colors, int nbOfColors,
@@ -358,6 +362,8 @@ public:
     int whitepointCode() const { return whitepoint_ == Whitepoint::D50 ? HQ_WHITEPOINT_D50 : HQ_WHITEPOINT_D65; }
     // sRGBToScielab (:374-381) with the identity filter: uploads the image, converts on the GPU
     void sRGBToScielab(const uint8_t* rgb, int w, int rows) { imageProcessing_->setImage(rgb, w, rows, whitepointCode()); }
+    // float[][] sRGBImage as the reference passes it (:374): one plane per channel
+    void sRGBToScielab(const float* r, const float* g, const float* b, int w, int rows) { imageProcessing_->setImage(r, g, b, w, rows, whitepointCode()); }
     std::vector<float> bestColors(int nbOfColors, SWASA& simulatedAnnealing, uint64_t nTotal, int space, double* bestError = nullptr) {
         return imageProcessing_->findBestQuantization(nbOfColors, simulatedAnnealing, nTotal, space, bestError);
     }
@@ -424,6 +430,18 @@ struct HybridQuantization {
     // (:65-70: an image with at least 3 channels is required).
     std::vector<float> quantization(const uint8_t* rgb, int w, int h, uint8_t* outRgb, double* bestError = nullptr) {
         if (!rgb || w <= 0 || h <= 0) throw std::invalid_argument("Please open an image first.");
+        return run(w, h, outRgb, bestError, [&](ScielabProcessor& sp) { sp.sRGBToScielab(rgb, w, h); });
+    }
+    // the same on the converted float image the plugin holds (im.getDataXYCAsFloat(), :95-98): one plane per channel
+    std::vector<float> quantization(const float* r, const float* g, const float* b, int w, int h, uint8_t* outRgb, double* bestError = nullptr) {
+        if (!r || !g || !b || w <= 0 || h <= 0) throw std::invalid_argument("Please open an image first.");
+        return run(w, h, outRgb, bestError, [&](ScielabProcessor& sp) { sp.sRGBToScielab(r, g, b, w, h); });
+    }
+
+  private:
+    template <class Upload>
+    std::vector<float> run(int w, int h, uint8_t* outRgb, double* bestError, Upload upload) {
+        (void)w; (void)h;
         stopFlag = false;
         ImageManipulation imageProcessor(ImageManipulation::deltaETypes::CIE76, verbose, convEnable, device);  // :96
         imageProcessor.setStopFlag(&stopFlag);
@@ -431,7 +449,7 @@ struct HybridQuantization {
         JavaRandom random(seed);
         SWASA swasa(populationSize, imax, iTc, delta, convDelay, convSpread, T0, alpha, s0, beta, &random);  // :97
         ScielabProcessor scielabProcessor(dpi, viewingDistance, whitePoint, &imageProcessor);               // :101
-        scielabProcessor.sRGBToScielab(rgb, w, h);                                                          // :104
+        upload(scielabProcessor);                                                                           // :104
         if (costModel == HQ_COST_SCIELAB) {  // :180 updateOpenCLFilters with the bank built from dpi / viewing distance
             const std::vector<float> flat = scielabProcessor.filters().flat();
             if (hq_scielab_set_filters(imageProcessor.context(), flat.data(), scielabProcessor.filters().absOfilters.data(), scielabProcessor.filters().taps()) != HQ_OK)

@@ -39,6 +39,19 @@ JNIEXPORT void JNICALL CLS(nSetImage)(JNIEnv* env, jclass c, jlong h, jbyteArray
     if (rc != HQ_OK) throw_hq(env, ctx, "hq_set_image_u8");
 }
 
+/* float[] planes exactly as im.getDataXYCAsFloat() holds them (HybridQuantization.java:98) */
+JNIEXPORT void JNICALL CLS(nSetImageFloat)(JNIEnv* env, jclass c, jlong h, jfloatArray r, jfloatArray g, jfloatArray b, jint w, jint rows, jint wp) {
+    hq_ctx* ctx = (hq_ctx*)(intptr_t)h;
+    jfloat* pr = (*env)->GetPrimitiveArrayCritical(env, r, NULL);
+    jfloat* pg = (*env)->GetPrimitiveArrayCritical(env, g, NULL);
+    jfloat* pb = (*env)->GetPrimitiveArrayCritical(env, b, NULL);
+    const int rc = hq_set_image_f32_planar(ctx, pr, pg, pb, w, rows, wp);
+    (*env)->ReleasePrimitiveArrayCritical(env, b, pb, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, g, pg, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, r, pr, JNI_ABORT);
+    if (rc != HQ_OK) throw_hq(env, ctx, "hq_set_image_f32_planar");
+}
+
 JNIEXPORT void JNICALL CLS(nEvalPalettes)(JNIEnv* env, jclass c, jlong h, jfloatArray pal, jint b, jint k, jint space,
                                           jlongArray errFx, jlongArray counts) {
     hq_ctx* ctx = (hq_ctx*)(intptr_t)h;

@@ -22,6 +22,11 @@ public class CudaImageManipulation implements AutoCloseable {
     /** packed u8 RGB, row-major; replaces the uploads at ImageManipulation.java:451,471-472 */
     public void setImage(byte[] rgb, int width, int rows, int whitepoint) { nSetImage(ctx, rgb, width, rows, whitepoint); }
 
+    /** the converted float image as the plugin holds it: im.getDataXYCAsFloat() (HybridQuantization.java:95-98), channels 0..2 */
+    public void setImage(float[][] dataXYC, int width, int rows, int whitepoint) {
+        nSetImageFloat(ctx, dataXYC[0], dataXYC[1], dataXYC[2], width, rows, whitepoint);
+    }
+
     /**
      * colors: [population][4*K] as SWASA.generateRandomColors lays them out (SWASA.java:42-50).
      * Returns the costs averageArray(err) + computePenalty(used) of ImageManipulation.java:712.
@@ -56,6 +61,7 @@ public class CudaImageManipulation implements AutoCloseable {
     private static native void nDestroy(long ctx);
     private static native long nPixels(long ctx);
     private static native void nSetImage(long ctx, byte[] rgb, int width, int rows, int whitepoint);
+    private static native void nSetImageFloat(long ctx, float[] r, float[] g, float[] b, int width, int rows, int whitepoint);
     private static native void nEvalPalettes(long ctx, float[] palettes, int b, int k, int space, long[] errFx, long[] counts);
     private static native void nQuantize(long ctx, float[] palette, int k, int space, byte[] outRgb);
 }

@@ -160,6 +160,23 @@ void hqo_image_planes(const uint8_t* rgb, size_t n, int whitepoint, float* unit_
     parallel_ranges(n, threads, planes_range, &c);
 }
 
+/* float image planes (HybridQuantization.java:95,98: im.getDataXYCAsFloat(), any Icy type rescaled to [0,1]) */
+typedef struct { const float* unit3; size_t n; int wp; float* lab3; } planes_f32_ctx;
+static void planes_f32_range(void* p, size_t lo, size_t hi, int tid) {
+    (void)tid;
+    planes_f32_ctx* c = (planes_f32_ctx*)p;
+    for (size_t i = lo; i < hi; ++i) {
+        const float rgb[3] = {c->unit3[i], c->unit3[c->n + i], c->unit3[2 * c->n + i]};
+        float lab[3];
+        hqo_srgb_to_lab(rgb, c->wp, lab);
+        c->lab3[i] = lab[0]; c->lab3[c->n + i] = lab[1]; c->lab3[2 * c->n + i] = lab[2];
+    }
+}
+void hqo_image_planes_f32(const float* unit3, size_t n, int whitepoint, float* lab3, int threads) {
+    planes_f32_ctx c = {unit3, n, whitepoint, lab3};
+    parallel_ranges(n, threads, planes_f32_range, &c);
+}
+
 /* ------------------------------------------------------------------ assign + reduce */
 static int64_t to_fx(float v) { return (int64_t)llrintf(v * 16777216.0f); }
 
@@ -593,12 +610,11 @@ static void pack_filters(const float* filters, int taps, float* k1, float* k2) {
 }
 
 /* S-CIELAB representation of the ORIGINAL image: sRGBToScielab (ScielabProcessor.java:374-381) */
-void hqo_scielab_image(const uint8_t* rgb, int w, int h, int whitepoint, const float* filters, const float* abs3,
-                       int taps, float* lab /*[3][n]*/, int threads) {
+/* lin: linear-light RGB [n][3] */
+static void scielab_image_lin(const float* lin, int w, int h, int whitepoint, const float* filters, const float* abs3,
+                              int taps, float* lab /*[3][n]*/, int threads) {
     const size_t n = (size_t)w * h;
     const float* ill = WHITE[whitepoint == HQO_WHITE_D50 ? 1 : 0];
-    float lin[256];
-    for (unsigned v = 0; v < 256; ++v) lin[v] = hqo_srgb_decode(hqo_u8_to_unit(v));
     float* opp = (float*)malloc(sizeof(float) * 3 * n);
     float* tmp = (float*)malloc(sizeof(float) * 3 * n);
     float* conv = (float*)malloc(sizeof(float) * 3 * n);
@@ -609,7 +625,7 @@ void hqo_scielab_image(const uint8_t* rgb, int w, int h, int whitepoint, const f
     float* k2 = (float*)malloc(sizeof(float) * 3 * taps);
     pack_filters(filters, taps, k1, k2);
     for (size_t i = 0; i < n; ++i) { /* RGB2XYZ cl:79-90 then XYZ2Opp cl:111-116 */
-        const float R = lin[rgb[3 * i]], G = lin[rgb[3 * i + 1]], B = lin[rgb[3 * i + 2]];
+        const float R = lin[3 * i], G = lin[3 * i + 1], B = lin[3 * i + 2];
         const float X = cl_dot3(CL_RGB2XYZ[0], R, G, B), Y = cl_dot3(CL_RGB2XYZ[1], R, G, B), Z = cl_dot3(CL_RGB2XYZ[2], R, G, B);
         for (int c = 0; c < 3; ++c) opp[3 * i + c] = cl_dot3(CL_XYZ2OPP[c], X, Y, Z);
         o1[i] = opp[3 * i];
@@ -628,6 +644,27 @@ void hqo_scielab_image(const uint8_t* rgb, int w, int h, int whitepoint, const f
         lab[i] = l[0]; lab[n + i] = l[1]; lab[2 * n + i] = l[2];
     }
     free(opp); free(tmp); free(conv); free(o1); free(t1); free(c1); free(k1); free(k2);
+}
+
+void hqo_scielab_image(const uint8_t* rgb, int w, int h, int whitepoint, const float* filters, const float* abs3,
+                       int taps, float* lab /*[3][n]*/, int threads) {
+    const size_t n = (size_t)w * h;
+    float tab[256];
+    for (unsigned v = 0; v < 256; ++v) tab[v] = hqo_srgb_decode(hqo_u8_to_unit(v));
+    float* lin = (float*)malloc(sizeof(float) * 3 * (n ? n : 1));
+    for (size_t i = 0; i < 3 * n; ++i) lin[i] = tab[rgb[i]];
+    scielab_image_lin(lin, w, h, whitepoint, filters, abs3, taps, lab, threads);
+    free(lin);
+}
+
+void hqo_scielab_image_f32(const float* unit3 /*[3][n]*/, int w, int h, int whitepoint, const float* filters, const float* abs3,
+                           int taps, float* lab /*[3][n]*/, int threads) {
+    const size_t n = (size_t)w * h;
+    float* lin = (float*)malloc(sizeof(float) * 3 * (n ? n : 1));
+    for (size_t i = 0; i < n; ++i)
+        for (int c = 0; c < 3; ++c) lin[3 * i + c] = hqo_srgb_decode(unit3[(size_t)c * n + i]);
+    scielab_image_lin(lin, w, h, whitepoint, filters, abs3, taps, lab, threads);
+    free(lin);
 }
 
 typedef struct {
@@ -679,10 +716,21 @@ void hqo_scielab_eval(const uint8_t* rgb, int w, int h, int whitepoint, const fl
                       const float* scielab_orig, const float* palettes, int B, int K, int space, int64_t* err_fx,
                       uint64_t* counts, int threads) {
     const size_t n = (size_t)w * h;
+    float* lab = (float*)malloc(sizeof(float) * 3 * (n ? n : 1));
+    float* unit = (float*)malloc(sizeof(float) * 3 * (n ? n : 1));
+    hqo_image_planes(rgb, n, whitepoint, unit, unit + n, unit + 2 * n, lab, lab + n, lab + 2 * n, threads);
+    hqo_scielab_eval_planes(unit, lab, w, h, whitepoint, filters, abs3, taps, scielab_orig, palettes, B, K, space, err_fx, counts, threads);
+    free(lab); free(unit);
+}
+
+void hqo_scielab_eval_planes(const float* unit3, const float* lab3, int w, int h, int whitepoint, const float* filters, const float* abs3,
+                             int taps, const float* scielab_orig, const float* palettes, int B, int K, int space, int64_t* err_fx,
+                             uint64_t* counts, int threads) {
+    const size_t n = (size_t)w * h;
     if (threads < 1) threads = 1;
     if (threads > 256) threads = 256;
     uint16_t* idx = (uint16_t*)malloc(sizeof(uint16_t) * n * B);
-    hqo_assign_reduce(rgb, n, whitepoint, palettes, B, K, space, NULL, counts, NULL, idx, threads);
+    hqo_assign_reduce_planes(unit3, lab3, n, whitepoint, palettes, B, K, space, NULL, counts, NULL, idx, threads);
     sc_ctx c; memset(&c, 0, sizeof c);
     float* k1 = (float*)malloc(sizeof(float) * 3 * taps); float* k2 = (float*)malloc(sizeof(float) * 3 * taps);
     pack_filters(filters, taps, k1, k2);

@@ -71,6 +71,9 @@ def load() -> C.CDLL:
         L.hqo_scielab_filters.restype = C.c_int; L.hqo_scielab_filters.argtypes = [C.c_int, C.c_double, _P, _P, C.c_int]
         L.hqo_scielab_image.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, C.c_int]
         L.hqo_scielab_eval.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int]
+        L.hqo_image_planes_f32.argtypes = [_P, C.c_size_t, C.c_int, _P, C.c_int]
+        L.hqo_scielab_image_f32.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, C.c_int]
+        L.hqo_scielab_eval_planes.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int]
         L.hqo_error_image.restype = C.c_double
         L.hqo_error_image.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int]
         _lib = L
@@ -98,6 +101,14 @@ def image_planes(rgb_u8: np.ndarray, whitepoint=WHITE_D65, threads=None):
     unit = np.empty((3, n), np.float32); lab = np.empty((3, n), np.float32)
     load().hqo_image_planes(_ptr(rgb), n, whitepoint, _ptr(unit[0]), _ptr(unit[1]), _ptr(unit[2]),
                             _ptr(lab[0]), _ptr(lab[1]), _ptr(lab[2]), threads or default_threads())
+    return unit, lab
+
+
+def image_planes_f32(planes: np.ndarray, whitepoint=WHITE_D65, threads=None):
+    """planes: float32 sRGB in [0,1], [3, rows, width] or [3, n] (im.getDataXYCAsFloat()); returns (unit [3,n], lab [3,n])"""
+    unit = np.ascontiguousarray(planes, np.float32).reshape(3, -1)
+    lab = np.empty_like(unit)
+    load().hqo_image_planes_f32(_ptr(unit), unit.shape[1], whitepoint, _ptr(lab), threads or default_threads())
     return unit, lab
 
 
@@ -194,6 +205,32 @@ def scielab_eval(rgb_u8, filters, abs3, scielab_orig, palettes, space=SPACE_SRGB
     so = np.ascontiguousarray(scielab_orig, np.float32)
     load().hqo_scielab_eval(_ptr(rgb), w, h, whitepoint, _ptr(filters), _ptr(abs3), filters.shape[1], _ptr(so), _ptr(palettes), B, K, space,
                             _ptr(err), _ptr(counts), threads or default_threads())
+    return {"err_fx": err, "counts": counts}
+
+
+def scielab_image_f32(planes, filters, abs3, whitepoint=WHITE_D65, threads=None) -> np.ndarray:
+    """planes: float32 [3, rows, width]"""
+    unit = np.ascontiguousarray(planes, np.float32)
+    _, h, w = unit.shape
+    lab = np.empty((3, h * w), np.float32)
+    filters = np.ascontiguousarray(filters, np.float32); abs3 = np.ascontiguousarray(abs3, np.float32)
+    load().hqo_scielab_image_f32(_ptr(unit), w, h, whitepoint, _ptr(filters), _ptr(abs3), filters.shape[1], _ptr(lab), threads or default_threads())
+    return lab
+
+
+def scielab_eval_f32(planes, filters, abs3, scielab_orig, palettes, space=SPACE_SRGB, whitepoint=WHITE_D65, threads=None):
+    unit = np.ascontiguousarray(planes, np.float32)
+    _, h, w = unit.shape
+    _, lab = image_planes_f32(unit, whitepoint, threads)
+    palettes = np.ascontiguousarray(palettes, np.float32)
+    if palettes.ndim == 2:
+        palettes = palettes[None]
+    B, K, _ = palettes.shape
+    err = np.empty(B, np.int64); counts = np.empty((B, K), np.uint64)
+    filters = np.ascontiguousarray(filters, np.float32); abs3 = np.ascontiguousarray(abs3, np.float32)
+    so = np.ascontiguousarray(scielab_orig, np.float32)
+    load().hqo_scielab_eval_planes(_ptr(unit), _ptr(lab), w, h, whitepoint, _ptr(filters), _ptr(abs3), filters.shape[1], _ptr(so), _ptr(palettes),
+                                   B, K, space, _ptr(err), _ptr(counts), threads or default_threads())
     return {"err_fx": err, "counts": counts}
 
 

@@ -21,6 +21,7 @@ jlong CLS(nCreate)(JNIEnv*, jclass, jint);
 void CLS(nDestroy)(JNIEnv*, jclass, jlong);
 jlong CLS(nPixels)(JNIEnv*, jclass, jlong);
 void CLS(nSetImage)(JNIEnv*, jclass, jlong, jbyteArray, jint, jint, jint);
+void CLS(nSetImageFloat)(JNIEnv*, jclass, jlong, jfloatArray, jfloatArray, jfloatArray, jint, jint, jint);
 void CLS(nEvalPalettes)(JNIEnv*, jclass, jlong, jfloatArray, jint, jint, jint, jlongArray, jlongArray);
 void CLS(nQuantize)(JNIEnv*, jclass, jlong, jfloatArray, jint, jint, jbyteArray);
 
@@ -63,6 +64,16 @@ int main(int argc, char** argv) {
     if (g_thrown) { fprintf(stderr, "nQuantize threw: %s\n", g_msg); return 2; }
     unsigned long long hash = 0;
     for (size_t j = 0; j < n * 3; ++j) hash = hash * 1099511628211ULL + out[j];
+    /* the same image as the plugin's float planes (c/255, HybridQuantization.java:95-98): same integers expected */
+    float* planes = malloc(n * 3 * sizeof(float));
+    for (size_t j = 0; j < n; ++j)
+        for (int c = 0; c < 3; ++c) planes[(size_t)c * n + j] = (float)(rgb[3 * j + c] / 255.0);
+    jlong* errf = calloc((size_t)B, sizeof(jlong));
+    struct _jobject a_r = {planes}, a_g = {planes + n}, a_b = {planes + 2 * n}, a_errf = {errf};
+    CLS(nSetImageFloat)(env, &g_class, ctx, &a_r, &a_g, &a_b, w, h, 0);
+    if (g_thrown) { fprintf(stderr, "nSetImageFloat threw: %s\n", g_msg); return 2; }
+    CLS(nEvalPalettes)(env, &g_class, ctx, &a_pal, B, K, 0, &a_errf, &a_cnt);
+    if (g_thrown) { fprintf(stderr, "nEvalPalettes (float image) threw: %s\n", g_msg); return 2; }
     /* error path: K beyond the limit must surface as a Java exception, not as silence */
     CLS(nEvalPalettes)(env, &g_class, ctx, &a_pal, 1, 100000, 0, &a_err, &a_cnt);
     const int threw_on_bad_k = g_thrown;
@@ -70,6 +81,8 @@ int main(int argc, char** argv) {
 
     printf("{\"pixels\": %lld, \"image_hash\": %llu, \"threw_on_bad_k\": %d, \"err_fx\": [", (long long)px, hash, threw_on_bad_k);
     for (int b = 0; b < B; ++b) printf("%s%lld", b ? ", " : "", (long long)err[b]);
+    printf("], \"err_fx_float_image\": [");
+    for (int b = 0; b < B; ++b) printf("%s%lld", b ? ", " : "", (long long)errf[b]);
     printf("], \"counts\": [");
     for (int i = 0; i < B * K; ++i) printf("%s%lld", i ? ", " : "", (long long)cnt[i]);
     printf("]}\n");

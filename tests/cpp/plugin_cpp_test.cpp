@@ -38,6 +38,16 @@ int main(int argc, char** argv) {
         printf("{\"best_error\": \"%a\", \"image_hash\": %llu, \"best_colors\": [", bestError, sum);
         for (size_t i = 0; i < best.size(); ++i) printf("%s\"%a\"", i ? ", " : "", best[i]);
         printf("], ");
+        {   // the same search fed with the plugin's own float planes (c/255, HybridQuantization.java:95-98)
+            const size_t n = (size_t)w * h;
+            std::vector<float> planes(3 * n);
+            for (size_t j = 0; j < n; ++j)
+                for (int c = 0; c < 3; ++c) planes[(size_t)c * n + j] = (float)(rgb[3 * j + c] / 255.0);
+            std::vector<uint8_t> out2(rgb.size());
+            double err2 = 0;
+            const std::vector<float> best2 = plugin.quantization(planes.data(), planes.data() + n, planes.data() + 2 * n, w, h, out2.data(), &err2);
+            printf("\"float_image_same\": %d, ", (int)(best2 == best && out2 == out && err2 == bestError));
+        }
         // class-level API: SWASA draws + one population evaluation
         hq::JavaRandom rnd(77760);
         hq::SWASA swasa(4, 5000, 20, 2.0f, 0.75f, 0.15f, 20.0f, 0.9f, 100.0f, 5.3f, &rnd);

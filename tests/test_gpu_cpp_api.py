@@ -28,6 +28,7 @@ def test_cpp_plugin_end_to_end(oracle, hqlib, tmp_path, w, h, K, imax):
     p = oracle.swasa_params(population=4, imax=imax, seed=4242)
     obest, oerr, _ = oracle.find_best_quantization(img, K, p, threads=THREADS)
     assert float.fromhex(got["best_error"]) == oerr
+    assert got["float_image_same"] == 1   # quantization(float planes) == quantization(u8)
     assert np.array_equal(np.array([float.fromhex(x) for x in got["best_colors"]], np.float32).view(np.uint32), obest.reshape(-1).view(np.uint32))
     q = oracle.quantize(img, obest)["rgb"].reshape(-1)
     hsh = 0
@@ -62,6 +63,7 @@ def test_jni_shim_through_a_fake_jnienv(oracle, hqlib, tmp_path):
     want = oracle.assign_reduce(img, pal, threads=THREADS)
     assert got["pixels"] == w * h and got["threw_on_bad_k"] == 1
     assert got["err_fx"] == [int(v) for v in want["err_fx"]]
+    assert got["err_fx_float_image"] == got["err_fx"]   # nSetImageFloat with the c/255 planes
     assert got["counts"] == [int(v) for v in want["counts"].reshape(-1)]
     q = oracle.quantize(img, pal[0])["rgb"].reshape(-1)
     hsh = 0

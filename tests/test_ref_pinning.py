@@ -77,6 +77,29 @@ def test_java_srgb_to_lab_float_colours(oracle, ref):
     assert np.array_equal(bits(got[:, :3000].T.copy()), bits(want))
 
 
+def test_java_srgb_to_lab_16bit_image_planes(oracle, ref):
+    """a 16-bit Icy image after the rescaling conversion (c/65535, HybridQuantization.java:95): the float-image entry of the
+    oracle (hqo_image_planes_f32, what hq_set_image_f32_planar is held to) == the compiled Java helpers, both white points"""
+    rng = np.random.default_rng(16)
+    c = rng.integers(0, 65536, (3, 1 << 18), dtype=np.uint32)
+    c[:, :8] = [0, 1, 2650, 2651, 2652, 32768, 65534, 65535]
+    planes = (c.astype(np.float64) / 65535.0).astype(np.float32)
+    for d50 in (False, True):
+        want = oracle.image_planes_f32(planes, oracle.WHITE_D50 if d50 else oracle.WHITE_D65)[1]
+        assert np.array_equal(bits(ref.srgb_to_lab_java(planes, d50)), bits(want))
+
+
+def test_scielab_of_a_float_image(oracle, ref):
+    """XYZtoScielab(RGBtoXYZ(.)) on float planes (what the plugin passes, :374-381) == the oracle's float-image entry"""
+    rng = np.random.default_rng(17)
+    w, h = 41, 29
+    planes = (rng.integers(0, 65536, (3, h, w)).astype(np.float64) / 65535.0).astype(np.float32)
+    f, a = oracle.scielab_filters()
+    got = ref.xyz_to_scielab(ref.rgb_to_xyz(planes.reshape(3, -1)), ref.pack_filters(f, a), w, ref.D65)
+    want = oracle.scielab_image_f32(planes, f, a)
+    assert np.array_equal(bits(got[:, :3].T.copy()), bits(want))
+
+
 # ---------------------------------------------------------------- filter bank (ScielabProcessor ctor)
 @pytest.mark.parametrize("dpi,vd", [(72, 45.0), (96, 50.0), (150, 30.0), (300, 60.0), (20, 100.0), (600, 20.0), (224, 57.0)])
 def test_filter_bank(oracle, ref, dpi, vd):
