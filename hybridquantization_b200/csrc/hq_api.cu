@@ -673,7 +673,7 @@ static int sc_ensure_image(hq_ctx* c) {
     HQ_CUDA(c, c->d_sc_opp.reserve(3 * c->stride));
     HQ_CUDA(c, c->d_sc_tmp.reserve(7 * c->stride));
     HQ_CUDA(c, c->d_sc_lab.reserve(3 * c->stride));
-    if (c->image_f32) HQ_CUDA(c, hq::launch_sc_unit_to_opp(c->d_unit.p, c->n, c->stride, c->d_sc_opp.p, c->stream));
+    if (c->image_f32) HQ_CUDA(c, hq::launch_sc_unit_to_opp(c->d_unit.p, c->n, c->stride, c->d_sc_opp.p, nullptr, c->stream));  // range checked at upload
     else HQ_CUDA(c, hq::launch_sc_rgb_to_opp(c->d_rgb.p, c->n, c->stride, c->d_table.p, c->d_sc_opp.p, c->stream));
     HQ_CUDA(c, hq::launch_sc_original(c->d_sc_opp.p, c->width, c->rows, c->stride, c->d_sc_filters.p, c->sc_generic ? nullptr : c->sc_block.data(), c->sc_taps,
                                       c->whitepoint, sc_rows(c), c->d_sc_tmp.p, c->d_sc_lab.p, c->stream));
@@ -693,19 +693,32 @@ int hq_scielab_get_image(hq_ctx* c, float* planes) {
 }
 
 // error-image mode: HybridQuantization.errorImage (:139-182) + ImageManipulation.computeError (:858-894)
-int hq_error_image(hq_ctx* c, const uint8_t* quantized_rgb, float* error_map, uint8_t* error_map_u8, double* mean_de) {
-    if (!c || !quantized_rgb) return c ? fail(c, HQ_ERR_INVALID, "quantized_rgb is NULL") : HQ_ERR_INVALID;
+namespace {
+// the second image of error-image mode, as packed u8 (rgb8) or as float planes (f32[3])
+int error_image_common(hq_ctx* c, const uint8_t* rgb8, const float* const* f32, float* error_map, uint8_t* error_map_u8, double* mean_de) {
     int rc = bind_device(c); if (rc) return rc;
     rc = sc_ensure_image(c); if (rc) return rc;
     const size_t n = c->n;
-    HQ_CUDA(c, c->d_sc_rgb2.reserve(n * 3 > 0 ? n * 3 : 1));
     HQ_CUDA(c, c->d_sc_lab2.reserve(3 * c->stride));
     HQ_CUDA(c, c->d_sc_err.reserve(1));
     if (error_map) HQ_CUDA(c, c->d_sc_map.reserve(n ? n : 1));
     if (error_map_u8) HQ_CUDA(c, c->d_sc_map8.reserve(n ? n : 1));
-    HQ_CUDA(c, cudaMemcpyAsync(c->d_sc_rgb2.p, quantized_rgb, n * 3, cudaMemcpyHostToDevice, c->stream));
     // S-CIELAB of the second image through the same route as the original (sRGBToScielab, ScielabProcessor.java:374-381)
-    HQ_CUDA(c, hq::launch_sc_rgb_to_opp(c->d_sc_rgb2.p, n, c->stride, c->d_table.p, c->d_sc_opp.p, c->stream));
+    if (rgb8) {
+        HQ_CUDA(c, c->d_sc_rgb2.reserve(n * 3 > 0 ? n * 3 : 1));
+        HQ_CUDA(c, cudaMemcpyAsync(c->d_sc_rgb2.p, rgb8, n * 3, cudaMemcpyHostToDevice, c->stream));
+        HQ_CUDA(c, hq::launch_sc_rgb_to_opp(c->d_sc_rgb2.p, n, c->stride, c->d_table.p, c->d_sc_opp.p, c->stream));
+    } else {  // the planes land in the opponent buffer and are converted in place (element-wise kernel)
+        HQ_CUDA(c, c->d_flag.reserve(1));
+        HQ_CUDA(c, cudaMemsetAsync(c->d_flag.p, 0, sizeof(unsigned int), c->stream));
+        for (int pl = 0; pl < 3 && n; ++pl)
+            HQ_CUDA(c, cudaMemcpyAsync(c->d_sc_opp.p + (size_t)pl * c->stride, f32[pl], n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        HQ_CUDA(c, hq::launch_sc_unit_to_opp(c->d_sc_opp.p, n, c->stride, c->d_sc_opp.p, c->d_flag.p, c->stream));
+        unsigned int bad = 0;
+        HQ_CUDA(c, cudaMemcpyAsync(&bad, c->d_flag.p, sizeof bad, cudaMemcpyDeviceToHost, c->stream));
+        HQ_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (bad) return fail(c, HQ_ERR_INVALID, "float image values must lie in [0,1] (Icy's rescaled convertToType, HybridQuantization.java:142-143)");
+    }
     HQ_CUDA(c, hq::launch_sc_original(c->d_sc_opp.p, c->width, c->rows, c->stride, c->d_sc_filters.p, c->sc_generic ? nullptr : c->sc_block.data(),
                                       c->sc_taps, c->whitepoint, sc_rows(c), c->d_sc_tmp.p, c->d_sc_lab2.p, c->stream));
     HQ_CUDA(c, cudaMemsetAsync(c->d_sc_err.p, 0, 8, c->stream));
@@ -722,6 +735,18 @@ int hq_error_image(hq_ctx* c, const uint8_t* quantized_rgb, float* error_map, ui
     const double n_div = c->allreduce ? n_all : (double)no;
     if (mean_de) *mean_de = n_div > 0 ? ((double)(int64_t)sum * (1.0 / 16777216.0)) / n_div : 0.0;  // :893 error/errorArray.length
     return HQ_OK;
+}
+}  // namespace
+
+int hq_error_image(hq_ctx* c, const uint8_t* quantized_rgb, float* error_map, uint8_t* error_map_u8, double* mean_de) {
+    if (!c || !quantized_rgb) return c ? fail(c, HQ_ERR_INVALID, "quantized_rgb is NULL") : HQ_ERR_INVALID;
+    return error_image_common(c, quantized_rgb, nullptr, error_map, error_map_u8, mean_de);
+}
+
+int hq_error_image_f32_planar(hq_ctx* c, const float* r, const float* g, const float* b, float* error_map, uint8_t* error_map_u8, double* mean_de) {
+    if (!c || !r || !g || !b) return c ? fail(c, HQ_ERR_INVALID, "an image plane is NULL") : HQ_ERR_INVALID;
+    const float* planes[3] = {r, g, b};
+    return error_image_common(c, nullptr, planes, error_map, error_map_u8, mean_de);
 }
 
 int hq_eval_palettes_scielab(hq_ctx* c, const float* palettes, int B, int K, int space, int64_t* err_fx, uint64_t* counts) {

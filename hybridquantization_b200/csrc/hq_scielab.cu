@@ -32,10 +32,14 @@ __global__ void sc_rgb_to_opp_kernel(const uint8_t* __restrict__ rgb, size_t n, 
 }
 
 // the same for a planar float image: decoded per value, as the reference's RGB2XYZ kernel does (cl:79-90)
-__global__ void sc_unit_to_opp_kernel(const float* __restrict__ unit, size_t n, size_t stride, float* __restrict__ opp) {
+// (unit and opp may be the same buffer: element-wise; bad, when given, reports values outside [0,1])
+__global__ void sc_unit_to_opp_kernel(const float* unit, size_t n, size_t stride, float* opp, unsigned int* __restrict__ bad) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const hq_float3 o = hq_cl_linrgb_to_opp_via_xyz(hq_srgb_decode(unit[i]), hq_srgb_decode(unit[stride + i]), hq_srgb_decode(unit[2 * stride + i]));
+    const float r = unit[i], g = unit[stride + i], b = unit[2 * stride + i];
+    hq_float3 o; o.x = o.y = o.z = 0.f;
+    if (!bad || (r >= 0.f && r <= 1.f && g >= 0.f && g <= 1.f && b >= 0.f && b <= 1.f)) o = hq_cl_linrgb_to_opp_via_xyz(hq_srgb_decode(r), hq_srgb_decode(g), hq_srgb_decode(b));
+    else atomicOr(bad, 1u);
     opp[i] = o.x; opp[stride + i] = o.y; opp[2 * stride + i] = o.z;
 }
 
@@ -319,9 +323,9 @@ cudaError_t launch_sc_palette_opp(const float* d_palettes, int total, float4* d_
     return cudaGetLastError();
 }
 
-cudaError_t launch_sc_unit_to_opp(const float* d_unit, size_t n, size_t stride, float* d_opp, cudaStream_t st) {
+cudaError_t launch_sc_unit_to_opp(const float* d_unit, size_t n, size_t stride, float* d_opp, unsigned int* d_bad, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    sc_unit_to_opp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_unit, n, stride, d_opp);
+    sc_unit_to_opp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_unit, n, stride, d_opp, d_bad);
     return cudaGetLastError();
 }
 

@@ -331,6 +331,18 @@ class ImageManipulation:
     def requestStop(self) -> None:
         self._lib.hq_request_stop(self._ctx)
 
+    def computeErrorFloat(self, planes: np.ndarray) -> dict:
+        """computeError with the second image as float planes [3, rows, width] in [0,1] (HybridQuantization.java:142-143)"""
+        p = np.ascontiguousarray(planes, np.float32)
+        if p.ndim != 3 or p.shape[0] < 3 or p.shape[1] * p.shape[2] != self._local_pixels:
+            raise ValueError("Mismatching image sizes or not enough channels, abort.")  # HybridQuantization.java:81
+        emap = np.empty(self.pixels(), np.float32); e8 = np.empty(self.pixels(), np.uint8)
+        mean = C.c_double()
+        _lib.check(self._ctx, self._lib.hq_error_image_f32_planar(self._ctx, _ptr(p[0]), _ptr(p[1]), _ptr(p[2]), _ptr(emap), _ptr(e8), C.byref(mean)))
+        if self.shape is not None:
+            emap, e8 = emap.reshape(self.shape), e8.reshape(self.shape)
+        return {"deltaE": mean.value, "errorImage": emap, "errorImageU8": e8}
+
     def quantize(self, colors: np.ndarray, space: int = SPACE_LAB, want_f32: bool = False) -> dict:
         """ImageManipulation.java:770-798 -> packed u8 image, indices, optionally the float RGBA image."""
         colors = np.ascontiguousarray(colors, np.float32)
@@ -366,7 +378,11 @@ class ScielabProcessor:
         self.imageProcessing = imageProcessor
 
     def sRGBToScielab(self, rgb: np.ndarray) -> None:
-        self.imageProcessing.setImage(rgb, self.whitepoint)
+        """uint8 [rows, width, 3], or the plugin's float planes [3, rows, width] in [0,1] (float[][] sRGBImage, :374)"""
+        if np.asarray(rgb).dtype == np.uint8:
+            self.imageProcessing.setImage(rgb, self.whitepoint)
+        else:
+            self.imageProcessing.setImageFloat(rgb, self.whitepoint)
 
     def bestColors(self, nbOfColors: int, simulatedAnnealing: SWASA, n_total: int = 0):
         return self.imageProcessing.findBestQuantization(nbOfColors, simulatedAnnealing, n_total)
@@ -409,13 +425,15 @@ class HybridQuantization:
             raise ValueError("Please open/select the original image first.")  # :76-77
         if quantized is None or quantized.size == 0:
             raise ValueError("Please open/select the quantized image first.")  # :78-79
-        if original.shape != quantized.shape or original.shape[-1] < 3:
+        planar = original.dtype != np.uint8  # float planes [3, rows, width] (both converted to FLOAT, :142-143) or u8 [rows, width, 3]
+        if original.shape != quantized.shape or original.dtype != quantized.dtype or original.shape[0 if planar else -1] < 3:
             raise ValueError("Mismatching image sizes or not enough channels, abort.")  # :80-81
         imageProcessor = ImageManipulation("CIE76", self.Verbose, False, self.device)  # :145
         try:
-            imageProcessor.setImage(original, WHITEPOINT_D50 if self.WhitePoint == "D50" else WHITEPOINT_D65)
+            wp = WHITEPOINT_D50 if self.WhitePoint == "D50" else WHITEPOINT_D65
+            imageProcessor.setImageFloat(original, wp) if planar else imageProcessor.setImage(original, wp)
             imageProcessor.scielabConfigure(self.dpi, self.ViewingDistance)  # :146
-            return imageProcessor.computeError(quantized)  # :153,160
+            return imageProcessor.computeErrorFloat(quantized) if planar else imageProcessor.computeError(quantized)  # :153,160
         finally:
             imageProcessor.close()
 
@@ -424,6 +442,7 @@ class HybridQuantization:
                      self.alpha, self.s0, self.beta, seed=self.seed, convergence=self.ConvEnable, space=self.space, costModel=self.costModel)
 
     def quantization(self, rgb: np.ndarray) -> dict:
+        """rgb: uint8 [rows, width, 3], or float32 planes [3, rows, width] in [0,1] (im.getDataXYCAsFloat(), :95-98)"""
         if rgb is None or rgb.size == 0:
             raise ValueError("Please open an image first.")  # :65-67
         imageProcessor = ImageManipulation("CIE76", self.Verbose, self.ConvEnable, self.device)  # :96

@@ -177,6 +177,9 @@ int hq_scielab_get_image(hq_ctx* ctx, float* planes);
  * the resident image's size.  error_map [n] = ((255 - dE)^2)/(255*255) (:890), error_map_u8 [n] its
  * 8-bit rendering, *mean_de = mean dE between the two S-CIELAB images.  Outputs may be NULL. */
 int hq_error_image(hq_ctx* ctx, const uint8_t* quantized_rgb, float* error_map, uint8_t* error_map_u8, double* mean_de);
+/* the second image as float planes in [0,1] (errorImage converts both sequences to FLOAT, HybridQuantization.java:142-143) */
+int hq_error_image_f32_planar(hq_ctx* ctx, const float* r, const float* g, const float* b, float* error_map, uint8_t* error_map_u8,
+                              double* mean_de);
 /* test hook: 1 = always run the generic any-tap-count kernels instead of the 21-tap specialisation */
 int hq_scielab_force_generic(hq_ctx* ctx, int enabled);
 /* host only (no GPU needed): the filter bank for (dpi, viewing distance); *taps as above */

@@ -757,12 +757,7 @@ void hqo_scielab_eval_planes(const float* unit3, const float* lab3, int w, int h
 }
 
 /* error-image mode: ImageManipulation.computeError (:858-894) on two S-CIELAB images */
-double hqo_error_image(const uint8_t* rgb_a, const uint8_t* rgb_b, int w, int h, int whitepoint, const float* filters, const float* abs3,
-                       int taps, float* error_map, uint8_t* error_map_u8, int threads) {
-    const size_t n = (size_t)w * h;
-    float* la = (float*)malloc(sizeof(float) * 3 * n); float* lb = (float*)malloc(sizeof(float) * 3 * n);
-    hqo_scielab_image(rgb_a, w, h, whitepoint, filters, abs3, taps, la, threads);
-    hqo_scielab_image(rgb_b, w, h, whitepoint, filters, abs3, taps, lb, threads);
+static double error_image_of_labs(const float* la, const float* lb, size_t n, float* error_map, uint8_t* error_map_u8) {
     int64_t sum = 0;
     for (size_t i = 0; i < n; ++i) {
         const float e = sqrtf(dist2(la[i], la[n + i], la[2 * n + i], lb[i], lb[n + i], lb[2 * n + i])); /* cl:209 */
@@ -772,8 +767,30 @@ double hqo_error_image(const uint8_t* rgb_a, const uint8_t* rgb_b, int w, int h,
         if (error_map_u8) { float q = v * 255.0f + 0.5f; q = q < 0 ? 0 : (q > 255 ? 255 : q); error_map_u8[i] = (uint8_t)(int)q; }
         sum += to_fx(e);
     }
-    free(la); free(lb);
     return n ? ((double)sum * (1.0 / 16777216.0)) / (double)n : 0.0;
+}
+
+double hqo_error_image(const uint8_t* rgb_a, const uint8_t* rgb_b, int w, int h, int whitepoint, const float* filters, const float* abs3,
+                       int taps, float* error_map, uint8_t* error_map_u8, int threads) {
+    const size_t n = (size_t)w * h;
+    float* la = (float*)malloc(sizeof(float) * 3 * n); float* lb = (float*)malloc(sizeof(float) * 3 * n);
+    hqo_scielab_image(rgb_a, w, h, whitepoint, filters, abs3, taps, la, threads);
+    hqo_scielab_image(rgb_b, w, h, whitepoint, filters, abs3, taps, lb, threads);
+    const double mean = error_image_of_labs(la, lb, n, error_map, error_map_u8);
+    free(la); free(lb);
+    return mean;
+}
+
+/* both images as float planes (errorImage converts both sequences to FLOAT, HybridQuantization.java:142-143) */
+double hqo_error_image_f32(const float* unit3_a, const float* unit3_b, int w, int h, int whitepoint, const float* filters, const float* abs3,
+                           int taps, float* error_map, uint8_t* error_map_u8, int threads) {
+    const size_t n = (size_t)w * h;
+    float* la = (float*)malloc(sizeof(float) * 3 * n); float* lb = (float*)malloc(sizeof(float) * 3 * n);
+    hqo_scielab_image_f32(unit3_a, w, h, whitepoint, filters, abs3, taps, la, threads);
+    hqo_scielab_image_f32(unit3_b, w, h, whitepoint, filters, abs3, taps, lb, threads);
+    const double mean = error_image_of_labs(la, lb, n, error_map, error_map_u8);
+    free(la); free(lb);
+    return mean;
 }
 
 /* ------------------------------------------------------------------ range evaluation (tests) */

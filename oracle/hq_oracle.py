@@ -74,6 +74,8 @@ def load() -> C.CDLL:
         L.hqo_image_planes_f32.argtypes = [_P, C.c_size_t, C.c_int, _P, C.c_int]
         L.hqo_scielab_image_f32.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, C.c_int]
         L.hqo_scielab_eval_planes.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int]
+        L.hqo_error_image_f32.restype = C.c_double
+        L.hqo_error_image_f32.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int]
         L.hqo_error_image.restype = C.c_double
         L.hqo_error_image.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int]
         _lib = L
@@ -241,4 +243,15 @@ def error_image(rgb_a, rgb_b, filters, abs3, whitepoint=WHITE_D65, threads=None)
     filters = np.ascontiguousarray(filters, np.float32); abs3 = np.ascontiguousarray(abs3, np.float32)
     mean = load().hqo_error_image(_ptr(a), _ptr(b), w, h, whitepoint, _ptr(filters), _ptr(abs3), filters.shape[1], _ptr(emap), _ptr(e8),
                                   threads or default_threads())
+    return {"deltaE": mean, "errorImage": emap, "errorImageU8": e8}
+
+
+def error_image_f32(planes_a, planes_b, filters, abs3, whitepoint=WHITE_D65, threads=None):
+    """both images as float planes [3, rows, width]"""
+    a = np.ascontiguousarray(planes_a, np.float32); b = np.ascontiguousarray(planes_b, np.float32)
+    _, h, w = a.shape
+    emap = np.empty(h * w, np.float32); e8 = np.empty(h * w, np.uint8)
+    filters = np.ascontiguousarray(filters, np.float32); abs3 = np.ascontiguousarray(abs3, np.float32)
+    mean = load().hqo_error_image_f32(_ptr(a), _ptr(b), w, h, whitepoint, _ptr(filters), _ptr(abs3), filters.shape[1], _ptr(emap), _ptr(e8),
+                                      threads or default_threads())
     return {"deltaE": mean, "errorImage": emap, "errorImageU8": e8}

@@ -136,6 +136,39 @@ def test_search_on_a_float_image_equals_the_u8_search(backend):
     assert a[1] == b[1] and np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32))
 
 
+def test_plugin_entry_points_take_float_planes(hqlib):
+    from hybridquantization_b200 import HybridQuantization
+    img = synth.synth_image(96, 64, 5)
+    planes = np.ascontiguousarray((img.astype(np.float64) / 255.0).astype(np.float32).transpose(2, 0, 1))
+    hq = HybridQuantization(nbOfColors=8, imax=60, seed=4242)
+    a = dict(hq.quantization(img)); b = dict(hq.quantization(planes))
+    assert a["bestError"] == b["bestError"] and np.array_equal(a["image"], b["image"]) and np.array_equal(a["bestColors"].view(np.uint32), b["bestColors"].view(np.uint32))
+    qp = np.ascontiguousarray((a["image"].astype(np.float64) / 255.0).astype(np.float32).transpose(2, 0, 1))
+    assert hq.errorImage(img, a["image"])["deltaE"] == hq.errorImage(planes, qp)["deltaE"]
+
+
+def test_error_image_mode_on_float_images(backend, oracle):
+    a = u16_planes(120, 64, 1)
+    b = np.clip(a + np.random.default_rng(2).normal(0, 0.02, a.shape).astype(np.float32), 0, 1).astype(np.float32)
+    backend.setImageFloat(a)
+    backend.scielabConfigure(72, 45.0)
+    got = backend.computeErrorFloat(b)
+    of, oa = oracle.scielab_filters(72, 45.0)
+    want = oracle.error_image_f32(a, b, of, oa, 0, THREADS)
+    assert got["deltaE"] == want["deltaE"] and got["deltaE"] > 0
+    assert np.array_equal(got["errorImage"].reshape(-1).view(np.uint32), want["errorImage"].view(np.uint32))
+    assert np.array_equal(got["errorImageU8"].reshape(-1), want["errorImageU8"])
+    # a u8 second image through either entry: same result
+    img = synth.synth_image(120, 64, 3)
+    p8 = np.ascontiguousarray((img.astype(np.float64) / 255.0).astype(np.float32).transpose(2, 0, 1))
+    r8, rf = backend.computeError(img), backend.computeErrorFloat(p8)
+    assert r8["deltaE"] == rf["deltaE"] and np.array_equal(r8["errorImageU8"], rf["errorImageU8"])
+    bad = b.copy(); bad[2, 5, 5] = 1.5
+    with pytest.raises(HqError):
+        backend.computeErrorFloat(bad)
+    assert backend.computeErrorFloat(b)["deltaE"] == want["deltaE"]   # the context survives the refusal
+
+
 @pytest.mark.parametrize("bad", [1.0000001, -1e-9, float("nan"), float("inf")])
 def test_values_outside_the_unit_interval_are_refused(hqlib, bad):
     be = ImageManipulation("CIE76", False, True, 0)
