@@ -81,6 +81,9 @@ struct hq_ctx {
     DevBuf<float> d_out_f32;
     PinBuf<float> h_pal;
     PinBuf<unsigned long long> h_results;
+    PinBuf<unsigned long long> h_flag;      // sequence number written by export_results_kernel after the result words
+    unsigned long long export_seq = 0;
+    bool direct_io = true;                  // HQ_DIRECT_IO=0: the H2D copy / D2H copy / stream wait path instead (A/B measurements)
 
     // exact pruning (hq_pruned.cu): cell-sorted copy of the own pixels, chunk table, boxes; built on first use per image
     int prune_mode = HQ_PRUNE_AUTO;
@@ -169,6 +172,19 @@ cudaError_t wait_stream(cudaStream_t st) {
             if (e != cudaErrorNotReady) return e;
         }
         if (clock::now() - t0 > std::chrono::milliseconds(8)) return cudaStreamSynchronize(st);
+    }
+}
+
+// Spin on the sequence number export_results_kernel writes into pinned host memory after the result words; the stream is
+// queried now and then so that a failed launch surfaces as an error instead of a hang.
+cudaError_t wait_flag(const unsigned long long* flag, unsigned long long seq, cudaStream_t st) {
+    const volatile unsigned long long* f = flag;
+    for (;;) {
+        for (int i = 0; i < 2048; ++i)
+            if (*f == seq) return cudaSuccess;
+        const cudaError_t e = cudaStreamQuery(st);
+        if (e == cudaSuccess) return *f == seq ? cudaSuccess : cudaErrorUnknown;
+        if (e != cudaErrorNotReady) return e;
     }
 }
 
@@ -322,11 +338,16 @@ int hq_create(int device, hq_ctx** out) {
         delete c;
         return fail(nullptr, HQ_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     }
-    if ((e = c->d_table.reserve(512)) != cudaSuccess || (e = hq::launch_decode_table(c->d_table.p, c->stream)) != cudaSuccess ||
+    if ((e = c->h_flag.reserve(1)) == cudaSuccess) c->h_flag.p[0] = 0ull;
+    if (e != cudaSuccess || (e = c->d_table.reserve(512)) != cudaSuccess || (e = hq::launch_decode_table(c->d_table.p, c->stream)) != cudaSuccess ||
         (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) {
         cudaStreamDestroy(c->stream);
         delete c;
         return fail(nullptr, HQ_ERR_CUDA, "device %d: decode table kernel failed: %s (is the library built for this GPU?)", device, cudaGetErrorString(e));
+    }
+    {
+        const char* d = std::getenv("HQ_DIRECT_IO");
+        c->direct_io = !(d && d[0] == '0');
     }
     {   // HQ_CUDA_GRAPHS=1 turns hq_set_graphs on for every new context
         const char* g = std::getenv("HQ_CUDA_GRAPHS");
@@ -350,7 +371,7 @@ void hq_destroy(hq_ctx* c) {
     if (c->ev3) cudaEventDestroy(c->ev3);
     c->d_rgb.release(); c->d_flag.release(); c->d_lab.release(); c->d_unit.release(); c->d_table.release(); c->d_pal.release();
     c->d_pal_lab.release(); c->d_pal_rgb.release(); c->d_results.release(); c->d_idx.release();
-    c->d_out_rgb.release(); c->d_out_f32.release(); c->h_pal.release(); c->h_results.release();
+    c->d_out_rgb.release(); c->d_out_f32.release(); c->h_pal.release(); c->h_results.release(); c->h_flag.release();
     c->d_sc_filters.release(); c->d_sc_opp.release(); c->d_sc_tmp.release(); c->d_sc_lab.release(); c->d_sc_tab.release(); c->d_sc_err.release();
     c->d_sc_lab2.release(); c->d_sc_map.release(); c->d_sc_rgb2.release(); c->d_sc_map8.release();
     c->pr_own.release(); c->pr_all.release(); c->d_pr_scratch.release();
@@ -498,11 +519,20 @@ int hq_eval_palettes(hq_ctx* c, const float* palettes, int B, int K, int space, 
         // first call with this signature: plain launches (also configures the kernels); second: captured into a graph
         const bool capture = graphable && key == c->seen_key;
         c->seen_key = key;
+        if (!graphable && c->direct_io) {
+            // Latency path (a search iteration is four dependent stream operations; this makes it two): the palette kernel reads
+            // the pinned host copy directly (UVA: a cudaMallocHost pointer is device-accessible) and a one-CTA kernel writes the
+            // result words plus a sequence number back into pinned host memory, which the host spins on.
+            rc = eval_device(c, c->h_pal.p, B, K, space, flags, c->d_results.p, nullptr, c->stream); if (rc) return rc;
+            if (c->allreduce && c->allreduce(c->allreduce_user, c->d_results.p, nwords, c->stream) != 0) return fail(c, HQ_ERR_CALLBACK, "all-reduce hook failed");
+            const unsigned long long seq = ++c->export_seq;
+            HQ_CUDA(c, hq::launch_export_results(c->d_results.p, c->h_results.p, nwords, c->h_flag.p, seq, c->stream));
+            HQ_CUDA(c, wait_flag(c->h_flag.p, seq, c->stream));
+            goto unpack;
+        }
         if (capture) HQ_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         cudaError_t e = cudaMemcpyAsync(c->d_pal.p, c->h_pal.p, npal * sizeof(float), cudaMemcpyHostToDevice, c->stream);
         rc = e == cudaSuccess ? eval_device(c, c->d_pal.p, B, K, space, flags, c->d_results.p, nullptr, c->stream) : HQ_ERR_CUDA;
-        if (rc == HQ_OK && c->allreduce && c->allreduce(c->allreduce_user, c->d_results.p, nwords, c->stream) != 0)
-            rc = fail(c, HQ_ERR_CALLBACK, "all-reduce hook failed");
         if (rc == HQ_OK) e = cudaMemcpyAsync(c->h_results.p, c->d_results.p, nwords * 8, cudaMemcpyDeviceToHost, c->stream);
         if (capture) {
             cudaGraph_t g = nullptr;
@@ -525,6 +555,7 @@ int hq_eval_palettes(hq_ctx* c, const float* palettes, int B, int K, int space, 
         }
     }
     HQ_CUDA(c, wait_stream(c->stream));
+unpack:
     for (int b = 0; b < B; ++b) {
         const unsigned long long* w = c->h_results.p + (size_t)b * words;
         if (err_fx) err_fx[b] = (int64_t)w[0];

@@ -789,6 +789,22 @@ cudaError_t launch_decode_table(float* d_table, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+// Result words -> the caller's pinned (mapped) host buffer, then a sequence number the host spins on: replaces the D2H copy
+// node and the stream wait of a host-buffer evaluation (two of the four dependent stream operations of a search iteration).
+__global__ void __launch_bounds__(256) export_results_kernel(const unsigned long long* __restrict__ src, unsigned long long* dst, size_t nwords,
+                                                             volatile unsigned long long* flag, unsigned long long seq) {
+    for (size_t i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();   // every thread's stores are visible to the host before ...
+    __syncthreads();
+    if (threadIdx.x == 0) *flag = seq;  // ... the flag is
+}
+
+cudaError_t launch_export_results(const unsigned long long* d_src, unsigned long long* h_dst_mapped, size_t nwords, unsigned long long* h_flag_mapped,
+                                  unsigned long long seq, cudaStream_t stream) {
+    export_results_kernel<<<1, 256, 0, stream>>>(d_src, h_dst_mapped, nwords, h_flag_mapped, seq);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_unit_to_lab(const float* d_unit, size_t n, size_t stride, int whitepoint, float* d_lab, unsigned int* d_bad,
                                int sm_count, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;

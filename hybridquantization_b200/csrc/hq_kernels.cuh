@@ -22,6 +22,9 @@ inline size_t plane_stride(size_t n) { return (n + 31) / 32 * 32; }
 // packed u8 RGB -> fp32 planes.  lab = [3][stride] (L, a, b); unit = [3][stride] (r, g, b)/255 or null.
 // d_table: 512 floats built once by launch_decode_table (u8 -> unit, u8 -> linear light)
 cudaError_t launch_decode_table(float* d_table, cudaStream_t stream);
+// d_src[nwords] -> pinned host memory (device-accessible under UVA), then *h_flag = seq (system-scope ordered after the words)
+cudaError_t launch_export_results(const unsigned long long* d_src, unsigned long long* h_dst_mapped, size_t nwords, unsigned long long* h_flag_mapped,
+                                  unsigned long long seq, cudaStream_t stream);
 // planar float sRGB in [0,1] ([3][stride]) -> Lab planes; *d_bad |= 1 when a value is outside [0,1] or NaN
 cudaError_t launch_unit_to_lab(const float* d_unit, size_t n, size_t stride, int whitepoint, float* d_lab, unsigned int* d_bad,
                                int sm_count, cudaStream_t stream);
