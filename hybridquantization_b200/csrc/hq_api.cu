@@ -188,6 +188,12 @@ cudaError_t wait_flag(const unsigned long long* flag, unsigned long long seq, cu
     }
 }
 
+// no C++ exception (std::bad_alloc from a host-side vector, std::runtime_error from the host classes) may cross the C ABI
+int api_exception(hq_ctx* c, const std::exception& ex) {
+    if (c) c->err = std::string("internal error: ") + ex.what();
+    return HQ_ERR_CUDA;
+}
+
 int bind_device(hq_ctx* c) {
     HQ_CUDA(c, cudaSetDevice(c->device));
     return HQ_OK;
@@ -392,7 +398,7 @@ int hq_device_info(const hq_ctx* c, int* sm_count, int* sm_clock_khz, char* name
 uint64_t hq_image_pixels(const hq_ctx* c) { return c ? (uint64_t)(c->own_hi - c->own_lo) : 0; }
 
 int hq_set_image_u8_sharded(hq_ctx* c, const uint8_t* rgb, int width, int own_rows, int halo_top, int halo_bottom,
-                            int global_row0, int global_rows, int whitepoint) {
+                            int global_row0, int global_rows, int whitepoint) try {
     if (!c) return HQ_ERR_INVALID;
     const long long rows = (long long)halo_top + own_rows + halo_bottom;
     if (width < 0 || own_rows < 0 || halo_top < 0 || halo_bottom < 0 || (!rgb && (size_t)width * rows > 0)) return fail(c, HQ_ERR_INVALID, "bad image arguments");
@@ -409,10 +415,10 @@ int hq_set_image_u8_sharded(hq_ctx* c, const uint8_t* rgb, int width, int own_ro
     rc = convert_image(c, width, own_rows, halo_top, halo_bottom, global_row0, global_rows, whitepoint, c->stream); if (rc) return rc;
     HQ_CUDA(c, cudaStreamSynchronize(c->stream));
     return HQ_OK;
-}
+} catch (const std::exception& ex) { return api_exception(c, ex); }
 
 int hq_set_image_f32_planar_sharded(hq_ctx* c, const float* r, const float* g, const float* b, int width, int own_rows, int halo_top,
-                                    int halo_bottom, int global_row0, int global_rows, int whitepoint) {
+                                    int halo_bottom, int global_row0, int global_rows, int whitepoint) try {
     if (!c) return HQ_ERR_INVALID;
     const long long rows = (long long)halo_top + own_rows + halo_bottom;
     if (width < 0 || own_rows < 0 || halo_top < 0 || halo_bottom < 0 || ((!r || !g || !b) && (size_t)width * rows > 0))
@@ -440,7 +446,7 @@ int hq_set_image_f32_planar_sharded(hq_ctx* c, const float* r, const float* g, c
         return fail(c, HQ_ERR_INVALID, "float image values must lie in [0,1] (Icy's rescaled convertToType, HybridQuantization.java:95)");
     }
     return HQ_OK;
-}
+} catch (const std::exception& ex) { return api_exception(c, ex); }
 
 int hq_set_image_f32_planar(hq_ctx* c, const float* r, const float* g, const float* b, int width, int rows, int whitepoint) {
     return hq_set_image_f32_planar_sharded(c, r, g, b, width, rows, 0, 0, 0, rows, whitepoint);
@@ -487,7 +493,7 @@ int hq_eval_palettes_device(hq_ctx* c, const void* d_palettes, int B, int K, int
     return eval_device(c, static_cast<const float*>(d_palettes), B, K, space, flags, static_cast<unsigned long long*>(d_results), nullptr, st);
 }
 
-int hq_eval_palettes(hq_ctx* c, const float* palettes, int B, int K, int space, int flags, int64_t* err_fx, uint64_t* counts, int64_t* sums_fx) {
+int hq_eval_palettes(hq_ctx* c, const float* palettes, int B, int K, int space, int flags, int64_t* err_fx, uint64_t* counts, int64_t* sums_fx) try {
     int rc = check_eval_args(c, B, K, space); if (rc) return rc;
     if (!palettes) return fail(c, HQ_ERR_INVALID, "palettes is NULL");
     const bool sums = (flags & HQ_EVAL_SUMS) != 0;
@@ -564,7 +570,7 @@ unpack:
         if (sums_fx) std::memcpy(sums_fx + (size_t)b * K * 3, w + 1 + K, sizeof(int64_t) * 3 * K);
     }
     return HQ_OK;
-}
+} catch (const std::exception& ex) { return api_exception(c, ex); }
 
 double hq_cost(int64_t err_fx, const uint64_t* counts, int K, uint64_t n_total, float delta) {
     double penalty = 0;
@@ -574,7 +580,7 @@ double hq_cost(int64_t err_fx, const uint64_t* counts, int K, uint64_t n_total, 
     return sum / (double)n_total + penalty;
 }
 
-int hq_quantize(hq_ctx* c, const float* palette, int K, int space, uint8_t* out_rgb, float* out_f32, uint16_t* out_idx) {
+int hq_quantize(hq_ctx* c, const float* palette, int K, int space, uint8_t* out_rgb, float* out_f32, uint16_t* out_idx) try {
     int rc = check_eval_args(c, 1, K, space); if (rc) return rc;
     if (!palette) return fail(c, HQ_ERR_INVALID, "palette is NULL");
     rc = bind_device(c); if (rc) return rc;
@@ -613,7 +619,7 @@ int hq_quantize(hq_ctx* c, const float* palette, int K, int space, uint8_t* out_
     if (out_idx && no && !idx16)
         for (size_t i = 0; i < no; ++i) out_idx[i] = idx8[i];
     return HQ_OK;
-}
+} catch (const std::exception& ex) { return api_exception(c, ex); }
 
 // ------------------------------------------------------------------ S-CIELAB stage
 static int sc_upload_filters(hq_ctx* c) {
@@ -634,7 +640,7 @@ static int sc_upload_filters(hq_ctx* c) {
     return HQ_OK;
 }
 
-int hq_scielab_set_filters(hq_ctx* c, const float* filters7, const float* abs3, int taps) {
+int hq_scielab_set_filters(hq_ctx* c, const float* filters7, const float* abs3, int taps) try {
     if (!c || !filters7 || !abs3) return c ? fail(c, HQ_ERR_INVALID, "NULL filter arrays") : HQ_ERR_INVALID;
     if (taps < 1 || taps > hq::kMaxScielabTaps || (taps & 1) == 0) return fail(c, HQ_ERR_UNSUPPORTED, "taps must be odd and in [1,%d] (got %d)", hq::kMaxScielabTaps, taps);
     int rc = bind_device(c); if (rc) return rc;
@@ -642,15 +648,15 @@ int hq_scielab_set_filters(hq_ctx* c, const float* filters7, const float* abs3, 
     c->sc_abs3.assign(abs3, abs3 + taps);
     c->sc_taps = taps;
     return sc_upload_filters(c);
-}
+} catch (const std::exception& ex) { return api_exception(c, ex); }
 
-int hq_scielab_configure(hq_ctx* c, int dpi, float viewing_distance_cm) {
+int hq_scielab_configure(hq_ctx* c, int dpi, float viewing_distance_cm) try {
     if (!c) return HQ_ERR_INVALID;
     if (dpi < 1 || !(viewing_distance_cm >= 1.0f)) return fail(c, HQ_ERR_INVALID, "dpi >= 1 and viewing distance >= 1 cm required (HybridQuantization.java:229-231)");
     const hq::ScielabProcessor::FilterBank bank = hq::ScielabProcessor::buildFilters(dpi, (double)viewing_distance_cm);
     const std::vector<float> flat = bank.flat();
     return hq_scielab_set_filters(c, flat.data(), bank.absOfilters.data(), bank.taps());
-}
+} catch (const std::exception& ex) { return api_exception(c, ex); }
 
 int hq_scielab_force_generic(hq_ctx* c, int enabled) {
     if (!c) return HQ_ERR_INVALID;
@@ -770,18 +776,18 @@ int error_image_common(hq_ctx* c, const uint8_t* rgb8, const float* const* f32, 
 }
 }  // namespace
 
-int hq_error_image(hq_ctx* c, const uint8_t* quantized_rgb, float* error_map, uint8_t* error_map_u8, double* mean_de) {
+int hq_error_image(hq_ctx* c, const uint8_t* quantized_rgb, float* error_map, uint8_t* error_map_u8, double* mean_de) try {
     if (!c || !quantized_rgb) return c ? fail(c, HQ_ERR_INVALID, "quantized_rgb is NULL") : HQ_ERR_INVALID;
     return error_image_common(c, quantized_rgb, nullptr, error_map, error_map_u8, mean_de);
-}
+} catch (const std::exception& ex) { return api_exception(c, ex); }
 
-int hq_error_image_f32_planar(hq_ctx* c, const float* r, const float* g, const float* b, float* error_map, uint8_t* error_map_u8, double* mean_de) {
+int hq_error_image_f32_planar(hq_ctx* c, const float* r, const float* g, const float* b, float* error_map, uint8_t* error_map_u8, double* mean_de) try {
     if (!c || !r || !g || !b) return c ? fail(c, HQ_ERR_INVALID, "an image plane is NULL") : HQ_ERR_INVALID;
     const float* planes[3] = {r, g, b};
     return error_image_common(c, nullptr, planes, error_map, error_map_u8, mean_de);
-}
+} catch (const std::exception& ex) { return api_exception(c, ex); }
 
-int hq_eval_palettes_scielab(hq_ctx* c, const float* palettes, int B, int K, int space, int64_t* err_fx, uint64_t* counts) {
+int hq_eval_palettes_scielab(hq_ctx* c, const float* palettes, int B, int K, int space, int64_t* err_fx, uint64_t* counts) try {
     int rc = check_eval_args(c, B, K, space); if (rc) return rc;
     if (!palettes) return fail(c, HQ_ERR_INVALID, "palettes is NULL");
     rc = bind_device(c); if (rc) return rc;
@@ -823,7 +829,7 @@ int hq_eval_palettes_scielab(hq_ctx* c, const float* palettes, int B, int K, int
         if (counts) std::memcpy(counts + (size_t)b * K, c->h_results.p + (size_t)b * words + 1, sizeof(uint64_t) * K);
     }
     return HQ_OK;
-}
+} catch (const std::exception& ex) { return api_exception(c, ex); }
 
 int hq_set_allreduce(hq_ctx* c, hq_allreduce_fn fn, void* user) {
     if (!c) return HQ_ERR_INVALID;
