@@ -540,6 +540,8 @@ int hq_eval_palettes(hq_ctx* c, const float* palettes, int B, int K, int space, 
         if (capture) HQ_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         cudaError_t e = cudaMemcpyAsync(c->d_pal.p, c->h_pal.p, npal * sizeof(float), cudaMemcpyHostToDevice, c->stream);
         rc = e == cudaSuccess ? eval_device(c, c->d_pal.p, B, K, space, flags, c->d_results.p, nullptr, c->stream) : HQ_ERR_CUDA;
+        if (rc == HQ_OK && c->allreduce && c->allreduce(c->allreduce_user, c->d_results.p, nwords, c->stream) != 0)
+            rc = fail(c, HQ_ERR_CALLBACK, "all-reduce hook failed");
         if (rc == HQ_OK) e = cudaMemcpyAsync(c->h_results.p, c->d_results.p, nwords * 8, cudaMemcpyDeviceToHost, c->stream);
         if (capture) {
             cudaGraph_t g = nullptr;

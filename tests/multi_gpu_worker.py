@@ -30,6 +30,9 @@ def main():
     install_nccl_allreduce(be)
     got = be.evalPalettes(pal, sums=True)                     # totals over all ranks
     got_pruned = be.evalPalettes(pal, sums=True, flags=EVAL_PRUNE)   # the exact pruned kernel on every shard, same all-reduce
+    # a population whose palettes / results exceed the direct host I/O thresholds (64 KB / 32 KB): the DMA-copy path, same hook
+    big_pal = synth.synth_palettes(24, 300, seed=9)
+    got_big = be.evalPalettes(big_pal, sums=False)
     sw = SWASA(population=4, imax=60, seed=2024)
     best, err, tr, its = be.findBestQuantization(K, sw, n_total=w * h, trace=True)
     res = {"rank": rank, "ok": True}
@@ -45,6 +48,8 @@ def main():
         single.setImage(img)
         single.setPruning(PRUNE_OFF)   # the single-GPU reference run scores exhaustively; the sharded run above prunes (AUTO)
         want = single.evalPalettes(pal, sums=True)
+        want_big = single.evalPalettes(big_pal, sums=False)
+        res["large_population_equal_single_gpu"] = all(np.array_equal(got_big[k], want_big[k]) for k in ("err_fx", "counts"))
         sbest, serr, str_, _ = single.findBestQuantization(K, SWASA(population=4, imax=60, seed=2024), trace=True)
         single.close()
         res["totals_equal_single_gpu"] = all(np.array_equal(got[k], want[k]) for k in ("err_fx", "counts", "sums_fx"))

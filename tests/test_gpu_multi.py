@@ -34,4 +34,5 @@ def test_sharded_equals_single_gpu(world, tmp_path, hqlib):
     res = json.load(open(out))
     assert len(res) == world and all(x["same_on_all_ranks"] and x["pruned_equals_exhaustive"] for x in res)
     assert res[0]["totals_equal_single_gpu"] and res[0]["trajectory_equal_single_gpu"] and res[0]["iterations"] == 60
+    assert res[0]["large_population_equal_single_gpu"]   # both host I/O paths of hq_eval_palettes go through the all-reduce
     assert res[0]["scielab_totals_equal_single_gpu"] and res[0]["scielab_trajectory_equal_single_gpu"]
