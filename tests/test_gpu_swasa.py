@@ -106,3 +106,42 @@ def test_cuda_graph_replay_gives_the_same_search(backend, oracle):
                 assert np.array_equal(got["err_fx"], want["err_fx"]) and np.array_equal(got["counts"], want["counts"])
     finally:
         backend.setGraphs(False)
+
+
+def test_allreduce_hook_is_applied_on_every_path(hqlib):
+    """One GPU standing in for three identical ranks: the hook multiplies the device result words by 3 on the library's
+    stream.  Every entry that reduces (both host I/O paths of hq_eval_palettes, the S-CIELAB chain, the error image) must
+    then return exactly three times the hook-less integers."""
+    import torch
+
+    from hybridquantization_b200 import EVAL_PRUNE, ImageManipulation
+    from hybridquantization_b200.dist import _DevWords
+
+    calls = []
+
+    def triple(d_ptr, n_words, stream):
+        t = torch.as_tensor(_DevWords(d_ptr, n_words), device=torch.device("cuda", 0))
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+            t.mul_(3)
+        calls.append(n_words)
+        return 0
+
+    img = synth.synth_image(320, 200, 8, smooth=True)
+    be = ImageManipulation("CIE76", False, True, 0)
+    try:
+        be.setImage(img)
+        be.scielabConfigure(72, 45.0)
+        small, big = synth.synth_palettes(3, 16), synth.synth_palettes(24, 300, seed=4)   # direct host I/O / DMA copies
+        base = {"small": be.evalPalettes(small, sums=True), "big": be.evalPalettes(big), "pruned": be.evalPalettes(big, flags=EVAL_PRUNE),
+                "sc": be.evalPalettesScielab(small, SPACE_SRGB), "err": be.computeError(img[::-1].copy())["deltaE"]}
+        be.setAllreduce(triple)
+        got = {"small": be.evalPalettes(small, sums=True), "big": be.evalPalettes(big), "pruned": be.evalPalettes(big, flags=EVAL_PRUNE),
+               "sc": be.evalPalettesScielab(small, SPACE_SRGB), "err": be.computeError(img[::-1].copy())["deltaE"]}
+        assert len(calls) == 5
+        for k in ("small", "big", "pruned", "sc"):
+            assert np.array_equal(got[k]["err_fx"], 3 * base[k]["err_fx"]) and np.array_equal(got[k]["counts"], 3 * base[k]["counts"]), k
+        assert np.array_equal(got["small"]["sums_fx"], 3 * base["small"]["sums_fx"])
+        # the error image divides the summed error by the GLOBAL pixel count (here the same image): 3x the mean
+        assert abs(got["err"] - 3 * base["err"]) <= 1e-12 * base["err"]
+    finally:
+        be.close()
