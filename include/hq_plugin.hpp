@@ -256,6 +256,29 @@ public:
         return quantizedImage;
     }
 
+    // updateOpenCLFilters (:800-841): the 7 separable filters [7][taps] and |k3| [taps] of the S-CIELAB stage
+    void updateFilters(const float* filters7, const float* absfilters, int taps) {
+        check(hq_scielab_set_filters(ctx_, filters7, absfilters, taps), "hq_scielab_set_filters");
+    }
+    // XYZtoScielab(RGBtoXYZ(.)) of the resident image (:100-153, :285-370): planes [3][pixels]
+    std::vector<float> scielabImage() {
+        std::vector<float> planes(static_cast<size_t>(hq_image_pixels(ctx_)) * 3);
+        check(hq_scielab_get_image(ctx_, planes.data()), "hq_scielab_get_image");
+        return planes;
+    }
+    // computeError (:858-894): mean dE between S-CIELAB(resident image) and S-CIELAB(other image of the same size);
+    // errorMap / errorMapU8 (optional, one value per pixel) receive ((255 - dE)^2) / 255^2 of :890
+    double computeError(const uint8_t* otherRgb, float* errorMap = nullptr, uint8_t* errorMapU8 = nullptr) {
+        double mean = 0;
+        check(hq_error_image(ctx_, otherRgb, errorMap, errorMapU8, &mean), "hq_error_image");
+        return mean;
+    }
+    double computeError(const float* r, const float* g, const float* b, float* errorMap = nullptr, uint8_t* errorMapU8 = nullptr) {
+        double mean = 0;
+        check(hq_error_image_f32_planar(ctx_, r, g, b, errorMap, errorMapU8, &mean), "hq_error_image_f32_planar");
+        return mean;
+    }
+
 private:
     void check(int rc, const char* what) const {
         if (rc != HQ_OK) throw std::runtime_error(std::string(what) + ": " + hq_last_error(ctx_));
@@ -436,6 +459,21 @@ struct HybridQuantization {
     std::vector<float> quantization(const float* r, const float* g, const float* b, int w, int h, uint8_t* outRgb, double* bestError = nullptr) {
         if (!r || !g || !b || w <= 0 || h <= 0) throw std::invalid_argument("Please open an image first.");
         return run(w, h, outRgb, bestError, [&](ScielabProcessor& sp) { sp.sRGBToScielab(r, g, b, w, h); });
+    }
+
+    // errorImage(), :139-182: mean S-CIELAB dE between two images of the same size and the error map of :890
+    double errorImage(const uint8_t* original, const uint8_t* quantized, int w, int h, float* errorMap = nullptr, uint8_t* errorMapU8 = nullptr) {
+        if (!original) throw std::invalid_argument("Please open/select the original image first.");    // :76-77
+        if (!quantized) throw std::invalid_argument("Please open/select the quantized image first.");   // :78-79
+        if (w <= 0 || h <= 0) throw std::invalid_argument("Mismatching image sizes or not enough channels, abort.");  // :80-81
+        ImageManipulation imageProcessor(ImageManipulation::deltaETypes::CIE76, verbose, false, device);  // :145
+        ScielabProcessor scielabProcessor(dpi, viewingDistance, whitePoint, &imageProcessor);              // :146
+        scielabProcessor.sRGBToScielab(original, w, h);                                                    // :148
+        const std::vector<float> flat = scielabProcessor.filters().flat();
+        imageProcessor.updateFilters(flat.data(), scielabProcessor.filters().absOfilters.data(), scielabProcessor.filters().taps());
+        const double mean = imageProcessor.computeError(quantized, errorMap, errorMapU8);                  // :151-160
+        scielabProcessor.close();
+        return mean;
     }
 
   private:

@@ -48,6 +48,13 @@ int main(int argc, char** argv) {
             const std::vector<float> best2 = plugin.quantization(planes.data(), planes.data() + n, planes.data() + 2 * n, w, h, out2.data(), &err2);
             printf("\"float_image_same\": %d, ", (int)(best2 == best && out2 == out && err2 == bestError));
         }
+        {   // error-image mode (HybridQuantization.errorImage :139-182) between the input and its quantisation
+            std::vector<uint8_t> map8((size_t)w * h);
+            const double mean = plugin.errorImage(rgb.data(), out.data(), w, h, nullptr, map8.data());
+            unsigned long long mh = 0;
+            for (size_t j = 0; j < map8.size(); ++j) mh = mh * 1099511628211ULL + map8[j];
+            printf("\"error_image_mean\": \"%a\", \"error_map_hash\": %llu, ", mean, mh);
+        }
         // class-level API: SWASA draws + one population evaluation
         hq::JavaRandom rnd(77760);
         hq::SWASA swasa(4, 5000, 20, 2.0f, 0.75f, 0.15f, 20.0f, 0.9f, 100.0f, 5.3f, &rnd);

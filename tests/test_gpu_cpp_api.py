@@ -35,6 +35,13 @@ def test_cpp_plugin_end_to_end(oracle, hqlib, tmp_path, w, h, K, imax):
     for b in q.tolist():
         hsh = (hsh * 1099511628211 + b) & 0xFFFFFFFFFFFFFFFF
     assert got["image_hash"] == hsh
+    of, oa = oracle.scielab_filters(72, 45.0)
+    oe = oracle.error_image(img, q.reshape(img.shape), of, oa, 0, THREADS)
+    assert float.fromhex(got["error_image_mean"]) == oe["deltaE"]
+    mh = 0
+    for b in oe["errorImageU8"].tolist():
+        mh = (mh * 1099511628211 + b) & 0xFFFFFFFFFFFFFFFF
+    assert got["error_map_hash"] == mh
     pal = synth.synth_palettes(4, K)
     ores = oracle.assign_reduce(img, pal)
     want = [oracle.cost(int(ores["err_fx"][i]), ores["counts"][i], w * h, 2.0) for i in range(4)]
