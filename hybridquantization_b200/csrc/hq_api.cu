@@ -83,6 +83,7 @@ struct hq_ctx {
     PinBuf<unsigned long long> h_results;
     PinBuf<unsigned long long> h_flag;      // sequence number written by export_results_kernel after the result words
     unsigned long long export_seq = 0;
+    DevBuf<unsigned> d_export_counter;      // ticket counter of the scoring kernels' export tail (zero between launches)
     bool direct_io = true;                  // HQ_DIRECT_IO=0: the H2D copy / D2H copy / stream wait path instead (A/B measurements)
 
     // exact pruning (hq_pruned.cu): cell-sorted copy of the own pixels, chunk table, boxes; built on first use per image
@@ -283,8 +284,10 @@ int prepare_pruned(hq_ctx* c, int K, int space, int flags, bool want_idx, cudaSt
     return want_idx ? ensure_pruned(c, c->pr_all, space, 0, c->n, true, st) : ensure_pruned(c, c->pr_own, HQ_SPACE_LAB, c->own_lo, c->own_hi, false, st);
 }
 
+// tail (optional): have the scoring kernel itself export the results to pinned host memory; *tail_used reports whether a
+// kernel carrying it was actually launched (nothing is launched for an empty image)
 int eval_device(hq_ctx* c, const float* d_palettes, int B, int K, int space, int flags, unsigned long long* d_results,
-                void* d_idx, cudaStream_t st) {
+                void* d_idx, cudaStream_t st, const hq::ExportTail* tail = nullptr, bool* tail_used = nullptr) {
     const int K8 = hq::padded_colors(K);
     const bool sums = (flags & HQ_EVAL_SUMS) != 0;
     const int words = hq::result_words(K, sums);
@@ -312,6 +315,8 @@ int eval_device(hq_ctx* c, const float* d_palettes, int B, int K, int space, int
         if (d_idx) { pa.perm = ps.perm.p; pa.idx_out = d_idx; pa.istride = c->stride; pa.own_lo = c->own_lo; pa.own_hi = c->own_hi; }
         HQ_CUDA(c, hq::launch_pruned_assign(pa, st));
     } else {
+        const bool direct_variant = a.variant == 1 || (a.variant == 0 && K <= hq::kDirectMaxColors);  // the kernel that carries the tail
+        if (tail && c->n > 0 && direct_variant) { a.tail = *tail; if (tail_used) *tail_used = true; }
         HQ_CUDA(c, hq::launch_assign_reduce(a, st));
     }
     if (c->profiling) { HQ_CUDA(c, cudaEventRecord(c->ev1, st)); c->ev_valid = true; }
@@ -345,6 +350,7 @@ int hq_create(int device, hq_ctx** out) {
         return fail(nullptr, HQ_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     }
     if ((e = c->h_flag.reserve(1)) == cudaSuccess) c->h_flag.p[0] = 0ull;
+    if (e == cudaSuccess && (e = c->d_export_counter.reserve(1)) == cudaSuccess) e = cudaMemsetAsync(c->d_export_counter.p, 0, sizeof(unsigned), c->stream);
     if (e != cudaSuccess || (e = c->d_table.reserve(512)) != cudaSuccess || (e = hq::launch_decode_table(c->d_table.p, c->stream)) != cudaSuccess ||
         (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) {
         cudaStreamDestroy(c->stream);
@@ -377,7 +383,7 @@ void hq_destroy(hq_ctx* c) {
     if (c->ev3) cudaEventDestroy(c->ev3);
     c->d_rgb.release(); c->d_flag.release(); c->d_lab.release(); c->d_unit.release(); c->d_table.release(); c->d_pal.release();
     c->d_pal_lab.release(); c->d_pal_rgb.release(); c->d_results.release(); c->d_idx.release();
-    c->d_out_rgb.release(); c->d_out_f32.release(); c->h_pal.release(); c->h_results.release(); c->h_flag.release();
+    c->d_out_rgb.release(); c->d_out_f32.release(); c->h_pal.release(); c->h_results.release(); c->h_flag.release(); c->d_export_counter.release();
     c->d_sc_filters.release(); c->d_sc_opp.release(); c->d_sc_tmp.release(); c->d_sc_lab.release(); c->d_sc_tab.release(); c->d_sc_err.release();
     c->d_sc_lab2.release(); c->d_sc_map.release(); c->d_sc_rgb2.release(); c->d_sc_map8.release();
     c->pr_own.release(); c->pr_all.release(); c->d_pr_scratch.release();
@@ -530,10 +536,14 @@ int hq_eval_palettes(hq_ctx* c, const float* palettes, int B, int K, int space, 
             // Latency path (a search iteration is four dependent stream operations; this makes it two): the palette kernel reads
             // the pinned host copy directly (UVA: a cudaMallocHost pointer is device-accessible) and a one-CTA kernel writes the
             // result words plus a sequence number back into pinned host memory, which the host spins on.
-            rc = eval_device(c, c->h_pal.p, B, K, space, flags, c->d_results.p, nullptr, c->stream); if (rc) return rc;
-            if (c->allreduce && c->allreduce(c->allreduce_user, c->d_results.p, nwords, c->stream) != 0) return fail(c, HQ_ERR_CALLBACK, "all-reduce hook failed");
             const unsigned long long seq = ++c->export_seq;
-            HQ_CUDA(c, hq::launch_export_results(c->d_results.p, c->h_results.p, nwords, c->h_flag.p, seq, c->stream));
+            hq::ExportTail tail;   // single GPU, small palettes: the scoring kernel's last CTA exports; otherwise a one-CTA kernel after it
+            tail.host_dst = c->h_results.p; tail.host_flag = c->h_flag.p; tail.seq = seq; tail.counter = c->d_export_counter.p;
+            tail.src = c->d_results.p; tail.nwords = (unsigned)nwords;
+            bool tail_used = false;
+            rc = eval_device(c, c->h_pal.p, B, K, space, flags, c->d_results.p, nullptr, c->stream, c->allreduce ? nullptr : &tail, &tail_used); if (rc) return rc;
+            if (c->allreduce && c->allreduce(c->allreduce_user, c->d_results.p, nwords, c->stream) != 0) return fail(c, HQ_ERR_CALLBACK, "all-reduce hook failed");
+            if (!tail_used) HQ_CUDA(c, hq::launch_export_results(c->d_results.p, c->h_results.p, nwords, c->h_flag.p, seq, c->stream));
             HQ_CUDA(c, wait_flag(c->h_flag.p, seq, c->stream));
             goto unpack;
         }

@@ -298,6 +298,7 @@ struct AssignParams {
     size_t own_lo, own_hi;      // pixels [own_lo, own_hi) are reduced; the rest (halo rows of a shard) only get an index
     unsigned long long* results;
     void* idx_out;
+    ExportTail tail;
 };
 
 constexpr int kWorklistCap = 1024;  // ambiguous pixels deferred per CTA (variant 3)
@@ -673,6 +674,7 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : 2) a
             }
         }
     }
+    if (VARIANT == 1) export_tail(p.tail, gridDim.x * gridDim.y);
 }
 
 // per (kernel instantiation, device): the dynamic shared-memory size last configured and the occupancy it gave, so that
@@ -851,6 +853,7 @@ cudaError_t launch_assign_reduce(const AssignArgs& a, cudaStream_t stream) {
     p.words = result_words(a.K, a.want_sums);
     p.results = a.results;
     p.idx_out = a.idx_out;
+    p.tail = a.tail;
     p.own_lo = a.own_lo; p.own_hi = a.own_hi > a.own_lo ? a.own_hi : a.n;
     const int idxw = a.idx_out ? (a.K <= 256 ? 1 : 2) : 0;
     // |feature| bounds of the image for the prefilter's error bound: CIELAB of in-gamut sRGB has
@@ -858,7 +861,8 @@ cudaError_t launch_assign_reduce(const AssignArgs& a, cudaStream_t stream) {
     if (a.space == 1) { p.xmax0 = p.xmax1 = p.xmax2 = 1.0f; }
     else { p.xmax0 = 100.5f; p.xmax1 = 128.0f; p.xmax2 = 128.0f; }
     int variant = a.variant;
-    if (variant == 0) variant = (a.K <= 32) ? 1 : 3;  // measured crossover (4K, 64 candidates): K=32 direct 42 % vs prefilter 36 %, K=64 46 % vs 50 %
+    if (variant == 0) variant = (a.K <= kDirectMaxColors) ? 1 : 3;  // measured crossover (4K, 64 candidates): K=32 direct 42 % vs prefilter 36 %, K=64 46 % vs 50 %
+    if (a.tail.host_dst && variant != 1) return cudaErrorInvalidValue;  // the export tail only exists in variant 1
     if (variant == 1) return launch_assign_v<1>(p, a.B, a.space == 1, a.want_sums, idxw, a.sm_count, stream);
     if (variant == 2) return launch_assign_v<2>(p, a.B, a.space == 1, a.want_sums, idxw, a.sm_count, stream);
     return launch_assign_v<3>(p, a.B, a.space == 1, a.want_sums, idxw, a.sm_count, stream);

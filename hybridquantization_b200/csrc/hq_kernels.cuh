@@ -38,6 +38,40 @@ cudaError_t launch_palette_features(const float* d_palettes, int B, int K, int w
                                     float4* d_pal_lab, float4* d_pal_rgb, cudaStream_t stream, unsigned long long* d_zero = nullptr,
                                     size_t zero_words = 0);
 
+// Optional tail of the small-palette scoring kernel (assign_reduce_kernel variant 1, K <= 32 — where a search iteration is
+// latency-bound): the LAST CTA of the grid to finish copies every result word to pinned host memory and then writes a
+// sequence number there (what export_results_kernel does as a separate launch) — one dependent stream operation fewer per
+// search iteration (C1: 28.1 -> 26.1 us).  Not compiled into variant 3 or the pruned kernel: there it bought nothing and its
+// mere presence cost the pruned kernel 1.5 %.  counter: one device word, zero on entry; the last CTA resets it.
+struct ExportTail {
+    unsigned long long* host_dst = nullptr;   // null = no tail
+    unsigned long long* host_flag = nullptr;
+    unsigned long long seq = 0;
+    unsigned* counter = nullptr;
+    const unsigned long long* src = nullptr;  // [nwords] all result words of the launch
+    unsigned nwords = 0;
+};
+#ifdef __CUDACC__
+// every thread of every CTA calls this after its last result atomic
+__device__ __forceinline__ void export_tail(const ExportTail& x, unsigned total_ctas) {
+    if (x.host_dst == nullptr) return;
+    __shared__ unsigned s_ticket;
+    __threadfence();     // this thread's result atomics are performed device-wide before the ticket is taken
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(x.counter, 1u);
+    __syncthreads();
+    if (s_ticket != total_ctas - 1) return;
+    __threadfence();
+    for (unsigned i = threadIdx.x; i < x.nwords; i += blockDim.x) x.host_dst[i] = __ldcg(x.src + i);
+    __threadfence_system();   // the words are visible to the host before the sequence number is
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *x.counter = 0u;
+        *reinterpret_cast<volatile unsigned long long*>(x.host_flag) = x.seq;
+    }
+}
+#endif
+
 struct AssignArgs {
     const float* lab;      // [3][stride]
     const float* unit;     // [3][stride], required when space == 1
@@ -52,7 +86,9 @@ struct AssignArgs {
     int sm_count;
     size_t own_lo = 0, own_hi = 0;  // reduce only pixels [own_lo, own_hi) (0,0 = all): halo rows of a shard are assigned but not counted
     int variant;           // 0 auto, 1 direct index tracking, 2 chunked min + recompute, 3 prefilter + exact
+    ExportTail tail;       // optional (see above); only with variant 1 (explicit, or auto with K <= kDirectMaxColors)
 };
+constexpr int kDirectMaxColors = 32;  // auto picks variant 1 up to here (measured crossover, hq_kernels.cu)
 cudaError_t launch_assign_reduce(const AssignArgs& a, cudaStream_t stream);
 
 // ---- exact assignment with geometric pruning (hq_pruned.cu): the own pixels are counting-sorted once per image by a
