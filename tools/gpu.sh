@@ -8,6 +8,7 @@
 #   sweep                 tools/sweep.py (rgb_to_lab sizes, K sweep, S-CIELAB stage, full searches)
 #   multi N               NCCL parity test + bench at 1 and N GPUs   (gpurun --gpus N)
 #   micro                 FP32-pipe / issue-model microbenchmarks
+#   latency               tools/latency_ab.py: us per search iteration with / without the direct host I/O path
 set -u
 mkdir -p gpurun_out
 task=${1:-tests}; shift || true
@@ -54,5 +55,7 @@ PY
     done ;;
 micro)
     for m in microbench microbench2 microbench3; do [ -x tools/$m ] && timeout 200 ./tools/$m > gpurun_out/$m.json 2> gpurun_out/$m.err; done; ls -la gpurun_out/microbench* ;;
+latency)
+    timeout 500 python tools/latency_ab.py > gpurun_out/latency_ab.json 2> gpurun_out/latency_ab.err; tail -3 gpurun_out/latency_ab.err; ls -la gpurun_out/latency_ab.json ;;
 *) echo "unknown task $task"; exit 2 ;;
 esac
