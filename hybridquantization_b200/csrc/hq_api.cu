@@ -179,11 +179,14 @@ cudaError_t wait_stream(cudaStream_t st) {
 // Spin on the sequence number export_results_kernel writes into pinned host memory after the result words; the stream is
 // queried now and then so that a failed launch surfaces as an error instead of a hang.
 cudaError_t wait_flag(const unsigned long long* flag, unsigned long long seq, cudaStream_t st) {
+    using clock = std::chrono::steady_clock;
     const volatile unsigned long long* f = flag;
+    const auto t0 = clock::now();
     for (;;) {
         for (int i = 0; i < 2048; ++i)
             if (*f == seq) return cudaSuccess;
-        const cudaError_t e = cudaStreamQuery(st);
+        cudaError_t e = cudaStreamQuery(st);
+        if (e == cudaErrorNotReady && clock::now() - t0 > std::chrono::milliseconds(8)) e = cudaStreamSynchronize(st);  // long kernel: stop burning a core
         if (e == cudaSuccess) return *f == seq ? cudaSuccess : cudaErrorUnknown;
         if (e != cudaErrorNotReady) return e;
     }
