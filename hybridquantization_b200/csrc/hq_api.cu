@@ -715,6 +715,8 @@ static int sc_ensure_image(hq_ctx* c) {
     if (c->width < half || c->g_rows < half)
         return fail(c, HQ_ERR_UNSUPPORTED, "image %dx%d is smaller than the filter half-width %d (the reference's single reflection, "
                     "OptimizedConvolution.cl:20-27, would read out of bounds)", c->width, c->g_rows, half);
+    if (c->rows > 65535)  // the filter kernels put one image row per blockIdx.y
+        return fail(c, HQ_ERR_UNSUPPORTED, "the S-CIELAB stage handles at most 65,535 local rows per context (got %d): shard the image by rows", c->rows);
     {   // a row shard must carry the neighbours' rows the vertical filter reaches (reflection is at the GLOBAL borders)
         const int need_top = c->g_row0 < half ? c->g_row0 : half;
         const int below = c->g_rows - (c->g_row0 + c->own_rows);
