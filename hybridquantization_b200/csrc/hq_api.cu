@@ -245,6 +245,8 @@ int ensure_pruned(hq_ctx* c, hq_ctx::PrunedSet& ps, int space, size_t lo, size_t
     if (ps.ready && ps.space == space) return HQ_OK;
     ps.ready = false;
     const size_t n = hi - lo;
+    if (n >= 0xffffffffull)  // 32-bit pixel positions in the sort permutation and the chunk table
+        return fail(c, HQ_ERR_UNSUPPORTED, "the pruned kernel handles fewer than 2^32 pixels per context (got %zu): use the exhaustive kernel or shard the image", n);
     ps.sstride = hq::plane_stride(n);
     const size_t words = hq::pruned_scratch_words();
     HQ_CUDA(c, ps.sorted.reserve(3 * ps.sstride > 0 ? 3 * ps.sstride : 1));
