@@ -898,7 +898,7 @@ int hq_search_eval_flags(const hq_ctx* c, int K, int space, int cost_model) {
     // measured crossover (4 candidates, profiles/r01/sweep_v10.json + DESIGN.md section 6): from K = 32 on every image of
     // >= 256 x 256, from K = 12 on images of >= 1024 x 768
     const size_t own = c->own_hi - c->own_lo;
-    const bool pays = (K >= 32 && own >= 65536) || (K >= 12 && own >= 786432);
+    const bool pays = ((K >= 32 && own >= 65536) || (K >= 12 && own >= 786432)) && own < 0xffffffffull;
     return (K > HQ_MAX_COLORS || c->prune_mode == HQ_PRUNE_ON || (c->prune_mode == HQ_PRUNE_AUTO && pays)) ? HQ_EVAL_PRUNE : 0;
 }
 
