@@ -401,6 +401,11 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
         t0 = time.perf_counter(); be2.evalPalettes(pal[:1], a.space, flags=EVAL_PRUNE); t1 = time.perf_counter()
         be2.evalPalettes(pal[:1], a.space, flags=EVAL_PRUNE); t2 = time.perf_counter()
         setup["pruned_sort_ms"] = 1e3 * max(0.0, (t1 - t0) - (t2 - t1))
+    # the same image entering as the plugin's float planes (getDataXYCAsFloat, 12 B/px over PCIe, exact pow per channel on the device)
+    planes = np.ascontiguousarray((img.astype(np.float64) / 255.0).astype(np.float32).transpose(2, 0, 1))
+    be2.setImageFloat(planes)
+    t0 = time.perf_counter(); be2.setImageFloat(planes); setup["set_image_f32_planar_host_ms"] = 1e3 * (time.perf_counter() - t0)
+    del planes
     be2.close()
 
     # ---- roofline of the dominant kernel (assign_reduce_kernel): FP32 CUDA-core bound at K=256
