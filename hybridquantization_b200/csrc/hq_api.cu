@@ -184,7 +184,7 @@ cudaError_t wait_flag(const unsigned long long* flag, unsigned long long seq, cu
     const auto t0 = clock::now();
     for (;;) {
         for (int i = 0; i < 2048; ++i)
-            if (*f == seq) return cudaSuccess;
+            if (*f == seq) { std::atomic_thread_fence(std::memory_order_acquire); return cudaSuccess; }  // result words are read after this
         cudaError_t e = cudaStreamQuery(st);
         if (e == cudaErrorNotReady && clock::now() - t0 > std::chrono::milliseconds(8)) e = cudaStreamSynchronize(st);  // long kernel: stop burning a core
         if (e == cudaSuccess) return *f == seq ? cudaSuccess : cudaErrorUnknown;
