@@ -76,6 +76,30 @@ def test_live_reference_kernels(backend, ref, w, h, K, smooth):
         assert np.array_equal(det[i]["used"] != 0, got["counts"][i] > 0)
 
 
+def test_live_reference_on_a_16bit_float_image(backend, ref):
+    """hq_set_image_f32_planar with the planes of a 16-bit image (c/65535, the plugin's getDataXYCAsFloat layout) against the
+    compiled reference fed with the same floats: Java helpers, S-CIELAB of the original, candidate chain, quantize kernel"""
+    w, h, K = 131, 77, 24
+    rng = np.random.default_rng(1016)
+    planes = (rng.integers(0, 65536, (3, h, w)).astype(np.float64) / 65535.0).astype(np.float32)
+    flat = planes.reshape(3, -1)
+    pal = synth.synth_palettes(2, K)
+    backend.setImageFloat(planes)
+    backend.scielabConfigure(72, 45.0)
+    f, a = ref.scielab_filters(72, 45.0)
+    packed = ref.pack_filters(f, a)
+    so4 = ref.xyz_to_scielab(ref.rgb_to_xyz(flat), packed, w, ref.D65)
+    assert np.array_equal(bits(backend.labImage()), bits(ref.srgb_to_lab_java(flat)))
+    assert np.array_equal(bits(backend.scielabImage()), bits(so4[:, :3].T.copy()))
+    costs, det = ref.eval_population(ref.makeinline(flat), so4, w, packed, pal, details=True)
+    got = backend.evalPalettesScielab(pal, SPACE_SRGB)
+    for i in range(2):
+        assert int(np.rint(det[i]["err"].astype(np.float64) * 2.0 ** 24).astype(np.int64).sum()) == int(got["err_fx"][i])
+        assert np.array_equal(det[i]["used"] != 0, got["counts"][i] > 0)
+    rq, _ = ref.quantize(ref.makeinline(flat), pal[0])
+    assert np.array_equal(bits(backend.quantize(pal[0], SPACE_SRGB, want_f32=True)["f32"]), bits(rq))
+
+
 def test_4k_k256_search_and_image_match_the_compiled_reference(backend, ref):
     """north_star's last clause at the NAMED size: a fixed-seed 3840x2160, K=256 SWASA run (shortened to 10 iterations of a
     population of 4 so that the reference's kernels finish on the host cores in about half a minute) through the CUDA path in
