@@ -360,7 +360,7 @@ __device__ __forceinline__ void exact_chunk(const float* __restrict__ s_sk, int 
 #endif
 constexpr int kV3Unroll = HQ_V3_UNROLL;  // chunks per unrolled iteration of the prefilter sweep
 template <int VARIANT, bool SRGB, bool SUMS, int IDXW>
-__global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : 2) assign_reduce_kernel(const AssignParams p) {
+__global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VARIANT == 1 ? 3 : 2)) assign_reduce_kernel(const AssignParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = p.K, K8 = p.K8;
     const int tid = threadIdx.x;
@@ -436,12 +436,7 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : 2) a
 
     // error / counts / sums / index of ONE resolved pixel (q = its Lab, d2v = exact squared distance in
     // the assignment space)
-    auto resolve = [&](size_t px, int k, float d2v, float q0, float q1, float q2, bool write_idx) {
-        if (write_idx) {
-            if (IDXW == 1) reinterpret_cast<uint8_t*>(p.idx_out)[(size_t)b * p.stride + px] = (uint8_t)k;
-            if (IDXW == 2) reinterpret_cast<uint16_t*>(p.idx_out)[(size_t)b * p.stride + px] = (uint16_t)k;
-        }
-        if (px < p.own_lo || px >= p.own_hi) return;  // halo pixel of a row shard: assigned, not counted
+    auto account = [&](int k, float d2v, float q0, float q1, float q2) {
         if (SRGB) {  // assign in sRGB, score in CIELAB (OptimizedConvolution.cl:209)
             const float4 pl = s_lab[k];
             d2v = hq_dist2(q0, q1, q2, pl.x, pl.y, pl.z);
@@ -453,6 +448,14 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : 2) a
             atomicAdd(&s_sum[3 * k + 1], (unsigned long long)hq_to_fx(q1));
             atomicAdd(&s_sum[3 * k + 2], (unsigned long long)hq_to_fx(q2));
         }
+    };
+    auto resolve = [&](size_t px, int k, float d2v, float q0, float q1, float q2, bool write_idx) {
+        if (write_idx) {
+            if (IDXW == 1) reinterpret_cast<uint8_t*>(p.idx_out)[(size_t)b * p.stride + px] = (uint8_t)k;
+            if (IDXW == 2) reinterpret_cast<uint16_t*>(p.idx_out)[(size_t)b * p.stride + px] = (uint16_t)k;
+        }
+        if (px < p.own_lo || px >= p.own_hi) return;  // halo pixel of a row shard: assigned, not counted
+        account(k, d2v, q0, q1, q2);
     };
     // exact sweep over every colour (ambiguous pixels of variant 3)
     auto exact_all = [&](float x0, float x1, float x2, float& bd, int& bi) {
@@ -616,9 +619,16 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : 2) a
 #pragma unroll
             for (int j = 0; j < 4; ++j) { q0[j] = x0[j]; q1[j] = x1[j]; q2[j] = x2[j]; }
         }
+        // small palettes are instruction-bound in this epilogue: a thread whose four pixels are all own pixels (every thread but
+        // those at the edges of a shard) skips the per-pixel range tests
+        if (VARIANT == 1 && nvalid == 4 && base >= p.own_lo && base + 4 <= p.own_hi) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (j < nvalid && !deferred[j]) resolve(base + j, idx[j], best[j], q0[j], q1[j], q2[j], false);
+            for (int j = 0; j < 4; ++j) account(idx[j], best[j], q0[j], q1[j], q2[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < nvalid && !deferred[j]) resolve(base + j, idx[j], best[j], q0[j], q1[j], q2[j], false);
+        }
         if (IDXW == 1) {
             uint8_t* o = reinterpret_cast<uint8_t*>(p.idx_out) + (size_t)b * p.stride + base;
             if (nvalid == 4) {

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--skip-swasa", action="store_true")
     ap.add_argument("--only-scielab", action="store_true")
     ap.add_argument("--only-swasa", action="store_true")
+    ap.add_argument("--only-ksweep", type=str, default="", help="comma-separated K list: run only the K sweep for these palette sizes")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
@@ -62,6 +63,9 @@ def main():
 
     # ---- RGB -> Lab (15 B/pixel algorithmic: 3 B read + 12 B written)
     out["rgb_to_lab"] = []
+    only_k = tuple(int(v) for v in a.only_ksweep.split(",") if v)
+    if only_k:
+        a.only_scielab = False; a.only_swasa = True; a.skip_swasa = True
     for (w, h) in (() if (a.only_scielab or a.only_swasa) else ((1920, 1080), (3840, 2160), (8192, 8192))):
         img = synth.synth_image_rows(w, h, synth.SEED_BASE + 3, 0, h)
         d_img = torch.from_numpy(img).to(dev)
@@ -89,7 +93,7 @@ def main():
     d_img = torch.from_numpy(img).to(dev)
     be.setImageDevice(d_img.data_ptr(), w, h, stream=st.cuda_stream)
     out["k_sweep"] = []
-    ks = () if (a.only_scielab or a.only_swasa) else (8, 16, 32, 64, 128, 256, 512, 1024)
+    ks = only_k if only_k else (() if (a.only_scielab or a.only_swasa) else (8, 16, 32, 64, 128, 256, 512, 1024))
     for K in ks:
         for B in (1, 64):
             if a.quick and B == 64 and K > 256:
