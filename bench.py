@@ -60,27 +60,83 @@ def workload_name(a, world):
 
 # ------------------------------------------------------------------ clocks sampler (recipe's clocks line)
 class ClockSampler:
+    """SM clock, power and throttle reasons sampled every 25 ms during the timed region.  NVML in-process (pynvml) when
+    it loads — no start-up delay — else a streaming `nvidia-smi -lms 25` child; `wait_ready` blocks until a first sample exists
+    so that a short timed region cannot end before the sampler has started."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,clocks_event_reasons.active")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc, self.thread = index, [], None, None
+        self.index, self.rows, self.proc, self.thread, self.source = index, [], None, None, None
+        self._stop = threading.Event()
+
+    def _physical_index(self) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v.strip() for v in vis.split(",") if v.strip()]
+        if ids and self.index < len(ids) and ids[self.index].isdigit():
+            return int(ids[self.index])
+        return self.index
 
     def start(self):
         try:
+            import pynvml as N
+
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self._physical_index())
+            N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, args=(N, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            pass
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "25",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-i", str(self._physical_index())], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
             return
+        self.source = "nvidia-smi"
         self.thread = threading.Thread(target=self._read, daemon=True)
         self.thread.start()
+
+    def _poll_nvml(self, N, h):
+        bits = [("hw_slowdown", getattr(N, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+                ("hw_thermal_slowdown", getattr(N, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                ("sw_thermal_slowdown", getattr(N, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                ("sw_power_cap", getattr(N, "nvmlClocksThrottleReasonSwPowerCap", 0x4))]
+        try:
+            mx = str(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+        except Exception:
+            mx = ""
+        while not self._stop.is_set():
+            try:
+                sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                try:
+                    pw = "%.2f" % (N.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:
+                    pw = ""
+                try:
+                    mask = int(N.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                except Exception:
+                    mask = 0
+                self.rows.append((time.perf_counter(), [str(sm), mx, pw] + ["Active" if mask & b else "Not Active" for _, b in bits] + [hex(mask)]))
+            except Exception:
+                pass
+            self._stop.wait(0.025)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
+    def wait_ready(self, seconds: float = 10.0) -> bool:
+        t0 = time.perf_counter()
+        while not self.rows and self.thread is not None and time.perf_counter() - t0 < seconds:
+            time.sleep(0.02)
+        return bool(self.rows)
+
     def stop(self):
+        self._stop.set()
         if self.proc:
             self.proc.terminate()
             try:
@@ -97,7 +153,7 @@ class ClockSampler:
         reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(rows[0][1]) if rows[0][1].isdigit() else None,
                 "power_w_max": max((float(r[2]) for r in rows if r[2].replace(".", "").isdigit()), default=None),
-                "samples": len(rows), "reasons": reasons}
+                "samples": len(rows), "source": self.source, "reasons": reasons}
 
 
 # ------------------------------------------------------------------ CPU arm (oracle port)
@@ -235,6 +291,8 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
         raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    sampler = ClockSampler(local_rank)   # started first: by the timed region it has long been sampling
+    sampler.start()
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     if rank == 0:
@@ -283,9 +341,7 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
     if not counts_ok:
         raise SystemExit("bench: counts do not sum to the pixel count — the kernel is not doing the work")
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.3)
+    sampler.wait_ready()
     be.setProfiling(True)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     kernel_ms = []
