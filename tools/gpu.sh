@@ -54,7 +54,7 @@ except Exception as e:
 PY
     done ;;
 micro)
-    for m in microbench microbench2 microbench3; do [ -x tools/$m ] && timeout 200 ./tools/$m > gpurun_out/$m.json 2> gpurun_out/$m.err; done; ls -la gpurun_out/microbench* ;;
+    for m in microbench microbench2 microbench3 microbench4; do [ -x tools/$m ] && timeout 200 ./tools/$m > gpurun_out/$m.json 2> gpurun_out/$m.err; done; ls -la gpurun_out/microbench* ;;
 latency)
     timeout 500 python tools/latency_ab.py > gpurun_out/latency_ab.json 2> gpurun_out/latency_ab.err; tail -3 gpurun_out/latency_ab.err; ls -la gpurun_out/latency_ab.json ;;
 *) echo "unknown task $task"; exit 2 ;;
