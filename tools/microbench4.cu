@@ -178,6 +178,61 @@ __global__ void __launch_bounds__(256) ffma_sweep(const float* __restrict__ f0, 
     if (CHECK) atomicMax(max_err, dbits(worst));
 }
 
+// rate-only variants of the FFMA sweep: PX pixels per thread (coefficient loads amortised over more pairs), MIN3 = FMNMX3 or two FMNMX
+template <int PX, bool MIN3>
+__global__ void __launch_bounds__(256) ffma_sweep_px(const float* __restrict__ f0, const float* __restrict__ f1, const float* __restrict__ f2, size_t n,
+                                                    const float4* __restrict__ pal, float* __restrict__ out_min) {
+    __shared__ float4 s_coef[K];
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const float4 c = pal[k];
+        s_coef[k] = make_float4(-2.f * c.x, -2.f * c.y, -2.f * c.z, (float)((double)c.x * c.x + (double)c.y * c.y + (double)c.z * c.z));
+    }
+    __syncthreads();
+    for (size_t base = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * PX; base + PX <= n; base += (size_t)gridDim.x * blockDim.x * PX) {
+        float x[PX][3], m[PX];
+#pragma unroll
+        for (int j = 0; j < PX; ++j) { x[j][0] = f0[base + j]; x[j][1] = f1[base + j]; x[j][2] = f2[base + j]; m[j] = INFINITY; }
+#pragma unroll 4
+        for (int k = 0; k < K; k += 2) {
+            const float4 u = s_coef[k], v = s_coef[k + 1];
+#pragma unroll
+            for (int j = 0; j < PX; ++j) {
+                const float su = __fmaf_rn(x[j][0], u.x, __fmaf_rn(x[j][1], u.y, __fmaf_rn(x[j][2], u.z, u.w)));
+                const float sv = __fmaf_rn(x[j][0], v.x, __fmaf_rn(x[j][1], v.y, __fmaf_rn(x[j][2], v.z, v.w)));
+                m[j] = MIN3 ? min3(m[j], su, sv) : fminf(fminf(m[j], su), sv);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PX; ++j) out_min[base + j] = m[j];
+    }
+}
+
+// the same sweep with the coefficients in CONSTANT memory: they reach the FFMA through the uniform datapath (LDCU -> UR operand),
+// so every FFMA reads two registers instead of three (the ncu capture of ffma_sweep_px shows dispatch stalls, i.e. register-file
+// read pressure, capping the issue rate at 72 %)
+__constant__ float4 c_coef[K];
+template <int PX>
+__global__ void __launch_bounds__(256) ffma_sweep_const(const float* __restrict__ f0, const float* __restrict__ f1, const float* __restrict__ f2, size_t n,
+                                                       float* __restrict__ out_min) {
+    for (size_t base = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * PX; base + PX <= n; base += (size_t)gridDim.x * blockDim.x * PX) {
+        float x[PX][3], m[PX];
+#pragma unroll
+        for (int j = 0; j < PX; ++j) { x[j][0] = f0[base + j]; x[j][1] = f1[base + j]; x[j][2] = f2[base + j]; m[j] = INFINITY; }
+#pragma unroll 4
+        for (int k = 0; k < K; k += 2) {
+            const float4 u = c_coef[k], v = c_coef[k + 1];
+#pragma unroll
+            for (int j = 0; j < PX; ++j) {
+                const float su = __fmaf_rn(x[j][0], u.x, __fmaf_rn(x[j][1], u.y, __fmaf_rn(x[j][2], u.z, u.w)));
+                const float sv = __fmaf_rn(x[j][0], v.x, __fmaf_rn(x[j][1], v.y, __fmaf_rn(x[j][2], v.z, v.w)));
+                m[j] = min3(m[j], su, sv);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PX; ++j) out_min[base + j] = m[j];
+    }
+}
+
 static double lcg(uint64_t& s) { s = s * 6364136223846793005ULL + 1442695040888963407ULL; return (double)(s >> 11) / 9007199254740992.0; }
 
 int main() {
@@ -233,6 +288,49 @@ int main() {
     }
     CK(cudaGetLastError());
     const double pairs = (double)n * K;
+    // rate-only variants of the FFMA sweep
+    float ms_v[4] = {1e30f, 1e30f, 1e30f, 1e30f};
+    for (int rep = 0; rep < 4; ++rep) {
+        float ms;
+        CK(cudaEventRecord(e0)); ffma_sweep_px<8, true><<<sms * 4, 256>>>(d_f, d_f + n, d_f + 2 * n, n, d_pal, d_min_f); CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1)); if (rep) ms_v[0] = fminf(ms_v[0], ms);
+        CK(cudaEventRecord(e0)); ffma_sweep_px<8, false><<<sms * 4, 256>>>(d_f, d_f + n, d_f + 2 * n, n, d_pal, d_min_f); CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1)); if (rep) ms_v[1] = fminf(ms_v[1], ms);
+        CK(cudaEventRecord(e0)); ffma_sweep_px<4, false><<<sms * 4, 256>>>(d_f, d_f + n, d_f + 2 * n, n, d_pal, d_min_f); CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1)); if (rep) ms_v[2] = fminf(ms_v[2], ms);
+        CK(cudaEventRecord(e0)); ffma_sweep_px<16, true><<<sms * 4, 256>>>(d_f, d_f + n, d_f + 2 * n, n, d_pal, d_min_f); CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1)); if (rep) ms_v[3] = fminf(ms_v[3], ms);
+    }
+    {
+        std::vector<float4> hc(K);
+        for (int k = 0; k < K; ++k) {
+            const float4 c = hp[k];
+            hc[k] = make_float4(-2.f * c.x, -2.f * c.y, -2.f * c.z, (float)((double)c.x * c.x + (double)c.y * c.y + (double)c.z * c.z));
+        }
+        CK(cudaMemcpyToSymbol(c_coef, hc.data(), K * sizeof(float4)));
+    }
+    float ms_c[2] = {1e30f, 1e30f};
+    for (int rep = 0; rep < 4; ++rep) {
+        float ms;
+        CK(cudaEventRecord(e0)); ffma_sweep_const<8><<<sms * 4, 256>>>(d_f, d_f + n, d_f + 2 * n, n, d_min_t); CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1)); if (rep) ms_c[0] = fminf(ms_c[0], ms);
+        CK(cudaEventRecord(e0)); ffma_sweep_const<4><<<sms * 4, 256>>>(d_f, d_f + n, d_f + 2 * n, n, d_min_t); CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1)); if (rep) ms_c[1] = fminf(ms_c[1], ms);
+    }
+    {   // same minima as the shared-memory sweep?
+        std::vector<float> a(n_check), b(n_check);
+        ffma_sweep_const<4><<<sms * 4, 256>>>(d_f, d_f + n, d_f + 2 * n, n, d_min_t);
+        ffma_sweep_px<4, true><<<sms * 4, 256>>>(d_f, d_f + n, d_f + 2 * n, n, d_pal, d_min_f);
+        CK(cudaMemcpy(a.data(), d_min_t, n_check * sizeof(float), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(b.data(), d_min_f, n_check * sizeof(float), cudaMemcpyDeviceToHost));
+        size_t diff = 0;
+        for (size_t i = 0; i < n_check; ++i) diff += a[i] != b[i];
+        fprintf(stderr, "{\"const_vs_shared_minima_differing\": %zu}\n", diff);
+    }
+    CK(cudaGetLastError());
+    fprintf(stderr, "{\"ffma_constant_bank_tera_pairs_per_s\": {\"px8\": %.3f, \"px4\": %.3f}}\n", pairs / (ms_c[0] * 1e-3) / 1e12, pairs / (ms_c[1] * 1e-3) / 1e12);
+    fprintf(stderr, "{\"ffma_variants_tera_pairs_per_s\": {\"px8_fmnmx3\": %.3f, \"px8_two_fmnmx\": %.3f, \"px4_two_fmnmx\": %.3f, \"px16_fmnmx3\": %.3f}}\n",
+            pairs / (ms_v[0] * 1e-3) / 1e12, pairs / (ms_v[1] * 1e-3) / 1e12, pairs / (ms_v[2] * 1e-3) / 1e12, pairs / (ms_v[3] * 1e-3) / 1e12);
     printf("{\"pixels\": %zu, \"colours\": %d, \"error_sample_pixels\": %zu, "
            "\"tensor_split_tf32\": {\"max_abs_err\": %.6g, \"ms\": %.4f, \"tera_pairs_per_s\": %.3f}, "
            "\"ffma_fp32\": {\"max_abs_err\": %.6g, \"ms\": %.4f, \"tera_pairs_per_s\": %.3f}, "
