@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256) ffma_sweep(const float* __restrict__ f0, 
 }
 
 // rate-only variants of the FFMA sweep: PX pixels per thread (coefficient loads amortised over more pairs), MIN3 = FMNMX3 or two FMNMX
-template <int PX, bool MIN3>
+template <int PX, int MIN3>   // MIN3: 1 = FMNMX3, 0 = two FMNMX, 2 = no minimum at all (FADD accumulate: every instruction on the FMA pipe)
 __global__ void __launch_bounds__(256) ffma_sweep_px(const float* __restrict__ f0, const float* __restrict__ f1, const float* __restrict__ f2, size_t n,
                                                     const float4* __restrict__ pal, float* __restrict__ out_min) {
     __shared__ float4 s_coef[K];
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256) ffma_sweep_px(const float* __restrict__ f
             for (int j = 0; j < PX; ++j) {
                 const float su = __fmaf_rn(x[j][0], u.x, __fmaf_rn(x[j][1], u.y, __fmaf_rn(x[j][2], u.z, u.w)));
                 const float sv = __fmaf_rn(x[j][0], v.x, __fmaf_rn(x[j][1], v.y, __fmaf_rn(x[j][2], v.z, v.w)));
-                m[j] = MIN3 ? min3(m[j], su, sv) : fminf(fminf(m[j], su), sv);
+                m[j] = MIN3 == 2 ? __fadd_rn(__fadd_rn(m[j], su), sv) : (MIN3 == 1 ? min3(m[j], su, sv) : fminf(fminf(m[j], su), sv));
             }
         }
 #pragma unroll
@@ -292,13 +292,13 @@ int main() {
     float ms_v[4] = {1e30f, 1e30f, 1e30f, 1e30f};
     for (int rep = 0; rep < 4; ++rep) {
         float ms;
-        CK(cudaEventRecord(e0)); ffma_sweep_px<8, true><<<sms * 4, 256>>>(d_f, d_f + n, d_f + 2 * n, n, d_pal, d_min_f); CK(cudaEventRecord(e1));
+        CK(cudaEventRecord(e0)); ffma_sweep_px<8, 1><<<sms * 4, 256>>>(d_f, d_f + n, d_f + 2 * n, n, d_pal, d_min_f); CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1)); if (rep) ms_v[0] = fminf(ms_v[0], ms);
-        CK(cudaEventRecord(e0)); ffma_sweep_px<8, false><<<sms * 4, 256>>>(d_f, d_f + n, d_f + 2 * n, n, d_pal, d_min_f); CK(cudaEventRecord(e1));
+        CK(cudaEventRecord(e0)); ffma_sweep_px<8, 0><<<sms * 4, 256>>>(d_f, d_f + n, d_f + 2 * n, n, d_pal, d_min_f); CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1)); if (rep) ms_v[1] = fminf(ms_v[1], ms);
-        CK(cudaEventRecord(e0)); ffma_sweep_px<4, false><<<sms * 4, 256>>>(d_f, d_f + n, d_f + 2 * n, n, d_pal, d_min_f); CK(cudaEventRecord(e1));
+        CK(cudaEventRecord(e0)); ffma_sweep_px<4, 0><<<sms * 4, 256>>>(d_f, d_f + n, d_f + 2 * n, n, d_pal, d_min_f); CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1)); if (rep) ms_v[2] = fminf(ms_v[2], ms);
-        CK(cudaEventRecord(e0)); ffma_sweep_px<16, true><<<sms * 4, 256>>>(d_f, d_f + n, d_f + 2 * n, n, d_pal, d_min_f); CK(cudaEventRecord(e1));
+        CK(cudaEventRecord(e0)); ffma_sweep_px<16, 1><<<sms * 4, 256>>>(d_f, d_f + n, d_f + 2 * n, n, d_pal, d_min_f); CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1)); if (rep) ms_v[3] = fminf(ms_v[3], ms);
     }
     {
@@ -320,12 +320,20 @@ int main() {
     {   // same minima as the shared-memory sweep?
         std::vector<float> a(n_check), b(n_check);
         ffma_sweep_const<4><<<sms * 4, 256>>>(d_f, d_f + n, d_f + 2 * n, n, d_min_t);
-        ffma_sweep_px<4, true><<<sms * 4, 256>>>(d_f, d_f + n, d_f + 2 * n, n, d_pal, d_min_f);
+        ffma_sweep_px<4, 1><<<sms * 4, 256>>>(d_f, d_f + n, d_f + 2 * n, n, d_pal, d_min_f);
         CK(cudaMemcpy(a.data(), d_min_t, n_check * sizeof(float), cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(b.data(), d_min_f, n_check * sizeof(float), cudaMemcpyDeviceToHost));
         size_t diff = 0;
         for (size_t i = 0; i < n_check; ++i) diff += a[i] != b[i];
         fprintf(stderr, "{\"const_vs_shared_minima_differing\": %zu}\n", diff);
+    }
+    {
+        float best = 1e30f, ms;
+        for (int rep = 0; rep < 4; ++rep) {
+            CK(cudaEventRecord(e0)); ffma_sweep_px<8, 2><<<sms * 4, 256>>>(d_f, d_f + n, d_f + 2 * n, n, d_pal, d_min_f); CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1)); if (rep) best = fminf(best, ms);
+        }
+        fprintf(stderr, "{\"ffma_plus_fadd_no_minimum_px8_tera_pairs_per_s\": %.3f}\n", pairs / (best * 1e-3) / 1e12);
     }
     CK(cudaGetLastError());
     fprintf(stderr, "{\"ffma_constant_bank_tera_pairs_per_s\": {\"px8\": %.3f, \"px4\": %.3f}}\n", pairs / (ms_c[0] * 1e-3) / 1e12, pairs / (ms_c[1] * 1e-3) / 1e12);
