@@ -51,7 +51,7 @@ enum {
     HQ_EVAL_SUMS = 1,            /* also reduce per-colour Lab sums */
     HQ_EVAL_FORCE_DIRECT = 2,    /* kernel variant selection, for tests / profiling */
     HQ_EVAL_FORCE_CHUNKED = 4,
-    HQ_EVAL_FORCE_PREFILTER = 8, /* expanded-form prefilter + exact re-check (default for K > 16) */
+    HQ_EVAL_FORCE_PREFILTER = 8, /* expanded-form prefilter + exact re-check (default for K > 32) */
     HQ_EVAL_PRUNE = 16           /* exact assignment with geometric pruning (LAB space; same integers as the exhaustive
                                   * kernel, ~10x less arithmetic at K=256): see hq_set_pruning */
 };
