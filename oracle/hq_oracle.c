@@ -793,6 +793,26 @@ double hqo_error_image_f32(const float* unit3_a, const float* unit3_b, int w, in
     return mean;
 }
 
+/* ------------------------------------------------------------------ CIE94 (scope row f4: restated and pinned, not built on the GPU)
+ * The CIE94 branch of the reference's CIEDE kernel (OptimizedConvolution.cl:217-226, selected by -DCIE94,
+ * ImageManipulation.java:63; the plugin itself always passes CIE76, HybridQuantization.java:96,145).  fp32 arithmetic with exact
+ * fma(); the weights 1 + 0.045*C1 and 1 + 0.015*C1 are evaluated in double (the literals are doubles in OpenCL C) and narrowed
+ * on assignment; deltaH takes the square root of da^2 + db^2 - dC^2, which rounding makes slightly negative for collinear chroma
+ * vectors: the result is then NaN, exactly as the reference kernel's. */
+float hqo_delta_e94(const float lab1[3], const float lab2[3]) {
+    const float dL = lab1[0] - lab2[0];
+    const float c1 = sqrtf(fmaf(lab1[1], lab1[1], lab1[2] * lab1[2]));
+    const float dC = c1 - sqrtf(fmaf(lab2[1], lab2[1], lab2[2] * lab2[2]));
+    const float da = lab1[1] - lab2[1], db = lab1[2] - lab2[2];
+    const float dH = sqrtf(fmaf(da, da, db * db) - dC * dC);
+    const float sc = (float)(1 + 0.045 * (double)c1), sh = (float)(1 + 0.015 * (double)c1);
+    const float qc = dC / sc, qh = dH / sh;
+    return sqrtf(fmaf(dL, dL, fmaf(qc, qc, qh * qh)));
+}
+void hqo_delta_e94_array(const float* lab1 /*[n][3]*/, const float* lab2, size_t n, float* out) {
+    for (size_t i = 0; i < n; ++i) out[i] = hqo_delta_e94(lab1 + 3 * i, lab2 + 3 * i);
+}
+
 /* ------------------------------------------------------------------ range evaluation (tests) */
 typedef struct { int which; uint32_t first; float* out; } mrange_ctx;
 static void mrange_fn(void* p, size_t lo, size_t hi, int tid) {

@@ -74,6 +74,7 @@ def load() -> C.CDLL:
         L.hqo_image_planes_f32.argtypes = [_P, C.c_size_t, C.c_int, _P, C.c_int]
         L.hqo_scielab_image_f32.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, C.c_int]
         L.hqo_scielab_eval_planes.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int]
+        L.hqo_delta_e94_array.argtypes = [_P, _P, C.c_size_t, _P]
         L.hqo_error_image_f32.restype = C.c_double
         L.hqo_error_image_f32.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int]
         L.hqo_error_image.restype = C.c_double
@@ -255,3 +256,11 @@ def error_image_f32(planes_a, planes_b, filters, abs3, whitepoint=WHITE_D65, thr
     mean = load().hqo_error_image_f32(_ptr(a), _ptr(b), w, h, whitepoint, _ptr(filters), _ptr(abs3), filters.shape[1], _ptr(emap), _ptr(e8),
                                       threads or default_threads())
     return {"deltaE": mean, "errorImage": emap, "errorImageU8": e8}
+
+
+def delta_e94(lab1, lab2) -> np.ndarray:
+    """CIE94 branch of the reference's CIEDE kernel (cl:217-226) on [n, 3] Lab arrays; NaN where the reference's is"""
+    a = np.ascontiguousarray(lab1, np.float32).reshape(-1, 3); b = np.ascontiguousarray(lab2, np.float32).reshape(-1, 3)
+    out = np.empty(a.shape[0], np.float32)
+    load().hqo_delta_e94_array(_ptr(a), _ptr(b), a.shape[0], _ptr(out))
+    return out

@@ -302,3 +302,23 @@ def reference_plugin_search(rgb_u8, K, swasa: Swasa, filters, abs3, illuminant=D
     rgb4 = makeinline(unit_planes(rgb))
     ev = lambda pal: eval_population(rgb4, scielab4, w, packed, pal, swasa.h, illuminant, threads, depth)
     return find_best_quantization(swasa, K, ev, convergence, trace)
+
+
+# ---------------------------------------------------------------- the CIEDE kernel built with -DCIE94 (scope row f4)
+LIB94_PATH = os.path.join(_HERE, "_ref", "libhq_ref94.so")
+_lib94 = None
+
+
+def ciede94(lab1: np.ndarray, lab2: np.ndarray) -> np.ndarray:
+    """The reference's CIEDE kernel compiled with -DCIE94 (cl:217-226) on [n, 3] Lab arrays (padded to float4 as the kernel reads them)"""
+    global _lib94
+    if _lib94 is None:
+        if not os.path.exists(LIB94_PATH):
+            raise RuntimeError("oracle/_ref/libhq_ref94.so is not built (run oracle/ref_build/build_ref.sh)")
+        _lib94 = C.CDLL(LIB94_PATH)
+        _lib94.refcl94_CIEDE.argtypes = [_P, _P, _P, C.c_int]
+    a = np.zeros((len(lab1), 4), np.float32); a[:, :3] = lab1
+    b = np.zeros((len(lab2), 4), np.float32); b[:, :3] = lab2
+    out = np.empty(len(a), np.float32)
+    _lib94.refcl94_CIEDE(_ptr(a), _ptr(b), _ptr(out), len(a))
+    return out

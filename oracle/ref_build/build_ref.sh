@@ -58,3 +58,15 @@ java2cpp() { python3 "$HERE/java2cpp.py"; }
 } | ${CXX:-g++} -x c++ -std=c++17 -O3 -march=x86-64-v3 -ffp-contract=off -fno-math-errno -fPIC -shared -DCIE76 \
         -Wno-unused-variable -Wno-unused-but-set-variable -I"$HERE" -o "$OUT/libhq_ref.so" - -lpthread -lm
 echo "[build_ref] built $OUT/libhq_ref.so from $REF"
+
+# The same kernels built as ImageManipulation.java:63 would for deltaETypes.CIE94 ("-DCIE94"): only CIEDE's branch cl:217-226 differs.
+# Pins the oracle's restatement of that branch (hqo_delta_e94); the plugin itself never selects it (HybridQuantization.java:96,145).
+{
+    echo '#include "cl_shim.hpp"'
+    echo 'namespace refcl {'
+    sed 's/(float4)(/float4(/g' "$REF/OptimizedConvolution.cl"
+    echo '}  // namespace refcl'
+    cat "$HERE/ref_entry94.inc"
+} | ${CXX:-g++} -x c++ -std=c++17 -O3 -march=x86-64-v3 -ffp-contract=off -fno-math-errno -fPIC -shared -DCIE94 \
+        -Wno-unused-variable -Wno-unused-but-set-variable -Wno-unused-function -I"$HERE" -o "$OUT/libhq_ref94.so" - -lm
+echo "[build_ref] built $OUT/libhq_ref94.so (CIEDE kernel, -DCIE94)"

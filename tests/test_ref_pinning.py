@@ -100,6 +100,29 @@ def test_scielab_of_a_float_image(oracle, ref):
     assert np.array_equal(bits(got[:, :3].T.copy()), bits(want))
 
 
+def test_cie94_branch_of_the_ciede_kernel(oracle, ref):
+    """scope row f4 (not built on the GPU): the oracle's restatement of the CIE94 branch (cl:217-226) against the
+    reference kernel compiled with -DCIE94 — same bits, and NaN exactly where the reference's sqrt goes negative"""
+    rng = np.random.default_rng(94)
+    n = 1 << 20
+    a = np.stack([rng.uniform(0, 100, n), rng.uniform(-90, 100, n), rng.uniform(-110, 95, n)], 1).astype(np.float32)
+    b = (a + rng.normal(0, 8, a.shape)).astype(np.float32)
+    # collinear chroma vectors (same hue, different chroma): da^2 + db^2 - dC^2 cancels and rounding decides its sign
+    k = n // 4
+    scale = rng.uniform(0.2, 3.0, k).astype(np.float32)
+    b[:k, 1] = a[:k, 1] * scale; b[:k, 2] = a[:k, 2] * scale
+    b[k:k + 1000] = a[k:k + 1000]                     # identical pixels
+    a[k + 1000:k + 2000, 1:] = 0                      # greys
+    got, want = ref.ciede94(a, b), oracle.delta_e94(a, b)
+    nan_g, nan_w = np.isnan(got), np.isnan(want)
+    assert np.array_equal(nan_g, nan_w)
+    assert np.array_equal(bits(got[~nan_g]), bits(want[~nan_w]))
+    # the reference's latent NaN is real: ~40 % of collinear pairs, ~1 in 4 comparisons against a grey, and about 1 in 4,000
+    # GENERIC pairs — any real image's mean CIE94 error is NaN, which is why the mode is not built on the GPU (DESIGN.md section 2)
+    assert nan_g[:k].sum() > k // 10 and not nan_g[k:k + 1000].any() and nan_g[k + 1000:k + 2000].any()
+    assert 0 < nan_g[k + 2000:].sum() < (n - k - 2000) // 1000
+
+
 # ---------------------------------------------------------------- filter bank (ScielabProcessor ctor)
 @pytest.mark.parametrize("dpi,vd", [(72, 45.0), (96, 50.0), (150, 30.0), (300, 60.0), (20, 100.0), (600, 20.0), (224, 57.0)])
 def test_filter_bank(oracle, ref, dpi, vd):
