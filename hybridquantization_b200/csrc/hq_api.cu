@@ -232,7 +232,7 @@ int convert_image(hq_ctx* c, int width, int own_rows, int halo_top, int halo_bot
 
 int check_eval_args(hq_ctx* c, int B, int K, int space) {
     if (!c) return HQ_ERR_INVALID;
-    if (!c->have_image) return fail(c, HQ_ERR_NO_IMAGE, "no image: call hq_set_image_u8 first");
+    if (!c->have_image) return fail(c, HQ_ERR_NO_IMAGE, "no image: call hq_set_image_u8 or hq_set_image_f32_planar first");
     if (B < 1 || K < 1) return fail(c, HQ_ERR_INVALID, "B and K must be >= 1 (got B=%d K=%d)", B, K);
     if (K > HQ_MAX_COLORS_PRUNED) return fail(c, HQ_ERR_UNSUPPORTED, "K=%d exceeds HQ_MAX_COLORS_PRUNED=%d", K, HQ_MAX_COLORS_PRUNED);
     if (space != HQ_SPACE_LAB && space != HQ_SPACE_SRGB) return fail(c, HQ_ERR_INVALID, "unknown space %d", space);
@@ -711,7 +711,7 @@ static hq::ScRows sc_rows(const hq_ctx* c) { return hq::ScRows{c->halo_top, c->o
 // S-CIELAB representation of the resident image (sRGBToScielab, ScielabProcessor.java:374-381)
 static int sc_ensure_image(hq_ctx* c) {
     if (c->sc_image_ready) return HQ_OK;
-    if (!c->have_image) return fail(c, HQ_ERR_NO_IMAGE, "no image: call hq_set_image_u8 first");
+    if (!c->have_image) return fail(c, HQ_ERR_NO_IMAGE, "no image: call hq_set_image_u8 or hq_set_image_f32_planar first");
     if (c->sc_taps == 0) { int rc = hq_scielab_configure(c, 72, 45.0f); if (rc) return rc; }  // plugin defaults :229-231
     const int half = c->sc_taps / 2;
     if (c->width < half || c->g_rows < half)
@@ -724,7 +724,7 @@ static int sc_ensure_image(hq_ctx* c) {
         const int below = c->g_rows - (c->g_row0 + c->own_rows);
         const int need_bottom = below < half ? below : half;
         if (c->halo_top < need_top || c->halo_bottom < need_bottom || (c->own_rows > 0 && c->rows < half))
-            return fail(c, HQ_ERR_UNSUPPORTED, "S-CIELAB on a row shard needs %d halo rows above and %d below (got %d / %d): use hq_set_image_u8_sharded",
+            return fail(c, HQ_ERR_UNSUPPORTED, "S-CIELAB on a row shard needs %d halo rows above and %d below (got %d / %d): use hq_set_image_u8_sharded / hq_set_image_f32_planar_sharded",
                         need_top, need_bottom, c->halo_top, c->halo_bottom);
     }
     HQ_CUDA(c, c->d_sc_opp.reserve(3 * c->stride));
