@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 direct, 2 chunked, 3 prefilter (profiling)")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweeps", action="store_true", help="skip the strong_64mp / k_sweep / reference_faithful sub-records (profiling runs)")
+    ap.add_argument("--force-sweeps", action="store_true", help="k_sweep at any N (default: N = 1 and 8, BASELINE configs[4])")
     return ap.parse_args()
 
 
@@ -280,12 +282,37 @@ def main_reference(a, rank: int, world: int) -> None:
 
 
 # ------------------------------------------------------------------ GPU arm
+K_SWEEP = (8, 16, 32, 64, 128, 256, 512, 1024)
+
+
+def _file_sha(path: str) -> str:
+    import hashlib
+    return hashlib.sha256(open(path, "rb").read()).hexdigest()[:12]
+
+
+def measured_traffic(key: str):
+    """DRAM bytes per launch of a kernel from its last `ncu --set full` capture (profiles/traffic.json, written by
+    tools/ncu_summary.py).  Only reported while the kernel source is the one that was captured (sha of csrc/hq_kernels.cu)."""
+    tpath = os.path.join(REPO, "profiles", "traffic.json")
+    if not os.path.exists(tpath):
+        return None, "no ncu capture"
+    t = json.load(open(tpath))
+    v = t.get(key)
+    if isinstance(v, dict):
+        src = os.path.join(REPO, "hybridquantization_b200", "csrc", v.get("source_file", "hq_kernels.cu"))
+        if v.get("source_sha") and v["source_sha"] != _file_sha(src):
+            return None, f"stale: {v.get('capture')} was taken on another version of {v.get('source_file')}"
+        return v.get("bytes"), v.get("capture")
+    return v, t.get("source")
+
+
 def main_b200(a, rank: int, local_rank: int, world: int) -> None:
     import torch
     import torch.distributed as dist
 
-    from hybridquantization_b200 import EVAL_FORCE_CHUNKED, EVAL_FORCE_DIRECT, EVAL_FORCE_PREFILTER, EVAL_PRUNE, ImageManipulation, build, synth
-    from hybridquantization_b200.dist import install_nccl_allreduce, row_shard
+    from hybridquantization_b200 import (EVAL_FORCE_CHUNKED, EVAL_FORCE_DIRECT, EVAL_FORCE_PREFILTER, EVAL_PRUNE, PRUNE_OFF, SPACE_SRGB, SWASA,
+                                         ImageManipulation, build, synth)
+    from hybridquantization_b200.dist import install_native_nccl, row_shard, row_shard_with_halo
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
@@ -294,7 +321,7 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
     sampler = ClockSampler(local_rank)   # started first: by the timed region it has long been sampling
     sampler.start()
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)   # plumbing only: barriers, max over ranks, shipping the NCCL id bytes
     if rank == 0:
         build.build_library()
     if world > 1:
@@ -302,9 +329,7 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
 
     be = ImageManipulation("CIE76", False, True, local_rank)
     info = be.deviceInfo()
-    H = a.rows_per_gpu * world
-    r0, r1 = row_shard(H, world, rank)
-    n_shard, n_total = a.width * (r1 - r0), a.width * H
+    comm = install_native_nccl(be)   # the exchange step runs inside libhq_b200 (ncclAllReduce on the library's communicator)
     K, B = a.colors, a.batch
     flags = {0: 0, 1: EVAL_FORCE_DIRECT, 2: EVAL_FORCE_CHUNKED, 3: EVAL_FORCE_PREFILTER}[a.variant]
 
@@ -312,65 +337,83 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
     # context's own stream", so every launch and every timing event below is on this one stream
     bench_stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(bench_stream)
-
-    # inputs resident in HBM before the timed region
-    img = synth.synth_image_rows(a.width, H, synth.SEED_BASE + 3, r0, r1)
-    d_img = torch.from_numpy(img).to(dev)
     stream = bench_stream.cuda_stream
     assert stream != 0
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    peak = be.measureFp32Peak()  # FFMA microbenchmark at this device's current clocks
+    peak_tf = max(peak["ffma_tflops"], peak["ffma2_tflops"])
+    hbm_peak = None
+    ppath = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(ppath):
+        hbm_peak = json.load(open(ppath)).get("hbm_gbs")
+    hbm_source = "MEASURED_PEAKS.json hbm_gbs (of measured)" if hbm_peak else "fallback 6650 GB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+    hbm_bw = hbm_peak or 6650.0
+
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed_device_steps(ctx, d_pal, Bn, Kn, d_res, fl, steps, warmup, n_total_px, profile=False):
+        """W warm-up + K timed launches of the scoring kernel (+ the library's all-reduce), inputs resident in HBM, one CUDA
+        event pair per step on the launching stream, L2 flushed between steps; returns (seconds: max over ranks of the summed
+        step times, kernel ms list, wall window)."""
+        nwords = d_res.numel()
+
+        def step():
+            ctx.evalPalettesDevice(d_pal.data_ptr(), Bn, Kn, d_res.data_ptr(), a.space, fl, stream)
+            if world > 1:
+                ctx.commAllreduce(d_res.data_ptr(), nwords, stream)
+
+        for _ in range(warmup):
+            flush.fill_(1)
+            step()
+        torch.cuda.synchronize()
+        if not bool((d_res[:, 1:1 + Kn].sum(dim=1) == n_total_px).all().item()):
+            raise SystemExit("bench: counts do not sum to the pixel count — the kernel is not doing the work")
+        if profile:
+            ctx.setProfiling(True)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        kms = []
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        for i in range(steps):
+            flush.fill_(i & 255)          # L2 flush between timed iterations (outside the event pair)
+            ev[i][0].record()
+            step()
+            ev[i][1].record()
+            if profile:
+                ev[i][1].synchronize()
+                kms.append(ctx.lastAssignMs())
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        w1 = time.perf_counter()
+        if profile:
+            ctx.setProfiling(False)
+        return max_over_ranks(sum(e0.elapsed_time(e1) for e0, e1 in ev)) * 1e-3, kms, (w0, w1)
+
+    # ================================================================== the headline workload (weak: 4K rows per GPU)
+    H = a.rows_per_gpu * world
+    r0, r1 = row_shard(H, world, rank)
+    n_shard, n_total = a.width * (r1 - r0), a.width * H
+    img = synth.synth_image_rows(a.width, H, synth.SEED_BASE + 3, r0, r1)
+    d_img = torch.from_numpy(img).to(dev)
     be.setImageDevice(d_img.data_ptr(), a.width, r1 - r0, stream=stream)
     pal = synth.synth_palettes(B, K)
     d_pal = torch.from_numpy(pal).to(dev)
     words = be.resultWords(K, 0)
     d_res = torch.zeros((B, words), dtype=torch.int64, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     torch.cuda.synchronize()
-
-    peak = be.measureFp32Peak()  # FFMA microbenchmark at this device's current clocks
-
-    def step():
-        be.evalPalettesDevice(d_pal.data_ptr(), B, K, d_res.data_ptr(), a.space, flags, stream)
-        if world > 1:
-            dist.all_reduce(d_res, op=dist.ReduceOp.SUM)
-
-    for _ in range(a.warmup):
-        flush.fill_(1)
-        step()
-    torch.cuda.synchronize()
-    counts_ok = bool((d_res[:, 1:1 + K].sum(dim=1) == n_total).all().item())
-    if not counts_ok:
-        raise SystemExit("bench: counts do not sum to the pixel count — the kernel is not doing the work")
-
     sampler.wait_ready()
-    be.setProfiling(True)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
-    kernel_ms = []
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t_wall0 = time.perf_counter()
-    for i in range(a.steps):
-        flush.fill_(i & 255)          # L2 flush between timed iterations (outside the event pair)
-        ev[i][0].record()
-        step()
-        ev[i][1].record()
-        ev[i][1].synchronize()
-        kernel_ms.append(be.lastAssignMs())
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t_wall1 = time.perf_counter()
-    be.setProfiling(False)
-    step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_s = float(total_ms.item()) * 1e-3
+    total_s, kernel_ms, (t_wall0, t_wall1) = timed_device_steps(be, d_pal, B, K, d_res, flags, a.steps, a.warmup, n_total, profile=True)
     value = n_total * B * a.steps / total_s / 1e9
     clocks = sampler.summary(t_wall0, t_wall1)
 
     # ---- e2e: host buffers through the C ABI call, H2D + D2H inside the timed region
-    install_nccl_allreduce(be)
     for _ in range(max(1, a.warmup // 2)):
         be.evalPalettes(pal, a.space, flags=flags)
     torch.cuda.synchronize()
@@ -379,12 +422,9 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
     t0 = time.perf_counter()
     for i in range(a.steps):
         r = be.evalPalettes(pal, a.space, flags=flags)
-    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
     assert int(r["counts"][0].sum()) == n_total
-    e2e_value = n_total * B * a.steps / float(t_e2e.item()) / 1e9
-    sampler.stop()
+    e2e_value = n_total * B * a.steps / t_e2e / 1e9
 
     # ---- the same step through the EXACT PRUNED kernel (HQ_EVAL_PRUNE, csrc/hq_pruned.cu): identical integers, ~K/S times
     # less arithmetic.  Reported beside the exhaustive kernel, never instead of it: `value`, `e2e` and `roofline` above are
@@ -392,47 +432,66 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
     pruned = None
     if a.space == 0:
         d_res2 = torch.zeros_like(d_res)
-        def pstep():
-            be.evalPalettesDevice(d_pal.data_ptr(), B, K, d_res2.data_ptr(), a.space, flags | EVAL_PRUNE, stream)
-            if world > 1:
-                dist.all_reduce(d_res2, op=dist.ReduceOp.SUM)
-        for _ in range(a.warmup):
-            flush.fill_(1)
-            pstep()
-        torch.cuda.synchronize()
+        p_s, _, _ = timed_device_steps(be, d_pal, B, K, d_res2, flags | EVAL_PRUNE, a.steps, a.warmup, n_total)
         if not torch.equal(d_res2, d_res):
             raise SystemExit("bench: the pruned kernel's integers differ from the exhaustive kernel's")
         be.setProfiling(True)
-        pev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        for i in range(a.steps):
-            flush.fill_(i & 255)
-            pev[i][0].record()
-            pstep()
-            pev[i][1].record()
+        be.evalPalettesDevice(d_pal.data_ptr(), B, K, d_res2.data_ptr(), a.space, flags | EVAL_PRUNE, stream)
         torch.cuda.synchronize()
         stats = be.pruningStats()
         be.setProfiling(False)
-        p_ms = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in pev)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(p_ms, op=dist.ReduceOp.MAX)
-        p_s = float(p_ms.item()) * 1e-3
         t0 = time.perf_counter()
         for i in range(a.steps):
             r2 = be.evalPalettes(pal, a.space, flags=flags | EVAL_PRUNE)
-        t_p = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_p, op=dist.ReduceOp.MAX)
+        t_p = max_over_ranks(time.perf_counter() - t0)
         assert np.array_equal(r2["err_fx"], r["err_fx"]) and np.array_equal(r2["counts"], r["counts"])
         pruned = {"value": n_total * B * a.steps / p_s / 1e9, "unit": UNIT, "ms_per_step": 1e3 * p_s / a.steps,
                   "swasa_evals_per_s": B * a.steps / p_s, "speedup_over_exhaustive": total_s / p_s,
-                  "e2e": {"value": n_total * B * a.steps / float(t_p.item()) / 1e9, "unit": UNIT, "evals_per_s": B * a.steps / float(t_p.item())},
+                  "e2e": {"value": n_total * B * a.steps / t_p / 1e9, "unit": UNIT, "evals_per_s": B * a.steps / t_p},
                   "chunks": stats["chunks"], "mean_surviving_colours": stats["mean_survivors"], "of_colours": K,
                   "identical_to_exhaustive": True,
                   "note": "exact geometric pruning (hq_pruned.cu): pixels cell-sorted once per image, per (chunk, candidate) only colours that can be "
                           "nearest to some pixel of the chunk are swept; not the kernel the roofline above describes"}
+
+    # ================================================================== parity of the sharded path, checked in this very run (N > 1)
+    parity = None
+    if world > 1:
+        PB, PIT = 8, 30
+        sub = pal[:PB]
+        got = be.evalPalettes(sub, a.space, sums=True, flags=flags)                 # all-reduced totals, exhaustive kernel
+        got_pr = be.evalPalettes(sub, a.space, sums=True, flags=flags | EVAL_PRUNE) if a.space == 0 else got
+        sw = dict(population=4, imax=PIT, seed=77760, space=a.space)
+        best, err, tr, its = be.findBestQuantization(K, SWASA(**sw), n_total=n_total, trace=True)   # sharded search, native all-reduce per iteration
+        blob = torch.from_numpy(np.concatenate([got["err_fx"], got["counts"].astype(np.int64).ravel(), got["sums_fx"].ravel(),
+                                                tr.view(np.int64).ravel(), best.view(np.int32).astype(np.int64).ravel()])).to(dev)
+        ref = blob.clone()
+        dist.broadcast(ref, 0)
+        same = torch.tensor([int(torch.equal(blob, ref))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        parity = {"candidates": PB, "search_iterations": PIT, "same_on_all_ranks": bool(same.item()),
+                  "pruned_equals_exhaustive": all(np.array_equal(got[k], got_pr[k]) for k in ("err_fx", "counts", "sums_fx")),
+                  "exchange": f"ncclAllReduce(int64, sum) on libhq_b200's own communicator (hq_comm_init_rank), NCCL {comm['nccl_version']}, "
+                              f"{comm['size']} ranks; torch.distributed only shipped the 128 id bytes"}
+        if rank == 0:   # the whole image on ONE GPU, no exchange: the integers and the trajectory must be the same
+            whole = synth.synth_image_rows(a.width, H, synth.SEED_BASE + 3, 0, H)
+            single = ImageManipulation("CIE76", False, True, local_rank)
+            single.setImage(whole)
+            want = single.evalPalettes(sub, a.space, sums=True, flags=flags)
+            single.setPruning(PRUNE_OFF)   # the single-GPU search scores exhaustively; the sharded one above under the default policy
+            sbest, serr, str_, sits = single.findBestQuantization(K, SWASA(**sw), trace=True)
+            single.close()
+            del whole
+            parity["evals_equal_single_gpu"] = all(np.array_equal(got[k], want[k]) for k in ("err_fx", "counts", "sums_fx"))
+            parity["search_trace_equal_single_gpu"] = bool(np.array_equal(tr.view(np.uint64), str_.view(np.uint64)) and err == serr and its == sits == PIT
+                                                           and np.array_equal(best.view(np.uint32), sbest.view(np.uint32)))
+            parity["ok"] = bool(parity["evals_equal_single_gpu"] and parity["search_trace_equal_single_gpu"] and parity["same_on_all_ranks"]
+                                and parity["pruned_equals_exhaustive"])
+        okt = torch.tensor([int(parity.get("ok", True))], device=dev)
+        dist.broadcast(okt, 0)
+        if not bool(okt.item()):
+            if rank == 0:
+                print(json.dumps({"error": "sharded result differs from the single-GPU result", "parity": parity}), file=sys.stderr, flush=True)
+            raise SystemExit("bench: the sharded path's integers / trajectory differ from the single-GPU ones")
 
     # ---- the one-time image conversion kernel (HBM-bound by design: 15 B/pixel), CUDA events around the kernel
     be.setProfiling(True)
@@ -443,6 +502,76 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
         rl_ms.append(be.lastRgbToLabMs())
     be.setProfiling(False)
     rl_ms = sorted(rl_ms[1:])[len(rl_ms[1:]) // 2]
+
+    # ================================================================== C5: palette-size sweep on ONE 4K image (strong over the N GPUs)
+    k_sweep = None
+    if not a.no_sweeps and (world in (1, 8) or a.force_sweeps):
+        sw_rows = a.rows_per_gpu
+        s0_, s1_ = row_shard(sw_rows, world, rank)
+        simg = torch.from_numpy(synth.synth_image_rows(a.width, sw_rows, synth.SEED_BASE + 5, s0_, s1_)).to(dev)
+        be.setImageDevice(simg.data_ptr(), a.width, s1_ - s0_, stream=stream)
+        n_sw = a.width * sw_rows
+        k_sweep = {"image": f"{a.width}x{sw_rows} synthetic RGB, rows sharded over {world} GPU(s)", "steps": 5, "warmup": 3, "rows": [],
+                   "roofline": "t_floor = max(12 B x pixels-per-GPU / HBM peak, 8 K flop x pixels-per-GPU x candidates / FP32 peak); frac = t_floor / t_measured "
+                               "(at N > 1 the measured time includes the all-reduce, the floor does not)",
+                   "hbm_gbs_peak": hbm_bw, "hbm_peak_source": hbm_source, "fp32_tflops_peak": peak_tf}
+        for Ks in K_SWEEP:
+            row = {"K": Ks}
+            for Bs in (1, B):
+                spal = torch.from_numpy(synth.synth_palettes(Bs, Ks)).to(dev)
+                sres = torch.zeros((Bs, be.resultWords(Ks, 0)), dtype=torch.int64, device=dev)
+                t_s, _, _ = timed_device_steps(be, spal, Bs, Ks, sres, 0, 5, 3, n_sw)
+                ms = 1e3 * t_s / 5
+                t_hbm = 12.0 * (n_sw / world) / (hbm_bw * 1e9) * 1e3
+                t_fp = 8.0 * Ks * (n_sw / world) * Bs / (peak_tf * 1e12) * 1e3
+                row[f"b{Bs}"] = {"ms_per_step": ms, "gpixel_per_s": n_sw * Bs / (ms * 1e-3) / 1e9, "evals_per_s": Bs / (ms * 1e-3),
+                                 "bound": "hbm" if t_hbm > t_fp else "fp32", "roofline_floor_ms": max(t_hbm, t_fp), "frac": max(t_hbm, t_fp) / ms}
+            k_sweep["rows"].append(row)
+        del simg
+
+    # ================================================================== C4: ONE 64 MP image, strong scaling over the N GPUs
+    strong = None
+    if not a.no_sweeps:
+        SW = SH = 8192
+        g0, g1 = row_shard(SH, world, rank)
+        gimg = torch.from_numpy(synth.synth_image_rows(SW, SH, synth.SEED_BASE + 4, g0, g1)).to(dev)
+        be.setImageDevice(gimg.data_ptr(), SW, g1 - g0, stream=stream)
+        s_steps, s_warm = 5, 3
+        s_s, s_kms, (sw0, sw1) = timed_device_steps(be, d_pal, B, K, d_res, flags, s_steps, s_warm, SW * SH, profile=True)
+        k_ms_s = sum(s_kms) / len(s_kms)
+        strong = {"workload": f"{SW}x{SH} (64 MP) synthetic RGB, FIXED image, rows sharded over {world} GPU(s), {K}-colour palettes, {B} candidates per launch",
+                  "scaling": "strong", "n_gpus": world, "steps": s_steps, "warmup": s_warm, "ms_per_step": 1e3 * s_s / s_steps,
+                  "value": SW * SH * B * s_steps / s_s / 1e9, "unit": UNIT, "swasa_evals_per_s": B * s_steps / s_s,
+                  "kernel_ms_rank0": k_ms_s, "roofline_frac_rank0": (8.0 * K * SW * (g1 - g0) * B / (k_ms_s * 1e-3) / 1e12) / peak_tf,
+                  "clocks": sampler.summary(sw0, sw1)}
+        del gimg
+
+    # ================================================================== the plugin's REAL cost model on the headline image (row f1)
+    faithful = None
+    if not a.no_sweeps and world == 1:
+        be.setImage(img)
+        be.scielabConfigure(72, 45.0)
+        FB = 4
+        fpal = pal[:FB]
+        be.scielabImage()                          # S-CIELAB of the original: once per image
+        for _ in range(2):
+            fr = be.evalPalettesScielab(fpal, SPACE_SRGB)
+        torch.cuda.synchronize()
+        reps = 5
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fr = be.evalPalettesScielab(fpal, SPACE_SRGB)
+        dt = (time.perf_counter() - t0) / reps
+        assert int(fr["counts"][0].sum()) == n_shard
+        sc_flop = 650.0   # per pixel and candidate: 2 x 21 taps x 7 filter planes x 2 flop + Opp->Lab + dE
+        faithful = {"workload": f"{a.width}x{a.rows_per_gpu}, {K} colours, {FB} candidates per call, sRGB assignment + 21-tap S-CIELAB filters + CIE76 "
+                                "(what the reference plugin computes per candidate, ImageManipulation.java:635-699)",
+                    "call": "hq_eval_palettes_scielab (host palettes in, host integers out)",
+                    "e2e": {"evals_per_s": FB / dt, "gpixel_per_s": FB * n_shard / dt / 1e9, "ms_per_candidate": 1e3 * dt / FB,
+                            "h2d_bytes_per_step": int(fpal.nbytes), "d2h_bytes_per_step": int(FB * words * 8)},
+                    "roofline": {"bound": "fp32", "flop_per_pixel_filter_stage": sc_flop, "assign_flop_per_pixel": 8.0 * K,
+                                 "achieved_tflops_whole_call": (sc_flop + 8.0 * K) * n_shard * FB / dt / 1e12, "peak": peak_tf,
+                                 "frac_whole_call": (sc_flop + 8.0 * K) * n_shard * FB / dt / 1e12 / peak_tf}}
 
     # ---- what a search pays ONCE per image before its first evaluation (not part of `value` / `e2e`, which time the
     # per-iteration call as the reference's loop issues it): host image upload + RGB->Lab, and the cell sort of the pruned path
@@ -463,20 +592,13 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
     t0 = time.perf_counter(); be2.setImageFloat(planes); setup["set_image_f32_planar_host_ms"] = 1e3 * (time.perf_counter() - t0)
     del planes
     be2.close()
+    sampler.stop()
 
     # ---- roofline of the dominant kernel (assign_reduce_kernel): FP32 CUDA-core bound at K=256
     flops_per_launch = 8.0 * K * n_shard * B
     k_ms = sum(kernel_ms) / len(kernel_ms)
     achieved = flops_per_launch / (k_ms * 1e-3) / 1e12
-    peak_tf = max(peak["ffma_tflops"], peak["ffma2_tflops"])
-    traffic = None
-    tpath = os.path.join(REPO, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(f"assign_reduce_w{a.width}_h{a.rows_per_gpu}_k{K}_b{B}")
-    hbm_peak = None
-    ppath = os.path.join(REPO, "MEASURED_PEAKS.json")
-    if os.path.exists(ppath):
-        hbm_peak = json.load(open(ppath)).get("hbm_gbs")
+    traffic, traffic_src = measured_traffic(f"assign_reduce_w{a.width}_h{a.rows_per_gpu}_k{K}_b{B}")
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -484,27 +606,40 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a, world), "timing": "CUDA events per step on the launching stream, max over ranks; "
                    "L2 flushed (256 MiB write) between timed iterations", "space": "LAB" if a.space == 0 else "SRGB",
-                   "parallelism": f"row-shard x{world} + int64 all-reduce" if world > 1 else "single GPU", "device": info["name"]},
+                   "parallelism": (f"row-shard x{world} + ncclAllReduce(int64) inside libhq_b200 (NCCL {comm['nccl_version']})" if world > 1 else "single GPU"),
+                   "device": info["name"]},
         "swasa_evals_per_s": B * a.steps / total_s,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pal.nbytes), "d2h_bytes_per_step": int(B * words * 8),
-                "evals_per_s": B * a.steps / float(t_e2e.item()),
-                "call": "hq_eval_palettes (host palettes in, host integers out); the image is uploaded once per search, as in the reference"},
+                "evals_per_s": B * a.steps / t_e2e,
+                "call": "hq_eval_palettes (host palettes in, host integers out; at N > 1 the all-reduce is the library's own); the image is uploaded once per search, as in the reference"},
         "gpu_launches": 2 * a.steps,
         "clocks": clocks,
         "roofline": {"bound": "fp32", "kernel": "assign_reduce_kernel", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic,
+                     "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": "FFMA/FFMA2 microbenchmark (hq_measure_fp32_peak) in this run; MEASURED_PEAKS.json has no FP32 CUDA-core figure",
                      "peak_ffma_tflops": peak["ffma_tflops"], "peak_ffma2_tflops": peak["ffma2_tflops"],
                      "kernel_ms": k_ms, "flops_per_launch": flops_per_launch, "flop_per_pair": 8,
+                     "frac_kind": "ALGORITHMIC: 8 flop per (pixel, colour) pair as SURVEY 8(d) counts the direct form (3 sub, 3 mul, 2 add) over the measured "
+                                  "FFMA peak.  The kernel EXECUTES 3 FFMA (6 flop) per pair in its expanded-form prefilter plus an exact direct-form re-check of "
+                                  "one 8-colour chunk per pixel (about 6.4 flop per pair in all); FMA-pipe utilisation from ncu is in profiles/",
+                     "executed_flop_per_pair": 6.0 + 8.0 * 8 / K if K > 32 else 8.0,
                      "algorithmic_bytes_per_launch": 12 * n_shard, "hbm_gbs_measured_peak": hbm_peak,
                      "hbm_floor_ms": (12 * n_shard / (hbm_peak * 1e9) * 1e3) if hbm_peak else None},
     }
     line["secondary_rooflines"] = [{"kernel": "rgb_to_lab_kernel", "bound": "hbm", "achieved": 15.0 * n_shard / (rl_ms * 1e-3) / 1e9,
-                                    "peak": hbm_peak, "unit": "GB/s", "frac": (15.0 * n_shard / (rl_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
+                                    "peak": hbm_bw, "unit": "GB/s", "frac": 15.0 * n_shard / (rl_ms * 1e-3) / 1e9 / hbm_bw,
                                     "kernel_ms": rl_ms, "algorithmic_bytes_per_pixel": 15, "runs": "once per image, not per step",
-                                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if hbm_peak else None}]
+                                    "peak_source": hbm_source}]
     if pruned is not None:
         line["pruned"] = pruned
+    if parity is not None:
+        line["parity"] = parity
+    if strong is not None:
+        line["strong_64mp"] = strong
+    if k_sweep is not None:
+        line["k_sweep"] = k_sweep
+    if faithful is not None:
+        line["reference_faithful"] = faithful
     line["once_per_image"] = setup
     if world == 1 and rank == 0 and not a.no_cpu_baseline:
         cb = run_reference_kernels(a, steps=1000, warmup=1, seconds_budget=a.cpu_baseline_seconds)

@@ -21,6 +21,7 @@ EVAL_SUMS, EVAL_FORCE_DIRECT, EVAL_FORCE_CHUNKED, EVAL_FORCE_PREFILTER, EVAL_PRU
 PRUNE_OFF, PRUNE_AUTO, PRUNE_ON = 0, 1, 2
 MAX_COLORS = 1024
 MAX_COLORS_PRUNED = 4096
+COMM_ID_BYTES = 128
 
 
 class HqError(RuntimeError):
@@ -76,6 +77,12 @@ SIGNATURES = {
     "hq_scielab_build_filters": (C.c_int, [C.c_int, C.c_float, _P, _P, C.POINTER(C.c_int)]),
     "hq_eval_palettes_scielab": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "hq_set_allreduce": (C.c_int, [_P, ALLREDUCE_FN, _P]),
+    "hq_comm_get_unique_id": (C.c_int, [_P]),
+    "hq_comm_init_rank": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "hq_comm_allreduce": (C.c_int, [_P, _P, C.c_size_t, _P]),
+    "hq_comm_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "hq_create_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    "hq_multi_device_count": (C.c_int, [_P]),
     "hq_swasa_default_params": (None, [C.POINTER(SwasaParams)]),
     "hq_find_best_quantization": (C.c_int, [_P, C.c_int, C.POINTER(SwasaParams), C.c_uint64, _P, C.POINTER(C.c_double), _P, C.POINTER(C.c_int)]),
     "hq_request_stop": (None, [_P]),

@@ -46,13 +46,32 @@ def sources() -> list[str]:
     return src
 
 
+CU_FILES = ("hq_kernels.cu", "hq_pruned.cu", "hq_scielab.cu", "hq_api.cu", "hq_multi.cu")
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    cu = [os.path.join(CSRC, f) for f in ("hq_kernels.cu", "hq_pruned.cu", "hq_scielab.cu", "hq_api.cu")]
+    """One object per .cu (compiled in parallel, only when stale against its own source and the shared headers), then one link."""
+    from concurrent.futures import ThreadPoolExecutor
+
     if not force and not _stale(LIB, sources()):
-        return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + cu
-    print("[build]", " ".join(cmd), flush=True)
-    subprocess.run(cmd, check=True)
+        return LIB  # (the objects stay behind on this machine; the .so alone travels to the GPU box)
+    headers = [s for s in sources() if not s.endswith(".cu")]
+    objdir = os.path.join(ROOT, "build")
+    os.makedirs(objdir, exist_ok=True)
+    jobs = []
+    for f in CU_FILES:
+        src, obj = os.path.join(CSRC, f), os.path.join(objdir, f[:-3] + ".o")
+        if force or _stale(obj, [src] + headers):
+            jobs.append([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src])
+    def run(cmd):
+        print("[build]", " ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
+
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
+        list(ex.map(run, jobs))
+    objs = [os.path.join(objdir, f[:-3] + ".o") for f in CU_FILES]
+    # libdl: NCCL is resolved at run time with dlopen (hq_multi.cu), so the library loads on machines without it
+    run([_nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-ldl"])
     return LIB
 
 

@@ -1,207 +1,11 @@
 // hq_api.cu — the C ABI (include/hq_b200.h): context, device memory, launch orchestration.
 // No CPU fallback: every compute entry fails with HQ_ERR_CUDA if the device is unusable.
-#include <cuda_runtime.h>
+#include "hq_ctx.h"
 
-#include <atomic>
-#include <chrono>
-#include <cstdarg>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <string>
-#include <thread>
-#include <vector>
-
-#include "../../include/hq_b200.h"
-#include "../../include/hq_plugin.hpp"
-#include "hq_kernels.cuh"
-#include "hq_math.h"
+namespace hqi { thread_local std::string g_create_error; }
+using namespace hqi;
 
 namespace {
-
-thread_local std::string g_create_error;
-
-template <typename T>
-struct DevBuf {
-    T* p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t count) {
-        if (count <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
-        if (e == cudaSuccess) cap = count;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-template <typename T>
-struct PinBuf {
-    T* p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t count) {
-        if (count <= cap) return cudaSuccess;
-        if (p) cudaFreeHost(p);
-        p = nullptr; cap = 0;
-        cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&p), count * sizeof(T));
-        if (e == cudaSuccess) cap = count;
-        return e;
-    }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
-};
-
-}  // namespace
-
-struct hq_ctx {
-    int device = 0;
-    int sm_count = 0;
-    int clock_khz = 0;
-    char name[128] = {0};
-    cudaStream_t stream = nullptr;
-    std::string err;
-
-    // image state (this rank's shard)
-    size_t n = 0, stride = 0;
-    int width = 0, rows = 0, whitepoint = 0;   // rows = local rows INCLUDING halo rows
-    int halo_top = 0, halo_bottom = 0, own_rows = 0;  // rows [halo_top, halo_top + own_rows) are this rank's own
-    int g_row0 = 0, g_rows = 0;                // global index of the first own row, global image height
-    size_t own_lo = 0, own_hi = 0;             // own pixel range inside the local arrays
-    bool have_image = false, have_unit = false;
-    bool image_f32 = false;                    // the resident image is the planar float one (d_unit); d_rgb is not used then
-    DevBuf<unsigned int> d_flag;               // out-of-range report of the float conversion
-    DevBuf<uint8_t> d_rgb;
-    DevBuf<float> d_lab, d_unit, d_table;
-
-    // evaluation scratch
-    DevBuf<float> d_pal;
-    DevBuf<float4> d_pal_lab, d_pal_rgb;
-    DevBuf<unsigned long long> d_results;
-    DevBuf<uint8_t> d_idx;
-    DevBuf<uint8_t> d_out_rgb;
-    DevBuf<float> d_out_f32;
-    PinBuf<float> h_pal;
-    PinBuf<unsigned long long> h_results;
-    PinBuf<unsigned long long> h_flag;      // sequence number written by export_results_kernel after the result words
-    unsigned long long export_seq = 0;
-    DevBuf<unsigned> d_export_counter;      // ticket counter of the scoring kernels' export tail (zero between launches)
-    bool direct_io = true;                  // HQ_DIRECT_IO=0: the H2D copy / D2H copy / stream wait path instead (A/B measurements)
-
-    // exact pruning (hq_pruned.cu): cell-sorted copy of the own pixels, chunk table, boxes; built on first use per image
-    int prune_mode = HQ_PRUNE_AUTO;
-    struct PrunedSet {   // one cell-sorted copy of (a range of) the resident image
-        bool ready = false;
-        int space = -1;
-        size_t sstride = 0;
-        unsigned nchunks = 0;
-        DevBuf<float> sorted, box;
-        DevBuf<unsigned> perm, chunk_start, chunk_len;
-        void release() { sorted.release(); box.release(); perm.release(); chunk_start.release(); chunk_len.release(); ready = false; }
-    };
-    PrunedSet pr_own;   // CIELAB features of the OWN pixels: the LAB cost model (error, counts, sums; no indices)
-    PrunedSet pr_all;   // features of EVERY local pixel (own + halo) in the space asked for, with their image positions:
-                        // index-producing evaluations (the S-CIELAB chain, hq_quantize)
-    DevBuf<unsigned> d_pr_scratch;
-    DevBuf<unsigned long long> d_pr_stats;
-    PinBuf<unsigned long long> h_pr_small;
-
-    // S-CIELAB stage (next row 1)
-    std::vector<float> sc_filters7, sc_abs3;  // [7][taps], [taps] as ScielabProcessor builds them
-    std::vector<float> sc_block;              // [8][taps] device layout, host copy
-    bool sc_generic = false;                  // test hook: force the generic (any-taps) kernels
-    int sc_taps = 0;
-    bool sc_image_ready = false;
-    DevBuf<float> d_sc_filters, d_sc_opp, d_sc_tmp, d_sc_lab, d_sc_lab2, d_sc_map;
-    DevBuf<uint8_t> d_sc_rgb2, d_sc_map8;
-    DevBuf<float4> d_sc_tab;
-    DevBuf<unsigned long long> d_sc_err;
-
-    // CUDA graph of one host-buffer evaluation (H2D palettes, palette kernel, scoring kernel, D2H results): a search repeats
-    // the same launch set thousands of times; for small images the per-launch driver cost dominated an iteration
-    struct EvalKey {
-        int B = 0, K = 0, space = 0, flags = 0; unsigned long long image_gen = 0;
-        const void *d_pal = nullptr, *d_results = nullptr, *h_pal = nullptr, *h_results = nullptr, *d_pal_lab = nullptr, *d_pal_rgb = nullptr;
-        bool operator==(const EvalKey& o) const {
-            return B == o.B && K == o.K && space == o.space && flags == o.flags && image_gen == o.image_gen && d_pal == o.d_pal &&
-                   d_results == o.d_results && h_pal == o.h_pal && h_results == o.h_results && d_pal_lab == o.d_pal_lab && d_pal_rgb == o.d_pal_rgb;
-        }
-    };
-    EvalKey graph_key, seen_key;
-    cudaGraphExec_t graph_exec = nullptr;
-    unsigned long long image_gen = 0;
-    bool use_graphs = false;  // off by default: see hq_set_graphs
-
-    hq_progress_fn progress = nullptr;
-    void* progress_user = nullptr;
-    hq_allreduce_fn allreduce = nullptr;
-    void* allreduce_user = nullptr;
-    bool profiling = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
-    bool ev_valid = false, ev_rl_valid = false;
-    std::atomic<bool> stop{false};
-    volatile bool stop_flag_view = false;
-};
-
-namespace {
-
-int fail(hq_ctx* c, int code, const char* fmt, ...) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
-    va_end(ap);
-    if (c) c->err = buf; else g_create_error = buf;
-    return code;
-}
-
-#define HQ_CUDA(c, call)                                                                   \
-    do {                                                                                   \
-        cudaError_t e__ = (call);                                                          \
-        if (e__ != cudaSuccess)                                                            \
-            return fail((c), HQ_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
-    } while (0)
-
-// Completion wait of the per-iteration calls (hq_eval_palettes*): poll the stream for a few milliseconds before falling
-// back to cudaStreamSynchronize.  The default synchronisation may yield the CPU, and in a process with other busy threads
-// (a Python host with a thread pool, a JVM) the wake-up then costs as much as a whole pruned scoring step — measured: a
-// 1080p search of 1,000 iterations took 0.18 s instead of 0.09 s, a 4K / 64-candidate one 0.67 s instead of 0.37 s.
-cudaError_t wait_stream(cudaStream_t st) {
-    using clock = std::chrono::steady_clock;
-    const auto t0 = clock::now();
-    for (;;) {
-        for (int i = 0; i < 64; ++i) {
-            const cudaError_t e = cudaStreamQuery(st);
-            if (e != cudaErrorNotReady) return e;
-        }
-        if (clock::now() - t0 > std::chrono::milliseconds(8)) return cudaStreamSynchronize(st);
-    }
-}
-
-// Spin on the sequence number export_results_kernel writes into pinned host memory after the result words; the stream is
-// queried now and then so that a failed launch surfaces as an error instead of a hang.
-cudaError_t wait_flag(const unsigned long long* flag, unsigned long long seq, cudaStream_t st) {
-    using clock = std::chrono::steady_clock;
-    const volatile unsigned long long* f = flag;
-    const auto t0 = clock::now();
-    for (;;) {
-        for (int i = 0; i < 2048; ++i)
-            if (*f == seq) { std::atomic_thread_fence(std::memory_order_acquire); return cudaSuccess; }  // result words are read after this
-        cudaError_t e = cudaStreamQuery(st);
-        if (e == cudaErrorNotReady && clock::now() - t0 > std::chrono::milliseconds(8)) e = cudaStreamSynchronize(st);  // long kernel: stop burning a core
-        if (e == cudaSuccess) return *f == seq ? cudaSuccess : cudaErrorUnknown;
-        if (e != cudaErrorNotReady) return e;
-    }
-}
-
-// no C++ exception (std::bad_alloc from a host-side vector, std::runtime_error from the host classes) may cross the C ABI
-int api_exception(hq_ctx* c, const std::exception& ex) {
-    if (c) c->err = std::string("internal error: ") + ex.what();
-    return HQ_ERR_CUDA;
-}
-
-int bind_device(hq_ctx* c) {
-    HQ_CUDA(c, cudaSetDevice(c->device));
-    return HQ_OK;
-}
 
 // sRGB-assign mode needs the unit planes; they are produced on first use from the resident RGB
 int ensure_unit(hq_ctx* c, cudaStream_t st) {
@@ -379,7 +183,15 @@ int hq_create(int device, hq_ctx** out) {
 
 void hq_destroy(hq_ctx* c) {
     if (!c) return;
+    if (c->is_multi()) {   // the leader owns its members
+        std::vector<hq_ctx*> ms(c->members.begin() + 1, c->members.end());
+        c->members.clear();
+        for (hq_ctx* m : ms) { m->leader = nullptr; hq_destroy(m); }
+    }
     cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    comm_release(c);
+    if (c->ev_image) cudaEventDestroy(c->ev_image);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -406,11 +218,40 @@ int hq_device_info(const hq_ctx* c, int* sm_count, int* sm_clock_khz, char* name
     return HQ_OK;
 }
 
-uint64_t hq_image_pixels(const hq_ctx* c) { return c ? (uint64_t)(c->own_hi - c->own_lo) : 0; }
+uint64_t hq_image_pixels(const hq_ctx* c) {
+    if (!c) return 0;
+    if (c->is_multi()) return (uint64_t)c->m_width * (uint64_t)c->m_rows;  // the whole image the members share
+    return (uint64_t)(c->own_hi - c->own_lo);
+}
 
-int hq_set_image_u8_sharded(hq_ctx* c, const uint8_t* rgb, int width, int own_rows, int halo_top, int halo_bottom,
-                            int global_row0, int global_rows, int whitepoint) try {
-    if (!c) return HQ_ERR_INVALID;
+namespace {
+// the image of a context has changed hands: forget a foreign-stream conversion (hq_set_image_u8_device)
+void image_on_own_stream(hq_ctx* c) { c->image_foreign = false; }
+
+// row block of member i of G (rows i*H/G .. (i+1)*H/G) plus the neighbour rows the S-CIELAB stage's vertical
+// filter reaches; an empty block carries no halo (there is nothing to filter)
+struct Shard { int r0, own, ht, hb; };
+Shard shard_of(int H, int G, int i, int halo) {
+    const int r0 = (int)((long long)H * i / G), r1 = (int)((long long)H * (i + 1) / G);
+    if (r1 == r0) return Shard{r0, 0, 0, 0};
+    return Shard{r0, r1 - r0, halo < r0 ? halo : r0, halo < H - r1 ? halo : H - r1};
+}
+// halo rows of a multi-device context: the filter bank configured when the image arrives (21 taps by default -> 10)
+int multi_halo(const hq_ctx* c) { const int h = c->sc_taps / 2; return h > 10 ? h : 10; }
+int member_rc(hq_ctx* leader, hq_ctx* m, int rc) {
+    if (rc != HQ_OK && m != leader) leader->err = "device " + std::to_string(m->device) + ": " + m->err;
+    return rc;
+}
+int sync_members(hq_ctx* c) {
+    for (hq_ctx* m : c->members) {
+        HQ_CUDA(c, cudaSetDevice(m->device));
+        HQ_CUDA(c, cudaStreamSynchronize(m->stream));
+    }
+    return bind_device(c);
+}
+
+int set_image_u8_shard(hq_ctx* c, const uint8_t* rgb, int width, int own_rows, int halo_top, int halo_bottom,
+                       int global_row0, int global_rows, int whitepoint, bool sync) {
     const long long rows = (long long)halo_top + own_rows + halo_bottom;
     if (width < 0 || own_rows < 0 || halo_top < 0 || halo_bottom < 0 || (!rgb && (size_t)width * rows > 0)) return fail(c, HQ_ERR_INVALID, "bad image arguments");
     if (global_row0 < halo_top || global_row0 + own_rows + halo_bottom > global_rows)
@@ -423,14 +264,37 @@ int hq_set_image_u8_sharded(hq_ctx* c, const uint8_t* rgb, int width, int own_ro
     c->stride = hq::plane_stride(c->n);
     HQ_CUDA(c, c->d_rgb.reserve(c->n * 3 > 0 ? c->n * 3 : 1));
     if (c->n) HQ_CUDA(c, cudaMemcpyAsync(c->d_rgb.p, rgb, c->n * 3, cudaMemcpyHostToDevice, c->stream));
+    image_on_own_stream(c);
     rc = convert_image(c, width, own_rows, halo_top, halo_bottom, global_row0, global_rows, whitepoint, c->stream); if (rc) return rc;
-    HQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (sync) HQ_CUDA(c, cudaStreamSynchronize(c->stream));
     return HQ_OK;
+}
+const char* kMultiShards = "a multi-device context shards the image itself: pass the whole image to hq_set_image_u8 / hq_set_image_f32_planar";
+}  // namespace
+
+int hq_set_image_u8_sharded(hq_ctx* c, const uint8_t* rgb, int width, int own_rows, int halo_top, int halo_bottom,
+                            int global_row0, int global_rows, int whitepoint) try {
+    if (!c) return HQ_ERR_INVALID;
+    if (c->is_multi()) return fail(c, HQ_ERR_UNSUPPORTED, "%s", kMultiShards);
+    return set_image_u8_shard(c, rgb, width, own_rows, halo_top, halo_bottom, global_row0, global_rows, whitepoint, true);
 } catch (const std::exception& ex) { return api_exception(c, ex); }
 
-int hq_set_image_f32_planar_sharded(hq_ctx* c, const float* r, const float* g, const float* b, int width, int own_rows, int halo_top,
-                                    int halo_bottom, int global_row0, int global_rows, int whitepoint) try {
-    if (!c) return HQ_ERR_INVALID;
+namespace {
+// waits for a float image's conversion and judges the range flag its kernel raised
+int f32_image_verdict(hq_ctx* c) {
+    int rc = bind_device(c); if (rc) return rc;
+    unsigned int bad = 0;
+    HQ_CUDA(c, cudaMemcpyAsync(&bad, c->d_flag.p, sizeof bad, cudaMemcpyDeviceToHost, c->stream));
+    HQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (bad) {
+        c->have_image = false;
+        return fail(c, HQ_ERR_INVALID, "float image values must lie in [0,1] (Icy's rescaled convertToType, HybridQuantization.java:95)");
+    }
+    return HQ_OK;
+}
+// sync = false: upload and conversion are only enqueued; the caller runs f32_image_verdict later
+int set_image_f32_shard(hq_ctx* c, const float* r, const float* g, const float* b, int width, int own_rows, int halo_top,
+                        int halo_bottom, int global_row0, int global_rows, int whitepoint, bool sync) {
     const long long rows = (long long)halo_top + own_rows + halo_bottom;
     if (width < 0 || own_rows < 0 || halo_top < 0 || halo_bottom < 0 || ((!r || !g || !b) && (size_t)width * rows > 0))
         return fail(c, HQ_ERR_INVALID, "bad image arguments");
@@ -448,27 +312,58 @@ int hq_set_image_f32_planar_sharded(hq_ctx* c, const float* r, const float* g, c
     const float* planes[3] = {r, g, b};
     for (int pl = 0; pl < 3 && c->n; ++pl)
         HQ_CUDA(c, cudaMemcpyAsync(c->d_unit.p + (size_t)pl * c->stride, planes[pl], c->n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    image_on_own_stream(c);
     rc = convert_image(c, width, own_rows, halo_top, halo_bottom, global_row0, global_rows, whitepoint, c->stream); if (rc) return rc;
-    unsigned int bad = 0;
-    HQ_CUDA(c, cudaMemcpyAsync(&bad, c->d_flag.p, sizeof bad, cudaMemcpyDeviceToHost, c->stream));
-    HQ_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (bad) {
-        c->have_image = false;
-        return fail(c, HQ_ERR_INVALID, "float image values must lie in [0,1] (Icy's rescaled convertToType, HybridQuantization.java:95)");
-    }
-    return HQ_OK;
+    return sync ? f32_image_verdict(c) : HQ_OK;
+}
+}  // namespace
+
+int hq_set_image_f32_planar_sharded(hq_ctx* c, const float* r, const float* g, const float* b, int width, int own_rows, int halo_top,
+                                    int halo_bottom, int global_row0, int global_rows, int whitepoint) try {
+    if (!c) return HQ_ERR_INVALID;
+    if (c->is_multi()) return fail(c, HQ_ERR_UNSUPPORTED, "%s", kMultiShards);
+    return set_image_f32_shard(c, r, g, b, width, own_rows, halo_top, halo_bottom, global_row0, global_rows, whitepoint, true);
 } catch (const std::exception& ex) { return api_exception(c, ex); }
 
-int hq_set_image_f32_planar(hq_ctx* c, const float* r, const float* g, const float* b, int width, int rows, int whitepoint) {
-    return hq_set_image_f32_planar_sharded(c, r, g, b, width, rows, 0, 0, 0, rows, whitepoint);
-}
+int hq_set_image_f32_planar(hq_ctx* c, const float* r, const float* g, const float* b, int width, int rows, int whitepoint) try {
+    if (!c) return HQ_ERR_INVALID;
+    if (!c->is_multi()) return set_image_f32_shard(c, r, g, b, width, rows, 0, 0, 0, rows, whitepoint, true);
+    if (width < 0 || rows < 0 || ((!r || !g || !b) && (size_t)width * rows > 0)) return fail(c, HQ_ERR_INVALID, "bad image arguments");
+    const int G = (int)c->members.size(), halo = multi_halo(c);
+    for (hq_ctx* m : c->members) m->have_image = false;
+    for (int i = 0; i < G; ++i) {   // every member's upload and conversion are enqueued before any is waited for
+        const Shard sh = shard_of(rows, G, i, halo);
+        const size_t off = (size_t)(sh.r0 - sh.ht) * width;
+        hq_ctx* m = c->members[i];
+        const int rc = member_rc(c, m, set_image_f32_shard(m, r + off, g + off, b + off, width, sh.own, sh.ht, sh.hb, sh.r0, rows, whitepoint, false));
+        if (rc) return rc;
+    }
+    int verdict = HQ_OK;
+    for (hq_ctx* m : c->members) { const int rc = member_rc(c, m, f32_image_verdict(m)); if (rc && !verdict) verdict = rc; }
+    if (verdict) { for (hq_ctx* m : c->members) m->have_image = false; return verdict; }
+    c->m_width = width; c->m_rows = rows;
+    return bind_device(c);
+} catch (const std::exception& ex) { return api_exception(c, ex); }
 
-int hq_set_image_u8(hq_ctx* c, const uint8_t* rgb, int width, int rows, int whitepoint) {
-    return hq_set_image_u8_sharded(c, rgb, width, rows, 0, 0, 0, rows, whitepoint);
-}
+int hq_set_image_u8(hq_ctx* c, const uint8_t* rgb, int width, int rows, int whitepoint) try {
+    if (!c) return HQ_ERR_INVALID;
+    if (!c->is_multi()) return set_image_u8_shard(c, rgb, width, rows, 0, 0, 0, rows, whitepoint, true);
+    if (width < 0 || rows < 0 || (!rgb && (size_t)width * rows > 0)) return fail(c, HQ_ERR_INVALID, "bad image arguments");
+    const int G = (int)c->members.size(), halo = multi_halo(c);
+    for (hq_ctx* m : c->members) m->have_image = false;
+    for (int i = 0; i < G; ++i) {
+        const Shard sh = shard_of(rows, G, i, halo);
+        hq_ctx* m = c->members[i];
+        const int rc = member_rc(c, m, set_image_u8_shard(m, rgb + (size_t)(sh.r0 - sh.ht) * width * 3, width, sh.own, sh.ht, sh.hb, sh.r0, rows, whitepoint, false));
+        if (rc) return rc;
+    }
+    c->m_width = width; c->m_rows = rows;
+    return sync_members(c);
+} catch (const std::exception& ex) { return api_exception(c, ex); }
 
 int hq_set_image_u8_device(hq_ctx* c, const void* d_rgb, int width, int rows, int whitepoint, void* stream) {
     if (!c) return HQ_ERR_INVALID;
+    if (c->is_multi()) return fail(c, HQ_ERR_UNSUPPORTED, "a device buffer belongs to one device: a multi-device context takes host images");
     if (width < 0 || rows < 0 || (!d_rgb && (size_t)width * rows > 0)) return fail(c, HQ_ERR_INVALID, "bad image arguments");
     if (whitepoint != HQ_WHITEPOINT_D65 && whitepoint != HQ_WHITEPOINT_D50) return fail(c, HQ_ERR_INVALID, "unknown white point %d", whitepoint);
     int rc = bind_device(c); if (rc) return rc;
@@ -479,19 +374,42 @@ int hq_set_image_u8_device(hq_ctx* c, const void* d_rgb, int width, int rows, in
     c->stride = hq::plane_stride(c->n);
     HQ_CUDA(c, c->d_rgb.reserve(c->n * 3 > 0 ? c->n * 3 : 1));
     if (c->n) HQ_CUDA(c, cudaMemcpyAsync(c->d_rgb.p, d_rgb, c->n * 3, cudaMemcpyDeviceToDevice, st));
-    return convert_image(c, width, rows, 0, 0, 0, rows, whitepoint, st);
+    rc = convert_image(c, width, rows, 0, 0, 0, rows, whitepoint, st); if (rc) return rc;
+    c->image_foreign = st != c->stream;
+    if (c->image_foreign) {
+        // the conversion runs on the caller's stream; the context's own (non-blocking) stream — every host-buffer entry —
+        // and any other stream handed to hq_eval_palettes_device wait for it through this event
+        if (!c->ev_image) HQ_CUDA(c, cudaEventCreateWithFlags(&c->ev_image, cudaEventDisableTiming));
+        HQ_CUDA(c, cudaEventRecord(c->ev_image, st));
+        HQ_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_image, 0));
+    }
+    return HQ_OK;
 }
+
+namespace {
+// own pixels of three device planes [3][stride] -> planes[pl * plane_len + at ...] (a member of a multi-device context
+// writes its row block into the whole image's planes)
+int own_planes_to_host(hq_ctx* c, const float* d_planes, float* planes, size_t plane_len, size_t at) {
+    int rc = bind_device(c); if (rc) return rc;
+    const size_t no = c->own_hi - c->own_lo;
+    for (int pl = 0; pl < 3 && no; ++pl)
+        HQ_CUDA(c, cudaMemcpyAsync(planes + (size_t)pl * plane_len + at, d_planes + (size_t)pl * c->stride + c->own_lo, no * sizeof(float),
+                                   cudaMemcpyDeviceToHost, c->stream));
+    HQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HQ_OK;
+}
+}  // namespace
 
 int hq_get_lab(hq_ctx* c, float* planes) {
     if (!c || !planes) return HQ_ERR_INVALID;
     if (!c->have_image) return fail(c, HQ_ERR_NO_IMAGE, "no image");
-    int rc = bind_device(c); if (rc) return rc;
-    const size_t no = c->own_hi - c->own_lo;
-    for (int pl = 0; pl < 3 && no; ++pl)
-        HQ_CUDA(c, cudaMemcpyAsync(planes + (size_t)pl * no, c->d_lab.p + (size_t)pl * c->stride + c->own_lo, no * sizeof(float),
-                                   cudaMemcpyDeviceToHost, c->stream));
-    HQ_CUDA(c, cudaStreamSynchronize(c->stream));
-    return HQ_OK;
+    if (!c->is_multi()) return own_planes_to_host(c, c->d_lab.p, planes, c->own_hi - c->own_lo, 0);
+    const size_t n_all = (size_t)c->m_width * c->m_rows;
+    for (hq_ctx* m : c->members) {
+        const int rc = member_rc(c, m, own_planes_to_host(m, m->d_lab.p, planes, n_all, (size_t)m->g_row0 * m->width));
+        if (rc) return rc;
+    }
+    return bind_device(c);
 }
 
 int hq_result_words(int K, int flags) { return hq::result_words(K, (flags & HQ_EVAL_SUMS) != 0); }
@@ -500,9 +418,59 @@ int hq_eval_palettes_device(hq_ctx* c, const void* d_palettes, int B, int K, int
     int rc = check_eval_args(c, B, K, space); if (rc) return rc;
     if (!d_palettes || !d_results) return fail(c, HQ_ERR_INVALID, "NULL device buffer");
     rc = bind_device(c); if (rc) return rc;
+    if (c->is_multi()) return fail(c, HQ_ERR_UNSUPPORTED, "a device buffer belongs to one device: use hq_eval_palettes on a multi-device context");
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    if (c->image_foreign && st != c->stream) HQ_CUDA(c, cudaStreamWaitEvent(st, c->ev_image, 0));  // image converted on another stream
     return eval_device(c, static_cast<const float*>(d_palettes), B, K, space, flags, static_cast<unsigned long long*>(d_results), nullptr, st);
 }
+
+namespace {
+// palette colours must be sRGB in [0,1] (what SWASA.java:93-106 produces): NaN or out-of-range values would leave the domain
+// hq_srgb_decode is verified on.  The copy into the pinned staging buffer is the one pass over them anyway.
+bool copy_palettes_checked(float* dst, const float* src, size_t npal) {
+    bool ok = true;
+    for (size_t i = 0; i < npal; i += 4) {
+        const float r = src[i], g = src[i + 1], b = src[i + 2];
+        dst[i] = r; dst[i + 1] = g; dst[i + 2] = b; dst[i + 3] = src[i + 3];
+        ok &= (r >= 0.f) & (r <= 1.f) & (g >= 0.f) & (g <= 1.f) & (b >= 0.f) & (b <= 1.f);  // false for NaN
+    }
+    return ok;
+}
+const char* kBadPalette = "palette colours must be finite sRGB values in [0,1] (SWASA.java:93-106 clamps them)";
+
+struct EvalPlan {
+    int B, K, space, flags, words;
+    size_t npal, nwords;
+    bool direct;   // palettes read from / results exported to pinned host memory by kernels (small transfers)
+};
+// everything an evaluation may allocate or build lazily on context m (outside any graph capture)
+int eval_prepare(hq_ctx* m, const EvalPlan& e) {
+    int rc = bind_device(m); if (rc) return rc;
+    const int K8 = hq::padded_colors(e.K);
+    HQ_CUDA(m, m->d_pal.reserve(e.npal));
+    HQ_CUDA(m, m->d_results.reserve(e.nwords));
+    HQ_CUDA(m, m->d_pal_lab.reserve((size_t)e.B * K8));
+    HQ_CUDA(m, m->d_pal_rgb.reserve((size_t)e.B * K8));
+    if (e.space == HQ_SPACE_SRGB) { rc = ensure_unit(m, m->stream); if (rc) return rc; }
+    return prepare_pruned(m, e.K, e.space, e.flags, false, m->stream);
+}
+// palettes (pinned, portable host memory) -> result words of this context's pixels in m->d_results, on m->stream
+int eval_enqueue(hq_ctx* m, const float* h_pal, const EvalPlan& e, const hq::ExportTail* tail, bool* tail_used) {
+    int rc = bind_device(m); if (rc) return rc;
+    if (e.direct) return eval_device(m, h_pal, e.B, e.K, e.space, e.flags, m->d_results.p, nullptr, m->stream, tail, tail_used);
+    HQ_CUDA(m, cudaMemcpyAsync(m->d_pal.p, h_pal, e.npal * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    return eval_device(m, m->d_pal.p, e.B, e.K, e.space, e.flags, m->d_results.p, nullptr, m->stream);
+}
+// the exchange step: sum of the result words over every shard, left in place on every device
+int eval_reduce(hq_ctx* c, size_t nwords) {
+    if (c->is_multi()) {
+        std::vector<unsigned long long*> bufs;
+        for (hq_ctx* m : c->members) bufs.push_back(m->d_results.p);
+        return group_reduce(c, bufs, nwords);
+    }
+    return reduce_words(c, c->d_results.p, nwords, c->stream);
+}
+}  // namespace
 
 int hq_eval_palettes(hq_ctx* c, const float* palettes, int B, int K, int space, int flags, int64_t* err_fx, uint64_t* counts, int64_t* sums_fx) try {
     int rc = check_eval_args(c, B, K, space); if (rc) return rc;
@@ -510,26 +478,25 @@ int hq_eval_palettes(hq_ctx* c, const float* palettes, int B, int K, int space, 
     const bool sums = (flags & HQ_EVAL_SUMS) != 0;
     if (sums_fx && !sums) return fail(c, HQ_ERR_INVALID, "sums_fx requires HQ_EVAL_SUMS");
     rc = bind_device(c); if (rc) return rc;
-    const size_t npal = (size_t)B * K * 4;
-    const int words = hq::result_words(K, sums);
-    const size_t nwords = (size_t)B * words;
+    EvalPlan e{};
+    e.B = B; e.K = K; e.space = space; e.flags = flags;
+    e.npal = (size_t)B * K * 4;
+    e.words = hq::result_words(K, sums);
+    e.nwords = (size_t)B * e.words;
+    const size_t npal = e.npal, nwords = e.nwords;
+    const int words = e.words;
     HQ_CUDA(c, c->h_pal.reserve(npal));
-    HQ_CUDA(c, c->d_pal.reserve(npal));
     HQ_CUDA(c, c->h_results.reserve(nwords));
-    HQ_CUDA(c, c->d_results.reserve(nwords));
-    std::memcpy(c->h_pal.p, palettes, npal * sizeof(float));
-    // Everything eval_device may allocate or build lazily happens here, outside any capture
-    {
-        const int K8 = hq::padded_colors(K);
-        HQ_CUDA(c, c->d_pal_lab.reserve((size_t)B * K8));
-        HQ_CUDA(c, c->d_pal_rgb.reserve((size_t)B * K8));
-        if (space == HQ_SPACE_SRGB) { rc = ensure_unit(c, c->stream); if (rc) return rc; }
-        rc = prepare_pruned(c, K, space, flags, false, c->stream); if (rc) return rc;
-    }
+    if (!copy_palettes_checked(c->h_pal.p, palettes, npal)) return fail(c, HQ_ERR_INVALID, "%s", kBadPalette);
+    const bool multi = c->is_multi(), reduce = reduces(c);
+    std::vector<hq_ctx*> self(1, c);
+    const std::vector<hq_ctx*>& targets = multi ? c->members : self;
+    for (hq_ctx* m : targets) { rc = member_rc(c, m, eval_prepare(m, e)); if (rc) return rc; }
+    rc = bind_device(c); if (rc) return rc;
     hq_ctx::EvalKey key;
     key.B = B; key.K = K; key.space = space; key.flags = flags; key.image_gen = c->image_gen; key.d_pal = c->d_pal.p; key.d_results = c->d_results.p;
     key.h_pal = c->h_pal.p; key.h_results = c->h_results.p; key.d_pal_lab = c->d_pal_lab.p; key.d_pal_rgb = c->d_pal_rgb.p;
-    const bool graphable = c->use_graphs && !c->allreduce && !c->profiling;
+    const bool graphable = c->use_graphs && !reduce && !c->profiling;
     if (graphable && c->graph_exec && key == c->graph_key) {
         HQ_CUDA(c, cudaGraphLaunch(c->graph_exec, c->stream));  // the third and later identical calls: one launch for the whole step
     } else {
@@ -537,31 +504,37 @@ int hq_eval_palettes(hq_ctx* c, const float* palettes, int B, int K, int space, 
         const bool capture = graphable && key == c->seen_key;
         c->seen_key = key;
         // (small transfers only: one CTA pushing 131 KB of results over PCIe took 0.16 ms at 64 candidates x 256 colours, a DMA copy 5 us)
-        if (!graphable && c->direct_io && npal * sizeof(float) <= 65536 && nwords * 8 <= 32768) {
+        e.direct = !graphable && c->direct_io && npal * sizeof(float) <= 65536 && nwords * 8 <= 32768;
+        if (e.direct) {
             // Latency path (a search iteration is four dependent stream operations; this makes it two): the palette kernel reads
-            // the pinned host copy directly (UVA: a cudaMallocHost pointer is device-accessible) and a one-CTA kernel writes the
+            // the pinned host copy directly (UVA: pinned host memory is device-accessible) and a one-CTA kernel writes the
             // result words plus a sequence number back into pinned host memory, which the host spins on.
             const unsigned long long seq = ++c->export_seq;
             hq::ExportTail tail;   // single GPU, small palettes: the scoring kernel's last CTA exports; otherwise a one-CTA kernel after it
             tail.host_dst = c->h_results.p; tail.host_flag = c->h_flag.p; tail.seq = seq; tail.counter = c->d_export_counter.p;
             tail.src = c->d_results.p; tail.nwords = (unsigned)nwords;
             bool tail_used = false;
-            rc = eval_device(c, c->h_pal.p, B, K, space, flags, c->d_results.p, nullptr, c->stream, c->allreduce ? nullptr : &tail, &tail_used); if (rc) return rc;
-            if (c->allreduce && c->allreduce(c->allreduce_user, c->d_results.p, nwords, c->stream) != 0) return fail(c, HQ_ERR_CALLBACK, "all-reduce hook failed");
+            for (size_t i = targets.size(); i-- > 0;) {   // the leader (targets[0]) last: its stream carries the export
+                hq_ctx* m = targets[i];
+                rc = member_rc(c, m, eval_enqueue(m, c->h_pal.p, e, (reduce || m != c) ? nullptr : &tail, &tail_used)); if (rc) return rc;
+            }
+            if (reduce) { rc = eval_reduce(c, nwords); if (rc) return rc; }
+            rc = bind_device(c); if (rc) return rc;
             if (!tail_used) HQ_CUDA(c, hq::launch_export_results(c->d_results.p, c->h_results.p, nwords, c->h_flag.p, seq, c->stream));
             HQ_CUDA(c, wait_flag(c->h_flag.p, seq, c->stream));
             goto unpack;
         }
         if (capture) HQ_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-        cudaError_t e = cudaMemcpyAsync(c->d_pal.p, c->h_pal.p, npal * sizeof(float), cudaMemcpyHostToDevice, c->stream);
-        rc = e == cudaSuccess ? eval_device(c, c->d_pal.p, B, K, space, flags, c->d_results.p, nullptr, c->stream) : HQ_ERR_CUDA;
-        if (rc == HQ_OK && c->allreduce && c->allreduce(c->allreduce_user, c->d_results.p, nwords, c->stream) != 0)
-            rc = fail(c, HQ_ERR_CALLBACK, "all-reduce hook failed");
-        if (rc == HQ_OK) e = cudaMemcpyAsync(c->h_results.p, c->d_results.p, nwords * 8, cudaMemcpyDeviceToHost, c->stream);
+        cudaError_t ce = cudaSuccess;
+        rc = HQ_OK;
+        for (size_t i = targets.size(); i-- > 0 && rc == HQ_OK;) rc = member_rc(c, targets[i], eval_enqueue(targets[i], c->h_pal.p, e, nullptr, nullptr));
+        if (rc == HQ_OK && reduce) rc = eval_reduce(c, nwords);
+        if (rc == HQ_OK) rc = bind_device(c);
+        if (rc == HQ_OK) ce = cudaMemcpyAsync(c->h_results.p, c->d_results.p, nwords * 8, cudaMemcpyDeviceToHost, c->stream);
         if (capture) {
             cudaGraph_t g = nullptr;
             const cudaError_t ec = cudaStreamEndCapture(c->stream, &g);
-            if (rc == HQ_OK && e == cudaSuccess && ec == cudaSuccess && g) {
+            if (rc == HQ_OK && ce == cudaSuccess && ec == cudaSuccess && g) {
                 if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
                 const cudaError_t ei = cudaGraphInstantiate(&c->graph_exec, g, 0);
                 cudaGraphDestroy(g);
@@ -571,11 +544,11 @@ int hq_eval_palettes(hq_ctx* c, const float* palettes, int B, int K, int space, 
             } else {
                 if (g) cudaGraphDestroy(g);
                 if (rc != HQ_OK) return rc;
-                return fail(c, HQ_ERR_CUDA, "graph capture of the evaluation failed: %s", cudaGetErrorString(e != cudaSuccess ? e : ec));
+                return fail(c, HQ_ERR_CUDA, "graph capture of the evaluation failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : ec));
             }
         } else {
             if (rc != HQ_OK) return rc;
-            if (e != cudaSuccess) return fail(c, HQ_ERR_CUDA, "evaluation launch failed: %s", cudaGetErrorString(e));
+            if (ce != cudaSuccess) return fail(c, HQ_ERR_CUDA, "evaluation launch failed: %s", cudaGetErrorString(ce));
         }
     }
     HQ_CUDA(c, wait_stream(c->stream));
@@ -588,7 +561,6 @@ unpack:
     }
     return HQ_OK;
 } catch (const std::exception& ex) { return api_exception(c, ex); }
-
 double hq_cost(int64_t err_fx, const uint64_t* counts, int K, uint64_t n_total, float delta) {
     double penalty = 0;
     for (int k = 0; k < K; ++k)
@@ -597,9 +569,9 @@ double hq_cost(int64_t err_fx, const uint64_t* counts, int K, uint64_t n_total, 
     return sum / (double)n_total + penalty;
 }
 
-int hq_quantize(hq_ctx* c, const float* palette, int K, int space, uint8_t* out_rgb, float* out_f32, uint16_t* out_idx) try {
+namespace {
+int quantize_one(hq_ctx* c, const float* palette, int K, int space, uint8_t* out_rgb, float* out_f32, uint16_t* out_idx) {
     int rc = check_eval_args(c, 1, K, space); if (rc) return rc;
-    if (!palette) return fail(c, HQ_ERR_INVALID, "palette is NULL");
     rc = bind_device(c); if (rc) return rc;
     const size_t n = c->n;
     const bool idx16 = K > 256;
@@ -609,7 +581,7 @@ int hq_quantize(hq_ctx* c, const float* palette, int K, int space, uint8_t* out_
     HQ_CUDA(c, c->d_pal.reserve(npal));
     HQ_CUDA(c, c->d_results.reserve(words));
     HQ_CUDA(c, c->d_idx.reserve((c->stride ? c->stride : 1) * (idx16 ? 2 : 1)));
-    std::memcpy(c->h_pal.p, palette, npal * sizeof(float));
+    if (!copy_palettes_checked(c->h_pal.p, palette, npal)) return fail(c, HQ_ERR_INVALID, "%s", kBadPalette);
     HQ_CUDA(c, cudaMemcpyAsync(c->d_pal.p, c->h_pal.p, npal * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     rc = eval_device(c, c->d_pal.p, 1, K, space, (K > HQ_MAX_COLORS || c->prune_mode == HQ_PRUNE_ON) ? HQ_EVAL_PRUNE : 0, c->d_results.p, c->d_idx.p,
                      c->stream); if (rc) return rc;
@@ -636,6 +608,20 @@ int hq_quantize(hq_ctx* c, const float* palette, int K, int space, uint8_t* out_
     if (out_idx && no && !idx16)
         for (size_t i = 0; i < no; ++i) out_idx[i] = idx8[i];
     return HQ_OK;
+}
+}  // namespace
+
+int hq_quantize(hq_ctx* c, const float* palette, int K, int space, uint8_t* out_rgb, float* out_f32, uint16_t* out_idx) try {
+    if (!c) return HQ_ERR_INVALID;
+    if (!palette) return fail(c, HQ_ERR_INVALID, "palette is NULL");
+    if (!c->is_multi()) return quantize_one(c, palette, K, space, out_rgb, out_f32, out_idx);
+    for (hq_ctx* m : c->members) {   // every member writes its own row block of the outputs
+        const size_t at = (size_t)m->g_row0 * m->width;
+        const int rc = member_rc(c, m, quantize_one(m, palette, K, space, out_rgb ? out_rgb + at * 3 : nullptr, out_f32 ? out_f32 + at * 4 : nullptr,
+                                                    out_idx ? out_idx + at : nullptr));
+        if (rc) return rc;
+    }
+    return bind_device(c);
 } catch (const std::exception& ex) { return api_exception(c, ex); }
 
 // ------------------------------------------------------------------ S-CIELAB stage
@@ -660,11 +646,15 @@ static int sc_upload_filters(hq_ctx* c) {
 int hq_scielab_set_filters(hq_ctx* c, const float* filters7, const float* abs3, int taps) try {
     if (!c || !filters7 || !abs3) return c ? fail(c, HQ_ERR_INVALID, "NULL filter arrays") : HQ_ERR_INVALID;
     if (taps < 1 || taps > hq::kMaxScielabTaps || (taps & 1) == 0) return fail(c, HQ_ERR_UNSUPPORTED, "taps must be odd and in [1,%d] (got %d)", hq::kMaxScielabTaps, taps);
-    int rc = bind_device(c); if (rc) return rc;
-    c->sc_filters7.assign(filters7, filters7 + (size_t)7 * taps);
-    c->sc_abs3.assign(abs3, abs3 + taps);
-    c->sc_taps = taps;
-    return sc_upload_filters(c);
+    std::vector<hq_ctx*> self(1, c);
+    for (hq_ctx* m : (c->is_multi() ? c->members : self)) {   // every member filters its own rows with the same bank
+        int rc = bind_device(m); if (rc) return member_rc(c, m, rc);
+        m->sc_filters7.assign(filters7, filters7 + (size_t)7 * taps);
+        m->sc_abs3.assign(abs3, abs3 + taps);
+        m->sc_taps = taps;
+        rc = member_rc(c, m, sc_upload_filters(m)); if (rc) return rc;
+    }
+    return bind_device(c);
 } catch (const std::exception& ex) { return api_exception(c, ex); }
 
 int hq_scielab_configure(hq_ctx* c, int dpi, float viewing_distance_cm) try {
@@ -677,8 +667,8 @@ int hq_scielab_configure(hq_ctx* c, int dpi, float viewing_distance_cm) try {
 
 int hq_scielab_force_generic(hq_ctx* c, int enabled) {
     if (!c) return HQ_ERR_INVALID;
-    c->sc_generic = enabled != 0;
-    c->sc_image_ready = false;
+    std::vector<hq_ctx*> self(1, c);
+    for (hq_ctx* m : (c->is_multi() ? c->members : self)) { m->sc_generic = enabled != 0; m->sc_image_ready = false; }
     return HQ_OK;
 }
 
@@ -740,19 +730,23 @@ static int sc_ensure_image(hq_ctx* c) {
 
 int hq_scielab_get_image(hq_ctx* c, float* planes) {
     if (!c || !planes) return HQ_ERR_INVALID;
-    int rc = bind_device(c); if (rc) return rc;
-    rc = sc_ensure_image(c); if (rc) return rc;
-    const size_t no = c->own_hi - c->own_lo;
-    for (int pl = 0; pl < 3 && no; ++pl)
-        HQ_CUDA(c, cudaMemcpyAsync(planes + (size_t)pl * no, c->d_sc_lab.p + (size_t)pl * c->stride + c->own_lo, no * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    HQ_CUDA(c, cudaStreamSynchronize(c->stream));
-    return HQ_OK;
+    std::vector<hq_ctx*> self(1, c);
+    const size_t n_all = c->is_multi() ? (size_t)c->m_width * c->m_rows : c->own_hi - c->own_lo;
+    for (hq_ctx* m : (c->is_multi() ? c->members : self)) {
+        if (c->is_multi() && m->own_rows == 0) continue;   // an empty row block
+        int rc = bind_device(m); if (rc) return member_rc(c, m, rc);
+        rc = member_rc(c, m, sc_ensure_image(m)); if (rc) return rc;
+        rc = member_rc(c, m, own_planes_to_host(m, m->d_sc_lab.p, planes, n_all, c->is_multi() ? (size_t)m->g_row0 * m->width : 0)); if (rc) return rc;
+    }
+    return bind_device(c);
 }
 
 // error-image mode: HybridQuantization.errorImage (:139-182) + ImageManipulation.computeError (:858-894)
 namespace {
 // the second image of error-image mode, as packed u8 (rgb8) or as float planes (f32[3])
-int error_image_common(hq_ctx* c, const uint8_t* rgb8, const float* const* f32, float* error_map, uint8_t* error_map_u8, double* mean_de) {
+// raw_sum (optional): a member of a multi-device context — no exchange, no mean; the fixed-point sum of its own rows goes there
+int error_image_common(hq_ctx* c, const uint8_t* rgb8, const float* const* f32, float* error_map, uint8_t* error_map_u8, double* mean_de,
+                       unsigned long long* raw_sum = nullptr) {
     int rc = bind_device(c); if (rc) return rc;
     rc = sc_ensure_image(c); if (rc) return rc;
     const size_t n = c->n;
@@ -782,14 +776,16 @@ int error_image_common(hq_ctx* c, const uint8_t* rgb8, const float* const* f32, 
     const size_t lo = c->own_lo, no = c->own_hi - c->own_lo;  // maps and the sum cover the own rows
     HQ_CUDA(c, hq::launch_sc_error_image(c->d_sc_lab.p + lo, c->d_sc_lab2.p + lo, no, c->stride, error_map ? c->d_sc_map.p : nullptr,
                                          error_map_u8 ? c->d_sc_map8.p : nullptr, c->d_sc_err.p, c->stream));
-    if (c->allreduce && c->allreduce(c->allreduce_user, c->d_sc_err.p, 1, c->stream) != 0) return fail(c, HQ_ERR_CALLBACK, "all-reduce hook failed");
+    const bool reduce = !raw_sum && reduces(c);
+    if (reduce) { rc = reduce_words(c, c->d_sc_err.p, 1, c->stream); if (rc) return rc; }
     unsigned long long sum = 0;
     HQ_CUDA(c, cudaMemcpyAsync(&sum, c->d_sc_err.p, 8, cudaMemcpyDeviceToHost, c->stream));
     if (error_map && no) HQ_CUDA(c, cudaMemcpyAsync(error_map, c->d_sc_map.p, no * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     if (error_map_u8 && no) HQ_CUDA(c, cudaMemcpyAsync(error_map_u8, c->d_sc_map8.p, no, cudaMemcpyDeviceToHost, c->stream));
     HQ_CUDA(c, cudaStreamSynchronize(c->stream));
     const double n_all = (double)c->width * (double)c->g_rows;  // with the hook the sum is over the whole image
-    const double n_div = c->allreduce ? n_all : (double)no;
+    const double n_div = reduce ? n_all : (double)no;
+    if (raw_sum) *raw_sum = sum;
     if (mean_de) *mean_de = n_div > 0 ? ((double)(int64_t)sum * (1.0 / 16777216.0)) / n_div : 0.0;  // :893 error/errorArray.length
     return HQ_OK;
 }
@@ -797,50 +793,97 @@ int error_image_common(hq_ctx* c, const uint8_t* rgb8, const float* const* f32, 
 
 int hq_error_image(hq_ctx* c, const uint8_t* quantized_rgb, float* error_map, uint8_t* error_map_u8, double* mean_de) try {
     if (!c || !quantized_rgb) return c ? fail(c, HQ_ERR_INVALID, "quantized_rgb is NULL") : HQ_ERR_INVALID;
-    return error_image_common(c, quantized_rgb, nullptr, error_map, error_map_u8, mean_de);
+    if (!c->is_multi()) return error_image_common(c, quantized_rgb, nullptr, error_map, error_map_u8, mean_de);
+    long long total = 0;
+    for (hq_ctx* m : c->members) {   // each member: its rows (+ halo) of the second image in, its rows of the maps out
+        if (m->own_rows == 0) continue;
+        const size_t in_at = (size_t)(m->g_row0 - m->halo_top) * m->width, out_at = (size_t)m->g_row0 * m->width;
+        unsigned long long part = 0;
+        const int rc = member_rc(c, m, error_image_common(m, quantized_rgb + in_at * 3, nullptr, error_map ? error_map + out_at : nullptr,
+                                                          error_map_u8 ? error_map_u8 + out_at : nullptr, nullptr, &part));
+        if (rc) return rc;
+        total += (long long)part;
+    }
+    const double n_all = (double)c->m_width * (double)c->m_rows;
+    if (mean_de) *mean_de = n_all > 0 ? ((double)total * (1.0 / 16777216.0)) / n_all : 0.0;
+    return bind_device(c);
 } catch (const std::exception& ex) { return api_exception(c, ex); }
 
 int hq_error_image_f32_planar(hq_ctx* c, const float* r, const float* g, const float* b, float* error_map, uint8_t* error_map_u8, double* mean_de) try {
     if (!c || !r || !g || !b) return c ? fail(c, HQ_ERR_INVALID, "an image plane is NULL") : HQ_ERR_INVALID;
     const float* planes[3] = {r, g, b};
-    return error_image_common(c, nullptr, planes, error_map, error_map_u8, mean_de);
+    if (!c->is_multi()) return error_image_common(c, nullptr, planes, error_map, error_map_u8, mean_de);
+    long long total = 0;
+    for (hq_ctx* m : c->members) {
+        if (m->own_rows == 0) continue;
+        const size_t in_at = (size_t)(m->g_row0 - m->halo_top) * m->width, out_at = (size_t)m->g_row0 * m->width;
+        const float* mp[3] = {r + in_at, g + in_at, b + in_at};
+        unsigned long long part = 0;
+        const int rc = member_rc(c, m, error_image_common(m, nullptr, mp, error_map ? error_map + out_at : nullptr,
+                                                          error_map_u8 ? error_map_u8 + out_at : nullptr, nullptr, &part));
+        if (rc) return rc;
+        total += (long long)part;
+    }
+    const double n_all = (double)c->m_width * (double)c->m_rows;
+    if (mean_de) *mean_de = n_all > 0 ? ((double)total * (1.0 / 16777216.0)) / n_all : 0.0;
+    return bind_device(c);
 } catch (const std::exception& ex) { return api_exception(c, ex); }
+
+namespace {
+// one context's share of a reference-faithful evaluation, enqueued on m->stream: result words (error in word 0, counts) of its
+// own rows in m->d_results.  h_pal: pinned, portable.
+int sc_eval_enqueue(hq_ctx* m, const float* h_pal, int B, int K, int space) {
+    int rc = bind_device(m); if (rc) return rc;
+    const size_t npal = (size_t)B * K * 4;
+    const int words = hq::result_words(K, false);
+    const size_t nwords = (size_t)B * words;
+    const bool idx16 = K > 256;
+    HQ_CUDA(m, m->d_results.reserve(nwords));
+    if (m->own_rows == 0) {   // an empty row block of a multi-device context contributes zeros
+        HQ_CUDA(m, cudaMemsetAsync(m->d_results.p, 0, nwords * 8, m->stream));
+        return HQ_OK;
+    }
+    rc = sc_ensure_image(m); if (rc) return rc;
+    HQ_CUDA(m, m->d_pal.reserve(npal));
+    HQ_CUDA(m, m->d_sc_err.reserve(B));
+    HQ_CUDA(m, m->d_sc_tab.reserve((size_t)B * K));
+    HQ_CUDA(m, m->d_idx.reserve((size_t)B * (m->stride ? m->stride : 1) * (idx16 ? 2 : 1)));
+    HQ_CUDA(m, cudaMemcpyAsync(m->d_pal.p, h_pal, npal * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    // 1. assignment (quantizeAndConvertToOpp's argmin, cl:178-193): indices + counts for every candidate
+    //    (exact pruned kernel where it pays: same indices and counts, DESIGN.md 4c)
+    const bool prune_idx = K > HQ_MAX_COLORS || m->prune_mode == HQ_PRUNE_ON || (m->prune_mode == HQ_PRUNE_AUTO && K >= 32 && m->n >= 65536);
+    rc = eval_device(m, m->d_pal.p, B, K, space, prune_idx ? HQ_EVAL_PRUNE : 0, m->d_results.p, m->d_idx.p, m->stream); if (rc) return rc;
+    // 2. the K opponent colours each quantised image is made of (cl:194-198)
+    HQ_CUDA(m, hq::launch_sc_palette_opp(m->d_pal.p, B * K, m->d_sc_tab.p, m->stream));
+    HQ_CUDA(m, cudaMemsetAsync(m->d_sc_err.p, 0, (size_t)B * 8, m->stream));
+    // 3. per candidate: separable filters, Opp2LAB, CIE76 against the original, fixed-point sum
+    for (int b = 0; b < B; ++b) {
+        const uint8_t* idx_b = m->d_idx.p + (size_t)b * m->stride * (idx16 ? 2 : 1);
+        HQ_CUDA(m, hq::launch_sc_candidate(idx_b, idx16, m->d_sc_tab.p + (size_t)b * K, m->width, m->rows, m->stride, m->d_sc_filters.p,
+                                           m->sc_generic ? nullptr : m->sc_block.data(), m->sc_taps, m->whitepoint, sc_rows(m), m->d_sc_tmp.p,
+                                           m->d_sc_lab.p, m->d_sc_err.p + b, m->stream));
+    }
+    // word 0 of every candidate <- the S-CIELAB error sum, so that one all-reduce covers error and counts
+    HQ_CUDA(m, cudaMemcpy2DAsync(m->d_results.p, (size_t)words * 8, m->d_sc_err.p, 8, 8, (size_t)B, cudaMemcpyDeviceToDevice, m->stream));
+    return HQ_OK;
+}
+}  // namespace
 
 int hq_eval_palettes_scielab(hq_ctx* c, const float* palettes, int B, int K, int space, int64_t* err_fx, uint64_t* counts) try {
     int rc = check_eval_args(c, B, K, space); if (rc) return rc;
     if (!palettes) return fail(c, HQ_ERR_INVALID, "palettes is NULL");
     rc = bind_device(c); if (rc) return rc;
-    rc = sc_ensure_image(c); if (rc) return rc;
     const size_t npal = (size_t)B * K * 4;
     const int words = hq::result_words(K, false);
     const size_t nwords = (size_t)B * words;
-    const bool idx16 = K > 256;
     HQ_CUDA(c, c->h_pal.reserve(npal));
-    HQ_CUDA(c, c->d_pal.reserve(npal));
     HQ_CUDA(c, c->h_results.reserve(nwords + B));
-    HQ_CUDA(c, c->d_results.reserve(nwords));
-    HQ_CUDA(c, c->d_sc_err.reserve(B));
-    HQ_CUDA(c, c->d_sc_tab.reserve((size_t)B * K));
-    HQ_CUDA(c, c->d_idx.reserve((size_t)B * (c->stride ? c->stride : 1) * (idx16 ? 2 : 1)));
-    std::memcpy(c->h_pal.p, palettes, npal * sizeof(float));
-    HQ_CUDA(c, cudaMemcpyAsync(c->d_pal.p, c->h_pal.p, npal * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    // 1. assignment (quantizeAndConvertToOpp's argmin, cl:178-193): indices + counts for every candidate
-    //    (exact pruned kernel where it pays: same indices and counts, DESIGN.md 4c)
-    const bool prune_idx = K > HQ_MAX_COLORS || c->prune_mode == HQ_PRUNE_ON || (c->prune_mode == HQ_PRUNE_AUTO && K >= 32 && c->n >= 65536);
-    rc = eval_device(c, c->d_pal.p, B, K, space, prune_idx ? HQ_EVAL_PRUNE : 0, c->d_results.p, c->d_idx.p, c->stream); if (rc) return rc;
-    // 2. the K opponent colours each quantised image is made of (cl:194-198)
-    HQ_CUDA(c, hq::launch_sc_palette_opp(c->d_pal.p, B * K, c->d_sc_tab.p, c->stream));
-    HQ_CUDA(c, cudaMemsetAsync(c->d_sc_err.p, 0, (size_t)B * 8, c->stream));
-    // 3. per candidate: separable filters, Opp2LAB, CIE76 against the original, fixed-point sum
-    for (int b = 0; b < B; ++b) {
-        const uint8_t* idx_b = c->d_idx.p + (size_t)b * c->stride * (idx16 ? 2 : 1);
-        HQ_CUDA(c, hq::launch_sc_candidate(idx_b, idx16, c->d_sc_tab.p + (size_t)b * K, c->width, c->rows, c->stride, c->d_sc_filters.p,
-                                           c->sc_generic ? nullptr : c->sc_block.data(), c->sc_taps, c->whitepoint, sc_rows(c), c->d_sc_tmp.p,
-                                           c->d_sc_lab.p, c->d_sc_err.p + b, c->stream));
-    }
-    // word 0 of every candidate <- the S-CIELAB error sum, so that one all-reduce covers error and counts
-    HQ_CUDA(c, cudaMemcpy2DAsync(c->d_results.p, (size_t)words * 8, c->d_sc_err.p, 8, 8, (size_t)B, cudaMemcpyDeviceToDevice, c->stream));
-    if (c->allreduce && c->allreduce(c->allreduce_user, c->d_results.p, nwords, c->stream) != 0) return fail(c, HQ_ERR_CALLBACK, "all-reduce hook failed");
+    if (!copy_palettes_checked(c->h_pal.p, palettes, npal)) return fail(c, HQ_ERR_INVALID, "%s", kBadPalette);
+    std::vector<hq_ctx*> self(1, c);
+    const std::vector<hq_ctx*>& targets = c->is_multi() ? c->members : self;
+    for (size_t i = targets.size(); i-- > 0;) { rc = member_rc(c, targets[i], sc_eval_enqueue(targets[i], c->h_pal.p, B, K, space)); if (rc) return rc; }
+    if (reduces(c)) { rc = eval_reduce(c, nwords); if (rc) return rc; }
+    rc = bind_device(c); if (rc) return rc;
     HQ_CUDA(c, cudaMemcpyAsync(c->h_results.p, c->d_results.p, nwords * 8, cudaMemcpyDeviceToHost, c->stream));
     HQ_CUDA(c, wait_stream(c->stream));
     for (int b = 0; b < B; ++b) {
@@ -852,6 +895,7 @@ int hq_eval_palettes_scielab(hq_ctx* c, const float* palettes, int B, int K, int
 
 int hq_set_allreduce(hq_ctx* c, hq_allreduce_fn fn, void* user) {
     if (!c) return HQ_ERR_INVALID;
+    if (c->is_multi() && fn) return fail(c, HQ_ERR_UNSUPPORTED, "a multi-device context reduces over its own NCCL communicator");
     c->allreduce = fn;
     c->allreduce_user = user;
     return HQ_OK;
@@ -913,6 +957,7 @@ int hq_set_pruning(hq_ctx* c, int mode) {
     if (!c) return HQ_ERR_INVALID;
     if (mode != HQ_PRUNE_OFF && mode != HQ_PRUNE_AUTO && mode != HQ_PRUNE_ON) return fail(c, HQ_ERR_INVALID, "unknown pruning mode %d", mode);
     c->prune_mode = mode;
+    for (hq_ctx* m : c->members) m->prune_mode = mode;
     return HQ_OK;
 }
 

@@ -17,6 +17,8 @@
 // hence independent of block order, grid size and GPU count.
 //
 // Tensor cores are deliberately not used: the inner dimension of the distance is 3.
+#include <mutex>
+
 #include "hq_kernels.cuh"
 #include "hq_math.h"
 
@@ -687,27 +689,36 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VAR
     if (VARIANT == 1) export_tail(p.tail, gridDim.x * gridDim.y);
 }
 
-// per (kernel instantiation, device): the dynamic shared-memory size last configured and the occupancy it gave, so that
-// the per-iteration launches of a search do not pay cudaFuncSetAttribute + an occupancy query every time
-struct LaunchCache { size_t smem = ~(size_t)0; int occ = 0; };
+// per (kernel instantiation, device), PROCESS-wide: cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the function on
+// the device, not to the calling thread, so it is only ever RAISED (two host threads with different palette sizes must not
+// lower it under each other); the occupancy of the last launch shape is remembered beside it so that the per-iteration
+// launches of a search pay neither cudaFuncSetAttribute nor an occupancy query
+struct LaunchCache { std::mutex mu; size_t attr = 0; size_t smem = ~(size_t)0; int occ = 0; };
 template <int VARIANT, bool SRGB, bool SUMS, int IDXW>
 cudaError_t launch_assign_t(const AssignParams& p, int B, int sm_count, cudaStream_t stream) {
     auto kern = assign_reduce_kernel<VARIANT, SRGB, SUMS, IDXW>;
     const size_t smem = AssignSmem<VARIANT, SRGB, SUMS>(p.K8).total;
-    static thread_local LaunchCache cache[64];
+    static LaunchCache cache[64];
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    LaunchCache& lc = cache[dev & 63];
-    if (lc.smem != smem) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        int o = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, smem);
-        if (e != cudaSuccess) return e;
-        lc.smem = smem; lc.occ = o < 1 ? 1 : o;
+    int occ;
+    {
+        LaunchCache& lc = cache[dev & 63];
+        std::lock_guard<std::mutex> lock(lc.mu);
+        if (smem > lc.attr) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            lc.attr = smem;
+        }
+        if (lc.smem != smem) {
+            int o = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, smem);
+            if (e != cudaSuccess) return e;
+            lc.smem = smem; lc.occ = o < 1 ? 1 : o;
+        }
+        occ = lc.occ;
     }
-    const int occ = lc.occ;
     const long long slots = (long long)sm_count * occ;
     const long long ntiles = (long long)((p.n + kTilePx - 1) / kTilePx);
     // CTAs per candidate (G): B*G must be a whole number of waves of the `slots` resident CTAs,
@@ -864,7 +875,8 @@ cudaError_t launch_assign_reduce(const AssignArgs& a, cudaStream_t stream) {
     p.results = a.results;
     p.idx_out = a.idx_out;
     p.tail = a.tail;
-    p.own_lo = a.own_lo; p.own_hi = a.own_hi > a.own_lo ? a.own_hi : a.n;
+    // (an EMPTY own range — a shard that only carries halo rows — is honoured as empty: indices for every pixel, no reduction)
+    p.own_lo = a.own_lo; p.own_hi = a.own_hi == kAllPixels ? a.n : a.own_hi;
     const int idxw = a.idx_out ? (a.K <= 256 ? 1 : 2) : 0;
     // |feature| bounds of the image for the prefilter's error bound: CIELAB of in-gamut sRGB has
     // L in [0,100], |a|,|b| < 128 (extremes 98.3 / 107.9); unit sRGB is in [0,1]

@@ -72,6 +72,7 @@ __device__ __forceinline__ void export_tail(const ExportTail& x, unsigned total_
 }
 #endif
 
+constexpr size_t kAllPixels = ~(size_t)0;
 struct AssignArgs {
     const float* lab;      // [3][stride]
     const float* unit;     // [3][stride], required when space == 1
@@ -84,7 +85,7 @@ struct AssignArgs {
     unsigned long long* results;  // [B][result_words], must be zeroed by the caller
     void* idx_out;         // [B][stride] u8 (K <= 256) or u16, or null
     int sm_count;
-    size_t own_lo = 0, own_hi = 0;  // reduce only pixels [own_lo, own_hi) (0,0 = all): halo rows of a shard are assigned but not counted
+    size_t own_lo = 0, own_hi = kAllPixels;  // reduce only pixels [own_lo, own_hi) (default: all): halo rows of a shard are assigned but not counted
     int variant;           // 0 auto, 1 direct index tracking, 2 chunked min + recompute, 3 prefilter + exact
     ExportTail tail;       // optional (see above); only with variant 1 (explicit, or auto with K <= kDirectMaxColors)
 };

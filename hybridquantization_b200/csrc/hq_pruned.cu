@@ -22,6 +22,8 @@
 // each pixel's image position and scatters the winner's index there; the scoring mode needs no index image.
 #include <cstdlib>
 
+#include <mutex>
+
 #include "hq_kernels.cuh"
 #include "hq_math.h"
 
@@ -366,15 +368,20 @@ __global__ void __launch_bounds__(kThreads, SUMS ? 2 : 4) pruned_assign_kernel(c
 
 template <bool SUMS, int IDXW>
 cudaError_t launch_pruned_t(const PrunedParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-    static thread_local size_t configured[64];  // per device: dynamic shared memory last set + 1 (0 = never)
+    // process-wide and monotonic: the attribute belongs to the function on the device, not to the calling thread
+    static std::mutex mu;
+    static size_t configured[64];  // per device: largest dynamic shared memory set so far
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    size_t& have = configured[dev & 63];
-    if (have != smem + 1) {
-        e = cudaFuncSetAttribute(pruned_assign_kernel<SUMS, IDXW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        have = smem + 1;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        size_t& have = configured[dev & 63];
+        if (smem > have) {
+            e = cudaFuncSetAttribute(pruned_assign_kernel<SUMS, IDXW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            have = smem;
+        }
     }
     pruned_assign_kernel<SUMS, IDXW><<<grid, kThreads, smem, st>>>(p);
     return cudaGetLastError();

@@ -61,6 +61,22 @@ def install_nccl_allreduce(backend) -> None:
     backend.setAllreduce(hook)
 
 
+def install_native_nccl(backend) -> dict:
+    """The exchange step inside the library: rank 0 asks libhq_b200 for an NCCL unique id, torch.distributed only ships those
+    128 bytes to the other ranks, and every rank's context joins the library's OWN communicator (hq_comm_init_rank).  From
+    then on hq_eval_palettes* / the search all-reduce the integer result words with ncclAllReduce on the context's stream —
+    no Python in the data path.  Returns hq_comm_info."""
+    import torch.distributed as dist
+
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return backend.commInfo()
+    box = [backend.commUniqueId() if dist.get_rank() == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    backend.setAllreduce(None)
+    backend.commInitRank(box[0], dist.get_world_size(), dist.get_rank())
+    return backend.commInfo()
+
+
 def reduce_partials_numpy(parts: list[dict]) -> dict:
     """Host-side statement of what the all-reduce computes (used by the CPU gloo tests)."""
     out = {k: np.zeros_like(parts[0][k]) for k in ("err_fx", "counts", "sums_fx") if parts[0].get(k) is not None}

@@ -91,13 +91,19 @@ class ImageManipulation:
     """The compute backend (ImageManipulation.java) on one GPU.  Creation raises HqError when
     no usable device exists — the reference's silent zero-output mode (:79-92) is gone."""
 
-    def __init__(self, deltaEType: str = "CIE76", verbose: bool = False, convergence: bool = True, device: int = 0):
+    def __init__(self, deltaEType: str = "CIE76", verbose: bool = False, convergence: bool = True, device=0):
+        """device: a CUDA device index, or a list of them -> ONE context over several GPUs of this process (hq_create_multi:
+        the image rows are split inside the library, every evaluation ends in one grouped NCCL all-reduce)."""
         if deltaEType != "CIE76":
             raise ValueError("only CIE76 is implemented (the plugin never selects another, HybridQuantization.java:96)")
         self._lib = _lib.load()
         self._ctx = C.c_void_p()
         self.verbose, self.convergence = verbose, convergence
-        rc = self._lib.hq_create(device, C.byref(self._ctx))
+        if isinstance(device, (list, tuple)):
+            devs = (C.c_int * len(device))(*device)
+            rc = self._lib.hq_create_multi(devs, len(device), C.byref(self._ctx))
+        else:
+            rc = self._lib.hq_create(device, C.byref(self._ctx))
         if rc != 0:
             msg = self._lib.hq_last_error(None)
             self._ctx = C.c_void_p()
@@ -132,6 +138,29 @@ class ImageManipulation:
         name = C.create_string_buffer(128)
         _lib.check(self._ctx, self._lib.hq_device_info(self._ctx, C.byref(sm), C.byref(clk), name, 128))
         return {"name": name.value.decode(), "sm_count": sm.value, "sm_clock_khz": clk.value}
+
+    # -- native NCCL (one process per GPU): the library owns the communicator, the host only ships the id bytes
+    @staticmethod
+    def commUniqueId() -> bytes:
+        buf = C.create_string_buffer(_lib.COMM_ID_BYTES)
+        rc = _lib.load().hq_comm_get_unique_id(buf)
+        if rc != 0:
+            msg = _lib.load().hq_last_error(None)
+            raise HqError(rc, msg.decode() if msg else "")
+        return buf.raw
+
+    def commInitRank(self, unique_id: bytes, nranks: int, rank: int) -> None:
+        if len(unique_id) != _lib.COMM_ID_BYTES:
+            raise ValueError("unique_id must be the %d bytes of commUniqueId()" % _lib.COMM_ID_BYTES)
+        _lib.check(self._ctx, self._lib.hq_comm_init_rank(self._ctx, C.c_char_p(unique_id), nranks, rank))
+
+    def commAllreduce(self, d_words_ptr: int, n_words: int, stream: int = 0) -> None:
+        _lib.check(self._ctx, self._lib.hq_comm_allreduce(self._ctx, d_words_ptr, n_words, stream or None))
+
+    def commInfo(self) -> dict:
+        r, s_, v = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(self._ctx, self._lib.hq_comm_info(self._ctx, C.byref(r), C.byref(s_), C.byref(v)))
+        return {"rank": r.value, "size": s_.value, "nccl_version": v.value, "devices": int(self._lib.hq_multi_device_count(self._ctx))}
 
     # -- measurement hooks
     def setProfiling(self, enabled: bool) -> None:
@@ -260,7 +289,9 @@ class ImageManipulation:
         palettes = np.ascontiguousarray(palettes, np.float32)
         if palettes.ndim == 2:
             palettes = palettes[None]
-        B, K, _ = palettes.shape
+        B, K, four = palettes.shape
+        if four != 4:
+            raise ValueError("palettes must be [B, K, 4]")
         err = np.empty(B, np.int64); counts = np.empty((B, K), np.uint64)
         _lib.check(self._ctx, self._lib.hq_eval_palettes_scielab(self._ctx, _ptr(palettes), B, K, space, _ptr(err), _ptr(counts)))
         return {"err_fx": err, "counts": counts}

@@ -85,6 +85,8 @@ int hq_set_image_u8_sharded(hq_ctx* ctx, const uint8_t* rgb, int width, int own_
  * cudaStream_t, NULL = the context's stream) and does not synchronise */
 int hq_set_image_u8_device(hq_ctx* ctx, const void* d_rgb, int width, int rows, int whitepoint,
                            void* stream);
+/* (the conversion is ordered before every later entry: the context's own stream, and any other stream passed to
+ * hq_eval_palettes_device, waits on an event recorded behind it) */
 /* The image as the plugin itself holds it: planar floats in [0,1], one array per channel (`im.getDataXYCAsFloat()` after
  * `IcyBufferedImageUtil.convertToType(..., DataType.FLOAT, true)`, HybridQuantization.java:95-98) — so 16-bit and float
  * Icy images need no detour through u8.  Each value is decoded on the device exactly as ScielabProcessor.java:282-284
@@ -101,7 +103,8 @@ uint64_t hq_image_pixels(const hq_ctx* ctx);
 /* ---- candidate evaluation: replaces computeQuantizationErrorPopulation
  * (ImageManipulation.java:620-727): kernels quantizeAndConvertToOpp + CIEDE, the
  * used-colour flags and the host-side averageArray.
- * palettes: [B][K][4] floats, sRGB in [0,1] laid out R,G,B,0 as SWASA.java:42-50.
+ * palettes: [B][K][4] floats, sRGB in [0,1] laid out R,G,B,0 as SWASA.java:42-50; a NaN or a value outside [0,1]
+ * (nothing SWASA.java:93-106 can produce) is refused with HQ_ERR_INVALID by every host-pointer entry.
  * Outputs (each may be NULL), all exact integers so that shards add up bit-identically:
  *   err_fx [B]        sum over pixels of round(dE * 2^24)
  *   counts [B][K]     pixels assigned to each colour (colour used <=> count > 0)
@@ -194,6 +197,31 @@ int hq_eval_palettes_scielab(hq_ctx* ctx, const float* palettes, int B, int K, i
  * and return 0. */
 typedef int (*hq_allreduce_fn)(void* user, void* d_words, size_t n_words, void* stream);
 int hq_set_allreduce(hq_ctx* ctx, hq_allreduce_fn fn, void* user);
+
+/* ---- the exchange step inside the library: native NCCL (added in round 2).
+ * (a) One process per GPU (torchrun, MPI, ...): rank 0 calls hq_comm_get_unique_id and ships the HQ_COMM_ID_BYTES to the
+ *     other ranks by any means; every rank then calls hq_comm_init_rank on its context (collective).  From then on
+ *     hq_eval_palettes, hq_eval_palettes_scielab, hq_error_image* and the search return totals over all ranks through
+ *     ncclAllReduce(ncclInt64, ncclSum) on the context's stream; hq_comm_allreduce does the same for the buffers of the
+ *     device-pointer API.  A hook installed with hq_set_allreduce takes precedence.
+ * (b) One process, several GPUs — what replaces JavaCL.createBestContext() + one queue (ImageManipulation.java:58-59) for
+ *     a JVM host: hq_create_multi returns ONE context over the listed devices.  hq_set_image_u8 / hq_set_image_f32_planar
+ *     take the WHOLE image and split its rows over the devices (rows i*H/G .. (i+1)*H/G on device i, plus the halo rows
+ *     the S-CIELAB stage needs: 10, or taps/2 of the filter bank configured at that time); every evaluation runs on all
+ *     devices and one grouped ncclAllReduce follows; hq_quantize, hq_get_lab, hq_scielab_get_image and hq_error_image*
+ *     gather whole-image outputs.  Entries that take device pointers or explicit shards return HQ_ERR_UNSUPPORTED on it.
+ * The sums are exact integers: totals and the annealing trajectory are identical for any number of GPUs.
+ * NCCL is loaded at run time (libnccl.so.2 of the process, else of the system; HQ_NCCL_LIB overrides); without it these
+ * entries fail with HQ_ERR_UNSUPPORTED. */
+#define HQ_COMM_ID_BYTES 128
+int hq_comm_get_unique_id(void* id128);
+int hq_comm_init_rank(hq_ctx* ctx, const void* id128, int nranks, int rank);
+int hq_comm_allreduce(hq_ctx* ctx, void* d_words, size_t n_words, void* stream);
+/* rank / size of the context's communicator (0 / 1 without one; size = devices of a multi-device context) and the NCCL
+ * version in use (0 = not loaded); each pointer may be NULL */
+int hq_comm_info(const hq_ctx* ctx, int* rank, int* size, int* nccl_version);
+int hq_create_multi(const int* devices, int ndev, hq_ctx** out);
+int hq_multi_device_count(const hq_ctx* ctx);
 
 /* ---- the annealing search: replaces findBestQuantization (ImageManipulation.java:383-591)
  * with SWASA.java's schedule.  Accept/reject logic and RNG stay on the host; only the

@@ -1,6 +1,7 @@
 """torchrun worker for tests/test_gpu_multi.py: every rank holds a row shard, the integer result
-words are all-reduced over NCCL through the C ABI's hook, and the totals plus a full sharded
-SWASA run must equal the single-GPU result computed on rank 0 over the whole image."""
+words are all-reduced by the library's own NCCL communicator (hq_comm_init_rank; the torch hook of
+hq_set_allreduce is exercised once beside it), and the totals plus a full sharded SWASA run must
+equal the single-GPU result computed on rank 0 over the whole image."""
 import json
 import os
 import sys
@@ -13,7 +14,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 
 from hybridquantization_b200 import COST_SCIELAB, EVAL_PRUNE, PRUNE_OFF, SPACE_SRGB, SWASA, ImageManipulation, synth  # noqa: E402
-from hybridquantization_b200.dist import install_nccl_allreduce, row_shard, row_shard_with_halo  # noqa: E402
+from hybridquantization_b200.dist import install_native_nccl, install_nccl_allreduce, row_shard, row_shard_with_halo  # noqa: E402
 
 
 def main():
@@ -27,7 +28,9 @@ def main():
     r0, r1 = row_shard(h, world, rank)
     be = ImageManipulation("CIE76", False, True, local)
     be.setImage(img[r0:r1])
-    install_nccl_allreduce(be)
+    install_nccl_allreduce(be)                                # round-1 path: torch.distributed through the C ABI's hook
+    got_hook = be.evalPalettes(pal, sums=True)
+    info = install_native_nccl(be)                            # the library's own communicator from here on
     got = be.evalPalettes(pal, sums=True)                     # totals over all ranks
     got_pruned = be.evalPalettes(pal, sums=True, flags=EVAL_PRUNE)   # the exact pruned kernel on every shard, same all-reduce
     # a population whose palettes / results exceed the direct host I/O thresholds (64 KB / 32 KB): the DMA-copy path, same hook
@@ -35,7 +38,8 @@ def main():
     got_big = be.evalPalettes(big_pal, sums=False)
     sw = SWASA(population=4, imax=60, seed=2024)
     best, err, tr, its = be.findBestQuantization(K, sw, n_total=w * h, trace=True)
-    res = {"rank": rank, "ok": True}
+    res = {"rank": rank, "ok": True, "comm": info}
+    res["hook_equals_native"] = all(np.array_equal(got[k], got_hook[k]) for k in ("err_fx", "counts", "sums_fx"))
     res["pruned_equals_exhaustive"] = all(np.array_equal(got[k], got_pruned[k]) for k in ("err_fx", "counts", "sums_fx"))
     # every rank must hold identical totals / trajectory
     blob = torch.from_numpy(np.concatenate([got["err_fx"], got["counts"].astype(np.int64).ravel(), got["sums_fx"].ravel(),
@@ -62,7 +66,7 @@ def main():
     sc = ImageManipulation("CIE76", False, True, local)
     sc.setImageSharded(img[r0 - top:r1 + bot], top, bot, r0, h)
     sc.scielabConfigure(72, 45.0)
-    install_nccl_allreduce(sc)
+    install_native_nccl(sc)
     sc_tot = sc.evalPalettesScielab(pal[:2, :32])
     sw2 = SWASA(population=3, imax=25, seed=7, space=SPACE_SRGB, costModel=COST_SCIELAB)
     sbest2, serr2, str2, _ = sc.findBestQuantization(32, sw2, n_total=w * h, trace=True)

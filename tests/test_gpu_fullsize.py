@@ -64,7 +64,7 @@ def test_c4_64mp_row_shards_add_up(backend):
     assert all(np.array_equal(a, b) for a, b in zip(whole, ragged))
 
 
-@pytest.mark.parametrize("K", [8, 32, 128, 512, 1024])
+@pytest.mark.parametrize("K", [8, 16, 32, 64, 128, 256, 512, 1024])
 def test_c5_palette_sweep_4k_conservation_and_srgb(backend, oracle, K):
     img = synth.synth_image(3840, 2160, synth.SEED_BASE + 5)
     pal = synth.synth_palettes(1, K)
@@ -76,9 +76,9 @@ def test_c5_palette_sweep_4k_conservation_and_srgb(backend, oracle, K):
     lab = backend.labImage()
     tot = np.array([np.rint(lab[c].astype(np.float64) * 16777216.0).astype(np.int64).sum() for c in range(3)])
     assert np.array_equal(got["sums_fx"][0].sum(axis=0), tot)
-    if K <= 128:
-        want = oracle.assign_reduce(img, pal, threads=THREADS)
-        assert got["err_fx"][0] == want["err_fx"][0] and np.array_equal(got["counts"], want["counts"])
+    # the oracle on the same candidate at every K of the sweep (BASELINE configs[4]; < 0.3 s of host time even at K = 1024)
+    want = oracle.assign_reduce(img, pal, threads=THREADS)
+    assert got["err_fx"][0] == want["err_fx"][0] and np.array_equal(got["counts"], want["counts"]) and np.array_equal(got["sums_fx"], want["sums_fx"])
 
 
 def test_pruned_scoring_at_full_sizes(backend):

@@ -32,7 +32,8 @@ def test_sharded_equals_single_gpu(world, tmp_path, hqlib):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     res = json.load(open(out))
-    assert len(res) == world and all(x["same_on_all_ranks"] and x["pruned_equals_exhaustive"] for x in res)
+    assert len(res) == world and all(x["same_on_all_ranks"] and x["pruned_equals_exhaustive"] and x["hook_equals_native"] for x in res)
+    assert all(x["comm"]["size"] == world and x["comm"]["rank"] == x["rank"] and x["comm"]["nccl_version"] > 20000 for x in res)
     assert res[0]["totals_equal_single_gpu"] and res[0]["trajectory_equal_single_gpu"] and res[0]["iterations"] == 60
     assert res[0]["large_population_equal_single_gpu"]   # both host I/O paths of hq_eval_palettes go through the all-reduce
     assert res[0]["scielab_totals_equal_single_gpu"] and res[0]["scielab_trajectory_equal_single_gpu"]
