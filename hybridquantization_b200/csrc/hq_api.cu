@@ -170,6 +170,10 @@ int hq_create(int device, hq_ctx** out) {
         const char* d = std::getenv("HQ_DIRECT_IO");
         c->direct_io = !(d && d[0] == '0');
     }
+    {   // HQ_SC_UNFUSED=1: the S-CIELAB candidate stage as two kernels per candidate with a 7-plane intermediate (round 1; A/B runs)
+        const char* u = std::getenv("HQ_SC_UNFUSED");
+        c->sc_unfused = u && u[0] == '1';
+    }
     {   // HQ_CUDA_GRAPHS=1 turns hq_set_graphs on for every new context
         const char* g = std::getenv("HQ_CUDA_GRAPHS");
         c->use_graphs = g && g[0] == '1';
@@ -668,7 +672,7 @@ int hq_scielab_configure(hq_ctx* c, int dpi, float viewing_distance_cm) try {
 int hq_scielab_force_generic(hq_ctx* c, int enabled) {
     if (!c) return HQ_ERR_INVALID;
     std::vector<hq_ctx*> self(1, c);
-    for (hq_ctx* m : (c->is_multi() ? c->members : self)) { m->sc_generic = enabled != 0; m->sc_image_ready = false; }
+    for (hq_ctx* m : (c->is_multi() ? c->members : self)) { m->sc_generic = enabled == 1; m->sc_unfused = enabled == 2; m->sc_image_ready = false; }
     return HQ_OK;
 }
 
@@ -857,7 +861,12 @@ int sc_eval_enqueue(hq_ctx* m, const float* h_pal, int B, int K, int space) {
     HQ_CUDA(m, hq::launch_sc_palette_opp(m->d_pal.p, B * K, m->d_sc_tab.p, m->stream));
     HQ_CUDA(m, cudaMemsetAsync(m->d_sc_err.p, 0, (size_t)B * 8, m->stream));
     // 3. per candidate: separable filters, Opp2LAB, CIE76 against the original, fixed-point sum
-    for (int b = 0; b < B; ++b) {
+    cudaError_t fe = (m->sc_generic || m->sc_unfused) ? cudaErrorNotSupported
+                     : hq::launch_sc_candidates_fused(m->d_idx.p, idx16, m->d_sc_tab.p, K, B, m->width, m->rows, m->stride, m->sc_block.data(), m->sc_taps,
+                                                      m->whitepoint, sc_rows(m), m->d_sc_lab.p, m->d_sc_err.p, m->stream);
+    if (fe != cudaSuccess && fe != cudaErrorNotSupported) return fail(m, HQ_ERR_CUDA, "fused S-CIELAB kernel launch failed: %s", cudaGetErrorString(fe));
+    if (fe == cudaErrorNotSupported) HQ_CUDA(m, m->d_sc_tmp.reserve(7 * m->stride));
+    for (int b = 0; b < B && fe == cudaErrorNotSupported; ++b) {   // other tap counts, K > 1024: two kernels per candidate
         const uint8_t* idx_b = m->d_idx.p + (size_t)b * m->stride * (idx16 ? 2 : 1);
         HQ_CUDA(m, hq::launch_sc_candidate(idx_b, idx16, m->d_sc_tab.p + (size_t)b * K, m->width, m->rows, m->stride, m->d_sc_filters.p,
                                            m->sc_generic ? nullptr : m->sc_block.data(), m->sc_taps, m->whitepoint, sc_rows(m), m->d_sc_tmp.p,

@@ -113,6 +113,7 @@ struct hq_ctx {
     std::vector<float> sc_filters7, sc_abs3;  // [7][taps], [taps] as ScielabProcessor builds them
     std::vector<float> sc_block;              // [8][taps] device layout, host copy
     bool sc_generic = false;                  // test hook: force the generic (any-taps) kernels
+    bool sc_unfused = false;                  // HQ_SC_UNFUSED=1: the two-kernel 21-tap candidate path of round 1 (A/B measurements, tests)
     int sc_taps = 0;
     bool sc_image_ready = false;
     DevBuf<float> d_sc_filters, d_sc_opp, d_sc_tmp, d_sc_lab, d_sc_lab2, d_sc_map;

@@ -8,6 +8,8 @@
 // chain has the reference's order (bit-exact against the oracle).  The reference transposes between
 // the passes; here the vertical pass reads column neighbours directly (coalesced across a row), which
 // is the same arithmetic.
+#include <mutex>
+
 #include "hq_kernels.cuh"
 #include "hq_math.h"
 
@@ -273,6 +275,147 @@ sc_vpass21_kernel(const float* __restrict__ tmp, int w, int h, size_t stride, co
     }
 }
 
+// ---------------------------------------------------------------- fused candidate stage, taps = 21 (round 2)
+// One kernel per population instead of two per candidate with a 7-plane fp32 intermediate in HBM (28 B/px written
+// and read back ~3.5x: ~510 MB per 4K candidate where the stage needs the 1 B/px of indices and the 12 B/px of the
+// original's S-CIELAB).  A CTA owns a tile of kFW x kFH output pixels of one candidate:
+//   1. the tile's palette indices (+10 columns / rows of halo, reflected at the GLOBAL image borders) and the
+//      candidate's K-entry opponent table (cl:194-198) go to shared memory;
+//   2. horizontal pass (cl:234-272): every (row, 4 outputs) task builds its 24-pixel window by table look-up and runs
+//      the 7 x 21 fma chains in ascending tap order -> 7 planes of kFH+20 rows in shared memory;
+//   3. vertical pass (cl:274-306): every (column, 8 output rows) task streams 28 of those rows through registers,
+//      per tap fma(t1,k1,fma(t2,k2,out)); out.x = fma(t3,|k3|,out.x) -> Opp2LAB (cl:124-145) -> CIE76 against the
+//      resident S-CIELAB of the original (cl:209) -> 2^-24 fixed point, one atomic per CTA.
+// Arithmetic, operand order and fma nesting are those of sc_hpass21_kernel / sc_vpass21_kernel<1>: same bits.
+// Cost of the fusion: the horizontal pass is recomputed for the 20 halo rows of every tile ((kFH+20)/kFH = 1.16x).
+constexpr int kFW = 32, kFH = 128, kFThreads = 256;
+constexpr int kFRows = kFH + kT - 1;   // 148 horizontally filtered rows per tile
+constexpr int kFCols = kFW + kT - 1;   // 52 input columns per tile row (13 words of u8)
+static_assert(kFCols % 4 == 0 && kFW % kHOut == 0 && kFH % kVRows == 0, "tile geometry");
+
+template <typename IdxT>
+struct FusedSmem {
+    size_t off_h, off_idx, off_lut, total;
+    __host__ __device__ explicit FusedSmem(int K) {
+        size_t o = 0;
+        off_h = o;   o += (size_t)kFRows * 7 * kFW * sizeof(float);
+        off_lut = o; o += (size_t)K * sizeof(float4);
+        off_idx = o; o += (size_t)kFRows * kFCols * sizeof(IdxT);
+        total = (o + 15) / 16 * 16;
+    }
+};
+
+template <typename IdxT>
+__global__ void __launch_bounds__(kFThreads, 1)
+sc_candidate_fused21_kernel(const IdxT* __restrict__ idx, const float4* __restrict__ tab, int K, int w, int h, size_t stride,
+                            const __grid_constant__ Filt21 f, hq_float3 ill, ScRows rows, const float* __restrict__ lab_orig,
+                            unsigned long long* __restrict__ err_out) {
+    extern __shared__ __align__(16) unsigned char fused_smem[];
+    const FusedSmem<IdxT> L(K);
+    float* s_h = reinterpret_cast<float*>(fused_smem + L.off_h);           // [kFRows][7][kFW]
+    float4* s_lut = reinterpret_cast<float4*>(fused_smem + L.off_lut);     // [K]
+    IdxT* s_idx = reinterpret_cast<IdxT*>(fused_smem + L.off_idx);         // [kFRows][kFCols]
+    const int tid = threadIdx.x;
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * kFW, y0 = rows.y_begin + blockIdx.y * kFH;   // first output pixel of the tile (local rows)
+    const IdxT* idx_b = idx + (size_t)b * stride;
+    const float4* tab_b = tab + (size_t)b * K;
+
+    // ---- 1. stage the table and the index tile
+    for (int k = tid; k < K; k += kFThreads) s_lut[k] = __ldg(tab_b + k);
+    for (int i = tid; i < kFRows * kFCols; i += kFThreads) {
+        const int s = i / kFCols, cix = i - s * kFCols;
+        // slot s holds the row the vertical filter reads for virtual row y0 - 10 + s: reflection at the GLOBAL borders;
+        // rows only needed by discarded outputs are clamped into the local array (as sc_vpass21_kernel does)
+        int lr = hq_reflect(rows.g0 + y0 - kHalf + s, rows.gh) - rows.g0;
+        lr = lr < 0 ? 0 : (lr >= h ? h - 1 : lr);
+        int xx = x0 - kHalf + cix;
+        xx = xx < w + kHalf ? hq_reflect(xx, w) : 0;   // beyond the last output's right halo: never used
+        xx = xx < 0 ? 0 : (xx >= w ? w - 1 : xx);
+        s_idx[i] = idx_b[(size_t)lr * w + xx];
+    }
+    __syncthreads();
+
+    // ---- 2. horizontal pass: tasks (slot s, group g of 4 outputs)
+    for (int q = tid; q < kFRows * (kFW / kHOut); q += kFThreads) {
+        const int s = q / (kFW / kHOut), lx = (q - s * (kFW / kHOut)) * kHOut;
+        const IdxT* irow = s_idx + s * kFCols + lx;
+        float win[3][kHOut + kT - 1];
+#pragma unroll
+        for (int i = 0; i < kHOut + kT - 1; ++i) {
+            const float4 v = s_lut[irow[i]];
+            win[0][i] = v.x; win[1][i] = v.y; win[2][i] = v.z;
+        }
+        float acc[kHOut][7];
+#pragma unroll
+        for (int o = 0; o < kHOut; ++o)
+#pragma unroll
+            for (int c = 0; c < 7; ++c) acc[o][c] = 0.f;
+#pragma unroll
+        for (int t = 0; t < kT; ++t)
+#pragma unroll
+            for (int o = 0; o < kHOut; ++o) {
+                const float i0 = win[0][o + t], i1 = win[1][o + t], i2 = win[2][o + t];
+                acc[o][0] = HQ_FFMA(i0, f.v[3 * t], acc[o][0]); acc[o][1] = HQ_FFMA(i1, f.v[3 * t + 1], acc[o][1]); acc[o][2] = HQ_FFMA(i2, f.v[3 * t + 2], acc[o][2]);
+                acc[o][3] = HQ_FFMA(i0, f.v[3 * kT + 3 * t], acc[o][3]); acc[o][4] = HQ_FFMA(i1, f.v[3 * kT + 3 * t + 1], acc[o][4]); acc[o][5] = HQ_FFMA(i2, f.v[3 * kT + 3 * t + 2], acc[o][5]);
+                acc[o][6] = HQ_FFMA(i0, f.v[6 * kT + t], acc[o][6]);
+            }
+        float* dst = s_h + (size_t)s * 7 * kFW + lx;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) *reinterpret_cast<float4*>(dst + c * kFW) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+    }
+    __syncthreads();
+
+    // ---- 3. vertical pass + Opp2LAB + CIE76: tasks (column lx, group j of 8 output rows); a warp = 32 columns of one group
+    long long fx = 0;
+    const int y_end = rows.y_begin + rows.y_count;
+    for (int q = tid; q < kFW * (kFH / kVRows); q += kFThreads) {
+        const int j = q / kFW, lx = q - j * kFW;
+        const int x = x0 + lx, yb = y0 + j * kVRows;
+        if (x >= w || yb >= y_end) continue;
+        float a[kVRows][3];
+#pragma unroll
+        for (int o = 0; o < kVRows; ++o) a[o][0] = a[o][1] = a[o][2] = 0.f;
+        const float* src = s_h + (size_t)(j * kVRows) * 7 * kFW + lx;
+#pragma unroll
+        for (int r = 0; r < kVRows + kT - 1; ++r) {
+            const float* p = src + (size_t)r * 7 * kFW;
+            const float t10 = p[0], t11 = p[kFW], t12 = p[2 * kFW], t20 = p[3 * kFW], t21 = p[4 * kFW], t22 = p[5 * kFW], t3 = p[6 * kFW];
+#pragma unroll
+            for (int o = 0; o < kVRows; ++o) {
+                const int t = r - o;  // tap of input row r for output row o: ascending in r, the reference's order
+                if (t >= 0 && t < kT) {
+                    a[o][0] = HQ_FFMA(t10, f.v[3 * t], HQ_FFMA(t20, f.v[3 * kT + 3 * t], a[o][0]));
+                    a[o][1] = HQ_FFMA(t11, f.v[3 * t + 1], HQ_FFMA(t21, f.v[3 * kT + 3 * t + 1], a[o][1]));
+                    a[o][2] = HQ_FFMA(t12, f.v[3 * t + 2], HQ_FFMA(t22, f.v[3 * kT + 3 * t + 2], a[o][2]));
+                    a[o][0] = HQ_FFMA(t3, f.v[7 * kT + t], a[o][0]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < kVRows; ++o) {
+            const int y = yb + o;
+            if (y < y_end) {
+                const hq_float3 lab = hq_cl_opp_to_lab(a[o][0], a[o][1], a[o][2], ill);
+                const size_t p = (size_t)y * w + x;
+                const float d2 = hq_dist2(__ldg(lab_orig + p), __ldg(lab_orig + stride + p), __ldg(lab_orig + 2 * stride + p), lab.x, lab.y, lab.z);
+                fx += hq_to_fx(HQ_FSQRT(d2));
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) fx += __shfl_down_sync(0xffffffffu, fx, off);
+    __shared__ long long s_err[kFThreads / 32];
+    if ((tid & 31) == 0) s_err[tid >> 5] = fx;
+    __syncthreads();
+    if (tid == 0) {
+        long long e = 0;
+#pragma unroll
+        for (int i = 0; i < kFThreads / 32; ++i) e += s_err[i];
+        if (e) atomicAdd(err_out + b, (unsigned long long)e);
+    }
+}
+
 // error-image mode (ImageManipulation.computeError :858-894): dE between two S-CIELAB images, the
 // map value ((255 - dE)^2) / (255*255) (:890) and the fixed-point sum of dE
 __global__ void sc_error_image_kernel(const float* __restrict__ lab_a, const float* __restrict__ lab_b, size_t n, size_t stride,
@@ -365,6 +508,39 @@ cudaError_t launch_sc_candidate(const void* d_idx, bool idx16, const float4* d_t
     if (idx16) sc_hpass_kernel<1, uint16_t><<<grid, kScThreads, 7 * taps * sizeof(float), st>>>(nullptr, static_cast<const uint16_t*>(d_idx), d_tab, w, h, stride, f, d_tmp);
     else sc_hpass_kernel<1, uint8_t><<<grid, kScThreads, 7 * taps * sizeof(float), st>>>(nullptr, static_cast<const uint8_t*>(d_idx), d_tab, w, h, stride, f, d_tmp);
     sc_vpass_kernel<1><<<gridv, kScThreads, 8 * taps * sizeof(float), st>>>(d_tmp, w, h, stride, f, hq_whitepoint(whitepoint), rows, nullptr, d_lab_orig, d_err);
+    return cudaGetLastError();
+}
+
+// all B candidates of a population in ONE launch (taps = 21, K <= kMaxColors); d_idx: [B][stride] indices, d_tab: [B][K] opponent
+// colours, d_err: [B] fixed-point sums (added to).  Returns cudaErrorNotSupported when the fused kernel does not apply
+// (then the caller runs launch_sc_candidate per candidate).
+cudaError_t launch_sc_candidates_fused(const void* d_idx, bool idx16, const float4* d_tab, int K, int B, int w, int h, size_t stride,
+                                       const float* h_filters, int taps, int whitepoint, ScRows rows, const float* d_lab_orig,
+                                       unsigned long long* d_err, cudaStream_t st) {
+    if (taps != kT || !h_filters || K > kMaxColors || B > 65535) return cudaErrorNotSupported;
+    if (w == 0 || h == 0 || rows.y_count == 0 || B == 0) return cudaSuccess;
+    Filt21 f21;
+    for (int i = 0; i < 8 * kT; ++i) f21.v[i] = h_filters[i];
+    const dim3 grid((unsigned)((w + kFW - 1) / kFW), (unsigned)((rows.y_count + kFH - 1) / kFH), (unsigned)B);
+    if (grid.y > 65535) return cudaErrorNotSupported;
+    static std::mutex mu;
+    static size_t configured[2][64];   // per index width and device: largest dynamic shared memory set so far (process-wide, monotonic)
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const size_t smem = idx16 ? FusedSmem<uint16_t>(K).total : FusedSmem<uint8_t>(K).total;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        size_t& have = configured[idx16 ? 1 : 0][dev & 63];
+        if (smem > have) {
+            e = idx16 ? cudaFuncSetAttribute(sc_candidate_fused21_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                      : cudaFuncSetAttribute(sc_candidate_fused21_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            have = smem;
+        }
+    }
+    if (idx16) sc_candidate_fused21_kernel<uint16_t><<<grid, kFThreads, smem, st>>>(static_cast<const uint16_t*>(d_idx), d_tab, K, w, h, stride, f21, hq_whitepoint(whitepoint), rows, d_lab_orig, d_err);
+    else sc_candidate_fused21_kernel<uint8_t><<<grid, kFThreads, smem, st>>>(static_cast<const uint8_t*>(d_idx), d_tab, K, w, h, stride, f21, hq_whitepoint(whitepoint), rows, d_lab_orig, d_err);
     return cudaGetLastError();
 }
 

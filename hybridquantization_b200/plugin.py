@@ -269,8 +269,9 @@ class ImageManipulation:
         filters7 = np.ascontiguousarray(filters7, np.float32); abs3 = np.ascontiguousarray(abs3, np.float32)
         _lib.check(self._ctx, self._lib.hq_scielab_set_filters(self._ctx, _ptr(filters7), _ptr(abs3), filters7.shape[1]))
 
-    def scielabForceGeneric(self, enabled: bool) -> None:
-        _lib.check(self._ctx, self._lib.hq_scielab_force_generic(self._ctx, int(enabled)))
+    def scielabForceGeneric(self, mode) -> None:
+        """test hook: 0 default (fused candidate kernel), 1 generic any-tap kernels, 2 round 1's two-kernel 21-tap candidate path"""
+        _lib.check(self._ctx, self._lib.hq_scielab_force_generic(self._ctx, int(mode)))
 
     def scielabFilters(self):
         taps = C.c_int(0)

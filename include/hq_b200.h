@@ -183,7 +183,8 @@ int hq_error_image(hq_ctx* ctx, const uint8_t* quantized_rgb, float* error_map, 
 /* the second image as float planes in [0,1] (errorImage converts both sequences to FLOAT, HybridQuantization.java:142-143) */
 int hq_error_image_f32_planar(hq_ctx* ctx, const float* r, const float* g, const float* b, float* error_map, uint8_t* error_map_u8,
                               double* mean_de);
-/* test hook: 1 = always run the generic any-tap-count kernels instead of the 21-tap specialisation */
+/* test hook: 1 = always run the generic any-tap-count kernels instead of the 21-tap specialisations; 2 = the 21-tap
+ * candidate stage as two kernels per candidate with an intermediate in HBM (round 1) instead of the fused kernel; 0 = default */
 int hq_scielab_force_generic(hq_ctx* ctx, int enabled);
 /* host only (no GPU needed): the filter bank for (dpi, viewing distance); *taps as above */
 int hq_scielab_build_filters(int dpi, float viewing_distance_cm, float* filters7, float* abs3, int* taps);

@@ -40,20 +40,27 @@ def test_scielab_candidate_costs_match_oracle(backend, oracle, K, space):
 
 
 def test_generic_and_specialised_kernels_agree(backend, oracle):
-    # taps == 21 runs the specialised kernels; the generic ones must give the same integers
-    for (w, h) in ((1037, 53), (64, 300), (2051, 19)):
+    # taps == 21 runs the specialised kernels — for candidates the FUSED tile kernel (mode 0); the generic any-tap kernels
+    # (mode 1) and round 1's two-kernel 21-tap path (mode 2) must give the same integers, at sizes that cut the fused
+    # kernel's 32 x 128 tiles everywhere (single partial tile, exact multiples, one column / row over)
+    for (w, h, K) in ((1037, 53, 24), (64, 300, 24), (2051, 19, 24), (32, 128, 5), (33, 129, 300), (31, 257, 256), (96, 256, 1024)):
         img = synth.synth_image(w, h, 3, smooth=True)
-        pal = synth.synth_palettes(2, 24)
+        pal = synth.synth_palettes(2, K)
         backend.setImage(img)
         backend.scielabConfigure(72, 45.0)
         res = []
-        for generic in (False, True):
-            backend.scielabForceGeneric(generic)
-            res.append((backend.scielabImage().view(np.uint32).copy(), backend.evalPalettesScielab(pal)["err_fx"].copy()))
-        backend.scielabForceGeneric(False)
-        assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+        for mode in (0, 1, 2):
+            backend.scielabForceGeneric(mode)
+            r = backend.evalPalettesScielab(pal)
+            res.append((backend.scielabImage().view(np.uint32).copy(), r["err_fx"].copy(), r["counts"].copy()))
+        backend.scielabForceGeneric(0)
+        for other in res[1:]:
+            assert all(np.array_equal(a, b) for a, b in zip(res[0], other)), (w, h, K)
         of, oa = oracle.scielab_filters(72, 45.0)
-        assert np.array_equal(res[0][0], oracle.scielab_image(img, of, oa, 0, THREADS).view(np.uint32))
+        so = oracle.scielab_image(img, of, oa, 0, THREADS)
+        assert np.array_equal(res[0][0], so.view(np.uint32))
+        want = oracle.scielab_eval(img, of, oa, so, pal, SPACE_SRGB, 0, THREADS)
+        assert np.array_equal(res[0][1], want["err_fx"]) and np.array_equal(res[0][2], want["counts"]), (w, h, K)
 
 
 def test_other_viewing_conditions_and_custom_filters(backend, oracle):

@@ -40,21 +40,27 @@ sweep)
 multi)
     N=${1:-2}
     nvidia-smi -L | head -8
-    timeout 900 python -m pytest tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -4
+    timeout 1200 python -m pytest tests/test_gpu_multi.py tests/test_gpu_multi_native.py -x -q -m gpu 2>&1 | tail -6
     for n in 1 $N; do
-        if [ "$n" -eq 1 ]; then timeout 600 python bench.py --gpus 1 --no-cpu-baseline > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+        if [ "$n" -eq 1 ]; then timeout 600 python bench.py --gpus 1 --no-cpu-baseline --no-sweeps > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
         else timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus "$n" > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err; fi
         python - <<PY
 import json
 try:
     d = json.loads([l for l in open('gpurun_out/bench_n$n.json') if l.startswith('{')][-1])
-    print('N=$n exhaustive', round(d['value'], 2), 'Gpixel/s', round(d['ms_per_step'], 3), 'ms/step, frac', round(d['roofline']['frac'], 3), '| pruned', round(d['pruned']['value'], 1), 'Gpixel/s | clocks', d['clocks'])
+    print('N=$n exhaustive', round(d['value'], 2), 'Gpixel/s', round(d['ms_per_step'], 3), 'ms/step, frac', round(d['roofline']['frac'], 3), '| e2e', round(d['e2e']['value'], 2), '| pruned', round(d['pruned']['value'], 1), 'Gpixel/s | clocks', d['clocks'])
+    print('   parity', d.get('parity')); print('   strong_64mp', {k: v for k, v in (d.get('strong_64mp') or {}).items() if k in ('ms_per_step', 'value', 'clocks')})
 except Exception as e:
     print('N=$n parse failed', e)
 PY
     done ;;
 micro)
     for m in microbench microbench2 microbench3 microbench4; do [ -x tools/$m ] && timeout 200 ./tools/$m > gpurun_out/$m.json 2> gpurun_out/$m.err; done; ls -la gpurun_out/microbench* ;;
+scbench)
+    timeout 300 python tools/sc_bench.py "$@" > gpurun_out/sc_bench.json 2> gpurun_out/sc_bench.err; tail -2 gpurun_out/sc_bench.err; cat gpurun_out/sc_bench.json
+    timeout 300 python tools/sc_bench.py --once > gpurun_out/sc_plain.log 2>&1 &&
+    timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/sc_launches.csv python tools/sc_bench.py --once > gpurun_out/sc_ncu.log 2>&1
+    grep -E "sc_|assign|pruned" gpurun_out/sc_launches.csv | awk -F'","' '{print $5, $NF}' | tail -14 ;;
 latency)
     timeout 500 python tools/latency_ab.py > gpurun_out/latency_ab.json 2> gpurun_out/latency_ab.err; tail -3 gpurun_out/latency_ab.err; ls -la gpurun_out/latency_ab.json ;;
 *) echo "unknown task $task"; exit 2 ;;
