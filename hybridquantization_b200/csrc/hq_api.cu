@@ -863,7 +863,7 @@ int sc_eval_enqueue(hq_ctx* m, const float* h_pal, int B, int K, int space) {
     // 3. per candidate: separable filters, Opp2LAB, CIE76 against the original, fixed-point sum
     cudaError_t fe = (m->sc_generic || m->sc_unfused) ? cudaErrorNotSupported
                      : hq::launch_sc_candidates_fused(m->d_idx.p, idx16, m->d_sc_tab.p, K, B, m->width, m->rows, m->stride, m->sc_block.data(), m->sc_taps,
-                                                      m->whitepoint, sc_rows(m), m->d_sc_lab.p, m->d_sc_err.p, m->stream);
+                                                      m->whitepoint, sc_rows(m), m->d_sc_lab.p, m->d_sc_err.p, m->sm_count, m->stream);
     if (fe != cudaSuccess && fe != cudaErrorNotSupported) return fail(m, HQ_ERR_CUDA, "fused S-CIELAB kernel launch failed: %s", cudaGetErrorString(fe));
     if (fe == cudaErrorNotSupported) HQ_CUDA(m, m->d_sc_tmp.reserve(7 * m->stride));
     for (int b = 0; b < B && fe == cudaErrorNotSupported; ++b) {   // other tap counts, K > 1024: two kernels per candidate

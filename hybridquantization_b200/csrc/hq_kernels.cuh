@@ -156,7 +156,7 @@ cudaError_t launch_sc_candidate(const void* d_idx, bool idx16, const float4* d_t
 // call launch_sc_candidate per candidate).  d_idx [B][stride], d_tab [B][K], d_err [B]
 cudaError_t launch_sc_candidates_fused(const void* d_idx, bool idx16, const float4* d_tab, int K, int B, int w, int h, size_t stride,
                                        const float* h_filters, int taps, int whitepoint, ScRows rows, const float* d_lab_orig,
-                                       unsigned long long* d_err, cudaStream_t st);
+                                       unsigned long long* d_err, int sm_count, cudaStream_t st);
 
 // error-image mode: dE map between two S-CIELAB images + fixed-point sum
 cudaError_t launch_sc_error_image(const float* d_lab_a, const float* d_lab_b, size_t n, size_t stride, float* d_map, uint8_t* d_map_u8,

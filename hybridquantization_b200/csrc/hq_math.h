@@ -163,6 +163,8 @@ HQ_HD float hq_cbrtf_f64(float t) {
 // The SFU operations carry .ftz: all operands are normal floats on the domain, .ftz only removes the
 // denormal pre-scaling code nvcc otherwise wraps around MUFU.
 #define HQ_CBRT_ETA 0x1p-39f
+// the rare fp64 decision as a CALL: inlined, its ~60 instructions sat in every unrolled copy of every caller's epilogue
+static __device__ __noinline__ float hq_cbrtf_f64_call(float t) { return hq_cbrtf_f64(t); }
 __device__ __forceinline__ float hq_cbrtf_fast(float t) {
     float lg, y0, rq;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(t));
@@ -176,7 +178,7 @@ __device__ __forceinline__ float hq_cbrtf_fast(float t) {
     const float d = __fmul_rn(__fmul_rn(r, 0x1.555556p-2f), rq);
     const float s_lo = __fadd_rn(y0, __fmaf_rn(y0, -HQ_CBRT_ETA, d));
     const float s_hi = __fadd_rn(y0, __fmaf_rn(y0, HQ_CBRT_ETA, d));
-    if (s_lo != s_hi) return hq_cbrtf_f64(t);
+    if (s_lo != s_hi) return hq_cbrtf_f64_call(t);
     return s_lo;
 }
 #endif
@@ -410,6 +412,21 @@ HQ_HD hq_float3 hq_cl_opp_to_lab(float o0, float o1, float o2, hq_float3 ill) {
     const float fx = hq_cl_lab_f(HQ_FDIV(X, ill.x));
     const float fy = hq_cl_lab_f(HQ_FDIV(Y, ill.y));
     const float fz = hq_cl_lab_f(HQ_FDIV(Z, ill.z));
+    hq_float3 lab;
+    lab.x = HQ_FSUB(HQ_FMUL(116.0f, fy), 16.0f);
+    lab.y = HQ_FMUL(500.0f, HQ_FSUB(fx, fy));
+    lab.z = HQ_FMUL(200.0f, HQ_FSUB(fy, fz));
+    return lab;
+}
+// the same with the illuminant known to be one of the plugin's two white points (ScielabProcessor.java:20-21; Y = 1):
+// X / Xn and Z / Zn by the exhaustively verified constant division (hq_div_const == x / c for every float), Y / 1 = Y
+HQ_HD hq_float3 hq_cl_opp_to_lab_white(float o0, float o1, float o2, hq_white w) {
+    const float X = hq_cl_dot3(0.624045f, -1.87044f, -0.155304f, o0, o1, o2);
+    const float Y = hq_cl_dot3(1.36606f, 0.931563f, 0.433903f, o0, o1, o2);
+    const float Z = hq_cl_dot3(1.5013f, 1.41761f, 2.53307f, o0, o1, o2);
+    const float fx = hq_cl_lab_f(hq_div_const(X, w.x, w.rx));
+    const float fy = hq_cl_lab_f(Y);
+    const float fz = hq_cl_lab_f(hq_div_const(Z, w.z, w.rz));
     hq_float3 lab;
     lab.x = HQ_FSUB(HQ_FMUL(116.0f, fy), 16.0f);
     lab.y = HQ_FMUL(500.0f, HQ_FSUB(fx, fy));

@@ -276,142 +276,192 @@ sc_vpass21_kernel(const float* __restrict__ tmp, int w, int h, size_t stride, co
 }
 
 // ---------------------------------------------------------------- fused candidate stage, taps = 21 (round 2)
-// One kernel per population instead of two per candidate with a 7-plane fp32 intermediate in HBM (28 B/px written
-// and read back ~3.5x: ~510 MB per 4K candidate where the stage needs the 1 B/px of indices and the 12 B/px of the
-// original's S-CIELAB).  A CTA owns a tile of kFW x kFH output pixels of one candidate:
-//   1. the tile's palette indices (+10 columns / rows of halo, reflected at the GLOBAL image borders) and the
-//      candidate's K-entry opponent table (cl:194-198) go to shared memory;
-//   2. horizontal pass (cl:234-272): every (row, 4 outputs) task builds its 24-pixel window by table look-up and runs
-//      the 7 x 21 fma chains in ascending tap order -> 7 planes of kFH+20 rows in shared memory;
-//   3. vertical pass (cl:274-306): every (column, 8 output rows) task streams 28 of those rows through registers,
-//      per tap fma(t1,k1,fma(t2,k2,out)); out.x = fma(t3,|k3|,out.x) -> Opp2LAB (cl:124-145) -> CIE76 against the
-//      resident S-CIELAB of the original (cl:209) -> 2^-24 fixed point, one atomic per CTA.
-// Arithmetic, operand order and fma nesting are those of sc_hpass21_kernel / sc_vpass21_kernel<1>: same bits.
-// Cost of the fusion: the horizontal pass is recomputed for the 20 halo rows of every tile ((kFH+20)/kFH = 1.16x).
-constexpr int kFW = 32, kFH = 128, kFThreads = 256;
-constexpr int kFRows = kFH + kT - 1;   // 148 horizontally filtered rows per tile
-constexpr int kFCols = kFW + kT - 1;   // 52 input columns per tile row (13 words of u8)
-static_assert(kFCols % 4 == 0 && kFW % kHOut == 0 && kFH % kVRows == 0, "tile geometry");
+// One kernel per population instead of two per candidate with a 7-plane fp32 intermediate in HBM (28 B/px written and
+// read back ~3.5x: ~510 MB per 4K candidate where the stage needs the 1 B/px of indices and the 12 B/px of the original's
+// S-CIELAB).  A CTA owns a vertical STRIP of kSW columns of one candidate and walks down it in bands of kSBand rows; the
+// horizontally filtered rows live in a ring of kSRing = kSBand + 20 rows in shared memory (7 planes), so every image row
+// is filtered horizontally ONCE per strip (plus 20 rows at each segment start):
+//   H phase (cl:234-272): task = (row, 8 outputs): 28 palette indices from HBM/L2 -> opponent colours by look-up in the
+//       candidate's K-entry table (cl:194-198, shared memory) -> 7 x 21 fma chains per output in ascending tap order
+//       -> ring;
+//   V phase (cl:274-306): task = (column, 8 output rows): 28 ring rows stream through registers, per tap
+//       fma(t1,k1,fma(t2,k2,out)); out.x = fma(t3,|k3|,out.x) -> Opp2LAB (cl:124-145) -> CIE76 against the resident
+//       S-CIELAB of the original (cl:209, its 24 values prefetched before the fma work) -> 2^-24 fixed point.
+// One atomic per CTA.  Arithmetic, operand order and fma nesting are those of sc_hpass21_kernel / sc_vpass21_kernel<1>:
+// same bits (tests/test_gpu_scielab.py holds all three paths and the oracle together).
+// The first version of the fusion (a 32 x 128 tile with all 148 filtered rows in 145 KB of shared memory, 1 CTA/SM) ran
+// 1.8x SLOWER than the two kernels it replaced: ncu showed 28 % issue utilisation at 2 warps per scheduler, 23 % of the
+// stall samples on the index staging loop and 17 % on the S-CIELAB loads of the epilogue (profiles/r02).
+// Second version (this one): strips + a TRANSPOSED vertical filter.  A thread owns one column and streams down its rows;
+// input row v updates the 21 pending outputs o = v+10-t with tap t (ascending t per output = the reference's order) and
+// completes output v-10, so only the CURRENT band of horizontally filtered rows has to sit in shared memory (57 KB for
+// 128 columns -> 3 CTAs/SM) and each ring value is read from shared memory once instead of 3.5 times.  Code size matters:
+// a fully unrolled 8-row register window per phase (38 KB of FFMAs, twice for the prologue) stalled 1.7 cycles per issue
+// on instruction fetch (L1.5 I-cache: 32 KB); here the H task is 4 outputs + a window shift, looped, and the V loop is
+// unrolled by 4 rows with one accumulator shift per 4 rows.
+// The two phases have different register needs (the V accumulators persist for the whole strip, the H window is 84 floats),
+// so they run in different WARPS: warps 0-3 filter vertically (one column each thread), warps 4-7 filter horizontally one
+// band of 8 rows ahead, through a double-buffered ring and four named barriers (full / empty per buffer).
+#ifndef HQ_SC_VUNROLL
+#define HQ_SC_VUNROLL 4   // rows per unrolled V group (4 or 8): one accumulator shift per group vs code size
+#endif
+#ifndef HQ_SC_HHALVES
+#define HQ_SC_HHALVES 2   // 2: the H task is 4 outputs + a window shift, looped twice; 1: 8 outputs fully unrolled
+#endif
+constexpr int kSW = 128, kSBand = 8, kSThreads = 256;
+constexpr int kSHOut = 8;                                              // outputs per H task
+constexpr int kSHPer = kSHOut / HQ_SC_HHALVES;                         // ... per unrolled pass
+constexpr int kSVUnroll = HQ_SC_VUNROLL;
+static_assert(kSBand % kSVUnroll == 0 && kSBand * (kSW / kSHOut) == kSThreads / 2 && kSW == kSThreads / 2, "task geometry");
+
+// named barriers with IMMEDIATE ids (a register id makes ptxas reserve all 16 barriers for the CTA)
+template <int ID> __device__ __forceinline__ void named_bar_sync_i(int count) { asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(count) : "memory"); }
+template <int ID> __device__ __forceinline__ void named_bar_arrive_i(int count) { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(count) : "memory"); }
+template <int ID0> __device__ __forceinline__ void named_bar_sync(int which, int count) { if (which) named_bar_sync_i<ID0 + 1>(count); else named_bar_sync_i<ID0>(count); }
+template <int ID0> __device__ __forceinline__ void named_bar_arrive(int which, int count) { if (which) named_bar_arrive_i<ID0 + 1>(count); else named_bar_arrive_i<ID0>(count); }
 
 template <typename IdxT>
-struct FusedSmem {
-    size_t off_h, off_idx, off_lut, total;
-    __host__ __device__ explicit FusedSmem(int K) {
-        size_t o = 0;
-        off_h = o;   o += (size_t)kFRows * 7 * kFW * sizeof(float);
-        off_lut = o; o += (size_t)K * sizeof(float4);
-        off_idx = o; o += (size_t)kFRows * kFCols * sizeof(IdxT);
-        total = (o + 15) / 16 * 16;
-    }
-};
-
-template <typename IdxT>
-__global__ void __launch_bounds__(kFThreads, 1)
-sc_candidate_fused21_kernel(const IdxT* __restrict__ idx, const float4* __restrict__ tab, int K, int w, int h, size_t stride,
-                            const __grid_constant__ Filt21 f, hq_float3 ill, ScRows rows, const float* __restrict__ lab_orig,
+__global__ void __launch_bounds__(kSThreads, 2)
+sc_candidate_strip21_kernel(const IdxT* __restrict__ idx, const float4* __restrict__ tab, int K, int w, int h, size_t stride, int seg_rows,
+                            const __grid_constant__ Filt21 f, hq_white white, ScRows rows, const float* __restrict__ lab_orig,
                             unsigned long long* __restrict__ err_out) {
-    extern __shared__ __align__(16) unsigned char fused_smem[];
-    const FusedSmem<IdxT> L(K);
-    float* s_h = reinterpret_cast<float*>(fused_smem + L.off_h);           // [kFRows][7][kFW]
-    float4* s_lut = reinterpret_cast<float4*>(fused_smem + L.off_lut);     // [K]
-    IdxT* s_idx = reinterpret_cast<IdxT*>(fused_smem + L.off_idx);         // [kFRows][kFCols]
+    extern __shared__ __align__(16) unsigned char strip_smem[];
+    float* s_ring = reinterpret_cast<float*>(strip_smem);                                              // [2][kSBand][7][kSW]
+    float4* s_lut = reinterpret_cast<float4*>(strip_smem + (size_t)2 * kSBand * 7 * kSW * sizeof(float));  // [K]
+    __shared__ long long s_err[kSW / 32];
     const int tid = threadIdx.x;
     const int b = blockIdx.z;
-    const int x0 = blockIdx.x * kFW, y0 = rows.y_begin + blockIdx.y * kFH;   // first output pixel of the tile (local rows)
-    const IdxT* idx_b = idx + (size_t)b * stride;
-    const float4* tab_b = tab + (size_t)b * K;
+    const int x0 = blockIdx.x * kSW;
+    const int ya = rows.y_begin + blockIdx.y * seg_rows;                 // output rows [ya, yb) of this segment (local rows)
+    const int yb = min(ya + seg_rows, rows.y_begin + rows.y_count);
+    // input (horizontally filtered) rows v = ya-10 .. yb+9 in bands of 8; row v completes output row v-10
+    const int nbands = (yb - ya + 2 * kHalf + kSBand - 1) / kSBand;
+    enum { kBarFull = 1, kBarEmpty = 3 };            // named barriers 1,2 (full[buf]) and 3,4 (empty[buf]); 0 is __syncthreads
 
-    // ---- 1. stage the table and the index tile
-    for (int k = tid; k < K; k += kFThreads) s_lut[k] = __ldg(tab_b + k);
-    for (int i = tid; i < kFRows * kFCols; i += kFThreads) {
-        const int s = i / kFCols, cix = i - s * kFCols;
-        // slot s holds the row the vertical filter reads for virtual row y0 - 10 + s: reflection at the GLOBAL borders;
-        // rows only needed by discarded outputs are clamped into the local array (as sc_vpass21_kernel does)
-        int lr = hq_reflect(rows.g0 + y0 - kHalf + s, rows.gh) - rows.g0;
-        lr = lr < 0 ? 0 : (lr >= h ? h - 1 : lr);
-        int xx = x0 - kHalf + cix;
-        xx = xx < w + kHalf ? hq_reflect(xx, w) : 0;   // beyond the last output's right halo: never used
-        xx = xx < 0 ? 0 : (xx >= w ? w - 1 : xx);
-        s_idx[i] = idx_b[(size_t)lr * w + xx];
-    }
-    __syncthreads();
-
-    // ---- 2. horizontal pass: tasks (slot s, group g of 4 outputs)
-    for (int q = tid; q < kFRows * (kFW / kHOut); q += kFThreads) {
-        const int s = q / (kFW / kHOut), lx = (q - s * (kFW / kHOut)) * kHOut;
-        const IdxT* irow = s_idx + s * kFCols + lx;
-        float win[3][kHOut + kT - 1];
+    if (tid >= kSW) {
+        // =============================== H warps (cl:234-272): one task (row, 8 outputs) per thread and band
+        const int q = tid - kSW;
+        const IdxT* idx_b = idx + (size_t)b * stride;
+        for (int k = q; k < K; k += kSW) s_lut[k] = __ldg(tab + (size_t)b * K + k);
+        named_bar_sync_i<5>(kSW);                      // the table is staged (H warps only)
+        const int hrow = q / (kSW / kSHOut), hg = q - hrow * (kSW / kSHOut);
+        const int xs = x0 + hg * kSHOut - kHalf;
+        const bool interior = xs >= 0 && xs + kSHOut + kT - 1 <= w;
+        for (int band = 0; band < nbands; ++band) {
+            const int buf = band & 1;
+            // virtual row -> array row: reflection at the GLOBAL borders; rows only discarded outputs need are clamped
+            int lr = hq_reflect(rows.g0 + ya - kHalf + band * kSBand + hrow, rows.gh) - rows.g0;
+            lr = lr < 0 ? 0 : (lr >= h ? h - 1 : lr);
+            const IdxT* irow = idx_b + (size_t)lr * w;
+            float win[3][kSHOut + kT - 1];
+            if (interior) {
+                IdxT id[kSHOut + kT - 1];
 #pragma unroll
-        for (int i = 0; i < kHOut + kT - 1; ++i) {
-            const float4 v = s_lut[irow[i]];
-            win[0][i] = v.x; win[1][i] = v.y; win[2][i] = v.z;
-        }
-        float acc[kHOut][7];
+                for (int i = 0; i < kSHOut + kT - 1; ++i) id[i] = __ldg(irow + xs + i);
 #pragma unroll
-        for (int o = 0; o < kHOut; ++o)
+                for (int i = 0; i < kSHOut + kT - 1; ++i) { const float4 c = s_lut[id[i]]; win[0][i] = c.x; win[1][i] = c.y; win[2][i] = c.z; }
+            } else {
 #pragma unroll
-            for (int c = 0; c < 7; ++c) acc[o][c] = 0.f;
-#pragma unroll
-        for (int t = 0; t < kT; ++t)
-#pragma unroll
-            for (int o = 0; o < kHOut; ++o) {
-                const float i0 = win[0][o + t], i1 = win[1][o + t], i2 = win[2][o + t];
-                acc[o][0] = HQ_FFMA(i0, f.v[3 * t], acc[o][0]); acc[o][1] = HQ_FFMA(i1, f.v[3 * t + 1], acc[o][1]); acc[o][2] = HQ_FFMA(i2, f.v[3 * t + 2], acc[o][2]);
-                acc[o][3] = HQ_FFMA(i0, f.v[3 * kT + 3 * t], acc[o][3]); acc[o][4] = HQ_FFMA(i1, f.v[3 * kT + 3 * t + 1], acc[o][4]); acc[o][5] = HQ_FFMA(i2, f.v[3 * kT + 3 * t + 2], acc[o][5]);
-                acc[o][6] = HQ_FFMA(i0, f.v[6 * kT + t], acc[o][6]);
-            }
-        float* dst = s_h + (size_t)s * 7 * kFW + lx;
-#pragma unroll
-        for (int c = 0; c < 7; ++c) *reinterpret_cast<float4*>(dst + c * kFW) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
-    }
-    __syncthreads();
-
-    // ---- 3. vertical pass + Opp2LAB + CIE76: tasks (column lx, group j of 8 output rows); a warp = 32 columns of one group
-    long long fx = 0;
-    const int y_end = rows.y_begin + rows.y_count;
-    for (int q = tid; q < kFW * (kFH / kVRows); q += kFThreads) {
-        const int j = q / kFW, lx = q - j * kFW;
-        const int x = x0 + lx, yb = y0 + j * kVRows;
-        if (x >= w || yb >= y_end) continue;
-        float a[kVRows][3];
-#pragma unroll
-        for (int o = 0; o < kVRows; ++o) a[o][0] = a[o][1] = a[o][2] = 0.f;
-        const float* src = s_h + (size_t)(j * kVRows) * 7 * kFW + lx;
-#pragma unroll
-        for (int r = 0; r < kVRows + kT - 1; ++r) {
-            const float* p = src + (size_t)r * 7 * kFW;
-            const float t10 = p[0], t11 = p[kFW], t12 = p[2 * kFW], t20 = p[3 * kFW], t21 = p[4 * kFW], t22 = p[5 * kFW], t3 = p[6 * kFW];
-#pragma unroll
-            for (int o = 0; o < kVRows; ++o) {
-                const int t = r - o;  // tap of input row r for output row o: ascending in r, the reference's order
-                if (t >= 0 && t < kT) {
-                    a[o][0] = HQ_FFMA(t10, f.v[3 * t], HQ_FFMA(t20, f.v[3 * kT + 3 * t], a[o][0]));
-                    a[o][1] = HQ_FFMA(t11, f.v[3 * t + 1], HQ_FFMA(t21, f.v[3 * kT + 3 * t + 1], a[o][1]));
-                    a[o][2] = HQ_FFMA(t12, f.v[3 * t + 2], HQ_FFMA(t22, f.v[3 * kT + 3 * t + 2], a[o][2]));
-                    a[o][0] = HQ_FFMA(t3, f.v[7 * kT + t], a[o][0]);
+                for (int i = 0; i < kSHOut + kT - 1; ++i) {
+                    int xx = xs + i;
+                    xx = xx < w + kHalf ? hq_reflect(xx, w) : 0;   // beyond the last output's right halo: never used
+                    xx = xx < 0 ? 0 : (xx >= w ? w - 1 : xx);
+                    const float4 c = s_lut[__ldg(irow + xx)];
+                    win[0][i] = c.x; win[1][i] = c.y; win[2][i] = c.z;
                 }
             }
-        }
+            if (band >= 2) named_bar_sync<kBarEmpty>(buf, kSThreads);   // the V warps have read this buffer's previous band
+            float* dst = s_ring + ((size_t)buf * kSBand + hrow) * 7 * kSW + hg * kSHOut;
+#pragma unroll 1
+            for (int half = 0; half < HQ_SC_HHALVES; ++half) {   // kSHPer outputs from the head of the window, then the window moves down
+                float acc[kSHPer][7];
 #pragma unroll
-        for (int o = 0; o < kVRows; ++o) {
-            const int y = yb + o;
-            if (y < y_end) {
-                const hq_float3 lab = hq_cl_opp_to_lab(a[o][0], a[o][1], a[o][2], ill);
-                const size_t p = (size_t)y * w + x;
-                const float d2 = hq_dist2(__ldg(lab_orig + p), __ldg(lab_orig + stride + p), __ldg(lab_orig + 2 * stride + p), lab.x, lab.y, lab.z);
-                fx += hq_to_fx(HQ_FSQRT(d2));
+                for (int o = 0; o < kSHPer; ++o)
+#pragma unroll
+                    for (int c = 0; c < 7; ++c) acc[o][c] = 0.f;
+#pragma unroll
+                for (int t = 0; t < kT; ++t)
+#pragma unroll
+                    for (int o = 0; o < kSHPer; ++o) {
+                        const float i0 = win[0][o + t], i1 = win[1][o + t], i2 = win[2][o + t];
+                        acc[o][0] = HQ_FFMA(i0, f.v[3 * t], acc[o][0]); acc[o][1] = HQ_FFMA(i1, f.v[3 * t + 1], acc[o][1]); acc[o][2] = HQ_FFMA(i2, f.v[3 * t + 2], acc[o][2]);
+                        acc[o][3] = HQ_FFMA(i0, f.v[3 * kT + 3 * t], acc[o][3]); acc[o][4] = HQ_FFMA(i1, f.v[3 * kT + 3 * t + 1], acc[o][4]); acc[o][5] = HQ_FFMA(i2, f.v[3 * kT + 3 * t + 2], acc[o][5]);
+                        acc[o][6] = HQ_FFMA(i0, f.v[6 * kT + t], acc[o][6]);
+                    }
+#pragma unroll
+                for (int c = 0; c < 7; ++c)
+#pragma unroll
+                    for (int o4 = 0; o4 < kSHPer; o4 += 4)
+                        *reinterpret_cast<float4*>(dst + c * kSW + kSHPer * half + o4) = make_float4(acc[o4][c], acc[o4 + 1][c], acc[o4 + 2][c], acc[o4 + 3][c]);
+                if (HQ_SC_HHALVES > 1) {
+#pragma unroll
+                    for (int i = 0; i < kSHOut + kT - 1 - kSHPer; ++i) { win[0][i] = win[0][i + kSHPer]; win[1][i] = win[1][i + kSHPer]; win[2][i] = win[2][i + kSHPer]; }
+                }
+            }
+            named_bar_arrive<kBarFull>(buf, kSThreads);
+        }
+        return;
+    }
+
+    // =================================== V warps (cl:274-306), transposed: one column per thread
+    const int x = x0 + tid;
+    const bool vact = x < w;
+    float A[kT + kSVUnroll - 1][3];                   // pending outputs: at phase p of a row group, tap t lives in slot t + kSVUnroll - 1 - p
+#pragma unroll
+    for (int j = 0; j < kT + kSVUnroll - 1; ++j) A[j][0] = A[j][1] = A[j][2] = 0.f;
+    long long fx = 0;
+    for (int band = 0; band < nbands; ++band) {
+        const int buf = band & 1;
+        const int vb = ya - kHalf + band * kSBand;    // first input row of the band
+        named_bar_sync<kBarFull>(buf, kSThreads);
+        if (vact) {
+#pragma unroll 1
+            for (int r0 = 0; r0 < kSBand; r0 += kSVUnroll) {
+                // the four outputs this group completes: rows vb + r0 + p - 10; their S-CIELAB originals fly during the fma work
+                float lo[kSVUnroll][3];
+#pragma unroll
+                for (int p = 0; p < kSVUnroll; ++p) {
+                    int y = vb + r0 + p - kHalf;
+                    y = y < ya ? ya : (y >= yb ? yb - 1 : y);
+                    const size_t pp = (size_t)y * w + x;
+                    lo[p][0] = __ldg(lab_orig + pp); lo[p][1] = __ldg(lab_orig + stride + pp); lo[p][2] = __ldg(lab_orig + 2 * stride + pp);
+                }
+#pragma unroll
+                for (int p = 0; p < kSVUnroll; ++p) {
+                    const float* src = s_ring + ((size_t)buf * kSBand + r0 + p) * 7 * kSW + tid;
+                    const float t10 = src[0], t11 = src[kSW], t12 = src[2 * kSW], t20 = src[3 * kSW], t21 = src[4 * kSW], t22 = src[5 * kSW], t3 = src[6 * kSW];
+#pragma unroll
+                    for (int t = 0; t < kT; ++t) {
+                        float* a = A[t + kSVUnroll - 1 - p];
+                        a[0] = HQ_FFMA(t10, f.v[3 * t], HQ_FFMA(t20, f.v[3 * kT + 3 * t], a[0]));
+                        a[1] = HQ_FFMA(t11, f.v[3 * t + 1], HQ_FFMA(t21, f.v[3 * kT + 3 * t + 1], a[1]));
+                        a[2] = HQ_FFMA(t12, f.v[3 * t + 2], HQ_FFMA(t22, f.v[3 * kT + 3 * t + 2], a[2]));
+                        a[0] = HQ_FFMA(t3, f.v[7 * kT + t], a[0]);
+                    }
+                    const int y = vb + r0 + p - kHalf;            // completed: tap 20 was the last
+                    if (y >= ya && y < yb) {
+                        const float* a = A[kT + kSVUnroll - 2 - p];
+                        const hq_float3 lab = hq_cl_opp_to_lab_white(a[0], a[1], a[2], white);
+                        fx += hq_to_fx(HQ_FSQRT(hq_dist2(lo[p][0], lo[p][1], lo[p][2], lab.x, lab.y, lab.z)));
+                    }
+                }
+                // kSVUnroll rows further every pending output's tap has grown by as much: slot j -> j + kSVUnroll, fresh outputs enter below
+#pragma unroll
+                for (int j = kT + kSVUnroll - 2; j >= kSVUnroll; --j) { A[j][0] = A[j - kSVUnroll][0]; A[j][1] = A[j - kSVUnroll][1]; A[j][2] = A[j - kSVUnroll][2]; }
+#pragma unroll
+                for (int j = 0; j < kSVUnroll; ++j) A[j][0] = A[j][1] = A[j][2] = 0.f;
             }
         }
+        if (band + 2 < nbands) named_bar_arrive<kBarEmpty>(buf, kSThreads);   // an H warp will wait for it
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) fx += __shfl_down_sync(0xffffffffu, fx, off);
-    __shared__ long long s_err[kFThreads / 32];
     if ((tid & 31) == 0) s_err[tid >> 5] = fx;
-    __syncthreads();
+    named_bar_sync_i<6>(kSW);                          // V warps only
     if (tid == 0) {
         long long e = 0;
 #pragma unroll
-        for (int i = 0; i < kFThreads / 32; ++i) e += s_err[i];
+        for (int i = 0; i < kSW / 32; ++i) e += s_err[i];
         if (e) atomicAdd(err_out + b, (unsigned long long)e);
     }
 }
@@ -516,31 +566,45 @@ cudaError_t launch_sc_candidate(const void* d_idx, bool idx16, const float4* d_t
 // (then the caller runs launch_sc_candidate per candidate).
 cudaError_t launch_sc_candidates_fused(const void* d_idx, bool idx16, const float4* d_tab, int K, int B, int w, int h, size_t stride,
                                        const float* h_filters, int taps, int whitepoint, ScRows rows, const float* d_lab_orig,
-                                       unsigned long long* d_err, cudaStream_t st) {
+                                       unsigned long long* d_err, int sm_count, cudaStream_t st) {
     if (taps != kT || !h_filters || K > kMaxColors || B > 65535) return cudaErrorNotSupported;
     if (w == 0 || h == 0 || rows.y_count == 0 || B == 0) return cudaSuccess;
     Filt21 f21;
     for (int i = 0; i < 8 * kT; ++i) f21.v[i] = h_filters[i];
-    const dim3 grid((unsigned)((w + kFW - 1) / kFW), (unsigned)((rows.y_count + kFH - 1) / kFH), (unsigned)B);
+    const size_t smem = (size_t)2 * kSBand * 7 * kSW * sizeof(float) + (size_t)K * sizeof(float4);
+    const int strips = (w + kSW - 1) / kSW;
+    // rows per segment: every segment start costs 20 extra horizontally filtered rows, so segments are as long as they can
+    // be while the grid still holds >= 2.5 waves of the resident CTAs (2 per SM)
+    const long long slots = (long long)(sm_count > 0 ? sm_count : 148) * 2;
+    int seg_rows = 64;
+    for (int cand = 1024; cand >= 64; cand = cand * 3 / 4) {
+        const long long nseg = (rows.y_count + cand - 1) / cand;
+        if ((long long)strips * B * nseg >= 5 * slots / 2) { seg_rows = cand; break; }
+    }
+    {   // equal segments: the last one must not be a stub
+        const int nseg = (rows.y_count + seg_rows - 1) / seg_rows;
+        seg_rows = ((rows.y_count + nseg - 1) / nseg + kSBand - 1) / kSBand * kSBand;
+    }
+    const dim3 grid((unsigned)strips, (unsigned)((rows.y_count + seg_rows - 1) / seg_rows), (unsigned)B);
     if (grid.y > 65535) return cudaErrorNotSupported;
     static std::mutex mu;
     static size_t configured[2][64];   // per index width and device: largest dynamic shared memory set so far (process-wide, monotonic)
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    const size_t smem = idx16 ? FusedSmem<uint16_t>(K).total : FusedSmem<uint8_t>(K).total;
     {
         std::lock_guard<std::mutex> lock(mu);
         size_t& have = configured[idx16 ? 1 : 0][dev & 63];
         if (smem > have) {
-            e = idx16 ? cudaFuncSetAttribute(sc_candidate_fused21_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                      : cudaFuncSetAttribute(sc_candidate_fused21_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e = idx16 ? cudaFuncSetAttribute(sc_candidate_strip21_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                      : cudaFuncSetAttribute(sc_candidate_strip21_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             have = smem;
         }
     }
-    if (idx16) sc_candidate_fused21_kernel<uint16_t><<<grid, kFThreads, smem, st>>>(static_cast<const uint16_t*>(d_idx), d_tab, K, w, h, stride, f21, hq_whitepoint(whitepoint), rows, d_lab_orig, d_err);
-    else sc_candidate_fused21_kernel<uint8_t><<<grid, kFThreads, smem, st>>>(static_cast<const uint8_t*>(d_idx), d_tab, K, w, h, stride, f21, hq_whitepoint(whitepoint), rows, d_lab_orig, d_err);
+    const hq_white white = hq_make_white(whitepoint);
+    if (idx16) sc_candidate_strip21_kernel<uint16_t><<<grid, kSThreads, smem, st>>>(static_cast<const uint16_t*>(d_idx), d_tab, K, w, h, stride, seg_rows, f21, white, rows, d_lab_orig, d_err);
+    else sc_candidate_strip21_kernel<uint8_t><<<grid, kSThreads, smem, st>>>(static_cast<const uint8_t*>(d_idx), d_tab, K, w, h, stride, seg_rows, f21, white, rows, d_lab_orig, d_err);
     return cudaGetLastError();
 }
 

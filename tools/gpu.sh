@@ -61,6 +61,15 @@ scbench)
     timeout 300 python tools/sc_bench.py --once > gpurun_out/sc_plain.log 2>&1 &&
     timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/sc_launches.csv python tools/sc_bench.py --once > gpurun_out/sc_ncu.log 2>&1
     grep -E "sc_|assign|pruned" gpurun_out/sc_launches.csv | awk -F'","' '{print $5, $NF}' | tail -14 ;;
+ncupy)
+    # one `ncu --set full` capture of a kernel of any python command: ncupy <kernel-regex> <skip> <script and args...>
+    regex=${1:?kernel regex}; skip=${2:-0}; shift; shift
+    python "$@" > gpurun_out/plain_ncu.log 2>&1 &&
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:$regex -s $skip -c 1 -f -o gpurun_out/prof python "$@" > gpurun_out/ncu.log 2>&1
+    echo "capture rc=$?"
+    ncu -i gpurun_out/prof.ncu-rep --page raw --csv > gpurun_out/prof_raw.csv 2>/dev/null
+    ncu -i gpurun_out/prof.ncu-rep --page source --csv > gpurun_out/prof_source.csv 2>/dev/null
+    ls -la gpurun_out/prof* ;;
 latency)
     timeout 500 python tools/latency_ab.py > gpurun_out/latency_ab.json 2> gpurun_out/latency_ab.err; tail -3 gpurun_out/latency_ab.err; ls -la gpurun_out/latency_ab.json ;;
 *) echo "unknown task $task"; exit 2 ;;
