@@ -73,6 +73,10 @@ SIGNATURES = {
     "hq_scielab_get_image": (C.c_int, [_P, _P]),
     "hq_error_image": (C.c_int, [_P, _P, _P, _P, C.POINTER(C.c_double)]),
     "hq_error_image_f32_planar": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "hq_rgb_to_xyz": (C.c_int, [_P, _P, _P, _P, C.c_size_t, _P]),
+    "hq_xyz_to_scielab": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
+    "hq_scielab_set_image": (C.c_int, [_P, _P]),
+    "hq_delta_e_images": (C.c_int, [_P, _P, _P, C.c_size_t, _P, C.POINTER(C.c_double)]),
     "hq_scielab_force_generic": (C.c_int, [_P, C.c_int]),
     "hq_scielab_build_filters": (C.c_int, [C.c_int, C.c_float, _P, _P, C.POINTER(C.c_int)]),
     "hq_eval_palettes_scielab": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),

@@ -745,6 +745,112 @@ int hq_scielab_get_image(hq_ctx* c, float* planes) {
     return bind_device(c);
 }
 
+// ---- the reference class's one-shot entries on its own layouts (what a Java drop-in with the reference's signatures calls)
+int hq_rgb_to_xyz(hq_ctx* c, const float* r, const float* g, const float* b, size_t n, float* xyz4) try {
+    if (!c || !xyz4 || ((!r || !g || !b) && n)) return c ? fail(c, HQ_ERR_INVALID, "NULL array") : HQ_ERR_INVALID;
+    int rc = bind_device(c); if (rc) return rc;
+    DevBuf<float> in, out;
+    HQ_CUDA(c, in.reserve(3 * n ? 3 * n : 1));
+    HQ_CUDA(c, out.reserve(4 * n ? 4 * n : 1));
+    HQ_CUDA(c, c->d_flag.reserve(1));
+    cudaError_t e = cudaMemsetAsync(c->d_flag.p, 0, sizeof(unsigned int), c->stream);
+    const float* src[3] = {r, g, b};
+    for (int pl = 0; pl < 3 && n && e == cudaSuccess; ++pl) e = cudaMemcpyAsync(in.p + (size_t)pl * n, src[pl], n * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = hq::launch_sc_unit_to_xyz4(in.p, in.p + n, in.p + 2 * n, n, out.p, c->d_flag.p, c->stream);
+    unsigned int bad = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, c->d_flag.p, sizeof bad, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(xyz4, out.p, 4 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    in.release(); out.release();
+    if (e != cudaSuccess) return fail(c, HQ_ERR_CUDA, "hq_rgb_to_xyz failed: %s", cudaGetErrorString(e));
+    if (bad) return fail(c, HQ_ERR_INVALID, "float image values must lie in [0,1] (Icy's rescaled convertToType, HybridQuantization.java:95)");
+    return HQ_OK;
+} catch (const std::exception& ex) { return api_exception(c, ex); }
+
+int hq_xyz_to_scielab(hq_ctx* c, const float* xyz4, int width, int rows, const float* illuminant3, float* lab4) try {
+    if (!c || !xyz4 || !lab4 || !illuminant3) return c ? fail(c, HQ_ERR_INVALID, "NULL array") : HQ_ERR_INVALID;
+    if (width < 1 || rows < 1) return fail(c, HQ_ERR_INVALID, "bad image size %d x %d", width, rows);
+    int rc = bind_device(c); if (rc) return rc;
+    if (c->sc_taps == 0) { rc = hq_scielab_configure(c, 72, 45.0f); if (rc) return rc; }  // plugin defaults :229-231
+    const int half = c->sc_taps / 2;
+    if (width < half || rows < half)
+        return fail(c, HQ_ERR_UNSUPPORTED, "image %dx%d is smaller than the filter half-width %d (the reference's single reflection, "
+                    "OptimizedConvolution.cl:20-27, would read out of bounds)", width, rows, half);
+    if (rows > 65535) return fail(c, HQ_ERR_UNSUPPORTED, "at most 65,535 rows (got %d)", rows);
+    const size_t n = (size_t)width * rows, stride = hq::plane_stride(n);
+    DevBuf<float> io, opp, tmp, lab;
+    cudaError_t e = io.reserve(4 * n);
+    if (e == cudaSuccess) e = opp.reserve(3 * stride);
+    if (e == cudaSuccess) e = tmp.reserve(7 * stride);
+    if (e == cudaSuccess) e = lab.reserve(3 * stride);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(io.p, xyz4, 4 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = hq::launch_sc_xyz4_to_opp(io.p, n, stride, opp.p, c->stream);
+    if (e == cudaSuccess) e = hq::launch_sc_original(opp.p, width, rows, stride, c->d_sc_filters.p, c->sc_generic ? nullptr : c->sc_block.data(), c->sc_taps,
+                                                     HQ_WHITEPOINT_D65, hq::ScRows{0, rows, 0, rows}, tmp.p, lab.p, c->stream, illuminant3);
+    if (e == cudaSuccess) e = hq::launch_sc_planes_to_f4(lab.p, n, stride, io.p, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(lab4, io.p, 4 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    io.release(); opp.release(); tmp.release(); lab.release();
+    if (e != cudaSuccess) return fail(c, HQ_ERR_CUDA, "hq_xyz_to_scielab failed: %s", cudaGetErrorString(e));
+    return HQ_OK;
+} catch (const std::exception& ex) { return api_exception(c, ex); }
+
+namespace {
+// lab4: the WHOLE image's [n][4] S-CIELAB values; context m takes the rows it holds (halo rows included)
+int scielab_set_image_one(hq_ctx* m, const float* lab4_whole) {
+    int rc = bind_device(m); if (rc) return rc;
+    if (!m->have_image) return fail(m, HQ_ERR_NO_IMAGE, "no image: call hq_set_image_u8 or hq_set_image_f32_planar first");
+    if (m->sc_taps == 0) { rc = hq_scielab_configure(m, 72, 45.0f); if (rc) return rc; }
+    if (m->n == 0) { m->sc_image_ready = true; return HQ_OK; }
+    const size_t first = (size_t)(m->g_row0 - m->halo_top) * m->width;
+    DevBuf<float> in;
+    HQ_CUDA(m, in.reserve(4 * m->n));
+    HQ_CUDA(m, m->d_sc_opp.reserve(3 * m->stride));
+    HQ_CUDA(m, m->d_sc_tmp.reserve(7 * m->stride));
+    HQ_CUDA(m, m->d_sc_lab.reserve(3 * m->stride));
+    cudaError_t e = cudaMemcpyAsync(in.p, lab4_whole + 4 * first, 4 * m->n * sizeof(float), cudaMemcpyHostToDevice, m->stream);
+    if (e == cudaSuccess) e = hq::launch_sc_f4_to_planes(in.p, m->n, m->stride, m->d_sc_lab.p, m->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+    in.release();
+    if (e != cudaSuccess) return fail(m, HQ_ERR_CUDA, "hq_scielab_set_image failed: %s", cudaGetErrorString(e));
+    m->sc_image_ready = true;
+    return HQ_OK;
+}
+}  // namespace
+
+int hq_scielab_set_image(hq_ctx* c, const float* lab4) try {
+    if (!c || !lab4) return c ? fail(c, HQ_ERR_INVALID, "lab4 is NULL") : HQ_ERR_INVALID;
+    if (!c->is_multi() && (c->halo_top || c->halo_bottom || c->g_rows != c->own_rows))
+        return fail(c, HQ_ERR_UNSUPPORTED, "hq_scielab_set_image takes the whole image: not available on an explicit row shard");
+    std::vector<hq_ctx*> self(1, c);
+    for (hq_ctx* m : (c->is_multi() ? c->members : self)) { const int rc = member_rc(c, m, scielab_set_image_one(m, lab4)); if (rc) return rc; }
+    return bind_device(c);
+} catch (const std::exception& ex) { return api_exception(c, ex); }
+
+int hq_delta_e_images(hq_ctx* c, const float* lab4_a, const float* lab4_b, size_t n, float* error_rgba4, double* mean_de) try {
+    if (!c || ((!lab4_a || !lab4_b) && n)) return c ? fail(c, HQ_ERR_INVALID, "NULL array") : HQ_ERR_INVALID;
+    int rc = bind_device(c); if (rc) return rc;
+    DevBuf<float> a, b, e, img;
+    std::vector<float> he(n);
+    cudaError_t ce = a.reserve(4 * n ? 4 * n : 1);
+    if (ce == cudaSuccess) ce = b.reserve(4 * n ? 4 * n : 1);
+    if (ce == cudaSuccess) ce = e.reserve(n ? n : 1);
+    if (ce == cudaSuccess && error_rgba4) ce = img.reserve(4 * n ? 4 * n : 1);
+    if (ce == cudaSuccess && n) ce = cudaMemcpyAsync(a.p, lab4_a, 4 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+    if (ce == cudaSuccess && n) ce = cudaMemcpyAsync(b.p, lab4_b, 4 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+    if (ce == cudaSuccess && n && error_rgba4) ce = cudaMemcpyAsync(img.p, error_rgba4, 4 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+    if (ce == cudaSuccess) ce = hq::launch_sc_delta_e4(a.p, b.p, n, e.p, error_rgba4 ? img.p : nullptr, c->stream);
+    if (ce == cudaSuccess && n) ce = cudaMemcpyAsync(he.data(), e.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (ce == cudaSuccess && n && error_rgba4) ce = cudaMemcpyAsync(error_rgba4, img.p, 4 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
+    a.release(); b.release(); e.release(); img.release();
+    if (ce != cudaSuccess) return fail(c, HQ_ERR_CUDA, "hq_delta_e_images failed: %s", cudaGetErrorString(ce));
+    double sum = 0.0;   // ImageManipulation.java:886-893: the floats summed in a double, in pixel order, then / n
+    for (size_t i = 0; i < n; ++i) sum += (double)he[i];
+    if (mean_de) *mean_de = n ? sum / (double)n : 0.0;
+    return HQ_OK;
+} catch (const std::exception& ex) { return api_exception(c, ex); }
+
 // error-image mode: HybridQuantization.errorImage (:139-182) + ImageManipulation.computeError (:858-894)
 namespace {
 // the second image of error-image mode, as packed u8 (rgb8) or as float planes (f32[3])

@@ -145,8 +145,16 @@ cudaError_t launch_sc_palette_opp(const float* d_palettes, int total, float4* d_
 // original image: opp planes -> S-CIELAB Lab planes (d_tmp: 7 planes of scratch)
 // h_filters: the same block on the host (nullptr = always use the generic kernels); with taps == 21
 // (plugin defaults) the specialised kernels take it as a kernel parameter
+// illuminant3 (optional): an explicit white point instead of the enum's (XYZtoScielab's float[] illuminant, ImageManipulation.java:285)
 cudaError_t launch_sc_original(const float* d_opp, int w, int h, size_t stride, const float* d_filters, const float* h_filters, int taps,
-                               int whitepoint, ScRows rows, float* d_tmp, float* d_lab_out, cudaStream_t st);
+                               int whitepoint, ScRows rows, float* d_tmp, float* d_lab_out, cudaStream_t st, const float* illuminant3 = nullptr);
+// the reference class's one-shot entries on its interleaved float4 layouts (hq_rgb_to_xyz, hq_xyz_to_scielab, hq_scielab_set_image,
+// hq_delta_e_images)
+cudaError_t launch_sc_unit_to_xyz4(const float* d_r, const float* d_g, const float* d_b, size_t n, float* d_xyz4, unsigned int* d_bad, cudaStream_t st);
+cudaError_t launch_sc_xyz4_to_opp(const float* d_xyz4, size_t n, size_t stride, float* d_opp, cudaStream_t st);
+cudaError_t launch_sc_planes_to_f4(const float* d_planes, size_t n, size_t stride, float* d_out4, cudaStream_t st);
+cudaError_t launch_sc_f4_to_planes(const float* d_in4, size_t n, size_t stride, float* d_planes, cudaStream_t st);
+cudaError_t launch_sc_delta_e4(const float* d_a4, const float* d_b4, size_t n, float* d_e, float* d_err_img4, cudaStream_t st);
 // one candidate: index image + opponent table -> fixed-point sum of dE against d_lab_orig, added to *d_err
 cudaError_t launch_sc_candidate(const void* d_idx, bool idx16, const float4* d_tab, int w, int h, size_t stride, const float* d_filters,
                                 const float* h_filters, int taps, int whitepoint, ScRows rows, float* d_tmp, const float* d_lab_orig,

@@ -495,7 +495,89 @@ __global__ void sc_error_image_kernel(const float* __restrict__ lab_a, const flo
     }
 }
 
+// ---- the reference class's one-shot entries on its own interleaved layouts (float4 per pixel, 4th lane 0)
+// RGBtoXYZ (ImageManipulation.java:100-152, kernel RGB2XYZ cl:79-90): planar sRGB floats -> XYZ float4
+__global__ void sc_unit_to_xyz4_kernel(const float* __restrict__ r, const float* __restrict__ g, const float* __restrict__ b, size_t n,
+                                       float4* __restrict__ xyz, unsigned int* __restrict__ bad) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float cr = r[i], cg = g[i], cb = b[i];
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cr >= 0.f && cr <= 1.f && cg >= 0.f && cg <= 1.f && cb >= 0.f && cb <= 1.f) {
+        const float R = hq_srgb_decode(cr), G = hq_srgb_decode(cg), B = hq_srgb_decode(cb);
+        o.x = hq_cl_dot3(0.4124564f, 0.3575761f, 0.1804375f, R, G, B);
+        o.y = hq_cl_dot3(0.2126729f, 0.7151522f, 0.0721750f, R, G, B);
+        o.z = hq_cl_dot3(0.0193339f, 0.1191920f, 0.9503041f, R, G, B);
+    } else {
+        atomicOr(bad, 1u);
+    }
+    xyz[i] = o;
+}
+// XYZ2Opp (cl:111-116) into the planes the filter kernels read
+__global__ void sc_xyz4_to_opp_kernel(const float4* __restrict__ xyz, size_t n, size_t stride, float* __restrict__ opp) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 v = xyz[i];
+    opp[i] = hq_cl_dot3(0.2787336f, 0.7218031f, -0.1065520f, v.x, v.y, v.z);
+    opp[stride + i] = hq_cl_dot3(-0.4487736f, 0.2898056f, -0.0771569f, v.x, v.y, v.z);
+    opp[2 * stride + i] = hq_cl_dot3(0.0859513f, -0.5899859f, 0.5011089f, v.x, v.y, v.z);
+}
+__global__ void sc_planes_to_f4_kernel(const float* __restrict__ planes, size_t n, size_t stride, float4* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_float4(planes[i], planes[stride + i], planes[2 * stride + i], 0.f);
+}
+__global__ void sc_f4_to_planes_kernel(const float4* __restrict__ in, size_t n, size_t stride, float* __restrict__ planes) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 v = in[i];
+    planes[i] = v.x; planes[stride + i] = v.y; planes[2 * stride + i] = v.z;
+}
+// computeError (ImageManipulation.java:858-894): CIEDE kernel (cl:201-209) on two interleaved Lab images + the error image
+// value ((255 - e) * (255 - e)) / (255 * 255) of :890, written to the first three lanes as the reference does
+__global__ void sc_delta_e4_kernel(const float4* __restrict__ a, const float4* __restrict__ b, size_t n, float* __restrict__ e_out,
+                                   float4* __restrict__ err_img) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = a[i], q = b[i];
+    const float e = HQ_FSQRT(hq_dist2(p.x, p.y, p.z, q.x, q.y, q.z));
+    e_out[i] = e;
+    if (err_img) {
+        const float d = HQ_FSUB(255.0f, e);
+        const float v = HQ_FDIV(HQ_FMUL(d, d), 65025.0f);
+        float4 o = err_img[i];   // the 4th lane is left as the caller has it (:890 writes off .. off+2)
+        o.x = v; o.y = v; o.z = v;
+        err_img[i] = o;
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_sc_unit_to_xyz4(const float* d_r, const float* d_g, const float* d_b, size_t n, float* d_xyz4, unsigned int* d_bad, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    sc_unit_to_xyz4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_r, d_g, d_b, n, reinterpret_cast<float4*>(d_xyz4), d_bad);
+    return cudaGetLastError();
+}
+cudaError_t launch_sc_xyz4_to_opp(const float* d_xyz4, size_t n, size_t stride, float* d_opp, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    sc_xyz4_to_opp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(d_xyz4), n, stride, d_opp);
+    return cudaGetLastError();
+}
+cudaError_t launch_sc_planes_to_f4(const float* d_planes, size_t n, size_t stride, float* d_out4, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    sc_planes_to_f4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_planes, n, stride, reinterpret_cast<float4*>(d_out4));
+    return cudaGetLastError();
+}
+cudaError_t launch_sc_f4_to_planes(const float* d_in4, size_t n, size_t stride, float* d_planes, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    sc_f4_to_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(d_in4), n, stride, d_planes);
+    return cudaGetLastError();
+}
+cudaError_t launch_sc_delta_e4(const float* d_a4, const float* d_b4, size_t n, float* d_e, float* d_err_img4, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    sc_delta_e4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(d_a4), reinterpret_cast<const float4*>(d_b4), n, d_e,
+                                                                     reinterpret_cast<float4*>(d_err_img4));
+    return cudaGetLastError();
+}
 
 cudaError_t launch_sc_error_image(const float* d_lab_a, const float* d_lab_b, size_t n, size_t stride, float* d_map, uint8_t* d_map_u8,
                                   unsigned long long* d_err, cudaStream_t st) {
@@ -523,20 +605,22 @@ cudaError_t launch_sc_unit_to_opp(const float* d_unit, size_t n, size_t stride, 
 }
 
 cudaError_t launch_sc_original(const float* d_opp, int w, int h, size_t stride, const float* d_filters, const float* h_filters, int taps,
-                               int whitepoint, ScRows rows, float* d_tmp, float* d_lab_out, cudaStream_t st) {
+                               int whitepoint, ScRows rows, float* d_tmp, float* d_lab_out, cudaStream_t st, const float* illuminant3) {
     if (w == 0 || h == 0 || rows.y_count == 0) return cudaSuccess;
+    hq_float3 ill = hq_whitepoint(whitepoint);
+    if (illuminant3) { ill.x = illuminant3[0]; ill.y = illuminant3[1]; ill.z = illuminant3[2]; }   // XYZtoScielab's float[] illuminant (:285)
     if (taps == kT && h_filters) {
         Filt21 f21;
         for (int i = 0; i < 8 * kT; ++i) f21.v[i] = h_filters[i];
         const dim3 gh((unsigned)((w + kHSeg - 1) / kHSeg), (unsigned)h), gv((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)((rows.y_count + kVRows - 1) / kVRows));
         sc_hpass21_kernel<0, uint8_t><<<gh, kScThreads, 0, st>>>(d_opp, nullptr, nullptr, w, h, stride, f21, d_tmp);
-        sc_vpass21_kernel<0><<<gv, kScThreads, 0, st>>>(d_tmp, w, h, stride, f21, hq_whitepoint(whitepoint), rows, d_lab_out, nullptr, nullptr);
+        sc_vpass21_kernel<0><<<gv, kScThreads, 0, st>>>(d_tmp, w, h, stride, f21, ill, rows, d_lab_out, nullptr, nullptr);
         return cudaGetLastError();
     }
     const ScFilters f{d_filters, taps};
     const dim3 grid((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)h), gridv((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)rows.y_count);
     sc_hpass_kernel<0, uint8_t><<<grid, kScThreads, 7 * taps * sizeof(float), st>>>(d_opp, nullptr, nullptr, w, h, stride, f, d_tmp);
-    sc_vpass_kernel<0><<<gridv, kScThreads, 8 * taps * sizeof(float), st>>>(d_tmp, w, h, stride, f, hq_whitepoint(whitepoint), rows, d_lab_out, nullptr, nullptr);
+    sc_vpass_kernel<0><<<gridv, kScThreads, 8 * taps * sizeof(float), st>>>(d_tmp, w, h, stride, f, ill, rows, d_lab_out, nullptr, nullptr);
     return cudaGetLastError();
 }
 

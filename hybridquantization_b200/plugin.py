@@ -297,6 +297,42 @@ class ImageManipulation:
         _lib.check(self._ctx, self._lib.hq_eval_palettes_scielab(self._ctx, _ptr(palettes), B, K, space, _ptr(err), _ptr(counts)))
         return {"err_fx": err, "counts": counts}
 
+    # -- the reference class's own entries on its interleaved float4 layouts (what CudaImageManipulation.java calls)
+    def RGBtoXYZ(self, R: np.ndarray, G: np.ndarray, B: np.ndarray) -> np.ndarray:
+        """ImageManipulation.RGBtoXYZ (:100-152): planar sRGB floats in [0,1] -> XYZ float32 [n, 4]"""
+        R, G, B = (np.ascontiguousarray(a, np.float32).ravel() for a in (R, G, B))
+        out = np.empty((R.size, 4), np.float32)
+        _lib.check(self._ctx, self._lib.hq_rgb_to_xyz(self._ctx, _ptr(R), _ptr(G), _ptr(B), R.size, _ptr(out)))
+        return out
+
+    def XYZtoScielab(self, XYZ: np.ndarray, w: int, illuminant) -> np.ndarray:
+        """ImageManipulation.XYZtoScielab (:285-370) with the context's filter bank: XYZ [n, 4] -> S-CIELAB [n, 4]"""
+        XYZ = np.ascontiguousarray(XYZ, np.float32).reshape(-1, 4)
+        ill = np.ascontiguousarray(illuminant, np.float32)
+        out = np.empty_like(XYZ)
+        _lib.check(self._ctx, self._lib.hq_xyz_to_scielab(self._ctx, _ptr(XYZ), w, XYZ.shape[0] // w, _ptr(ill), _ptr(out)))
+        return out
+
+    def scielabSetImage(self, lab4: np.ndarray) -> None:
+        """findBestQuantization's inlineScielabOriginal argument (:383): the caller's S-CIELAB image [n, 4] becomes the target"""
+        lab4 = np.ascontiguousarray(lab4, np.float32).reshape(-1, 4)
+        if lab4.shape[0] != self.pixels():
+            raise ValueError("the S-CIELAB image must have one float4 per pixel of the resident image")
+        _lib.check(self._ctx, self._lib.hq_scielab_set_image(self._ctx, _ptr(lab4)))
+
+    def computeErrorLab(self, original: np.ndarray, quantized: np.ndarray, errorImage: np.ndarray | None = None) -> float:
+        """ImageManipulation.computeError (:858-894) as the reference declares it: two Lab images [n, 4] -> mean dE; errorImage
+        [n, 4] (optional) receives ((255 - e)^2) / 255^2 in its first three lanes"""
+        a = np.ascontiguousarray(original, np.float32).reshape(-1, 4)
+        b = np.ascontiguousarray(quantized, np.float32).reshape(-1, 4)
+        if a.shape != b.shape:
+            raise ValueError("Mismatching image sizes or not enough channels, abort.")
+        if errorImage is not None and (errorImage.dtype != np.float32 or not errorImage.flags.c_contiguous or errorImage.size != a.size):
+            raise ValueError("errorImage must be a contiguous float32 array of the images' size")
+        mean = C.c_double()
+        _lib.check(self._ctx, self._lib.hq_delta_e_images(self._ctx, _ptr(a), _ptr(b), a.shape[0], _ptr(errorImage), C.byref(mean)))
+        return mean.value
+
     def computeError(self, quantized_rgb: np.ndarray) -> dict:
         """Error-image mode (ImageManipulation.computeError :858-894): mean dE between S-CIELAB(original) and
         S-CIELAB(quantized) and the ((255-dE)^2)/255^2 map."""

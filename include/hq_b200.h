@@ -183,6 +183,20 @@ int hq_error_image(hq_ctx* ctx, const uint8_t* quantized_rgb, float* error_map, 
 /* the second image as float planes in [0,1] (errorImage converts both sequences to FLOAT, HybridQuantization.java:142-143) */
 int hq_error_image_f32_planar(hq_ctx* ctx, const float* r, const float* g, const float* b, float* error_map, uint8_t* error_map_u8,
                               double* mean_de);
+/* ---- the reference class's remaining one-shot entries, on its own interleaved layouts ([n][4] floats, 4th lane 0), so that a
+ * Java drop-in can keep the reference's method signatures (java/plugins/.../CudaImageManipulation.java):
+ *   hq_rgb_to_xyz         RGBtoXYZ (ImageManipulation.java:100-152, kernel RGB2XYZ cl:79-90): planar sRGB in [0,1] -> XYZ
+ *   hq_xyz_to_scielab     XYZtoScielab (:285-370): XYZ2Opp, the three separable filter pairs, Opp2LAB with the caller's
+ *                         illuminant[3]; uses the context's filter bank (hq_scielab_configure / _set_filters; defaults 72 dpi, 45 cm)
+ *   hq_scielab_set_image  installs the caller's S-CIELAB image of the resident image (findBestQuantization's
+ *                         inlineScielabOriginal argument, :383) as the target candidates are compared with, instead of the
+ *                         one hq_eval_palettes_scielab would compute itself (whole image; also on multi-device contexts)
+ *   hq_delta_e_images     computeError (:858-894): CIEDE/CIE76 between two Lab images, the error image value
+ *                         ((255 - e)^2) / (255 * 255) in lanes 0..2 of error_rgba4 (may be NULL), *mean_de = sum in double / n */
+int hq_rgb_to_xyz(hq_ctx* ctx, const float* r, const float* g, const float* b, size_t n, float* xyz4);
+int hq_xyz_to_scielab(hq_ctx* ctx, const float* xyz4, int width, int rows, const float* illuminant3, float* lab4);
+int hq_scielab_set_image(hq_ctx* ctx, const float* lab4);
+int hq_delta_e_images(hq_ctx* ctx, const float* lab4_a, const float* lab4_b, size_t n, float* error_rgba4, double* mean_de);
 /* test hook: 1 = always run the generic any-tap-count kernels instead of the 21-tap specialisations; 2 = the 21-tap
  * candidate stage as two kernels per candidate with an intermediate in HBM (round 1) instead of the fused kernel; 0 = default */
 int hq_scielab_force_generic(hq_ctx* ctx, int enabled);
