@@ -22,6 +22,8 @@ PRUNE_OFF, PRUNE_AUTO, PRUNE_ON = 0, 1, 2
 MAX_COLORS = 1024
 MAX_COLORS_PRUNED = 4096
 COMM_ID_BYTES = 128
+DELTAE_CIE76, DELTAE_CIE94, DELTAE_CIEDE2000 = 0, 1, 2
+ERR_FX_NAN = -(1 << 63)
 
 
 class HqError(RuntimeError):
@@ -55,6 +57,7 @@ SIGNATURES = {
     "hq_destroy": (None, [_P]),
     "hq_last_error": (C.c_char_p, [_P]),
     "hq_device_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_int]),
+    "hq_set_delta_e": (C.c_int, [_P, C.c_int]),
     "hq_set_image_u8": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int]),
     "hq_set_image_u8_sharded": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "hq_set_image_f32_planar": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int]),

@@ -465,6 +465,14 @@ int eval_enqueue(hq_ctx* m, const float* h_pal, const EvalPlan& e, const hq::Exp
     HQ_CUDA(m, cudaMemcpyAsync(m->d_pal.p, h_pal, e.npal * sizeof(float), cudaMemcpyHostToDevice, m->stream));
     return eval_device(m, m->d_pal.p, e.B, e.K, e.space, e.flags, m->d_results.p, nullptr, m->stream);
 }
+void unpack_results(const unsigned long long* h, int B, int K, int words, int64_t* err_fx, uint64_t* counts, int64_t* sums_fx) {
+    for (int b = 0; b < B; ++b) {
+        const unsigned long long* w = h + (size_t)b * words;
+        if (err_fx) err_fx[b] = (int64_t)w[0];
+        if (counts) std::memcpy(counts + (size_t)b * K, w + 1, sizeof(uint64_t) * K);
+        if (sums_fx) std::memcpy(sums_fx + (size_t)b * K * 3, w + 1 + K, sizeof(int64_t) * 3 * K);
+    }
+}
 // the exchange step: sum of the result words over every shard, left in place on every device
 int eval_reduce(hq_ctx* c, size_t nwords) {
     if (c->is_multi()) {
@@ -495,6 +503,36 @@ int hq_eval_palettes(hq_ctx* c, const float* palettes, int B, int K, int space, 
     const bool multi = c->is_multi(), reduce = reduces(c);
     std::vector<hq_ctx*> self(1, c);
     const std::vector<hq_ctx*>& targets = multi ? c->members : self;
+    if (c->delta_e != HQ_DELTAE_CIE76) {
+        // scope row f4: the assignment kernels score with the squared distance they minimise; another dE is scored from the index
+        // images in a second pass, with B words of NaN-pixel counts behind the result words (the CIE94 branch's latent NaN)
+        const bool idx16 = K > 256;
+        for (size_t i = targets.size(); i-- > 0;) {
+            hq_ctx* m = targets[i];
+            m->delta_e = c->delta_e;
+            rc = member_rc(c, m, bind_device(m)); if (rc) return rc;
+            HQ_CUDA(m, m->d_pal.reserve(npal));
+            HQ_CUDA(m, m->d_results.reserve(nwords + B));
+            HQ_CUDA(m, m->d_sc_err.reserve(B));
+            HQ_CUDA(m, m->d_idx.reserve((size_t)B * (m->stride ? m->stride : 1) * (idx16 ? 2 : 1)));
+            HQ_CUDA(m, cudaMemcpyAsync(m->d_pal.p, c->h_pal.p, npal * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+            rc = member_rc(c, m, eval_device(m, m->d_pal.p, B, K, space, flags & ~HQ_EVAL_PRUNE, m->d_results.p, m->d_idx.p, m->stream)); if (rc) return rc;
+            HQ_CUDA(m, cudaMemsetAsync(m->d_results.p + nwords, 0, (size_t)B * 8, m->stream));
+            HQ_CUDA(m, cudaMemsetAsync(m->d_sc_err.p, 0, (size_t)B * 8, m->stream));
+            HQ_CUDA(m, hq::launch_sc_score_indices(m->d_idx.p, idx16, m->d_lab.p, m->stride, m->own_lo, m->own_hi, m->d_pal_lab.p, hq::padded_colors(K), B,
+                                                   m->delta_e, m->d_sc_err.p, m->d_results.p + nwords, m->sm_count, m->stream));
+            HQ_CUDA(m, cudaMemcpy2DAsync(m->d_results.p, (size_t)words * 8, m->d_sc_err.p, 8, 8, (size_t)B, cudaMemcpyDeviceToDevice, m->stream));
+        }
+        if (reduce) { rc = eval_reduce(c, nwords + B); if (rc) return rc; }
+        rc = bind_device(c); if (rc) return rc;
+        HQ_CUDA(c, c->h_results.reserve(nwords + B));
+        HQ_CUDA(c, cudaMemcpyAsync(c->h_results.p, c->d_results.p, (nwords + B) * 8, cudaMemcpyDeviceToHost, c->stream));
+        HQ_CUDA(c, wait_stream(c->stream));
+        for (int b = 0; b < B; ++b)
+            if (c->h_results.p[nwords + b]) c->h_results.p[(size_t)b * words] = (unsigned long long)HQ_ERR_FX_NAN;
+        unpack_results(c->h_results.p, B, K, words, err_fx, counts, sums_fx);
+        return HQ_OK;
+    }
     for (hq_ctx* m : targets) { rc = member_rc(c, m, eval_prepare(m, e)); if (rc) return rc; }
     rc = bind_device(c); if (rc) return rc;
     hq_ctx::EvalKey key;
@@ -557,18 +595,14 @@ int hq_eval_palettes(hq_ctx* c, const float* palettes, int B, int K, int space, 
     }
     HQ_CUDA(c, wait_stream(c->stream));
 unpack:
-    for (int b = 0; b < B; ++b) {
-        const unsigned long long* w = c->h_results.p + (size_t)b * words;
-        if (err_fx) err_fx[b] = (int64_t)w[0];
-        if (counts) std::memcpy(counts + (size_t)b * K, w + 1, sizeof(uint64_t) * K);
-        if (sums_fx) std::memcpy(sums_fx + (size_t)b * K * 3, w + 1 + K, sizeof(int64_t) * 3 * K);
-    }
+    unpack_results(c->h_results.p, B, K, words, err_fx, counts, sums_fx);
     return HQ_OK;
 } catch (const std::exception& ex) { return api_exception(c, ex); }
 double hq_cost(int64_t err_fx, const uint64_t* counts, int K, uint64_t n_total, float delta) {
     double penalty = 0;
     for (int k = 0; k < K; ++k)
         if (counts[k] == 0) penalty += delta;
+    if (err_fx == HQ_ERR_FX_NAN) return std::nan("");   // a NaN pixel of the CIE94 branch: the reference's mean, hence its cost, is NaN
     const double sum = (double)err_fx * (1.0 / 16777216.0);
     return sum / (double)n_total + penalty;
 }
@@ -750,8 +784,8 @@ int hq_rgb_to_xyz(hq_ctx* c, const float* r, const float* g, const float* b, siz
     if (!c || !xyz4 || ((!r || !g || !b) && n)) return c ? fail(c, HQ_ERR_INVALID, "NULL array") : HQ_ERR_INVALID;
     int rc = bind_device(c); if (rc) return rc;
     DevBuf<float> in, out;
-    HQ_CUDA(c, in.reserve(3 * n ? 3 * n : 1));
-    HQ_CUDA(c, out.reserve(4 * n ? 4 * n : 1));
+    HQ_CUDA(c, in.reserve(n ? 3 * n : 1));
+    HQ_CUDA(c, out.reserve(n ? 4 * n : 1));
     HQ_CUDA(c, c->d_flag.reserve(1));
     cudaError_t e = cudaMemsetAsync(c->d_flag.p, 0, sizeof(unsigned int), c->stream);
     const float* src[3] = {r, g, b};
@@ -832,14 +866,14 @@ int hq_delta_e_images(hq_ctx* c, const float* lab4_a, const float* lab4_b, size_
     int rc = bind_device(c); if (rc) return rc;
     DevBuf<float> a, b, e, img;
     std::vector<float> he(n);
-    cudaError_t ce = a.reserve(4 * n ? 4 * n : 1);
-    if (ce == cudaSuccess) ce = b.reserve(4 * n ? 4 * n : 1);
+    cudaError_t ce = a.reserve(n ? 4 * n : 1);
+    if (ce == cudaSuccess) ce = b.reserve(n ? 4 * n : 1);
     if (ce == cudaSuccess) ce = e.reserve(n ? n : 1);
-    if (ce == cudaSuccess && error_rgba4) ce = img.reserve(4 * n ? 4 * n : 1);
+    if (ce == cudaSuccess && error_rgba4) ce = img.reserve(n ? 4 * n : 1);
     if (ce == cudaSuccess && n) ce = cudaMemcpyAsync(a.p, lab4_a, 4 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream);
     if (ce == cudaSuccess && n) ce = cudaMemcpyAsync(b.p, lab4_b, 4 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream);
     if (ce == cudaSuccess && n && error_rgba4) ce = cudaMemcpyAsync(img.p, error_rgba4, 4 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream);
-    if (ce == cudaSuccess) ce = hq::launch_sc_delta_e4(a.p, b.p, n, e.p, error_rgba4 ? img.p : nullptr, c->stream);
+    if (ce == cudaSuccess) ce = hq::launch_sc_delta_e4(a.p, b.p, n, e.p, error_rgba4 ? img.p : nullptr, c->delta_e, c->stream);
     if (ce == cudaSuccess && n) ce = cudaMemcpyAsync(he.data(), e.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
     if (ce == cudaSuccess && n && error_rgba4) ce = cudaMemcpyAsync(error_rgba4, img.p, 4 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
@@ -854,14 +888,15 @@ int hq_delta_e_images(hq_ctx* c, const float* lab4_a, const float* lab4_b, size_
 // error-image mode: HybridQuantization.errorImage (:139-182) + ImageManipulation.computeError (:858-894)
 namespace {
 // the second image of error-image mode, as packed u8 (rgb8) or as float planes (f32[3])
-// raw_sum (optional): a member of a multi-device context — no exchange, no mean; the fixed-point sum of its own rows goes there
+// raw_sum (optional): a member of a multi-device context — no exchange, no mean; the fixed-point sum of its own rows and the
+// number of NaN pixels (CIE94 only) go to raw_sum[0], raw_sum[1]
 int error_image_common(hq_ctx* c, const uint8_t* rgb8, const float* const* f32, float* error_map, uint8_t* error_map_u8, double* mean_de,
                        unsigned long long* raw_sum = nullptr) {
     int rc = bind_device(c); if (rc) return rc;
     rc = sc_ensure_image(c); if (rc) return rc;
     const size_t n = c->n;
     HQ_CUDA(c, c->d_sc_lab2.reserve(3 * c->stride));
-    HQ_CUDA(c, c->d_sc_err.reserve(1));
+    HQ_CUDA(c, c->d_sc_err.reserve(2));
     if (error_map) HQ_CUDA(c, c->d_sc_map.reserve(n ? n : 1));
     if (error_map_u8) HQ_CUDA(c, c->d_sc_map8.reserve(n ? n : 1));
     // S-CIELAB of the second image through the same route as the original (sRGBToScielab, ScielabProcessor.java:374-381)
@@ -882,21 +917,23 @@ int error_image_common(hq_ctx* c, const uint8_t* rgb8, const float* const* f32, 
     }
     HQ_CUDA(c, hq::launch_sc_original(c->d_sc_opp.p, c->width, c->rows, c->stride, c->d_sc_filters.p, c->sc_generic ? nullptr : c->sc_block.data(),
                                       c->sc_taps, c->whitepoint, sc_rows(c), c->d_sc_tmp.p, c->d_sc_lab2.p, c->stream));
-    HQ_CUDA(c, cudaMemsetAsync(c->d_sc_err.p, 0, 8, c->stream));
+    HQ_CUDA(c, cudaMemsetAsync(c->d_sc_err.p, 0, 16, c->stream));
     const size_t lo = c->own_lo, no = c->own_hi - c->own_lo;  // maps and the sum cover the own rows
     HQ_CUDA(c, hq::launch_sc_error_image(c->d_sc_lab.p + lo, c->d_sc_lab2.p + lo, no, c->stride, error_map ? c->d_sc_map.p : nullptr,
-                                         error_map_u8 ? c->d_sc_map8.p : nullptr, c->d_sc_err.p, c->stream));
+                                         error_map_u8 ? c->d_sc_map8.p : nullptr, c->d_sc_err.p, c->delta_e, c->stream));
     const bool reduce = !raw_sum && reduces(c);
-    if (reduce) { rc = reduce_words(c, c->d_sc_err.p, 1, c->stream); if (rc) return rc; }
-    unsigned long long sum = 0;
-    HQ_CUDA(c, cudaMemcpyAsync(&sum, c->d_sc_err.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    if (reduce) { rc = reduce_words(c, c->d_sc_err.p, 2, c->stream); if (rc) return rc; }
+    unsigned long long sums[2] = {0, 0};
+    HQ_CUDA(c, cudaMemcpyAsync(sums, c->d_sc_err.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    const unsigned long long& sum = sums[0];
     if (error_map && no) HQ_CUDA(c, cudaMemcpyAsync(error_map, c->d_sc_map.p, no * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     if (error_map_u8 && no) HQ_CUDA(c, cudaMemcpyAsync(error_map_u8, c->d_sc_map8.p, no, cudaMemcpyDeviceToHost, c->stream));
     HQ_CUDA(c, cudaStreamSynchronize(c->stream));
     const double n_all = (double)c->width * (double)c->g_rows;  // with the hook the sum is over the whole image
     const double n_div = reduce ? n_all : (double)no;
-    if (raw_sum) *raw_sum = sum;
-    if (mean_de) *mean_de = n_div > 0 ? ((double)(int64_t)sum * (1.0 / 16777216.0)) / n_div : 0.0;  // :893 error/errorArray.length
+    if (raw_sum) { raw_sum[0] = sums[0]; raw_sum[1] = sums[1]; }
+    if (mean_de && sums[1]) *mean_de = std::nan("");   // a NaN pixel of the CIE94 branch makes the reference's mean NaN (:886-893)
+    else if (mean_de) *mean_de = n_div > 0 ? ((double)(int64_t)sum * (1.0 / 16777216.0)) / n_div : 0.0;  // :893 error/errorArray.length
     return HQ_OK;
 }
 }  // namespace
@@ -905,17 +942,18 @@ int hq_error_image(hq_ctx* c, const uint8_t* quantized_rgb, float* error_map, ui
     if (!c || !quantized_rgb) return c ? fail(c, HQ_ERR_INVALID, "quantized_rgb is NULL") : HQ_ERR_INVALID;
     if (!c->is_multi()) return error_image_common(c, quantized_rgb, nullptr, error_map, error_map_u8, mean_de);
     long long total = 0;
+    unsigned long long nans = 0;
     for (hq_ctx* m : c->members) {   // each member: its rows (+ halo) of the second image in, its rows of the maps out
         if (m->own_rows == 0) continue;
         const size_t in_at = (size_t)(m->g_row0 - m->halo_top) * m->width, out_at = (size_t)m->g_row0 * m->width;
-        unsigned long long part = 0;
+        unsigned long long part[2] = {0, 0};
         const int rc = member_rc(c, m, error_image_common(m, quantized_rgb + in_at * 3, nullptr, error_map ? error_map + out_at : nullptr,
-                                                          error_map_u8 ? error_map_u8 + out_at : nullptr, nullptr, &part));
+                                                          error_map_u8 ? error_map_u8 + out_at : nullptr, nullptr, part));
         if (rc) return rc;
-        total += (long long)part;
+        total += (long long)part[0]; nans += part[1];
     }
     const double n_all = (double)c->m_width * (double)c->m_rows;
-    if (mean_de) *mean_de = n_all > 0 ? ((double)total * (1.0 / 16777216.0)) / n_all : 0.0;
+    if (mean_de) *mean_de = nans ? std::nan("") : (n_all > 0 ? ((double)total * (1.0 / 16777216.0)) / n_all : 0.0);
     return bind_device(c);
 } catch (const std::exception& ex) { return api_exception(c, ex); }
 
@@ -924,18 +962,19 @@ int hq_error_image_f32_planar(hq_ctx* c, const float* r, const float* g, const f
     const float* planes[3] = {r, g, b};
     if (!c->is_multi()) return error_image_common(c, nullptr, planes, error_map, error_map_u8, mean_de);
     long long total = 0;
+    unsigned long long nans = 0;
     for (hq_ctx* m : c->members) {
         if (m->own_rows == 0) continue;
         const size_t in_at = (size_t)(m->g_row0 - m->halo_top) * m->width, out_at = (size_t)m->g_row0 * m->width;
         const float* mp[3] = {r + in_at, g + in_at, b + in_at};
-        unsigned long long part = 0;
+        unsigned long long part[2] = {0, 0};
         const int rc = member_rc(c, m, error_image_common(m, nullptr, mp, error_map ? error_map + out_at : nullptr,
-                                                          error_map_u8 ? error_map_u8 + out_at : nullptr, nullptr, &part));
+                                                          error_map_u8 ? error_map_u8 + out_at : nullptr, nullptr, part));
         if (rc) return rc;
-        total += (long long)part;
+        total += (long long)part[0]; nans += part[1];
     }
     const double n_all = (double)c->m_width * (double)c->m_rows;
-    if (mean_de) *mean_de = n_all > 0 ? ((double)total * (1.0 / 16777216.0)) / n_all : 0.0;
+    if (mean_de) *mean_de = nans ? std::nan("") : (n_all > 0 ? ((double)total * (1.0 / 16777216.0)) / n_all : 0.0);
     return bind_device(c);
 } catch (const std::exception& ex) { return api_exception(c, ex); }
 
@@ -948,7 +987,9 @@ int sc_eval_enqueue(hq_ctx* m, const float* h_pal, int B, int K, int space) {
     const int words = hq::result_words(K, false);
     const size_t nwords = (size_t)B * words;
     const bool idx16 = K > 256;
-    HQ_CUDA(m, m->d_results.reserve(nwords));
+    const bool de94 = m->delta_e != HQ_DELTAE_CIE76;   // then B more words follow the result words: NaN pixels per candidate
+    HQ_CUDA(m, m->d_results.reserve(nwords + B));
+    if (de94) HQ_CUDA(m, cudaMemsetAsync(m->d_results.p + nwords, 0, (size_t)B * 8, m->stream));
     if (m->own_rows == 0) {   // an empty row block of a multi-device context contributes zeros
         HQ_CUDA(m, cudaMemsetAsync(m->d_results.p, 0, nwords * 8, m->stream));
         return HQ_OK;
@@ -967,7 +1008,7 @@ int sc_eval_enqueue(hq_ctx* m, const float* h_pal, int B, int K, int space) {
     HQ_CUDA(m, hq::launch_sc_palette_opp(m->d_pal.p, B * K, m->d_sc_tab.p, m->stream));
     HQ_CUDA(m, cudaMemsetAsync(m->d_sc_err.p, 0, (size_t)B * 8, m->stream));
     // 3. per candidate: separable filters, Opp2LAB, CIE76 against the original, fixed-point sum
-    cudaError_t fe = (m->sc_generic || m->sc_unfused) ? cudaErrorNotSupported
+    cudaError_t fe = (m->sc_generic || m->sc_unfused || de94) ? cudaErrorNotSupported   // (the fused kernel is CIE76 only)
                      : hq::launch_sc_candidates_fused(m->d_idx.p, idx16, m->d_sc_tab.p, K, B, m->width, m->rows, m->stride, m->sc_block.data(), m->sc_taps,
                                                       m->whitepoint, sc_rows(m), m->d_sc_lab.p, m->d_sc_err.p, m->sm_count, m->stream);
     if (fe != cudaSuccess && fe != cudaErrorNotSupported) return fail(m, HQ_ERR_CUDA, "fused S-CIELAB kernel launch failed: %s", cudaGetErrorString(fe));
@@ -976,7 +1017,7 @@ int sc_eval_enqueue(hq_ctx* m, const float* h_pal, int B, int K, int space) {
         const uint8_t* idx_b = m->d_idx.p + (size_t)b * m->stride * (idx16 ? 2 : 1);
         HQ_CUDA(m, hq::launch_sc_candidate(idx_b, idx16, m->d_sc_tab.p + (size_t)b * K, m->width, m->rows, m->stride, m->d_sc_filters.p,
                                            m->sc_generic ? nullptr : m->sc_block.data(), m->sc_taps, m->whitepoint, sc_rows(m), m->d_sc_tmp.p,
-                                           m->d_sc_lab.p, m->d_sc_err.p + b, m->stream));
+                                           m->d_sc_lab.p, m->d_sc_err.p + b, m->stream, m->delta_e, m->d_results.p + nwords + b));
     }
     // word 0 of every candidate <- the S-CIELAB error sum, so that one all-reduce covers error and counts
     HQ_CUDA(m, cudaMemcpy2DAsync(m->d_results.p, (size_t)words * 8, m->d_sc_err.p, 8, 8, (size_t)B, cudaMemcpyDeviceToDevice, m->stream));
@@ -996,13 +1037,15 @@ int hq_eval_palettes_scielab(hq_ctx* c, const float* palettes, int B, int K, int
     if (!copy_palettes_checked(c->h_pal.p, palettes, npal)) return fail(c, HQ_ERR_INVALID, "%s", kBadPalette);
     std::vector<hq_ctx*> self(1, c);
     const std::vector<hq_ctx*>& targets = c->is_multi() ? c->members : self;
+    const size_t tail = c->delta_e != HQ_DELTAE_CIE76 ? (size_t)B : 0;   // NaN pixel counts of the CIE94 branch, reduced with the rest
+    for (hq_ctx* m : targets) m->delta_e = c->delta_e;
     for (size_t i = targets.size(); i-- > 0;) { rc = member_rc(c, targets[i], sc_eval_enqueue(targets[i], c->h_pal.p, B, K, space)); if (rc) return rc; }
-    if (reduces(c)) { rc = eval_reduce(c, nwords); if (rc) return rc; }
+    if (reduces(c)) { rc = eval_reduce(c, nwords + tail); if (rc) return rc; }
     rc = bind_device(c); if (rc) return rc;
-    HQ_CUDA(c, cudaMemcpyAsync(c->h_results.p, c->d_results.p, nwords * 8, cudaMemcpyDeviceToHost, c->stream));
+    HQ_CUDA(c, cudaMemcpyAsync(c->h_results.p, c->d_results.p, (nwords + tail) * 8, cudaMemcpyDeviceToHost, c->stream));
     HQ_CUDA(c, wait_stream(c->stream));
     for (int b = 0; b < B; ++b) {
-        if (err_fx) err_fx[b] = (int64_t)c->h_results.p[(size_t)b * words];
+        if (err_fx) err_fx[b] = (tail && c->h_results.p[nwords + b]) ? HQ_ERR_FX_NAN : (int64_t)c->h_results.p[(size_t)b * words];
         if (counts) std::memcpy(counts + (size_t)b * K, c->h_results.p + (size_t)b * words + 1, sizeof(uint64_t) * K);
     }
     return HQ_OK;
@@ -1065,6 +1108,16 @@ int hq_set_graphs(hq_ctx* c, int enabled) {
     if (!c) return HQ_ERR_INVALID;
     c->use_graphs = enabled != 0;
     if (!c->use_graphs && c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; c->graph_key = hq_ctx::EvalKey(); }
+    return HQ_OK;
+}
+
+int hq_set_delta_e(hq_ctx* c, int type) {
+    if (!c) return HQ_ERR_INVALID;
+    if (type == HQ_DELTAE_CIEDE2000)
+        return fail(c, HQ_ERR_UNSUPPORTED, "CIEDE2000 has no definition to be faithful to: the reference's branch is an empty stub (OptimizedConvolution.cl:227-229)");
+    if (type != HQ_DELTAE_CIE76 && type != HQ_DELTAE_CIE94) return fail(c, HQ_ERR_INVALID, "unknown dE type %d", type);
+    c->delta_e = type;
+    for (hq_ctx* m : c->members) m->delta_e = type;
     return HQ_OK;
 }
 

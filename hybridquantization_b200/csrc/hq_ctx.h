@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cmath>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
@@ -108,6 +109,8 @@ struct hq_ctx {
     DevBuf<unsigned> d_pr_scratch;
     DevBuf<unsigned long long> d_pr_stats;
     PinBuf<unsigned long long> h_pr_small;
+
+    int delta_e = HQ_DELTAE_CIE76;            // ImageManipulation.deltaETypes (:20): what a pixel pair is scored with (hq_set_delta_e)
 
     // S-CIELAB stage (next row 1)
     std::vector<float> sc_filters7, sc_abs3;  // [7][taps], [taps] as ScielabProcessor builds them

@@ -17,6 +17,7 @@
 // hence independent of block order, grid size and GPU count.
 //
 // Tensor cores are deliberately not used: the inner dimension of the distance is 3.
+#include <cstdlib>
 #include <mutex>
 
 #include "hq_kernels.cuh"
@@ -288,6 +289,35 @@ __global__ void palette_features_kernel(const float* __restrict__ pal, int B, in
     pal_rgb[i] = rgbv;
 }
 
+// ---- TMA bulk copies (cp.async.bulk, global -> shared, completion counted in bytes on an mbarrier) and the mbarrier
+// primitives of the pixel pipeline of the small-palette kernel
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "HQ_MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra HQ_MBAR_DONE_%=;\n"
+        "bra HQ_MBAR_WAIT_%=;\n"
+        "HQ_MBAR_DONE_%=:\n"
+        "}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
+                 "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+
 // ====================================================================== assign + reduce
 struct AssignParams {
     const float* feat;   // [3][stride] planes the argmin runs on (Lab, or unit sRGB)
@@ -301,7 +331,9 @@ struct AssignParams {
     unsigned long long* results;
     void* idx_out;
     ExportTail tail;
+    int use_tma;   // variant 1: pixel tiles staged by TMA bulk copies through a 3-stage shared-memory ring
 };
+constexpr int kPxStages = 3;   // tiles in flight per CTA (variant 1 with TMA): 3 x 12 KB
 
 constexpr int kWorklistCap = 1024;  // ambiguous pixels deferred per CTA (variant 3)
 #ifndef HQ_PREFILTER_SCALAR
@@ -311,7 +343,7 @@ constexpr int kWorklistCap = 1024;  // ambiguous pixels deferred per CTA (varian
 // shared-memory carve-up, identical on host (size) and device (pointers)
 template <int VARIANT, bool SRGB, bool SUMS>
 struct AssignSmem {
-    size_t off_pairs01, off_lab, off_sum, off_pairs2, off_coef, off_skew, off_cnt, off_wl, total;
+    size_t off_pairs01, off_lab, off_sum, off_pairs2, off_coef, off_skew, off_cnt, off_wl, off_px, total;
     int skew_len;
     __host__ __device__ explicit AssignSmem(int K8) {
         skew_len = (K8 / kChunk) * (kChunk + 1);
@@ -324,6 +356,8 @@ struct AssignSmem {
         off_skew = o;    if (VARIANT != 1) o += (size_t)3 * skew_len * 4;  // skewed SoA copy of the features
         off_cnt = o;     o += (size_t)K8 * 4;                              // per-colour counts
         off_wl = o;      if (VARIANT == 3) o += (size_t)kWorklistCap * 4;
+        o = (o + 127) / 128 * 128;
+        off_px = o;      if (VARIANT == 1) o += (size_t)kPxStages * 3 * kTilePx * 4;   // TMA ring of pixel tiles: [stage][plane][1024]
         total = o;
     }
 };
@@ -465,11 +499,60 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VAR
         for (int c = 0; c < nchunks; ++c) exact_chunk(s_sk, skew_len, c, x0, x1, x2, bd, bi);
     };
 
-    for (size_t tile = blockIdx.y; tile < ntiles; tile += gridDim.y) {
+    // ---- variant 1: the feature planes of this CTA's tiles arrive through a ring of kPxStages tiles in shared memory, filled by
+    // TMA bulk copies (3 x 4 KB per tile, one elected thread, completion counted on an mbarrier) kPxStages - 1 tiles ahead of
+    // the arithmetic: no registers held for data in flight, no load instructions in the warps' instruction stream
+    float* s_px = reinterpret_cast<float*>(smem_raw + L.off_px);
+    __shared__ __align__(8) unsigned long long s_full[kPxStages], s_empty[kPxStages];
+    const bool tma = VARIANT == 1 && p.use_tma != 0;
+    const size_t my_tiles = blockIdx.y < ntiles ? (ntiles - blockIdx.y + gridDim.y - 1) / gridDim.y : 0;
+    auto tma_issue = [&](size_t i) {   // tile i of this CTA -> stage i % kPxStages (thread 0 only)
+        const size_t tb = (blockIdx.y + i * gridDim.y) * kTilePx;
+        const unsigned cnt = (unsigned)(n - tb < (size_t)kTilePx ? n - tb : (size_t)kTilePx);
+        const unsigned bytes = (cnt * 4u + 15u) & ~15u;   // the planes are padded to 32 pixels: the rounded copy stays inside
+        const int st = (int)(i % kPxStages);
+        mbar_expect_tx(&s_full[st], 3u * bytes);
+        bulk_g2s(s_px + (size_t)(st * 3 + 0) * kTilePx, f0 + tb, bytes, &s_full[st]);
+        bulk_g2s(s_px + (size_t)(st * 3 + 1) * kTilePx, f1 + tb, bytes, &s_full[st]);
+        bulk_g2s(s_px + (size_t)(st * 3 + 2) * kTilePx, f2 + tb, bytes, &s_full[st]);
+    };
+    if (tma) {
+        if (tid == 0) {
+            for (int st = 0; st < kPxStages; ++st) { mbar_init(&s_full[st], 1u); mbar_init(&s_empty[st], (unsigned)kThreads); }
+            mbar_fence_init();
+        }
+        __syncthreads();
+        if (tid == 0)
+            for (size_t i = 0; i < my_tiles && i < (size_t)kPxStages - 1; ++i) tma_issue(i);
+    }
+
+    size_t it = 0;
+    for (size_t tile = blockIdx.y; tile < ntiles; tile += gridDim.y, ++it) {
         const size_t base = tile * kTilePx + (size_t)kPxPerThread * tid;
         float x0[4], x1[4], x2[4];
         int nvalid;
-        if (base + 4 <= n) {
+        if (tma) {
+            // refill first: tile it + kPxStages - 1 goes into the stage tile it - 1 used, once every thread has read that one
+            if (tid == 0 && it + kPxStages - 1 < my_tiles) {
+                if (it >= 1) mbar_wait(&s_empty[(it - 1) % kPxStages], (unsigned)(((it - 1) / kPxStages) & 1));
+                tma_issue(it + kPxStages - 1);
+            }
+            const int st = (int)(it % kPxStages);
+            mbar_wait(&s_full[st], (unsigned)((it / kPxStages) & 1));
+            const float* sp = s_px + (size_t)st * 3 * kTilePx + kPxPerThread * tid;
+            const float4 a = *reinterpret_cast<const float4*>(sp);
+            const float4 c = *reinterpret_cast<const float4*>(sp + kTilePx);
+            const float4 d = *reinterpret_cast<const float4*>(sp + 2 * kTilePx);
+            mbar_arrive(&s_empty[st]);
+            x0[0] = a.x; x0[1] = a.y; x0[2] = a.z; x0[3] = a.w;
+            x1[0] = c.x; x1[1] = c.y; x1[2] = c.z; x1[3] = c.w;
+            x2[0] = d.x; x2[1] = d.y; x2[2] = d.z; x2[3] = d.w;
+            nvalid = base + 4 <= n ? 4 : (base < n ? (int)(n - base) : 0);
+            if (nvalid < 4) {   // the tail of the last tile: what lies beyond the image is not pixels
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (j >= nvalid) { x0[j] = 0.f; x1[j] = 0.f; x2[j] = 0.f; }
+            }
+        } else if (base + 4 <= n) {
             const float4 a = __ldg(reinterpret_cast<const float4*>(f0 + base));
             const float4 c = __ldg(reinterpret_cast<const float4*>(f1 + base));
             const float4 d = __ldg(reinterpret_cast<const float4*>(f2 + base));
@@ -875,6 +958,10 @@ cudaError_t launch_assign_reduce(const AssignArgs& a, cudaStream_t stream) {
     p.results = a.results;
     p.idx_out = a.idx_out;
     p.tail = a.tail;
+    {   // HQ_V1_TMA=0: the small-palette kernel loads its pixels with LDG.128 as in round 1 (A/B measurements)
+        static const int tma_env = [] { const char* e = std::getenv("HQ_V1_TMA"); return (e && e[0] == '0') ? 0 : 1; }();
+        p.use_tma = tma_env;
+    }
     // (an EMPTY own range — a shard that only carries halo rows — is honoured as empty: indices for every pixel, no reduction)
     p.own_lo = a.own_lo; p.own_hi = a.own_hi == kAllPixels ? a.n : a.own_hi;
     const int idxw = a.idx_out ? (a.K <= 256 ? 1 : 2) : 0;

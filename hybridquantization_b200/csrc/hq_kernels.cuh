@@ -154,11 +154,12 @@ cudaError_t launch_sc_unit_to_xyz4(const float* d_r, const float* d_g, const flo
 cudaError_t launch_sc_xyz4_to_opp(const float* d_xyz4, size_t n, size_t stride, float* d_opp, cudaStream_t st);
 cudaError_t launch_sc_planes_to_f4(const float* d_planes, size_t n, size_t stride, float* d_out4, cudaStream_t st);
 cudaError_t launch_sc_f4_to_planes(const float* d_in4, size_t n, size_t stride, float* d_planes, cudaStream_t st);
-cudaError_t launch_sc_delta_e4(const float* d_a4, const float* d_b4, size_t n, float* d_e, float* d_err_img4, cudaStream_t st);
+cudaError_t launch_sc_delta_e4(const float* d_a4, const float* d_b4, size_t n, float* d_e, float* d_err_img4, int de_type, cudaStream_t st);
 // one candidate: index image + opponent table -> fixed-point sum of dE against d_lab_orig, added to *d_err
 cudaError_t launch_sc_candidate(const void* d_idx, bool idx16, const float4* d_tab, int w, int h, size_t stride, const float* d_filters,
                                 const float* h_filters, int taps, int whitepoint, ScRows rows, float* d_tmp, const float* d_lab_orig,
-                                unsigned long long* d_err, cudaStream_t st);
+                                unsigned long long* d_err, cudaStream_t st, int de_type = 0, unsigned long long* d_nan = nullptr);
+// de_type: 0 CIE76 (cl:209), 1 the CIE94 branch (cl:217-226); d_nan counts the pixels whose CIE94 value is NaN
 
 // the whole population in one launch, no intermediate in HBM (taps == 21 and K <= kMaxColors; otherwise cudaErrorNotSupported:
 // call launch_sc_candidate per candidate).  d_idx [B][stride], d_tab [B][K], d_err [B]
@@ -167,8 +168,13 @@ cudaError_t launch_sc_candidates_fused(const void* d_idx, bool idx16, const floa
                                        unsigned long long* d_err, int sm_count, cudaStream_t st);
 
 // error-image mode: dE map between two S-CIELAB images + fixed-point sum
+// d_err: [2] words: fixed-point sum, NaN count (CIE94 only)
 cudaError_t launch_sc_error_image(const float* d_lab_a, const float* d_lab_b, size_t n, size_t stride, float* d_map, uint8_t* d_map_u8,
-                                  unsigned long long* d_err, cudaStream_t st);
+                                  unsigned long long* d_err, int de_type, cudaStream_t st);
+// identity-filter cost from index images under a dE type: d_err[B] += sum of dE(Lab(pixel), Lab(P[idx])) over [own_lo, own_hi), d_nan[B]
+cudaError_t launch_sc_score_indices(const void* d_idx, bool idx16, const float* d_lab, size_t stride, size_t own_lo, size_t own_hi,
+                                    const float4* d_pal_lab, int K8, int B, int de_type, unsigned long long* d_err, unsigned long long* d_nan,
+                                    int sm_count, cudaStream_t st);
 
 // FFMA-saturating probe: `iters` x 32 dependent-chain FMAs per thread (8 chains), scalar or packed
 cudaError_t launch_fp32_peak(bool packed, int iters, int sm_count, float* d_out, cudaStream_t stream);

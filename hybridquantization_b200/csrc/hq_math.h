@@ -433,6 +433,22 @@ HQ_HD hq_float3 hq_cl_opp_to_lab_white(float o0, float o1, float o2, hq_white w)
     lab.z = HQ_FMUL(200.0f, HQ_FSUB(fy, fz));
     return lab;
 }
+// CIEDE kernel, CIE94 branch (cl:217-226; scope row f4).  p1 = the original's Lab, p2 = the other image's.  OpenCL's device-
+// defined pieces pinned as the oracle pins them: fma exact, sqrt and the divisions correctly rounded, the weights
+// 1 + 0.045*C1 and 1 + 0.015*C1 evaluated in double (the literals are doubles in OpenCL C) and narrowed on assignment.
+// deltaH takes the square root of da^2 + db^2 - dC^2, which rounding makes slightly negative for collinear chroma vectors:
+// the result is then NaN, exactly as the reference kernel's (about one generic pixel pair in 4,000).
+HQ_HD float hq_cl_delta_e94(float L1, float a1, float b1, float L2, float a2, float b2) {
+    const float dL = HQ_FSUB(L1, L2);
+    const float c1 = HQ_FSQRT(HQ_FFMA(a1, a1, HQ_FMUL(b1, b1)));
+    const float dC = HQ_FSUB(c1, HQ_FSQRT(HQ_FFMA(a2, a2, HQ_FMUL(b2, b2))));
+    const float da = HQ_FSUB(a1, a2), db = HQ_FSUB(b1, b2);
+    const float dH = HQ_FSQRT(HQ_FSUB(HQ_FFMA(da, da, HQ_FMUL(db, db)), HQ_FMUL(dC, dC)));
+    const float sc = (float)HQ_DADD(1.0, HQ_DMUL(0.045, (double)c1));
+    const float sh = (float)HQ_DADD(1.0, HQ_DMUL(0.015, (double)c1));
+    const float qc = HQ_FDIV(dC, sc), qh = HQ_FDIV(dH, sh);
+    return HQ_FSQRT(HQ_FFMA(dL, dL, HQ_FFMA(qc, qc, HQ_FMUL(qh, qh))));
+}
 // reflect padding of the separable filters (cl:20-27)
 HQ_HD int hq_reflect(int off, int n) {
     if (off < 0) off = -off - 1;

@@ -24,6 +24,16 @@ struct ScFilters {
     int taps;
 };
 
+// dE of one pixel pair in 2^-24 fixed point: CIE76 (cl:209) or the CIE94 branch (cl:217-226, ImageManipulation.deltaETypes :20).
+// A NaN of the CIE94 branch cannot enter an integer sum: it is COUNTED (*nan_out) and the caller reports the whole sum as NaN.
+__device__ __forceinline__ long long sc_delta_e_fx(int de_type, float L1, float a1, float b1, float L2, float a2, float b2,
+                                                   unsigned long long* nan_out) {
+    if (de_type == 0) return hq_to_fx(HQ_FSQRT(hq_dist2(L1, a1, b1, L2, a2, b2)));
+    const float e = hq_cl_delta_e94(L1, a1, b1, L2, a2, b2);
+    if (e != e) { atomicAdd(nan_out, 1ull); return 0; }
+    return hq_to_fx(e);
+}
+
 __global__ void sc_rgb_to_opp_kernel(const uint8_t* __restrict__ rgb, size_t n, size_t stride,
                                      const float* __restrict__ table, float* __restrict__ opp) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -90,7 +100,8 @@ sc_hpass_kernel(const float* __restrict__ opp, const IdxT* __restrict__ idx, con
 template <int MODE>
 __global__ void __launch_bounds__(kScThreads)
 sc_vpass_kernel(const float* __restrict__ tmp, int w, int h, size_t stride, ScFilters f, hq_float3 ill, ScRows rows,
-                float* __restrict__ lab_out, const float* __restrict__ lab_orig, unsigned long long* __restrict__ err_out) {
+                float* __restrict__ lab_out, const float* __restrict__ lab_orig, unsigned long long* __restrict__ err_out,
+                int de_type, unsigned long long* __restrict__ nan_out) {
     extern __shared__ float s_f[];  // 8 * taps
     for (int i = threadIdx.x; i < 8 * f.taps; i += kScThreads) s_f[i] = f.data[i];
     __syncthreads();
@@ -123,8 +134,7 @@ sc_vpass_kernel(const float* __restrict__ tmp, int w, int h, size_t stride, ScFi
         if (MODE == 0) {
             lab_out[p] = lab.x; lab_out[stride + p] = lab.y; lab_out[2 * stride + p] = lab.z;
         } else {
-            const float d2 = hq_dist2(__ldg(lab_orig + p), __ldg(lab_orig + stride + p), __ldg(lab_orig + 2 * stride + p), lab.x, lab.y, lab.z);
-            fx = hq_to_fx(HQ_FSQRT(d2));  // CIE76, cl:209
+            fx = sc_delta_e_fx(de_type, __ldg(lab_orig + p), __ldg(lab_orig + stride + p), __ldg(lab_orig + 2 * stride + p), lab.x, lab.y, lab.z, nan_out);
         }
     }
     if (MODE == 1) {
@@ -209,7 +219,8 @@ constexpr int kVRows = 8;  // output rows per thread (vertical): 28 input rows s
 template <int MODE>
 __global__ void __launch_bounds__(kScThreads)
 sc_vpass21_kernel(const float* __restrict__ tmp, int w, int h, size_t stride, const __grid_constant__ Filt21 f, hq_float3 ill, ScRows rows,
-                  float* __restrict__ lab_out, const float* __restrict__ lab_orig, unsigned long long* __restrict__ err_out) {
+                  float* __restrict__ lab_out, const float* __restrict__ lab_orig, unsigned long long* __restrict__ err_out,
+                  int de_type, unsigned long long* __restrict__ nan_out) {
     const int x = blockIdx.x * kScThreads + threadIdx.x, y0 = rows.y_begin + blockIdx.y * kVRows;
     long long fx = 0;
     if (x < w) {
@@ -254,8 +265,7 @@ sc_vpass21_kernel(const float* __restrict__ tmp, int w, int h, size_t stride, co
                 if (MODE == 0) {
                     lab_out[p] = lab.x; lab_out[stride + p] = lab.y; lab_out[2 * stride + p] = lab.z;
                 } else {
-                    const float d2 = hq_dist2(__ldg(lab_orig + p), __ldg(lab_orig + stride + p), __ldg(lab_orig + 2 * stride + p), lab.x, lab.y, lab.z);
-                    fx += hq_to_fx(HQ_FSQRT(d2));
+                    fx += sc_delta_e_fx(de_type, __ldg(lab_orig + p), __ldg(lab_orig + stride + p), __ldg(lab_orig + 2 * stride + p), lab.x, lab.y, lab.z, nan_out);
                 }
             }
         }
@@ -469,19 +479,22 @@ sc_candidate_strip21_kernel(const IdxT* __restrict__ idx, const float4* __restri
 // error-image mode (ImageManipulation.computeError :858-894): dE between two S-CIELAB images, the
 // map value ((255 - dE)^2) / (255*255) (:890) and the fixed-point sum of dE
 __global__ void sc_error_image_kernel(const float* __restrict__ lab_a, const float* __restrict__ lab_b, size_t n, size_t stride,
-                                      float* __restrict__ map_out, uint8_t* __restrict__ map_u8, unsigned long long* __restrict__ err_out) {
+                                      float* __restrict__ map_out, uint8_t* __restrict__ map_u8, unsigned long long* __restrict__ err_out,
+                                      int de_type) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     long long fx = 0;
     if (i < n) {
-        const float e = HQ_FSQRT(hq_dist2(lab_a[i], lab_a[stride + i], lab_a[2 * stride + i], lab_b[i], lab_b[stride + i], lab_b[2 * stride + i]));
+        const float e = de_type == 0 ? HQ_FSQRT(hq_dist2(lab_a[i], lab_a[stride + i], lab_a[2 * stride + i], lab_b[i], lab_b[stride + i], lab_b[2 * stride + i]))
+                                     : hq_cl_delta_e94(lab_a[i], lab_a[stride + i], lab_a[2 * stride + i], lab_b[i], lab_b[stride + i], lab_b[2 * stride + i]);
         const float d = HQ_FSUB(255.0f, e);
         const float v = HQ_FDIV(HQ_FMUL(d, d), 65025.0f);
         if (map_out) map_out[i] = v;
         if (map_u8) {
             const float q = HQ_FADD(HQ_FMUL(v, 255.0f), 0.5f);
-            map_u8[i] = (uint8_t)__float2int_rz(fminf(fmaxf(q, 0.0f), 255.0f));
+            map_u8[i] = (uint8_t)__float2int_rz(fminf(fmaxf(q, 0.0f), 255.0f));   // (a NaN of the CIE94 branch renders as 0)
         }
-        fx = hq_to_fx(e);
+        if (e != e) atomicAdd(err_out + 1, 1ull);   // word 1: NaN count (CIE94 only)
+        else fx = hq_to_fx(e);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) fx += __shfl_down_sync(0xffffffffu, fx, off);
@@ -535,11 +548,11 @@ __global__ void sc_f4_to_planes_kernel(const float4* __restrict__ in, size_t n, 
 // computeError (ImageManipulation.java:858-894): CIEDE kernel (cl:201-209) on two interleaved Lab images + the error image
 // value ((255 - e) * (255 - e)) / (255 * 255) of :890, written to the first three lanes as the reference does
 __global__ void sc_delta_e4_kernel(const float4* __restrict__ a, const float4* __restrict__ b, size_t n, float* __restrict__ e_out,
-                                   float4* __restrict__ err_img) {
+                                   float4* __restrict__ err_img, int de_type) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 p = a[i], q = b[i];
-    const float e = HQ_FSQRT(hq_dist2(p.x, p.y, p.z, q.x, q.y, q.z));
+    const float e = de_type == 0 ? HQ_FSQRT(hq_dist2(p.x, p.y, p.z, q.x, q.y, q.z)) : hq_cl_delta_e94(p.x, p.y, p.z, q.x, q.y, q.z);
     e_out[i] = e;
     if (err_img) {
         const float d = HQ_FSUB(255.0f, e);
@@ -550,7 +563,34 @@ __global__ void sc_delta_e4_kernel(const float4* __restrict__ a, const float4* _
     }
 }
 
+// identity-filter cost under a dE other than CIE76: the assignment kernels score with the squared distance they minimise, so
+// for CIE94 the population is assigned first (index images) and scored here: dE94(Lab(pixel), Lab(P[idx])) over the own pixels
+template <typename IdxT>
+__global__ void sc_score_indices_kernel(const IdxT* __restrict__ idx, const float* __restrict__ lab, size_t stride, size_t own_lo, size_t own_hi,
+                                        const float4* __restrict__ pal_lab, int K8, int de_type, unsigned long long* __restrict__ err_out,
+                                        unsigned long long* __restrict__ nan_out) {
+    const int b = blockIdx.y;
+    long long fx = 0;
+    for (size_t i = own_lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < own_hi; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 c = __ldg(pal_lab + (size_t)b * K8 + idx[(size_t)b * stride + i]);
+        fx += sc_delta_e_fx(de_type, lab[i], lab[stride + i], lab[2 * stride + i], c.x, c.y, c.z, nan_out + b);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) fx += __shfl_down_sync(0xffffffffu, fx, off);
+    if ((threadIdx.x & 31) == 0 && fx) atomicAdd(err_out + b, (unsigned long long)fx);
+}
+
 }  // namespace
+
+cudaError_t launch_sc_score_indices(const void* d_idx, bool idx16, const float* d_lab, size_t stride, size_t own_lo, size_t own_hi,
+                                    const float4* d_pal_lab, int K8, int B, int de_type, unsigned long long* d_err, unsigned long long* d_nan,
+                                    int sm_count, cudaStream_t st) {
+    if (own_hi <= own_lo || B == 0) return cudaSuccess;
+    const dim3 grid((unsigned)((sm_count > 0 ? sm_count : 148) * 4), (unsigned)B);
+    if (idx16) sc_score_indices_kernel<uint16_t><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(d_idx), d_lab, stride, own_lo, own_hi, d_pal_lab, K8, de_type, d_err, d_nan);
+    else sc_score_indices_kernel<uint8_t><<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(d_idx), d_lab, stride, own_lo, own_hi, d_pal_lab, K8, de_type, d_err, d_nan);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_sc_unit_to_xyz4(const float* d_r, const float* d_g, const float* d_b, size_t n, float* d_xyz4, unsigned int* d_bad, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
@@ -572,17 +612,17 @@ cudaError_t launch_sc_f4_to_planes(const float* d_in4, size_t n, size_t stride, 
     sc_f4_to_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(d_in4), n, stride, d_planes);
     return cudaGetLastError();
 }
-cudaError_t launch_sc_delta_e4(const float* d_a4, const float* d_b4, size_t n, float* d_e, float* d_err_img4, cudaStream_t st) {
+cudaError_t launch_sc_delta_e4(const float* d_a4, const float* d_b4, size_t n, float* d_e, float* d_err_img4, int de_type, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     sc_delta_e4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(d_a4), reinterpret_cast<const float4*>(d_b4), n, d_e,
-                                                                     reinterpret_cast<float4*>(d_err_img4));
+                                                                     reinterpret_cast<float4*>(d_err_img4), de_type);
     return cudaGetLastError();
 }
 
 cudaError_t launch_sc_error_image(const float* d_lab_a, const float* d_lab_b, size_t n, size_t stride, float* d_map, uint8_t* d_map_u8,
-                                  unsigned long long* d_err, cudaStream_t st) {
+                                  unsigned long long* d_err, int de_type, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    sc_error_image_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_lab_a, d_lab_b, n, stride, d_map, d_map_u8, d_err);
+    sc_error_image_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_lab_a, d_lab_b, n, stride, d_map, d_map_u8, d_err, de_type);
     return cudaGetLastError();
 }
 
@@ -614,19 +654,19 @@ cudaError_t launch_sc_original(const float* d_opp, int w, int h, size_t stride, 
         for (int i = 0; i < 8 * kT; ++i) f21.v[i] = h_filters[i];
         const dim3 gh((unsigned)((w + kHSeg - 1) / kHSeg), (unsigned)h), gv((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)((rows.y_count + kVRows - 1) / kVRows));
         sc_hpass21_kernel<0, uint8_t><<<gh, kScThreads, 0, st>>>(d_opp, nullptr, nullptr, w, h, stride, f21, d_tmp);
-        sc_vpass21_kernel<0><<<gv, kScThreads, 0, st>>>(d_tmp, w, h, stride, f21, ill, rows, d_lab_out, nullptr, nullptr);
+        sc_vpass21_kernel<0><<<gv, kScThreads, 0, st>>>(d_tmp, w, h, stride, f21, ill, rows, d_lab_out, nullptr, nullptr, 0, nullptr);
         return cudaGetLastError();
     }
     const ScFilters f{d_filters, taps};
     const dim3 grid((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)h), gridv((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)rows.y_count);
     sc_hpass_kernel<0, uint8_t><<<grid, kScThreads, 7 * taps * sizeof(float), st>>>(d_opp, nullptr, nullptr, w, h, stride, f, d_tmp);
-    sc_vpass_kernel<0><<<gridv, kScThreads, 8 * taps * sizeof(float), st>>>(d_tmp, w, h, stride, f, ill, rows, d_lab_out, nullptr, nullptr);
+    sc_vpass_kernel<0><<<gridv, kScThreads, 8 * taps * sizeof(float), st>>>(d_tmp, w, h, stride, f, ill, rows, d_lab_out, nullptr, nullptr, 0, nullptr);
     return cudaGetLastError();
 }
 
 cudaError_t launch_sc_candidate(const void* d_idx, bool idx16, const float4* d_tab, int w, int h, size_t stride, const float* d_filters,
                                 const float* h_filters, int taps, int whitepoint, ScRows rows, float* d_tmp, const float* d_lab_orig,
-                                unsigned long long* d_err, cudaStream_t st) {
+                                unsigned long long* d_err, cudaStream_t st, int de_type, unsigned long long* d_nan) {
     if (w == 0 || h == 0 || rows.y_count == 0) return cudaSuccess;
     if (taps == kT && h_filters) {
         Filt21 f21;
@@ -634,14 +674,14 @@ cudaError_t launch_sc_candidate(const void* d_idx, bool idx16, const float4* d_t
         const dim3 gh((unsigned)((w + kHSeg - 1) / kHSeg), (unsigned)h), gv((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)((rows.y_count + kVRows - 1) / kVRows));
         if (idx16) sc_hpass21_kernel<1, uint16_t><<<gh, kScThreads, 0, st>>>(nullptr, static_cast<const uint16_t*>(d_idx), d_tab, w, h, stride, f21, d_tmp);
         else sc_hpass21_kernel<1, uint8_t><<<gh, kScThreads, 0, st>>>(nullptr, static_cast<const uint8_t*>(d_idx), d_tab, w, h, stride, f21, d_tmp);
-        sc_vpass21_kernel<1><<<gv, kScThreads, 0, st>>>(d_tmp, w, h, stride, f21, hq_whitepoint(whitepoint), rows, nullptr, d_lab_orig, d_err);
+        sc_vpass21_kernel<1><<<gv, kScThreads, 0, st>>>(d_tmp, w, h, stride, f21, hq_whitepoint(whitepoint), rows, nullptr, d_lab_orig, d_err, de_type, d_nan);
         return cudaGetLastError();
     }
     const ScFilters f{d_filters, taps};
     const dim3 grid((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)h), gridv((unsigned)((w + kScThreads - 1) / kScThreads), (unsigned)rows.y_count);
     if (idx16) sc_hpass_kernel<1, uint16_t><<<grid, kScThreads, 7 * taps * sizeof(float), st>>>(nullptr, static_cast<const uint16_t*>(d_idx), d_tab, w, h, stride, f, d_tmp);
     else sc_hpass_kernel<1, uint8_t><<<grid, kScThreads, 7 * taps * sizeof(float), st>>>(nullptr, static_cast<const uint8_t*>(d_idx), d_tab, w, h, stride, f, d_tmp);
-    sc_vpass_kernel<1><<<gridv, kScThreads, 8 * taps * sizeof(float), st>>>(d_tmp, w, h, stride, f, hq_whitepoint(whitepoint), rows, nullptr, d_lab_orig, d_err);
+    sc_vpass_kernel<1><<<gridv, kScThreads, 8 * taps * sizeof(float), st>>>(d_tmp, w, h, stride, f, hq_whitepoint(whitepoint), rows, nullptr, d_lab_orig, d_err, de_type, d_nan);
     return cudaGetLastError();
 }
 

@@ -94,8 +94,8 @@ class ImageManipulation:
     def __init__(self, deltaEType: str = "CIE76", verbose: bool = False, convergence: bool = True, device=0):
         """device: a CUDA device index, or a list of them -> ONE context over several GPUs of this process (hq_create_multi:
         the image rows are split inside the library, every evaluation ends in one grouped NCCL all-reduce)."""
-        if deltaEType != "CIE76":
-            raise ValueError("only CIE76 is implemented (the plugin never selects another, HybridQuantization.java:96)")
+        if deltaEType not in ("CIE76", "CIE94", "CIEDE2000"):
+            raise ValueError("deltaEType must be one of ImageManipulation.deltaETypes (CIE76, CIE94, CIEDE2000)")
         self._lib = _lib.load()
         self._ctx = C.c_void_p()
         self.verbose, self.convergence = verbose, convergence
@@ -111,6 +111,15 @@ class ImageManipulation:
         self._cb = None
         self.shape = None
         self._local_pixels = 0
+        if deltaEType != "CIE76":   # :63 -D<type>; CIEDE2000 (an empty stub in the reference, cl:227-229) is refused by the library
+            try:
+                self.setDeltaE({"CIE94": _lib.DELTAE_CIE94, "CIEDE2000": _lib.DELTAE_CIEDE2000}[deltaEType])
+            except HqError:
+                self.close()
+                raise
+
+    def setDeltaE(self, type_: int) -> None:
+        _lib.check(self._ctx, self._lib.hq_set_delta_e(self._ctx, type_))
 
     # -- lifetime
     def getCudaAvailable(self) -> bool:

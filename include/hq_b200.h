@@ -47,6 +47,18 @@ enum { HQ_SPACE_LAB = 0, HQ_SPACE_SRGB = 1 };
  * the accelerated path); HQ_COST_SCIELAB = the reference's full S-CIELAB chain (hq_eval_palettes_scielab) */
 enum { HQ_COST_LAB = 0, HQ_COST_SCIELAB = 1 };
 
+/* ImageManipulation.deltaETypes (ImageManipulation.java:20; the constructor's first argument, :52,:63).  The plugin itself only
+ * ever passes CIE76 (HybridQuantization.java:96,145).  HQ_DELTAE_CIE94 is the reference kernel's CIE94 branch
+ * (OptimizedConvolution.cl:217-226) bit for bit, INCLUDING its latent NaN: deltaH takes the square root of a difference that
+ * rounding makes slightly negative for about one generic pixel pair in 4,000, so the mean of any real image is NaN.  An integer
+ * sum cannot hold a NaN: such pixels are counted, and every entry that returns err_fx then reports HQ_ERR_FX_NAN for that
+ * candidate, which hq_cost (and the built-in search) turn into a NaN cost — exactly what the reference's host mean would be.
+ * HQ_DELTAE_CIEDE2000: the reference's branch is an empty stub (cl:227-229); hq_set_delta_e refuses it (HQ_ERR_UNSUPPORTED).
+ * Affects hq_eval_palettes (scored from index images in a second pass), hq_eval_palettes_scielab (two-kernel path),
+ * hq_error_image*, hq_delta_e_images and the search. */
+enum { HQ_DELTAE_CIE76 = 0, HQ_DELTAE_CIE94 = 1, HQ_DELTAE_CIEDE2000 = 2 };
+#define HQ_ERR_FX_NAN INT64_MIN
+
 enum {
     HQ_EVAL_SUMS = 1,            /* also reduce per-colour Lab sums */
     HQ_EVAL_FORCE_DIRECT = 2,    /* kernel variant selection, for tests / profiling */
@@ -68,6 +80,7 @@ void hq_destroy(hq_ctx* ctx);
 /* ctx may be NULL: then the message of the last failed hq_create() on this thread */
 const char* hq_last_error(const hq_ctx* ctx);
 int hq_device_info(const hq_ctx* ctx, int* sm_count, int* sm_clock_khz, char* name, int name_len);
+int hq_set_delta_e(hq_ctx* ctx, int type); /* HQ_DELTAE_*; default CIE76 */
 
 /* ---- image upload + RGB->CIELAB: replaces the uploads at ImageManipulation.java:451,471-472
  * and RGBtoXYZ/XYZtoScielab (:100, :285) with the identity spatial filter.

@@ -128,13 +128,20 @@ private:
 // ImageManipulation.java: the compute backend.  Owns (or borrows) one hq_ctx.
 class ImageManipulation {
 public:
-    enum class deltaETypes { CIE76, CIE94, CIEDE2000 };  // :20 — only CIE76 is ever used (HybridQuantization.java:96)
+    enum class deltaETypes { CIE76, CIE94, CIEDE2000 };  // :20 — the plugin only ever passes CIE76 (HybridQuantization.java:96)
 
     // :52 — creation failure THROWS; the reference's silent "pure Java mode" (:79-92) that
     // returns zero arrays does not exist here.
-    ImageManipulation(deltaETypes, bool verbose, bool convergence, int device = 0)
+    ImageManipulation(deltaETypes deltaEType, bool verbose, bool convergence, int device = 0)
         : verbose_(verbose), convergence_(convergence), owns_(true) {
         if (hq_create(device, &ctx_) != HQ_OK) throw std::runtime_error(std::string("hq_create: ") + hq_last_error(nullptr));
+        // :63 program.addBuildOption("-D" + deltaEType.name()); CIEDE2000 is an empty stub in the reference (cl:227-229) and refused here
+        const int t = deltaEType == deltaETypes::CIE76 ? HQ_DELTAE_CIE76 : (deltaEType == deltaETypes::CIE94 ? HQ_DELTAE_CIE94 : HQ_DELTAE_CIEDE2000);
+        if (hq_set_delta_e(ctx_, t) != HQ_OK) {
+            const std::string msg = std::string("hq_set_delta_e: ") + hq_last_error(ctx_);
+            hq_destroy(ctx_); ctx_ = nullptr;
+            throw std::runtime_error(msg);
+        }
     }
     // view over an existing context (used by the C ABI's hq_find_best_quantization)
     ImageManipulation(hq_ctx* borrowed, bool verbose, bool convergence)
@@ -179,7 +186,8 @@ public:
         for (int i = 0; i < populationSize; ++i) {
             // :712 averageArray(err) + computePenalty(used)
             const uint64_t* cnt = counts_.data() + static_cast<size_t>(i) * nbOfColors;
-            const double sum = static_cast<double>(errFx_[i]) * (1.0 / 16777216.0);
+            // (HQ_ERR_FX_NAN: a NaN pixel of the CIE94 branch — the reference's averageArray would return NaN)
+            const double sum = errFx_[i] == HQ_ERR_FX_NAN ? std::nan("") : static_cast<double>(errFx_[i]) * (1.0 / 16777216.0);
             results[i] = sum / static_cast<double>(nTotal) + swasa.computePenalty(cnt, nbOfColors);
         }
         return results;

@@ -72,6 +72,9 @@ JNIEXPORT jint JNICALL CLS(nDeviceCount)(JNIEnv* env, jclass c, jlong h) { retur
 JNIEXPORT void JNICALL CLS(nSetPruning)(JNIEnv* env, jclass c, jlong h, jint mode) {
     if (hq_set_pruning(CTX(h), mode) != HQ_OK) throw_hq(env, CTX(h), "hq_set_pruning");
 }
+JNIEXPORT void JNICALL CLS(nSetDeltaE)(JNIEnv* env, jclass c, jlong h, jint type) {   /* deltaETypes ordinal (:20): 0 CIE76, 1 CIE94, 2 CIEDE2000 (refused) */
+    if (hq_set_delta_e(CTX(h), type) != HQ_OK) throw_hq(env, CTX(h), "hq_set_delta_e");
+}
 JNIEXPORT void JNICALL CLS(nRequestStop)(JNIEnv* env, jclass c, jlong h) { hq_request_stop(CTX(h)); }
 
 /* ---- image */

@@ -41,11 +41,12 @@ public class CudaImageManipulation implements AutoCloseable {
 
     /** several devices = ONE context: rows are split and the integer partials all-reduced (NCCL) inside the library */
     public CudaImageManipulation(deltaETypes deltaEType, boolean verbose, boolean convergence, int[] devices) {
-        if (deltaEType != deltaETypes.CIE76) // the plugin never selects another (HybridQuantization.java:96,145); see DESIGN.md row f4
-            throw new IllegalArgumentException("only CIE76 is available on the CUDA backend");
         this.verbose = verbose;
         this.convergence = convergence;
         ctx = nCreate(devices); // throws RuntimeException when no usable device exists
+        // program.addBuildOption("-D" + deltaEType.name()) (:63).  CIE94 is the reference kernel's branch bit for bit, latent NaN
+        // included; CIEDE2000 is an empty stub in the reference (cl:227-229) and is refused (RuntimeException)
+        try { nSetDeltaE(ctx, deltaEType.ordinal()); } catch (RuntimeException e) { close(); throw e; }
     }
 
     private static int[] devicesFromProperty() {
@@ -184,7 +185,9 @@ public class CudaImageManipulation implements AutoCloseable {
         int[] used = new int[nbOfColors];
         for (int i = 0; i < p; i++) {
             for (int k = 0; k < nbOfColors; k++) used[k] = counts[i * nbOfColors + k] != 0 ? 1 : 0;
-            results[i] = (errFx[i] * (1.0 / 16777216.0)) / n + simulatedAnnealing.computePenalty(used); // SWASA.java:74-82
+            // Long.MIN_VALUE = HQ_ERR_FX_NAN: a NaN pixel of the CIE94 branch — the reference's averageArray would return NaN
+            final double sum = errFx[i] == Long.MIN_VALUE ? Double.NaN : errFx[i] * (1.0 / 16777216.0);
+            results[i] = sum / n + simulatedAnnealing.computePenalty(used); // SWASA.java:74-82
         }
         return results;
     }
@@ -227,6 +230,7 @@ public class CudaImageManipulation implements AutoCloseable {
     private static native long nPixels(long ctx);
     private static native int nDeviceCount(long ctx);
     private static native void nSetPruning(long ctx, int mode);
+    private static native void nSetDeltaE(long ctx, int type);
     private static native void nRequestStop(long ctx);
     private static native void nSetImage(long ctx, byte[] rgb, int width, int rows, int whitepoint);
     private static native void nSetImageFloat(long ctx, float[] r, float[] g, float[] b, int width, int rows, int whitepoint);

@@ -72,6 +72,7 @@ void CLS(nDestroy)(JNIEnv*, jclass, jlong);
 jlong CLS(nPixels)(JNIEnv*, jclass, jlong);
 jint CLS(nDeviceCount)(JNIEnv*, jclass, jlong);
 void CLS(nSetPruning)(JNIEnv*, jclass, jlong, jint);
+void CLS(nSetDeltaE)(JNIEnv*, jclass, jlong, jint);
 void CLS(nSetImage)(JNIEnv*, jclass, jlong, jbyteArray, jint, jint, jint);
 void CLS(nSetImageFloat)(JNIEnv*, jclass, jlong, jfloatArray, jfloatArray, jfloatArray, jint, jint, jint);
 void CLS(nEvalPalettes)(JNIEnv*, jclass, jlong, jfloatArray, jint, jint, jint, jint, jlongArray, jlongArray);
@@ -218,6 +219,12 @@ int main(int argc, char** argv) {
     struct _jobject a_small_out = {out, 16};
     CLS(nQuantize)(env, NULL, ctx, &a_pal, K, 0, &a_small_out, NULL);
     threw_short_out = g_thrown; g_thrown = 0;
+    /* deltaETypes: CIEDE2000 is refused (an empty stub in the reference), CIE94 and CIE76 are accepted */
+    CLS(nSetDeltaE)(env, NULL, ctx, 2);
+    const int threw_ciede2000 = g_thrown; g_thrown = 0;
+    CLS(nSetDeltaE)(env, NULL, ctx, 1); MUST("nSetDeltaE(CIE94)");
+    const double de94 = CLS(nDeltaEImages)(env, NULL, ctx, &a_lab, &a_labq, NULL); MUST("nDeltaEImages (CIE94)");
+    CLS(nSetDeltaE)(env, NULL, ctx, 0); MUST("nSetDeltaE(CIE76)");
     /* the image must still be intact after the refused calls */
     jlong* err_again = calloc(B, sizeof(jlong));
     struct _jobject a_err_again = {err_again, B};
@@ -232,7 +239,8 @@ int main(int argc, char** argv) {
            map_hash, map_equal, map_equal_f32);
     printf("\"iterations\": %d, \"best_error\": \"%a\", \"trace_hash\": %llu, \"best_hash\": %llu, \"progress\": [%d, %d, %d, %d], \"progress_best\": \"%a\", ",
            its, best_error, trace_hash, best_hash, prog_calls, prog_first, prog_last, prog_max, prog_best);
-    printf("\"iterations_stopped\": %d, \"threw_short\": %d, \"cls_short\": \"%s\", \"threw_null\": %d, \"cls_null\": \"%s\", \"threw_bad_k\": %d, \"threw_short_out\": %d}\n",
-           its_stopped, threw_short, cls_short, threw_null, cls_null, threw_bad_k, threw_short_out);
+    printf("\"iterations_stopped\": %d, \"threw_short\": %d, \"cls_short\": \"%s\", \"threw_null\": %d, \"cls_null\": \"%s\", \"threw_bad_k\": %d, \"threw_short_out\": %d, "
+           "\"threw_ciede2000\": %d, \"de94_is_nan_or_positive\": %d}\n",
+           its_stopped, threw_short, cls_short, threw_null, cls_null, threw_bad_k, threw_short_out, threw_ciede2000, (de94 != de94 || de94 > 0) ? 1 : 0);
     return 0;
 }

@@ -105,6 +105,7 @@ def test_jni_shim_through_a_fake_jnienv(oracle, hqlib, tmp_path):
     assert got["threw_short"] == 1 and got["cls_short"] == "java/lang/IllegalArgumentException"
     assert got["threw_null"] == 1 and got["cls_null"] == "java/lang/NullPointerException"
     assert got["threw_bad_k"] == 1 and got["threw_short_out"] == 1
+    assert got["threw_ciede2000"] == 1 and got["de94_is_nan_or_positive"] == 1
 
 
 def test_reference_one_shot_entries_match_the_compiled_reference(backend, oracle):
