@@ -958,8 +958,11 @@ cudaError_t launch_assign_reduce(const AssignArgs& a, cudaStream_t stream) {
     p.results = a.results;
     p.idx_out = a.idx_out;
     p.tail = a.tail;
-    {   // HQ_V1_TMA=0: the small-palette kernel loads its pixels with LDG.128 as in round 1 (A/B measurements)
-        static const int tma_env = [] { const char* e = std::getenv("HQ_V1_TMA"); return (e && e[0] == '0') ? 0 : 1; }();
+    {   // HQ_V1_TMA=1: the small-palette kernel stages its pixel tiles with TMA bulk copies + mbarriers instead of LDG.128.
+        // OFF by default — measured on the B200 (tools/smallk_bench.py, profiles/r02/smallk_tma_ab.txt): the kernel is bound by
+        // instruction issue, not by exposed load latency, and the ring costs instructions: K=8, 4K image, one candidate 41.7 -> 43.0 us,
+        // 64 candidates 1.68 -> 2.01 ms.  Kept selectable so that the measurement can be repeated.
+        static const int tma_env = [] { const char* e = std::getenv("HQ_V1_TMA"); return (e && e[0] == '1') ? 1 : 0; }();
         p.use_tma = tma_env;
     }
     // (an EMPTY own range — a shard that only carries halo rows — is honoured as empty: indices for every pixel, no reduction)
