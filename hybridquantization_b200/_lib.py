@@ -21,6 +21,7 @@ EVAL_SUMS, EVAL_FORCE_DIRECT, EVAL_FORCE_CHUNKED, EVAL_FORCE_PREFILTER, EVAL_PRU
 PRUNE_OFF, PRUNE_AUTO, PRUNE_ON = 0, 1, 2
 MAX_COLORS = 1024
 MAX_COLORS_PRUNED = 4096
+MAX_COLORS_ANY = 1 << 24
 COMM_ID_BYTES = 128
 DELTAE_CIE76, DELTAE_CIE94, DELTAE_CIEDE2000 = 0, 1, 2
 ERR_FX_NAN = -(1 << 63)

@@ -46,7 +46,7 @@ def sources() -> list[str]:
     return src
 
 
-CU_FILES = ("hq_kernels.cu", "hq_pruned.cu", "hq_scielab.cu", "hq_api.cu", "hq_multi.cu")
+CU_FILES = ("hq_kernels.cu", "hq_pruned.cu", "hq_scielab.cu", "hq_bigk.cu", "hq_api.cu", "hq_multi.cu")
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:

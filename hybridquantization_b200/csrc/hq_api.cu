@@ -38,7 +38,7 @@ int check_eval_args(hq_ctx* c, int B, int K, int space) {
     if (!c) return HQ_ERR_INVALID;
     if (!c->have_image) return fail(c, HQ_ERR_NO_IMAGE, "no image: call hq_set_image_u8 or hq_set_image_f32_planar first");
     if (B < 1 || K < 1) return fail(c, HQ_ERR_INVALID, "B and K must be >= 1 (got B=%d K=%d)", B, K);
-    if (K > HQ_MAX_COLORS_PRUNED) return fail(c, HQ_ERR_UNSUPPORTED, "K=%d exceeds HQ_MAX_COLORS_PRUNED=%d", K, HQ_MAX_COLORS_PRUNED);
+    if (K > HQ_MAX_COLORS_ANY) return fail(c, HQ_ERR_UNSUPPORTED, "K=%d exceeds the plugin's own range [1, 2^24] (HybridQuantization.java:192)", K);
     if (space != HQ_SPACE_LAB && space != HQ_SPACE_SRGB) return fail(c, HQ_ERR_INVALID, "unknown space %d", space);
     return HQ_OK;
 }
@@ -78,17 +78,18 @@ int ensure_pruned(hq_ctx* c, hq_ctx::PrunedSet& ps, int space, size_t lo, size_t
 // which evaluations go through the pruned kernel: asked for (HQ_EVAL_PRUNE) or forced by K > HQ_MAX_COLORS, and possible:
 // scoring (no index image) needs the features to BE CIELAB (the error is the CIELAB distance); index-producing
 // evaluations work in either space
+// palettes no tuned kernel stages: beyond the pruned kernel's 4,096 colours, or beyond the exhaustive kernel's 1,024 where the
+// pruned one cannot score (sRGB-space assignment without an index image) -> the chunked sweep of hq_bigk.cu
+bool use_bigk(int K, int space, bool want_idx) {
+    return K > HQ_MAX_COLORS_PRUNED || (K > HQ_MAX_COLORS && !(want_idx || space == HQ_SPACE_LAB));
+}
 bool use_pruned(int K, int space, int flags, bool want_idx) {
+    if (use_bigk(K, space, want_idx)) return false;
     const bool wanted = (flags & HQ_EVAL_PRUNE) != 0 || K > HQ_MAX_COLORS;
     return wanted && (want_idx || space == HQ_SPACE_LAB);
 }
 int prepare_pruned(hq_ctx* c, int K, int space, int flags, bool want_idx, cudaStream_t st) {
-    if (!use_pruned(K, space, flags, want_idx)) {
-        if (K > HQ_MAX_COLORS)
-            return fail(c, HQ_ERR_UNSUPPORTED, "K=%d > HQ_MAX_COLORS=%d is only supported where the pruned kernel applies "
-                        "(LAB space, or index-producing calls)", K, HQ_MAX_COLORS);
-        return HQ_OK;
-    }
+    if (!use_pruned(K, space, flags, want_idx)) return HQ_OK;
     if (space == HQ_SPACE_SRGB) { int rc = ensure_unit(c, st); if (rc) return rc; }
     return want_idx ? ensure_pruned(c, c->pr_all, space, 0, c->n, true, st) : ensure_pruned(c, c->pr_own, HQ_SPACE_LAB, c->own_lo, c->own_hi, false, st);
 }
@@ -114,7 +115,17 @@ int eval_device(hq_ctx* c, const float* d_palettes, int B, int K, int space, int
     const bool prune = use_pruned(K, space, flags, d_idx != nullptr);
     { int rc = prepare_pruned(c, K, space, flags, d_idx != nullptr, st); if (rc) return rc; }
     if (c->profiling) HQ_CUDA(c, cudaEventRecord(c->ev0, st));
-    if (prune) {
+    if (use_bigk(K, space, d_idx != nullptr)) {
+        if (d_idx && K > 65535) return fail(c, HQ_ERR_UNSUPPORTED, "index images hold 16 bits: K=%d > 65,535 is available for scoring and for the output image only", K);
+        HQ_CUDA(c, c->d_big_d2.reserve(c->n ? c->n : 1));
+        HQ_CUDA(c, c->d_big_idx.reserve(c->n ? c->n : 1));
+        const float* feat = space == HQ_SPACE_SRGB ? c->d_unit.p : c->d_lab.p;
+        for (int b = 0; b < B; ++b)
+            HQ_CUDA(c, hq::launch_bigk_candidate(feat, c->d_lab.p, c->n, c->stride, c->own_lo, c->own_hi,
+                                                 (space == HQ_SPACE_SRGB ? c->d_pal_rgb.p : c->d_pal_lab.p) + (size_t)b * K8, c->d_pal_lab.p + (size_t)b * K8, K,
+                                                 space == HQ_SPACE_SRGB, sums, c->d_big_d2.p, c->d_big_idx.p, d_results + (size_t)b * words,
+                                                 d_idx ? static_cast<uint16_t*>(d_idx) + (size_t)b * c->stride : nullptr, c->sm_count, st));
+    } else if (prune) {
         const hq_ctx::PrunedSet& ps = d_idx ? c->pr_all : c->pr_own;
         hq::PrunedArgs pa;
         pa.sorted = ps.sorted.p; pa.sstride = ps.sstride; pa.chunk_start = ps.chunk_start.p; pa.chunk_len = ps.chunk_len.p;
@@ -207,7 +218,7 @@ void hq_destroy(hq_ctx* c) {
     c->d_out_rgb.release(); c->d_out_f32.release(); c->h_pal.release(); c->h_results.release(); c->h_flag.release(); c->d_export_counter.release();
     c->d_sc_filters.release(); c->d_sc_opp.release(); c->d_sc_tmp.release(); c->d_sc_lab.release(); c->d_sc_tab.release(); c->d_sc_err.release();
     c->d_sc_lab2.release(); c->d_sc_map.release(); c->d_sc_rgb2.release(); c->d_sc_map8.release();
-    c->pr_own.release(); c->pr_all.release(); c->d_pr_scratch.release();
+    c->pr_own.release(); c->pr_all.release(); c->d_pr_scratch.release(); c->d_big_d2.release(); c->d_big_idx.release();
     c->d_pr_stats.release(); c->h_pr_small.release();
     delete c;
 }
@@ -621,11 +632,15 @@ int quantize_one(hq_ctx* c, const float* palette, int K, int space, uint8_t* out
     HQ_CUDA(c, c->d_idx.reserve((c->stride ? c->stride : 1) * (idx16 ? 2 : 1)));
     if (!copy_palettes_checked(c->h_pal.p, palette, npal)) return fail(c, HQ_ERR_INVALID, "%s", kBadPalette);
     HQ_CUDA(c, cudaMemcpyAsync(c->d_pal.p, c->h_pal.p, npal * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    rc = eval_device(c, c->d_pal.p, 1, K, space, (K > HQ_MAX_COLORS || c->prune_mode == HQ_PRUNE_ON) ? HQ_EVAL_PRUNE : 0, c->d_results.p, c->d_idx.p,
-                     c->stream); if (rc) return rc;
+    const bool big = K > 65535;   // beyond 16-bit index images: the chunked sweep's own 32-bit assignment feeds the output image
+    if (big && out_idx) return fail(c, HQ_ERR_UNSUPPORTED, "out_idx holds 16 bits: pass NULL for K=%d > 65,535", K);
+    rc = eval_device(c, c->d_pal.p, 1, K, space, (K > HQ_MAX_COLORS || c->prune_mode == HQ_PRUNE_ON) ? HQ_EVAL_PRUNE : 0, c->d_results.p,
+                     big ? nullptr : c->d_idx.p, c->stream); if (rc) return rc;
     if (out_rgb) HQ_CUDA(c, c->d_out_rgb.reserve(n * 3 > 0 ? n * 3 : 1));
     if (out_f32) HQ_CUDA(c, c->d_out_f32.reserve(n * 4 > 0 ? n * 4 : 1));
-    if (out_rgb || out_f32)
+    if ((out_rgb || out_f32) && big)
+        HQ_CUDA(c, hq::launch_apply_palette_u32(c->d_big_idx.p, n, c->d_pal.p, out_rgb ? c->d_out_rgb.p : nullptr, out_f32 ? c->d_out_f32.p : nullptr, c->stream));
+    else if (out_rgb || out_f32)
         HQ_CUDA(c, hq::launch_apply_palette(c->d_idx.p, idx16, n, c->d_pal.p, K, out_rgb ? c->d_out_rgb.p : nullptr,
                                             out_f32 ? c->d_out_f32.p : nullptr, c->stream));
     const size_t lo = c->own_lo, no = c->own_hi - c->own_lo;  // a shard returns its own rows only

@@ -106,6 +106,8 @@ struct hq_ctx {
     PrunedSet pr_own;   // CIELAB features of the OWN pixels: the LAB cost model (error, counts, sums; no indices)
     PrunedSet pr_all;   // features of EVERY local pixel (own + halo) in the space asked for, with their image positions:
                         // index-producing evaluations (the S-CIELAB chain, hq_quantize)
+    DevBuf<float> d_big_d2;                 // palettes beyond the staged kernels (hq_bigk.cu): per-pixel running best distance ...
+    DevBuf<unsigned> d_big_idx;             // ... and index of the candidate being swept (the final assignment afterwards)
     DevBuf<unsigned> d_pr_scratch;
     DevBuf<unsigned long long> d_pr_stats;
     PinBuf<unsigned long long> h_pr_small;

@@ -122,6 +122,16 @@ struct PrunedArgs {
 };
 cudaError_t launch_pruned_assign(const PrunedArgs& a, cudaStream_t st);
 
+// ---- palettes of ANY size (hq_bigk.cu): chunked sweep against a per-pixel running best in HBM, then one reduction pass.
+// One candidate per call: d_pal_feat / d_pal_lab are that candidate's [K8] tables, d_out its result words (zeroed by the
+// caller), d_best_d2 / d_best_idx [n] scratch that holds the final assignment afterwards, d_idx16 (optional, K <= 65535) the
+// index image of every local pixel.
+constexpr int kBigChunk = 2048;
+cudaError_t launch_bigk_candidate(const float* d_feat, const float* d_lab, size_t n, size_t stride, size_t own_lo, size_t own_hi, const float4* d_pal_feat,
+                                  const float4* d_pal_lab, int K, bool srgb, bool want_sums, float* d_best_d2, unsigned* d_best_idx,
+                                  unsigned long long* d_out, uint16_t* d_idx16, int sm_count, cudaStream_t st);
+cudaError_t launch_apply_palette_u32(const unsigned* d_idx, size_t n, const float* d_palette, uint8_t* d_out_rgb, float* d_out_f32, cudaStream_t st);
+
 // indices -> output image of the chosen palette colours (u8 RGB packed and/or float RGBA)
 cudaError_t launch_apply_palette(const void* d_idx, bool idx16, size_t n, const float* d_palette /*[K][4]*/,
                                  int K, uint8_t* d_out_rgb, float* d_out_f32, cudaStream_t stream);

@@ -32,7 +32,7 @@ enum {
     HQ_ERR_INVALID = 1,     /* bad argument */
     HQ_ERR_CUDA = 2,        /* CUDA runtime / driver error, no device */
     HQ_ERR_NO_IMAGE = 3,    /* hq_set_image_* has not been called */
-    HQ_ERR_UNSUPPORTED = 4, /* e.g. K > HQ_MAX_COLORS */
+    HQ_ERR_UNSUPPORTED = 4, /* e.g. K > HQ_MAX_COLORS_ANY, a 16-bit index image for K > 65,535 */
     HQ_ERR_CALLBACK = 5     /* the all-reduce hook reported failure */
 };
 
@@ -71,6 +71,11 @@ enum {
 #define HQ_MAX_COLORS 1024          /* palette sizes the exhaustive kernel stages in shared memory */
 #define HQ_MAX_COLORS_PRUNED 4096   /* palette sizes of the pruned kernel: 1024 < K <= 4096 works wherever that kernel applies
                                      * (LAB-space scoring, the S-CIELAB chain, hq_quantize) and is selected automatically */
+#define HQ_MAX_COLORS_ANY (1 << 24) /* the plugin's own range ("Number of colors" in [1, 2^24], HybridQuantization.java:192): beyond the
+                                     * staged kernels the palette is swept in chunks against a per-pixel running best (same integers,
+                                     * untuned: ~10 instructions per pair).  hq_eval_palettes (both spaces, sums) and hq_quantize's
+                                     * image outputs take any K up to here; 16-bit index images (hq_quantize's out_idx, the S-CIELAB
+                                     * chain) stop at 65,535 */
 
 typedef struct hq_ctx hq_ctx;
 

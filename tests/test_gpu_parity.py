@@ -192,12 +192,17 @@ def test_errors_are_loud(backend, hqlib):
         fresh.evalPalettes(synth.synth_palettes(1, 4))
     assert e.value.code == 3  # HQ_ERR_NO_IMAGE
     fresh.setImage(synth.synth_image(8, 8, 1))
+    few = synth.synth_palettes(1, 4)   # K beyond the plugin's own range (HybridQuantization.java:192) is refused before anything is read
+    assert fresh._lib.hq_eval_palettes(fresh._ctx, few.ctypes.data, 1, (1 << 24) + 1, 0, 0, None, None, None) == 4  # HQ_ERR_UNSUPPORTED
+    bad = synth.synth_palettes(1, 4)
+    bad[0, 2, 1] = np.nan
     with pytest.raises(HqError) as e:
-        fresh.evalPalettes(synth.synth_palettes(1, 4097))           # beyond HQ_MAX_COLORS_PRUNED
-    assert e.value.code == 4  # HQ_ERR_UNSUPPORTED
+        fresh.evalPalettes(bad)                                     # NaN / out-of-range palette colours are refused (SWASA.java:93-106 clamps them)
+    assert e.value.code == 1
+    bad[0, 2, 1] = 1.5
     with pytest.raises(HqError) as e:
-        fresh.evalPalettes(synth.synth_palettes(1, 1025), SPACE_SRGB)  # > HQ_MAX_COLORS where the pruned kernel cannot score
-    assert e.value.code == 4
+        fresh.quantize(bad[0])
+    assert e.value.code == 1
     with pytest.raises(ValueError):
         fresh.setImage(np.zeros((4, 4), np.uint8))  # fewer than 3 channels (HybridQuantization.java:68)
     fresh.close()

@@ -136,8 +136,42 @@ def test_quantize_with_large_palettes(backend, oracle, K, space):
     assert np.array_equal(got["f32"].view(np.uint32), want["f32"].view(np.uint32))
 
 
+# ---------------------------------------------------------------- palettes beyond every staged kernel: the chunked sweep (hq_bigk.cu)
+@pytest.mark.parametrize("K,space", [(4097, SPACE_LAB), (6000, SPACE_LAB), (1500, SPACE_SRGB), (9000, SPACE_SRGB)])
+def test_palettes_beyond_the_staged_kernels(backend, oracle, K, space):
+    """K > 4,096 (or K > 1,024 with sRGB-space scoring, which the pruned kernel cannot do): error, counts and Lab sums equal the oracle's"""
+    img = synth.synth_image(160, 120, K, K % 2 == 0)
+    pal = synth.synth_palettes(2, K, seed=K)
+    backend.setImage(img)
+    _same(backend.evalPalettes(pal, space, sums=True), oracle.assign_reduce(img, pal, space, threads=THREADS))
+
+
+def test_output_image_with_70000_colours(backend, oracle):
+    """beyond 16-bit index images: the output image comes from the sweep's own 32-bit assignment; out_idx is refused"""
+    from hybridquantization_b200 import HqError
+    K = 70000
+    img = synth.synth_image(96, 64, 21, True)
+    pal = synth.synth_palettes(1, K, seed=3)[0]
+    backend.setImage(img)
+    with pytest.raises(HqError) as ex:
+        backend.quantize(pal, SPACE_LAB)                # asks for the 16-bit index image
+    assert ex.value.code == 4
+    n = 96 * 64
+    import ctypes as C
+    rgb = np.empty((n, 3), np.uint8); f32 = np.empty((n, 4), np.float32)
+    rc = backend._lib.hq_quantize(backend._ctx, pal.ctypes.data_as(C.c_void_p), K, SPACE_LAB, rgb.ctypes.data_as(C.c_void_p), f32.ctypes.data_as(C.c_void_p), None)
+    assert rc == 0
+    # the oracle's nearest colour per pixel, by its own sweep over all 70,000 (first wins)
+    r = oracle.assign_reduce(img, pal[None], SPACE_LAB, threads=THREADS)
+    got = backend.evalPalettes(pal[None], SPACE_LAB)
+    assert np.array_equal(got["err_fx"], r["err_fx"]) and np.array_equal(got["counts"], r["counts"])
+    used = np.flatnonzero(r["counts"][0])
+    assert set(map(bytes, f32.view(np.uint8).reshape(n, 16))) == set(map(bytes, pal[used].view(np.uint8).reshape(-1, 16)))
+    assert np.array_equal(rgb, (f32[:, :3] * np.float32(255.0) + np.float32(0.5)).astype(np.int32).astype(np.uint8))
+
+
 # ---------------------------------------------------------------- index-producing pruning inside the S-CIELAB chain
-@pytest.mark.parametrize("w,h,K,space", [(640, 360, 256, SPACE_SRGB), (512, 300, 64, SPACE_LAB), (300, 260, 1500, SPACE_SRGB)])
+@pytest.mark.parametrize("w,h,K,space", [(640, 360, 256, SPACE_SRGB), (512, 300, 64, SPACE_LAB), (300, 260, 1500, SPACE_SRGB), (120, 90, 5000, SPACE_SRGB)])
 def test_scielab_chain_with_pruned_assignment(backend, oracle, w, h, K, space):
     """hq_eval_palettes_scielab assigns with the pruned kernel (indices scattered through the sort permutation) when it
     pays or K > 1024: errors and counts must equal the oracle's and the exhaustive assignment's"""
