@@ -349,7 +349,7 @@ struct AssignSmem {
         skew_len = (K8 / kChunk) * (kChunk + 1);
         size_t o = 0;
         off_pairs01 = o; if (VARIANT != 3) o += (size_t)K8 / 2 * 16;       // (f0,f0',f1,f1') per colour pair
-        off_coef = o;    if (VARIANT == 3) o += (size_t)K8 * 16;           // (-2p0,-2p1,-2p2,|p|^2) per colour
+        off_coef = o;    if (VARIANT == 3) o += (size_t)((K8 + 15) / 16 * 16) * 16;   // (-2p0,-2p1,-2p2,|p|^2) per colour, an even number of chunks
         off_lab = o;     if (SRGB) o += (size_t)K8 * 16;                   // Lab of the palette for scoring
         off_sum = o;     if (SUMS) o += (size_t)K8 * 3 * 8;                // per-colour Lab sums
         off_pairs2 = o;  if (VARIANT != 3) o += (size_t)K8 / 2 * 8;        // (f2,f2') per colour pair
@@ -394,7 +394,24 @@ __device__ __forceinline__ void exact_chunk(const float* __restrict__ s_sk, int 
 #ifndef HQ_V3_UNROLL
 #define HQ_V3_UNROLL 2
 #endif
-constexpr int kV3Unroll = HQ_V3_UNROLL;  // chunks per unrolled iteration of the prefilter sweep
+constexpr int kV3Unroll = HQ_V3_UNROLL;  // chunks per unrolled iteration of the prefilter sweep (HQ_V3_BOOK == 0)
+// Round 2: (a) 8 pixels per thread in variant 3 (two 1024-pixel sub-tiles per iteration, four packed pixel pairs): every
+// LDS.128 of a colour's coefficients now feeds 12 FFMA2 instead of 6; (b) chunk bookkeeping through the MANTISSA: the chunk
+// id replaces the low bits of the chunk minimum (one LOP3), so "best and second-best chunk" of a PAIR of chunks is
+// min, max, max, min3, min — 3.5 ALU-pipe instructions per pixel and chunk instead of 5 (FMNMX x2, FSETP, FSEL, SEL), and the
+// winner's chunk id falls out of the best value itself.  The perturbation (< 2^bits ulp) is added to the ambiguity threshold.
+#ifndef HQ_V3_PX
+#define HQ_V3_PX 8
+#endif
+#ifndef HQ_V3_BOOK
+#define HQ_V3_BOOK 1
+#endif
+static_assert(HQ_V3_PX == 4 || HQ_V3_PX == 8, "variant 3 handles one or two 1024-pixel sub-tiles per iteration");
+template <int VARIANT> struct AssignGeom {
+    static constexpr int kPx = VARIANT == 3 ? HQ_V3_PX : kPxPerThread;   // pixels per thread and iteration
+    static constexpr int kSub = kPx / kPxPerThread;                      // 1024-pixel sub-tiles per iteration
+    static constexpr int kTile = kTilePx * kSub;
+};
 template <int VARIANT, bool SRGB, bool SUMS, int IDXW>
 __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VARIANT == 1 ? 3 : 2)) assign_reduce_kernel(const AssignParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -422,6 +439,8 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VAR
         float* pla_f = reinterpret_cast<float*>(s_pla);
         float* pb_f = reinterpret_cast<float*>(s_pb);
         float m0 = 0.f, m1 = 0.f, m2 = 0.f, me = 0.f;
+        if (VARIANT == 3)   // the sweep takes chunks in pairs: a palette with an odd chunk count gets one more chunk that never wins
+            for (int k = K8 + tid; k < (K8 + 15) / 16 * 16; k += kThreads) s_coef[k] = make_float4(0.f, 0.f, 0.f, 1e30f);
         for (int k = tid; k < K8; k += kThreads) {
             const float4 f = gf[k];
             if (VARIANT != 3) {
@@ -464,7 +483,8 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VAR
     const float* f0 = p.feat; const float* f1 = p.feat + p.stride; const float* f2 = p.feat + 2 * p.stride;
     const float* l0 = p.lab;  const float* l1 = p.lab + p.stride;  const float* l2 = p.lab + 2 * p.stride;
     const size_t n = p.n;
-    const size_t ntiles = (n + kTilePx - 1) / kTilePx;
+    constexpr int PX = AssignGeom<VARIANT>::kPx, SUB = AssignGeom<VARIANT>::kSub, TILE = AssignGeom<VARIANT>::kTile;
+    const size_t ntiles = (n + TILE - 1) / TILE;
     const float INF = __int_as_float(0x7f800000);
     const int nchunks = K8 / kChunk;
     long long err_acc = 0;
@@ -526,11 +546,19 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VAR
             for (size_t i = 0; i < my_tiles && i < (size_t)kPxStages - 1; ++i) tma_issue(i);
     }
 
+    // variant 3, chunk id in the mantissa: ids 0 .. 2*ceil(nchunks/2)-1 need `bits` bits; a value moves by < 2^bits ulp
+    const int nchunks2 = (nchunks + 1) & ~1;
+    const int id_bits = nchunks2 > 1 ? 32 - __clz(nchunks2 - 1) : 1;
+    const unsigned id_mask = (1u << id_bits) - 1u;
+    const float rho25 = 2.5f * __uint_as_float((unsigned)(127 + id_bits - 23) << 23);   // 2.5 * 2^(bits-23)
+
     size_t it = 0;
     for (size_t tile = blockIdx.y; tile < ntiles; tile += gridDim.y, ++it) {
-        const size_t base = tile * kTilePx + (size_t)kPxPerThread * tid;
-        float x0[4], x1[4], x2[4];
-        int nvalid;
+        // pixel j of this thread: base + (j >> 2) * kTilePx + (j & 3) — every sub-tile is read with one 128-bit load per plane
+        const size_t base = tile * TILE + (size_t)kPxPerThread * tid;
+        auto pix = [&](int j) { return base + (size_t)(j >> 2) * kTilePx + (size_t)(j & 3); };
+        float x0[PX], x1[PX], x2[PX];
+        int nv[SUB];   // valid pixels of each sub-tile's quad
         if (tma) {
             // refill first: tile it + kPxStages - 1 goes into the stage tile it - 1 used, once every thread has read that one
             if (tid == 0 && it + kPxStages - 1 < my_tiles) {
@@ -547,43 +575,52 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VAR
             x0[0] = a.x; x0[1] = a.y; x0[2] = a.z; x0[3] = a.w;
             x1[0] = c.x; x1[1] = c.y; x1[2] = c.z; x1[3] = c.w;
             x2[0] = d.x; x2[1] = d.y; x2[2] = d.z; x2[3] = d.w;
-            nvalid = base + 4 <= n ? 4 : (base < n ? (int)(n - base) : 0);
-            if (nvalid < 4) {   // the tail of the last tile: what lies beyond the image is not pixels
+            nv[0] = base + 4 <= n ? 4 : (base < n ? (int)(n - base) : 0);
+            if (nv[0] < 4) {   // the tail of the last tile: what lies beyond the image is not pixels
 #pragma unroll
-                for (int j = 0; j < 4; ++j) if (j >= nvalid) { x0[j] = 0.f; x1[j] = 0.f; x2[j] = 0.f; }
+                for (int j = 0; j < 4; ++j) if (j >= nv[0]) { x0[j] = 0.f; x1[j] = 0.f; x2[j] = 0.f; }
             }
-        } else if (base + 4 <= n) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(f0 + base));
-            const float4 c = __ldg(reinterpret_cast<const float4*>(f1 + base));
-            const float4 d = __ldg(reinterpret_cast<const float4*>(f2 + base));
-            x0[0] = a.x; x0[1] = a.y; x0[2] = a.z; x0[3] = a.w;
-            x1[0] = c.x; x1[1] = c.y; x1[2] = c.z; x1[3] = c.w;
-            x2[0] = d.x; x2[1] = d.y; x2[2] = d.z; x2[3] = d.w;
-            nvalid = 4;
         } else {
-            nvalid = base < n ? (int)(n - base) : 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const bool ok = j < nvalid;
-                x0[j] = ok ? f0[base + j] : 0.f; x1[j] = ok ? f1[base + j] : 0.f; x2[j] = ok ? f2[base + j] : 0.f;
+            for (int s = 0; s < SUB; ++s) {
+                const size_t bs = base + (size_t)s * kTilePx;
+                if (bs + 4 <= n) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(f0 + bs));
+                    const float4 c = __ldg(reinterpret_cast<const float4*>(f1 + bs));
+                    const float4 d = __ldg(reinterpret_cast<const float4*>(f2 + bs));
+                    x0[4 * s] = a.x; x0[4 * s + 1] = a.y; x0[4 * s + 2] = a.z; x0[4 * s + 3] = a.w;
+                    x1[4 * s] = c.x; x1[4 * s + 1] = c.y; x1[4 * s + 2] = c.z; x1[4 * s + 3] = c.w;
+                    x2[4 * s] = d.x; x2[4 * s + 1] = d.y; x2[4 * s + 2] = d.z; x2[4 * s + 3] = d.w;
+                    nv[s] = 4;
+                } else {
+                    nv[s] = bs < n ? (int)(n - bs) : 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool ok = j < nv[s];
+                        x0[4 * s + j] = ok ? f0[bs + j] : 0.f; x1[4 * s + j] = ok ? f1[bs + j] : 0.f; x2[4 * s + j] = ok ? f2[bs + j] : 0.f;
+                    }
+                }
             }
         }
+        auto valid = [&](int j) { return (j & 3) < nv[j >> 2]; };
 
-        float best[4] = {INF, INF, INF, INF};  // exact squared distance of the winner
-        int idx[4] = {0, 0, 0, 0};
-        bool deferred[4] = {false, false, false, false};
+        float best[PX];  // exact squared distance of the winner
+        int idx[PX];
+        bool deferred[PX];
+#pragma unroll
+        for (int j = 0; j < PX; ++j) { best[j] = INF; idx[j] = 0; deferred[j] = false; }
 
         if (VARIANT == 1) {
-            uint64_t X[4], Y[4], Z[4];
+            uint64_t X[PX], Y[PX], Z[PX];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { X[j] = pack2(x0[j], x0[j]); Y[j] = pack2(x1[j], x1[j]); Z[j] = pack2(x2[j], x2[j]); }
+            for (int j = 0; j < PX; ++j) { X[j] = pack2(x0[j], x0[j]); Y[j] = pack2(x1[j], x1[j]); Z[j] = pack2(x2[j], x2[j]); }
 #pragma unroll 4
             for (int q = 0; q < K8 / 2; ++q) {
                 const float4 la = s_pla[q];
                 const float2 bb = s_pb[q];
                 const uint64_t P0 = pack2(la.x, la.y), P1 = pack2(la.z, la.w), P2 = pack2(bb.x, bb.y);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < PX; ++j) {
                     float dlo, dhi;
                     unpack2(dist2_pair(X[j], Y[j], Z[j], P0, P1, P2), dlo, dhi);
                     if (dlo < best[j]) { best[j] = dlo; idx[j] = 2 * q; }
@@ -591,30 +628,34 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VAR
                 }
             }
         } else if (VARIANT == 2) {
-            uint64_t X[4], Y[4], Z[4];
+            uint64_t X[PX], Y[PX], Z[PX];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { X[j] = pack2(x0[j], x0[j]); Y[j] = pack2(x1[j], x1[j]); Z[j] = pack2(x2[j], x2[j]); }
-            int cidx[4] = {0, 0, 0, 0};
+            for (int j = 0; j < PX; ++j) { X[j] = pack2(x0[j], x0[j]); Y[j] = pack2(x1[j], x1[j]); Z[j] = pack2(x2[j], x2[j]); }
+            int cidx[PX];
+#pragma unroll
+            for (int j = 0; j < PX; ++j) cidx[j] = 0;
             for (int c = 0; c < nchunks; ++c) {
-                float m[4] = {INF, INF, INF, INF};
+                float m[PX];
+#pragma unroll
+                for (int j = 0; j < PX; ++j) m[j] = INF;
 #pragma unroll
                 for (int q = 0; q < kChunk / 2; ++q) {
                     const float4 la = s_pla[c * (kChunk / 2) + q];
                     const float2 bb = s_pb[c * (kChunk / 2) + q];
                     const uint64_t P0 = pack2(la.x, la.y), P1 = pack2(la.z, la.w), P2 = pack2(bb.x, bb.y);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < PX; ++j) {
                         float dlo, dhi;
                         unpack2(dist2_pair(X[j], Y[j], Z[j], P0, P1, P2), dlo, dhi);
                         m[j] = min3(m[j], dlo, dhi);
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < PX; ++j)
                     if (m[j] < best[j]) { best[j] = m[j]; cidx[j] = c; }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < PX; ++j) {
                 const int s0 = cidx[j] * (kChunk + 1);
                 int found = 0;
 #pragma unroll
@@ -625,21 +666,24 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VAR
                 idx[j] = cidx[j] * kChunk + found;
             }
         } else {
-            // ---- prefilter sweep: two pixel PAIRS per thread, palette coefficients broadcast
-            const uint64_t X0 = pack2(x0[0], x0[1]), X1 = pack2(x0[2], x0[3]);
-            const uint64_t Y0 = pack2(x1[0], x1[1]), Y1 = pack2(x1[2], x1[3]);
-            const uint64_t Z0 = pack2(x2[0], x2[1]), Z1 = pack2(x2[2], x2[3]);
-            float sbest[4] = {INF, INF, INF, INF}, second[4] = {INF, INF, INF, INF};
-            int cidx[4] = {0, 0, 0, 0};
-#pragma unroll (kV3Unroll)
-            for (int c = 0; c < nchunks; ++c) {
-                float m[4] = {INF, INF, INF, INF};
+            // ---- prefilter sweep: PX / 2 pixel PAIRS per thread, palette coefficients broadcast
+            constexpr int NP = PX / 2;
+            uint64_t X[NP], Y[NP], Z[NP];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) { X[q] = pack2(x0[2 * q], x0[2 * q + 1]); Y[q] = pack2(x1[2 * q], x1[2 * q + 1]); Z[q] = pack2(x2[2 * q], x2[2 * q + 1]); }
+            float sbest[PX], second[PX];
+#pragma unroll
+            for (int j = 0; j < PX; ++j) { sbest[j] = INF; second[j] = INF; }
+            // minimum of the 8 prefilter values of chunk c, per pixel
+            auto chunk_min = [&](int c, float (&m)[PX]) {
+#pragma unroll
+                for (int j = 0; j < PX; ++j) m[j] = INF;
 #pragma unroll
                 for (int q = 0; q < kChunk; q += 2) {
                     const float4 u = s_coef[c * kChunk + q], v = s_coef[c * kChunk + q + 1];
 #if HQ_PREFILTER_SCALAR
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < PX; ++j) {
                         const float su = __fmaf_rn(x0[j], u.x, __fmaf_rn(x1[j], u.y, __fmaf_rn(x2[j], u.z, u.w)));
                         const float sv = __fmaf_rn(x0[j], v.x, __fmaf_rn(x1[j], v.y, __fmaf_rn(x2[j], v.z, v.w)));
                         m[j] = min3(m[j], su, sv);
@@ -647,33 +691,69 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VAR
 #else
                     const uint64_t ua = pack2(u.x, u.x), ub = pack2(u.y, u.y), uc = pack2(u.z, u.z), ue = pack2(u.w, u.w);
                     const uint64_t va = pack2(v.x, v.x), vb = pack2(v.y, v.y), vc = pack2(v.z, v.z), ve = pack2(v.w, v.w);
-                    float a0, a1, b0, b1;
-                    unpack2(fma2(X0, ua, fma2(Y0, ub, fma2(Z0, uc, ue))), a0, a1);
-                    unpack2(fma2(X0, va, fma2(Y0, vb, fma2(Z0, vc, ve))), b0, b1);
-                    m[0] = min3(m[0], a0, b0); m[1] = min3(m[1], a1, b1);
-                    unpack2(fma2(X1, ua, fma2(Y1, ub, fma2(Z1, uc, ue))), a0, a1);
-                    unpack2(fma2(X1, va, fma2(Y1, vb, fma2(Z1, vc, ve))), b0, b1);
-                    m[2] = min3(m[2], a0, b0); m[3] = min3(m[3], a1, b1);
+#pragma unroll
+                    for (int r = 0; r < NP; ++r) {
+                        float a0, a1, b0, b1;
+                        unpack2(fma2(X[r], ua, fma2(Y[r], ub, fma2(Z[r], uc, ue))), a0, a1);
+                        unpack2(fma2(X[r], va, fma2(Y[r], vb, fma2(Z[r], vc, ve))), b0, b1);
+                        m[2 * r] = min3(m[2 * r], a0, b0); m[2 * r + 1] = min3(m[2 * r + 1], a1, b1);
+                    }
 #endif
                 }
+            };
+#if HQ_V3_BOOK
+            // two chunks per iteration; each chunk minimum carries its chunk id in its low mantissa bits, so the two smallest
+            // chunk minima (and the winner's id) are kept with min / max alone
+            const unsigned nmask = ~id_mask;
+#pragma unroll 1
+            for (int c = 0; c < nchunks2; c += 2) {
+                float ma[PX], mb[PX];
+                chunk_min(c, ma);
+                chunk_min(c + 1, mb);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < PX; ++j) {
+                    const float a = __uint_as_float((__float_as_uint(ma[j]) & nmask) | (unsigned)c);
+                    const float d = __uint_as_float((__float_as_uint(mb[j]) & nmask) | (unsigned)(c + 1));
+                    const float lo = fminf(a, d), hi = fmaxf(a, d);
+                    second[j] = min3(second[j], hi, fmaxf(lo, sbest[j]));
+                    sbest[j] = fminf(sbest[j], lo);
+                }
+            }
+#else
+            int cidx[PX];
+#pragma unroll
+            for (int j = 0; j < PX; ++j) cidx[j] = 0;
+#pragma unroll (kV3Unroll)
+            for (int c = 0; c < nchunks; ++c) {
+                float m[PX];
+                chunk_min(c, m);
+#pragma unroll
+                for (int j = 0; j < PX; ++j) {
                     second[j] = fminf(second[j], fmaxf(m[j], sbest[j]));  // 2nd smallest chunk minimum
                     if (m[j] < sbest[j]) { sbest[j] = m[j]; cidx[j] = c; }
                 }
             }
+#endif
             // ---- decide: unique chunk -> exact evaluation of that chunk; else defer / exact sweep
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (j < nvalid) {
+            for (int j = 0; j < PX; ++j) {
+                if (valid(j)) {
                     const float nx = fmaf(x2[j], x2[j], fmaf(x1[j], x1[j], x0[j] * x0[j]));
-                    const float T = 2.01f * E + 1.0e-6f * (fabsf(sbest[j] + nx) + E);
+                    float T = 2.01f * E + 1.0e-6f * (fabsf(sbest[j] + nx) + E);
+#if HQ_V3_BOOK
+                    // every carried value is within 2^bits ulp of the chunk minimum it stands for: if the winner lay outside the
+                    // best chunk, second <= sbest + T + rho (|m_best| + |m_winner's chunk|) would hold, both magnitudes <= (|sbest| + T)(1 + 4 rho)
+                    T += rho25 * (fabsf(sbest[j]) + T);
+                    const int cw = (int)(__float_as_uint(sbest[j]) & id_mask);
+#else
+                    const int cw = cidx[j];
+#endif
                     if (second[j] > sbest[j] + T) {
-                        exact_chunk(s_sk, skew_len, cidx[j], x0[j], x1[j], x2[j], best[j], idx[j]);
+                        exact_chunk(s_sk, skew_len, cw, x0[j], x1[j], x2[j], best[j], idx[j]);
                     } else {
                         const unsigned slot = atomicAdd(&s_wl_n, 1u);
-                        if (slot < (unsigned)kWorklistCap && base + j < 0xffffffffull) {
-                            s_wl[slot] = (unsigned)(base + j);
+                        if (slot < (unsigned)kWorklistCap && pix(j) < 0xffffffffull) {
+                            s_wl[slot] = (unsigned)pix(j);
                             deferred[j] = true;
                         } else {
                             exact_all(x0[j], x1[j], x2[j], best[j], idx[j]);  // worklist full: resolve here
@@ -684,51 +764,59 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VAR
         }
 
         // ---- per-pixel epilogue: error, counts, sums, indices
-        float q0[4], q1[4], q2[4];  // Lab of the pixel
+        float q0[PX], q1[PX], q2[PX];  // Lab of the pixel
         if (SRGB) {
-            if (nvalid == 4) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(l0 + base));
-                const float4 c = __ldg(reinterpret_cast<const float4*>(l1 + base));
-                const float4 d = __ldg(reinterpret_cast<const float4*>(l2 + base));
-                q0[0] = a.x; q0[1] = a.y; q0[2] = a.z; q0[3] = a.w;
-                q1[0] = c.x; q1[1] = c.y; q1[2] = c.z; q1[3] = c.w;
-                q2[0] = d.x; q2[1] = d.y; q2[2] = d.z; q2[3] = d.w;
-            } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const bool ok = j < nvalid;
-                    q0[j] = ok ? l0[base + j] : 0.f; q1[j] = ok ? l1[base + j] : 0.f; q2[j] = ok ? l2[base + j] : 0.f;
+            for (int s = 0; s < SUB; ++s) {
+                const size_t bs = base + (size_t)s * kTilePx;
+                if (nv[s] == 4) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(l0 + bs));
+                    const float4 c = __ldg(reinterpret_cast<const float4*>(l1 + bs));
+                    const float4 d = __ldg(reinterpret_cast<const float4*>(l2 + bs));
+                    q0[4 * s] = a.x; q0[4 * s + 1] = a.y; q0[4 * s + 2] = a.z; q0[4 * s + 3] = a.w;
+                    q1[4 * s] = c.x; q1[4 * s + 1] = c.y; q1[4 * s + 2] = c.z; q1[4 * s + 3] = c.w;
+                    q2[4 * s] = d.x; q2[4 * s + 1] = d.y; q2[4 * s + 2] = d.z; q2[4 * s + 3] = d.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool ok = j < nv[s];
+                        q0[4 * s + j] = ok ? l0[bs + j] : 0.f; q1[4 * s + j] = ok ? l1[bs + j] : 0.f; q2[4 * s + j] = ok ? l2[bs + j] : 0.f;
+                    }
                 }
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { q0[j] = x0[j]; q1[j] = x1[j]; q2[j] = x2[j]; }
+            for (int j = 0; j < PX; ++j) { q0[j] = x0[j]; q1[j] = x1[j]; q2[j] = x2[j]; }
         }
         // small palettes are instruction-bound in this epilogue: a thread whose four pixels are all own pixels (every thread but
         // those at the edges of a shard) skips the per-pixel range tests
-        if (VARIANT == 1 && nvalid == 4 && base >= p.own_lo && base + 4 <= p.own_hi) {
+        if (VARIANT == 1 && nv[0] == 4 && base >= p.own_lo && base + 4 <= p.own_hi) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) account(idx[j], best[j], q0[j], q1[j], q2[j]);
         } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (j < nvalid && !deferred[j]) resolve(base + j, idx[j], best[j], q0[j], q1[j], q2[j], false);
+            for (int j = 0; j < PX; ++j)
+                if (valid(j) && !deferred[j]) resolve(pix(j), idx[j], best[j], q0[j], q1[j], q2[j], false);
         }
-        if (IDXW == 1) {
-            uint8_t* o = reinterpret_cast<uint8_t*>(p.idx_out) + (size_t)b * p.stride + base;
-            if (nvalid == 4) {
-                *reinterpret_cast<uint32_t*>(o) = (uint32_t)idx[0] | ((uint32_t)idx[1] << 8) | ((uint32_t)idx[2] << 16) | ((uint32_t)idx[3] << 24);
-            } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) if (j < nvalid) o[j] = (uint8_t)idx[j];
-            }
-        } else if (IDXW == 2) {
-            uint16_t* o = reinterpret_cast<uint16_t*>(p.idx_out) + (size_t)b * p.stride + base;
-            if (nvalid == 4) {
-                *reinterpret_cast<uint2*>(o) = make_uint2((uint32_t)idx[0] | ((uint32_t)idx[1] << 16), (uint32_t)idx[2] | ((uint32_t)idx[3] << 16));
-            } else {
+        for (int s = 0; s < SUB; ++s) {
+            const size_t bs = base + (size_t)s * kTilePx;
+            if (IDXW == 1) {
+                uint8_t* o = reinterpret_cast<uint8_t*>(p.idx_out) + (size_t)b * p.stride + bs;
+                if (nv[s] == 4) {
+                    *reinterpret_cast<uint32_t*>(o) = (uint32_t)idx[4 * s] | ((uint32_t)idx[4 * s + 1] << 8) | ((uint32_t)idx[4 * s + 2] << 16) | ((uint32_t)idx[4 * s + 3] << 24);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) if (j < nvalid) o[j] = (uint16_t)idx[j];
+                    for (int j = 0; j < 4; ++j) if (j < nv[s]) o[j] = (uint8_t)idx[4 * s + j];
+                }
+            } else if (IDXW == 2) {
+                uint16_t* o = reinterpret_cast<uint16_t*>(p.idx_out) + (size_t)b * p.stride + bs;
+                if (nv[s] == 4) {
+                    *reinterpret_cast<uint2*>(o) = make_uint2((uint32_t)idx[4 * s] | ((uint32_t)idx[4 * s + 1] << 16), (uint32_t)idx[4 * s + 2] | ((uint32_t)idx[4 * s + 3] << 16));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (j < nv[s]) o[j] = (uint16_t)idx[4 * s + j];
+                }
             }
         }
     }
@@ -803,14 +891,14 @@ cudaError_t launch_assign_t(const AssignParams& p, int B, int sm_count, cudaStre
         occ = lc.occ;
     }
     const long long slots = (long long)sm_count * occ;
-    const long long ntiles = (long long)((p.n + kTilePx - 1) / kTilePx);
+    const long long ntiles = (long long)((p.n + AssignGeom<VARIANT>::kTile - 1) / AssignGeom<VARIANT>::kTile);
     // CTAs per candidate (G): B*G must be a whole number of waves of the `slots` resident CTAs,
     // otherwise the last wave leaves SMs idle (first measurement: 256 CTAs on 296 slots ->
     // 20 SMs half empty).  G = slots / gcd(B, slots) is the smallest such count; it is then
-    // doubled while every CTA still gets >= 32 tiles, which shortens the ragged tail.
+    // doubled while every CTA still gets >= 32 x 1024 pixels, which shortens the ragged tail.
     auto gcd = [](long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a; };
     long long G = slots / gcd((long long)B, slots);
-    while (G * 2 * 32 <= ntiles && G * 2 * B <= slots * 16) G *= 2;
+    while (G * 2 * (32 / AssignGeom<VARIANT>::kSub) <= ntiles && G * 2 * B <= slots * 16) G *= 2;   // (32 x 1024 pixels per CTA)
     if (G > ntiles) G = ntiles;
     if (G < 1) G = 1;
     if (G > 65535) G = 65535;
