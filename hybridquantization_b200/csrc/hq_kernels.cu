@@ -373,6 +373,14 @@ __device__ __forceinline__ void exact_chunk(const float* __restrict__ s_sk, int 
     }
 }
 
+// exact sweep over every colour (the ambiguous pixels of variant 3: rare, so kept out of line): (squared distance bits, index)
+__device__ __noinline__ unsigned long long exact_all_colours(const float* __restrict__ s_sk, int skew_len, int nchunks, float x0, float x1, float x2) {
+    float bd = __int_as_float(0x7f800000);
+    int bi = 0;
+    for (int c = 0; c < nchunks; ++c) exact_chunk(s_sk, skew_len, c, x0, x1, x2, bd, bi);
+    return ((unsigned long long)(unsigned)bi << 32) | (unsigned long long)__float_as_uint(bd);
+}
+
 // VARIANT 1: running (min, index) per colour, direct (x-p)^2 form — small palettes.
 // VARIANT 2: direct form, running min per chunk of 8 colours with FMNMX3; the winning chunk is
 //            re-evaluated once per pixel to recover the index (first colour whose distance equals
@@ -515,8 +523,8 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VAR
     };
     // exact sweep over every colour (ambiguous pixels of variant 3)
     auto exact_all = [&](float x0, float x1, float x2, float& bd, int& bi) {
-        bd = INF; bi = 0;
-        for (int c = 0; c < nchunks; ++c) exact_chunk(s_sk, skew_len, c, x0, x1, x2, bd, bi);
+        const unsigned long long r = exact_all_colours(s_sk, skew_len, nchunks, x0, x1, x2);
+        bd = __uint_as_float((unsigned)r); bi = (int)(r >> 32);
     };
 
     // ---- variant 1: the feature planes of this CTA's tiles arrive through a ring of kPxStages tiles in shared memory, filled by
@@ -607,6 +615,7 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VAR
         float best[PX];  // exact squared distance of the winner
         int idx[PX];
         bool deferred[PX];
+        bool any_def = false;
 #pragma unroll
         for (int j = 0; j < PX; ++j) { best[j] = INF; idx[j] = 0; deferred[j] = false; }
 
@@ -734,27 +743,37 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VAR
                 }
             }
 #endif
-            // ---- decide: unique chunk -> exact evaluation of that chunk; else defer / exact sweep
+            // ---- decide: unique chunk -> exact evaluation of that chunk; else defer / exact sweep.
+            // Straight-line: the winning chunk of ALL the thread's pixels is evaluated exactly in one basic block (independent
+            // chains the scheduler interleaves; as a branch per pixel the 8 evaluations ran one after the other, each waiting for
+            // its own shared-memory loads); the rare ambiguous pixels are dealt with afterwards and overwrite what was computed.
+            bool amb[PX];
+            bool any_amb = false;
 #pragma unroll
             for (int j = 0; j < PX; ++j) {
-                if (valid(j)) {
-                    const float nx = fmaf(x2[j], x2[j], fmaf(x1[j], x1[j], x0[j] * x0[j]));
-                    float T = 2.01f * E + 1.0e-6f * (fabsf(sbest[j] + nx) + E);
+                const float nx = fmaf(x2[j], x2[j], fmaf(x1[j], x1[j], x0[j] * x0[j]));
+                float T = 2.01f * E + 1.0e-6f * (fabsf(sbest[j] + nx) + E);
 #if HQ_V3_BOOK
-                    // every carried value is within 2^bits ulp of the chunk minimum it stands for: if the winner lay outside the
-                    // best chunk, second <= sbest + T + rho (|m_best| + |m_winner's chunk|) would hold, both magnitudes <= (|sbest| + T)(1 + 4 rho)
-                    T += rho25 * (fabsf(sbest[j]) + T);
-                    const int cw = (int)(__float_as_uint(sbest[j]) & id_mask);
+                // every carried value is within 2^bits ulp of the chunk minimum it stands for: if the winner lay outside the
+                // best chunk, second <= sbest + T + rho (|m_best| + |m_winner's chunk|) would hold, both magnitudes <= (|sbest| + T)(1 + 4 rho)
+                T += rho25 * (fabsf(sbest[j]) + T);
+                const int cw = min((int)(__float_as_uint(sbest[j]) & id_mask), nchunks - 1);   // (a padding chunk never wins)
 #else
-                    const int cw = cidx[j];
+                const int cw = cidx[j];
 #endif
-                    if (second[j] > sbest[j] + T) {
-                        exact_chunk(s_sk, skew_len, cw, x0[j], x1[j], x2[j], best[j], idx[j]);
-                    } else {
+                amb[j] = valid(j) && !(second[j] > sbest[j] + T);
+                any_amb = any_amb || amb[j];
+                exact_chunk(s_sk, skew_len, cw, x0[j], x1[j], x2[j], best[j], idx[j]);
+            }
+            if (any_amb) {
+#pragma unroll
+                for (int j = 0; j < PX; ++j) {
+                    if (amb[j]) {
                         const unsigned slot = atomicAdd(&s_wl_n, 1u);
                         if (slot < (unsigned)kWorklistCap && pix(j) < 0xffffffffull) {
                             s_wl[slot] = (unsigned)pix(j);
                             deferred[j] = true;
+                            any_def = true;
                         } else {
                             exact_all(x0[j], x1[j], x2[j], best[j], idx[j]);  // worklist full: resolve here
                         }
@@ -790,9 +809,12 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VAR
         }
         // small palettes are instruction-bound in this epilogue: a thread whose four pixels are all own pixels (every thread but
         // those at the edges of a shard) skips the per-pixel range tests
-        if (VARIANT == 1 && nv[0] == 4 && base >= p.own_lo && base + 4 <= p.own_hi) {
+        bool all_own = !any_def;   // (variant 3: and none of them waits on the worklist)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) account(idx[j], best[j], q0[j], q1[j], q2[j]);
+        for (int s = 0; s < SUB; ++s) all_own = all_own && nv[s] == 4 && base + (size_t)s * kTilePx >= p.own_lo && base + (size_t)s * kTilePx + 4 <= p.own_hi;
+        if (VARIANT != 2 && all_own) {
+#pragma unroll
+            for (int j = 0; j < PX; ++j) account(idx[j], best[j], q0[j], q1[j], q2[j]);
         } else {
 #pragma unroll
             for (int j = 0; j < PX; ++j)
