@@ -180,6 +180,8 @@ int hq_create(int device, hq_ctx** out) {
     {
         const char* d = std::getenv("HQ_DIRECT_IO");
         c->direct_io = !(d && d[0] == '0');
+        const char* sm = std::getenv("HQ_SMALL_EVAL");   // 0: keep the two-launch latency path (A/B measurements)
+        c->small_eval = !(sm && sm[0] == '0');
     }
     {   // HQ_SC_UNFUSED=1: the S-CIELAB candidate stage as two kernels per candidate with a 7-plane intermediate (round 1; A/B runs)
         const char* u = std::getenv("HQ_SC_UNFUSED");
@@ -215,7 +217,7 @@ void hq_destroy(hq_ctx* c) {
     if (c->ev3) cudaEventDestroy(c->ev3);
     c->d_rgb.release(); c->d_flag.release(); c->d_lab.release(); c->d_unit.release(); c->d_table.release(); c->d_pal.release();
     c->d_pal_lab.release(); c->d_pal_rgb.release(); c->d_results.release(); c->d_idx.release();
-    c->d_out_rgb.release(); c->d_out_f32.release(); c->h_pal.release(); c->h_results.release(); c->h_flag.release(); c->d_export_counter.release();
+    c->d_out_rgb.release(); c->d_out_f32.release(); c->h_pal.release(); c->h_results.release(); c->h_flag.release(); c->d_export_counter.release(); c->d_results_small.release();
     c->d_sc_filters.release(); c->d_sc_opp.release(); c->d_sc_tmp.release(); c->d_sc_lab.release(); c->d_sc_tab.release(); c->d_sc_err.release();
     c->d_sc_lab2.release(); c->d_sc_map.release(); c->d_sc_rgb2.release(); c->d_sc_map8.release();
     c->pr_own.release(); c->pr_all.release(); c->d_pr_scratch.release(); c->d_big_d2.release(); c->d_big_idx.release();
@@ -558,6 +560,34 @@ int hq_eval_palettes(hq_ctx* c, const float* palettes, int B, int K, int space, 
         c->seen_key = key;
         // (small transfers only: one CTA pushing 131 KB of results over PCIe took 0.16 ms at 64 candidates x 256 colours, a DMA copy 5 us)
         e.direct = !graphable && c->direct_io && npal * sizeof(float) <= 65536 && nwords * 8 <= 32768;
+        // ONE launch (round 2): small searches (B*K <= 192 colours, K <= 32 — the plugin's defaults are 8 colours x 4 candidates) pass the
+        // palettes as a kernel parameter; every CTA converts its candidate's palette itself and the last CTA exports and re-zeroes the
+        // result words (d_results_small is only ever touched by these launches: zero between them).
+        if (e.direct && c->small_eval && !multi && !reduce && !c->profiling && c->n > 0 && K <= hq::kDirectMaxColors && (long long)B * K <= hq::kSmallPalColors &&
+            !(flags & (HQ_EVAL_PRUNE | HQ_EVAL_FORCE_DIRECT | HQ_EVAL_FORCE_CHUNKED | HQ_EVAL_FORCE_PREFILTER))) {
+            if (nwords > c->d_results_small.cap) {
+                HQ_CUDA(c, c->d_results_small.reserve(nwords > 4096 ? nwords : 4096));
+                HQ_CUDA(c, cudaMemsetAsync(c->d_results_small.p, 0, c->d_results_small.cap * 8, c->stream));
+            }
+            const unsigned long long seq = ++c->export_seq;
+            hq::AssignArgs a;
+            a.lab = c->d_lab.p; a.unit = c->d_unit.p; a.n = c->n; a.stride = c->stride;
+            a.pal_lab = nullptr; a.pal_rgb = nullptr;
+            a.B = B; a.K = K; a.space = space; a.want_sums = sums;
+            a.results = c->d_results_small.p; a.idx_out = nullptr; a.sm_count = c->sm_count;
+            a.own_lo = c->own_lo; a.own_hi = c->own_hi;
+            a.variant = 1;
+            a.tail.host_dst = c->h_results.p; a.tail.host_flag = c->h_flag.p; a.tail.seq = seq; a.tail.counter = c->d_export_counter.p;
+            a.tail.src = c->d_results_small.p; a.tail.nwords = (unsigned)nwords;
+            const cudaError_t le = hq::launch_assign_small(a, c->h_pal.p, c->whitepoint, c->stream);
+            cudaError_t we = le;
+            if (le == cudaSuccess) we = wait_flag(c->h_flag.p, seq, c->stream);
+            if (we != cudaSuccess) {
+                c->d_results_small.release();   // whatever the failed launch left behind is not reused
+                return fail(c, HQ_ERR_CUDA, "one-launch evaluation failed: %s", cudaGetErrorString(we));
+            }
+            goto unpack;
+        }
         if (e.direct) {
             // Latency path (a search iteration is four dependent stream operations; this makes it two): the palette kernel reads
             // the pinned host copy directly (UVA: pinned host memory is device-accessible) and a one-CTA kernel writes the

@@ -90,6 +90,8 @@ struct hq_ctx {
     PinBuf<unsigned long long> h_flag;      // sequence number written by export_results_kernel after the result words
     unsigned long long export_seq = 0;
     DevBuf<unsigned> d_export_counter;      // ticket counter of the scoring kernels' export tail (zero between launches)
+    DevBuf<unsigned long long> d_results_small;   // result words of the one-launch evaluations: zero between launches (the last CTA re-zeroes them)
+    bool small_eval = true;                 // HQ_SMALL_EVAL=0: never take the one-launch path
     bool direct_io = true;                  // HQ_DIRECT_IO=0: the H2D copy / D2H copy / stream wait path instead (A/B measurements)
 
     // exact pruning (hq_pruned.cu): cell-sorted copy of the own pixels, chunk table, boxes; built on first use per image

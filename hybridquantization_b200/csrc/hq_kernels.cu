@@ -18,7 +18,9 @@
 //
 // Tensor cores are deliberately not used: the inner dimension of the distance is 3.
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
+#include <type_traits>
 
 #include "hq_kernels.cuh"
 #include "hq_math.h"
@@ -332,6 +334,7 @@ struct AssignParams {
     void* idx_out;
     ExportTail tail;
     int use_tma;   // variant 1: pixel tiles staged by TMA bulk copies through a 3-stage shared-memory ring
+    int whitepoint;   // assign_small_kernel converts its palettes itself
 };
 constexpr int kPxStages = 3;   // tiles in flight per CTA (variant 1 with TMA): 3 x 12 KB
 
@@ -402,7 +405,7 @@ __device__ __noinline__ unsigned long long exact_all_colours(const float* __rest
 #ifndef HQ_V3_UNROLL
 #define HQ_V3_UNROLL 2
 #endif
-constexpr int kV3Unroll = HQ_V3_UNROLL;  // chunks per unrolled iteration of the prefilter sweep (HQ_V3_BOOK == 0)
+[[maybe_unused]] constexpr int kV3Unroll = HQ_V3_UNROLL;  // chunks per unrolled iteration of the prefilter sweep (HQ_V3_BOOK == 0)
 // Round 2: (a) 8 pixels per thread in variant 3 (two 1024-pixel sub-tiles per iteration, four packed pixel pairs): every
 // LDS.128 of a colour's coefficients now feeds 12 FFMA2 instead of 6; (b) chunk bookkeeping through the MANTISSA: the chunk
 // id replaces the low bits of the chunk minimum (one LOP3), so "best and second-best chunk" of a PAIR of chunks is
@@ -420,8 +423,39 @@ template <int VARIANT> struct AssignGeom {
     static constexpr int kSub = kPx / kPxPerThread;                      // 1024-pixel sub-tiles per iteration
     static constexpr int kTile = kTilePx * kSub;
 };
-template <int VARIANT, bool SRGB, bool SUMS, int IDXW>
-__global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VARIANT == 1 ? 3 : 2)) assign_reduce_kernel(const AssignParams p) {
+// Palettes as a KERNEL PARAMETER (the one-launch evaluation of small searches, launch_assign_small): B*K <= kSmallPalColors
+// sRGB colours travel with the launch command itself — no H2D copy, no separate palette kernel, no PCIe read from the kernel.
+// (sized in steps: the plugin's defaults, 8 colours x 4 candidates, launch with 512 bytes of parameters, not 3 KB)
+template <int NCOL> struct SmallPalettes { float v[NCOL * 4]; };   // [B][K][4] as the plugin lays them out (SWASA.java:42-50)
+
+// sRGB palette of candidate b (parameter space) -> the staged tables of variant 1, with the arithmetic of
+// palette_features_kernel (hq_srgb_to_lab = hq_linrgb_to_lab of the three decoded channels): 3K threads decode one channel
+// each (the exact pow(., 2.4) is the long pole: in parallel it costs one evaluation instead of three), K threads finish.
+// Out of line: its fp64 code must not shape the register allocation of the sweep.
+__device__ __noinline__ void stage_small_palette(const float* __restrict__ cpal, int K, int K8, int whitepoint, bool srgb, float* __restrict__ pla_f,
+                                                 float* __restrict__ pb_f, float4* __restrict__ s_lab, float* __restrict__ s_lin) {
+    const int tid = threadIdx.x;
+    if (tid < 3 * K) s_lin[tid] = hq_srgb_decode(cpal[(tid / 3) * 4 + tid % 3]);
+    __syncthreads();
+    if (tid < K8) {
+        const int k = tid;
+        float f0 = kFar, f1 = kFar, f2 = kFar;
+        float4 lab = make_float4(kFar, kFar, kFar, 0.f);
+        if (k < K) {
+            const hq_float3 v = hq_linrgb_to_lab(s_lin[3 * k], s_lin[3 * k + 1], s_lin[3 * k + 2], hq_make_white(whitepoint));
+            lab = make_float4(v.x, v.y, v.z, 0.f);
+            if (srgb) { f0 = cpal[4 * k]; f1 = cpal[4 * k + 1]; f2 = cpal[4 * k + 2]; }
+            else { f0 = v.x; f1 = v.y; f2 = v.z; }
+        }
+        pla_f[(k >> 1) * 4 + (k & 1)] = f0;
+        pla_f[(k >> 1) * 4 + 2 + (k & 1)] = f1;
+        pb_f[k] = f2;
+        if (srgb) s_lab[k] = lab;
+    }
+}
+
+template <int VARIANT, bool SRGB, bool SUMS, int IDXW, bool FUSED>
+__device__ __forceinline__ void assign_body(const AssignParams& p, const float* __restrict__ cpal) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = p.K, K8 = p.K8;
     const int tid = threadIdx.x;
@@ -441,7 +475,27 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VAR
     if (tid < 4) s_bound[tid] = 0u;
     if (tid == 0) s_wl_n = 0u;
     __syncthreads();
-    {
+    // one-launch evaluation: the first tile's pixels are requested before the palette is converted (the exact pow of the sRGB decode
+    // is a ~1 us dependent chain; the loads fly meanwhile)
+    float4 pf0 = make_float4(0.f, 0.f, 0.f, 0.f), pf1 = pf0, pf2 = pf0;
+    bool pf_ok = false;
+    if (FUSED) {
+        const size_t bs = (size_t)blockIdx.y * kTilePx + (size_t)kPxPerThread * tid;
+        if (bs + 4 <= p.n) {
+            pf0 = __ldg(reinterpret_cast<const float4*>(p.feat + bs));
+            pf1 = __ldg(reinterpret_cast<const float4*>(p.feat + p.stride + bs));
+            pf2 = __ldg(reinterpret_cast<const float4*>(p.feat + 2 * p.stride + bs));
+            pf_ok = true;
+        }
+    }
+    if (FUSED) {
+        __shared__ float s_lin[3 * kDirectMaxColors];
+        stage_small_palette(cpal + (size_t)b * K * 4, K, K8, p.whitepoint, SRGB, reinterpret_cast<float*>(s_pla), reinterpret_cast<float*>(s_pb), s_lab, s_lin);
+        for (int k = tid; k < K8; k += kThreads) {
+            s_cnt[k] = 0u;
+            if (SUMS) { s_sum[3 * k] = 0ull; s_sum[3 * k + 1] = 0ull; s_sum[3 * k + 2] = 0ull; }
+        }
+    } else {
         const float4* gf = p.pal_feat + (size_t)b * K8;
         const float4* gl = p.pal_lab + (size_t)b * K8;
         float* pla_f = reinterpret_cast<float*>(s_pla);
@@ -559,6 +613,7 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VAR
     const int id_bits = nchunks2 > 1 ? 32 - __clz(nchunks2 - 1) : 1;
     const unsigned id_mask = (1u << id_bits) - 1u;
     const float rho25 = 2.5f * __uint_as_float((unsigned)(127 + id_bits - 23) << 23);   // 2.5 * 2^(bits-23)
+    (void)id_mask; (void)rho25;
 
     size_t it = 0;
     for (size_t tile = blockIdx.y; tile < ntiles; tile += gridDim.y, ++it) {
@@ -593,9 +648,10 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VAR
             for (int s = 0; s < SUB; ++s) {
                 const size_t bs = base + (size_t)s * kTilePx;
                 if (bs + 4 <= n) {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(f0 + bs));
-                    const float4 c = __ldg(reinterpret_cast<const float4*>(f1 + bs));
-                    const float4 d = __ldg(reinterpret_cast<const float4*>(f2 + bs));
+                    const bool pre = FUSED && it == 0 && pf_ok;
+                    const float4 a = pre ? pf0 : __ldg(reinterpret_cast<const float4*>(f0 + bs));
+                    const float4 c = pre ? pf1 : __ldg(reinterpret_cast<const float4*>(f1 + bs));
+                    const float4 d = pre ? pf2 : __ldg(reinterpret_cast<const float4*>(f2 + bs));
                     x0[4 * s] = a.x; x0[4 * s + 1] = a.y; x0[4 * s + 2] = a.z; x0[4 * s + 3] = a.w;
                     x1[4 * s] = c.x; x1[4 * s + 1] = c.y; x1[4 * s + 2] = c.z; x1[4 * s + 3] = c.w;
                     x2[4 * s] = d.x; x2[4 * s + 1] = d.y; x2[4 * s + 2] = d.z; x2[4 * s + 3] = d.w;
@@ -879,7 +935,18 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VAR
             }
         }
     }
-    if (VARIANT == 1) export_tail(p.tail, gridDim.x * gridDim.y);
+    if (VARIANT == 1) export_tail(p.tail, gridDim.x * gridDim.y, FUSED);
+}
+
+template <int VARIANT, bool SRGB, bool SUMS, int IDXW>
+__global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VARIANT == 1 ? 3 : 2)) assign_reduce_kernel(const __grid_constant__ AssignParams p) {
+    assign_body<VARIANT, SRGB, SUMS, IDXW, false>(p, nullptr);
+}
+// one launch per evaluation: variant 1 with the palettes in parameter space; the last CTA exports the result words to pinned
+// host memory and leaves them ZERO for the next launch (no clearing pass)
+template <bool SRGB, bool SUMS, int NCOL>
+__global__ void __launch_bounds__(kThreads, 3) assign_small_kernel(const __grid_constant__ AssignParams p, const __grid_constant__ SmallPalettes<NCOL> pal) {
+    assign_body<1, SRGB, SUMS, 0, true>(p, pal.v);
 }
 
 // per (kernel instantiation, device), PROCESS-wide: cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the function on
@@ -926,6 +993,46 @@ cudaError_t launch_assign_t(const AssignParams& p, int B, int sm_count, cudaStre
     if (G > 65535) G = 65535;
     const dim3 grid((unsigned)B, (unsigned)G);
     kern<<<grid, kThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <bool SRGB, bool SUMS, int NCOL>
+cudaError_t launch_small_t(const AssignParams& p, const float* h_palettes, int B, int sm_count, cudaStream_t stream) {
+    auto kern = assign_small_kernel<SRGB, SUMS, NCOL>;
+    SmallPalettes<NCOL> pal;
+    std::memcpy(pal.v, h_palettes, (size_t)B * p.K * 4 * sizeof(float));
+    const size_t smem = AssignSmem<1, SRGB, SUMS>(p.K8).total;
+    static LaunchCache cache[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    int occ;
+    {
+        LaunchCache& lc = cache[dev & 63];
+        std::lock_guard<std::mutex> lock(lc.mu);
+        if (smem > lc.attr) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            lc.attr = smem;
+        }
+        if (lc.smem != smem) {
+            int o = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, smem);
+            if (e != cudaSuccess) return e;
+            lc.smem = smem; lc.occ = o < 1 ? 1 : o;
+        }
+        occ = lc.occ;
+    }
+    // a latency-bound launch: ONE wave at most, every CTA with at least two tiles (fewer CTAs = fewer result atomics and a
+    // shorter ticket queue in front of the exporting CTA)
+    const long long slots = (long long)sm_count * occ;
+    const long long ntiles = (long long)((p.n + kTilePx - 1) / kTilePx);
+    long long G = slots / B;
+    if (G > (ntiles + 1) / 2) G = (ntiles + 1) / 2;
+    if (G < 1) G = 1;
+    if (G > 65535) G = 65535;
+    const dim3 grid((unsigned)B, (unsigned)G);
+    kern<<<grid, kThreads, smem, stream>>>(p, pal);
     return cudaGetLastError();
 }
 
@@ -1068,6 +1175,7 @@ cudaError_t launch_assign_reduce(const AssignArgs& a, cudaStream_t stream) {
     p.results = a.results;
     p.idx_out = a.idx_out;
     p.tail = a.tail;
+    p.whitepoint = 0;
     {   // HQ_V1_TMA=1: the small-palette kernel stages its pixel tiles with TMA bulk copies + mbarriers instead of LDG.128.
         // OFF by default — measured on the B200 (tools/smallk_bench.py, profiles/r02/smallk_tma_ab.txt): the kernel is bound by
         // instruction issue, not by exposed load latency, and the ring costs instructions: K=8, 4K image, one candidate 41.7 -> 43.0 us,
@@ -1088,6 +1196,36 @@ cudaError_t launch_assign_reduce(const AssignArgs& a, cudaStream_t stream) {
     if (variant == 1) return launch_assign_v<1>(p, a.B, a.space == 1, a.want_sums, idxw, a.sm_count, stream);
     if (variant == 2) return launch_assign_v<2>(p, a.B, a.space == 1, a.want_sums, idxw, a.sm_count, stream);
     return launch_assign_v<3>(p, a.B, a.space == 1, a.want_sums, idxw, a.sm_count, stream);
+}
+
+cudaError_t launch_assign_small(const AssignArgs& a, const float* h_palettes, int whitepoint, cudaStream_t stream) {
+    if (a.B <= 0 || a.K <= 0 || a.K > kDirectMaxColors || (long long)a.B * a.K > kSmallPalColors || a.idx_out || !a.tail.host_dst || !h_palettes) return cudaErrorInvalidValue;
+    if (a.space == 1 && a.unit == nullptr) return cudaErrorInvalidValue;
+    if (a.n == 0) return cudaErrorInvalidValue;   // (nothing would export: the caller handles an empty image)
+    AssignParams p;
+    p.feat = a.space == 1 ? a.unit : a.lab;
+    p.lab = a.lab;
+    p.n = a.n; p.stride = a.stride;
+    p.pal_feat = nullptr; p.pal_lab = nullptr;
+    p.K = a.K; p.K8 = padded_colors(a.K);
+    p.words = result_words(a.K, a.want_sums);
+    p.results = a.results;
+    p.idx_out = nullptr;
+    p.tail = a.tail;
+    p.use_tma = 0;
+    p.whitepoint = whitepoint;
+    p.xmax0 = p.xmax1 = p.xmax2 = 0.f;
+    p.own_lo = a.own_lo; p.own_hi = a.own_hi == kAllPixels ? a.n : a.own_hi;
+    const int ncol = a.B * a.K;
+    auto go = [&](auto srgb, auto sums) -> cudaError_t {
+        constexpr bool S = decltype(srgb)::value, U = decltype(sums)::value;
+        if (ncol <= 32) return launch_small_t<S, U, 32>(p, h_palettes, a.B, a.sm_count, stream);
+        if (ncol <= 64) return launch_small_t<S, U, 64>(p, h_palettes, a.B, a.sm_count, stream);
+        if (ncol <= 128) return launch_small_t<S, U, 128>(p, h_palettes, a.B, a.sm_count, stream);
+        return launch_small_t<S, U, kSmallPalColors>(p, h_palettes, a.B, a.sm_count, stream);
+    };
+    if (a.space == 1) return a.want_sums ? go(std::true_type{}, std::true_type{}) : go(std::true_type{}, std::false_type{});
+    return a.want_sums ? go(std::false_type{}, std::true_type{}) : go(std::false_type{}, std::false_type{});
 }
 
 cudaError_t launch_apply_palette(const void* d_idx, bool idx16, size_t n, const float* d_palette, int K,

@@ -53,7 +53,8 @@ struct ExportTail {
 };
 #ifdef __CUDACC__
 // every thread of every CTA calls this after its last result atomic
-__device__ __forceinline__ void export_tail(const ExportTail& x, unsigned total_ctas) {
+// zero_after: the result words are left zero for the next launch (the one-launch evaluation has no clearing pass)
+__device__ __forceinline__ void export_tail(const ExportTail& x, unsigned total_ctas, bool zero_after = false) {
     if (x.host_dst == nullptr) return;
     __shared__ unsigned s_ticket;
     __threadfence();     // this thread's result atomics are performed device-wide before the ticket is taken
@@ -62,7 +63,10 @@ __device__ __forceinline__ void export_tail(const ExportTail& x, unsigned total_
     __syncthreads();
     if (s_ticket != total_ctas - 1) return;
     __threadfence();
-    for (unsigned i = threadIdx.x; i < x.nwords; i += blockDim.x) x.host_dst[i] = __ldcg(x.src + i);
+    for (unsigned i = threadIdx.x; i < x.nwords; i += blockDim.x) {
+        x.host_dst[i] = __ldcg(x.src + i);
+        if (zero_after) const_cast<unsigned long long*>(x.src)[i] = 0ull;
+    }
     __threadfence_system();   // the words are visible to the host before the sequence number is
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -91,6 +95,12 @@ struct AssignArgs {
 };
 constexpr int kDirectMaxColors = 32;  // auto picks variant 1 up to here (measured crossover, hq_kernels.cu)
 cudaError_t launch_assign_reduce(const AssignArgs& a, cudaStream_t stream);
+// ONE launch per evaluation for the searches that are latency-bound (the plugin's defaults: 8 colours, population 4): B * K <=
+// kSmallPalColors sRGB colours travel as a kernel parameter, every CTA converts its candidate's palette itself, the last CTA
+// exports the result words (a.tail, required) and zeroes them again.  h_palettes: [B][K][4] host floats (validated by the
+// caller); a.results must be zero on entry and is zero again when the launch completes; K <= kDirectMaxColors, no index image.
+constexpr int kSmallPalColors = 192;
+cudaError_t launch_assign_small(const AssignArgs& a, const float* h_palettes, int whitepoint, cudaStream_t stream);
 
 // ---- exact assignment with geometric pruning (hq_pruned.cu): the own pixels are counting-sorted once per image by a
 // coarse CIELAB cell into chunks of <= kPrunedChunkPx pixels with exact bounding boxes; per (chunk, candidate) only

@@ -318,7 +318,10 @@ sc_vpass21_kernel(const float* __restrict__ tmp, int w, int h, size_t stride, co
 #ifndef HQ_SC_HHALVES
 #define HQ_SC_HHALVES 2   // 2: the H task is 4 outputs + a window shift, looped twice; 1: 8 outputs fully unrolled
 #endif
-constexpr int kSW = 128, kSBand = 8, kSThreads = 256;
+#ifndef HQ_SC_SW
+#define HQ_SC_SW 128      // columns per strip (128: 2 CTAs of 256 threads per SM; 256: 1 CTA of 512 threads, half the horizontal halo overhead)
+#endif
+constexpr int kSW = HQ_SC_SW, kSBand = 8, kSThreads = 2 * kSW, kSCtasPerSm = 256 / kSW;
 constexpr int kSHOut = 8;                                              // outputs per H task
 constexpr int kSHPer = kSHOut / HQ_SC_HHALVES;                         // ... per unrolled pass
 constexpr int kSVUnroll = HQ_SC_VUNROLL;
@@ -330,8 +333,62 @@ template <int ID> __device__ __forceinline__ void named_bar_arrive_i(int count) 
 template <int ID0> __device__ __forceinline__ void named_bar_sync(int which, int count) { if (which) named_bar_sync_i<ID0 + 1>(count); else named_bar_sync_i<ID0>(count); }
 template <int ID0> __device__ __forceinline__ void named_bar_arrive(int which, int count) { if (which) named_bar_arrive_i<ID0 + 1>(count); else named_bar_arrive_i<ID0>(count); }
 
+// Opp2LAB (cl:124-145) of one pixel in STRAIGHT-LINE form.  hq_cl_opp_to_lab_white branches nine times per pixel (the range
+// check of each constant division, the dark-value segment and the fp64 decision of each cube root), and every one of those
+// branches cost the V warps a BSSY / BRA / BSYNC triple and a basic-block boundary the scheduler cannot move loads across
+// (ncu, round 2: 25 control instructions per pixel, 0.86 stall cycles per issue waiting for instructions).  Here the common
+// case of every branch is computed unconditionally — the same operations in the same order, so the same bits — and ONE flag
+// collects "some value needs another branch" (a value outside the constant division's verified range, a value on the linear
+// segment, a cube root the fp32 path cannot decide): such a pixel is redone by the reference routine, out of line.
+#ifndef HQ_SC_STRAIGHT
+#define HQ_SC_STRAIGHT 1
+#endif
+__device__ __noinline__ hq_float3 sc_opp_to_lab_general(float o0, float o1, float o2, hq_white w) { return hq_cl_opp_to_lab_white(o0, o1, o2, w); }
+__device__ __forceinline__ float sc_cbrt_common(float t, bool& other) {   // hq_cbrtf_fast up to its decision
+    float lg, y0, rq;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(t));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(__fmul_rn(lg, 0x1.555556p-2f)));
+    const float q = __fmul_rn(y0, y0);
+    const float nql = __fmaf_rn(-y0, y0, q);
+    const float p = __fmul_rn(q, y0);
+    const float npl = __fmaf_rn(q, -y0, p);
+    const float r = __fmaf_rn(nql, y0, __fadd_rn(__fsub_rn(t, p), npl));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rq) : "f"(q));
+    const float d = __fmul_rn(__fmul_rn(r, 0x1.555556p-2f), rq);
+    const float s_lo = __fadd_rn(y0, __fmaf_rn(y0, -HQ_CBRT_ETA, d));
+    const float s_hi = __fadd_rn(y0, __fmaf_rn(y0, HQ_CBRT_ETA, d));
+    other = other || !(s_lo == s_hi) || !(t > HQ_LABDELTA3);   // (a NaN from a negative t lands here too)
+    return s_lo;
+}
+__device__ __forceinline__ float sc_div_const_common(float x, float c, float rc, bool& other) {   // hq_div_const inside its verified range
+    const uint32_t ax = __float_as_uint(x) & 0x7fffffffu;
+    other = other || !(ax - 0x21800000u <= 0x40800000u - 0x21800000u);
+    const float q0 = __fmul_rn(x, rc);
+    const float rem = __fmaf_rn(-q0, c, x);
+    return __fmaf_rn(rem, rc, q0);
+}
+__device__ __forceinline__ hq_float3 sc_opp_to_lab_straight(float o0, float o1, float o2, const hq_white& w) {
+#if HQ_SC_STRAIGHT
+    const float X = hq_cl_dot3(0.624045f, -1.87044f, -0.155304f, o0, o1, o2);
+    const float Y = hq_cl_dot3(1.36606f, 0.931563f, 0.433903f, o0, o1, o2);
+    const float Z = hq_cl_dot3(1.5013f, 1.41761f, 2.53307f, o0, o1, o2);
+    bool other = false;
+    const float fx = sc_cbrt_common(sc_div_const_common(X, w.x, w.rx, other), other);
+    const float fy = sc_cbrt_common(Y, other);
+    const float fz = sc_cbrt_common(sc_div_const_common(Z, w.z, w.rz, other), other);
+    hq_float3 lab;
+    lab.x = HQ_FSUB(HQ_FMUL(116.0f, fy), 16.0f);
+    lab.y = HQ_FMUL(500.0f, HQ_FSUB(fx, fy));
+    lab.z = HQ_FMUL(200.0f, HQ_FSUB(fy, fz));
+    if (other) lab = sc_opp_to_lab_general(o0, o1, o2, w);
+    return lab;
+#else
+    return hq_cl_opp_to_lab_white(o0, o1, o2, w);
+#endif
+}
+
 template <typename IdxT>
-__global__ void __launch_bounds__(kSThreads, 2)
+__global__ void __launch_bounds__(kSThreads, kSCtasPerSm)
 sc_candidate_strip21_kernel(const IdxT* __restrict__ idx, const float4* __restrict__ tab, int K, int w, int h, size_t stride, int seg_rows,
                             const __grid_constant__ Filt21 f, hq_white white, ScRows rows, const float* __restrict__ lab_orig,
                             unsigned long long* __restrict__ err_out) {
@@ -449,11 +506,20 @@ sc_candidate_strip21_kernel(const IdxT* __restrict__ idx, const float4* __restri
                         a[0] = HQ_FFMA(t3, f.v[7 * kT + t], a[0]);
                     }
                     const int y = vb + r0 + p - kHalf;            // completed: tap 20 was the last
+#if HQ_SC_STRAIGHT
+                    {   // rows outside the segment are computed like the others and dropped by a select (no divergence, no branch)
+                        const float* a = A[kT + kSVUnroll - 2 - p];
+                        const hq_float3 lab = sc_opp_to_lab_straight(a[0], a[1], a[2], white);
+                        const long long e = hq_to_fx(HQ_FSQRT(hq_dist2(lo[p][0], lo[p][1], lo[p][2], lab.x, lab.y, lab.z)));
+                        fx += (y >= ya && y < yb) ? e : 0ll;
+                    }
+#else
                     if (y >= ya && y < yb) {
                         const float* a = A[kT + kSVUnroll - 2 - p];
                         const hq_float3 lab = hq_cl_opp_to_lab_white(a[0], a[1], a[2], white);
                         fx += hq_to_fx(HQ_FSQRT(hq_dist2(lo[p][0], lo[p][1], lo[p][2], lab.x, lab.y, lab.z)));
                     }
+#endif
                 }
                 // kSVUnroll rows further every pending output's tap has grown by as much: slot j -> j + kSVUnroll, fresh outputs enter below
 #pragma unroll
@@ -699,7 +765,7 @@ cudaError_t launch_sc_candidates_fused(const void* d_idx, bool idx16, const floa
     const int strips = (w + kSW - 1) / kSW;
     // rows per segment: every segment start costs 20 extra horizontally filtered rows, so segments are as long as they can
     // be while the grid still holds >= 2.5 waves of the resident CTAs (2 per SM)
-    const long long slots = (long long)(sm_count > 0 ? sm_count : 148) * 2;
+    const long long slots = (long long)(sm_count > 0 ? sm_count : 148) * kSCtasPerSm;
     int seg_rows = 64;
     for (int cand = 1024; cand >= 64; cand = cand * 3 / 4) {
         const long long nseg = (rows.y_count + cand - 1) / cand;

@@ -10,7 +10,8 @@ import time
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 
-CASES = {"C1_512x512_k16_p4_i5000": (512, 512, 16, 4, 5000, True), "C2_1080p_k256_p4_i1000": (1920, 1080, 256, 4, 1000, True),
+CASES = {"defaults_512x512_k8_p4_i5000": (512, 512, 8, 4, 5000, True), "defaults_1080p_k8_p4_i2000": (1920, 1080, 8, 4, 2000, True),
+         "C1_512x512_k16_p4_i5000": (512, 512, 16, 4, 5000, True), "C2_1080p_k256_p4_i1000": (1920, 1080, 256, 4, 1000, True),
          "1080p_k32_p4_i1000": (1920, 1080, 32, 4, 1000, True), "C3_4k_k256_p64_i50": (3840, 2160, 256, 64, 50, False)}
 
 
@@ -37,7 +38,8 @@ if __name__ == "__main__":
     else:
         res = {}
         for rep in range(2):
-            for mode in ("1", "0"):
-                r = subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, HQ_DIRECT_IO=mode), capture_output=True, text=True, check=True)
-                res[f"direct_io={mode} run{rep}"] = json.loads(r.stdout.strip().splitlines()[-1])
+            # one launch per evaluation (round 2) / two launches with direct host I/O (round 1) / copies + stream wait
+            for name, env in (("one_launch", {}), ("two_launches_direct_io", {"HQ_SMALL_EVAL": "0"}), ("copies", {"HQ_SMALL_EVAL": "0", "HQ_DIRECT_IO": "0"})):
+                r = subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, **env), capture_output=True, text=True, check=True)
+                res[f"{name} run{rep}"] = json.loads(r.stdout.strip().splitlines()[-1])
         print(json.dumps(res, indent=1))

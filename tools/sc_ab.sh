@@ -1,4 +1,8 @@
-for v in "" _v8 _h1 _v8h1; do
+#!/bin/bash
+# tools/sc_ab.sh [variant suffixes...] — tools/sc_bench.py (filter stage + assignment, 4K, K=256) for each build
+# hybridquantization_b200/libhq_b200<suffix>.so ("default" = the default build)
+for v in "$@"; do
+  [ "$v" = "default" ] && v=""
   echo "== variant [$v]"
   HQ_B200_LIB=$PWD/hybridquantization_b200/libhq_b200$v.so timeout 300 python tools/sc_bench.py --modes 0 2>&1 | python -c "
 import json,sys
