@@ -338,7 +338,13 @@ struct AssignParams {
 };
 constexpr int kPxStages = 3;   // tiles in flight per CTA (variant 1 with TMA): 3 x 12 KB
 
-constexpr int kWorklistCap = 1024;  // ambiguous pixels deferred per CTA (variant 3)
+// Ambiguous pixels deferred per CTA (variant 3) and the most pixels a CTA of that variant is given: ~0.2 % of the pixels are
+// ambiguous at K = 256 (0.7 % at K = 1,024, where the chunk id takes 7 mantissa bits), and an entry that finds the list full is
+// resolved on the spot by ONE lane while 31 wait.  Round 1 sized the grid by waves alone: a CTA of a 64 MP image held 900 k pixels,
+// overflowed its 1,024 entries and the 64 MP runs sat 1.5 points below the 4K ones; so did K = 1,024 at 64 candidates per launch.
+// (Per-warp lists drained inside the tile loop were measured too: no overflow at any size, but 2.5 % slower at 4K.)
+constexpr int kWorklistCap = 2048;
+constexpr long long kV3MaxPxPerCta = 128 * 1024;
 #ifndef HQ_PREFILTER_SCALAR
 #define HQ_PREFILTER_SCALAR 0  // 1: scalar FFMA sweep instead of packed FFMA2 (experiment)
 #endif
@@ -988,6 +994,11 @@ cudaError_t launch_assign_t(const AssignParams& p, int B, int sm_count, cudaStre
     auto gcd = [](long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a; };
     long long G = slots / gcd((long long)B, slots);
     while (G * 2 * (32 / AssignGeom<VARIANT>::kSub) <= ntiles && G * 2 * B <= slots * 16) G *= 2;   // (32 x 1024 pixels per CTA)
+    if (VARIANT == 3) {   // bound the pixels per CTA (worklist capacity, above), in whole waves
+        const long long unit = slots / gcd((long long)B, slots);
+        const long long need = ((long long)p.n + kV3MaxPxPerCta - 1) / kV3MaxPxPerCta;
+        if (G < need) G = (need + unit - 1) / unit * unit;
+    }
     if (G > ntiles) G = ntiles;
     if (G < 1) G = 1;
     if (G > 65535) G = 65535;

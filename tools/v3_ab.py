@@ -34,7 +34,7 @@ def main():
     d_img = torch.from_numpy(synth.synth_image_rows(w, h, synth.SEED_BASE + 3, 0, h)).to(dev)
     be.setImageDevice(d_img.data_ptr(), w, h, stream=st.cuda_stream)
     out = {"lib": os.environ.get("HQ_B200_LIB", "default"), "fp32_tflops_peak": p_fp32, "rows": []}
-    for K, B in ((64, 64), (128, 64), (256, 64), (512, 32), (1024, 16), (72, 8), (40, 8)):
+    for K, B in ((64, 64), (128, 64), (256, 64), (512, 32), (1024, 16), (1024, 64), (72, 8), (40, 8)):
         pal = torch.from_numpy(synth.synth_palettes(B, K)).to(dev)
         res = torch.zeros((B, be.resultWords(K, 0)), dtype=torch.int64, device=dev)
         fn = lambda: be.evalPalettesDevice(pal.data_ptr(), B, K, res.data_ptr(), 0, EVAL_FORCE_PREFILTER, st.cuda_stream)
