@@ -1043,26 +1043,37 @@ int sc_eval_enqueue(hq_ctx* m, const float* h_pal, int B, int K, int space) {
     HQ_CUDA(m, m->d_pal.reserve(npal));
     HQ_CUDA(m, m->d_sc_err.reserve(B));
     HQ_CUDA(m, m->d_sc_tab.reserve((size_t)B * K));
-    HQ_CUDA(m, m->d_idx.reserve((size_t)B * (m->stride ? m->stride : 1) * (idx16 ? 2 : 1)));
-    HQ_CUDA(m, cudaMemcpyAsync(m->d_pal.p, h_pal, npal * sizeof(float), cudaMemcpyHostToDevice, m->stream));
-    // 1. assignment (quantizeAndConvertToOpp's argmin, cl:178-193): indices + counts for every candidate
-    //    (exact pruned kernel where it pays: same indices and counts)
+    // Candidates go through assignment and filter stage in SUB-BATCHES whose index images stay in L2 (126 MB): with all 16
+    // candidates of a 4K population in flight (133 MB of indices) the pruned kernel's scattered 1-byte index stores turned into
+    // partial-sector DRAM writes — 0.338 ms per candidate against 0.284 ms at four (profiles/r02).
+    const size_t idx_bytes = (m->stride ? m->stride : 1) * (idx16 ? 2 : 1);
     const bool prune_idx = K > HQ_MAX_COLORS || m->prune_mode == HQ_PRUNE_ON || (m->prune_mode == HQ_PRUNE_AUTO && K >= 32 && m->n >= 65536);
-    rc = eval_device(m, m->d_pal.p, B, K, space, prune_idx ? HQ_EVAL_PRUNE : 0, m->d_results.p, m->d_idx.p, m->stream); if (rc) return rc;
-    // 2. the K opponent colours each quantised image is made of (cl:194-198)
-    HQ_CUDA(m, hq::launch_sc_palette_opp(m->d_pal.p, B * K, m->d_sc_tab.p, m->stream));
+    int bs = prune_idx ? (int)(((size_t)40 << 20) / idx_bytes) : B;   // (the exhaustive kernel stores its indices coalesced and likes large batches)
+    bs = bs < 1 ? 1 : (bs > B ? B : bs);
+    HQ_CUDA(m, m->d_idx.reserve((size_t)bs * idx_bytes));
+    HQ_CUDA(m, cudaMemcpyAsync(m->d_pal.p, h_pal, npal * sizeof(float), cudaMemcpyHostToDevice, m->stream));
     HQ_CUDA(m, cudaMemsetAsync(m->d_sc_err.p, 0, (size_t)B * 8, m->stream));
-    // 3. per candidate: separable filters, Opp2LAB, CIE76 against the original, fixed-point sum
-    cudaError_t fe = (m->sc_generic || m->sc_unfused || de94) ? cudaErrorNotSupported   // (the fused kernel is CIE76 only)
-                     : hq::launch_sc_candidates_fused(m->d_idx.p, idx16, m->d_sc_tab.p, K, B, m->width, m->rows, m->stride, m->sc_block.data(), m->sc_taps,
-                                                      m->whitepoint, sc_rows(m), m->d_sc_lab.p, m->d_sc_err.p, m->sm_count, m->stream);
-    if (fe != cudaSuccess && fe != cudaErrorNotSupported) return fail(m, HQ_ERR_CUDA, "fused S-CIELAB kernel launch failed: %s", cudaGetErrorString(fe));
-    if (fe == cudaErrorNotSupported) HQ_CUDA(m, m->d_sc_tmp.reserve(7 * m->stride));
-    for (int b = 0; b < B && fe == cudaErrorNotSupported; ++b) {   // other tap counts, K > 1024: two kernels per candidate
-        const uint8_t* idx_b = m->d_idx.p + (size_t)b * m->stride * (idx16 ? 2 : 1);
-        HQ_CUDA(m, hq::launch_sc_candidate(idx_b, idx16, m->d_sc_tab.p + (size_t)b * K, m->width, m->rows, m->stride, m->d_sc_filters.p,
-                                           m->sc_generic ? nullptr : m->sc_block.data(), m->sc_taps, m->whitepoint, sc_rows(m), m->d_sc_tmp.p,
-                                           m->d_sc_lab.p, m->d_sc_err.p + b, m->stream, m->delta_e, m->d_results.p + nwords + b));
+    // the K opponent colours each quantised image is made of (cl:194-198)
+    HQ_CUDA(m, hq::launch_sc_palette_opp(m->d_pal.p, B * K, m->d_sc_tab.p, m->stream));
+    bool tmp_reserved = false;
+    for (int b0 = 0; b0 < B; b0 += bs) {
+        const int nb = B - b0 < bs ? B - b0 : bs;
+        // 1. assignment (quantizeAndConvertToOpp's argmin, cl:178-193): indices + counts for every candidate of the sub-batch
+        //    (exact pruned kernel where it pays: same indices and counts)
+        rc = eval_device(m, m->d_pal.p + (size_t)b0 * K * 4, nb, K, space, prune_idx ? HQ_EVAL_PRUNE : 0, m->d_results.p + (size_t)b0 * words, m->d_idx.p, m->stream);
+        if (rc) return rc;
+        // 2. per candidate: separable filters, Opp2LAB, CIE76 against the original, fixed-point sum
+        cudaError_t fe = (m->sc_generic || m->sc_unfused || de94) ? cudaErrorNotSupported   // (the fused kernel is CIE76 only)
+                         : hq::launch_sc_candidates_fused(m->d_idx.p, idx16, m->d_sc_tab.p + (size_t)b0 * K, K, nb, m->width, m->rows, m->stride, m->sc_block.data(),
+                                                          m->sc_taps, m->whitepoint, sc_rows(m), m->d_sc_lab.p, m->d_sc_err.p + b0, m->sm_count, m->stream);
+        if (fe != cudaSuccess && fe != cudaErrorNotSupported) return fail(m, HQ_ERR_CUDA, "fused S-CIELAB kernel launch failed: %s", cudaGetErrorString(fe));
+        if (fe == cudaErrorNotSupported && !tmp_reserved) { HQ_CUDA(m, m->d_sc_tmp.reserve(7 * m->stride)); tmp_reserved = true; }
+        for (int b = 0; b < nb && fe == cudaErrorNotSupported; ++b) {   // other tap counts, K > 1024: two kernels per candidate
+            const uint8_t* idx_b = m->d_idx.p + (size_t)b * idx_bytes;
+            HQ_CUDA(m, hq::launch_sc_candidate(idx_b, idx16, m->d_sc_tab.p + (size_t)(b0 + b) * K, m->width, m->rows, m->stride, m->d_sc_filters.p,
+                                               m->sc_generic ? nullptr : m->sc_block.data(), m->sc_taps, m->whitepoint, sc_rows(m), m->d_sc_tmp.p,
+                                               m->d_sc_lab.p, m->d_sc_err.p + b0 + b, m->stream, m->delta_e, m->d_results.p + nwords + b0 + b));
+        }
     }
     // word 0 of every candidate <- the S-CIELAB error sum, so that one all-reduce covers error and counts
     HQ_CUDA(m, cudaMemcpy2DAsync(m->d_results.p, (size_t)words * 8, m->d_sc_err.p, 8, 8, (size_t)B, cudaMemcpyDeviceToDevice, m->stream));
