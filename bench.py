@@ -310,9 +310,9 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
     import torch
     import torch.distributed as dist
 
-    from hybridquantization_b200 import (EVAL_FORCE_CHUNKED, EVAL_FORCE_DIRECT, EVAL_FORCE_PREFILTER, EVAL_PRUNE, PRUNE_OFF, SPACE_SRGB, SWASA,
+    from hybridquantization_b200 import (EVAL_ALLREDUCE, EVAL_FORCE_CHUNKED, EVAL_FORCE_DIRECT, EVAL_FORCE_PREFILTER, EVAL_PRUNE, PRUNE_OFF, SPACE_SRGB, SWASA,
                                          ImageManipulation, build, synth)
-    from hybridquantization_b200.dist import install_native_nccl, row_shard, row_shard_with_halo
+    from hybridquantization_b200.dist import close_peer_exchange, install_native_nccl, row_shard, row_shard_with_halo
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
@@ -362,9 +362,9 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
         nwords = d_res.numel()
 
         def step():
-            ctx.evalPalettesDevice(d_pal.data_ptr(), Bn, Kn, d_res.data_ptr(), a.space, fl, stream)
-            if world > 1:
-                ctx.commAllreduce(d_res.data_ptr(), nwords, stream)
+            # scoring + exchange in ONE library call: over NVLink peer memory the exporting CTA of the scoring kernel does the
+            # all-reduce itself (small payloads), else ncclAllReduce follows on the same stream
+            ctx.evalPalettesDevice(d_pal.data_ptr(), Bn, Kn, d_res.data_ptr(), a.space, fl | (EVAL_ALLREDUCE if world > 1 else 0), stream)
 
         for _ in range(warmup):
             flush.fill_(1)
@@ -470,8 +470,17 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         parity = {"candidates": PB, "search_iterations": PIT, "same_on_all_ranks": bool(same.item()),
                   "pruned_equals_exhaustive": all(np.array_equal(got[k], got_pr[k]) for k in ("err_fx", "counts", "sums_fx")),
-                  "exchange": f"ncclAllReduce(int64, sum) on libhq_b200's own communicator (hq_comm_init_rank), NCCL {comm['nccl_version']}, "
-                              f"{comm['size']} ranks; torch.distributed only shipped the 128 id bytes"}
+                  "exchange": f"payloads <= 4,096 words (the {PIT}-iteration searches): " + ("all-reduce over NVLink peer memory by the exporting CTA "
+                              "(hq_comm_open_peers; inside the scoring kernel for K <= 32)" if comm.get("peer_exchange") else "ncclAllReduce") +
+                              f"; larger ones (the {PB}-candidate evaluation with sums): ncclAllReduce(int64, sum) on libhq_b200's own communicator "
+                              f"(hq_comm_init_rank), NCCL {comm['nccl_version']}, {comm['size']} ranks; torch.distributed only shipped the id / handle bytes",
+                  "peer_exchange": bool(comm.get("peer_exchange"))}
+        # the plugin's default palette size: the one-launch evaluation whose last CTA exchanges over peer memory
+        SK = 8
+        spal8 = synth.synth_palettes(4, SK)
+        got8 = be.evalPalettes(spal8, a.space, sums=True)
+        sw8 = dict(population=4, imax=PIT, seed=77760, space=a.space)
+        best8, err8, tr8, its8 = be.findBestQuantization(SK, SWASA(**sw8), n_total=n_total, trace=True)
         if rank == 0:   # the whole image on ONE GPU, no exchange: the integers and the trajectory must be the same
             whole = synth.synth_image_rows(a.width, H, synth.SEED_BASE + 3, 0, H)
             single = ImageManipulation("CIE76", False, True, local_rank)
@@ -479,13 +488,18 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
             want = single.evalPalettes(sub, a.space, sums=True, flags=flags)
             single.setPruning(PRUNE_OFF)   # the single-GPU search scores exhaustively; the sharded one above under the default policy
             sbest, serr, str_, sits = single.findBestQuantization(K, SWASA(**sw), trace=True)
+            want8 = single.evalPalettes(spal8, a.space, sums=True)
+            sbest8, serr8, str8, sits8 = single.findBestQuantization(SK, SWASA(**sw8), trace=True)
+            parity["small_k_equal_single_gpu"] = bool(all(np.array_equal(got8[k], want8[k]) for k in ("err_fx", "counts", "sums_fx")) and
+                                                      np.array_equal(tr8.view(np.uint64), str8.view(np.uint64)) and err8 == serr8 and its8 == sits8
+                                                      and np.array_equal(best8.view(np.uint32), sbest8.view(np.uint32)))
             single.close()
             del whole
             parity["evals_equal_single_gpu"] = all(np.array_equal(got[k], want[k]) for k in ("err_fx", "counts", "sums_fx"))
             parity["search_trace_equal_single_gpu"] = bool(np.array_equal(tr.view(np.uint64), str_.view(np.uint64)) and err == serr and its == sits == PIT
                                                            and np.array_equal(best.view(np.uint32), sbest.view(np.uint32)))
             parity["ok"] = bool(parity["evals_equal_single_gpu"] and parity["search_trace_equal_single_gpu"] and parity["same_on_all_ranks"]
-                                and parity["pruned_equals_exhaustive"])
+                                and parity["pruned_equals_exhaustive"] and parity["small_k_equal_single_gpu"])
         okt = torch.tensor([int(parity.get("ok", True))], device=dev)
         dist.broadcast(okt, 0)
         if not bool(okt.item()):
@@ -563,15 +577,27 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
             fr = be.evalPalettesScielab(fpal, SPACE_SRGB)
         dt = (time.perf_counter() - t0) / reps
         assert int(fr["counts"][0].sum()) == n_shard
+        # the filter stage alone (index images -> error sums: the kernel row f1 added), device-timed by the library's events
+        be.setProfiling(True)
+        stage = []
+        for _ in range(3):
+            be.evalPalettesScielab(fpal, SPACE_SRGB)
+            stage.append(be.lastScielabStageMs())
+        be.setProfiling(False)
+        st_ms, st_nb = min(stage)
         sc_flop = 650.0   # per pixel and candidate: 2 x 21 taps x 7 filter planes x 2 flop + Opp->Lab + dE
+        st_tf = sc_flop * n_shard * st_nb / (st_ms * 1e-3) / 1e12
         faithful = {"workload": f"{a.width}x{a.rows_per_gpu}, {K} colours, {FB} candidates per call, sRGB assignment + 21-tap S-CIELAB filters + CIE76 "
                                 "(what the reference plugin computes per candidate, ImageManipulation.java:635-699)",
                     "call": "hq_eval_palettes_scielab (host palettes in, host integers out)",
                     "e2e": {"evals_per_s": FB / dt, "gpixel_per_s": FB * n_shard / dt / 1e9, "ms_per_candidate": 1e3 * dt / FB,
                             "h2d_bytes_per_step": int(fpal.nbytes), "d2h_bytes_per_step": int(FB * words * 8)},
-                    "roofline": {"bound": "fp32", "flop_per_pixel_filter_stage": sc_flop, "assign_flop_per_pixel": 8.0 * K,
-                                 "achieved_tflops_whole_call": (sc_flop + 8.0 * K) * n_shard * FB / dt / 1e12, "peak": peak_tf,
-                                 "frac_whole_call": (sc_flop + 8.0 * K) * n_shard * FB / dt / 1e12 / peak_tf}}
+                    "roofline": {"bound": "fp32", "kernel": "sc_candidate_strip21_kernel", "flop_per_pixel_filter_stage": sc_flop,
+                                 "filter_stage_ms_per_candidate": st_ms / st_nb, "achieved": st_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": st_tf / peak_tf,
+                                 "algorithmic_bytes_per_pixel": 13, "hbm_floor_ms_per_candidate": 13.0 * n_shard / (hbm_bw * 1e9) * 1e3,
+                                 "assignment": "indices come from the exact pruned kernel (DESIGN.md 4c), which skips most of the 8 K flop per pixel the "
+                                               "exhaustive argmin spends: the whole call is therefore NOT put over a flop roofline; the stage is",
+                                 "assignment_ms_per_candidate": 1e3 * dt / FB - st_ms / st_nb}}
 
     # ---- what a search pays ONCE per image before its first evaluation (not part of `value` / `e2e`, which time the
     # per-iteration call as the reference's loop issues it): host image upload + RGB->Lab, and the cell sort of the pruned path
@@ -606,7 +632,8 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a, world), "timing": "CUDA events per step on the launching stream, max over ranks; "
                    "L2 flushed (256 MiB write) between timed iterations", "space": "LAB" if a.space == 0 else "SRGB",
-                   "parallelism": (f"row-shard x{world} + ncclAllReduce(int64) inside libhq_b200 (NCCL {comm['nccl_version']})" if world > 1 else "single GPU"),
+                   "parallelism": (f"row-shard x{world} + exchange inside libhq_b200: ncclAllReduce(int64) (NCCL {comm['nccl_version']}) for this payload; "
+                                   f"payloads <= 4,096 words {'over NVLink peer memory in the exporting CTA' if comm.get('peer_exchange') else 'also on NCCL'}" if world > 1 else "single GPU"),
                    "device": info["name"]},
         "swasa_evals_per_s": B * a.steps / total_s,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pal.nbytes), "d2h_bytes_per_step": int(B * words * 8),
@@ -648,6 +675,8 @@ def main_b200(a, rank: int, local_rank: int, world: int) -> None:
             cb = port
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line["cpu_baseline"]["oracle_port"] = {k: port[k] for k in ("value", "unit", "cores", "sample")}
+    if world > 1:
+        close_peer_exchange(be)   # every rank unmaps the others' mailboxes before any rank frees its own
     be.close()
     if world > 1:
         dist.barrier()

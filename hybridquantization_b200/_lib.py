@@ -17,12 +17,13 @@ ERR_NAMES = {1: "HQ_ERR_INVALID", 2: "HQ_ERR_CUDA", 3: "HQ_ERR_NO_IMAGE", 4: "HQ
 WHITEPOINT_D65, WHITEPOINT_D50 = 0, 1
 SPACE_LAB, SPACE_SRGB = 0, 1
 COST_LAB, COST_SCIELAB = 0, 1
-EVAL_SUMS, EVAL_FORCE_DIRECT, EVAL_FORCE_CHUNKED, EVAL_FORCE_PREFILTER, EVAL_PRUNE = 1, 2, 4, 8, 16
+EVAL_SUMS, EVAL_FORCE_DIRECT, EVAL_FORCE_CHUNKED, EVAL_FORCE_PREFILTER, EVAL_PRUNE, EVAL_ALLREDUCE = 1, 2, 4, 8, 16, 32
 PRUNE_OFF, PRUNE_AUTO, PRUNE_ON = 0, 1, 2
 MAX_COLORS = 1024
 MAX_COLORS_PRUNED = 4096
 MAX_COLORS_ANY = 1 << 24
 COMM_ID_BYTES = 128
+PEER_HANDLE_BYTES = 64
 DELTAE_CIE76, DELTAE_CIE94, DELTAE_CIEDE2000 = 0, 1, 2
 ERR_FX_NAN = -(1 << 63)
 
@@ -106,9 +107,14 @@ SIGNATURES = {
     "hq_swasa_generate_random_colors": (None, [C.POINTER(JavaRandomState), C.c_int, _P]),
     "hq_swasa_generate_neighboring_colors": (None, [C.POINTER(SwasaParams), C.POINTER(JavaRandomState), _P, _P, C.c_int, C.c_int]),
     "hq_swasa_max_step_width": (C.c_float, [C.POINTER(SwasaParams), C.c_int]),
+    "hq_comm_peer_handle": (C.c_int, [_P, _P]),
+    "hq_comm_open_peers": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "hq_comm_close_peers": (None, [_P]),
+    "hq_comm_peers_open": (C.c_int, [_P]),
     "hq_set_profiling": (C.c_int, [_P, C.c_int]),
     "hq_last_assign_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "hq_last_rgb_to_lab_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "hq_last_scielab_stage_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "hq_measure_fp32_peak": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "hq_host_math_range": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, _P, C.c_int]),
     "hq_device_math_range": (C.c_int, [_P, C.c_int, C.c_uint32, C.c_uint32, _P]),

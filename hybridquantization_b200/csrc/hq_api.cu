@@ -215,6 +215,8 @@ void hq_destroy(hq_ctx* c) {
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
     if (c->ev3) cudaEventDestroy(c->ev3);
+    if (c->ev4) cudaEventDestroy(c->ev4);
+    if (c->ev5) cudaEventDestroy(c->ev5);
     c->d_rgb.release(); c->d_flag.release(); c->d_lab.release(); c->d_unit.release(); c->d_table.release(); c->d_pal.release();
     c->d_pal_lab.release(); c->d_pal_rgb.release(); c->d_results.release(); c->d_idx.release();
     c->d_out_rgb.release(); c->d_out_f32.release(); c->h_pal.release(); c->h_results.release(); c->h_flag.release(); c->d_export_counter.release(); c->d_results_small.release();
@@ -438,7 +440,23 @@ int hq_eval_palettes_device(hq_ctx* c, const void* d_palettes, int B, int K, int
     if (c->is_multi()) return fail(c, HQ_ERR_UNSUPPORTED, "a device buffer belongs to one device: use hq_eval_palettes on a multi-device context");
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
     if (c->image_foreign && st != c->stream) HQ_CUDA(c, cudaStreamWaitEvent(st, c->ev_image, 0));  // image converted on another stream
-    return eval_device(c, static_cast<const float*>(d_palettes), B, K, space, flags, static_cast<unsigned long long*>(d_results), nullptr, st);
+    unsigned long long* words = static_cast<unsigned long long*>(d_results);
+    if (!(flags & HQ_EVAL_ALLREDUCE) || !reduces(c))
+        return eval_device(c, static_cast<const float*>(d_palettes), B, K, space, flags & ~HQ_EVAL_ALLREDUCE, words, nullptr, st);
+    // scoring + exchange: over peer memory the last CTA of the scoring kernel all-reduces (K <= 32) or a one-CTA launch behind it does
+    const size_t nwords = (size_t)B * hq::result_words(K, (flags & HQ_EVAL_SUMS) != 0);
+    if (!peer_ready(c, nwords)) {
+        rc = eval_device(c, static_cast<const float*>(d_palettes), B, K, space, flags & ~HQ_EVAL_ALLREDUCE, words, nullptr, st); if (rc) return rc;
+        return reduce_words(c, words, nwords, st);
+    }
+    HQ_CUDA(c, c->d_export_counter.reserve(1));
+    hq::ExportTail tail;
+    tail.peer_only = true; tail.counter = c->d_export_counter.p; tail.src = words; tail.nwords = (unsigned)nwords;
+    tail.peer = peer_next(c);
+    bool used = false;
+    rc = eval_device(c, static_cast<const float*>(d_palettes), B, K, space, flags & ~HQ_EVAL_ALLREDUCE, words, nullptr, st, &tail, &used); if (rc) return rc;
+    if (!used) HQ_CUDA(c, hq::launch_peer_allreduce(tail.peer, words, nwords, nullptr, nullptr, 0, st));
+    return HQ_OK;
 }
 
 namespace {
@@ -563,27 +581,40 @@ int hq_eval_palettes(hq_ctx* c, const float* palettes, int B, int K, int space, 
         // ONE launch (round 2): small searches (B*K <= 192 colours, K <= 32 — the plugin's defaults are 8 colours x 4 candidates) pass the
         // palettes as a kernel parameter; every CTA converts its candidate's palette itself and the last CTA exports and re-zeroes the
         // result words (d_results_small is only ever touched by these launches: zero between them).
-        if (e.direct && c->small_eval && !multi && !reduce && !c->profiling && c->n > 0 && K <= hq::kDirectMaxColors && (long long)B * K <= hq::kSmallPalColors &&
+        // a sharded image: the exchange rides in the exporting CTA over peer memory when that path is open (hq_kernels.cuh)
+        const bool peer = reduce && e.direct && peer_ready(c, nwords);
+        bool all_nonempty = true;
+        for (hq_ctx* m : targets) all_nonempty = all_nonempty && m->n > 0;
+        if (e.direct && c->small_eval && (!reduce || peer) && all_nonempty && !c->profiling && K <= hq::kDirectMaxColors && (long long)B * K <= hq::kSmallPalColors &&
             !(flags & (HQ_EVAL_PRUNE | HQ_EVAL_FORCE_DIRECT | HQ_EVAL_FORCE_CHUNKED | HQ_EVAL_FORCE_PREFILTER))) {
-            if (nwords > c->d_results_small.cap) {
-                HQ_CUDA(c, c->d_results_small.reserve(nwords > 4096 ? nwords : 4096));
-                HQ_CUDA(c, cudaMemsetAsync(c->d_results_small.p, 0, c->d_results_small.cap * 8, c->stream));
-            }
             const unsigned long long seq = ++c->export_seq;
-            hq::AssignArgs a;
-            a.lab = c->d_lab.p; a.unit = c->d_unit.p; a.n = c->n; a.stride = c->stride;
-            a.pal_lab = nullptr; a.pal_rgb = nullptr;
-            a.B = B; a.K = K; a.space = space; a.want_sums = sums;
-            a.results = c->d_results_small.p; a.idx_out = nullptr; a.sm_count = c->sm_count;
-            a.own_lo = c->own_lo; a.own_hi = c->own_hi;
-            a.variant = 1;
-            a.tail.host_dst = c->h_results.p; a.tail.host_flag = c->h_flag.p; a.tail.seq = seq; a.tail.counter = c->d_export_counter.p;
-            a.tail.src = c->d_results_small.p; a.tail.nwords = (unsigned)nwords;
-            const cudaError_t le = hq::launch_assign_small(a, c->h_pal.p, c->whitepoint, c->stream);
+            cudaError_t le = cudaSuccess;
+            for (size_t i = targets.size(); i-- > 0 && le == cudaSuccess;) {   // the leader last: its launch exports
+                hq_ctx* m = targets[i];
+                rc = bind_device(m); if (rc) return rc;
+                if (nwords > m->d_results_small.cap) {
+                    HQ_CUDA(c, m->d_results_small.reserve(nwords > 4096 ? nwords : 4096));
+                    HQ_CUDA(c, cudaMemsetAsync(m->d_results_small.p, 0, m->d_results_small.cap * 8, m->stream));
+                }
+                hq::AssignArgs a;
+                a.lab = m->d_lab.p; a.unit = m->d_unit.p; a.n = m->n; a.stride = m->stride;
+                a.pal_lab = nullptr; a.pal_rgb = nullptr;
+                a.B = B; a.K = K; a.space = space; a.want_sums = sums;
+                a.results = m->d_results_small.p; a.idx_out = nullptr; a.sm_count = m->sm_count;
+                a.own_lo = m->own_lo; a.own_hi = m->own_hi;
+                a.variant = 1;
+                a.tail.host_dst = m == c ? c->h_results.p : nullptr; a.tail.host_flag = m == c ? c->h_flag.p : nullptr; a.tail.seq = seq; a.tail.counter = m->d_export_counter.p;
+                a.tail.src = m->d_results_small.p; a.tail.nwords = (unsigned)nwords;
+                a.tail.peer_only = m != c;
+                if (peer) a.tail.peer = peer_next(m);
+                le = hq::launch_assign_small(a, c->h_pal.p, m->whitepoint, m->stream);
+            }
+            rc = bind_device(c); if (rc) return rc;
             cudaError_t we = le;
             if (le == cudaSuccess) we = wait_flag(c->h_flag.p, seq, c->stream);
             if (we != cudaSuccess) {
-                c->d_results_small.release();   // whatever the failed launch left behind is not reused
+                for (hq_ctx* m : targets) { cudaSetDevice(m->device); m->d_results_small.release(); }   // whatever the failed launch left behind is not reused
+                cudaSetDevice(c->device);
                 return fail(c, HQ_ERR_CUDA, "one-launch evaluation failed: %s", cudaGetErrorString(we));
             }
             goto unpack;
@@ -593,15 +624,22 @@ int hq_eval_palettes(hq_ctx* c, const float* palettes, int B, int K, int space, 
             // the pinned host copy directly (UVA: pinned host memory is device-accessible) and a one-CTA kernel writes the
             // result words plus a sequence number back into pinned host memory, which the host spins on.
             const unsigned long long seq = ++c->export_seq;
-            hq::ExportTail tail;   // single GPU, small palettes: the scoring kernel's last CTA exports; otherwise a one-CTA kernel after it
-            tail.host_dst = c->h_results.p; tail.host_flag = c->h_flag.p; tail.seq = seq; tail.counter = c->d_export_counter.p;
-            tail.src = c->d_results.p; tail.nwords = (unsigned)nwords;
             bool tail_used = false;
             for (size_t i = targets.size(); i-- > 0;) {   // the leader (targets[0]) last: its stream carries the export
                 hq_ctx* m = targets[i];
-                rc = member_rc(c, m, eval_enqueue(m, c->h_pal.p, e, (reduce || m != c) ? nullptr : &tail, &tail_used)); if (rc) return rc;
+                // single GPU, small palettes: the scoring kernel's last CTA exports; sharded with the peer path open: every rank's
+                // last CTA exchanges, the leader's also exports; otherwise one-CTA kernels after it
+                hq::ExportTail tail;
+                tail.host_dst = m == c ? c->h_results.p : nullptr; tail.host_flag = m == c ? c->h_flag.p : nullptr; tail.seq = seq; tail.counter = m->d_export_counter.p;
+                tail.src = m->d_results.p; tail.nwords = (unsigned)nwords; tail.peer_only = m != c;
+                if (peer) tail.peer = peer_next(m);
+                bool used = false;
+                rc = member_rc(c, m, eval_enqueue(m, c->h_pal.p, e, (peer || (!reduce && m == c)) ? &tail : nullptr, &used)); if (rc) return rc;
+                if (peer && !used)
+                    HQ_CUDA(c, hq::launch_peer_allreduce(tail.peer, m->d_results.p, nwords, m == c ? c->h_results.p : nullptr, m == c ? c->h_flag.p : nullptr, seq, m->stream));
+                if (m == c) tail_used = used || peer;
             }
-            if (reduce) { rc = eval_reduce(c, nwords); if (rc) return rc; }
+            if (reduce && !peer) { rc = eval_reduce(c, nwords); if (rc) return rc; }
             rc = bind_device(c); if (rc) return rc;
             if (!tail_used) HQ_CUDA(c, hq::launch_export_results(c->d_results.p, c->h_results.p, nwords, c->h_flag.p, seq, c->stream));
             HQ_CUDA(c, wait_flag(c->h_flag.p, seq, c->stream));
@@ -636,6 +674,7 @@ int hq_eval_palettes(hq_ctx* c, const float* palettes, int B, int K, int space, 
     }
     HQ_CUDA(c, wait_stream(c->stream));
 unpack:
+    if (reduce) { rc = peer_check(c); if (rc) return rc; }
     unpack_results(c->h_results.p, B, K, words, err_fx, counts, sums_fx);
     return HQ_OK;
 } catch (const std::exception& ex) { return api_exception(c, ex); }
@@ -1063,6 +1102,7 @@ int sc_eval_enqueue(hq_ctx* m, const float* h_pal, int B, int K, int space) {
         rc = eval_device(m, m->d_pal.p + (size_t)b0 * K * 4, nb, K, space, prune_idx ? HQ_EVAL_PRUNE : 0, m->d_results.p + (size_t)b0 * words, m->d_idx.p, m->stream);
         if (rc) return rc;
         // 2. per candidate: separable filters, Opp2LAB, CIE76 against the original, fixed-point sum
+        if (m->profiling) HQ_CUDA(m, cudaEventRecord(m->ev4, m->stream));
         cudaError_t fe = (m->sc_generic || m->sc_unfused || de94) ? cudaErrorNotSupported   // (the fused kernel is CIE76 only)
                          : hq::launch_sc_candidates_fused(m->d_idx.p, idx16, m->d_sc_tab.p + (size_t)b0 * K, K, nb, m->width, m->rows, m->stride, m->sc_block.data(),
                                                           m->sc_taps, m->whitepoint, sc_rows(m), m->d_sc_lab.p, m->d_sc_err.p + b0, m->sm_count, m->stream);
@@ -1074,6 +1114,7 @@ int sc_eval_enqueue(hq_ctx* m, const float* h_pal, int B, int K, int space) {
                                                m->sc_generic ? nullptr : m->sc_block.data(), m->sc_taps, m->whitepoint, sc_rows(m), m->d_sc_tmp.p,
                                                m->d_sc_lab.p, m->d_sc_err.p + b0 + b, m->stream, m->delta_e, m->d_results.p + nwords + b0 + b));
         }
+        if (m->profiling) { HQ_CUDA(m, cudaEventRecord(m->ev5, m->stream)); m->ev_sc_valid = true; m->ev_sc_candidates = nb; }
     }
     // word 0 of every candidate <- the S-CIELAB error sum, so that one all-reduce covers error and counts
     HQ_CUDA(m, cudaMemcpy2DAsync(m->d_results.p, (size_t)words * 8, m->d_sc_err.p, 8, 8, (size_t)B, cudaMemcpyDeviceToDevice, m->stream));
@@ -1100,6 +1141,7 @@ int hq_eval_palettes_scielab(hq_ctx* c, const float* palettes, int B, int K, int
     rc = bind_device(c); if (rc) return rc;
     HQ_CUDA(c, cudaMemcpyAsync(c->h_results.p, c->d_results.p, (nwords + tail) * 8, cudaMemcpyDeviceToHost, c->stream));
     HQ_CUDA(c, wait_stream(c->stream));
+    if (reduces(c)) { rc = peer_check(c); if (rc) return rc; }
     for (int b = 0; b < B; ++b) {
         if (err_fx) err_fx[b] = (tail && c->h_results.p[nwords + b]) ? HQ_ERR_FX_NAN : (int64_t)c->h_results.p[(size_t)b * words];
         if (counts) std::memcpy(counts + (size_t)b * K, c->h_results.p + (size_t)b * words + 1, sizeof(uint64_t) * K);
@@ -1243,10 +1285,12 @@ int hq_set_profiling(hq_ctx* c, int enabled) {
     if (enabled && !c->ev0) {
         HQ_CUDA(c, cudaEventCreate(&c->ev0)); HQ_CUDA(c, cudaEventCreate(&c->ev1));
         HQ_CUDA(c, cudaEventCreate(&c->ev2)); HQ_CUDA(c, cudaEventCreate(&c->ev3));
+        HQ_CUDA(c, cudaEventCreate(&c->ev4)); HQ_CUDA(c, cudaEventCreate(&c->ev5));
     }
     c->profiling = enabled != 0;
     c->ev_valid = false;
     c->ev_rl_valid = false;
+    c->ev_sc_valid = false;
     return HQ_OK;
 }
 
@@ -1265,6 +1309,16 @@ int hq_last_rgb_to_lab_ms(hq_ctx* c, float* ms) {
     int rc = bind_device(c); if (rc) return rc;
     HQ_CUDA(c, cudaEventSynchronize(c->ev3));
     HQ_CUDA(c, cudaEventElapsedTime(ms, c->ev2, c->ev3));
+    return HQ_OK;
+}
+
+int hq_last_scielab_stage_ms(hq_ctx* c, float* ms, int* candidates) {
+    if (!c || !ms) return HQ_ERR_INVALID;
+    if (!c->ev_sc_valid) return fail(c, HQ_ERR_INVALID, "no profiled S-CIELAB evaluation yet (hq_set_profiling)");
+    int rc = bind_device(c); if (rc) return rc;
+    HQ_CUDA(c, cudaEventSynchronize(c->ev5));
+    HQ_CUDA(c, cudaEventElapsedTime(ms, c->ev4, c->ev5));
+    if (candidates) *candidates = c->ev_sc_candidates;
     return HQ_OK;
 }
 

@@ -157,14 +157,24 @@ struct hq_ctx {
     hq_ctx* leader = nullptr;               // set on the members the leader owns
     int m_width = 0, m_rows = 0;            // whole image of a multi-device context
     bool is_multi() const { return members.size() > 1; }
+    // ---- the same exchange over NVLink peer memory for small payloads (hq_kernels.cuh, PeerExchange): this context's mailbox
+    // and every other rank's, mapped (peer access inside one process, CUDA IPC between processes)
+    DevBuf<unsigned long long> d_peer_box;
+    unsigned long long* peer_box[hq::kPeerMaxRanks] = {};
+    bool peer_ipc[hq::kPeerMaxRanks] = {};    // opened with cudaIpcOpenMemHandle: closed in comm_release
+    bool peer_open = false;
+    unsigned long long peer_seq = 0;          // exchanges done; in lockstep on every rank
+    unsigned long long peer_timeout_ns = 60ull * 1000000000ull;   // HQ_PEER_TIMEOUT_MS
+    PinBuf<unsigned long long> h_peer_status; // one word: sequence number of an exchange that timed out
 
     hq_progress_fn progress = nullptr;
     void* progress_user = nullptr;
     hq_allreduce_fn allreduce = nullptr;
     void* allreduce_user = nullptr;
     bool profiling = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
-    bool ev_valid = false, ev_rl_valid = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr;
+    bool ev_valid = false, ev_rl_valid = false, ev_sc_valid = false;
+    int ev_sc_candidates = 0;               // candidates of the filter-stage launch between ev4 and ev5
     std::atomic<bool> stop{false};
     volatile bool stop_flag_view = false;
 };
@@ -237,4 +247,7 @@ bool reduces(const hq_ctx* c);   // an all-reduce follows every evaluation (hook
 int reduce_words(hq_ctx* c, unsigned long long* d_words, size_t n_words, cudaStream_t st);          // one rank per process
 int group_reduce(hq_ctx* leader, const std::vector<unsigned long long*>& bufs, size_t n_words);     // one process, all members
 void comm_release(hq_ctx* c);
+bool peer_ready(const hq_ctx* c, size_t n_words);   // this exchange goes over peer memory (the same answer on every rank)
+hq::PeerExchange peer_next(hq_ctx* c);              // parameters of the context's next exchange (advances its sequence)
+int peer_check(hq_ctx* c);                          // after a completed call: a timed-out exchange is an error, not a wrong total
 }  // namespace hqi

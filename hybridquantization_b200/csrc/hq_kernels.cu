@@ -1139,6 +1139,27 @@ cudaError_t launch_export_results(const unsigned long long* d_src, unsigned long
     return cudaGetLastError();
 }
 
+// The exchange step as its own one-CTA launch, for the scoring kernels that carry no export tail (prefilter, pruned, the
+// S-CIELAB chain, caller-owned buffers): all-reduce of the words over peer memory (hq_kernels.cuh), in place, and — when a
+// host buffer is given — the export of the totals plus the sequence number, i.e. what ncclAllReduce + export_results_kernel did.
+__global__ void __launch_bounds__(1024) peer_allreduce_kernel(const __grid_constant__ PeerExchange px, unsigned long long* words, unsigned nwords,
+                                                              unsigned long long* host_dst, volatile unsigned long long* host_flag, unsigned long long host_seq) {
+    peer_allreduce_cta(px, words, nwords, host_dst, false);
+    if (host_dst) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) *host_flag = host_seq;
+    }
+}
+
+cudaError_t launch_peer_allreduce(const PeerExchange& px, unsigned long long* d_words, size_t nwords, unsigned long long* h_dst_mapped,
+                                  unsigned long long* h_flag_mapped, unsigned long long host_seq, cudaStream_t stream) {
+    if (px.nranks < 1 || px.nranks > kPeerMaxRanks || nwords > kPeerCapWords) return cudaErrorInvalidValue;
+    const unsigned threads = nwords > 512 ? 1024u : (nwords > 128 ? 512u : 128u);
+    peer_allreduce_kernel<<<1, threads, 0, stream>>>(px, d_words, (unsigned)nwords, h_dst_mapped, h_flag_mapped, host_seq);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_unit_to_lab(const float* d_unit, size_t n, size_t stride, int whitepoint, float* d_lab, unsigned int* d_bad,
                                int sm_count, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
@@ -1203,14 +1224,14 @@ cudaError_t launch_assign_reduce(const AssignArgs& a, cudaStream_t stream) {
     else { p.xmax0 = 100.5f; p.xmax1 = 128.0f; p.xmax2 = 128.0f; }
     int variant = a.variant;
     if (variant == 0) variant = (a.K <= kDirectMaxColors) ? 1 : 3;  // measured crossover (4K, 64 candidates): K=32 direct 42 % vs prefilter 36 %, K=64 46 % vs 50 %
-    if (a.tail.host_dst && variant != 1) return cudaErrorInvalidValue;  // the export tail only exists in variant 1
+    if (a.tail.active() && variant != 1) return cudaErrorInvalidValue;  // the export tail only exists in variant 1
     if (variant == 1) return launch_assign_v<1>(p, a.B, a.space == 1, a.want_sums, idxw, a.sm_count, stream);
     if (variant == 2) return launch_assign_v<2>(p, a.B, a.space == 1, a.want_sums, idxw, a.sm_count, stream);
     return launch_assign_v<3>(p, a.B, a.space == 1, a.want_sums, idxw, a.sm_count, stream);
 }
 
 cudaError_t launch_assign_small(const AssignArgs& a, const float* h_palettes, int whitepoint, cudaStream_t stream) {
-    if (a.B <= 0 || a.K <= 0 || a.K > kDirectMaxColors || (long long)a.B * a.K > kSmallPalColors || a.idx_out || !a.tail.host_dst || !h_palettes) return cudaErrorInvalidValue;
+    if (a.B <= 0 || a.K <= 0 || a.K > kDirectMaxColors || (long long)a.B * a.K > kSmallPalColors || a.idx_out || !a.tail.active() || !h_palettes) return cudaErrorInvalidValue;
     if (a.space == 1 && a.unit == nullptr) return cudaErrorInvalidValue;
     if (a.n == 0) return cudaErrorInvalidValue;   // (nothing would export: the caller handles an empty image)
     AssignParams p;

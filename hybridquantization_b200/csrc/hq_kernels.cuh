@@ -38,6 +38,81 @@ cudaError_t launch_palette_features(const float* d_palettes, int B, int K, int w
                                     float4* d_pal_lab, float4* d_pal_rgb, cudaStream_t stream, unsigned long long* d_zero = nullptr,
                                     size_t zero_words = 0);
 
+// ---- the exchange step over NVLink / NVSwitch PEER MEMORY (round 2): an all-reduce of the integer result words done by the
+// exporting CTA itself — no separate collective launch.  Every rank owns a MAILBOX in its own HBM (one arrival flag per sender,
+// two parity sets of one slot per sender); the other ranks hold it mapped (cudaDeviceEnablePeerAccess inside one process,
+// cudaIpcOpenMemHandle between processes).  Per exchange `seq` the CTA
+//   1. stores its words into slot[seq & 1][my rank] of EVERY rank's mailbox (plain 8-byte stores travelling over NVLink),
+//   2. fences at system scope and releases `seq` into its flag in every mailbox,
+//   3. acquires the flags of all senders in its OWN mailbox (local polling; a globaltimer bound turns a dead peer into an
+//      error word instead of a hung GPU),
+//   4. adds the slots up locally — integer sums, so the order is free and every rank gets the same bits.
+// Two parity sets suffice: a rank cannot start exchange seq + 2 before it has completed seq + 1, which needs every
+// peer's flag for seq + 1, which that peer releases only after it has read its slots of seq.
+// Payloads above kPeerCapWords (64 candidates x 256 colours = 16 k words) stay on ncclAllReduce: there the collective's
+// launch latency no longer matters and one CTA's stores would.
+constexpr int kPeerMaxRanks = 16;
+constexpr unsigned kPeerCapWords = 4096;                 // 32 KB per sender and parity
+constexpr unsigned kPeerFlagStride = 16;                 // words: one 128-byte line per sender's flag
+constexpr size_t kPeerSlotBase = (size_t)kPeerMaxRanks * kPeerFlagStride;
+constexpr size_t kPeerBoxWords = kPeerSlotBase + (size_t)2 * kPeerMaxRanks * kPeerCapWords;   // 1 MB + 2 KB
+struct PeerExchange {
+    unsigned long long* box[kPeerMaxRanks] = {};   // every rank's mailbox in THIS device's address space (box[rank] is local)
+    int nranks = 0, rank = 0;                      // nranks == 0: no exchange
+    unsigned long long seq = 0;                    // 1, 2, 3, ... in lockstep on every rank
+    unsigned long long timeout_ns = 0;
+    unsigned long long* status = nullptr;          // pinned host word: seq of an exchange that timed out (0 = fine)
+};
+#ifdef __CUDACC__
+// called by ALL threads of ONE CTA (any block size >= nranks); words[0 .. nwords) in: this rank's partial sums (complete and
+// visible: the caller has fenced), out: the totals (or zero, zero_after); host_dst (optional): the totals as well
+__device__ __noinline__ static void peer_allreduce_cta(const PeerExchange& px, unsigned long long* words, unsigned nwords,
+                                                       unsigned long long* host_dst, bool zero_after) {
+    const int nr = px.nranks, me = px.rank;
+    const unsigned tid = threadIdx.x;
+    const size_t slot_mine = kPeerSlotBase + ((size_t)(px.seq & 1ull) * kPeerMaxRanks + me) * kPeerCapWords;
+    for (unsigned i = tid; i < nwords; i += blockDim.x) {
+        const unsigned long long v = __ldcg(words + i);
+        for (int k = 0; k < nr; ++k) {
+            int r = me + k; r -= r >= nr ? nr : 0;   // own mailbox first, then round the ring: the ranks do not all hit rank 0 at once
+            *reinterpret_cast<volatile unsigned long long*>(px.box[r] + slot_mine + i) = v;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int s_dead;
+    if (tid == 0) s_dead = 0;
+    if ((int)tid < nr)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(px.box[tid] + (size_t)me * kPeerFlagStride), "l"(px.seq) : "memory");
+    __syncthreads();
+    if ((int)tid < nr) {
+        const unsigned long long* f = px.box[me] + (size_t)tid * kPeerFlagStride;
+        unsigned long long t0 = 0, v;
+        for (unsigned spin = 0;; ++spin) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v >= px.seq) break;
+            if ((spin & 255u) == 255u) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t0 == 0) t0 = t;
+                else if (t - t0 > px.timeout_ns) { s_dead = 1; break; }
+            }
+        }
+    }
+    __syncthreads();
+    if (s_dead && tid == 0 && px.status) *reinterpret_cast<volatile unsigned long long*>(px.status) = px.seq;
+    const unsigned long long* base = px.box[me] + kPeerSlotBase + (size_t)(px.seq & 1ull) * kPeerMaxRanks * kPeerCapWords;
+    for (unsigned i = tid; i < nwords; i += blockDim.x) {
+        unsigned long long s = 0;
+        for (int r = 0; r < nr; ++r) s += *reinterpret_cast<const volatile unsigned long long*>(base + (size_t)r * kPeerCapWords + i);
+        if (host_dst) host_dst[i] = s;
+        words[i] = zero_after ? 0ull : s;
+    }
+}
+#endif
+cudaError_t launch_peer_allreduce(const PeerExchange& px, unsigned long long* d_words, size_t nwords, unsigned long long* h_dst_mapped,
+                                  unsigned long long* h_flag_mapped, unsigned long long host_seq, cudaStream_t stream);
+
 // Optional tail of the small-palette scoring kernel (assign_reduce_kernel variant 1, K <= 32 — where a search iteration is
 // latency-bound): the LAST CTA of the grid to finish copies every result word to pinned host memory and then writes a
 // sequence number there (what export_results_kernel does as a separate launch) — one dependent stream operation fewer per
@@ -50,12 +125,15 @@ struct ExportTail {
     unsigned* counter = nullptr;
     const unsigned long long* src = nullptr;  // [nwords] all result words of the launch
     unsigned nwords = 0;
+    bool peer_only = false;                   // a member of a multi-device context: exchange, no host export (host_dst unused)
+    PeerExchange peer;                        // nranks > 0: the last CTA all-reduces the words over peer memory before it exports
+    bool active() const { return host_dst != nullptr || peer_only; }
 };
 #ifdef __CUDACC__
 // every thread of every CTA calls this after its last result atomic
 // zero_after: the result words are left zero for the next launch (the one-launch evaluation has no clearing pass)
 __device__ __forceinline__ void export_tail(const ExportTail& x, unsigned total_ctas, bool zero_after = false) {
-    if (x.host_dst == nullptr) return;
+    if (x.host_dst == nullptr && !x.peer_only) return;
     __shared__ unsigned s_ticket;
     __threadfence();     // this thread's result atomics are performed device-wide before the ticket is taken
     __syncthreads();
@@ -63,15 +141,19 @@ __device__ __forceinline__ void export_tail(const ExportTail& x, unsigned total_
     __syncthreads();
     if (s_ticket != total_ctas - 1) return;
     __threadfence();
-    for (unsigned i = threadIdx.x; i < x.nwords; i += blockDim.x) {
-        x.host_dst[i] = __ldcg(x.src + i);
-        if (zero_after) const_cast<unsigned long long*>(x.src)[i] = 0ull;
+    if (x.peer.nranks > 0) {   // sharded image: totals over all ranks first, over NVLink peer memory
+        peer_allreduce_cta(x.peer, const_cast<unsigned long long*>(x.src), x.nwords, x.peer_only ? nullptr : x.host_dst, zero_after);
+    } else {
+        for (unsigned i = threadIdx.x; i < x.nwords; i += blockDim.x) {
+            x.host_dst[i] = __ldcg(x.src + i);
+            if (zero_after) const_cast<unsigned long long*>(x.src)[i] = 0ull;
+        }
     }
     __threadfence_system();   // the words are visible to the host before the sequence number is
     __syncthreads();
     if (threadIdx.x == 0) {
         *x.counter = 0u;
-        *reinterpret_cast<volatile unsigned long long*>(x.host_flag) = x.seq;
+        if (!x.peer_only) *reinterpret_cast<volatile unsigned long long*>(x.host_flag) = x.seq;
     }
 }
 #endif

@@ -74,7 +74,50 @@ def install_native_nccl(backend) -> dict:
     dist.broadcast_object_list(box, src=0)
     backend.setAllreduce(None)
     backend.commInitRank(box[0], dist.get_world_size(), dist.get_rank())
+    open_peer_exchange(backend)
     return backend.commInfo()
+
+
+def open_peer_exchange(backend) -> bool:
+    """Small exchanges over NVLink peer memory (hq_comm_open_peers): every rank's mailbox handle (64 bytes) goes to every rank
+    through torch.distributed, each rank maps the others' mailboxes with CUDA IPC.  Collective; if ANY rank cannot (no IPC
+    between the processes, HQ_PEER_EXCHANGE=0, more than 16 ranks) every rank closes again and the exchange stays on
+    ncclAllReduce.  Returns whether the peer path is open."""
+    import torch.distributed as dist
+
+    from ._lib import HqError
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    ok, handle = True, b""
+    try:
+        handle = backend.commPeerHandle()
+    except HqError:
+        ok = False
+    handles = [None] * world
+    dist.all_gather_object(handles, handle if ok else None)
+    if ok and all(h is not None for h in handles):
+        try:
+            backend.commOpenPeers(handles, rank)
+        except HqError:
+            ok = False
+    else:
+        ok = False
+    oks = [None] * world
+    dist.all_gather_object(oks, ok)
+    if not all(oks):
+        backend.commClosePeers()
+        return False
+    return True
+
+
+def close_peer_exchange(backend) -> None:
+    """Unmaps the other ranks' mailboxes before any rank frees its own (call on every rank before close())."""
+    import torch.distributed as dist
+
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+        backend.commClosePeers()
+        dist.barrier()
 
 
 def reduce_partials_numpy(parts: list[dict]) -> dict:

@@ -169,7 +169,26 @@ class ImageManipulation:
     def commInfo(self) -> dict:
         r, s_, v = C.c_int(), C.c_int(), C.c_int()
         _lib.check(self._ctx, self._lib.hq_comm_info(self._ctx, C.byref(r), C.byref(s_), C.byref(v)))
-        return {"rank": r.value, "size": s_.value, "nccl_version": v.value, "devices": int(self._lib.hq_multi_device_count(self._ctx))}
+        return {"rank": r.value, "size": s_.value, "nccl_version": v.value, "devices": int(self._lib.hq_multi_device_count(self._ctx)),
+                "peer_exchange": bool(self._lib.hq_comm_peers_open(self._ctx))}
+
+    # -- the exchange of small payloads over NVLink peer memory (hq_b200.h): mailbox handle out, every rank's handles in
+    def commPeerHandle(self) -> bytes:
+        buf = C.create_string_buffer(_lib.PEER_HANDLE_BYTES)
+        _lib.check(self._ctx, self._lib.hq_comm_peer_handle(self._ctx, buf))
+        return buf.raw
+
+    def commOpenPeers(self, handles: list, rank: int) -> None:
+        if any(len(h) != _lib.PEER_HANDLE_BYTES for h in handles):
+            raise ValueError("every handle must be the %d bytes of commPeerHandle()" % _lib.PEER_HANDLE_BYTES)
+        blob = b"".join(handles)
+        _lib.check(self._ctx, self._lib.hq_comm_open_peers(self._ctx, C.c_char_p(blob), len(handles), rank))
+
+    def commClosePeers(self) -> None:
+        self._lib.hq_comm_close_peers(self._ctx)
+
+    def commPeersOpen(self) -> bool:
+        return bool(self._lib.hq_comm_peers_open(self._ctx))
 
     # -- measurement hooks
     def setProfiling(self, enabled: bool) -> None:
@@ -184,6 +203,12 @@ class ImageManipulation:
         ms = C.c_float()
         _lib.check(self._ctx, self._lib.hq_last_rgb_to_lab_ms(self._ctx, C.byref(ms)))
         return ms.value
+
+    def lastScielabStageMs(self):
+        """(ms, candidates) of the filter-stage launches of the last sub-batch of the latest evalPalettesScielab (profiling on)."""
+        ms, nb = C.c_float(), C.c_int()
+        _lib.check(self._ctx, self._lib.hq_last_scielab_stage_ms(self._ctx, C.byref(ms), C.byref(nb)))
+        return ms.value, nb.value
 
     def measureFp32Peak(self) -> dict:
         a, b = C.c_double(), C.c_double()

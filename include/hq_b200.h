@@ -64,8 +64,11 @@ enum {
     HQ_EVAL_FORCE_DIRECT = 2,    /* kernel variant selection, for tests / profiling */
     HQ_EVAL_FORCE_CHUNKED = 4,
     HQ_EVAL_FORCE_PREFILTER = 8, /* expanded-form prefilter + exact re-check (default for K > 32) */
-    HQ_EVAL_PRUNE = 16           /* exact assignment with geometric pruning (LAB space; same integers as the exhaustive
+    HQ_EVAL_PRUNE = 16,          /* exact assignment with geometric pruning (LAB space; same integers as the exhaustive
                                   * kernel, ~10x less arithmetic at K=256): see hq_set_pruning */
+    HQ_EVAL_ALLREDUCE = 32       /* hq_eval_palettes_device only: d_results holds the totals over the context's communicator
+                                  * when the call's work completes — folded into the scoring kernel's last CTA over peer
+                                  * memory where that path is open (hq_comm_open_peers), else hq_comm_allreduce behind it */
 };
 
 #define HQ_MAX_COLORS 1024          /* palette sizes the exhaustive kernel stages in shared memory */
@@ -137,7 +140,7 @@ int hq_eval_palettes(hq_ctx* ctx, const float* palettes, int B, int K, int space
 int hq_result_words(int K, int flags);
 /* fully asynchronous variant on device memory: d_palettes [B][K][4] floats, d_results
  * [B][hq_result_words] words (zeroed by the call).  Runs on `stream` (cudaStream_t; NULL =
- * the context's stream), no host synchronisation, no all-reduce.  (With HQ_EVAL_PRUNE the first call after an image
+ * the context's stream), no host synchronisation, no all-reduce unless HQ_EVAL_ALLREDUCE asks for it.  (With HQ_EVAL_PRUNE the first call after an image
  * change builds the cell-sorted copy of the image and synchronises `stream` once to read the chunk count.) */
 int hq_eval_palettes_device(hq_ctx* ctx, const void* d_palettes, int B, int K, int space,
                             int flags, void* d_results, void* stream);
@@ -255,6 +258,20 @@ int hq_comm_allreduce(hq_ctx* ctx, void* d_words, size_t n_words, void* stream);
 int hq_comm_info(const hq_ctx* ctx, int* rank, int* size, int* nccl_version);
 int hq_create_multi(const int* devices, int ndev, hq_ctx** out);
 int hq_multi_device_count(const hq_ctx* ctx);
+/* ---- the same exchange over NVLink / NVSwitch PEER MEMORY for small payloads (<= 4,096 result words: every search with
+ * B x (K + 1) <= 4,096): the CTA that finishes an evaluation stores its words into a mailbox in every rank's HBM, signals,
+ * waits for the other ranks' signals and adds the slots up — inside the scoring kernel itself for K <= 32, else in a one-CTA
+ * launch behind it; no collective launch, identical integers.  Larger payloads stay on ncclAllReduce.
+ * A multi-device context (hq_create_multi) sets it up itself (cudaDeviceEnablePeerAccess).  One process per GPU: after
+ * hq_comm_init_rank every rank calls hq_comm_peer_handle, the host ships the HQ_PEER_HANDLE_BYTES of every rank to every
+ * rank (rank order), and every rank calls hq_comm_open_peers (cudaIpcOpenMemHandle).  COLLECTIVE: if it fails on any rank
+ * (HQ_ERR_UNSUPPORTED: no IPC between the processes, HQ_PEER_EXCHANGE=0), call hq_comm_close_peers on every rank and the
+ * exchange stays on NCCL.  A rank that never arrives turns into HQ_ERR_CUDA after HQ_PEER_TIMEOUT_MS (60 s), not a hang. */
+#define HQ_PEER_HANDLE_BYTES 64
+int hq_comm_peer_handle(hq_ctx* ctx, void* handle64);
+int hq_comm_open_peers(hq_ctx* ctx, const void* handles /* [nranks][HQ_PEER_HANDLE_BYTES] */, int nranks, int rank);
+void hq_comm_close_peers(hq_ctx* ctx);
+int hq_comm_peers_open(const hq_ctx* ctx);   /* 1: small exchanges go over peer memory */
 
 /* ---- the annealing search: replaces findBestQuantization (ImageManipulation.java:383-591)
  * with SWASA.java's schedule.  Accept/reject logic and RNG stay on the host; only the
@@ -311,6 +328,9 @@ float hq_swasa_max_step_width(const hq_swasa_params* p, int iteration);
 int hq_set_profiling(hq_ctx* ctx, int enabled);
 int hq_last_assign_ms(hq_ctx* ctx, float* ms);
 int hq_last_rgb_to_lab_ms(hq_ctx* ctx, float* ms);
+/* the S-CIELAB filter-stage launch(es) of the last sub-batch of the most recent hq_eval_palettes_scielab, and how many
+ * candidates that sub-batch held (row f1: cl:234-306 + Opp2LAB + CIEDE, without the assignment) */
+int hq_last_scielab_stage_ms(hq_ctx* ctx, float* ms, int* candidates);
 int hq_measure_fp32_peak(hq_ctx* ctx, double* tflops_ffma, double* tflops_ffma2);
 
 /* ---- test hooks: the single-source arithmetic of csrc/hq_math.h evaluated on the host

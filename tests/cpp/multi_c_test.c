@@ -142,7 +142,7 @@ int main(int argc, char** argv) {
         }
         free(t1); free(tN); free(best1); free(bestN);
     }
-    printf("MULTI_C_TEST OK ndev=%d comm_size=%d nccl=%d image=%dx%d K=%d B=%d checks=%d\n", ndev, size, nccl_version, w, h, K, B, checks);
+    printf("MULTI_C_TEST OK ndev=%d comm_size=%d nccl=%d peers=%d image=%dx%d K=%d B=%d checks=%d\n", ndev, size, nccl_version, hq_comm_peers_open(multi), w, h, K, B, checks);
     hq_destroy(multi);
     hq_destroy(one);
     free(img); free(pal); free(lab1); free(labN); free(e1); free(eN); free(c1); free(cN); free(s1); free(sN); free(sc1); free(scN);

@@ -25,11 +25,16 @@ def test_c_host_on_n_devices_equals_one_device(ndev, hqlib, tmp_path):
     if torch.cuda.device_count() < ndev:
         pytest.skip(f"needs {ndev} GPUs, have {torch.cuda.device_count()}")
     exe = _build(tmp_path)
-    for args in (["1031", "517", "64", "5"],      # ragged rows, pruning on (AUTO) inside the search
-                 ["640", "37", "16", "3"]):       # fewer than 10 rows per device at 4/8 devices: halos overlap several neighbours
-        r = subprocess.run([exe, str(ndev)] + args, capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-        assert "MULTI_C_TEST OK" in r.stdout and f"comm_size={ndev}" in r.stdout, r.stdout
+    # the exchange of small payloads over NVLink peer memory (default: inside the scoring kernel's last CTA for K <= 32, a
+    # one-CTA launch otherwise) and, with HQ_PEER_EXCHANGE=0, everything on ncclAllReduce: the same integers either way
+    for peers in ("1", "0"):
+        env = dict(os.environ, HQ_PEER_EXCHANGE=peers, HQ_PEER_TIMEOUT_MS="20000")
+        for args in (["1031", "517", "64", "5"],      # ragged rows, pruning on (AUTO) inside the search
+                     ["640", "37", "16", "3"],        # fewer than 10 rows per device at 4/8 devices: halos overlap several neighbours
+                     ["512", "512", "8", "4"]):       # the plugin's defaults: one launch per device and iteration, exchange included
+            r = subprocess.run([exe, str(ndev)] + args, capture_output=True, text=True, timeout=600, env=env)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+            assert "MULTI_C_TEST OK" in r.stdout and f"comm_size={ndev}" in r.stdout and f"peers={peers}" in r.stdout, r.stdout
 
 
 def test_single_device_list_is_a_plain_context(hqlib, tmp_path):
