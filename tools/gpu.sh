@@ -8,6 +8,7 @@
 #   sweep                 tools/sweep.py (rgb_to_lab sizes, K sweep, S-CIELAB stage, full searches)
 #   multi N               NCCL parity test + bench at 1 and N GPUs   (gpurun --gpus N)
 #   micro                 FP32-pipe / issue-model microbenchmarks
+#   final                 tests + bench + launches + latency in one call
 #   latency               tools/latency_ab.py: us per search iteration with / without the direct host I/O path
 set -u
 mkdir -p gpurun_out
@@ -70,6 +71,12 @@ ncupy)
     ncu -i gpurun_out/prof.ncu-rep --page raw --csv > gpurun_out/prof_raw.csv 2>/dev/null
     ncu -i gpurun_out/prof.ncu-rep --page source --csv > gpurun_out/prof_source.csv 2>/dev/null
     ls -la gpurun_out/prof* ;;
+final)
+    # the evidence set of a finished state: GPU tests + smoke, both bench arms, the launch list of the bench command, latencies
+    bash tools/gpu.sh tests
+    bash tools/gpu.sh bench
+    bash tools/gpu.sh launches
+    bash tools/gpu.sh latency ;;
 latency)
     timeout 500 python tools/latency_ab.py > gpurun_out/latency_ab.json 2> gpurun_out/latency_ab.err; tail -3 gpurun_out/latency_ab.err; ls -la gpurun_out/latency_ab.json ;;
 *) echo "unknown task $task"; exit 2 ;;

@@ -18,8 +18,13 @@ CASES = {"defaults_512x512_k8_p4_i5000": (512, 512, 8, 4, 5000, True), "defaults
 def child():
     import numpy as np
     from hybridquantization_b200 import SWASA, ImageManipulation, synth
+    from bench import ClockSampler
+    sampler = ClockSampler(0)
+    sampler.start()
     be = ImageManipulation("CIE76", False, True, 0)
     out = {}
+    sampler.wait_ready()
+    w0 = time.perf_counter()
     for name, (w, h, K, P, imax, smooth) in CASES.items():
         be.setImage(synth.synth_image(w, h, synth.SEED_BASE + 2, smooth=smooth))
         ts = []
@@ -28,6 +33,7 @@ def child():
             best, err, _, its = be.findBestQuantization(K, SWASA(population=P, imax=imax, seed=77760))
             ts.append(time.perf_counter() - t0)
         out[name] = {"min_s": min(ts[1:]), "median_s": float(np.median(ts[1:])), "us_per_iteration_min": min(ts[1:]) / (its + 1) * 1e6, "best_error": err}
+    out["clocks"] = sampler.summary(w0, time.perf_counter())   # SM clock / throttle reasons over the whole timed window
     be.close()
     print(json.dumps(out))
 
