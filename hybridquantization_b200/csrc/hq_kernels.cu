@@ -408,6 +408,9 @@ __device__ __noinline__ unsigned long long exact_all_colours(const float* __rest
 #ifndef HQ_V3_MIN_CTAS
 #define HQ_V3_MIN_CTAS 2
 #endif
+#ifndef HQ_V1_MIN_CTAS
+#define HQ_V1_MIN_CTAS 3   // variant 1 (K <= 32): 80 registers; 4 (64 registers) was measured too
+#endif
 #ifndef HQ_V3_UNROLL
 #define HQ_V3_UNROLL 2
 #endif
@@ -945,13 +948,13 @@ __device__ __forceinline__ void assign_body(const AssignParams& p, const float* 
 }
 
 template <int VARIANT, bool SRGB, bool SUMS, int IDXW>
-__global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VARIANT == 1 ? 3 : 2)) assign_reduce_kernel(const __grid_constant__ AssignParams p) {
+__global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VARIANT == 1 ? HQ_V1_MIN_CTAS : 2)) assign_reduce_kernel(const __grid_constant__ AssignParams p) {
     assign_body<VARIANT, SRGB, SUMS, IDXW, false>(p, nullptr);
 }
 // one launch per evaluation: variant 1 with the palettes in parameter space; the last CTA exports the result words to pinned
 // host memory and leaves them ZERO for the next launch (no clearing pass)
 template <bool SRGB, bool SUMS, int NCOL>
-__global__ void __launch_bounds__(kThreads, 3) assign_small_kernel(const __grid_constant__ AssignParams p, const __grid_constant__ SmallPalettes<NCOL> pal) {
+__global__ void __launch_bounds__(kThreads, HQ_V1_MIN_CTAS) assign_small_kernel(const __grid_constant__ AssignParams p, const __grid_constant__ SmallPalettes<NCOL> pal) {
     assign_body<1, SRGB, SUMS, 0, true>(p, pal.v);
 }
 
