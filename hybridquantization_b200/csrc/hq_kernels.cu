@@ -335,6 +335,7 @@ struct AssignParams {
     ExportTail tail;
     int use_tma;   // variant 1: pixel tiles staged by TMA bulk copies through a 3-stage shared-memory ring
     int whitepoint;   // assign_small_kernel converts its palettes itself
+    float one_f = 1.0f, zero_f = 0.0f;   // a 1 and a 0 the compiler cannot see through (track_min)
 };
 constexpr int kPxStages = 3;   // tiles in flight per CTA (variant 1 with TMA): 3 x 12 KB
 
@@ -461,6 +462,26 @@ __device__ __noinline__ void stage_small_palette(const float* __restrict__ cpal,
         pb_f[k] = f2;
         if (srgb) s_lab[k] = lab;
     }
+}
+
+// Running (minimum, index) of variant 1.  `if (d < best) { best = d; idx = k; }` compiles to FSETP + FSEL + SEL, three ALU-pipe
+// instructions per (pixel, colour) pair beside the six FMA-pipe operations of the distance.  EXPERIMENT (HQ_V1_PRED_TRACK=1, off):
+// keep the FSETP but make the two updates predicated FFMAs (best = d * 1 + (-0), index as a float = d * 0 + k, the 1 and the 0 from
+// kernel parameters so that ptxas cannot fold them back into selects; a predicated integer move IS folded back into a SEL).  ptxas
+// emits exactly that (64 @P FFMA per 32 pairs, no FSEL / SEL left) and the integers are unchanged, but it measured SLOWER — K=32 x 64
+// candidates 4.48 -> 5.12 ms, K=8 1.68 -> 1.72 ms (profiles/r02/smallk_pred_track_ab.txt): the packed distance arithmetic already
+// keeps the FMA pipe busier than the ALU pipe, and the selects ride beside it for free.
+#ifndef HQ_V1_PRED_TRACK
+#define HQ_V1_PRED_TRACK 0
+#endif
+__device__ __forceinline__ void track_min(float d, float kf, float& best, float& idxf, float one_f, float zero_f) {
+#if HQ_V1_PRED_TRACK
+    // (the index update multiplies the finite, non-negative distance by an opaque zero: d * 0 + kf == kf, and nothing of it can be hoisted)
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %2, %0;\n\t@p fma.rn.f32 %1, %2, %5, %3;\n\t@p fma.rn.f32 %0, %2, %4, 0f80000000;\n\t}"
+        : "+f"(best), "+f"(idxf) : "f"(d), "f"(kf), "f"(one_f), "f"(zero_f));
+#else
+    if (d < best) { best = d; idxf = kf; }
+#endif
 }
 
 template <int VARIANT, bool SRGB, bool SUMS, int IDXW, bool FUSED>
@@ -688,19 +709,27 @@ __device__ __forceinline__ void assign_body(const AssignParams& p, const float* 
             uint64_t X[PX], Y[PX], Z[PX];
 #pragma unroll
             for (int j = 0; j < PX; ++j) { X[j] = pack2(x0[j], x0[j]); Y[j] = pack2(x1[j], x1[j]); Z[j] = pack2(x2[j], x2[j]); }
+            float idxf[PX];
+#pragma unroll
+            for (int j = 0; j < PX; ++j) idxf[j] = 0.f;
+            float kf = 0.f;
 #pragma unroll 4
             for (int q = 0; q < K8 / 2; ++q) {
                 const float4 la = s_pla[q];
                 const float2 bb = s_pb[q];
                 const uint64_t P0 = pack2(la.x, la.y), P1 = pack2(la.z, la.w), P2 = pack2(bb.x, bb.y);
+                const float kf1 = kf + 1.0f;
 #pragma unroll
                 for (int j = 0; j < PX; ++j) {
                     float dlo, dhi;
                     unpack2(dist2_pair(X[j], Y[j], Z[j], P0, P1, P2), dlo, dhi);
-                    if (dlo < best[j]) { best[j] = dlo; idx[j] = 2 * q; }
-                    if (dhi < best[j]) { best[j] = dhi; idx[j] = 2 * q + 1; }
+                    track_min(dlo, kf, best[j], idxf[j], p.one_f, p.zero_f);
+                    track_min(dhi, kf1, best[j], idxf[j], p.one_f, p.zero_f);
                 }
+                kf += 2.0f;
             }
+#pragma unroll
+            for (int j = 0; j < PX; ++j) idx[j] = __float2int_rn(idxf[j]);
         } else if (VARIANT == 2) {
             uint64_t X[PX], Y[PX], Z[PX];
 #pragma unroll
