@@ -480,7 +480,7 @@ __device__ __forceinline__ void track_min(float d, float kf, float& best, float&
     asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %2, %0;\n\t@p fma.rn.f32 %1, %2, %5, %3;\n\t@p fma.rn.f32 %0, %2, %4, 0f80000000;\n\t}"
         : "+f"(best), "+f"(idxf) : "f"(d), "f"(kf), "f"(one_f), "f"(zero_f));
 #else
-    if (d < best) { best = d; idxf = kf; }
+    if (d < best) { best = d; idxf = kf; }   // (not compiled into the default build: the select form keeps its integer index)
 #endif
 }
 
@@ -709,6 +709,7 @@ __device__ __forceinline__ void assign_body(const AssignParams& p, const float* 
             uint64_t X[PX], Y[PX], Z[PX];
 #pragma unroll
             for (int j = 0; j < PX; ++j) { X[j] = pack2(x0[j], x0[j]); Y[j] = pack2(x1[j], x1[j]); Z[j] = pack2(x2[j], x2[j]); }
+#if HQ_V1_PRED_TRACK
             float idxf[PX];
 #pragma unroll
             for (int j = 0; j < PX; ++j) idxf[j] = 0.f;
@@ -730,6 +731,21 @@ __device__ __forceinline__ void assign_body(const AssignParams& p, const float* 
             }
 #pragma unroll
             for (int j = 0; j < PX; ++j) idx[j] = __float2int_rn(idxf[j]);
+#else
+#pragma unroll 4
+            for (int q = 0; q < K8 / 2; ++q) {
+                const float4 la = s_pla[q];
+                const float2 bb = s_pb[q];
+                const uint64_t P0 = pack2(la.x, la.y), P1 = pack2(la.z, la.w), P2 = pack2(bb.x, bb.y);
+#pragma unroll
+                for (int j = 0; j < PX; ++j) {
+                    float dlo, dhi;
+                    unpack2(dist2_pair(X[j], Y[j], Z[j], P0, P1, P2), dlo, dhi);
+                    if (dlo < best[j]) { best[j] = dlo; idx[j] = 2 * q; }
+                    if (dhi < best[j]) { best[j] = dhi; idx[j] = 2 * q + 1; }
+                }
+            }
+#endif
         } else if (VARIANT == 2) {
             uint64_t X[PX], Y[PX], Z[PX];
 #pragma unroll
