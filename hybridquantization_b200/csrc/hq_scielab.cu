@@ -321,11 +321,21 @@ sc_vpass21_kernel(const float* __restrict__ tmp, int w, int h, size_t stride, co
 #ifndef HQ_SC_SW
 #define HQ_SC_SW 128      // columns per strip (128: 2 CTAs of 256 threads per SM; 256: 1 CTA of 512 threads, half the horizontal halo overhead)
 #endif
+#ifndef HQ_SC_EPI_H
+#define HQ_SC_EPI_H 0     // who runs Opp2LAB + dE: 0 the V warps (every row; default), 1 the H warps (every row, one band later, through
+#endif                    // shared memory), 2 both: of every group of four rows the V warps score two in place and hand two to the H
+                          // warps.  EXPERIMENT: per pixel the V warps execute ~342 instructions and the H warps ~200, so 1 and 2 were
+                          // built to even the halves out (2: 289 / 275) — identical integers, and SLOWER: 0.285 -> 0.318 (1) / 0.336 (2)
+                          // ms per 4K candidate (profiles/r02/sc_stage_ab_variants.txt).  The H warps' slack is not what limits the kernel.
 constexpr int kSW = HQ_SC_SW, kSBand = 8, kSThreads = 2 * kSW, kSCtasPerSm = 256 / kSW;
+constexpr int kEpiV = HQ_SC_EPI_H == 0 ? 4 : (HQ_SC_EPI_H == 1 ? 0 : 2);   // rows of each group of four that the V warps score themselves
+constexpr int kEpiHRows = kSBand * (4 - kEpiV) / 4;                       // rows per band handed to the H warps
+constexpr size_t kSOutFloats = (size_t)2 * kEpiHRows * 3 * kSW;           // their vertically filtered opponent values: [2][kEpiHRows][3][kSW]
 constexpr int kSHOut = 8;                                              // outputs per H task
 constexpr int kSHPer = kSHOut / HQ_SC_HHALVES;                         // ... per unrolled pass
 constexpr int kSVUnroll = HQ_SC_VUNROLL;
 static_assert(kSBand % kSVUnroll == 0 && kSBand * (kSW / kSHOut) == kSThreads / 2 && kSW == kSThreads / 2, "task geometry");
+static_assert(HQ_SC_EPI_H == 0 || kSVUnroll == 4, "the epilogue split is per group of four rows");
 
 // named barriers with IMMEDIATE ids (a register id makes ptxas reserve all 16 barriers for the CTA)
 template <int ID> __device__ __forceinline__ void named_bar_sync_i(int count) { asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(count) : "memory"); }
@@ -387,6 +397,11 @@ __device__ __forceinline__ hq_float3 sc_opp_to_lab_straight(float o0, float o1, 
 #endif
 }
 
+// Never called (seg_rows is positive).  Without a call site inside the V loop ptxas hoists the loop-invariant filter coefficients
+// out of it into ~70 ordinary registers and then spills them (372 bytes); with one it keeps re-loading them into uniform
+// registers inside the loop, as it did while the Opp2LAB epilogue (which has a rare out-of-line call) lived there.
+__device__ __noinline__ void sc_never_called() { asm volatile("trap;"); }
+
 template <typename IdxT>
 __global__ void __launch_bounds__(kSThreads, kSCtasPerSm)
 sc_candidate_strip21_kernel(const IdxT* __restrict__ idx, const float4* __restrict__ tab, int K, int w, int h, size_t stride, int seg_rows,
@@ -394,8 +409,10 @@ sc_candidate_strip21_kernel(const IdxT* __restrict__ idx, const float4* __restri
                             unsigned long long* __restrict__ err_out) {
     extern __shared__ __align__(16) unsigned char strip_smem[];
     float* s_ring = reinterpret_cast<float*>(strip_smem);                                              // [2][kSBand][7][kSW]
-    float4* s_lut = reinterpret_cast<float4*>(strip_smem + (size_t)2 * kSBand * 7 * kSW * sizeof(float));  // [K]
-    __shared__ long long s_err[kSW / 32];
+    float* s_out = reinterpret_cast<float*>(strip_smem + (size_t)2 * kSBand * 7 * kSW * sizeof(float));    // [2][kEpiHRows][3][kSW]
+    float4* s_lut = reinterpret_cast<float4*>(strip_smem + ((size_t)2 * kSBand * 7 * kSW + kSOutFloats) * sizeof(float));  // [K]
+    (void)s_out;
+    __shared__ long long s_err[kSW / 32], s_err_v[kSW / 32];   // partial sums of the H warps / of the V warps
     const int tid = threadIdx.x;
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * kSW;
@@ -403,7 +420,7 @@ sc_candidate_strip21_kernel(const IdxT* __restrict__ idx, const float4* __restri
     const int yb = min(ya + seg_rows, rows.y_begin + rows.y_count);
     // input (horizontally filtered) rows v = ya-10 .. yb+9 in bands of 8; row v completes output row v-10
     const int nbands = (yb - ya + 2 * kHalf + kSBand - 1) / kSBand;
-    enum { kBarFull = 1, kBarEmpty = 3 };            // named barriers 1,2 (full[buf]) and 3,4 (empty[buf]); 0 is __syncthreads
+    enum { kBarFull = 1, kBarEmpty = 3, kBarOutFull = 7, kBarOutEmpty = 9 };   // named barriers 1,2 (full[buf]), 3,4 (empty[buf]), 7,8 / 9,10 (the same for s_out); 5, 6: one half only; 0 is __syncthreads
 
     if (tid >= kSW) {
         // =============================== H warps (cl:234-272): one task (row, 8 outputs) per thread and band
@@ -414,6 +431,48 @@ sc_candidate_strip21_kernel(const IdxT* __restrict__ idx, const float4* __restri
         const int hrow = q / (kSW / kSHOut), hg = q - hrow * (kSW / kSHOut);
         const int xs = x0 + hg * kSHOut - kHalf;
         const bool interior = xs >= 0 && xs + kSHOut + kT - 1 <= w;
+#if HQ_SC_EPI_H
+        // Opp2LAB (cl:124-145) + CIE76 (cl:209) + fixed-point sum for the rows the V warps hand over, one band later (they run one band
+        // behind this half).  With the whole epilogue on their side the V warps carried 342 of the stage's 591 instructions per pixel
+        // against 200 here: the H warps waited at the barriers 40 % of the time and a scheduler had two busy warps.  Task = kEpiHRows
+        // pixels of one handed-over row.
+        long long hfx = 0;
+        constexpr int kEpiPerRow = kSW / kEpiHRows;                   // threads per handed-over row
+        const int er = q / kEpiPerRow, ec0 = (q - er * kEpiPerRow) * kEpiHRows;
+        const int erow = (er / (4 - kEpiV)) * 4 + kEpiV + er % (4 - kEpiV);   // its row inside the band
+        auto h_epilogue = [&](int eb) {
+            const int ebuf = eb & 1;
+            const int y = ya - 2 * kHalf + eb * kSBand + erow;        // band eb's input row v = ya-10+8*eb+erow completed output v-10
+            const int yc = y < ya ? ya : (y >= yb ? yb - 1 : y);
+            const bool rowok = y >= ya && y < yb;
+            float lo[3][kEpiHRows];
+#pragma unroll
+            for (int i = 0; i < kEpiHRows; ++i) {
+                int x = x0 + ec0 + i;
+                x = x < w ? x : w - 1;
+                const size_t pp = (size_t)yc * w + x;
+                lo[0][i] = __ldg(lab_orig + pp); lo[1][i] = __ldg(lab_orig + stride + pp); lo[2][i] = __ldg(lab_orig + 2 * stride + pp);
+            }
+            named_bar_sync<kBarOutFull>(ebuf, kSThreads);
+            const float* src = s_out + ((size_t)ebuf * kEpiHRows + er) * 3 * kSW + ec0;
+#pragma unroll 1
+            for (int i4 = 0; i4 < kEpiHRows; i4 += 4) {   // four pixels at a time (registers, code size)
+                const float4 o0 = *reinterpret_cast<const float4*>(src + i4);
+                const float4 o1 = *reinterpret_cast<const float4*>(src + kSW + i4);
+                const float4 o2 = *reinterpret_cast<const float4*>(src + 2 * kSW + i4);
+                const float a0[4] = {o0.x, o0.y, o0.z, o0.w}, a1[4] = {o1.x, o1.y, o1.z, o1.w}, a2[4] = {o2.x, o2.y, o2.z, o2.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const hq_float3 lab = sc_opp_to_lab_straight(a0[i], a1[i], a2[i], white);
+                    const float l0 = (kEpiHRows > 4 && i4) ? lo[0][(4 + i) % kEpiHRows] : lo[0][i], l1 = (kEpiHRows > 4 && i4) ? lo[1][(4 + i) % kEpiHRows] : lo[1][i],
+                                l2 = (kEpiHRows > 4 && i4) ? lo[2][(4 + i) % kEpiHRows] : lo[2][i];
+                    const long long e = hq_to_fx(HQ_FSQRT(hq_dist2(l0, l1, l2, lab.x, lab.y, lab.z)));
+                    hfx += (rowok && x0 + ec0 + i4 + i < w) ? e : 0ll;
+                }
+            }
+            if (eb + 2 < nbands) named_bar_arrive<kBarOutEmpty>(ebuf, kSThreads);   // the buffer is read: a V warp may refill it
+        };
+#endif
         for (int band = 0; band < nbands; ++band) {
             const int buf = band & 1;
             // virtual row -> array row: reflection at the GLOBAL borders; rows only discarded outputs need are clamped
@@ -466,7 +525,23 @@ sc_candidate_strip21_kernel(const IdxT* __restrict__ idx, const float4* __restri
                 }
             }
             named_bar_arrive<kBarFull>(buf, kSThreads);
+#if HQ_SC_EPI_H
+            if (band >= 1) h_epilogue(band - 1);
+#endif
         }
+#if HQ_SC_EPI_H
+        h_epilogue(nbands - 1);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) hfx += __shfl_down_sync(0xffffffffu, hfx, off);
+        if ((q & 31) == 0) s_err[q >> 5] = hfx;
+        named_bar_sync_i<5>(kSW);                      // H warps only
+        if (q == 0) {
+            long long e = 0;
+#pragma unroll
+            for (int i = 0; i < kSW / 32; ++i) e += s_err[i];
+            if (e) atomicAdd(err_out + b, (unsigned long long)e);
+        }
+#endif
         return;
     }
 
@@ -481,13 +556,17 @@ sc_candidate_strip21_kernel(const IdxT* __restrict__ idx, const float4* __restri
         const int buf = band & 1;
         const int vb = ya - kHalf + band * kSBand;    // first input row of the band
         named_bar_sync<kBarFull>(buf, kSThreads);
+#if HQ_SC_EPI_H
+        if (band >= 2) named_bar_sync<kBarOutEmpty>(buf, kSThreads);   // the H warps hold this buffer's previous outputs in registers
+#endif
         if (vact) {
 #pragma unroll 1
             for (int r0 = 0; r0 < kSBand; r0 += kSVUnroll) {
-                // the four outputs this group completes: rows vb + r0 + p - 10; their S-CIELAB originals fly during the fma work
-                float lo[kSVUnroll][3];
+                // the outputs this group completes and the V warps score themselves: rows vb + r0 + p - 10, p < kEpiV; their S-CIELAB
+                // originals fly during the fma work
+                float lo[kEpiV > 0 ? kEpiV : 1][3];
 #pragma unroll
-                for (int p = 0; p < kSVUnroll; ++p) {
+                for (int p = 0; p < kEpiV; ++p) {
                     int y = vb + r0 + p - kHalf;
                     y = y < ya ? ya : (y >= yb ? yb - 1 : y);
                     const size_t pp = (size_t)y * w + x;
@@ -505,21 +584,25 @@ sc_candidate_strip21_kernel(const IdxT* __restrict__ idx, const float4* __restri
                         a[2] = HQ_FFMA(t12, f.v[3 * t + 2], HQ_FFMA(t22, f.v[3 * kT + 3 * t + 2], a[2]));
                         a[0] = HQ_FFMA(t3, f.v[7 * kT + t], a[0]);
                     }
-                    const int y = vb + r0 + p - kHalf;            // completed: tap 20 was the last
+                    const float* a = A[kT + kSVUnroll - 2 - p];            // completed: tap 20 was the last
+                    if (p >= kEpiV) {   // to the H warps, which score it one band later
+                        if (HQ_SC_EPI_H == 1 && seg_rows < 0) sc_never_called();
+                        float* dst = s_out + ((size_t)buf * kEpiHRows + (r0 / 4) * (4 - kEpiV) + (p - kEpiV)) * 3 * kSW + tid;
+                        dst[0] = a[0]; dst[kSW] = a[1]; dst[2 * kSW] = a[2];
+                    } else {
+                        const int y = vb + r0 + p - kHalf;
 #if HQ_SC_STRAIGHT
-                    {   // rows outside the segment are computed like the others and dropped by a select (no divergence, no branch)
-                        const float* a = A[kT + kSVUnroll - 2 - p];
+                        // rows outside the segment are computed like the others and dropped by a select (no divergence, no branch)
                         const hq_float3 lab = sc_opp_to_lab_straight(a[0], a[1], a[2], white);
-                        const long long e = hq_to_fx(HQ_FSQRT(hq_dist2(lo[p][0], lo[p][1], lo[p][2], lab.x, lab.y, lab.z)));
+                        const long long e = hq_to_fx(HQ_FSQRT(hq_dist2(lo[p < kEpiV ? p : 0][0], lo[p < kEpiV ? p : 0][1], lo[p < kEpiV ? p : 0][2], lab.x, lab.y, lab.z)));
                         fx += (y >= ya && y < yb) ? e : 0ll;
-                    }
 #else
-                    if (y >= ya && y < yb) {
-                        const float* a = A[kT + kSVUnroll - 2 - p];
-                        const hq_float3 lab = hq_cl_opp_to_lab_white(a[0], a[1], a[2], white);
-                        fx += hq_to_fx(HQ_FSQRT(hq_dist2(lo[p][0], lo[p][1], lo[p][2], lab.x, lab.y, lab.z)));
-                    }
+                        if (y >= ya && y < yb) {
+                            const hq_float3 lab = hq_cl_opp_to_lab_white(a[0], a[1], a[2], white);
+                            fx += hq_to_fx(HQ_FSQRT(hq_dist2(lo[p < kEpiV ? p : 0][0], lo[p < kEpiV ? p : 0][1], lo[p < kEpiV ? p : 0][2], lab.x, lab.y, lab.z)));
+                        }
 #endif
+                    }
                 }
                 // kSVUnroll rows further every pending output's tap has grown by as much: slot j -> j + kSVUnroll, fresh outputs enter below
 #pragma unroll
@@ -528,17 +611,22 @@ sc_candidate_strip21_kernel(const IdxT* __restrict__ idx, const float4* __restri
                 for (int j = 0; j < kSVUnroll; ++j) A[j][0] = A[j][1] = A[j][2] = 0.f;
             }
         }
+#if HQ_SC_EPI_H
+        named_bar_arrive<kBarOutFull>(buf, kSThreads);
+#endif
         if (band + 2 < nbands) named_bar_arrive<kBarEmpty>(buf, kSThreads);   // an H warp will wait for it
     }
+    if (kEpiV > 0) {
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) fx += __shfl_down_sync(0xffffffffu, fx, off);
-    if ((tid & 31) == 0) s_err[tid >> 5] = fx;
-    named_bar_sync_i<6>(kSW);                          // V warps only
-    if (tid == 0) {
-        long long e = 0;
+        for (int off = 16; off > 0; off >>= 1) fx += __shfl_down_sync(0xffffffffu, fx, off);
+        if ((tid & 31) == 0) s_err_v[tid >> 5] = fx;
+        named_bar_sync_i<6>(kSW);                          // V warps only
+        if (tid == 0) {
+            long long e = 0;
 #pragma unroll
-        for (int i = 0; i < kSW / 32; ++i) e += s_err[i];
-        if (e) atomicAdd(err_out + b, (unsigned long long)e);
+            for (int i = 0; i < kSW / 32; ++i) e += s_err_v[i];
+            if (e) atomicAdd(err_out + b, (unsigned long long)e);
+        }
     }
 }
 
@@ -761,7 +849,7 @@ cudaError_t launch_sc_candidates_fused(const void* d_idx, bool idx16, const floa
     if (w == 0 || h == 0 || rows.y_count == 0 || B == 0) return cudaSuccess;
     Filt21 f21;
     for (int i = 0; i < 8 * kT; ++i) f21.v[i] = h_filters[i];
-    const size_t smem = (size_t)2 * kSBand * 7 * kSW * sizeof(float) + (size_t)K * sizeof(float4);
+    const size_t smem = ((size_t)2 * kSBand * 7 * kSW + kSOutFloats) * sizeof(float) + (size_t)K * sizeof(float4);
     const int strips = (w + kSW - 1) / kSW;
     // rows per segment: every segment start costs 20 extra horizontally filtered rows, so segments are as long as they can
     // be while the grid still holds >= 2.5 waves of the resident CTAs (2 per SM)
