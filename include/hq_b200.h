@@ -258,7 +258,8 @@ int hq_comm_allreduce(hq_ctx* ctx, void* d_words, size_t n_words, void* stream);
 int hq_comm_info(const hq_ctx* ctx, int* rank, int* size, int* nccl_version);
 int hq_create_multi(const int* devices, int ndev, hq_ctx** out);
 int hq_multi_device_count(const hq_ctx* ctx);
-/* ---- the same exchange over NVLink / NVSwitch PEER MEMORY for small payloads (<= 4,096 result words: every search with
+/* ---- the same exchange over NVLink / NVSwitch PEER MEMORY (no reference counterpart: the reference owns one device and one
+ * queue, ImageManipulation.java:58-59) for small payloads (<= 4,096 result words: every search with
  * B x (K + 1) <= 4,096): the CTA that finishes an evaluation stores its words into a mailbox in every rank's HBM, signals,
  * waits for the other ranks' signals and adds the slots up — inside the scoring kernel itself for K <= 32, else in a one-CTA
  * launch behind it; no collective launch, identical integers.  Larger payloads stay on ncclAllReduce.

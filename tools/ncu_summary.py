@@ -22,6 +22,10 @@ def main():
     ap.add_argument("source", nargs="?")
     ap.add_argument("--units", type=float, default=0, help="pixels (or pixel x candidate pairs) one launch processes")
     ap.add_argument("--row", type=int, default=0, help="which captured launch (0 = first)")
+    ap.add_argument("--traffic-key", help="also record dram read + write bytes of this launch in profiles/traffic.json under this key "
+                                          "(bench.py's roofline.traffic), with the sha of the kernel source it was captured on")
+    ap.add_argument("--source-file", default="hq_kernels.cu", help="csrc file holding the captured kernel (for the staleness check)")
+    ap.add_argument("--capture-name", default="", help="name of the summary file this capture is kept as")
     a = ap.parse_args()
     rows = list(csv.reader(open(a.raw)))
     hdr, units, vals = rows[0], rows[1], rows[2 + a.row]
@@ -56,6 +60,21 @@ def main():
             out["instruction_mix_per_unit"] = {o: round(n * 32 / a.units, 2) for o, n in mix.most_common(24)}
         else:
             out["instruction_mix"] = dict(mix.most_common(24))
+    if a.traffic_key:
+        import hashlib
+        import os
+        repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        to_bytes = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        total = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            m = out["metrics"][k]
+            total += float(m["value"]) * to_bytes[m["unit"]]
+        tpath = os.path.join(repo, "profiles", "traffic.json")
+        t = json.load(open(tpath)) if os.path.exists(tpath) else {}
+        src = os.path.join(repo, "hybridquantization_b200", "csrc", a.source_file)
+        t[a.traffic_key] = {"bytes": int(round(total)), "capture": a.capture_name or "ncu --set full, one launch", "source_file": a.source_file,
+                            "source_sha": hashlib.sha256(open(src, "rb").read()).hexdigest()[:12]}
+        json.dump(t, open(tpath, "w"), indent=1)
     print(json.dumps(out, indent=1))
 
 
