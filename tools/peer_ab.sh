@@ -8,6 +8,7 @@ export HQ_PEER_TIMEOUT_MS=20000
 nvidia-smi -L | head -8
 nvidia-smi topo -m 2>/dev/null | head -12
 timeout 1500 python -m pytest tests/test_gpu_multi.py tests/test_gpu_multi_native.py -x -q -m gpu 2>&1 | tail -15 | tee gpurun_out/pytest_gpu_multi_n$N.txt
+HQ_SOAK_ITERS=20000 HQ_SOAK_LAUNCHES=5000 timeout 900 python -m pytest tests/test_gpu_multi_soak.py -x -q -m gpu 2>&1 | tail -3 | tee gpurun_out/pytest_gpu_soak_n$N.txt
 for peers in 1 0; do
     HQ_PEER_EXCHANGE=$peers timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 2951$peers \
         bench.py --gpus "$N" --no-cpu-baseline --force-sweeps > gpurun_out/bench_n${N}_peers$peers.json 2> gpurun_out/bench_n${N}_peers$peers.err
