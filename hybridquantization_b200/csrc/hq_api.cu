@@ -441,6 +441,7 @@ int hq_eval_palettes_device(hq_ctx* c, const void* d_palettes, int B, int K, int
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
     if (c->image_foreign && st != c->stream) HQ_CUDA(c, cudaStreamWaitEvent(st, c->ev_image, 0));  // image converted on another stream
     unsigned long long* words = static_cast<unsigned long long*>(d_results);
+    if ((flags & HQ_EVAL_ALLREDUCE) && reduces(c)) { rc = peer_check(c); if (rc) return rc; }   // (an EARLIER exchange that timed out: this entry never waits)
     if (!(flags & HQ_EVAL_ALLREDUCE) || !reduces(c))
         return eval_device(c, static_cast<const float*>(d_palettes), B, K, space, flags & ~HQ_EVAL_ALLREDUCE, words, nullptr, st);
     // scoring + exchange: over peer memory the last CTA of the scoring kernel all-reduces (K <= 32) or a one-CTA launch behind it does

@@ -274,6 +274,7 @@ int hq_comm_allreduce(hq_ctx* c, void* d_words, size_t n_words, void* stream) {
     if (!c || !d_words) return c ? fail(c, HQ_ERR_INVALID, "NULL device buffer") : HQ_ERR_INVALID;
     if (c->is_multi()) return fail(c, HQ_ERR_UNSUPPORTED, "device buffers belong to one device: a multi-device context reduces inside hq_eval_palettes");
     int rc = bind_device(c); if (rc) return rc;
+    rc = peer_check(c); if (rc) return rc;   // an earlier exchange over peer memory that timed out (this entry is asynchronous)
     return reduce_words(c, static_cast<unsigned long long*>(d_words), n_words, stream ? static_cast<cudaStream_t>(stream) : c->stream);
 }
 
