@@ -29,12 +29,21 @@ launches)
     echo "launch list rc=$?" ;;
 ncu)
     regex=${1:?kernel regex}; skip=${2:-0}; shift; shift || true
-    BENCH="python bench.py --steps 1 --warmup 3 --no-cpu-baseline $*"
+    BENCH="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-sweeps $*"
     $BENCH > gpurun_out/plain_ncu.log 2>&1 &&
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:$regex -s $skip -c 1 -f -o gpurun_out/prof $BENCH > gpurun_out/ncu.log 2>&1
     echo "capture rc=$?"
     ncu -i gpurun_out/prof.ncu-rep --page raw --csv > gpurun_out/prof_raw.csv 2>/dev/null
     ncu -i gpurun_out/prof.ncu-rep --page source --csv > gpurun_out/prof_source.csv 2>/dev/null
+    # the summary kept under profiles/ and, for the headline kernel at the bench's default shape, the measured DRAM bytes per launch
+    # (profiles/traffic.json = bench.py's roofline.traffic, tied to the sha of the kernel source: copy both back from gpurun_out/)
+    if [ "$regex" = "assign_reduce_kernel" ] && [ -z "$*" ]; then
+        python tools/ncu_summary.py gpurun_out/prof_raw.csv gpurun_out/prof_source.csv --units 530841600 \
+            --traffic-key assign_reduce_w3840_h2160_k256_b64 --capture-name "profiles/r02/ncu_assign_reduce_final_4k_k256_b64.json" > gpurun_out/ncu_summary.json
+        cp profiles/traffic.json gpurun_out/traffic.json
+    else
+        python tools/ncu_summary.py gpurun_out/prof_raw.csv gpurun_out/prof_source.csv > gpurun_out/ncu_summary.json
+    fi
     ls -la gpurun_out/prof* ;;
 sweep)
     timeout 1200 python tools/sweep.py "$@" > gpurun_out/sweep.json 2> gpurun_out/sweep.err; tail -2 gpurun_out/sweep.err; ls -la gpurun_out/sweep.json ;;
