@@ -9,6 +9,7 @@
 #   multi N               NCCL parity test + bench at 1 and N GPUs   (gpurun --gpus N)
 #   micro                 FP32-pipe / issue-model microbenchmarks
 #   final                 tests + bench + launches + latency in one call
+#   cbench N              tools/multi_c_bench.c: single-process C host on 1..N devices (headline step + default search), both exchange paths
 #   latency               tools/latency_ab.py: us per search iteration with / without the direct host I/O path
 set -u
 mkdir -p gpurun_out
@@ -86,6 +87,11 @@ final)
     bash tools/gpu.sh bench
     bash tools/gpu.sh launches
     bash tools/gpu.sh latency ;;
+cbench)
+    # tools/multi_c_bench.c: a plain C host on 1, 2, ... N devices of one process (gpurun --gpus N); once per exchange path
+    N=${1:-2}
+    gcc -O2 -Wall -Iinclude -o tools/multi_c_bench tools/multi_c_bench.c -Lhybridquantization_b200 -lhq_b200 -Wl,-rpath,$PWD/hybridquantization_b200 || exit 1
+    for peers in 1 0; do HQ_PEER_EXCHANGE=$peers timeout 600 ./tools/multi_c_bench "$N" | tee -a gpurun_out/multi_c_bench_n$N.jsonl; done ;;
 latency)
     timeout 500 python tools/latency_ab.py > gpurun_out/latency_ab.json 2> gpurun_out/latency_ab.err; tail -3 gpurun_out/latency_ab.err; ls -la gpurun_out/latency_ab.json ;;
 *) echo "unknown task $task"; exit 2 ;;
