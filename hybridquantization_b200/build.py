@@ -78,7 +78,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 def build_microbench(force: bool = False) -> str:
     """tools/microbench{,2,3}: FP32-pipe and issue-model probes (binaries are git-ignored, they ship with the gpurun snapshot)"""
     out = ""
-    for name in ("microbench", "microbench2", "microbench3", "microbench4"):
+    for name in ("microbench", "microbench2", "microbench3", "microbench4", "microbench5"):
         src = os.path.join(REPO, "tools", name + ".cu")
         out = os.path.join(REPO, "tools", name)
         if force or _stale(out, [src]):
