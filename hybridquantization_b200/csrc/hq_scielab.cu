@@ -8,6 +8,7 @@
 // chain has the reference's order (bit-exact against the oracle).  The reference transposes between
 // the passes; here the vertical pass reads column neighbours directly (coalesced across a row), which
 // is the same arithmetic.
+#include <cmath>
 #include <mutex>
 
 #include "hq_kernels.cuh"
@@ -851,17 +852,24 @@ cudaError_t launch_sc_candidates_fused(const void* d_idx, bool idx16, const floa
     for (int i = 0; i < 8 * kT; ++i) f21.v[i] = h_filters[i];
     const size_t smem = ((size_t)2 * kSBand * 7 * kSW + kSOutFloats) * sizeof(float) + (size_t)K * sizeof(float4);
     const int strips = (w + kSW - 1) / kSW;
-    // rows per segment: every segment start costs 20 extra horizontally filtered rows, so segments are as long as they can
-    // be while the grid still holds >= 2.5 waves of the resident CTAs (2 per SM)
+    // Rows per segment.  Every segment start costs 20 extra horizontally filtered rows, a CTA walks its segment band by band (8 rows),
+    // and `slots` CTAs run at a time: the segment length that minimises bands-per-CTA x rounds.  Round 2 first used "as long as the
+    // grid still holds >= 2.5 waves", which is what this picks for a 4K population too (7 segments, 840 CTAs), but it left a 512 x 512
+    // population at 128 CTAs of 11 bands on 296 slots (58 us; the plugin's default search is launch- and tail-bound there).
     const long long slots = (long long)(sm_count > 0 ? sm_count : 148) * kSCtasPerSm;
-    int seg_rows = 64;
-    for (int cand = 1024; cand >= 64; cand = cand * 3 / 4) {
-        const long long nseg = (rows.y_count + cand - 1) / cand;
-        if ((long long)strips * B * nseg >= 5 * slots / 2) { seg_rows = cand; break; }
-    }
-    {   // equal segments: the last one must not be a stub
-        const int nseg = (rows.y_count + seg_rows - 1) / seg_rows;
-        seg_rows = ((rows.y_count + nseg - 1) / nseg + kSBand - 1) / kSBand * kSBand;
+    int seg_rows = kSBand;
+    {
+        double best_cost = 1e300;
+        for (int cand = 2 * kSBand; cand <= 1024 + kSBand; cand += kSBand) {
+            const int nseg = (rows.y_count + cand - 1) / cand;
+            const int seg = ((rows.y_count + nseg - 1) / nseg + kSBand - 1) / kSBand * kSBand;   // equal segments: the last one must not be a stub
+            const int nseg_eq = (rows.y_count + seg - 1) / seg;
+            const double waves = (double)strips * B * nseg_eq / (double)slots;
+            const double rounds = waves < 3.0 ? std::ceil(waves) : waves + 0.5;                  // few waves run in lockstep, many average out
+            const double cost = rounds * (double)((seg + 2 * kHalf + kSBand - 1) / kSBand);
+            if (cost <= best_cost) { best_cost = cost; seg_rows = seg; }                           // ties: the longer segment
+            if (nseg == 1) break;
+        }
     }
     const dim3 grid((unsigned)strips, (unsigned)((rows.y_count + seg_rows - 1) / seg_rows), (unsigned)B);
     if (grid.y > 65535) return cudaErrorNotSupported;
