@@ -1066,7 +1066,8 @@ int hq_error_image_f32_planar(hq_ctx* c, const float* r, const float* g, const f
 namespace {
 // one context's share of a reference-faithful evaluation, enqueued on m->stream: result words (error in word 0, counts) of its
 // own rows in m->d_results.  h_pal: pinned, portable.
-int sc_eval_enqueue(hq_ctx* m, const float* h_pal, int B, int K, int space) {
+// direct: palettes read from the pinned host copy by the kernels and no result shuffle at the end (the caller exports with sc_export_kernel)
+int sc_eval_enqueue(hq_ctx* m, const float* h_pal, int B, int K, int space, bool direct = false) {
     int rc = bind_device(m); if (rc) return rc;
     const size_t npal = (size_t)B * K * 4;
     const int words = hq::result_words(K, false);
@@ -1091,16 +1092,16 @@ int sc_eval_enqueue(hq_ctx* m, const float* h_pal, int B, int K, int space) {
     int bs = prune_idx ? (int)(((size_t)40 << 20) / idx_bytes) : B;   // (the exhaustive kernel stores its indices coalesced and likes large batches)
     bs = bs < 1 ? 1 : (bs > B ? B : bs);
     HQ_CUDA(m, m->d_idx.reserve((size_t)bs * idx_bytes));
-    HQ_CUDA(m, cudaMemcpyAsync(m->d_pal.p, h_pal, npal * sizeof(float), cudaMemcpyHostToDevice, m->stream));
-    HQ_CUDA(m, cudaMemsetAsync(m->d_sc_err.p, 0, (size_t)B * 8, m->stream));
-    // the K opponent colours each quantised image is made of (cl:194-198)
-    HQ_CUDA(m, hq::launch_sc_palette_opp(m->d_pal.p, B * K, m->d_sc_tab.p, m->stream));
+    const float* pal_src = direct ? h_pal : m->d_pal.p;   // pinned host memory is device-accessible (UVA): no copy node for a few KB
+    if (!direct) HQ_CUDA(m, cudaMemcpyAsync(m->d_pal.p, h_pal, npal * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    // the K opponent colours each quantised image is made of (cl:194-198); the same launch clears the error sums
+    HQ_CUDA(m, hq::launch_sc_palette_opp(pal_src, B * K, m->d_sc_tab.p, m->stream, m->d_sc_err.p, B));
     bool tmp_reserved = false;
     for (int b0 = 0; b0 < B; b0 += bs) {
         const int nb = B - b0 < bs ? B - b0 : bs;
         // 1. assignment (quantizeAndConvertToOpp's argmin, cl:178-193): indices + counts for every candidate of the sub-batch
         //    (exact pruned kernel where it pays: same indices and counts)
-        rc = eval_device(m, m->d_pal.p + (size_t)b0 * K * 4, nb, K, space, prune_idx ? HQ_EVAL_PRUNE : 0, m->d_results.p + (size_t)b0 * words, m->d_idx.p, m->stream);
+        rc = eval_device(m, pal_src + (size_t)b0 * K * 4, nb, K, space, prune_idx ? HQ_EVAL_PRUNE : 0, m->d_results.p + (size_t)b0 * words, m->d_idx.p, m->stream);
         if (rc) return rc;
         // 2. per candidate: separable filters, Opp2LAB, CIE76 against the original, fixed-point sum
         if (m->profiling) HQ_CUDA(m, cudaEventRecord(m->ev4, m->stream));
@@ -1118,7 +1119,7 @@ int sc_eval_enqueue(hq_ctx* m, const float* h_pal, int B, int K, int space) {
         if (m->profiling) { HQ_CUDA(m, cudaEventRecord(m->ev5, m->stream)); m->ev_sc_valid = true; m->ev_sc_candidates = nb; }
     }
     // word 0 of every candidate <- the S-CIELAB error sum, so that one all-reduce covers error and counts
-    HQ_CUDA(m, cudaMemcpy2DAsync(m->d_results.p, (size_t)words * 8, m->d_sc_err.p, 8, 8, (size_t)B, cudaMemcpyDeviceToDevice, m->stream));
+    if (!direct) HQ_CUDA(m, cudaMemcpy2DAsync(m->d_results.p, (size_t)words * 8, m->d_sc_err.p, 8, 8, (size_t)B, cudaMemcpyDeviceToDevice, m->stream));
     return HQ_OK;
 }
 }  // namespace
@@ -1137,11 +1138,21 @@ int hq_eval_palettes_scielab(hq_ctx* c, const float* palettes, int B, int K, int
     const std::vector<hq_ctx*>& targets = c->is_multi() ? c->members : self;
     const size_t tail = c->delta_e != HQ_DELTAE_CIE76 ? (size_t)B : 0;   // NaN pixel counts of the CIE94 branch, reduced with the rest
     for (hq_ctx* m : targets) m->delta_e = c->delta_e;
-    for (size_t i = targets.size(); i-- > 0;) { rc = member_rc(c, targets[i], sc_eval_enqueue(targets[i], c->h_pal.p, B, K, space)); if (rc) return rc; }
+    // one device, a few KB each way (the plugin's default search): no copy nodes — the kernels read the pinned palettes, a one-CTA
+    // kernel merges the error sums into the result words, writes them to pinned host memory and raises the flag the host spins on
+    const bool direct = c->direct_io && !c->is_multi() && !reduces(c) && tail == 0 && !c->profiling && c->own_rows > 0 &&
+                        npal * sizeof(float) <= 65536 && nwords * 8 <= 32768;
+    for (size_t i = targets.size(); i-- > 0;) { rc = member_rc(c, targets[i], sc_eval_enqueue(targets[i], c->h_pal.p, B, K, space, direct)); if (rc) return rc; }
     if (reduces(c)) { rc = eval_reduce(c, nwords + tail); if (rc) return rc; }
     rc = bind_device(c); if (rc) return rc;
-    HQ_CUDA(c, cudaMemcpyAsync(c->h_results.p, c->d_results.p, (nwords + tail) * 8, cudaMemcpyDeviceToHost, c->stream));
-    HQ_CUDA(c, wait_stream(c->stream));
+    if (direct) {
+        const unsigned long long seq = ++c->export_seq;
+        HQ_CUDA(c, hq::launch_sc_export(c->d_results.p, c->d_sc_err.p, words, nwords, c->h_results.p, c->h_flag.p, seq, c->stream));
+        HQ_CUDA(c, wait_flag(c->h_flag.p, seq, c->stream));
+    } else {
+        HQ_CUDA(c, cudaMemcpyAsync(c->h_results.p, c->d_results.p, (nwords + tail) * 8, cudaMemcpyDeviceToHost, c->stream));
+        HQ_CUDA(c, wait_stream(c->stream));
+    }
     if (reduces(c)) { rc = peer_check(c); if (rc) return rc; }
     for (int b = 0; b < B; ++b) {
         if (err_fx) err_fx[b] = (tail && c->h_results.p[nwords + b]) ? HQ_ERR_FX_NAN : (int64_t)c->h_results.p[(size_t)b * words];

@@ -243,7 +243,9 @@ constexpr int kMaxScielabTaps = 255;
 cudaError_t launch_sc_rgb_to_opp(const uint8_t* d_rgb, size_t n, size_t stride, const float* d_table, float* d_opp, cudaStream_t st);
 // float image planes -> opponent planes (in place allowed); d_bad (optional) |= 1 for values outside [0,1]
 cudaError_t launch_sc_unit_to_opp(const float* d_unit, size_t n, size_t stride, float* d_opp, unsigned int* d_bad, cudaStream_t st);
-cudaError_t launch_sc_palette_opp(const float* d_palettes, int total, float4* d_tab, cudaStream_t st);
+cudaError_t launch_sc_palette_opp(const float* d_palettes, int total, float4* d_tab, cudaStream_t st, unsigned long long* d_zero = nullptr, int zero_words = 0);
+cudaError_t launch_sc_export(const unsigned long long* d_results, const unsigned long long* d_sc_err, int words, size_t nwords, unsigned long long* h_dst_mapped,
+                             unsigned long long* h_flag_mapped, unsigned long long seq, cudaStream_t st);
 // original image: opp planes -> S-CIELAB Lab planes (d_tmp: 7 planes of scratch)
 // h_filters: the same block on the host (nullptr = always use the generic kernels); with taps == 21
 // (plugin defaults) the specialised kernels take it as a kernel parameter

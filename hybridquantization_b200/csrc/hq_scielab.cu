@@ -57,8 +57,10 @@ __global__ void sc_unit_to_opp_kernel(const float* unit, size_t n, size_t stride
 }
 
 // palette colours -> opponent table (the K values the quantised image can take)
-__global__ void sc_palette_opp_kernel(const float* __restrict__ pal, int total, float4* __restrict__ tab) {
+// (optionally clears zero[0 .. zero_words): the error sums of the evaluation that follows on the same stream)
+__global__ void sc_palette_opp_kernel(const float* __restrict__ pal, int total, float4* __restrict__ tab, unsigned long long* __restrict__ zero, int zero_words) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < zero_words) zero[i] = 0ull;
     if (i >= total) return;
     const float4 c = reinterpret_cast<const float4*>(pal)[i];
     const hq_float3 o = hq_cl_linrgb_to_opp(hq_srgb_decode(c.x), hq_srgb_decode(c.y), hq_srgb_decode(c.z));
@@ -787,9 +789,29 @@ cudaError_t launch_sc_rgb_to_opp(const uint8_t* d_rgb, size_t n, size_t stride, 
     return cudaGetLastError();
 }
 
-cudaError_t launch_sc_palette_opp(const float* d_palettes, int total, float4* d_tab, cudaStream_t st) {
-    if (total == 0) return cudaSuccess;
-    sc_palette_opp_kernel<<<(total + 127) / 128, 128, 0, st>>>(d_palettes, total, d_tab);
+cudaError_t launch_sc_palette_opp(const float* d_palettes, int total, float4* d_tab, cudaStream_t st, unsigned long long* d_zero, int zero_words) {
+    const int nthreads = total > zero_words ? total : zero_words;
+    if (nthreads == 0) return cudaSuccess;
+    sc_palette_opp_kernel<<<(nthreads + 127) / 128, 128, 0, st>>>(d_palettes, total, d_tab, d_zero, d_zero ? zero_words : 0);
+    return cudaGetLastError();
+}
+
+// Result words of a reference-faithful evaluation -> the caller's pinned host buffer, word 0 of every candidate taken from the
+// S-CIELAB error sums, then the sequence number the host spins on: one launch instead of a strided D2D copy, a D2H copy and a
+// stream wait (small result sets on one device: the plugin's default search is a chain of dependent launches).
+__global__ void __launch_bounds__(256) sc_export_kernel(const unsigned long long* __restrict__ results, const unsigned long long* __restrict__ sc_err, int words,
+                                                        unsigned nwords, unsigned long long* dst, volatile unsigned long long* flag, unsigned long long seq) {
+    for (unsigned i = threadIdx.x; i < nwords; i += blockDim.x) {
+        const unsigned b = i / (unsigned)words;
+        dst[i] = (i - b * (unsigned)words == 0u) ? sc_err[b] : results[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *flag = seq;
+}
+cudaError_t launch_sc_export(const unsigned long long* d_results, const unsigned long long* d_sc_err, int words, size_t nwords, unsigned long long* h_dst_mapped,
+                             unsigned long long* h_flag_mapped, unsigned long long seq, cudaStream_t st) {
+    sc_export_kernel<<<1, 256, 0, st>>>(d_results, d_sc_err, words, (unsigned)nwords, h_dst_mapped, h_flag_mapped, seq);
     return cudaGetLastError();
 }
 
