@@ -79,3 +79,60 @@ def test_row_shard_partition():
             assert all(a[1] == b[0] for a, b in zip(cuts[:-1], cuts[1:]))
     with pytest.raises(ValueError):
         row_shard(10, 2, 2)
+
+
+class _FakeBackend:
+    """Stands in for ImageManipulation in the handshake of dist.open_peer_exchange (the mailboxes themselves need GPUs:
+    tests/test_gpu_multi*.py): records what the helper asks of it and fails where told to."""
+
+    def __init__(self, rank, fail_handle=False, fail_open=False):
+        self.rank, self.fail_handle, self.fail_open = rank, fail_handle, fail_open
+        self.opened, self.closed = None, 0
+
+    def commPeerHandle(self):
+        from hybridquantization_b200._lib import HqError
+        if self.fail_handle:
+            raise HqError(-4, "no mailbox")
+        return bytes([self.rank]) * 64
+
+    def commOpenPeers(self, handles, rank):
+        from hybridquantization_b200._lib import HqError
+        if self.fail_open:
+            raise HqError(-4, "cudaIpcOpenMemHandle failed")
+        self.opened = (list(handles), rank)
+
+    def commClosePeers(self):
+        self.closed += 1
+
+
+def _peer_worker(rank, world, port, scenario, out_q):
+    sys.path.insert(0, REPO)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hybridquantization_b200.dist import open_peer_exchange
+    be = _FakeBackend(rank, fail_handle=(scenario == "handle" and rank == 1), fail_open=(scenario == "open" and rank == 0))
+    ok = open_peer_exchange(be)
+    out_q.put((rank, ok, be.opened, be.closed))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("scenario", ["ok", "handle", "open"])
+def test_peer_exchange_handshake_is_all_or_nothing(scenario):
+    """Every rank's 64 handle bytes reach every rank in rank order; if ANY rank cannot export or map a mailbox, EVERY rank closes
+    again and reports False, so that no rank waits in a mailbox the others never write (the exchange then stays on NCCL)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, scenario, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    if scenario == "ok":
+        for rank, ok, opened, closed in got:
+            assert ok and closed == 0 and opened == ([bytes([0]) * 64, bytes([1]) * 64], rank)
+    else:
+        assert all(not ok and closed == 1 for _, ok, _, closed in got), got
