@@ -182,6 +182,8 @@ int hq_create(int device, hq_ctx** out) {
         c->direct_io = !(d && d[0] == '0');
         const char* sm = std::getenv("HQ_SMALL_EVAL");   // 0: keep the two-launch latency path (A/B measurements)
         c->small_eval = !(sm && sm[0] == '0');
+        const char* pe = std::getenv("HQ_PERSIST");   // 1: persistent evaluator inside hq_find_best_quantization (measured: -9 %; off by default)
+        c->persist_enabled = pe && pe[0] == '1';
     }
     {   // HQ_SC_UNFUSED=1: the S-CIELAB candidate stage as two kernels per candidate with a 7-plane intermediate (round 1; A/B runs)
         const char* u = std::getenv("HQ_SC_UNFUSED");
@@ -219,7 +221,7 @@ void hq_destroy(hq_ctx* c) {
     if (c->ev5) cudaEventDestroy(c->ev5);
     c->d_rgb.release(); c->d_flag.release(); c->d_lab.release(); c->d_unit.release(); c->d_table.release(); c->d_pal.release();
     c->d_pal_lab.release(); c->d_pal_rgb.release(); c->d_results.release(); c->d_idx.release();
-    c->d_out_rgb.release(); c->d_out_f32.release(); c->h_pal.release(); c->h_results.release(); c->h_flag.release(); c->d_export_counter.release(); c->d_results_small.release();
+    c->d_out_rgb.release(); c->d_out_f32.release(); c->h_pal.release(); c->h_results.release(); c->h_flag.release(); c->d_export_counter.release(); c->d_results_small.release(); c->h_persist.release(); c->d_persist_cmd.release();
     c->d_sc_filters.release(); c->d_sc_opp.release(); c->d_sc_tmp.release(); c->d_sc_lab.release(); c->d_sc_tab.release(); c->d_sc_err.release();
     c->d_sc_lab2.release(); c->d_sc_map.release(); c->d_sc_rgb2.release(); c->d_sc_map8.release();
     c->pr_own.release(); c->pr_all.release(); c->d_pr_scratch.release(); c->d_big_d2.release(); c->d_big_idx.release();
@@ -474,6 +476,50 @@ bool copy_palettes_checked(float* dst, const float* src, size_t npal) {
 }
 const char* kBadPalette = "palette colours must be finite sRGB values in [0,1] (SWASA.java:93-106 clamps them)";
 
+// ---- persistent evaluator of a small search: started by hq_find_best_quantization, fed by hq_eval_palettes
+void persist_end(hq_ctx* c) {
+    if (!c->persist_on) return;
+    c->persist_on = false;
+    cudaSetDevice(c->device);
+    *static_cast<volatile unsigned long long*>(c->h_persist.p) = hq::kPersistQuitCmd;
+    cudaStreamSynchronize(c->stream);
+}
+// true: the kernel is running and every evaluation with this signature goes through its mailbox
+bool persist_begin(hq_ctx* c, int B, int K, int space, bool sums) {
+    if (!c->persist_enabled || !c->small_eval || !c->direct_io || c->is_multi() || reduces(c) || c->profiling || c->use_graphs || c->n == 0 ||
+        c->delta_e != HQ_DELTAE_CIE76 || K > hq::kDirectMaxColors || (long long)B * K > hq::kSmallPalColors)
+        return false;
+    if (cudaSetDevice(c->device) != cudaSuccess) return false;
+    const size_t npal = (size_t)B * K * 4, nwords = (size_t)B * hq::result_words(K, sums);
+    if (c->h_pal.reserve(npal) != cudaSuccess || c->h_results.reserve(nwords) != cudaSuccess || c->h_persist.reserve(16) != cudaSuccess ||
+        c->d_persist_cmd.reserve(1) != cudaSuccess || c->d_pal.reserve(npal) != cudaSuccess)
+        return false;
+    if (space == HQ_SPACE_SRGB && ensure_unit(c, c->stream) != HQ_OK) return false;
+    if (nwords > c->d_results_small.cap) {
+        if (c->d_results_small.reserve(nwords > 4096 ? nwords : 4096) != cudaSuccess) return false;
+        if (cudaMemsetAsync(c->d_results_small.p, 0, c->d_results_small.cap * 8, c->stream) != cudaSuccess) return false;
+    }
+    const unsigned long long first = c->export_seq;
+    c->h_persist.p[0] = first; c->h_persist.p[8] = 0ull;
+    if (cudaMemcpyAsync(c->d_persist_cmd.p, c->h_persist.p, 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return false;
+    hq::AssignArgs a;
+    a.lab = c->d_lab.p; a.unit = c->d_unit.p; a.n = c->n; a.stride = c->stride;
+    a.pal_lab = nullptr; a.pal_rgb = nullptr;
+    a.B = B; a.K = K; a.space = space; a.want_sums = sums;
+    a.results = c->d_results_small.p; a.idx_out = nullptr; a.sm_count = c->sm_count;
+    a.own_lo = c->own_lo; a.own_hi = c->own_hi;
+    a.variant = 1;
+    a.tail.host_dst = c->h_results.p; a.tail.host_flag = c->h_flag.p; a.tail.seq = 0; a.tail.counter = c->d_export_counter.p;
+    a.tail.src = c->d_results_small.p; a.tail.nwords = (unsigned)nwords;
+    unsigned long long idle_ns = 200ull * 1000000ull;   // a search posts an evaluation every ~15 us; HQ_PERSIST_IDLE_MS
+    if (const char* t = std::getenv("HQ_PERSIST_IDLE_MS")) { const long long ms = std::atoll(t); if (ms > 0) idle_ns = (unsigned long long)ms * 1000000ull; }
+    const cudaError_t e = hq::launch_assign_persist(a, c->h_pal.p, c->d_pal.p, c->whitepoint, c->h_persist.p, c->h_persist.p + 8, c->d_persist_cmd.p, first, idle_ns, c->stream);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }   // (not resident in one wave, no cooperative launch: one launch per evaluation)
+    c->persist_on = true;
+    c->persist_B = B; c->persist_K = K; c->persist_space = space; c->persist_sums = sums; c->persist_image_gen = c->image_gen;
+    return true;
+}
+
 struct EvalPlan {
     int B, K, space, flags, words;
     size_t npal, nwords;
@@ -586,6 +632,21 @@ int hq_eval_palettes(hq_ctx* c, const float* palettes, int B, int K, int space, 
         const bool peer = reduce && e.direct && peer_ready(c, nwords);
         bool all_nonempty = true;
         for (hq_ctx* m : targets) all_nonempty = all_nonempty && m->n > 0;
+        if (c->persist_on) {
+            // a search is running its persistent evaluator: this evaluation is one mailbox write (the palettes are already in h_pal)
+            if (B == c->persist_B && K == c->persist_K && space == c->persist_space && sums == c->persist_sums && flags == (sums ? HQ_EVAL_SUMS : 0) &&
+                c->image_gen == c->persist_image_gen && *static_cast<volatile unsigned long long*>(c->h_persist.p + 8) == 0ull) {
+                const unsigned long long seq = ++c->export_seq;
+                std::atomic_thread_fence(std::memory_order_release);
+                *static_cast<volatile unsigned long long*>(c->h_persist.p) = seq;
+                const cudaError_t we = wait_flag(c->h_flag.p, seq, c->stream);
+                if (we == cudaSuccess) goto unpack;
+                cudaGetLastError();
+                if (we != cudaErrorUnknown) return fail(c, HQ_ERR_CUDA, "persistent evaluation failed: %s", cudaGetErrorString(we));
+                // the kernel left (idle time-out) before it saw the command: one launch per evaluation from here on
+            }
+            persist_end(c);
+        }
         if (e.direct && c->small_eval && (!reduce || peer) && all_nonempty && !c->profiling && K <= hq::kDirectMaxColors && (long long)B * K <= hq::kSmallPalColors &&
             !(flags & (HQ_EVAL_PRUNE | HQ_EVAL_FORCE_DIRECT | HQ_EVAL_FORCE_CHUNKED | HQ_EVAL_FORCE_PREFILTER))) {
             const unsigned long long seq = ++c->export_seq;
@@ -1190,18 +1251,31 @@ int hq_find_best_quantization(hq_ctx* c, int K, const hq_swasa_params* p, uint64
         backend.setStopFlag(&c->stop_flag_view);
         backend.setCostModel(p->cost_model);
         backend.setProgress(c->progress, c->progress_user);
-        backend.setEvalFlags(hq_search_eval_flags(c, K, p->space, p->cost_model));  // exact pruning where it pays: same costs, same trajectory
+        const int eval_flags = hq_search_eval_flags(c, K, p->space, p->cost_model);
+        backend.setEvalFlags(eval_flags);  // exact pruning where it pays: same costs, same trajectory
         hq::JavaRandom random(p->seed);
         hq::SWASA swasa(p->population, p->imax, p->iTc, p->delta, p->conv_delay, p->conv_spread, p->t0, p->alpha, p->s0, p->beta, &random);
         double err = 0;
-        const std::vector<float> best = backend.findBestQuantization(K, swasa, n_total, p->space, &err, trace_costs, iterations_done);
+        // a small search with the LAB cost (the plugin's defaults: 8 colours x 4 candidates) is thousands of evaluations whose cost is
+        // the kernel launch: with HQ_PERSIST=1 one persistent kernel serves them all through a mailbox (same integers; hq_eval_palettes
+        // falls back to one launch per evaluation whenever the kernel is not there).  Off by default: measured 18.3 against 20.0 us
+        // per iteration — the mailbox hops (PCIe poll, palette fetch, republish) cost almost what the launch did.
+        if (p->cost_model == HQ_COST_LAB && eval_flags == 0 && p->imax >= 16) persist_begin(c, p->population, K, p->space, false);
+        std::vector<float> best;
+        try {
+            best = backend.findBestQuantization(K, swasa, n_total, p->space, &err, trace_costs, iterations_done);
+        } catch (...) {
+            persist_end(c);
+            throw;
+        }
+        persist_end(c);
         std::memcpy(best_colors, best.data(), sizeof(float) * best.size());
         if (best_error) *best_error = err;
     } catch (const std::exception& ex) {
         if (c->err.empty()) c->err = ex.what();
         return HQ_ERR_CUDA;
     }
-    return HQ_OK;
+    return bind_device(c);
 }
 
 int hq_search_eval_flags(const hq_ctx* c, int K, int space, int cost_model) {

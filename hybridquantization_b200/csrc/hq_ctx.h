@@ -92,6 +92,15 @@ struct hq_ctx {
     DevBuf<unsigned> d_export_counter;      // ticket counter of the scoring kernels' export tail (zero between launches)
     DevBuf<unsigned long long> d_results_small;   // result words of the one-launch evaluations: zero between launches (the last CTA re-zeroes them)
     bool small_eval = true;                 // HQ_SMALL_EVAL=0: never take the one-launch path
+    // persistent evaluator of a small search (hq_kernels.cu, assign_persist_kernel): alive between persist_begin and persist_end
+    // inside hq_find_best_quantization
+    bool persist_enabled = false;           // HQ_PERSIST=1 (off by default: -9 % measured, a kernel that owns the GPU for the length of a search)
+    bool persist_on = false;
+    int persist_B = 0, persist_K = 0, persist_space = 0;
+    bool persist_sums = false;
+    unsigned long long persist_image_gen = 0;
+    PinBuf<unsigned long long> h_persist;   // [0] command word the kernel polls, [8] exit word it writes (separate cache lines)
+    DevBuf<unsigned long long> d_persist_cmd;
     bool direct_io = true;                  // HQ_DIRECT_IO=0: the H2D copy / D2H copy / stream wait path instead (A/B measurements)
 
     // exact pruning (hq_pruned.cu): cell-sorted copy of the own pixels, chunk table, boxes; built on first use per image

@@ -443,9 +443,12 @@ template <int NCOL> struct SmallPalettes { float v[NCOL * 4]; };   // [B][K][4] 
 // each (the exact pow(., 2.4) is the long pole: in parallel it costs one evaluation instead of three), K threads finish.
 // Out of line: its fp64 code must not shape the register allocation of the sweep.
 __device__ __noinline__ void stage_small_palette(const float* __restrict__ cpal, int K, int K8, int whitepoint, bool srgb, float* __restrict__ pla_f,
-                                                 float* __restrict__ pb_f, float4* __restrict__ s_lab, float* __restrict__ s_lin) {
+                                                 float* __restrict__ pb_f, float4* __restrict__ s_lab, float* __restrict__ s_lin, bool fresh = false) {
+    // fresh: the palettes live in pinned host memory that the host rewrites between the iterations of a PERSISTENT kernel (below):
+    // every read goes to the source (ld.cv), never to a line this SM fetched an iteration ago
+    auto rd = [&](int i) { return fresh ? __ldcv(cpal + i) : cpal[i]; };
     const int tid = threadIdx.x;
-    if (tid < 3 * K) s_lin[tid] = hq_srgb_decode(cpal[(tid / 3) * 4 + tid % 3]);
+    if (tid < 3 * K) s_lin[tid] = hq_srgb_decode(rd((tid / 3) * 4 + tid % 3));
     __syncthreads();
     if (tid < K8) {
         const int k = tid;
@@ -454,7 +457,7 @@ __device__ __noinline__ void stage_small_palette(const float* __restrict__ cpal,
         if (k < K) {
             const hq_float3 v = hq_linrgb_to_lab(s_lin[3 * k], s_lin[3 * k + 1], s_lin[3 * k + 2], hq_make_white(whitepoint));
             lab = make_float4(v.x, v.y, v.z, 0.f);
-            if (srgb) { f0 = cpal[4 * k]; f1 = cpal[4 * k + 1]; f2 = cpal[4 * k + 2]; }
+            if (srgb) { f0 = rd(4 * k); f1 = rd(4 * k + 1); f2 = rd(4 * k + 2); }
             else { f0 = v.x; f1 = v.y; f2 = v.z; }
         }
         pla_f[(k >> 1) * 4 + (k & 1)] = f0;
@@ -485,7 +488,7 @@ __device__ __forceinline__ void track_min(float d, float kf, float& best, float&
 }
 
 template <int VARIANT, bool SRGB, bool SUMS, int IDXW, bool FUSED>
-__device__ __forceinline__ void assign_body(const AssignParams& p, const float* __restrict__ cpal) {
+__device__ __forceinline__ void assign_body(const AssignParams& p, const float* __restrict__ cpal, unsigned long long seq_override = 0ull, bool fresh_pal = false) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = p.K, K8 = p.K8;
     const int tid = threadIdx.x;
@@ -520,7 +523,7 @@ __device__ __forceinline__ void assign_body(const AssignParams& p, const float* 
     }
     if (FUSED) {
         __shared__ float s_lin[3 * kDirectMaxColors];
-        stage_small_palette(cpal + (size_t)b * K * 4, K, K8, p.whitepoint, SRGB, reinterpret_cast<float*>(s_pla), reinterpret_cast<float*>(s_pb), s_lab, s_lin);
+        stage_small_palette(cpal + (size_t)b * K * 4, K, K8, p.whitepoint, SRGB, reinterpret_cast<float*>(s_pla), reinterpret_cast<float*>(s_pb), s_lab, s_lin, fresh_pal);
         for (int k = tid; k < K8; k += kThreads) {
             s_cnt[k] = 0u;
             if (SUMS) { s_sum[3 * k] = 0ull; s_sum[3 * k + 1] = 0ull; s_sum[3 * k + 2] = 0ull; }
@@ -989,7 +992,7 @@ __device__ __forceinline__ void assign_body(const AssignParams& p, const float* 
             }
         }
     }
-    if (VARIANT == 1) export_tail(p.tail, gridDim.x * gridDim.y, FUSED);
+    if (VARIANT == 1) export_tail(p.tail, gridDim.x * gridDim.y, FUSED, seq_override);
 }
 
 template <int VARIANT, bool SRGB, bool SUMS, int IDXW>
@@ -1001,6 +1004,70 @@ __global__ void __launch_bounds__(kThreads, VARIANT == 3 ? HQ_V3_MIN_CTAS : (VAR
 template <bool SRGB, bool SUMS, int NCOL>
 __global__ void __launch_bounds__(kThreads, HQ_V1_MIN_CTAS) assign_small_kernel(const __grid_constant__ AssignParams p, const __grid_constant__ SmallPalettes<NCOL> pal) {
     assign_body<1, SRGB, SUMS, 0, true>(p, pal.v);
+}
+
+// PERSISTENT evaluator of a small search (hq_find_best_quantization with the LAB cost: thousands of identical evaluations whose
+// cost is the launch itself — an empty kernel takes 8.8 us from launch to a flag in host memory on this box, the evaluation's own
+// work ~6 us, profiles/r02/microbench5_launch_floor.json).  Launched ONCE per search with every CTA resident (cooperative launch);
+// per iteration the host writes the palettes into pinned memory and then a sequence number into its mailbox word; CTA (0,0) polls that
+// word over PCIe and republishes it in a device word the other CTAs poll in L2; every CTA then runs the one-launch evaluation body
+// unchanged (palettes read fresh from the pinned buffer, last CTA exports the totals + the same sequence number and re-zeroes the
+// result words).  kQuit, or no command for idle_ns (a host that went away, a progress callback that blocks), ends the kernel — it
+// reports that in h_exit and the library falls back to one launch per evaluation.
+struct PersistCtl {
+    const unsigned long long* h_cmd;   // pinned host word: sequence number of the evaluation wanted (kPersistQuit: leave)
+    unsigned long long* h_exit;        // pinned host word: non-zero once the kernel has left
+    unsigned long long* d_cmd;         // device word: the command as seen by the dispatcher CTA
+    const float4* h_pal;               // pinned host palettes [B * K] (r, g, b, .)
+    float4* d_pal;                     // their device copy, refreshed by the dispatcher CTA before it republishes the command
+    int ncolors;
+    unsigned long long first_seq;      // the sequence number BEFORE the first evaluation
+    unsigned long long idle_ns;
+};
+constexpr unsigned long long kPersistQuit = ~0ull;
+template <bool SRGB, bool SUMS>
+__global__ void __launch_bounds__(kThreads, HQ_V1_MIN_CTAS) assign_persist_kernel(const __grid_constant__ AssignParams p, const __grid_constant__ PersistCtl ctl) {
+    __shared__ unsigned long long s_cmd;
+    unsigned long long last = ctl.first_seq;
+    const bool dispatcher = blockIdx.x == 0 && blockIdx.y == 0;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            unsigned long long v = last, t0 = 0;
+            for (unsigned spin = 0;; ++spin) {
+                if (dispatcher) v = *reinterpret_cast<const volatile unsigned long long*>(ctl.h_cmd);
+                else asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctl.d_cmd) : "memory");
+                if (v != last) break;
+                if ((spin & 63u) == 63u) {
+                    unsigned long long t;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                    if (t0 == 0) t0 = t;
+                    else if (t - t0 > (dispatcher ? ctl.idle_ns : 4 * ctl.idle_ns)) { v = kPersistQuit; break; }   // (the others outlast the dispatcher: they leave on ITS word)
+                }
+            }
+            s_cmd = v;
+        }
+        __syncthreads();
+        const unsigned long long cmd = s_cmd;
+        if (dispatcher) {
+            // the palettes cross PCIe ONCE per iteration, in a few coalesced 16-byte loads (every CTA reading its own colours from host
+            // memory was ~10,000 four-byte PCIe reads per iteration: 138 us), then the command is republished for the other CTAs
+            if (cmd != kPersistQuit) {
+                __threadfence_system();   // the palettes the host wrote before the command are read after it
+                for (int i = threadIdx.x; i < ctl.ncolors; i += blockDim.x) ctl.d_pal[i] = __ldcv(ctl.h_pal + i);
+                __threadfence();
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(ctl.d_cmd), "l"(cmd) : "memory");
+        }
+        __syncthreads();
+        if (cmd == kPersistQuit) break;
+        last = cmd;
+        assign_body<1, SRGB, SUMS, 0, true>(p, reinterpret_cast<const float*>(ctl.d_pal), cmd, true);
+    }
+    if (threadIdx.x == 0 && dispatcher) {
+        *reinterpret_cast<volatile unsigned long long*>(ctl.h_exit) = last + 1;
+        __threadfence_system();
+    }
 }
 
 // per (kernel instantiation, device), PROCESS-wide: cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the function on
@@ -1303,6 +1370,53 @@ cudaError_t launch_assign_small(const AssignArgs& a, const float* h_palettes, in
         if (ncol <= 64) return launch_small_t<S, U, 64>(p, h_palettes, a.B, a.sm_count, stream);
         if (ncol <= 128) return launch_small_t<S, U, 128>(p, h_palettes, a.B, a.sm_count, stream);
         return launch_small_t<S, U, kSmallPalColors>(p, h_palettes, a.B, a.sm_count, stream);
+    };
+    if (a.space == 1) return a.want_sums ? go(std::true_type{}, std::true_type{}) : go(std::true_type{}, std::false_type{});
+    return a.want_sums ? go(std::false_type{}, std::true_type{}) : go(std::false_type{}, std::false_type{});
+}
+
+cudaError_t launch_assign_persist(const AssignArgs& a, const float* h_palettes_mapped, float* d_palettes, int whitepoint, const unsigned long long* h_cmd,
+                                  unsigned long long* h_exit, unsigned long long* d_cmd, unsigned long long first_seq, unsigned long long idle_ns, cudaStream_t stream) {
+    if (a.B <= 0 || a.K <= 0 || a.K > kDirectMaxColors || (long long)a.B * a.K > kSmallPalColors || a.idx_out || !a.tail.active() || !h_palettes_mapped || !d_palettes || a.n == 0)
+        return cudaErrorInvalidValue;
+    if (a.space == 1 && a.unit == nullptr) return cudaErrorInvalidValue;
+    AssignParams p;
+    p.feat = a.space == 1 ? a.unit : a.lab;
+    p.lab = a.lab;
+    p.n = a.n; p.stride = a.stride;
+    p.pal_feat = nullptr; p.pal_lab = nullptr;
+    p.K = a.K; p.K8 = padded_colors(a.K);
+    p.words = result_words(a.K, a.want_sums);
+    p.results = a.results;
+    p.idx_out = nullptr;
+    p.tail = a.tail;
+    p.use_tma = 0;
+    p.whitepoint = whitepoint;
+    p.xmax0 = p.xmax1 = p.xmax2 = 0.f;
+    p.own_lo = a.own_lo; p.own_hi = a.own_hi == kAllPixels ? a.n : a.own_hi;
+    PersistCtl ctl;
+    ctl.h_cmd = h_cmd; ctl.h_exit = h_exit; ctl.d_cmd = d_cmd; ctl.first_seq = first_seq; ctl.idle_ns = idle_ns;
+    ctl.h_pal = reinterpret_cast<const float4*>(h_palettes_mapped); ctl.d_pal = reinterpret_cast<float4*>(d_palettes); ctl.ncolors = a.B * a.K;
+    auto go = [&](auto srgb, auto sums) -> cudaError_t {
+        constexpr bool S = decltype(srgb)::value, U = decltype(sums)::value;
+        auto kern = assign_persist_kernel<S, U>;
+        const size_t smem = AssignSmem<1, S, U>(p.K8).total;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) return cudaErrorLaunchOutOfResources;
+        // the same grid as the one-launch evaluation: one wave at most (every CTA must be resident: they wait for each other's tickets)
+        const long long slots = (long long)a.sm_count * occ;
+        const long long ntiles = (long long)((p.n + kTilePx - 1) / kTilePx);
+        long long G = slots / a.B;
+        if (G > (ntiles + 1) / 2) G = (ntiles + 1) / 2;
+        if (G < 1) G = 1;
+        if (G > 65535) G = 65535;
+        if ((long long)a.B * G > slots) return cudaErrorLaunchOutOfResources;
+        void* args[] = {(void*)&p, (void*)&ctl};
+        return cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)a.B, (unsigned)G), dim3(kThreads), args, smem, stream);
     };
     if (a.space == 1) return a.want_sums ? go(std::true_type{}, std::true_type{}) : go(std::true_type{}, std::false_type{});
     return a.want_sums ? go(std::false_type{}, std::true_type{}) : go(std::false_type{}, std::false_type{});

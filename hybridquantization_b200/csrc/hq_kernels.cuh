@@ -132,7 +132,7 @@ struct ExportTail {
 #ifdef __CUDACC__
 // every thread of every CTA calls this after its last result atomic
 // zero_after: the result words are left zero for the next launch (the one-launch evaluation has no clearing pass)
-__device__ __forceinline__ void export_tail(const ExportTail& x, unsigned total_ctas, bool zero_after = false) {
+__device__ __forceinline__ void export_tail(const ExportTail& x, unsigned total_ctas, bool zero_after = false, unsigned long long seq_override = 0ull) {
     if (x.host_dst == nullptr && !x.peer_only) return;
     __shared__ unsigned s_ticket;
     __threadfence();     // this thread's result atomics are performed device-wide before the ticket is taken
@@ -153,7 +153,7 @@ __device__ __forceinline__ void export_tail(const ExportTail& x, unsigned total_
     __syncthreads();
     if (threadIdx.x == 0) {
         *x.counter = 0u;
-        if (!x.peer_only) *reinterpret_cast<volatile unsigned long long*>(x.host_flag) = x.seq;
+        if (!x.peer_only) *reinterpret_cast<volatile unsigned long long*>(x.host_flag) = seq_override ? seq_override : x.seq;
     }
 }
 #endif
@@ -183,6 +183,13 @@ cudaError_t launch_assign_reduce(const AssignArgs& a, cudaStream_t stream);
 // caller); a.results must be zero on entry and is zero again when the launch completes; K <= kDirectMaxColors, no index image.
 constexpr int kSmallPalColors = 192;
 cudaError_t launch_assign_small(const AssignArgs& a, const float* h_palettes, int whitepoint, cudaStream_t stream);
+// The same evaluation as a PERSISTENT kernel for the length of a search (hq_kernels.cu, assign_persist_kernel): launched once, fed
+// through a pinned mailbox word (h_cmd: sequence number of the evaluation wanted, ~0 = leave), palettes read from the pinned buffer
+// h_palettes_mapped each iteration, totals + the sequence number exported as by launch_assign_small; h_exit becomes non-zero when
+// the kernel has left (asked to, or idle for idle_ns).
+constexpr unsigned long long kPersistQuitCmd = ~0ull;
+cudaError_t launch_assign_persist(const AssignArgs& a, const float* h_palettes_mapped, float* d_palettes, int whitepoint, const unsigned long long* h_cmd,
+                                  unsigned long long* h_exit, unsigned long long* d_cmd, unsigned long long first_seq, unsigned long long idle_ns, cudaStream_t stream);
 
 // ---- exact assignment with geometric pruning (hq_pruned.cu): the own pixels are counting-sorted once per image by a
 // coarse CIELAB cell into chunks of <= kPrunedChunkPx pixels with exact bounding boxes; per (chunk, candidate) only

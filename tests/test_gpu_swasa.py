@@ -145,3 +145,36 @@ def test_allreduce_hook_is_applied_on_every_path(hqlib):
         assert abs(got["err"] - 3 * base["err"]) <= 1e-12 * base["err"]
     finally:
         be.close()
+
+
+@pytest.mark.parametrize("space", [SPACE_LAB, SPACE_SRGB])
+def test_persistent_evaluator_gives_the_same_search(space, monkeypatch):
+    """HQ_PERSIST=1 (off by default): one persistent kernel serves every evaluation of a small LAB-cost search through a pinned mailbox
+    (hq_kernels.cu, assign_persist_kernel).  Same trajectory bit for bit — also when the kernel leaves in the middle of the search
+    because the host kept it waiting (HQ_PERSIST_IDLE_MS=2 and a progress listener that sleeps): the library then goes back to one
+    launch per evaluation."""
+    import time
+
+    from hybridquantization_b200 import ImageManipulation
+
+    img = synth.synth_image(300, 211, 99, smooth=True)
+    sw = dict(population=4, imax=400, seed=4321, space=space)
+    ref = ImageManipulation("CIE76", False, True, 0)
+    ref.setImage(img)
+    want = ref.findBestQuantization(8, SWASA(**sw), trace=True)
+    ref.close()
+    for idle_ms, sleeper in (("200", None), ("2", lambda *a: time.sleep(0.02))):
+        monkeypatch.setenv("HQ_PERSIST", "1")
+        monkeypatch.setenv("HQ_PERSIST_IDLE_MS", idle_ms)
+        be = ImageManipulation("CIE76", False, True, 0)
+        be.setImage(img)
+        if sleeper:
+            be.setProgress(sleeper)
+        got = be.findBestQuantization(8, SWASA(**sw), trace=True)
+        again = be.findBestQuantization(8, SWASA(**sw), trace=True)      # a second search on the same context starts a new kernel
+        q = be.quantize(got[0], space)                                    # and the stream is free again afterwards
+        be.close()
+        for g in (got, again):
+            assert g[3] == want[3] == 400 and g[1] == want[1]
+            assert np.array_equal(g[2].view(np.uint64), want[2].view(np.uint64)) and np.array_equal(bits(g[0]), bits(want[0]))
+        assert q["idx"].size == img.shape[0] * img.shape[1]
